@@ -1,0 +1,275 @@
+"""ORACLE — test infrastructure only.
+
+ctypes bindings for the two CPU checkers:
+  * ``RefExtractor``  -> oracle/_ref/liborb_ref.so  (the UNMODIFIED reference ORBextractor.cc + cv shim)
+  * ``oracle_lib()``  -> oracle/liborb_oracle.so    (our independent restatement, stage by stage)
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference arms may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "liborb_ref.so")
+ORACLE_SO = os.path.join(HERE, "liborb_oracle.so")
+
+BLUR_CV331, BLUR_CV4, BLUR_CV331_SSE2 = 0, 1, 2
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4")])
+
+_u8p = C.POINTER(C.c_uint8)
+
+
+def _ptr(a: np.ndarray, t=_u8p):
+    return a.ctypes.data_as(t)
+
+
+def build(ref: bool = True) -> None:
+    subprocess.check_call(["make", "-s", "-C", HERE])
+    if ref:
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            build(ref=True)
+        L = C.CDLL(REF_SO)
+        L.orbref_create.restype = C.c_void_p
+        L.orbref_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orbref_destroy.argtypes = [C.c_void_p]
+        L.orbref_set_canonical.argtypes = [C.c_void_p, C.c_int]
+        L.orbref_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.orbref_pattern.argtypes = [C.c_void_p, C.c_void_p]
+        L.orbref_extract.restype = C.c_int
+        L.orbref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_int]
+        L.orbref_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orbref_copy_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+        L.orbref_bench.restype = C.c_double
+        L.orbref_bench.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
+        L.orbref_arena_allocs.restype = C.c_long
+        _ref = L
+    return _ref
+
+
+class RefExtractor:
+    """The reference's ORBextractor (src/ORBextractor.cc) behind its own constructor signature."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, blur_mode=BLUR_CV331,
+                 canonical=True):
+        self.L = ref_lib()
+        self.nlevels = nlevels
+        self.blur_mode = blur_mode
+        self.h = self.L.orbref_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.L.orbref_set_canonical(self.h, 1 if canonical else 0)
+        self.cap = nfeatures + 4 * nlevels + 64
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orbref_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sf, isf, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        q = np.zeros(n, np.int32)
+        um = np.zeros(16, np.int32)
+        self.L.orbref_tables(self.h, sf.ctypes.data, isf.ctypes.data, s2.ctypes.data, is2.ctypes.data,
+                             q.ctypes.data, um.ctypes.data)
+        return dict(scale=sf, inv_scale=isf, sigma2=s2, inv_sigma2=is2, quotas=q, umax=um)
+
+    def pattern(self):
+        p = np.zeros(1024, np.int32)
+        self.L.orbref_pattern(self.h, p.ctypes.data)
+        return p
+
+    def extract(self, img: np.ndarray, keep_pyramid=False):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        self.L.orbref_set_blur_mode(self.blur_mode)
+        n = self.L.orbref_extract(self.h, img.ctypes.data, w, h, w, kps.ctypes.data, desc.ctypes.data, self.cap,
+                                  1 if keep_pyramid else 0)
+        if n < 0:
+            return None
+        assert n <= self.cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l: int, with_border=False) -> np.ndarray:
+        w, h = C.c_int(), C.c_int()
+        assert self.L.orbref_level_size(self.h, l, C.byref(w), C.byref(h)) == 0
+        W, H = (w.value + 38, h.value + 38) if with_border else (w.value, h.value)
+        out = np.zeros((H, W), np.uint8)
+        assert self.L.orbref_copy_level(self.h, l, out.ctypes.data, W, 1 if with_border else 0) == 0
+        return out
+
+
+def ref_bench(frames: np.ndarray, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, threads=1,
+              canonical=False, repeat=1, blur_mode=BLUR_CV331):
+    """Wall seconds for the reference extractor over frames (n,h,w) on `threads` host threads."""
+    L = ref_lib()
+    L.orbref_set_blur_mode(blur_mode)
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    tot = C.c_long(0)
+    secs = L.orbref_bench(nfeatures, scale_factor, nlevels, ini_th, min_th, frames.ctypes.data, n, w, h, threads,
+                          1 if canonical else 0, repeat, C.byref(tot))
+    return secs, tot.value
+
+
+# ------------------------------------------------------------------------------------------------
+# Independent restatement (oracle/orb_oracle.cc, oracle/match_oracle.cc)
+_orc = None
+
+
+def oracle_lib():
+    global _orc
+    if _orc is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        L = C.CDLL(ORACLE_SO)
+        vp, ci, cf, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+        L.eaoo_resize.argtypes = [vp, ci, ci, sz, vp, ci, ci, sz]
+        L.eaoo_border.argtypes = [vp, ci, ci, sz, vp, sz, ci]
+        L.eaoo_fast.restype = ci
+        L.eaoo_fast.argtypes = [vp, ci, ci, sz, ci, vp, ci]
+        L.eaoo_blur.argtypes = [vp, ci, ci, sz, vp, sz, ci]
+        L.eaoo_atan2.argtypes = [vp, vp, vp, ci]
+        L.eaoo_sincosf.argtypes = [vp, vp, vp, C.c_long]
+        L.eaoo_sincosf_sweep.restype = C.c_long
+        L.eaoo_sincosf_sweep.argtypes = [cf, C.c_uint32]
+        L.eaoo_tables.argtypes = [ci, cf, ci, vp, vp, vp, vp, vp, vp]
+        L.eaoo_fast_cells.restype = ci
+        L.eaoo_fast_cells.argtypes = [vp, ci, ci, ci, ci, vp, ci]
+        L.eaoo_octree.restype = ci
+        L.eaoo_octree.argtypes = [vp, ci, ci, ci, ci, vp, ci]
+        L.eaoo_extract.restype = ci
+        L.eaoo_extract.argtypes = [vp, ci, ci, sz, ci, cf, ci, ci, ci, ci, vp, vp, ci, vp, vp, vp, vp, ci]
+        _orc = L
+    return _orc
+
+
+def o_resize(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    oracle_lib().eaoo_resize(src.ctypes.data, src.shape[1], src.shape[0], src.shape[1], dst.ctypes.data, dw, dh, dw)
+    return dst
+
+
+def o_border(src: np.ndarray, b: int = 19) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.zeros((h + 2 * b, w + 2 * b), np.uint8)
+    oracle_lib().eaoo_border(src.ctypes.data, w, h, w, dst.ctypes.data, w + 2 * b, b)
+    return dst
+
+
+def o_fast(img: np.ndarray, th: int) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = (w // 2 + 1) * (h // 2 + 1)
+    out = np.zeros((cap, 3), np.int32)
+    n = oracle_lib().eaoo_fast(img.ctypes.data, w, h, w, th, out.ctypes.data, cap)
+    return out[:n].copy()
+
+
+def o_blur(img: np.ndarray, mode: int) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    dst = np.zeros((h, w), np.uint8)
+    oracle_lib().eaoo_blur(img.ctypes.data, w, h, w, dst.ctypes.data, w, mode)
+    return dst
+
+
+def o_atan2(y: np.ndarray, x: np.ndarray) -> np.ndarray:
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(len(y), np.float32)
+    oracle_lib().eaoo_atan2(y.ctypes.data, x.ctypes.data, out.ctypes.data, len(y))
+    return out
+
+
+def o_sincosf(x: np.ndarray):
+    x = np.ascontiguousarray(x, np.float32)
+    s = np.zeros_like(x)
+    c = np.zeros_like(x)
+    oracle_lib().eaoo_sincosf(x.ctypes.data, s.ctypes.data, c.ctypes.data, len(x))
+    return s, c
+
+
+def o_tables(nfeatures=1000, scale_factor=1.2, nlevels=8):
+    n = nlevels
+    sf, isf, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+    q = np.zeros(n, np.int32)
+    um = np.zeros(16, np.int32)
+    oracle_lib().eaoo_tables(nfeatures, scale_factor, nlevels, sf.ctypes.data, isf.ctypes.data, s2.ctypes.data,
+                             is2.ctypes.data, q.ctypes.data, um.ctypes.data)
+    return dict(scale=sf, inv_scale=isf, sigma2=s2, inv_sigma2=is2, quotas=q, umax=um)
+
+
+def level_sizes(width, height, scale_factor=1.2, nlevels=8):
+    t = o_tables(1000, scale_factor, nlevels)
+    return [(int(np.rint(np.float32(width) * t["inv_scale"][l])), int(np.rint(np.float32(height) * t["inv_scale"][l])))
+            for l in range(nlevels)]
+
+
+def o_fast_cells(bordered: np.ndarray, ini_th=20, min_th=7) -> np.ndarray:
+    bordered = np.ascontiguousarray(bordered, np.uint8)
+    h, w = bordered.shape[0] - 38, bordered.shape[1] - 38
+    cap = (w // 2 + 2) * (h // 2 + 2)
+    out = np.zeros((cap, 3), np.int32)
+    n = oracle_lib().eaoo_fast_cells(bordered.ctypes.data, w, h, ini_th, min_th, out.ctypes.data, cap)
+    return out[:n].copy()
+
+
+def o_octree(cands: np.ndarray, W: int, H: int, N: int) -> np.ndarray:
+    cands = np.ascontiguousarray(cands, np.int32)
+    cap = max(len(cands), 1)
+    sel = np.zeros(cap, np.int32)
+    n = oracle_lib().eaoo_octree(cands.ctypes.data, len(cands), W, H, N, sel.ctypes.data, cap)
+    return sel[:n].copy()
+
+
+def o_extract(img: np.ndarray, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
+              blur_mode=BLUR_CV331, dumps=False):
+    """Full restated operator().  Returns (kps, desc) or, with dumps, (kps, desc, pyr_levels, blur_levels, cands)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = nfeatures + 4 * nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    L = oracle_lib()
+    if not dumps:
+        n = L.eaoo_extract(img.ctypes.data, w, h, w, nfeatures, scale_factor, nlevels, ini_th, min_th, blur_mode,
+                           kps.ctypes.data, desc.ctypes.data, cap, None, None, None, None, 0)
+        if n < 0:
+            return None
+        return kps[:n].copy(), desc[:n].copy()
+    sizes = level_sizes(w, h, scale_factor, nlevels)
+    pyr = np.zeros(sum((a + 38) * (b + 38) for a, b in sizes), np.uint8)
+    blur = np.zeros(sum(a * b for a, b in sizes), np.uint8)
+    ccap = sum((a // 2 + 2) * (b // 2 + 2) for a, b in sizes)
+    cand = np.zeros((ccap, 3), np.int32)
+    ccnt = np.zeros(nlevels, np.int32)
+    n = L.eaoo_extract(img.ctypes.data, w, h, w, nfeatures, scale_factor, nlevels, ini_th, min_th, blur_mode,
+                       kps.ctypes.data, desc.ctypes.data, cap, pyr.ctypes.data, blur.ctypes.data, cand.ctypes.data,
+                       ccnt.ctypes.data, ccap)
+    pl, bl, cl = [], [], []
+    po = bo = co = 0
+    for l, (a, b) in enumerate(sizes):
+        pl.append(pyr[po:po + (a + 38) * (b + 38)].reshape(b + 38, a + 38)); po += (a + 38) * (b + 38)
+        bl.append(blur[bo:bo + a * b].reshape(b, a)); bo += a * b
+        cl.append(cand[co:co + ccnt[l]].copy()); co += ccnt[l]
+    return kps[:n].copy(), desc[:n].copy(), pl, bl, cl
