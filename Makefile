@@ -1,0 +1,27 @@
+# Builds the product library (CUDA, sm_100a only) and the test-only oracle libraries.
+#   make            -> eao-fusion_b200/lib/libeaof_orb.so
+#   make oracle     -> oracle/liborb_oracle.so (+ oracle/_ref/liborb_ref.so when /root/reference is present)
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 --fmad=false -Xcompiler -fPIC,-Wall -Xptxas -v
+PKG       := eao-fusion_b200
+LIB       := $(PKG)/lib/libeaof_orb.so
+SRCS      := $(PKG)/csrc/eaof_orb.cu $(wildcard $(PKG)/csrc/eaof_match.cu)
+HDRS      := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/eaof_orb.h
+
+all: $(LIB)
+
+$(LIB): $(SRCS) $(HDRS)
+	@mkdir -p $(PKG)/lib
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) 2> $(PKG)/lib/ptxas.log || (cat $(PKG)/lib/ptxas.log; exit 1)
+	@grep -E "registers|spill|error" $(PKG)/lib/ptxas.log | sed 's/^/  /' | head -60
+
+oracle:
+	$(MAKE) -C oracle
+	$(MAKE) -C oracle ref
+
+clean:
+	rm -f $(LIB) $(PKG)/lib/ptxas.log
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

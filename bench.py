@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — ORB front-end throughput on B200 (BASELINE.json metric: ORB frames/s @640x480/1000kp).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): a 1000-frame synthetic 640x480 sequence, nfeatures=1000, 8 levels, 1.2, 20/7.
+A "step" is one pass of the hot path over one batch of B consecutive frames of that sequence (extraction of every
+frame, plus — when the matcher is built — consecutive-frame SearchByProjection-style matching).
+  value  = frames/s with the frames already resident in HBM (device-timed, CUDA events, max over ranks);
+  e2e    = frames/s through the public C-ABI call eaof_orb_extract_batch with pinned HOST buffers: H2D of the
+           frames and D2H of keypoints+descriptors inside the timed region;
+  roofline / stages = per-stage device time (CUDA events inside the library) against the measured HBM peak;
+  cpu_baseline = the reference's own ORBextractor.cc (oracle/_ref) on this box's host cores, bounded sample.
+Multi-GPU: frames are sharded across ranks, no collective on the data path (weak scaling: B frames per GPU per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "eao-fusion_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
+SEQ_LEN = 1000
+METRIC = "ORB frames/s (pyramid+FAST+octree+rBRIEF) @640x480/1000kp"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(level_sizes, kp_per_frame, cand_per_frame):
+    """Per-frame algorithmic bytes per stage, SURVEY.md §8(d)."""
+    P = sum(w * h for w, h in level_sizes)
+    Pb = sum((w + 38) * (h + 38) for w, h in level_sizes)
+    w7, h7 = level_sizes[-1]
+    return {
+        "pyramid": W * H + (P - w7 * h7) + Pb,
+        "fast": P,
+        "octree": 12 * cand_per_frame + 20 * kp_per_frame,
+        "blur": 2 * P,
+        "angle_desc": kp_per_frame * (749 + 1369 + 52),
+    }
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_sequence(n):
+    from eaof import synth
+    tex = synth.base_texture(W, H, seed=1234 + 1)
+    return synth.make_frames(n, W, H, tex=tex)
+
+
+def cpu_baseline_run(frames, cores, seconds_target=8.0):
+    """Reference ORBextractor.cc (oracle/_ref) on host cores: frame-parallel, one extractor instance per thread."""
+    from oracle import pyoracle as po
+    n = min(len(frames), max(cores * 2, 8))
+    sample = frames[:n]
+    secs, _ = po.ref_bench(sample, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, repeat=1)
+    rep = max(1, int(seconds_target / max(secs, 1e-3)))
+    secs, _ = po.ref_bench(sample, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, repeat=rep)
+    return n * rep / secs, f"{n} frames x {rep} passes, frame-parallel on {cores} threads (one extractor per thread)"
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = make_sequence(max(cores * 2, 8))
+    n = len(frames)
+    from oracle import pyoracle as po
+    kind = "reference" if os.path.exists(po.REF_SO) else "port"
+    times = []
+    for i in range(args.warmup + args.steps):
+        secs, _ = po.ref_bench(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, repeat=1)
+        if i >= args.warmup:
+            times.append(secs)
+    tot = sum(times)
+    val = n * len(times) / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"synthetic 640x480 sequence, nfeatures=1000, 8 levels, 1.2, 20/7; step = {n} frames on the host CPU"},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{n} frames per step, frame-parallel on {cores} threads, unmodified reference ORBextractor.cc + cv shim"},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=250)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import eaof
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.batch
+    n_batches = SEQ_LEN // B
+    # every rank owns its own shard of the sequence (frame f -> rank f mod world would give the same work per rank;
+    # weak scaling: each rank processes B frames per step)
+    frames = make_sequence(SEQ_LEN)
+    d_frames = torch.from_numpy(frames).cuda(local_rank)  # inputs resident in HBM before the timed region
+    ex = eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=B, device=local_rank)
+    level_sizes = [ex.level_size(l) for l in range(NLEVELS)]
+    frame_bytes = W * H
+
+    def dev_step(i):
+        b = i % n_batches
+        ex.extract_batch_device(d_frames.data_ptr() + b * B * frame_bytes, B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        dev_step(i)
+    ex.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    # device timing: CUDA events recorded on the stream the kernels are launched on (the handle's own stream)
+    xs = torch.cuda.ExternalStream(ex.stream_ptr(), device=torch.device("cuda", local_rank))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(xs)
+    for i in range(args.steps):
+        dev_step(i)
+    ev1.record(xs)
+    ex.sync()
+    torch.cuda.synchronize()
+    dt_wall = ev0.elapsed_time(ev1) * 1e-3
+    launches_per_step = ex.last_launch_count()
+    counts = ex.fetch_counts(B)
+    kp_per_frame = float(counts.mean())
+    barrier()
+
+    # per-stage device times (CUDA events on the library's stream)
+    ex.set_profiling(True)
+    stage_acc = {}
+    nprof = min(args.steps, 8)
+    for i in range(nprof):
+        dev_step(i)
+        ex.sync()
+        for k, v in ex.stage_times().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / nprof
+    ex.set_profiling(False)
+    step_ms_dev = stage_acc["total"]
+
+    # e2e through the public API: pinned host frames in, keypoints + descriptors out
+    h_frames = torch.from_numpy(frames[:B].copy()).pin_memory()
+    cap = ex.cap
+    h_kps = torch.empty((B, cap, 6), dtype=torch.float32).pin_memory()
+    h_desc = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
+    h_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
+    import ctypes as C
+
+    def e2e_step():
+        rc = ex.L.eaof_orb_extract_batch(ex.h, h_frames.data_ptr(), B, W, H, W, W * H, h_kps.data_ptr(),
+                                         h_desc.data_ptr(), cap, h_cnt.data_ptr())
+        if rc != 0:
+            raise RuntimeError(ex.L.eaof_last_error().decode())
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t1 = time.perf_counter()  # host clock: the call is synchronous and includes the copies by construction
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt_e2e = time.perf_counter() - t1
+    clocks = sampler.finish()
+
+    # max over ranks
+    t = torch.tensor([dt_wall, dt_e2e, step_ms_dev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt_wall, dt_e2e, step_ms_dev = (float(v) for v in t.cpu())
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        value = world * B * args.steps / dt_wall
+        e2e_val = world * B * e2e_steps / dt_e2e
+        cand_per_frame = 6000.0
+        alg = algorithmic_bytes(level_sizes, kp_per_frame, cand_per_frame)
+        stages = {}
+        for k in ("pyramid", "fast", "octree", "blur", "angle_desc"):
+            ms = stage_acc[k]
+            gbs = alg[k] * B / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            stages[k] = {"ms_per_step": ms, "alg_bytes_per_frame": alg[k], "achieved_gbs": gbs, "frac": gbs / hbm_peak}
+        dom = max(("pyramid", "fast", "octree", "blur", "angle_desc"), key=lambda k: stage_acc[k])
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "whole_path": {"alg_bytes_per_frame": sum(alg.values()),
+                                   "achieved": sum(alg.values()) * value / 1e9, "frac": sum(alg.values()) * value / 1e9 / hbm_peak}}
+        cores = os.cpu_count() or 1
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                v, sample = cpu_baseline_run(frames, cores)
+                from oracle import pyoracle as po
+                cpu = {"value": v, "unit": "frames/s", "cores": cores,
+                       "kind": "reference" if os.path.exists(po.REF_SO) else "port", "sample": sample}
+            except Exception as e:  # the baseline is reported, never required for the GPU number
+                cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt_wall / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1000-frame synthetic 640x480 sequence, nfeatures=1000, nlevels=8, "
+                                   "scaleFactor=1.2, iniThFAST=20, minThFAST=7; batched extraction",
+                       "frames_per_step_per_gpu": B, "keypoints_per_frame": kp_per_frame,
+                       "l2_policy": "each step reads a different 77 MB batch and rewrites ~0.7 GB of pyramid/blur "
+                                    "workspace: working set per step exceeds the 126 MB L2",
+                       "parallelism": f"frame-sharded x{world}, no collective"},
+            "device_ms_per_step_events": step_ms_dev,
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
+                    "d2h_bytes_per_step": B * (cap * 56 + 4)},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ex.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,570 @@
+// libeaof_orb.so — host side of the extractor C ABI (include/eaof_orb.h).  Builds the geometry the reference
+// derives per frame (src/ORBextractor.cc:410-470 constructor tables, :1107-1118 level sizes, :773-806 cell grid),
+// owns the device workspace and issues the kernel sequence of orb_kernels.cuh on the handle's stream.
+// There is deliberately no CPU implementation here: every failure to reach the GPU is an error.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/eaof_orb.h"
+#include "orb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(EAOF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }  // cvRound: round-half-even
+inline int cv_floor_f(float v) { int i = (int)v; return i - (i > v); }
+inline short sat_short(int v) { return (short)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
+
+}  // namespace
+
+struct eaof_orb {
+    eaof_orb_params p{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Geom g{};
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> quota;
+    int kpCap = 0;
+    int nBlurTiles = 0;
+    // device
+    uint8_t* dIn = nullptr;      // staging for host-input calls: max_batch frames
+    uint8_t* dPyr = nullptr;     // max_batch pyramid blocks
+    uint8_t* dBlur = nullptr;    // same layout, blurred inner levels
+    int* dTabs = nullptr;        // resize coefficient tables
+    CellDesc* dCells = nullptr;
+    eaof::BlurTile* dTiles = nullptr;
+    uint32_t* dCand = nullptr;
+    uint16_t* dLabel = nullptr;
+    uint32_t* dCandCount = nullptr;  // [batch][nlevels]
+    uint32_t* dSlotXY = nullptr;
+    uint8_t* dSlotScore = nullptr;
+    int* dLvlCount = nullptr;
+    eaof_kp* dKps = nullptr;
+    uint8_t* dDesc = nullptr;
+    int* dKpCount = nullptr;
+    // pinned host staging
+    uint8_t* hIn = nullptr;
+    eaof_kp* hKps = nullptr;
+    uint8_t* hDesc = nullptr;
+    int* hKpCount = nullptr;
+    size_t octSmem = 0;
+    bool profiling = false;
+    cudaEvent_t ev[7] = {};
+    float stageMs[6] = {};
+    int lastLaunches = 0;
+    int lastFrames = 0;
+};
+
+namespace {
+
+// ORBextractor::ORBextractor, src/ORBextractor.cc:410-446 (scale tables + per-level quotas)
+void build_tables(eaof_orb* c) {
+    const int n = c->p.nlevels;
+    const double scaleFactor = c->p.scale_factor;  // the member is a double initialised from the float argument
+    c->scale.assign(n, 1.f);
+    c->sigma2.assign(n, 1.f);
+    for (int i = 1; i < n; ++i) {
+        c->scale[i] = (float)(c->scale[i - 1] * scaleFactor);
+        c->sigma2[i] = c->scale[i] * c->scale[i];
+    }
+    c->invScale.resize(n);
+    c->invSigma2.resize(n);
+    for (int i = 0; i < n; ++i) {
+        c->invScale[i] = 1.0f / c->scale[i];
+        c->invSigma2[i] = 1.0f / c->sigma2[i];
+    }
+    c->quota.assign(n, 0);
+    const float factor = (float)(1.0f / scaleFactor);
+    float nDesired = c->p.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)n));
+    int sum = 0;
+    for (int l = 0; l < n - 1; ++l) {
+        c->quota[l] = cv_round_f(nDesired);
+        sum += c->quota[l];
+        nDesired *= factor;
+    }
+    c->quota[n - 1] = c->p.nfeatures - sum > 0 ? c->p.nfeatures - sum : 0;
+}
+
+int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& cells,
+                   std::vector<eaof::BlurTile>& tiles) {
+    Geom& g = c->g;
+    memset(&g, 0, sizeof g);
+    g.nlevels = c->p.nlevels;
+    g.W = c->p.width;
+    g.H = c->p.height;
+    g.iniTh = c->p.ini_th_fast;
+    g.minTh = c->p.min_th_fast;
+    g.blurMode = c->p.blur_mode;
+    uint64_t off = 0;
+    uint32_t candOff = 0;
+    int slotOff = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        LevelGeom& L = g.L[l];
+        L.w = cv_round_f((float)g.W * c->invScale[l]);  // :1112
+        L.h = cv_round_f((float)g.H * c->invScale[l]);
+        if (L.w < 1 || L.h < 1) return fail(EAOF_ERR_UNSUPPORTED, "pyramid level %d is empty (%dx%d)", l, L.w, L.h);
+        L.pitch = (L.w + 64 + 63) & ~63;
+        L.rows = L.h + 2 * EAOF_EDGE;
+        L.off = (uint32_t)off;
+        off += ((uint64_t)L.pitch * L.rows + 255) & ~(uint64_t)255;
+        // cell grid, :773-787
+        const int maxBX = L.w - EAOF_EDGE + 3, maxBY = L.h - EAOF_EDGE + 3;
+        L.winW = maxBX - EAOF_MIN_BORDER;
+        L.winH = maxBY - EAOF_MIN_BORDER;
+        const float width = (float)L.winW, height = (float)L.winH;
+        L.nCols = (int)(width / 30.f);
+        L.nRows = (int)(height / 30.f);
+        if (L.nCols < 1 || L.nRows < 1) {
+            L.nCols = L.nRows = 0;  // the reference's cell loops do not execute
+            L.wCell = L.hCell = 1;
+        } else {
+            L.wCell = (int)ceilf(width / L.nCols);
+            L.hCell = (int)ceilf(height / L.nRows);
+        }
+        // root nodes, :543-545.  winH == 0 or nIni < 1 is undefined behaviour in the reference.
+        if (L.winH == 0) return fail(EAOF_ERR_UNSUPPORTED, "level %d: detection window height 0 (reference divides by zero)", l);
+        L.nIni = (int)roundf((float)L.winW / (float)L.winH);
+        if (L.nIni < 1) {
+            if (L.nCols > 0) return fail(EAOF_ERR_UNSUPPORTED, "level %d: aspect ratio gives 0 root nodes (reference indexes an empty vector)", l);
+            L.nIni = 0;
+        }
+        L.hX = L.nIni > 0 ? (float)L.winW / L.nIni : 1.f;
+        L.quota = c->quota[l];
+        L.nodeCap = L.quota + 3 > 4 * L.nIni ? L.quota + 3 : 4 * L.nIni;
+        if (L.nodeCap < 4) L.nodeCap = 4;
+        L.scale = c->scale[l];
+        L.kpSize = (float)(int)(31 * c->scale[l]);  // :835
+        L.slotOff = slotOff;
+        slotOff += L.nodeCap;
+        if (L.nodeCap > g.maxNodeCap) g.maxNodeCap = L.nodeCap;
+        // cells, :789-806 (same skips and clipping)
+        L.cellOff = (int)cells.size();
+        uint32_t cap = 0;
+        for (int i = 0; i < L.nRows; ++i) {
+            const int iniY = EAOF_MIN_BORDER + i * L.hCell;
+            int maxY = iniY + L.hCell + 6;
+            if (iniY >= maxBY - 3) continue;
+            if (maxY > maxBY) maxY = maxBY;
+            for (int j = 0; j < L.nCols; ++j) {
+                const int iniX = EAOF_MIN_BORDER + j * L.wCell;
+                int maxX = iniX + L.wCell + 6;
+                if (iniX >= maxBX - 6) continue;
+                if (maxX > maxBX) maxX = maxBX;
+                const int cw = maxX - iniX, ch = maxY - iniY;
+                if (cw < 7 || ch < 7) continue;  // cv::FAST finds nothing in fewer than 7 rows/cols
+                if (cw > 66 || ch > 66) return fail(EAOF_ERR_UNSUPPORTED, "cell larger than 66 px");
+                cells.push_back(CellDesc{(short)l, (short)iniX, (short)iniY, (short)cw, (short)ch, 0});
+                cap += (uint32_t)(((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2));  // NMS keeps no two 8-adjacent pixels
+            }
+        }
+        L.candOff = candOff;
+        L.candCap = (cap + 63) & ~63u;
+        candOff += L.candCap;
+        // resize tables (A.2): per destination column [sx, a0|a1<<16], per row [sy, b0|b1<<16]
+        L.xTab = (int)tabs.size();
+        if (l > 0) {
+            const LevelGeom& S = g.L[l - 1];
+            const double sx_ = 1.0 / ((double)L.w / S.w), sy_ = 1.0 / ((double)L.h / S.h);
+            for (int dx = 0; dx < L.w; ++dx) {
+                float fx = (float)((dx + 0.5) * sx_ - 0.5);
+                int sx = cv_floor_f(fx);
+                fx -= sx;
+                if (sx < 0) { fx = 0; sx = 0; }
+                if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+                const int a0 = sat_short(cv_round_f((1.f - fx) * 2048.f)), a1 = sat_short(cv_round_f(fx * 2048.f));
+                tabs.push_back(sx);
+                tabs.push_back((a0 & 0xffff) | (a1 << 16));
+            }
+            L.yTab = (int)tabs.size();
+            for (int dy = 0; dy < L.h; ++dy) {
+                float fy = (float)((dy + 0.5) * sy_ - 0.5);
+                const int sy = cv_floor_f(fy);
+                fy -= sy;
+                const int b0 = sat_short(cv_round_f((1.f - fy) * 2048.f)), b1 = sat_short(cv_round_f(fy * 2048.f));
+                tabs.push_back(sy);
+                tabs.push_back((b0 & 0xffff) | (b1 << 16));
+            }
+        } else {
+            L.yTab = L.xTab;
+        }
+        for (int ty = 0; ty * BLUR_TH < L.h; ++ty)
+            for (int tx = 0; tx * BLUR_TW < L.w; ++tx) tiles.push_back(eaof::BlurTile{(short)l, (short)tx, (short)ty, 0});
+        if (L.winW + 3 > 4095 || L.winH + 3 > 4095) return fail(EAOF_ERR_UNSUPPORTED, "frames larger than 4096 px are not supported");
+    }
+    g.pyrFrameBytes = off + 4096;  // slack: tile loaders may read a few bytes past the last row
+    g.candPerFrame = candOff;
+    g.slotsPerFrame = slotOff;
+    g.cellsPerFrame = (int)cells.size();
+    if (g.maxNodeCap > 60000) return fail(EAOF_ERR_UNSUPPORTED, "nfeatures too large for 16-bit node labels");
+    return EAOF_OK;
+}
+
+int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t framePitch) {
+    const Geom& g = c->g;
+    cudaStream_t s = c->stream;
+    int launches = 0;
+    const bool prof = c->profiling;
+    if (prof) CK(cudaEventRecord(c->ev[0], s));
+    CK(cudaMemsetAsync(c->dCandCount, 0, sizeof(uint32_t) * (size_t)n * g.nlevels, s));
+    {
+        const LevelGeom& L = g.L[0];
+        dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
+        eaof::k_level0<<<gr, b, 0, s>>>(dImgs, framePitch, stride, c->dPyr, g);
+        ++launches;
+    }
+    for (int l = 1; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.L[l];
+        dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
+        eaof::k_resize<<<gr, b, 0, s>>>(c->dPyr, c->dTabs, g, l);
+        ++launches;
+    }
+    if (prof) CK(cudaEventRecord(c->ev[1], s));
+    if (g.cellsPerFrame > 0) {
+        eaof::k_fast<<<dim3(g.cellsPerFrame, n), 256, 0, s>>>(c->dPyr, c->dCells, c->dCand, c->dCandCount, g);
+        ++launches;
+    }
+    if (prof) CK(cudaEventRecord(c->ev[2], s));
+    eaof::k_octree<<<dim3(g.nlevels, n), OCT_THREADS, c->octSmem, s>>>(c->dCand, c->dCandCount, c->dLabel, c->dSlotXY,
+                                                                         c->dSlotScore, c->dLvlCount, g);
+    ++launches;
+    if (prof) CK(cudaEventRecord(c->ev[3], s));
+    eaof::k_blur<<<dim3(c->nBlurTiles, n), 256, 0, s>>>(c->dPyr, c->dBlur, c->dTiles, g);
+    ++launches;
+    if (prof) CK(cudaEventRecord(c->ev[4], s));
+    {
+        const int warpsPerBlock = 8;
+        dim3 gr((g.slotsPerFrame + warpsPerBlock - 1) / warpsPerBlock, n);
+        eaof::k_angle_desc<<<gr, warpsPerBlock * 32, 0, s>>>(c->dPyr, c->dBlur, c->dSlotXY, c->dSlotScore, c->dLvlCount,
+                                                             c->dKps, c->dDesc, c->dKpCount, c->kpCap, g);
+        ++launches;
+    }
+    if (prof) CK(cudaEventRecord(c->ev[5], s));
+    CK(cudaGetLastError());
+    c->lastLaunches = launches;
+    c->lastFrames = n;
+    return EAOF_OK;
+}
+
+int check_shape(const eaof_orb* c, int width, int height, int n) {
+    if (!c) return fail(EAOF_ERR_ARG, "null handle");
+    if (width != c->p.width || height != c->p.height)
+        return fail(EAOF_ERR_ARG, "frame is %dx%d but the handle was created for %dx%d", width, height, c->p.width, c->p.height);
+    if (n < 1 || n > c->p.max_batch) return fail(EAOF_ERR_ARG, "n_frames %d outside [1, max_batch=%d]", n, c->p.max_batch);
+    return EAOF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* eaof_last_error(void) { return g_err.c_str(); }
+int eaof_abi_version(void) { return EAOF_ABI_VERSION; }
+
+int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
+    if (!params || !out) return fail(EAOF_ERR_ARG, "null argument");
+    *out = nullptr;
+    const eaof_orb_params& p = *params;
+    if (p.nlevels < 1 || p.nlevels > EAOF_MAX_LEVELS) return fail(EAOF_ERR_ARG, "nlevels must be in [1,%d]", EAOF_MAX_LEVELS);
+    if (p.nfeatures < 1 || !(p.scale_factor > 1.0f)) return fail(EAOF_ERR_ARG, "nfeatures >= 1 and scaleFactor > 1 required");
+    if (p.ini_th_fast < 0 || p.min_th_fast < 0 || p.ini_th_fast > 254 || p.min_th_fast > 254)
+        return fail(EAOF_ERR_ARG, "FAST thresholds must be in [0,254]");
+    if (p.blur_mode < 0 || p.blur_mode > 2) return fail(EAOF_ERR_ARG, "unknown blur_mode");
+    if (p.width < 1 || p.height < 1 || p.max_batch < 1) return fail(EAOF_ERR_ARG, "width, height, max_batch must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(EAOF_ERR_CUDA, "no CUDA device: libeaof_orb has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(EAOF_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+
+    eaof_orb* c = new eaof_orb;
+    c->p = p;
+    c->device = device;
+    build_tables(c);
+    std::vector<int> tabs;
+    std::vector<CellDesc> cells;
+    std::vector<eaof::BlurTile> tiles;
+    int rc = build_geometry(c, tabs, cells, tiles);
+    if (rc != EAOF_OK) { delete c; return rc; }
+    const Geom& g = c->g;
+    c->kpCap = g.slotsPerFrame;
+    c->nBlurTiles = (int)tiles.size();
+    const size_t B = (size_t)p.max_batch;
+#define CKD(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            fail(EAOF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                        \
+            eaof_orb_destroy(c);                                                                        \
+            return EAOF_ERR_CUDA;                                                                       \
+        }                                                                                               \
+    } while (0)
+    CKD(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKD(cudaMalloc(&c->dIn, B * (size_t)p.width * p.height));
+    CKD(cudaMalloc(&c->dPyr, B * g.pyrFrameBytes));
+    CKD(cudaMalloc(&c->dBlur, B * g.pyrFrameBytes));
+    CKD(cudaMalloc(&c->dTabs, sizeof(int) * (tabs.size() + 4)));
+    CKD(cudaMalloc(&c->dCells, sizeof(CellDesc) * (cells.size() + 1)));
+    CKD(cudaMalloc(&c->dTiles, sizeof(eaof::BlurTile) * (tiles.size() + 1)));
+    CKD(cudaMalloc(&c->dCand, sizeof(uint32_t) * B * (size_t)(g.candPerFrame + 64)));
+    CKD(cudaMalloc(&c->dLabel, sizeof(uint16_t) * B * (size_t)(g.candPerFrame + 64)));
+    CKD(cudaMalloc(&c->dCandCount, sizeof(uint32_t) * B * g.nlevels));
+    CKD(cudaMalloc(&c->dSlotXY, sizeof(uint32_t) * B * g.slotsPerFrame));
+    CKD(cudaMalloc(&c->dSlotScore, B * g.slotsPerFrame));
+    CKD(cudaMalloc(&c->dLvlCount, sizeof(int) * B * g.nlevels));
+    CKD(cudaMalloc(&c->dKps, sizeof(eaof_kp) * B * c->kpCap));
+    CKD(cudaMalloc(&c->dDesc, 32 * B * c->kpCap));
+    CKD(cudaMalloc(&c->dKpCount, sizeof(int) * B));
+    CKD(cudaMemset(c->dPyr, 0, B * g.pyrFrameBytes));
+    CKD(cudaMemset(c->dBlur, 0, B * g.pyrFrameBytes));
+    CKD(cudaMemset(c->dKpCount, 0, sizeof(int) * B));
+    CKD(cudaMemcpy(c->dTabs, tabs.data(), sizeof(int) * tabs.size(), cudaMemcpyHostToDevice));
+    if (!cells.empty()) CKD(cudaMemcpy(c->dCells, cells.data(), sizeof(CellDesc) * cells.size(), cudaMemcpyHostToDevice));
+    CKD(cudaMemcpy(c->dTiles, tiles.data(), sizeof(eaof::BlurTile) * tiles.size(), cudaMemcpyHostToDevice));
+    CKD(cudaMemcpyToSymbol(eaof::d_pattern, kOrbPattern31, EAOF_ORB_PATTERN_INTS));
+    CKD(cudaMallocHost(&c->hIn, B * (size_t)p.width * p.height));
+    CKD(cudaMallocHost(&c->hKps, sizeof(eaof_kp) * B * c->kpCap));
+    CKD(cudaMallocHost(&c->hDesc, 32 * B * c->kpCap));
+    CKD(cudaMallocHost(&c->hKpCount, sizeof(int) * B));
+    for (auto& e : c->ev) CKD(cudaEventCreate(&e));
+    c->octSmem = (size_t)g.maxNodeCap * 59 + 64;
+    c->octSmem = (c->octSmem + 15) & ~(size_t)15;
+    if (c->octSmem > 200 * 1024) {
+        fail(EAOF_ERR_UNSUPPORTED, "nfeatures too large: quadtree needs %zu B of shared memory", c->octSmem);
+        eaof_orb_destroy(c);
+        return EAOF_ERR_UNSUPPORTED;
+    }
+    CKD(cudaFuncSetAttribute(eaof::k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->octSmem));
+#undef CKD
+    *out = c;
+    return EAOF_OK;
+}
+
+void eaof_orb_destroy(eaof_orb* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->dIn); cudaFree(c->dPyr); cudaFree(c->dBlur); cudaFree(c->dTabs); cudaFree(c->dCells); cudaFree(c->dTiles);
+    cudaFree(c->dCand); cudaFree(c->dLabel); cudaFree(c->dCandCount); cudaFree(c->dSlotXY); cudaFree(c->dSlotScore);
+    cudaFree(c->dLvlCount); cudaFree(c->dKps); cudaFree(c->dDesc); cudaFree(c->dKpCount);
+    cudaFreeHost(c->hIn); cudaFreeHost(c->hKps); cudaFreeHost(c->hDesc); cudaFreeHost(c->hKpCount);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int eaof_orb_max_keypoints(const eaof_orb* c) { return c ? c->kpCap : fail(EAOF_ERR_ARG, "null handle"); }
+
+int eaof_orb_scale_tables(const eaof_orb* c, float* scale, float* inv, float* s2, float* is2, int* fpl) {
+    if (!c) return fail(EAOF_ERR_ARG, "null handle");
+    for (int i = 0; i < c->p.nlevels; ++i) {
+        if (scale) scale[i] = c->scale[i];
+        if (inv) inv[i] = c->invScale[i];
+        if (s2) s2[i] = c->sigma2[i];
+        if (is2) is2[i] = c->invSigma2[i];
+        if (fpl) fpl[i] = c->quota[i];
+    }
+    return EAOF_OK;
+}
+
+int eaof_orb_level_size(const eaof_orb* c, int level, int* w, int* h) {
+    if (!c || level < 0 || level >= c->p.nlevels) return fail(EAOF_ERR_ARG, "bad level");
+    if (w) *w = c->g.L[level].w;
+    if (h) *h = c->g.L[level].h;
+    return EAOF_OK;
+}
+
+int eaof_orb_extract_batch_device(eaof_orb* c, const uint8_t* dImgs, int n, int width, int height, size_t stride,
+                                  size_t framePitch) {
+    int rc = check_shape(c, width, height, n);
+    if (rc) return rc;
+    if (!dImgs || stride < (size_t)width) return fail(EAOF_ERR_ARG, "bad image pointer/stride");
+    CK(cudaSetDevice(c->device));
+    return run_batch(c, dImgs, n, stride, framePitch);
+}
+
+int eaof_orb_sync(eaof_orb* c) {
+    if (!c) return fail(EAOF_ERR_ARG, "null handle");
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->profiling && c->lastFrames > 0) {
+        float tot = 0;
+        for (int i = 0; i < 5; ++i) {
+            CK(cudaEventElapsedTime(&c->stageMs[i], c->ev[i], c->ev[i + 1]));
+            tot += c->stageMs[i];
+        }
+        c->stageMs[5] = tot;
+    }
+    return EAOF_OK;
+}
+
+int eaof_orb_device_results(eaof_orb* c, const eaof_kp** k, const uint8_t** d, const int** n, int* cap) {
+    if (!c) return fail(EAOF_ERR_ARG, "null handle");
+    if (k) *k = c->dKps;
+    if (d) *d = c->dDesc;
+    if (n) *n = c->dKpCount;
+    if (cap) *cap = c->kpCap;
+    return EAOF_OK;
+}
+
+int eaof_orb_fetch_results(eaof_orb* c, int n, eaof_kp* kps, uint8_t* desc, int cap, int* nOut) {
+    if (!c || !nOut || n < 1 || n > c->p.max_batch) return fail(EAOF_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    CK(cudaMemcpyAsync(c->hKpCount, c->dKpCount, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    if (kps) CK(cudaMemcpyAsync(c->hKps, c->dKps, sizeof(eaof_kp) * (size_t)n * c->kpCap, cudaMemcpyDeviceToHost, s));
+    if (desc) CK(cudaMemcpyAsync(c->hDesc, c->dDesc, 32 * (size_t)n * c->kpCap, cudaMemcpyDeviceToHost, s));
+    int rc = eaof_orb_sync(c);
+    if (rc) return rc;
+    for (int f = 0; f < n; ++f) {
+        const int k = c->hKpCount[f];
+        nOut[f] = k;
+        if (k > cap && (kps || desc)) return fail(EAOF_ERR_ARG, "frame %d has %d keypoints but cap is %d", f, k, cap);
+        if (kps) memcpy(kps + (size_t)f * cap, c->hKps + (size_t)f * c->kpCap, sizeof(eaof_kp) * k);
+        if (desc) memcpy(desc + (size_t)f * cap * 32, c->hDesc + (size_t)f * c->kpCap * 32, 32 * (size_t)k);
+    }
+    return EAOF_OK;
+}
+
+int eaof_orb_extract_batch(eaof_orb* c, const uint8_t* imgs, int n, int width, int height, size_t stride,
+                           size_t framePitch, eaof_kp* kps, uint8_t* desc, int cap, int* nOut) {
+    int rc = check_shape(c, width, height, n);
+    if (rc) return rc;
+    if (!imgs || !nOut || stride < (size_t)width) return fail(EAOF_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    // H2D straight from the caller's buffer (true async only when it is pinned)
+    if (stride == (size_t)width && framePitch == (size_t)width * height) {
+        CK(cudaMemcpyAsync(c->dIn, imgs, (size_t)n * width * height, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int f = 0; f < n; ++f)
+            CK(cudaMemcpy2DAsync(c->dIn + (size_t)f * width * height, (size_t)width, imgs + (size_t)f * framePitch, stride,
+                                 (size_t)width, (size_t)height, cudaMemcpyHostToDevice, c->stream));
+    }
+    rc = run_batch(c, c->dIn, n, (size_t)width, (size_t)width * height);
+    if (rc) return rc;
+    return eaof_orb_fetch_results(c, n, kps, desc, cap, nOut);
+}
+
+int eaof_orb_extract(eaof_orb* c, const uint8_t* img, int width, int height, size_t stride, eaof_kp* kps, uint8_t* desc,
+                     int cap, int* nOut) {
+    if (!img || width <= 0 || height <= 0) return fail(EAOF_ERR_EMPTY, "empty image");
+    return eaof_orb_extract_batch(c, img, 1, width, height, stride, stride * (size_t)height, kps, desc, cap, nOut);
+}
+
+int eaof_orb_pyramid_level(eaof_orb* c, int frame, int level, int withBorder, uint8_t* dst, size_t dstStride) {
+    if (!c || !dst || level < 0 || level >= c->p.nlevels || frame < 0 || frame >= c->p.max_batch)
+        return fail(EAOF_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const LevelGeom& L = c->g.L[level];
+    const uint8_t* base = c->dPyr + (size_t)frame * c->g.pyrFrameBytes + L.off;
+    CK(cudaStreamSynchronize(c->stream));
+    if (withBorder)
+        CK(cudaMemcpy2D(dst, dstStride, base + EAOF_INNER_X0 - EAOF_EDGE, L.pitch, L.w + 2 * EAOF_EDGE, L.rows, cudaMemcpyDeviceToHost));
+    else
+        CK(cudaMemcpy2D(dst, dstStride, base + (size_t)EAOF_EDGE * L.pitch + EAOF_INNER_X0, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return EAOF_OK;
+}
+
+int eaof_orb_debug_blurred_level(eaof_orb* c, int frame, int level, uint8_t* dst, size_t dstStride) {
+    if (!c || !dst || level < 0 || level >= c->p.nlevels || frame < 0 || frame >= c->p.max_batch)
+        return fail(EAOF_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const LevelGeom& L = c->g.L[level];
+    const uint8_t* base = c->dBlur + (size_t)frame * c->g.pyrFrameBytes + L.off;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy2D(dst, dstStride, base + (size_t)EAOF_EDGE * L.pitch + EAOF_INNER_X0, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return EAOF_OK;
+}
+
+int eaof_orb_debug_candidates(eaof_orb* c, int frame, int level, int* xys, int cap, int* nOut) {
+    if (!c || !nOut || level < 0 || level >= c->p.nlevels || frame < 0 || frame >= c->p.max_batch)
+        return fail(EAOF_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    uint32_t n = 0;
+    CK(cudaMemcpy(&n, c->dCandCount + (size_t)frame * c->g.nlevels + level, sizeof n, cudaMemcpyDeviceToHost));
+    *nOut = (int)n;
+    const int m = (int)n < cap ? (int)n : cap;
+    if (m > 0 && xys) {
+        std::vector<uint32_t> tmp(m);
+        CK(cudaMemcpy(tmp.data(), c->dCand + (size_t)frame * c->g.candPerFrame + c->g.L[level].candOff, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; ++i) {
+            xys[3 * i] = tmp[i] & 0xfff;
+            xys[3 * i + 1] = (tmp[i] >> 12) & 0xfff;
+            xys[3 * i + 2] = tmp[i] >> 24;
+        }
+    }
+    return EAOF_OK;
+}
+
+// Device sinf/cosf restatement vs this host's libm over every `stride`-th float in [0, hi]; returns mismatches.
+long eaof_debug_sincosf_mismatches(float hi, uint32_t stride) {
+    uint32_t ul;
+    memcpy(&ul, &hi, 4);
+    if (stride == 0) stride = 1;
+    const uint32_t chunk = 1u << 24;
+    float *ds = nullptr, *dc = nullptr;
+    if (cudaMalloc(&ds, sizeof(float) * chunk) != cudaSuccess || cudaMalloc(&dc, sizeof(float) * chunk) != cudaSuccess) {
+        fail(EAOF_ERR_CUDA, "cudaMalloc failed");
+        return -1;
+    }
+    std::vector<float> hs(chunk), hc(chunk);
+    long bad = 0;
+    const uint64_t total = (uint64_t)ul / stride + 1;
+    for (uint64_t base = 0; base < total; base += chunk) {
+        const uint32_t n = (uint32_t)((total - base) < chunk ? (total - base) : chunk);
+        eaof::k_debug_sincosf<<<(n + 255) / 256, 256>>>((uint32_t)(base * stride), stride, n, ds, dc);
+        if (cudaMemcpy(hs.data(), ds, sizeof(float) * n, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(hc.data(), dc, sizeof(float) * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            fail(EAOF_ERR_CUDA, "sincosf sweep failed: %s", cudaGetErrorString(cudaGetLastError()));
+            bad = -1;
+            break;
+        }
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t u = (uint32_t)(base * stride) + i * stride;
+            float f;
+            memcpy(&f, &u, 4);
+            const float rs = sinf(f), rc = cosf(f);
+            bad += memcmp(&rs, &hs[i], 4) != 0;
+            bad += memcmp(&rc, &hc[i], 4) != 0;
+        }
+    }
+    cudaFree(ds);
+    cudaFree(dc);
+    return bad;
+}
+
+int eaof_orb_set_profiling(eaof_orb* c, int on) {
+    if (!c) return fail(EAOF_ERR_ARG, "null handle");
+    c->profiling = on != 0;
+    return EAOF_OK;
+}
+int eaof_orb_stage_times(eaof_orb* c, float* ms6) {
+    if (!c || !ms6) return fail(EAOF_ERR_ARG, "null argument");
+    for (int i = 0; i < 6; ++i) ms6[i] = c->stageMs[i];
+    return EAOF_OK;
+}
+int eaof_orb_last_launch_count(const eaof_orb* c) { return c ? c->lastLaunches : 0; }
+void* eaof_orb_stream(eaof_orb* c) { return c ? (void*)c->stream : nullptr; }
+
+}  // extern "C"

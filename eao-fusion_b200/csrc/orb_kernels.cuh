@@ -1,0 +1,817 @@
+// Hand-written sm_100a kernels of the ORB extraction path (one batch of frames per launch).
+//
+//   k_level0        ComputePyramid level 0: copyMakeBorder(REFLECT_101)            src/ORBextractor.cc:1125-1129
+//   k_resize        ComputePyramid level l>0: resize(INTER_LINEAR)+copyMakeBorder  src/ORBextractor.cc:1118-1124
+//   k_fast          per-cell FAST-9/16 + NMS + iniThFAST/minThFAST retry           src/ORBextractor.cc:789-829
+//   k_octree        DistributeOctTree (+DivideNode), one CTA per (frame, level)    src/ORBextractor.cc:481-763
+//   k_blur          GaussianBlur 7x7 sigma 2, integer arithmetic                   src/ORBextractor.cc:1085-1086
+//   k_angle_desc    IC_Angle + computeOrbDescriptor + keypoint record              src/ORBextractor.cc:77-147,837-847,1095-1101
+//
+// Exactness rules: all pixel work is integer; the three float computations
+// (fastAtan2, angle*pi/180 -> sincosf, pattern rotation) use explicit round-to-nearest intrinsics so nvcc can
+// never contract a multiply-add, and sincosf restates glibc's algorithm because the reference calls
+// std::cos(float)/std::sin(float) (= cosf/sinf), see DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "geom.h"
+#include "orb_pattern.h"
+
+namespace eaof {
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pyramid.  A level row is `pitch` bytes; inner pixel x sits at byte EAOF_INNER_X0 + x, so the bordered
+// span is bytes [13, w+51).  Each thread produces one aligned 4-byte word of one bordered row.
+__global__ void __launch_bounds__(256) k_level0(const uint8_t* __restrict__ in, size_t framePitch, size_t stride,
+                                                uint8_t* __restrict__ pyr, const __grid_constant__ Geom g) {
+    const LevelGeom& L = g.L[0];
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int by = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.z;
+    const int c0 = 12 + 4 * wi;
+    if (by >= L.rows || c0 >= L.w + 52) return;
+    const int y = reflect101(by - EAOF_EDGE, L.h);
+    const uint8_t* src = in + (size_t)f * framePitch + (size_t)y * stride;
+    const int bx = c0 - EAOF_INNER_X0;
+    uint32_t v;
+    if (bx >= 0 && bx + 3 < L.w && ((reinterpret_cast<uintptr_t>(src + bx) & 3) == 0)) {
+        v = __ldg(reinterpret_cast<const uint32_t*>(src + bx));
+    } else {
+        v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v |= (uint32_t)__ldg(src + reflect101(bx + j, L.w)) << (8 * j);
+    }
+    *reinterpret_cast<uint32_t*>(pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)by * L.pitch + c0) = v;
+}
+
+// cv::resize 8UC1 INTER_LINEAR with 11-bit fixed-point coefficients; the border pixel at
+// bordered position (bx,by) equals the resized pixel at the reflected inner position, so resize and
+// copyMakeBorder are one pass.  tabs: per destination column [sx, a0|a1<<16], per row [sy, b0|b1<<16].
+__global__ void __launch_bounds__(256) k_resize(uint8_t* __restrict__ pyr, const int* __restrict__ tabs,
+                                                const __grid_constant__ Geom g, int l) {
+    const LevelGeom& D = g.L[l];
+    const LevelGeom& S = g.L[l - 1];
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int by = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.z;
+    const int c0 = 12 + 4 * wi;
+    if (by >= D.rows || c0 >= D.w + 52) return;
+    uint8_t* frame = pyr + (size_t)f * g.pyrFrameBytes;
+    const int y = reflect101(by - EAOF_EDGE, D.h);
+    const int sy = tabs[D.yTab + 2 * y];
+    const int bb = tabs[D.yTab + 2 * y + 1];
+    const int b0 = (short)(bb & 0xffff), b1 = bb >> 16;
+    const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
+    const uint8_t* sIn = frame + S.off + (size_t)EAOF_EDGE * S.pitch + EAOF_INNER_X0;
+    const uint8_t* r0 = sIn + (size_t)sy0 * S.pitch;
+    const uint8_t* r1 = sIn + (size_t)sy1 * S.pitch;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = reflect101(c0 - EAOF_INNER_X0 + j, D.w);
+        const int sx = tabs[D.xTab + 2 * x];
+        const int aa = tabs[D.xTab + 2 * x + 1];
+        const int a0 = (short)(aa & 0xffff), a1 = aa >> 16;
+        const int sx1 = min(sx + 1, S.w - 1);
+        const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+        const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+        const int d = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        v |= (uint32_t)(d & 0xff) << (8 * j);
+    }
+    *reinterpret_cast<uint32_t*>(frame + D.off + (size_t)by * D.pitch + c0) = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST-9/16.  Ring offsets k=0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)
+// (-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3).
+#define FAST_TP 72  // smem tile pitch (bytes)
+#define RING_OFF(k, P)                                                                                               \
+    ((k) == 0 ? 3 * (P) : (k) == 1 ? 3 * (P) + 1 : (k) == 2 ? 2 * (P) + 2 : (k) == 3 ? (P) + 3 : (k) == 4 ? 3           \
+     : (k) == 5 ? -(P) + 3 : (k) == 6 ? -2 * (P) + 2 : (k) == 7 ? -3 * (P) + 1 : (k) == 8 ? -3 * (P)                    \
+     : (k) == 9 ? -3 * (P)-1 : (k) == 10 ? -2 * (P)-2 : (k) == 11 ? -(P)-3 : (k) == 12 ? -3                             \
+     : (k) == 13 ? (P)-3 : (k) == 14 ? 2 * (P)-2 : 3 * (P)-1)
+
+// max over the 16 contiguous 9-arcs of min(ring - v) (brighter) and of min(v - ring) (darker).
+// corner at threshold t  <=>  result > t ;  OpenCV's cornerScore<16> == result - 1 for a corner.
+__device__ __forceinline__ int arc_best(const uint8_t* p) {
+    const int v = p[0];
+    int d[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = (int)p[RING_OFF(k, FAST_TP)] - v;
+    int mn2[16], mx2[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mn2[k] = min(d[k], d[(k + 1) & 15]);
+        mx2[k] = max(d[k], d[(k + 1) & 15]);
+    }
+    int mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
+        mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+    }
+    int best = -256;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+        best = max(best, max(mn9, -mx9));
+    }
+    return best;
+}
+
+__device__ __forceinline__ int fast_cls(int a, int lo, int hi) { return (a < lo ? 1 : 0) | (a > hi ? 2 : 0); }
+
+// One CTA per cell.  Candidates are appended to the (frame, level) list in arbitrary order; DistributeOctTree
+// only needs their cell-raster rank for tie-breaking, which k_octree recomputes from the coordinates.
+// cand word: x | y<<12 | score<<24 (detection-window coordinates, src/ORBextractor.cc:822-824).
+__global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ pyr, const CellDesc* __restrict__ cells,
+                                              uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount,
+                                              const __grid_constant__ Geom g) {
+    __shared__ __align__(16) uint8_t tile[66 * FAST_TP];
+    __shared__ __align__(16) uint8_t Bm[64 * 64];  // arc score, 1-px zero apron: (x-2, y-2)
+    __shared__ uint16_t lst[3600];
+    __shared__ uint32_t outl[900];
+    __shared__ int nList, nOut;
+    __shared__ uint32_t gBase;
+
+    const CellDesc c = cells[blockIdx.x];
+    const int f = blockIdx.y;
+    const LevelGeom& L = g.L[c.level];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cw = c.cw, ch = c.ch;
+    const int iw = cw - 6, ih = ch - 6;
+    if (iw <= 0 || ih <= 0) return;
+
+    const int col0 = EAOF_INNER_X0 + c.iniX;
+    const int mis = col0 & 3;
+    const uint8_t* src =
+        pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + c.iniY) * L.pitch + (col0 - mis);
+    const int nwords = (mis + cw + 3) >> 2;
+    for (int i = tid; i < ch * nwords; i += 256) {
+        const int r = i / nwords, w = i - r * nwords;
+        *reinterpret_cast<uint32_t*>(tile + r * FAST_TP + 4 * w) =
+            __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * L.pitch + 4 * w));
+    }
+    for (int i = tid; i < 64 * 64 / 4; i += 256) reinterpret_cast<uint32_t*>(Bm)[i] = 0;
+    if (tid == 0) { nList = 0; nOut = 0; }
+    __syncthreads();
+
+    // A: OpenCV's early-out at the lower of the two thresholds, survivors compacted with a warp ballot
+    const int tq = min(g.iniTh, g.minTh);
+    const int npx = iw * ih;
+    for (int i0 = 0; i0 < npx; i0 += 256) {
+        const int i = i0 + tid;
+        bool pass = false;
+        int x = 0, y = 0;
+        if (i < npx) {
+            y = i / iw;
+            x = i - y * iw + 3;
+            y += 3;
+            const uint8_t* p = tile + y * FAST_TP + mis + x;
+            const int v = p[0], lo = v - tq, hi = v + tq;
+            int d = fast_cls(p[RING_OFF(0, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(8, FAST_TP)], lo, hi);
+            if (d) {
+                d &= fast_cls(p[RING_OFF(4, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(12, FAST_TP)], lo, hi);
+                d &= fast_cls(p[RING_OFF(2, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(10, FAST_TP)], lo, hi);
+                d &= fast_cls(p[RING_OFF(6, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(14, FAST_TP)], lo, hi);
+                if (d) {
+                    d &= fast_cls(p[RING_OFF(1, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(9, FAST_TP)], lo, hi);
+                    d &= fast_cls(p[RING_OFF(3, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(11, FAST_TP)], lo, hi);
+                    d &= fast_cls(p[RING_OFF(5, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(13, FAST_TP)], lo, hi);
+                    d &= fast_cls(p[RING_OFF(7, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(15, FAST_TP)], lo, hi);
+                }
+            }
+            pass = d != 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&nList, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) lst[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 8) | x);
+        }
+    }
+    __syncthreads();
+    const int nl = nList;
+    if (nl == 0) return;
+
+    // B: exact arc score of the survivors
+    for (int i = tid; i < nl; i += 256) {
+        const int yx = lst[i], y = yx >> 8, x = yx & 255;
+        const int b = arc_best(tile + y * FAST_TP + mis + x);
+        Bm[(y - 2) * 64 + (x - 2)] = (uint8_t)max(b, 0);
+    }
+    __syncthreads();
+
+    // C: threshold + 8-neighbour NMS inside the cell; retry with minThFAST if nothing survives (:808-816)
+    for (int pass = 0; pass < 2; ++pass) {
+        const int th = pass == 0 ? g.iniTh : g.minTh;
+        for (int i = tid; i < nl; i += 256) {
+            const int yx = lst[i], y = yx >> 8, x = yx & 255;
+            const uint8_t* q = Bm + (y - 2) * 64 + (x - 2);
+            const int b = q[0];
+            if (b > th) {
+                const int s = b - 1;
+                bool keep = true;
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dx == 0 && dy == 0) continue;
+                        const int nb = q[dy * 64 + dx];
+                        keep = keep && (s > (nb > th ? nb - 1 : 0));
+                    }
+                if (keep) {
+                    const int o = atomicAdd(&nOut, 1);
+                    const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
+                    outl[o] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
+                }
+            }
+        }
+        __syncthreads();
+        if (nOut > 0) break;
+    }
+    const int no = nOut;
+    if (no == 0) return;
+    if (tid == 0) gBase = atomicAdd(&candCount[f * g.nlevels + c.level], (uint32_t)no);
+    __syncthreads();
+    uint32_t* dst = cand + (size_t)f * g.candPerFrame + L.candOff + gBase;
+    for (int i = tid; i < no; i += 256) dst[i] = outl[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// DistributeOctTree.  Parallel formulation (validated on the CPU by oracle/orb_oracle.cc against the
+// reference's std::list code): keys never move, each key carries the list position of its node, a pass
+// (a) counts the four quadrant populations of every node that may be split, (b) decides which nodes are split
+// and where their children land, (c) relabels the keys.  push_front puts children in front of the list in
+// reverse creation order, so "later created" == "smaller list position", which is also the canonical
+// tie-break for the reference's (size, pointer) sort.
+#define OCT_THREADS 512
+
+struct OctShared {
+    int n;        // list size
+    int cPrev;    // children created by the previous pass (= candidates live in [0, cPrev))
+    int m;        // nodes in processing order
+    int nsplit;   // how many of them are split
+    int created;  // children created by this pass
+    int flag;
+    int warp[32];
+};
+
+__device__ __forceinline__ int block_excl_scan(int v, int* total, int* warpSums) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warpSums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < (OCT_THREADS / 32) ? warpSums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        warpSums[lane] = s;
+    }
+    __syncthreads();
+    const int base = wid > 0 ? warpSums[wid - 1] : 0;
+    *total = warpSums[OCT_THREADS / 32 - 1];
+    const int r = base + incl - v;
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ int ceil_half(int a) { return (a + 1) >> 1; }  // ceil((float)a/2) for a >= 0
+
+__global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restrict__ cand,
+                                                         const uint32_t* __restrict__ candCount,
+                                                         uint16_t* __restrict__ label, uint32_t* __restrict__ slotXY,
+                                                         uint8_t* __restrict__ slotScore, int* __restrict__ lvlCount,
+                                                         const __grid_constant__ Geom g) {
+    extern __shared__ __align__(16) uint8_t smemRaw[];
+    __shared__ OctShared S;
+    const int l = blockIdx.x, f = blockIdx.y;
+    const LevelGeom& L = g.L[l];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cap = g.maxNodeCap;
+    const int N = L.quota;
+
+    // shared arrays
+    short4* bndA = reinterpret_cast<short4*>(smemRaw);                    // x0,y0,x1,y1
+    short4* bndB = bndA + cap;
+    uint32_t* cntA = reinterpret_cast<uint32_t*>(bndB + cap);
+    uint32_t* cntB = cntA + cap;
+    uint32_t* cc = cntB + cap;                                            // [cap*4] quadrant counts / final best (u64 x cap*2)
+    uint16_t* childPos = reinterpret_cast<uint16_t*>(cc + 4 * (size_t)cap);  // [cap*4]
+    uint16_t* keepPos = childPos + 4 * (size_t)cap;                       // [cap]
+    uint16_t* firstChild = keepPos + cap;                                 // [cap]
+    uint16_t* proc = firstChild + cap;                                    // [cap] processing order -> list position
+    uint16_t* tmpIdx = proc + cap;                                        // [cap]
+    uint8_t* wanted = reinterpret_cast<uint8_t*>(tmpIdx + cap);           // [cap]
+    uint8_t* split = wanted + cap;                                        // [cap]
+    uint8_t* ne = split + cap;                                            // [cap] non-empty children
+
+    const int nk = (int)candCount[f * g.nlevels + l];
+    const uint32_t* keys = cand + (size_t)f * g.candPerFrame + L.candOff;
+    uint16_t* lab = label + (size_t)f * g.candPerFrame + L.candOff;
+    int* outCount = lvlCount + f * g.nlevels + l;
+
+    if (nk == 0 || L.nIni < 1) {
+        if (tid == 0) *outCount = 0;
+        return;
+    }
+
+    // ---- roots (:543-585)
+    for (int i = tid; i < cap; i += OCT_THREADS) cc[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < nk; k += OCT_THREADS) {
+        const int x = keys[k] & 0xfff;
+        const int r = (int)__fdiv_rn((float)x, L.hX);
+        atomicAdd(&cc[r], 1u);
+    }
+    __syncthreads();
+    {
+        // nIni is tiny (1..4 for any sane aspect ratio): thread 0 compacts the non-empty roots
+        if (tid == 0) {
+            int n = 0;
+            for (int i = 0; i < L.nIni; ++i) {
+                if (cc[i] > 0) {
+                    bndA[n] = make_short4((short)(int)__fmul_rn(L.hX, (float)i), 0,
+                                          (short)(int)__fmul_rn(L.hX, (float)(i + 1)), (short)L.winH);
+                    cntA[n] = cc[i];
+                    tmpIdx[i] = (uint16_t)n;
+                    ++n;
+                }
+            }
+            S.n = n;
+            S.cPrev = 0;
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < nk; k += OCT_THREADS) {
+        const int x = keys[k] & 0xfff;
+        lab[k] = tmpIdx[(int)__fdiv_rn((float)x, L.hX)];
+    }
+    __syncthreads();
+
+    short4* bnd = bndA;
+    short4* bnd2 = bndB;
+    uint32_t* cnt = cntA;
+    uint32_t* cnt2 = cntB;
+
+    // One pass.  sorted == false: sweep, every node with more than one key is split (:594-665).
+    // sorted == true: candidates are the >1-key children of the previous pass, split in (size desc,
+    // position asc) order until the list reaches N nodes (:676-737).
+    auto run_pass = [&](bool sorted) {
+        const int n = S.n;
+        const int cPrev = S.cPrev;
+        // 1. processing order
+        int mTotal = 0;
+        for (int i0 = 0; i0 < n; i0 += OCT_THREADS) {
+            const int i = i0 + tid;
+            int w = 0;
+            if (i < n) {
+                w = (cnt[i] > 1 && (!sorted || i < cPrev)) ? 1 : 0;
+                wanted[i] = (uint8_t)w;
+                split[i] = 0;
+                cc[4 * i] = cc[4 * i + 1] = cc[4 * i + 2] = cc[4 * i + 3] = 0;
+            }
+            int tot;
+            const int e = block_excl_scan(w, &tot, S.warp);
+            if (w) (sorted ? tmpIdx : proc)[mTotal + e] = (uint16_t)i;
+            mTotal += tot;
+        }
+        __syncthreads();
+        const int m = mTotal;
+        if (sorted) {
+            // rank by (cnt desc, position asc); keys are unique so ranks are a permutation
+            for (int a = tid; a < m; a += OCT_THREADS) {
+                const int pa = tmpIdx[a];
+                const uint32_t ca = cnt[pa];
+                int r = 0;
+                for (int b = 0; b < m; ++b) {
+                    const int pb = tmpIdx[b];
+                    const uint32_t cb = cnt[pb];
+                    r += (cb > ca) || (cb == ca && pb < pa);
+                }
+                proc[r] = (uint16_t)pa;
+            }
+            __syncthreads();
+        }
+        // 2. quadrant populations
+        for (int k0 = 0; k0 < nk; k0 += OCT_THREADS) {
+            const int k = k0 + tid;
+            int slot = -1;
+            if (k < nk) {
+                const int p = lab[k];
+                if (wanted[p]) {
+                    const uint32_t kw = keys[k];
+                    const int x = kw & 0xfff, y = (kw >> 12) & 0xfff;
+                    const short4 b = bnd[p];
+                    const int midX = b.x + ceil_half(b.z - b.x), midY = b.y + ceil_half(b.w - b.y);
+                    slot = 4 * p + (x < midX ? 0 : 1) + (y < midY ? 0 : 2);
+                }
+            }
+            // warp-aggregated shared atomics (early passes put thousands of keys on four counters)
+            const unsigned act = __ballot_sync(0xffffffffu, slot >= 0);
+            if (slot >= 0) {
+                const unsigned peers = __match_any_sync(act, slot);
+                if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&cc[slot], (uint32_t)__popc(peers));
+            }
+        }
+        __syncthreads();
+        // 3. children per node, in processing order; stop rule for the sorted pass
+        if (tid == 0) { S.nsplit = m; }
+        __syncthreads();
+        if (sorted) {
+            int carry = 0;
+            for (int r0 = 0; r0 < m; r0 += OCT_THREADS) {
+                const int r = r0 + tid;
+                int v = 0;
+                if (r < m) {
+                    const int p = proc[r];
+                    v = (cc[4 * p] > 0) + (cc[4 * p + 1] > 0) + (cc[4 * p + 2] > 0) + (cc[4 * p + 3] > 0) - 1;
+                }
+                int tot;
+                const int e = block_excl_scan(v, &tot, S.warp);
+                if (r < m) {
+                    const int incl = carry + e + v;       // list growth after splitting r
+                    const int before = carry + e;
+                    if (n + incl >= N && n + before < N) atomicMin(&S.nsplit, r + 1);
+                }
+                carry += tot;
+            }
+            __syncthreads();
+        }
+        const int nsplit = S.nsplit;
+        int created = 0;
+        for (int r0 = 0; r0 < nsplit; r0 += OCT_THREADS) {
+            const int r = r0 + tid;
+            int v = 0, p = 0;
+            if (r < nsplit) {
+                p = proc[r];
+                v = (cc[4 * p] > 0) + (cc[4 * p + 1] > 0) + (cc[4 * p + 2] > 0) + (cc[4 * p + 3] > 0);
+            }
+            int tot;
+            const int e = block_excl_scan(v, &tot, S.warp);
+            if (r < nsplit) {
+                split[p] = 1;
+                ne[p] = (uint8_t)v;
+                firstChild[p] = (uint16_t)(created + e);
+            }
+            created += tot;
+        }
+        __syncthreads();
+        // 4. surviving nodes keep their relative order behind the new children
+        int kept = 0;
+        for (int i0 = 0; i0 < n; i0 += OCT_THREADS) {
+            const int i = i0 + tid;
+            const int v = (i < n && !split[i]) ? 1 : 0;
+            int tot;
+            const int e = block_excl_scan(v, &tot, S.warp);
+            if (v) keepPos[i] = (uint16_t)(created + kept + e);
+            kept += tot;
+        }
+        __syncthreads();
+        // 5. new list
+        for (int i = tid; i < n; i += OCT_THREADS) {
+            const short4 b = bnd[i];
+            if (!split[i]) {
+                bnd2[keepPos[i]] = b;
+                cnt2[keepPos[i]] = cnt[i];
+            } else {
+                const int mx = b.x + ceil_half(b.z - b.x), my = b.y + ceil_half(b.w - b.y);
+                int c = firstChild[i];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t kc = cc[4 * i + q];
+                    if (kc == 0) continue;
+                    const int np = created - 1 - c;
+                    bnd2[np] = make_short4((short)((q & 1) ? mx : b.x), (short)((q & 2) ? my : b.y),
+                                           (short)((q & 1) ? b.z : mx), (short)((q & 2) ? b.w : my));
+                    cnt2[np] = kc;
+                    childPos[4 * i + q] = (uint16_t)np;
+                    ++c;
+                }
+            }
+        }
+        __syncthreads();
+        // 6. relabel
+        for (int k = tid; k < nk; k += OCT_THREADS) {
+            const int p = lab[k];
+            if (!split[p]) {
+                lab[k] = keepPos[p];
+            } else {
+                const uint32_t kw = keys[k];
+                const int x = kw & 0xfff, y = (kw >> 12) & 0xfff;
+                const short4 b = bnd[p];
+                const int midX = b.x + ceil_half(b.z - b.x), midY = b.y + ceil_half(b.w - b.y);
+                lab[k] = childPos[4 * p + (x < midX ? 0 : 1) + (y < midY ? 0 : 2)];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            S.n = created + kept;
+            S.cPrev = created;
+        }
+        short4* tb = bnd; bnd = bnd2; bnd2 = tb;
+        uint32_t* tc = cnt; cnt = cnt2; cnt2 = tc;
+        __syncthreads();
+    };
+
+    auto count_expandable = [&]() -> int {  // children of the last pass with more than one key
+        const int cPrev = S.cPrev;
+        int v = 0;
+        for (int i = tid; i < cPrev; i += OCT_THREADS) v += cnt[i] > 1;
+        int tot;
+        block_excl_scan(v, &tot, S.warp);
+        return tot;
+    };
+
+    bool finish = false;
+    while (!finish) {
+        const int prevSize = S.n;
+        __syncthreads();
+        run_pass(false);
+        const int size = S.n;
+        if (size >= N || size == prevSize) {
+            finish = true;
+        } else {
+            const int nToExpand = count_expandable();
+            if (size + 3 * nToExpand > N) {
+                while (!finish) {
+                    const int prev2 = S.n;
+                    __syncthreads();
+                    if (count_expandable() > 0) run_pass(true);
+                    if (S.n >= N || S.n == prev2) finish = true;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- best response per node, first in cell-raster order wins (:741-760)
+    const int n = S.n;
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(cc);
+    for (int i = tid; i < n; i += OCT_THREADS) best[i] = 0ull;
+    __syncthreads();
+    for (int k = tid; k < nk; k += OCT_THREADS) {
+        const uint32_t kw = keys[k];
+        const int x = kw & 0xfff, y = (kw >> 12) & 0xfff;
+        const uint32_t sc = kw >> 24;
+        const int cj = (x - 3) / L.wCell, ci = (y - 3) / L.hCell;
+        const uint32_t ord = ((uint32_t)(ci * L.nCols + cj) << 12) | ((uint32_t)(y - 3 - ci * L.hCell) << 6) |
+                             (uint32_t)(x - 3 - cj * L.wCell);
+        atomicMax(&best[lab[k]], ((unsigned long long)(sc + 1) << 32) | (0xffffffffu - ord));
+    }
+    __syncthreads();
+    uint32_t* oXY = slotXY + (size_t)f * g.slotsPerFrame + L.slotOff;
+    uint8_t* oSc = slotScore + (size_t)f * g.slotsPerFrame + L.slotOff;
+    for (int i = tid; i < n; i += OCT_THREADS) {
+        const unsigned long long b = best[i];
+        const uint32_t ord = 0xffffffffu - (uint32_t)(b & 0xffffffffu);
+        const int cell = ord >> 12, ci = cell / L.nCols, cj = cell - ci * L.nCols;
+        const int y = ci * L.hCell + 3 + ((ord >> 6) & 63), x = cj * L.wCell + 3 + (ord & 63);
+        oXY[i] = (uint32_t)x | ((uint32_t)y << 16);
+        oSc[i] = (uint8_t)((b >> 32) - 1);
+    }
+    if (tid == 0) *outCount = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian blur 7x7, sigma 2 on the inner level (borders come from the REFLECT_101 pyramid border, which is
+// what cv::GaussianBlur(BORDER_REFLECT_101) on the cloned ROI sees).  Integer arithmetic, SURVEY.md A.6.
+#define BLUR_TW 64
+#define BLUR_TH 32
+struct BlurTile { short level, tx, ty, pad; };
+
+__global__ void __launch_bounds__(256) k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
+                                              const BlurTile* __restrict__ tiles, const __grid_constant__ Geom g) {
+    __shared__ __align__(16) uint8_t in[(BLUR_TH + 6) * (BLUR_TW + 8)];
+    __shared__ uint16_t hs[(BLUR_TH + 6) * BLUR_TW];
+    const BlurTile t = tiles[blockIdx.x];
+    const int f = blockIdx.y;
+    const LevelGeom& L = g.L[t.level];
+    const int x0 = t.tx * BLUR_TW, y0 = t.ty * BLUR_TH;
+    const int tid = threadIdx.x;
+    const uint8_t* base = pyr + (size_t)f * g.pyrFrameBytes + L.off;
+    // rows y0-3 .. y0+TH+2 (clamped to the bordered buffer), columns x0-4 .. x0+TW+3 as aligned words
+    constexpr int WPR = (BLUR_TW + 8) / 4;
+    for (int i = tid; i < (BLUR_TH + 6) * WPR; i += 256) {
+        const int r = i / WPR, w = i - r * WPR;
+        const int by = min(y0 - 3 + r + EAOF_EDGE, L.rows - 1);
+        int col = EAOF_INNER_X0 + x0 - 4 + 4 * w;
+        col = min(col, L.pitch - 4);
+        reinterpret_cast<uint32_t*>(in)[i] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)by * L.pitch + col));
+    }
+    __syncthreads();
+    const bool cv4 = g.blurMode == 1;
+    const int k0 = 18, k1 = 34, k2 = cv4 ? 48 : 49, k3 = cv4 ? 56 : 55;
+    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
+        const uint8_t* p = in + r * (BLUR_TW + 8) + c + 1;  // p[0] = pixel x-3
+        const int s = k0 * (p[0] + p[6]) + k1 * (p[1] + p[5]) + k2 * (p[2] + p[4]) + k3 * p[3];
+        hs[i] = (uint16_t)s;  // <= 255*257 = 65535
+    }
+    __syncthreads();
+    const int simdW = g.blurMode == 2 ? (L.w & ~3) : 0;
+    uint8_t* outBase = blur + (size_t)f * g.pyrFrameBytes + L.off + (size_t)EAOF_EDGE * L.pitch + EAOF_INNER_X0;
+    for (int i = tid; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
+        const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
+        const int y = y0 + r, x = x0 + c4;
+        if (y >= L.h || x >= L.w) continue;
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint16_t* q = hs + r * BLUR_TW + c4 + j;
+            const int acc = k0 * ((int)q[0] + q[6 * BLUR_TW]) + k1 * ((int)q[BLUR_TW] + q[5 * BLUR_TW]) +
+                            k2 * ((int)q[2 * BLUR_TW] + q[4 * BLUR_TW]) + k3 * (int)q[3 * BLUR_TW];
+            int o;
+            if (x + j < simdW) {
+                o = acc >> 16;
+                const int rem = acc & 0xffff;
+                o += (rem > 32768) || (rem == 32768 && (o & 1));
+            } else {
+                o = (acc + 32768) >> 16;
+            }
+            v |= (uint32_t)min(o, 255) << (8 * j);
+        }
+        // the padded row always has room for a full word (pitch >= w + 64)
+        *reinterpret_cast<uint32_t*>(outBase + (size_t)y * L.pitch + x) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fastAtan2 (degrees), SURVEY.md A.5 — every operation rounded to fp32 separately.
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float k180pi = (float)(180 / 3.1415926535897932384626433832795);
+    const float p1 = __fmul_rn(0.9997878412794807f, k180pi), p3 = __fmul_rn(-0.3258083974640975f, k180pi),
+                p5 = __fmul_rn(0.1555786518463281f, k180pi), p7 = __fmul_rn(-0.04432655554792128f, k180pi);
+    const float eps = 2.2204460492503131e-16f;  // (float)DBL_EPSILON
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// glibc 2.39 sinf/cosf (sysdeps/ieee754/flt-32/s_sincosf.h) for 0 <= y < 120, in double arithmetic.
+__device__ __forceinline__ float sincos_poly(double x, double x2, bool neg, int n) {
+    const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+                 C4 = 0x1.99343027bf8c3p-16;
+    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+    if ((n & 1) == 0) {
+        const double x3 = __dmul_rn(x, x2);
+        const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
+        const double x7 = __dmul_rn(x3, x2);
+        const double s = __dadd_rn(x, __dmul_rn(x3, S1));
+        return __double2float_rn(__dadd_rn(s, __dmul_rn(x7, s1)));
+    }
+    const double sg = neg ? -1.0 : 1.0;
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = __dadd_rn(sg * C3, __dmul_rn(x2, sg * C4));
+    const double c1 = __dadd_rn(sg * C0, __dmul_rn(x2, sg * C1));
+    const double x6 = __dmul_rn(x4, x2);
+    const double c = __dadd_rn(c1, __dmul_rn(x4, sg * C2));
+    return __double2float_rn(__dadd_rn(c, __dmul_rn(x6, c2)));
+}
+__device__ __forceinline__ void glibc_sincosf(float y, float* sp, float* cp) {
+    double x = (double)y;
+    const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ff;
+    if (top < ((0x3f490fdbu >> 20) & 0x7ff)) {  // |y| < pi/4 (abstop12 compare)
+        const double x2 = __dmul_rn(x, x);
+        if (top < ((0x39800000u >> 20) & 0x7ff)) {  // |y| < 2^-12
+            *sp = y;
+            *cp = 1.0f;
+            return;
+        }
+        *sp = sincos_poly(x, x2, false, 0);
+        *cp = sincos_poly(x, x2, false, 1);
+        return;
+    }
+    const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+    const int n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __dsub_rn(x, __dmul_rn((double)n, 0x1.921FB54442D18p0));
+    const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    const bool neg = (n & 2) != 0;
+    const double xs = __dmul_rn(x, s), x2 = __dmul_rn(x, x);
+    *sp = sincos_poly(xs, x2, neg, n);
+    *cp = sincos_poly(xs, x2, neg, n ^ 1);
+}
+
+__global__ void k_debug_sincosf(uint32_t firstBits, uint32_t stride, uint32_t n, float* s, float* c) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    glibc_sincosf(__uint_as_float(firstBits + i * stride), &s[i], &c[i]);
+}
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // src/ORBextractor.cc:454-469
+__device__ __align__(16) signed char d_pattern[EAOF_ORB_PATTERN_INTS];
+
+// One warp per keypoint slot.  IC_Angle on the unblurred bordered level, descriptor on the blurred level.
+__global__ void __launch_bounds__(256) k_angle_desc(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
+                                                    const uint32_t* __restrict__ slotXY,
+                                                    const uint8_t* __restrict__ slotScore,
+                                                    const int* __restrict__ lvlCount, void* __restrict__ kpsOut,
+                                                    uint8_t* __restrict__ descOut, int* __restrict__ kpCount,
+                                                    int kpCap, const __grid_constant__ Geom g) {
+    const int f = blockIdx.y;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= g.slotsPerFrame) return;
+    int l = 0;
+    while (l + 1 < g.nlevels && warp >= g.L[l + 1].slotOff) ++l;
+    const LevelGeom& L = g.L[l];
+    const int p = warp - L.slotOff;
+    const int* lc = lvlCount + f * g.nlevels;
+    if (warp == 0 && lane == 0) {
+        int tot = 0;
+        for (int i = 0; i < g.nlevels; ++i) tot += lc[i];
+        kpCount[f] = tot;
+    }
+    if (p >= lc[l]) return;
+    int outIdx = p;
+    for (int i = 0; i < l; ++i) outIdx += lc[i];
+
+    const uint32_t xy = slotXY[(size_t)f * g.slotsPerFrame + warp];
+    const int X = (int)(xy & 0xffff) + EAOF_MIN_BORDER, Y = (int)(xy >> 16) + EAOF_MIN_BORDER;  // :841-842
+    const size_t lvlBase = (size_t)f * g.pyrFrameBytes + L.off + (size_t)EAOF_EDGE * L.pitch + EAOF_INNER_X0;
+    const uint8_t* ctr = pyr + lvlBase + (size_t)Y * L.pitch + X;
+
+    // IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc
+    int m10 = 0, m01 = 0;
+    const int u = lane - 15;
+    if (lane < 31) {
+#pragma unroll 1
+        for (int v = -15; v <= 15; ++v) {
+            if (abs(u) <= c_umax[abs(v)]) {
+                const int val = ctr[v * L.pitch + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // computeOrbDescriptor: lane i produces byte i (pairs 8i..8i+7)
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    float a, b;
+    glibc_sincosf(__fmul_rn(angle, factorPI), &b, &a);
+    const uint8_t* bc = blur + lvlBase + (size_t)Y * L.pitch + X;
+    const int4 pa = reinterpret_cast<const int4*>(d_pattern)[2 * lane];
+    const int4 pb = reinterpret_cast<const int4*>(d_pattern)[2 * lane + 1];
+    const int words[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float x0 = (float)(signed char)(words[k] & 0xff), y0 = (float)(signed char)((words[k] >> 8) & 0xff);
+        const float x1 = (float)(signed char)((words[k] >> 16) & 0xff), y1 = (float)(signed char)(words[k] >> 24);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = bc[r0 * L.pitch + c0], t1 = bc[r1 * L.pitch + c1];
+        val |= (t0 < t1) << k;
+    }
+    if (outIdx < kpCap) {
+        descOut[((size_t)f * kpCap + outIdx) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            float* o = reinterpret_cast<float*>(kpsOut) + ((size_t)f * kpCap + outIdx) * 6;
+            float px = (float)X, py = (float)Y;
+            if (l != 0) { px = __fmul_rn(px, L.scale); py = __fmul_rn(py, L.scale); }
+            o[0] = px;
+            o[1] = py;
+            o[2] = L.kpSize;
+            o[3] = angle;
+            o[4] = (float)slotScore[(size_t)f * g.slotsPerFrame + warp];
+            reinterpret_cast<int*>(o)[5] = l;
+        }
+    }
+}
+
+}  // namespace eaof

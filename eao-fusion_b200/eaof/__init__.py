@@ -1,0 +1,214 @@
+"""Thin ctypes loader for libeaof_orb.so (the C ABI declared in include/eaof_orb.h).
+
+The product is the CUDA library plus the C++ drop-in classes in ../dropin; this Python layer exists only so that
+tests/, bench.py and __graft_entry__.py can drive the C ABI.  It never falls back to a CPU implementation: a missing
+library or a missing CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libeaof_orb.so")
+
+BLUR_CV331, BLUR_CV4, BLUR_CV331_SSE2 = 0, 1, 2
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4")])
+
+
+class EaofError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("ini_th_fast", C.c_int),
+                ("min_th_fast", C.c_int), ("blur_mode", C.c_int), ("width", C.c_int), ("height", C.c_int),
+                ("max_batch", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EaofError(f"{LIB_PATH} is missing: run `make` (python -c 'import __graft_entry__ as g; g.build()')")
+        L = C.CDLL(LIB_PATH)
+        vp, ci, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.eaof_last_error.restype = C.c_char_p
+        L.eaof_orb_create.argtypes = [C.POINTER(Params), ci, C.POINTER(vp)]
+        L.eaof_orb_destroy.argtypes = [vp]
+        L.eaof_orb_max_keypoints.argtypes = [vp]
+        L.eaof_orb_scale_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.eaof_orb_level_size.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
+        L.eaof_orb_extract.argtypes = [vp, vp, ci, ci, sz, vp, vp, ci, C.POINTER(ci)]
+        L.eaof_orb_extract_batch.argtypes = [vp, vp, ci, ci, ci, sz, sz, vp, vp, ci, vp]
+        L.eaof_orb_extract_batch_device.argtypes = [vp, vp, ci, ci, ci, sz, sz]
+        L.eaof_orb_sync.argtypes = [vp]
+        L.eaof_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ci)]
+        L.eaof_orb_fetch_results.argtypes = [vp, ci, vp, vp, ci, vp]
+        L.eaof_orb_pyramid_level.argtypes = [vp, ci, ci, ci, vp, sz]
+        L.eaof_orb_debug_blurred_level.argtypes = [vp, ci, ci, vp, sz]
+        L.eaof_orb_debug_candidates.argtypes = [vp, ci, ci, vp, ci, C.POINTER(ci)]
+        L.eaof_orb_set_profiling.argtypes = [vp, ci]
+        L.eaof_orb_stage_times.argtypes = [vp, vp]
+        L.eaof_orb_last_launch_count.argtypes = [vp]
+        L.eaof_orb_stream.restype = vp
+        L.eaof_orb_stream.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _ck(rc: int):
+    if rc != 0:
+        raise EaofError(f"eaof error {rc}: {lib().eaof_last_error().decode()}")
+
+
+class ORBextractor:
+    """Mirror of ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-111) over the C ABI.
+
+    Constructor arguments keep the reference's order and meaning; width/height/max_batch size the device workspace.
+    """
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, *, width=640,
+                 height=480, max_batch=1, blur_mode=BLUR_CV331, device=0):
+        self.L = lib()
+        self.params = Params(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, blur_mode, width, height, max_batch)
+        h = C.c_void_p()
+        _ck(self.L.eaof_orb_create(C.byref(self.params), device, C.byref(h)))
+        self.h = h
+        self.nlevels = nlevels
+        self.width, self.height, self.max_batch = width, height, max_batch
+        self.cap = self.L.eaof_orb_max_keypoints(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.eaof_orb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- getters (include/ORBextractor.h:60-80)
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return float(self.params.scale_factor)
+
+    def _tables(self):
+        n = self.nlevels
+        a, b, c, d = (np.zeros(n, np.float32) for _ in range(4))
+        q = np.zeros(n, np.int32)
+        _ck(self.L.eaof_orb_scale_tables(self.h, a.ctypes.data, b.ctypes.data, c.ctypes.data, d.ctypes.data, q.ctypes.data))
+        return a, b, c, d, q
+
+    def GetScaleFactors(self):
+        return self._tables()[0]
+
+    def GetInverseScaleFactors(self):
+        return self._tables()[1]
+
+    def GetScaleSigmaSquares(self):
+        return self._tables()[2]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tables()[3]
+
+    def features_per_level(self):
+        return self._tables()[4]
+
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        _ck(self.L.eaof_orb_level_size(self.h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    # ---- operator()
+    def __call__(self, image: np.ndarray):
+        """One frame, host buffers.  Returns (keypoints[KP_DTYPE], descriptors[n,32]) or None for an empty image."""
+        if image is None or image.size == 0:
+            return None  # the reference returns silently, src/ORBextractor.cc:1046-1047
+        assert image.dtype == np.uint8 and image.ndim == 2  # assert(image.type() == CV_8UC1), :1050
+        image = np.ascontiguousarray(image)
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int()
+        _ck(self.L.eaof_orb_extract(self.h, image.ctypes.data, image.shape[1], image.shape[0], image.strides[0],
+                                    kps.ctypes.data, desc.ctypes.data, self.cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, frames: np.ndarray):
+        """frames (n,h,w) u8 on the host -> list of (keypoints, descriptors)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w = frames.shape
+        kps = np.zeros((n, self.cap), KP_DTYPE)
+        desc = np.zeros((n, self.cap, 32), np.uint8)
+        cnt = np.zeros(n, np.int32)
+        _ck(self.L.eaof_orb_extract_batch(self.h, frames.ctypes.data, n, w, h, w, w * h, kps.ctypes.data,
+                                          desc.ctypes.data, self.cap, cnt.ctypes.data))
+        return [(kps[f, :cnt[f]].copy(), desc[f, :cnt[f]].copy()) for f in range(n)]
+
+    def extract_batch_device(self, d_ptr: int, n: int, stride=None, frame_pitch=None):
+        stride = stride or self.width
+        frame_pitch = frame_pitch or self.width * self.height
+        _ck(self.L.eaof_orb_extract_batch_device(self.h, d_ptr, n, self.width, self.height, stride, frame_pitch))
+
+    def sync(self):
+        _ck(self.L.eaof_orb_sync(self.h))
+
+    def fetch(self, n: int):
+        kps = np.zeros((n, self.cap), KP_DTYPE)
+        desc = np.zeros((n, self.cap, 32), np.uint8)
+        cnt = np.zeros(n, np.int32)
+        _ck(self.L.eaof_orb_fetch_results(self.h, n, kps.ctypes.data, desc.ctypes.data, self.cap, cnt.ctypes.data))
+        return [(kps[f, :cnt[f]].copy(), desc[f, :cnt[f]].copy()) for f in range(n)]
+
+    def fetch_counts(self, n: int):
+        cnt = np.zeros(n, np.int32)
+        _ck(self.L.eaof_orb_fetch_results(self.h, n, None, None, 0, cnt.ctypes.data))
+        return cnt
+
+    def device_results(self):
+        k, d, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        cap = C.c_int()
+        _ck(self.L.eaof_orb_device_results(self.h, C.byref(k), C.byref(d), C.byref(c), C.byref(cap)))
+        return k.value, d.value, c.value, cap.value
+
+    # ---- mvImagePyramid (include/ORBextractor.h:85) and stage dumps
+    def pyramid_level(self, level, frame=0, with_border=False):
+        w, h = self.level_size(level)
+        W, H = (w + 38, h + 38) if with_border else (w, h)
+        out = np.zeros((H, W), np.uint8)
+        _ck(self.L.eaof_orb_pyramid_level(self.h, frame, level, 1 if with_border else 0, out.ctypes.data, W))
+        return out
+
+    def blurred_level(self, level, frame=0):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        _ck(self.L.eaof_orb_debug_blurred_level(self.h, frame, level, out.ctypes.data, w))
+        return out
+
+    def candidates(self, level, frame=0):
+        w, h = self.level_size(level)
+        cap = (w // 2 + 2) * (h // 2 + 2)
+        out = np.zeros((cap, 3), np.int32)
+        n = C.c_int()
+        _ck(self.L.eaof_orb_debug_candidates(self.h, frame, level, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def set_profiling(self, on=True):
+        _ck(self.L.eaof_orb_set_profiling(self.h, 1 if on else 0))
+
+    def stage_times(self):
+        ms = np.zeros(6, np.float32)
+        _ck(self.L.eaof_orb_stage_times(self.h, ms.ctypes.data))
+        return dict(zip(("pyramid", "fast", "octree", "blur", "angle_desc", "total"), (float(v) for v in ms)))
+
+    def stream_ptr(self):
+        return self.L.eaof_orb_stream(self.h)
+
+    def last_launch_count(self):
+        return self.L.eaof_orb_last_launch_count(self.h)

@@ -1,0 +1,136 @@
+/*
+ * eaof_orb.h — C ABI of libeaof_orb.so, the B200 (sm_100a) ORB front-end.
+ *
+ * The reference (ChenJiahao031008/EAO-Fusion) has no plugin/FFI layer: the boundary of its ORB hot path is the
+ * C++ class interface in include/ORBextractor.h:45-111 and include/ORBmatcher.h:37-102.  Every entry point below
+ * names the reference interface it replaces; eao-fusion_b200/dropin/ re-creates those two classes on top of this
+ * ABI so that Frame.cc / Tracking.cc re-link without source changes.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative EAOF_ERR_* code,
+ * with a human-readable reason available from eaof_last_error() (thread-local).  There is NO CPU fallback: without
+ * a CUDA device eaof_orb_create fails with EAOF_ERR_CUDA.  One handle = one CUDA stream + one device workspace;
+ * calls on one handle must be serialised by the caller, different handles are independent (the reference runs two
+ * extractor instances concurrently for stereo, src/Frame.cc:113-116).
+ */
+#ifndef EAOF_ORB_H
+#define EAOF_ORB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EAOF_ABI_VERSION 1
+#define EAOF_MAX_LEVELS 16
+
+enum {
+    EAOF_OK = 0,
+    EAOF_ERR_ARG = -1,         /* null pointer, bad size, capacity too small */
+    EAOF_ERR_CUDA = -2,        /* CUDA runtime/driver failure (no device, launch error, out of memory) */
+    EAOF_ERR_UNSUPPORTED = -3, /* shape the reference itself has undefined behaviour for */
+    EAOF_ERR_EMPTY = -4,       /* empty image: the reference returns silently, src/ORBextractor.cc:1046-1047 */
+    EAOF_ERR_NCCL = -5
+};
+
+/* Gaussian-blur arithmetic: OpenCV-version-dependent, so explicit. */
+enum {
+    EAOF_BLUR_CV331 = 0,      /* OpenCV 3.3.1 8U path: taps 18,34,49,55,49,34,18 (sum 257), (S+2^15)>>16 [default] */
+    EAOF_BLUR_CV4 = 1,        /* OpenCV >=3.4.1/4.x: taps 18,34,48,56,48,34,18 (sum 256), (S+2^15)>>16 */
+    EAOF_BLUR_CV331_SSE2 = 2  /* 3.3.1 taps, columns x < 4*floor(w/4) rounded half-to-even (SSE2 float column pass) */
+};
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * include/ORBextractor.h:51-52, src/ORBextractor.cc:410-470 — plus workspace sizing. */
+typedef struct eaof_orb_params {
+    int nfeatures;
+    float scale_factor;
+    int nlevels;
+    int ini_th_fast;
+    int min_th_fast;
+    int blur_mode;  /* EAOF_BLUR_* */
+    int width;      /* frame size the workspace is built for (all frames of a handle share it) */
+    int height;
+    int max_batch;  /* frames per batched call (>= 1) */
+} eaof_orb_params;
+
+/* One output keypoint: the fields of cv::KeyPoint the reference fills (src/ORBextractor.cc:837-847,1095-1101);
+ * class_id is always -1 there and is not transported. */
+typedef struct eaof_kp {
+    float x, y;     /* pt, already multiplied by mvScaleFactor[octave] */
+    float size;     /* (int)(31 * mvScaleFactor[octave]) */
+    float angle;    /* IC_Angle, degrees in [0,360) */
+    float response; /* FAST score */
+    int octave;
+} eaof_kp;
+
+typedef struct eaof_orb eaof_orb;
+
+const char* eaof_last_error(void);
+int eaof_abi_version(void);
+
+int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out);
+void eaof_orb_destroy(eaof_orb* ctx);
+
+/* Upper bound on keypoints per frame (sum over levels of max(quota+3, 4*nIni)); size kps/desc with it. */
+int eaof_orb_max_keypoints(const eaof_orb* ctx);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:66-80) and mnFeaturesPerLevel; arrays of nlevels entries, any may be NULL. */
+int eaof_orb_scale_tables(const eaof_orb* ctx, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                          int* features_per_level);
+/* Inner size of pyramid level `level` (src/ORBextractor.cc:1112). */
+int eaof_orb_level_size(const eaof_orb* ctx, int level, int* width, int* height);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors)  src/ORBextractor.cc:1043-1105, one frame,
+ * HOST buffers, synchronous.  img: 8-bit single channel, `stride` bytes per row.  kps/desc hold `cap` entries
+ * (desc: cap x 32 bytes, row i belongs to kps[i]).  *n_out receives the count. */
+int eaof_orb_extract(eaof_orb* ctx, const uint8_t* img, int width, int height, size_t stride, eaof_kp* kps,
+                     uint8_t* desc, int cap, int* n_out);
+
+/* Batched form for frame sequences: n_frames <= max_batch images of width x height, image f at
+ * imgs + f*frame_pitch.  Outputs: frame f's keypoints at kps + f*cap, descriptors at desc + f*cap*32,
+ * count in n_out[f].  HOST buffers (pinned memory recommended), synchronous. */
+int eaof_orb_extract_batch(eaof_orb* ctx, const uint8_t* imgs, int n_frames, int width, int height, size_t stride,
+                           size_t frame_pitch, eaof_kp* kps, uint8_t* desc, int cap, int* n_out);
+
+/* Same, with the frames already resident in device memory (d_imgs, tightly packed rows of `stride` bytes); results
+ * stay on the device.  Asynchronous on the handle's stream; use eaof_orb_sync or the accessors below. */
+int eaof_orb_extract_batch_device(eaof_orb* ctx, const uint8_t* d_imgs, int n_frames, int width, int height,
+                                  size_t stride, size_t frame_pitch);
+int eaof_orb_sync(eaof_orb* ctx);
+/* Device-resident results of the last batch: kps[f*cap_out + i], desc[(f*cap_out + i)*32], counts[f].
+ * cap_out == eaof_orb_max_keypoints(). */
+int eaof_orb_device_results(eaof_orb* ctx, const eaof_kp** d_kps, const uint8_t** d_desc, const int** d_counts,
+                            int* cap_out);
+/* Copies the last batch's results to host buffers laid out as in eaof_orb_extract_batch. */
+int eaof_orb_fetch_results(eaof_orb* ctx, int n_frames, eaof_kp* kps, uint8_t* desc, int cap, int* n_out);
+
+/* mvImagePyramid[level] of frame `frame` of the last call (include/ORBextractor.h:85): copies the inner
+ * width x height image (with_border = 0) or the (w+38)x(h+38) bordered buffer to host memory. */
+int eaof_orb_pyramid_level(eaof_orb* ctx, int frame, int level, int with_border, uint8_t* dst, size_t dst_stride);
+
+/* ---- stage dumps for parity tests (debug; synchronous) ------------------------------------------------- */
+/* Blurred inner level (input of computeOrbDescriptor, src/ORBextractor.cc:1085-1086). */
+int eaof_orb_debug_blurred_level(eaof_orb* ctx, int frame, int level, uint8_t* dst, size_t dst_stride);
+/* FAST candidates of (frame, level) before DistributeOctTree, unordered: triples (x, y, score) in detection-window
+ * coordinates (src/ORBextractor.cc:822-824).  Returns the count through *n_out (may exceed cap). */
+int eaof_orb_debug_candidates(eaof_orb* ctx, int frame, int level, int* xys, int cap, int* n_out);
+/* Runs the device restatement of glibc sinf/cosf (used by the descriptor rotation) over every `stride`-th float in
+ * [0, hi] and compares with this host's libm; returns the number of mismatching results (0 expected), -1 on error. */
+long eaof_debug_sincosf_mismatches(float hi, uint32_t stride);
+/* Per-stage GPU time of the last batched call in milliseconds (CUDA events on the handle's stream):
+ * [0] pyramid, [1] FAST, [2] octree, [3] blur, [4] angle+descriptor, [5] total.  Requires
+ * eaof_orb_set_profiling(ctx, 1) before the call. */
+int eaof_orb_set_profiling(eaof_orb* ctx, int on);
+int eaof_orb_stage_times(eaof_orb* ctx, float* ms6);
+/* Number of kernel launches the last batched call issued. */
+int eaof_orb_last_launch_count(const eaof_orb* ctx);
+/* The handle's cudaStream_t, so callers can record their own CUDA events around batched calls. */
+void* eaof_orb_stream(eaof_orb* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAOF_ORB_H */

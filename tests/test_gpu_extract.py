@@ -1,0 +1,123 @@
+"""GPU parity tests proper: the CUDA path, through the C ABI, against the oracle — bit-exact at every stage.
+
+Stage order follows ORBextractor::operator() (src/ORBextractor.cc:1043-1105): pyramid -> per-cell FAST candidates ->
+DistributeOctTree -> IC_Angle -> GaussianBlur -> rBRIEF.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _sorted_rows(a):
+    a = np.asarray(a)
+    return a[np.lexsort((a[:, 2], a[:, 0], a[:, 1]))] if len(a) else a
+
+
+@pytest.fixture(scope="module")
+def ex640():
+    import eaof
+    e = eaof.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480, max_batch=8)
+    yield e
+    e.close()
+
+
+def test_tables_match_reference(ex640):
+    from oracle import pyoracle as po
+    t = po.RefExtractor().tables()
+    assert np.array_equal(ex640.GetScaleFactors(), t["scale"])
+    assert np.array_equal(ex640.GetInverseScaleFactors(), t["inv_scale"])
+    assert np.array_equal(ex640.GetScaleSigmaSquares(), t["sigma2"])
+    assert np.array_equal(ex640.GetInverseScaleSigmaSquares(), t["inv_sigma2"])
+    assert np.array_equal(ex640.features_per_level(), t["quotas"])
+
+
+def test_stages_match_oracle(ex640, frames640):
+    from oracle import pyoracle as po
+    for fi in range(2):
+        img = frames640[fi]
+        kps, desc = ex640(img)
+        okps, odesc, pl, bl, cl = po.o_extract(img, dumps=True)
+        for l in range(8):
+            assert np.array_equal(ex640.pyramid_level(l, with_border=True), pl[l]), f"pyramid level {l}"
+            assert np.array_equal(ex640.blurred_level(l), bl[l]), f"blur level {l}"
+            assert np.array_equal(_sorted_rows(ex640.candidates(l)), _sorted_rows(cl[l])), f"FAST candidates level {l}"
+        assert len(kps) == len(okps)
+        for field in ("x", "y", "octave", "response", "size", "angle"):
+            assert np.array_equal(kps[field], okps[field]), field
+        assert np.array_equal(desc, odesc)
+
+
+def test_end_to_end_matches_reference_binary(ex640, frames640):
+    """oracle/_ref = the reference's own ORBextractor.cc compiled unmodified."""
+    from oracle import pyoracle as po
+    ref = po.RefExtractor()
+    res = ex640.extract_batch(frames640)
+    for fi in range(len(frames640)):
+        rk, rd = ref.extract(frames640[fi])
+        k, d = res[fi]
+        assert len(k) == len(rk)
+        assert np.array_equal(k, rk)
+        assert np.array_equal(d, rd)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_blur_modes(frames640, mode):
+    import eaof
+    from oracle import pyoracle as po
+    e = eaof.ORBextractor(width=640, height=480, blur_mode=mode)
+    k, d = e(frames640[0])
+    ok, od = po.o_extract(frames640[0], blur_mode=mode)
+    assert np.array_equal(k, ok) and np.array_equal(d, od)
+    e.close()
+
+
+def test_adversarial_frames():
+    import eaof
+    from eaof import synth
+    from oracle import pyoracle as po
+    e = eaof.ORBextractor(width=320, height=240, max_batch=4)
+    ref = po.RefExtractor()
+    for name, img in synth.adversarial_frames(320, 240).items():
+        k, d = e(img)
+        rk, rd = ref.extract(img)
+        assert len(k) == len(rk), name
+        assert np.array_equal(k, rk), name
+        assert np.array_equal(d, rd), name
+    e.close()
+
+
+@pytest.mark.parametrize("shape,nf", [((848, 480), 1200), ((1920, 1080), 4000), ((100, 80), 300), ((64, 64), 100)])
+def test_other_config_sizes(shape, nf):
+    import eaof
+    from eaof import synth
+    from oracle import pyoracle as po
+    w, h = shape
+    tex = synth.base_texture(w, h, seed=1234 + w)
+    fr = synth.make_frames(2, w, h, tex=tex)
+    e = eaof.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=2)
+    ref = po.RefExtractor(nf, 1.2, 8, 20, 7)
+    res = e.extract_batch(fr)
+    for fi in range(2):
+        rk, rd = ref.extract(fr[fi])
+        k, d = res[fi]
+        assert len(k) == len(rk)
+        assert np.array_equal(k, rk) and np.array_equal(d, rd)
+    e.close()
+
+
+def test_batch_equals_single(ex640, frames640):
+    res = ex640.extract_batch(frames640)
+    for fi in (0, 3, 5):
+        k, d = ex640(frames640[fi])
+        assert np.array_equal(k, res[fi][0]) and np.array_equal(d, res[fi][1])
+
+
+def test_device_sincosf_sweep():
+    """The device restatement of glibc sinf/cosf against the host's libm, all floats in [0, 6.4] (strided)."""
+    import eaof
+    import ctypes as C
+    L = eaof.lib()
+    L.eaof_debug_sincosf_mismatches.restype = C.c_long
+    L.eaof_debug_sincosf_mismatches.argtypes = [C.c_float, C.c_uint32]
+    assert L.eaof_debug_sincosf_mismatches(6.4, 7) == 0
