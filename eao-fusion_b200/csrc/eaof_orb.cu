@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -355,7 +356,16 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
         eaof_orb_destroy(c);
         return EAOF_ERR_UNSUPPORTED;
     }
-    CKD(cudaFuncSetAttribute(eaof::k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->octSmem));
+    {
+        // the attribute is per function, not per handle: only ever raise it (handles with different nfeatures coexist)
+        static std::mutex mu;
+        static size_t maxSet[64] = {};
+        std::lock_guard<std::mutex> lk(mu);
+        if (device < 64 && c->octSmem > maxSet[device]) {
+            CKD(cudaFuncSetAttribute(eaof::k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->octSmem));
+            maxSet[device] = c->octSmem;
+        }
+    }
 #undef CKD
     *out = c;
     return EAOF_OK;

@@ -100,31 +100,30 @@ __global__ void __launch_bounds__(256) k_resize(uint8_t* __restrict__ pyr, const
 
 // max over the 16 contiguous 9-arcs of min(ring - v) (brighter) and of min(v - ring) (darker).
 // corner at threshold t  <=>  result > t ;  OpenCV's cornerScore<16> == result - 1 for a corner.
+// Both polarities are evaluated at once on packed s16x2 lanes (low half d = ring - v, high half -d) with the
+// DPX min/max instructions; sliding minima: m2 covers 2 ring pixels, m4 covers 4, m9 = min3(m4[k], m4[k+4], w[k+8]).
+// NOTE: a plain-int formulation of the same min/max tree (scalar min()/max() on int arrays) is MISCOMPILED by
+// nvcc 12.9 for sm_100a (wrong VIMNMX3 fusion; 97% of results wrong on a B200, identical source is right on the
+// host) — scratch repro kept as tests/cuda/arc_best_miscompile.cu; tests/test_gpu_extract.py::test_stages pins this.
 __device__ __forceinline__ int arc_best(const uint8_t* p) {
     const int v = p[0];
-    int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = (int)p[RING_OFF(k, FAST_TP)] - v;
-    int mn2[16], mx2[16];
+    unsigned w[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        mn2[k] = min(d[k], d[(k + 1) & 15]);
-        mx2[k] = max(d[k], d[(k + 1) & 15]);
+        const int d = (int)p[RING_OFF(k, FAST_TP)] - v;
+        w[k] = ((unsigned)d & 0xffffu) | ((unsigned)(-d) << 16);
     }
-    int mn4[16], mx4[16];
+    unsigned m2[16], m4[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
-        mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
-    }
-    int best = -256;
+    for (int k = 0; k < 16; ++k) m2[k] = __vmins2(w[k], w[(k + 1) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(mn9, -mx9));
-    }
-    return best;
+    for (int k = 0; k < 16; ++k) m4[k] = __vmins2(m2[k], m2[(k + 2) & 15]);
+    unsigned best = 0x80008000u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        best = __vmaxs2(best, __vimin3_s16x2(m4[k], m4[(k + 4) & 15], w[(k + 8) & 15]));
+    const int lo = (short)(best & 0xffff), hi = (short)(best >> 16);
+    return lo > hi ? lo : hi;
 }
 
 __device__ __forceinline__ int fast_cls(int a, int lo, int hi) { return (a < lo ? 1 : 0) | (a > hi ? 2 : 0); }
@@ -211,6 +210,10 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ pyr, c
     }
     __syncthreads();
 
+#ifdef EAOF_DEBUG_FAST
+    for (int i = tid; i < 66 * FAST_TP; i += 256) g_dbgTile[i] = tile[i + (i / FAST_TP) * 0 + 0];
+    for (int i = tid; i < 4096; i += 256) g_dbgBm[i] = Bm[i];
+#endif
     // C: threshold + 8-neighbour NMS inside the cell; retry with minThFAST if nothing survives (:808-816)
     for (int pass = 0; pass < 2; ++pass) {
         const int th = pass == 0 ? g.iniTh : g.minTh;

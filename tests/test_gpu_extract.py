@@ -87,7 +87,16 @@ def test_adversarial_frames():
     e.close()
 
 
-@pytest.mark.parametrize("shape,nf", [((848, 480), 1200), ((1920, 1080), 4000), ((100, 80), 300), ((64, 64), 100)])
+def test_shapes_the_reference_cannot_handle_are_rejected():
+    """100x80 with 8 levels gives a 0-row detection window at level 5: the reference divides by zero there
+    (src/ORBextractor.cc:543), so the C ABI refuses the shape instead of inventing a result."""
+    import eaof
+    with pytest.raises(eaof.EaofError, match="-3"):
+        eaof.ORBextractor(300, 1.2, 8, 20, 7, width=100, height=80)
+
+
+@pytest.mark.parametrize("shape,nf", [((848, 480), 1200), ((1920, 1080), 4000), ((160, 120), 300), ((200, 150), 50),
+                                      ((752, 480), 2000)])
 def test_other_config_sizes(shape, nf):
     import eaof
     from eaof import synth
@@ -104,6 +113,22 @@ def test_other_config_sizes(shape, nf):
         assert len(k) == len(rk)
         assert np.array_equal(k, rk) and np.array_equal(d, rd)
     e.close()
+
+
+def test_other_pyramid_parameters():
+    import eaof
+    from eaof import synth
+    from oracle import pyoracle as po
+    tex = synth.base_texture(320, 240, seed=77)
+    fr = synth.make_frames(1, 320, 240, tex=tex)
+    for nf, sf, nl, ini, mn in ((500, 1.5, 4, 20, 7), (800, 2.0, 3, 30, 10), (300, 1.1, 6, 12, 5), (40, 1.2, 8, 20, 7)):
+        e = eaof.ORBextractor(nf, sf, nl, ini, mn, width=320, height=240)
+        ref = po.RefExtractor(nf, sf, nl, ini, mn)
+        k, d = e(fr[0])
+        rk, rd = ref.extract(fr[0])
+        assert len(k) == len(rk), (nf, sf, nl)
+        assert np.array_equal(k, rk) and np.array_equal(d, rd), (nf, sf, nl)
+        e.close()
 
 
 def test_batch_equals_single(ex640, frames640):
