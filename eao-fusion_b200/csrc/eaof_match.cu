@@ -1,0 +1,930 @@
+// Hamming matcher of libeaof_orb.so (include/eaof_match.h): the descriptor search loops of the reference's
+// ORBmatcher (src/ORBmatcher.cc) as two-phase GPU algorithms.
+//
+//   phase 1 (dense, parallel over every query of every pair): all Hamming distances of a query against its
+//            candidate set on the INT pipe (8 x XOR + POPC per pair, ORBmatcher::DescriptorDistance :1649-1665),
+//            keeping only what the acceptance rule can ever look at: the candidates with dist < D ("near list", in
+//            candidate order) for the ratio-test loops, the 4 best candidates for the best-only projection loop.
+//   phase 2 (one warp per pair, queries in the reference's order): resolves the greedy "skip targets that are
+//            already matched" exclusion (:209-210, :576, :1405-1407), applies TH_LOW/TH_HIGH and the fp32 ratio
+//            test, fills the rotation histogram, runs ComputeThreeMaxima (:1603-1644) and prunes.
+//
+// Why the near list is exact: a match needs best <= TH and (float)best < ratio*(float)second.  With
+// s_min = min{s : (float)TH < ratio*(float)s} every second-best >= s_min passes the ratio test for every admissible
+// best, so only candidates with dist < D = max(s_min, TH+1) can influence the outcome; if a query has more such
+// candidates than the list holds, phase 2 re-scans that query exactly.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/eaof_match.h"
+
+extern "C" int eaof_internal_fail(int code, const char* msg);  // sets eaof_last_error (eaof_orb.cu)
+
+namespace {
+
+int mfail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    return eaof_internal_fail(code, buf);
+}
+#define MCK(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return mfail(EAOF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int GRID_COLS = 64, GRID_ROWS = 48, GRID_CELLS = GRID_COLS * GRID_ROWS;  // include/Frame.h:89-90
+constexpr int NEAR_K = 7;                                                          // near-list entries per query
+constexpr int TOP_K = 4;                                                           // projection: best candidates kept
+
+__device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) {
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d += __popc(a[i] ^ b[i]);
+    return d;
+}
+
+__global__ void k_hamming_pairs(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* pa = reinterpret_cast<const uint4*>(a + 32 * (size_t)i);
+    const uint4* pb = reinterpret_cast<const uint4*>(b + 32 * (size_t)i);
+    const uint4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+    out[i] = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+             __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SearchByBoW
+struct BowSeg { int qOff, qCnt, tOff, tCnt; };  // one vocabulary node present in both feature vectors
+
+struct BowArgs {
+    // per pair p: descriptors of the query/target blocks, optional CSR index lists (NULL = identity)
+    const uint8_t* desc;      // base
+    const float* angle;       // base, same indexing as desc rows
+    const int* counts;        // per block (brute force) or NULL
+    const int* pairQ;         // block index per pair (device) or NULL (=> host API: block 0 = Q, block 1 = T)
+    const int* pairT;
+    int blockStride;          // rows per block
+    const uint8_t* validQ;    // [pair][stride] or NULL
+    const uint8_t* validT;
+    const int* idxQ;          // [pair][stride] feature index lists (NULL = identity)
+    const int* idxT;
+    const BowSeg* segs;       // segments of all pairs (NULL = one segment covering everything)
+    const int* segStart;      // [pair+1] (NULL with segs)
+    int nQhost, nThost;       // used when counts == NULL
+    int stride;               // per-pair stride of the workspace arrays (= max_features)
+    int mode;
+    int thEff;                // accept best <= thEff
+    int D;                    // near-list threshold
+    float ratio;
+    int checkOri;
+};
+
+#define BOW_QT 128  // queries per CTA
+#define BOW_TT 64   // targets staged per step
+
+// phase 1: blockIdx.y = pair, blockIdx.x = tile of BOW_QT list positions inside segment `seg` (brute force: seg 0)
+__global__ void __launch_bounds__(BOW_QT) k_bow_dense(BowArgs A, const int2* __restrict__ tiles, uint32_t* __restrict__ nearBuf) {
+    __shared__ __align__(16) uint32_t sT[BOW_TT][8];
+    __shared__ int sIdx[BOW_TT];
+    int pair, qBeg, qEnd, tBeg, tEnd;
+    if (tiles) {  // host API: explicit (segment, first list position) tiles of pair 0
+        const int2 t = tiles[blockIdx.x];
+        pair = 0;
+        const BowSeg s = A.segs[t.x];
+        qBeg = t.y;
+        qEnd = min(s.qOff + s.qCnt, t.y + BOW_QT);
+        tBeg = s.tOff;
+        tEnd = s.tOff + s.tCnt;
+    } else {
+        pair = blockIdx.y;
+        const int nq = A.counts[A.pairQ[pair]], nt = A.counts[A.pairT[pair]];
+        qBeg = blockIdx.x * BOW_QT;
+        if (qBeg >= nq) return;
+        qEnd = min(nq, qBeg + BOW_QT);
+        tBeg = 0;
+        tEnd = nt;
+    }
+    const int bq = A.pairQ ? A.pairQ[pair] : 0, bt = A.pairT ? A.pairT[pair] : 1;
+    const uint8_t* dQ = A.desc + (size_t)bq * A.blockStride * 32;
+    const uint8_t* dT = A.desc + (size_t)bt * A.blockStride * 32;
+    const int* idxQ = A.idxQ ? A.idxQ + (size_t)pair * A.stride : nullptr;
+    const int* idxT = A.idxT ? A.idxT + (size_t)pair * A.stride : nullptr;
+
+    const int qpos = qBeg + threadIdx.x;
+    const bool active = qpos < qEnd;
+    const int q = active ? (idxQ ? idxQ[qpos] : qpos) : 0;
+    uint32_t qd[8];
+    {
+        const uint4* p = reinterpret_cast<const uint4*>(dQ + 32 * (size_t)q);
+        const uint4 a = p[0], b = p[1];
+        qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+    }
+    uint32_t near[NEAR_K];
+#pragma unroll
+    for (int i = 0; i < NEAR_K; ++i) near[i] = 0xffffffffu;
+    int cnt = 0;
+    for (int t0 = tBeg; t0 < tEnd; t0 += BOW_TT) {
+        const int tt = min(BOW_TT, tEnd - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tt * 2; i += BOW_QT) {
+            const int j = i >> 1, h = i & 1;
+            const int t = idxT ? idxT[t0 + j] : t0 + j;
+            reinterpret_cast<uint4*>(&sT[j][0])[h] = reinterpret_cast<const uint4*>(dT + 32 * (size_t)t)[h];
+            if (h == 0) sIdx[j] = t;
+        }
+        __syncthreads();
+        if (active) {
+            for (int j = 0; j < tt; ++j) {
+                const int d = hamming256(qd, sT[j]);
+                if (d < A.D) {
+                    if (cnt < NEAR_K) {
+                        const uint32_t e = (uint32_t)sIdx[j] | ((uint32_t)d << 16);
+#pragma unroll
+                        for (int i = 0; i < NEAR_K; ++i) if (i == cnt) near[i] = e;
+                    }
+                    ++cnt;
+                }
+            }
+        }
+    }
+    if (active) {
+        uint32_t* o = nearBuf + ((size_t)pair * A.stride + q) * 8;
+        reinterpret_cast<uint4*>(o)[0] = make_uint4(near[0], near[1], near[2], near[3]);
+        reinterpret_cast<uint4*>(o)[1] = make_uint4(near[4], near[5], near[6], (uint32_t)cnt);
+    }
+}
+
+// ComputeThreeMaxima, src/ORBmatcher.cc:1603-1644
+__device__ void three_maxima(const int* hist, int& i1, int& i2, int& i3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    i1 = i2 = i3 = -1;
+    for (int i = 0; i < EAOF_HISTO_LENGTH; ++i) {
+        const int s = hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+        else if (s > max3) { max3 = s; i3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3 = -1; }
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2, float factor) {
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == EAOF_HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// phase 2: one warp per pair
+__global__ void __launch_bounds__(32) k_bow_resolve(BowArgs A, const uint32_t* __restrict__ nearBuf,
+                                                    uint32_t* __restrict__ accBuf, int* __restrict__ matchOut,
+                                                    int* __restrict__ distOut, int* __restrict__ nMatches) {
+    extern __shared__ uint32_t smem[];  // matched-target bitmap [ (stride+31)/32 ]
+    __shared__ int hist[EAOF_HISTO_LENGTH];
+    const int pair = blockIdx.x, lane = threadIdx.x;
+    const int bq = A.pairQ ? A.pairQ[pair] : 0, bt = A.pairT ? A.pairT[pair] : 1;
+    const int nq = A.counts ? A.counts[bq] : A.nQhost, nt = A.counts ? A.counts[bt] : A.nThost;
+    const uint8_t* dQ = A.desc + (size_t)bq * A.blockStride * 32;
+    const uint8_t* dT = A.desc + (size_t)bt * A.blockStride * 32;
+    const float* angQ = A.angle + (size_t)bq * A.blockStride;
+    const float* angT = A.angle + (size_t)bt * A.blockStride;
+    const int* idxQ = A.idxQ ? A.idxQ + (size_t)pair * A.stride : nullptr;
+    const int* idxT = A.idxT ? A.idxT + (size_t)pair * A.stride : nullptr;
+    const uint8_t* validQ = A.validQ ? A.validQ + (size_t)pair * A.stride : nullptr;
+    const uint8_t* validT = (A.validT && A.mode == EAOF_BOW_KF_KF) ? A.validT + (size_t)pair * A.stride : nullptr;
+    const int nOut = A.mode == EAOF_BOW_KF_FRAME ? nt : nq;
+    int* mOut = matchOut + (size_t)pair * A.stride;
+    int* dOut = distOut ? distOut + (size_t)pair * A.stride : nullptr;
+    uint32_t* acc = accBuf + (size_t)pair * A.stride;
+    const uint32_t* nearP = nearBuf + (size_t)pair * A.stride * 8;
+
+    const int words = (A.stride + 31) >> 5;
+    for (int i = lane; i < words; i += 32) smem[i] = 0;
+    for (int i = lane; i < EAOF_HISTO_LENGTH; i += 32) hist[i] = 0;
+    for (int i = lane; i < nOut; i += 32) { mOut[i] = -1; if (dOut) dOut[i] = -1; }
+    __syncwarp();
+    if (validT)  // targets without a good map point are never candidates (:573-580)
+        for (int i = lane; i < nt; i += 32) if (!validT[i]) atomicOr(&smem[i >> 5], 1u << (i & 31));
+    __syncwarp();
+
+    const float factor = 1.0f / EAOF_HISTO_LENGTH;  // :172, :541
+    int nAcc = 0;
+    const int nSeg = A.segs ? (A.segStart[pair + 1] - A.segStart[pair]) : 1;
+    for (int si = 0; si < nSeg; ++si) {
+        BowSeg s;
+        if (A.segs) s = A.segs[A.segStart[pair] + si];
+        else s = BowSeg{0, nq, 0, nt};
+        for (int q0 = s.qOff; q0 < s.qOff + s.qCnt; q0 += 32) {
+            const int myPos = q0 + lane;
+            const bool have = myPos < s.qOff + s.qCnt;
+            const int myQ = have ? (idxQ ? idxQ[myPos] : myPos) : 0;
+            uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
+            bool ok = have && (!validQ || validQ[myQ]);
+            if (ok) {
+                const uint4* p = reinterpret_cast<const uint4*>(nearP + (size_t)myQ * 8);
+                w0 = p[0];
+                w1 = p[1];
+            }
+            const int myCnt = ok ? (int)w1.w : 0;
+            const unsigned todo = __ballot_sync(0xffffffffu, myCnt > 0);
+            unsigned rem = todo;
+            while (rem) {  // queries with at least one near candidate, in list order
+                const int j = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int q = __shfl_sync(0xffffffffu, myQ, j);
+                const int cnt = __shfl_sync(0xffffffffu, myCnt, j);
+                int best1 = 256, best2 = 256, bestIdx = -1;
+                if (cnt <= NEAR_K) {
+                    const uint32_t e[NEAR_K] = {__shfl_sync(0xffffffffu, w0.x, j), __shfl_sync(0xffffffffu, w0.y, j),
+                                                __shfl_sync(0xffffffffu, w0.z, j), __shfl_sync(0xffffffffu, w0.w, j),
+                                                __shfl_sync(0xffffffffu, w1.x, j), __shfl_sync(0xffffffffu, w1.y, j),
+                                                __shfl_sync(0xffffffffu, w1.z, j)};
+#pragma unroll
+                    for (int k = 0; k < NEAR_K; ++k) {
+                        if (k < cnt) {
+                            const int t = e[k] & 0xffff, d = (int)(e[k] >> 16);
+                            if (!((smem[t >> 5] >> (t & 31)) & 1u)) {
+                                if (d < best1) { best2 = best1; best1 = d; bestIdx = t; }
+                                else if (d < best2) best2 = d;
+                            }
+                        }
+                    }
+                    // an unseen second-best is >= D, which passes the ratio test for every best <= thEff
+                } else {
+                    // exact re-scan of this query over the whole node (rare: > NEAR_K near candidates)
+                    uint32_t qd[8];
+                    {
+                        const uint4* p = reinterpret_cast<const uint4*>(dQ + 32 * (size_t)q);
+                        const uint4 a = p[0], b = p[1];
+                        qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+                    }
+                    int a1 = 256, a2 = 256, aPos = 0x7fffffff, aIdx = -1;  // this lane's two smallest, first position of the min
+                    for (int tp = s.tOff + lane; tp < s.tOff + s.tCnt; tp += 32) {
+                        const int t = idxT ? idxT[tp] : tp;
+                        if ((smem[t >> 5] >> (t & 31)) & 1u) continue;
+                        uint32_t td[8];
+                        const uint4* p = reinterpret_cast<const uint4*>(dT + 32 * (size_t)t);
+                        const uint4 a = p[0], b = p[1];
+                        td[0] = a.x; td[1] = a.y; td[2] = a.z; td[3] = a.w; td[4] = b.x; td[5] = b.y; td[6] = b.z; td[7] = b.w;
+                        const int d = hamming256(qd, td);
+                        if (d < a1) { a2 = a1; a1 = d; aPos = tp; aIdx = t; }
+                        else if (d < a2) a2 = d;
+                    }
+                    // warp merge: global min by (dist, position), second = 2nd order statistic of the multiset
+                    int g1 = a1, gPos = aPos, gIdx = aIdx, gLane = lane;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const int o1 = __shfl_xor_sync(0xffffffffu, g1, o), oP = __shfl_xor_sync(0xffffffffu, gPos, o);
+                        const int oI = __shfl_xor_sync(0xffffffffu, gIdx, o), oL = __shfl_xor_sync(0xffffffffu, gLane, o);
+                        if (o1 < g1 || (o1 == g1 && oP < gPos)) { g1 = o1; gPos = oP; gIdx = oI; gLane = oL; }
+                    }
+                    int sec = (lane == gLane) ? a2 : a1;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sec = min(sec, __shfl_xor_sync(0xffffffffu, sec, o));
+                    best1 = g1; bestIdx = gIdx; best2 = sec;
+                }
+                if (bestIdx >= 0 && best1 <= A.thEff && (float)best1 < __fmul_rn(A.ratio, (float)best2)) {
+                    const int outIdx = A.mode == EAOF_BOW_KF_FRAME ? bestIdx : q;
+                    int bin = 0;
+                    if (A.checkOri) bin = rot_bin(angQ[q], angT[bestIdx], factor);
+                    if (lane == 0) {
+                        smem[bestIdx >> 5] |= 1u << (bestIdx & 31);
+                        mOut[outIdx] = A.mode == EAOF_BOW_KF_FRAME ? q : bestIdx;
+                        if (dOut) dOut[outIdx] = best1;
+                        acc[nAcc] = (uint32_t)outIdx | ((uint32_t)bin << 24);
+                        if (A.checkOri) hist[bin]++;
+                    }
+                    ++nAcc;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    __syncwarp();
+    int removed = 0;
+    if (A.checkOri) {
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        for (int k = lane; k < nAcc; k += 32) {
+            const uint32_t a = acc[k];
+            const int bin = (int)(a >> 24);
+            if (bin != i1 && bin != i2 && bin != i3) {
+                mOut[a & 0xffffff] = -1;
+                if (dOut) dOut[a & 0xffffff] = -1;
+                ++removed;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    }
+    if (lane == 0) nMatches[pair] = nAcc - removed;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SearchByProjection(Cur, Last)
+struct ProjArgs {
+    // Cur side, [pair][stride]
+    const float* cx; const float* cy; const int* coct; const float* cangle; const float* curight; const uint8_t* ctaken;
+    const int* nC;           // [pair]
+    // Last side, [pair][stride]
+    const float* lu; const float* lv; const float* linvz; const int* loct; const float* langle;
+    const uint8_t* lvalid; const uint8_t* lobs;
+    const int* nL;           // [pair]
+    const uint8_t* desc;     // descriptor base; rows of pair p: Cur at cRow[p], Last at lRow[p]
+    const int* cRow; const int* lRow;
+    int stride;
+    float minX, maxX, minY, maxY, invW, invH;
+    float scale[EAOF_MAX_LEVELS];
+    float th, mbf;
+    int searchMode, checkOri;
+};
+
+// Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:599-614,751-761): one CTA per pair builds the CSR grid of
+// the Cur frame; cell lists are sorted ascending so they equal the reference's push_back order.
+__global__ void __launch_bounds__(256) k_build_grid(ProjArgs A, int* __restrict__ cellStart, int* __restrict__ cellIdx) {
+    __shared__ int cnt[GRID_CELLS];
+    __shared__ int warpTot[8];
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    const int n = A.nC[pair];
+    const float* x = A.cx + (size_t)pair * A.stride;
+    const float* y = A.cy + (size_t)pair * A.stride;
+    int* cs = cellStart + (size_t)pair * (GRID_CELLS + 1);
+    int* ci = cellIdx + (size_t)pair * A.stride;
+    for (int i = tid; i < GRID_CELLS; i += 256) cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(x[i], A.minX), A.invW));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(y[i], A.minY), A.invH));
+        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) atomicAdd(&cnt[px * GRID_ROWS + py], 1);
+    }
+    __syncthreads();
+    // exclusive scan of 3072 counts: 12 per thread
+    int local[12], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { local[k] = cnt[tid * 12 + k]; sum += local[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+    if ((tid & 31) == 31) warpTot[tid >> 5] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (tid >> 5); ++w) base += warpTot[w];
+    int run = base + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { cs[tid * 12 + k] = run; cnt[tid * 12 + k] = run; run += local[k]; }
+    if (tid == 255) cs[GRID_CELLS] = run;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(x[i], A.minX), A.invW));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(y[i], A.minY), A.invH));
+        if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) ci[atomicAdd(&cnt[px * GRID_ROWS + py], 1)] = i;
+    }
+    __syncthreads();
+    for (int c = tid; c < GRID_CELLS; c += 256) {  // ascending feature index inside each cell
+        const int b = cs[c], e = cnt[c];
+        for (int i = b + 1; i < e; ++i) {
+            const int v = ci[i];
+            int j = i - 1;
+            while (j >= b && ci[j] > v) { ci[j + 1] = ci[j]; --j; }
+            ci[j + 1] = v;
+        }
+    }
+}
+
+// Walks Frame::GetFeaturesInArea (src/Frame.cc:696-749) for one query and calls f(k) for every candidate, in the
+// reference's order (ix, iy, insertion order).  Returns false if the query is skipped before the search.
+template <typename F>
+__device__ __forceinline__ void for_each_candidate(const ProjArgs& A, const int* cs, const int* ci, const float* cx,
+                                                    const float* cy, const int* coct, float u, float v, float r,
+                                                    int minLevel, int maxLevel, F f) {
+    const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, A.minX), r), A.invW)));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, A.minX), r), A.invW)));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, A.minY), r), A.invH)));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, A.minY), r), A.invH)));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+        for (int iy = nMinCellY; iy <= nMaxCellY; ++iy) {
+            const int c = ix * GRID_ROWS + iy;
+            for (int j = cs[c]; j < cs[c + 1]; ++j) {
+                const int k = ci[j];
+                if (bCheckLevels) {
+                    if (coct[k] < minLevel) continue;
+                    if (maxLevel >= 0 && coct[k] > maxLevel) continue;
+                }
+                const float dx = __fsub_rn(cx[k], u), dy = __fsub_rn(cy[k], v);
+                if (fabsf(dx) < r && fabsf(dy) < r) f(k);
+            }
+        }
+}
+
+__device__ __forceinline__ void level_window(int searchMode, int oct, int& minLevel, int& maxLevel) {
+    if (searchMode == 1) { minLevel = oct; maxLevel = -1; }        // bForward  :1387
+    else if (searchMode == 2) { minLevel = 0; maxLevel = oct; }    // bBackward :1389
+    else { minLevel = oct - 1; maxLevel = oct + 1; }               // :1391
+}
+
+// phase 1: one thread per Last feature: TOP_K best candidates (dist asc, candidate order asc) + candidate count
+__global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __restrict__ cellStart,
+                                                    const int* __restrict__ cellIdx, uint32_t* __restrict__ topBuf) {
+    const int pair = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.nL[pair]) return;
+    const size_t po = (size_t)pair * A.stride;
+    uint32_t* o = topBuf + (po + i) * 8;
+    int count = -1;
+    uint32_t top[TOP_K];
+#pragma unroll
+    for (int k = 0; k < TOP_K; ++k) top[k] = 0xffffffffu;
+    const float invz = A.linvz ? A.linvz[po + i] : 1.f;
+    const float u = A.lu[po + i], v = A.lv[po + i];
+    const bool ok = (!A.lvalid || A.lvalid[po + i]) && !(invz < 0) && !(u < A.minX || u > A.maxX) && !(v < A.minY || v > A.maxY);
+    if (ok) {
+        const int oct = A.loct[po + i];
+        const float r = __fmul_rn(A.th, A.scale[oct]);
+        int minLevel, maxLevel;
+        level_window(A.searchMode, oct, minLevel, maxLevel);
+        uint32_t qd[8];
+        {
+            const uint4* p = reinterpret_cast<const uint4*>(A.desc + 32 * ((size_t)A.lRow[pair] + i));
+            const uint4 a = p[0], b = p[1];
+            qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+        }
+        const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
+        const float* cur = A.curight ? A.curight + po : nullptr;
+        const float ur = __fsub_rn(u, __fmul_rn(A.mbf, invz));
+        count = 0;
+        for_each_candidate(A, cellStart + (size_t)pair * (GRID_CELLS + 1), cellIdx + po, A.cx + po, A.cy + po, A.coct + po,
+                           u, v, r, minLevel, maxLevel, [&](int k) {
+            if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) return;  // :1409-1415
+            uint32_t td[8];
+            const uint4* p = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
+            const uint4 a = p[0], b = p[1];
+            td[0] = a.x; td[1] = a.y; td[2] = a.z; td[3] = a.w; td[4] = b.x; td[5] = b.y; td[6] = b.z; td[7] = b.w;
+            const uint32_t d = (uint32_t)hamming256(qd, td);
+            uint32_t e = (d << 16) | (uint32_t)k;
+            // insertion into the sorted top-K by distance only; ties keep the earlier arrival in front
+            bool shifting = false;  // once inserted, everything behind moves down one slot
+#pragma unroll
+            for (int s = 0; s < TOP_K; ++s) {
+                if (shifting || (e >> 16) < (top[s] >> 16)) { const uint32_t t = top[s]; top[s] = e; e = t; shifting = true; }
+            }
+            ++count;
+        });
+    }
+    reinterpret_cast<uint4*>(o)[0] = make_uint4(top[0], top[1], top[2], top[3]);
+    reinterpret_cast<uint4*>(o)[1] = make_uint4(0, 0, 0, (uint32_t)count);
+}
+
+// phase 2: one warp per pair, Last features in index order
+__global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __restrict__ cellStart,
+                                                     const int* __restrict__ cellIdx, const uint32_t* __restrict__ topBuf,
+                                                     uint32_t* __restrict__ accBuf, int* __restrict__ matchOut,
+                                                     int* __restrict__ distOut, int* __restrict__ nMatches) {
+    extern __shared__ uint32_t smem[];  // taken bitmap
+    __shared__ int hist[EAOF_HISTO_LENGTH];
+    const int pair = blockIdx.x, lane = threadIdx.x;
+    const size_t po = (size_t)pair * A.stride;
+    const int nC = A.nC[pair], nL = A.nL[pair];
+    int* mOut = matchOut + po;
+    int* dOut = distOut ? distOut + po : nullptr;
+    uint32_t* acc = accBuf + po;
+    const int words = (A.stride + 31) >> 5;
+    for (int i = lane; i < words; i += 32) smem[i] = 0;
+    for (int i = lane; i < EAOF_HISTO_LENGTH; i += 32) hist[i] = 0;
+    for (int i = lane; i < nC; i += 32) { mOut[i] = -1; if (dOut) dOut[i] = -1; }
+    __syncwarp();
+    if (A.ctaken)
+        for (int i = lane; i < nC; i += 32) if (A.ctaken[po + i]) atomicOr(&smem[i >> 5], 1u << (i & 31));
+    __syncwarp();
+    const float factor = EAOF_HISTO_LENGTH / 360.0f;  // :1337
+    int nAcc = 0;
+    for (int i0 = 0; i0 < nL; i0 += 32) {
+        const int mine = i0 + lane;
+        uint4 w0 = make_uint4(0, 0, 0, 0);
+        int myCnt = 0;
+        if (mine < nL) {
+            const uint4* p = reinterpret_cast<const uint4*>(topBuf + (po + mine) * 8);
+            w0 = p[0];
+            myCnt = (int)p[1].w;
+        }
+        unsigned rem = __ballot_sync(0xffffffffu, myCnt > 0);
+        while (rem) {
+            const int j = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const int i = i0 + j;
+            const int cnt = __shfl_sync(0xffffffffu, myCnt, j);
+            const uint32_t e[TOP_K] = {__shfl_sync(0xffffffffu, w0.x, j), __shfl_sync(0xffffffffu, w0.y, j),
+                                       __shfl_sync(0xffffffffu, w0.z, j), __shfl_sync(0xffffffffu, w0.w, j)};
+            int bestDist = 256, bestIdx = -1;
+#pragma unroll
+            for (int k = 0; k < TOP_K; ++k) {
+                if (bestIdx < 0 && k < cnt) {
+                    const int t = e[k] & 0xffff;
+                    if (!((smem[t >> 5] >> (t & 31)) & 1u)) { bestIdx = t; bestDist = (int)(e[k] >> 16); }
+                }
+            }
+            if (bestIdx < 0 && cnt > TOP_K) {
+                // every kept candidate is taken: exact sequential re-scan of this query (uniform across the warp)
+                const float u = A.lu[po + i], v = A.lv[po + i];
+                const float invz = A.linvz ? A.linvz[po + i] : 1.f;
+                const int oct = A.loct[po + i];
+                const float r = __fmul_rn(A.th, A.scale[oct]);
+                int minLevel, maxLevel;
+                level_window(A.searchMode, oct, minLevel, maxLevel);
+                uint32_t qd[8];
+                const uint4* p = reinterpret_cast<const uint4*>(A.desc + 32 * ((size_t)A.lRow[pair] + i));
+                const uint4 a = p[0], b = p[1];
+                qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+                const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
+                const float* cur = A.curight ? A.curight + po : nullptr;
+                const float ur = __fsub_rn(u, __fmul_rn(A.mbf, invz));
+                for_each_candidate(A, cellStart + (size_t)pair * (GRID_CELLS + 1), cellIdx + po, A.cx + po, A.cy + po,
+                                   A.coct + po, u, v, r, minLevel, maxLevel, [&](int k) {
+                    if ((smem[k >> 5] >> (k & 31)) & 1u) return;
+                    if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) return;
+                    uint32_t td[8];
+                    const uint4* pp = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
+                    const uint4 a2 = pp[0], b2 = pp[1];
+                    td[0] = a2.x; td[1] = a2.y; td[2] = a2.z; td[3] = a2.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
+                    const int d = hamming256(qd, td);
+                    if (d < bestDist) { bestDist = d; bestIdx = k; }
+                });
+            }
+            if (bestIdx >= 0 && bestDist <= EAOF_TH_HIGH) {  // :1428
+                int bin = 0;
+                if (A.checkOri) bin = rot_bin(A.langle[po + i], A.cangle[po + bestIdx], factor);
+                if (lane == 0) {
+                    mOut[bestIdx] = i;
+                    if (dOut) dOut[bestIdx] = bestDist;
+                    const bool obs = A.lobs ? A.lobs[po + i] != 0 : true;
+                    if (obs) smem[bestIdx >> 5] |= 1u << (bestIdx & 31);
+                    else smem[bestIdx >> 5] &= ~(1u << (bestIdx & 31));
+                    acc[nAcc] = (uint32_t)bestIdx | ((uint32_t)bin << 24);
+                    if (A.checkOri) hist[bin]++;
+                }
+                ++nAcc;
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    int removed = 0;
+    if (A.checkOri) {
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        for (int k = lane; k < nAcc; k += 32) {
+            const uint32_t a = acc[k];
+            const int bin = (int)(a >> 24);
+            if (bin != i1 && bin != i2 && bin != i3) {
+                mOut[a & 0xffffff] = -1;
+                if (dOut) dOut[a & 0xffffff] = -1;
+                ++removed;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    }
+    if (lane == 0) nMatches[pair] = nAcc - removed;
+}
+
+// Queries of the consecutive-frame path: Last keypoints of an extractor batch shifted by the known motion.
+__global__ void k_proj_prepare(const eaof_kp* __restrict__ kps, const int* __restrict__ counts, int cap,
+                               const int* __restrict__ lastFrame, const int* __restrict__ curFrame,
+                               const float* __restrict__ shiftX, const float* __restrict__ shiftY, int stride,
+                               float* cx, float* cy, int* coct, float* cangle, float* lu, float* lv, int* loct,
+                               float* langle, int* nC, int* nL, int* cRow, int* lRow) {
+    const int pair = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int fl = lastFrame[pair], fc = curFrame[pair];
+    const size_t po = (size_t)pair * stride;
+    if (i == 0) { nC[pair] = counts[fc]; nL[pair] = counts[fl]; cRow[pair] = fc * cap; lRow[pair] = fl * cap; }
+    if (i < counts[fc]) {
+        const eaof_kp k = kps[(size_t)fc * cap + i];
+        cx[po + i] = k.x; cy[po + i] = k.y; coct[po + i] = k.octave; cangle[po + i] = k.angle;
+    }
+    if (i < counts[fl]) {
+        const eaof_kp k = kps[(size_t)fl * cap + i];
+        lu[po + i] = __fadd_rn(k.x, shiftX[pair]); lv[po + i] = __fadd_rn(k.y, shiftY[pair]);
+        loct[po + i] = k.octave; langle[po + i] = k.angle;
+    }
+}
+
+}  // namespace
+
+struct eaof_matcher {
+    int device = 0, maxPairs = 0, maxFeat = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evDep = nullptr;
+    uint32_t *nearBuf = nullptr, *accBuf = nullptr;
+    int *cellStart = nullptr, *cellIdx = nullptr;
+    // SoA staging, [maxPairs][maxFeat]
+    float *cx = nullptr, *cy = nullptr, *cangle = nullptr, *curight = nullptr, *lu = nullptr, *lv = nullptr,
+          *linvz = nullptr, *langle = nullptr;
+    int *coct = nullptr, *loct = nullptr, *nC = nullptr, *nL = nullptr, *cRow = nullptr, *lRow = nullptr;
+    uint8_t *ctaken = nullptr, *lvalid = nullptr, *lobs = nullptr;
+    // single-pair host API staging
+    uint8_t* desc2 = nullptr;   // 2 blocks of maxFeat descriptors
+    float* angle2 = nullptr;    // 2 blocks of maxFeat angles
+    uint8_t *validQ = nullptr, *validT = nullptr;
+    int *idxQ = nullptr, *idxT = nullptr;
+    BowSeg* segs = nullptr;
+    int* segStart = nullptr;
+    int2* tiles = nullptr;
+    int *pairIdx = nullptr;     // [4][maxPairs] device copies of pair arrays / shifts
+    float* pairShift = nullptr; // [2][maxPairs]
+    int *outMatch = nullptr, *outDist = nullptr, *outN = nullptr;
+    long long lastDistances = 0;
+};
+
+namespace {
+template <typename T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(p, sizeof(T) * (n ? n : 1)); }
+
+int near_threshold(int thEff, float ratio) {
+    int s = 0;
+    while (s <= 256 && !((float)thEff < ratio * (float)s)) ++s;  // s_min
+    int D = s > thEff + 1 ? s : thEff + 1;
+    return D > 257 ? 257 : D;
+}
+}  // namespace
+
+extern "C" {
+
+int eaof_matcher_create(int device, int maxPairs, int maxFeat, eaof_matcher** out) {
+    if (!out || maxPairs < 1 || maxFeat < 1 || maxFeat > 65535) return mfail(EAOF_ERR_ARG, "bad matcher size (max_features must be in [1,65535])");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return mfail(EAOF_ERR_CUDA, "no CUDA device: libeaof_orb has no CPU fallback");
+    if (device < 0 || device >= ndev) return mfail(EAOF_ERR_ARG, "device out of range");
+    MCK(cudaSetDevice(device));
+    eaof_matcher* m = new eaof_matcher;
+    m->device = device; m->maxPairs = maxPairs; m->maxFeat = maxFeat;
+    const size_t PF = (size_t)maxPairs * maxFeat;
+    cudaError_t e = cudaSuccess;
+#define A_(x) if (e == cudaSuccess) e = (x)
+    A_(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    A_(cudaEventCreateWithFlags(&m->evDep, cudaEventDisableTiming));
+    A_(dalloc(&m->nearBuf, PF * 8)); A_(dalloc(&m->accBuf, PF));
+    A_(dalloc(&m->cellStart, (size_t)maxPairs * (GRID_CELLS + 1))); A_(dalloc(&m->cellIdx, PF));
+    A_(dalloc(&m->cx, PF)); A_(dalloc(&m->cy, PF)); A_(dalloc(&m->cangle, PF)); A_(dalloc(&m->curight, PF));
+    A_(dalloc(&m->lu, PF)); A_(dalloc(&m->lv, PF)); A_(dalloc(&m->linvz, PF)); A_(dalloc(&m->langle, PF));
+    A_(dalloc(&m->coct, PF)); A_(dalloc(&m->loct, PF));
+    A_(dalloc(&m->nC, maxPairs)); A_(dalloc(&m->nL, maxPairs)); A_(dalloc(&m->cRow, maxPairs)); A_(dalloc(&m->lRow, maxPairs));
+    A_(dalloc(&m->ctaken, PF)); A_(dalloc(&m->lvalid, PF)); A_(dalloc(&m->lobs, PF));
+    A_(dalloc(&m->desc2, (size_t)2 * maxFeat * 32)); A_(dalloc(&m->angle2, (size_t)2 * maxFeat));
+    A_(dalloc(&m->validQ, maxFeat)); A_(dalloc(&m->validT, maxFeat)); A_(dalloc(&m->idxQ, maxFeat)); A_(dalloc(&m->idxT, maxFeat));
+    A_(dalloc(&m->segs, maxFeat)); A_(dalloc(&m->segStart, 2)); A_(dalloc(&m->tiles, (size_t)2 * maxFeat));
+    A_(dalloc(&m->pairIdx, (size_t)4 * maxPairs)); A_(dalloc(&m->pairShift, (size_t)2 * maxPairs));
+    A_(dalloc(&m->outMatch, PF)); A_(dalloc(&m->outDist, PF)); A_(dalloc(&m->outN, maxPairs));
+#undef A_
+    if (e != cudaSuccess) {
+        mfail(EAOF_ERR_CUDA, "matcher allocation failed: %s", cudaGetErrorString(e));
+        eaof_matcher_destroy(m);
+        return EAOF_ERR_CUDA;
+    }
+    *out = m;
+    return EAOF_OK;
+}
+
+void eaof_matcher_destroy(eaof_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    void* ptrs[] = {m->nearBuf, m->accBuf, m->cellStart, m->cellIdx, m->cx, m->cy, m->cangle, m->curight, m->lu, m->lv,
+                    m->linvz, m->langle, m->coct, m->loct, m->nC, m->nL, m->cRow, m->lRow, m->ctaken, m->lvalid, m->lobs,
+                    m->desc2, m->angle2, m->validQ, m->validT, m->idxQ, m->idxT, m->segs, m->segStart, m->tiles,
+                    m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN};
+    for (void* p : ptrs) cudaFree(p);
+    if (m->evDep) cudaEventDestroy(m->evDep);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+void* eaof_matcher_stream(eaof_matcher* m) { return m ? (void*)m->stream : nullptr; }
+int eaof_matcher_sync(eaof_matcher* m) {
+    if (!m) return mfail(EAOF_ERR_ARG, "null matcher");
+    MCK(cudaStreamSynchronize(m->stream));
+    return EAOF_OK;
+}
+long long eaof_matcher_last_distance_count(const eaof_matcher* m) { return m ? m->lastDistances : 0; }
+
+int eaof_hamming_distances(eaof_matcher* m, const uint8_t* a, const uint8_t* b, int n, int* out) {
+    if (!m || !a || !b || !out || n < 0) return mfail(EAOF_ERR_ARG, "bad argument");
+    if (n == 0) return EAOF_OK;
+    MCK(cudaSetDevice(m->device));
+    uint8_t *da = nullptr, *db = nullptr;
+    int* dout = nullptr;
+    MCK(cudaMalloc(&da, 32 * (size_t)n)); MCK(cudaMalloc(&db, 32 * (size_t)n)); MCK(cudaMalloc(&dout, sizeof(int) * (size_t)n));
+    MCK(cudaMemcpyAsync(da, a, 32 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    MCK(cudaMemcpyAsync(db, b, 32 * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    k_hamming_pairs<<<(n + 255) / 256, 256, 0, m->stream>>>(da, db, n, dout);
+    MCK(cudaMemcpyAsync(out, dout, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    m->lastDistances = n;
+    return EAOF_OK;
+}
+
+int eaof_match_bow(eaof_matcher* m, int mode, float ratio, int checkOri, int nQ, const uint8_t* descQ, const float* angleQ,
+                   const uint8_t* validQ, int nT, const uint8_t* descT, const float* angleT, const uint8_t* validT,
+                   int nNodesQ, const int* nodeIdQ, const int* nodeStartQ, const int* nodeIdxQ, int nNodesT,
+                   const int* nodeIdT, const int* nodeStartT, const int* nodeIdxT, int* matchOut, int* distOut,
+                   int* nMatches) {
+    if (!m || !matchOut || !nMatches || nQ < 0 || nT < 0) return mfail(EAOF_ERR_ARG, "bad argument");
+    if (mode != EAOF_BOW_KF_FRAME && mode != EAOF_BOW_KF_KF) return mfail(EAOF_ERR_ARG, "unknown mode");
+    if (nQ > m->maxFeat || nT > m->maxFeat) return mfail(EAOF_ERR_ARG, "feature count exceeds max_features=%d", m->maxFeat);
+    if ((nQ && (!descQ || !angleQ)) || (nT && (!descT || !angleT))) return mfail(EAOF_ERR_ARG, "null descriptor/angle array");
+    const int nOut = mode == EAOF_BOW_KF_FRAME ? nT : nQ;
+    *nMatches = 0;
+    for (int i = 0; i < nOut; ++i) { matchOut[i] = -1; if (distOut) distOut[i] = -1; }
+    if (nQ == 0 || nT == 0) return EAOF_OK;
+    // merge-walk of the two feature vectors (:182-264): segments of nodes present on both sides, ascending node id
+    std::vector<BowSeg> segs;
+    std::vector<int2> tiles;
+    long long dists = 0;
+    {
+        int a = 0, b = 0;
+        while (a < nNodesQ && b < nNodesT) {
+            if (nodeIdQ[a] == nodeIdT[b]) {
+                BowSeg s{nodeStartQ[a], nodeStartQ[a + 1] - nodeStartQ[a], nodeStartT[b], nodeStartT[b + 1] - nodeStartT[b]};
+                if (s.qCnt > 0 && s.tCnt > 0) {
+                    for (int q0 = s.qOff; q0 < s.qOff + s.qCnt; q0 += BOW_QT) tiles.push_back(make_int2((int)segs.size(), q0));
+                    segs.push_back(s);
+                    dists += (long long)s.qCnt * s.tCnt;
+                }
+                ++a; ++b;
+            } else if (nodeIdQ[a] < nodeIdT[b]) ++a;
+            else ++b;
+        }
+    }
+    if (segs.empty()) return EAOF_OK;
+    const int nIdxQ = nodeStartQ[nNodesQ], nIdxT = nodeStartT[nNodesT];
+    if (nIdxQ > m->maxFeat || nIdxT > m->maxFeat || (int)segs.size() > m->maxFeat || (int)tiles.size() > 2 * m->maxFeat)
+        return mfail(EAOF_ERR_ARG, "feature vector larger than max_features");
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    MCK(cudaMemcpyAsync(m->desc2, descQ, 32 * (size_t)nQ, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->desc2 + 32 * (size_t)m->maxFeat, descT, 32 * (size_t)nT, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->angle2, angleQ, sizeof(float) * nQ, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->angle2 + m->maxFeat, angleT, sizeof(float) * nT, cudaMemcpyHostToDevice, s));
+    if (validQ) MCK(cudaMemcpyAsync(m->validQ, validQ, nQ, cudaMemcpyHostToDevice, s));
+    if (validT) MCK(cudaMemcpyAsync(m->validT, validT, nT, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->idxQ, nodeIdxQ, sizeof(int) * nIdxQ, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->idxT, nodeIdxT, sizeof(int) * nIdxT, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->segs, segs.data(), sizeof(BowSeg) * segs.size(), cudaMemcpyHostToDevice, s));
+    const int segStart[2] = {0, (int)segs.size()};
+    MCK(cudaMemcpyAsync(m->segStart, segStart, sizeof segStart, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
+    BowArgs A{};
+    A.desc = m->desc2; A.angle = m->angle2; A.counts = nullptr; A.pairQ = nullptr; A.pairT = nullptr;
+    A.blockStride = m->maxFeat; A.validQ = validQ ? m->validQ : nullptr; A.validT = validT ? m->validT : nullptr;
+    A.idxQ = m->idxQ; A.idxT = m->idxT; A.segs = m->segs; A.segStart = m->segStart; A.nQhost = nQ; A.nThost = nT;
+    A.stride = m->maxFeat; A.mode = mode; A.thEff = mode == EAOF_BOW_KF_FRAME ? EAOF_TH_LOW : EAOF_TH_LOW - 1;
+    A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
+    MCK(cudaMemsetAsync(m->nearBuf, 0, sizeof(uint32_t) * 8 * (size_t)m->maxFeat, s));
+    k_bow_dense<<<dim3((unsigned)tiles.size(), 1), BOW_QT, 0, s>>>(A, m->tiles, m->nearBuf);
+    const size_t bm = sizeof(uint32_t) * ((m->maxFeat + 31) / 32);
+    k_bow_resolve<<<1, 32, bm, s>>>(A, m->nearBuf, m->accBuf, m->outMatch, m->outDist, m->outN);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(matchOut, m->outMatch, sizeof(int) * nOut, cudaMemcpyDeviceToHost, s));
+    if (distOut) MCK(cudaMemcpyAsync(distOut, m->outDist, sizeof(int) * nOut, cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    m->lastDistances = dists;
+    return EAOF_OK;
+}
+
+int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, int checkOri, int nPairs, const int* pairQ,
+                                       const int* pairT, const uint8_t* dDesc, const float* dAngle, const int* dCounts,
+                                       int blockStride, int* dMatch, int* dDist, int* dN) {
+    if (!m || !pairQ || !pairT || !dDesc || !dAngle || !dCounts || !dMatch || !dN) return mfail(EAOF_ERR_ARG, "null argument");
+    if (nPairs < 1 || nPairs > m->maxPairs) return mfail(EAOF_ERR_ARG, "n_pairs %d outside [1,%d]", nPairs, m->maxPairs);
+    if (blockStride < 1 || blockStride > m->maxFeat) return mfail(EAOF_ERR_ARG, "block_stride exceeds max_features");
+    if (mode != EAOF_BOW_KF_FRAME && mode != EAOF_BOW_KF_KF) return mfail(EAOF_ERR_ARG, "unknown mode");
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    MCK(cudaMemcpyAsync(m->pairIdx, pairQ, sizeof(int) * nPairs, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(m->pairIdx + m->maxPairs, pairT, sizeof(int) * nPairs, cudaMemcpyHostToDevice, s));
+    BowArgs A{};
+    A.desc = dDesc; A.angle = dAngle; A.counts = dCounts; A.pairQ = m->pairIdx; A.pairT = m->pairIdx + m->maxPairs;
+    A.blockStride = blockStride; A.stride = blockStride; A.mode = mode;
+    A.thEff = mode == EAOF_BOW_KF_FRAME ? EAOF_TH_LOW : EAOF_TH_LOW - 1;
+    A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
+    k_bow_dense<<<dim3((blockStride + BOW_QT - 1) / BOW_QT, nPairs), BOW_QT, 0, s>>>(A, nullptr, m->nearBuf);
+    const size_t bm = sizeof(uint32_t) * ((blockStride + 31) / 32);
+    k_bow_resolve<<<nPairs, 32, bm, s>>>(A, m->nearBuf, m->accBuf, dMatch, dDist, dN);
+    MCK(cudaGetLastError());
+    m->lastDistances = -1;  // counts live on the device; the caller knows nQ*nT per pair
+    return EAOF_OK;
+}
+
+static int run_projection(eaof_matcher* m, ProjArgs& A, int nPairs, int maxL, int* dMatch, int* dDist, int* dN) {
+    cudaStream_t s = m->stream;
+    k_build_grid<<<nPairs, 256, 0, s>>>(A, m->cellStart, m->cellIdx);
+    k_proj_dense<<<dim3((maxL + 127) / 128, nPairs), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
+    const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
+    k_proj_resolve<<<nPairs, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->accBuf, dMatch, dDist, dN);
+    MCK(cudaGetLastError());
+    return EAOF_OK;
+}
+
+int eaof_match_projection(eaof_matcher* m, int nC, const float* cx, const float* cy, const int* coct, const float* cangle,
+                          const uint8_t* cdesc, const float* curight, const uint8_t* ctaken, float minX, float maxX,
+                          float minY, float maxY, float invW, float invH, int nL, const uint8_t* lvalid, const float* lu,
+                          const float* lv, const float* linvz, const int* loct, const float* langle, const uint8_t* ldesc,
+                          const uint8_t* lobs, const float* scaleFactors, int nLevels, float th, float mbf, int searchMode,
+                          int checkOri, int* matchCur, int* distCur, int* nMatches) {
+    if (!m || !matchCur || !nMatches || nC < 0 || nL < 0) return mfail(EAOF_ERR_ARG, "bad argument");
+    if (nC > m->maxFeat || nL > m->maxFeat) return mfail(EAOF_ERR_ARG, "feature count exceeds max_features=%d", m->maxFeat);
+    if (nLevels < 1 || nLevels > EAOF_MAX_LEVELS || !scaleFactors) return mfail(EAOF_ERR_ARG, "bad scale table");
+    *nMatches = 0;
+    for (int i = 0; i < nC; ++i) { matchCur[i] = -1; if (distCur) distCur[i] = -1; }
+    if (nC == 0 || nL == 0) return EAOF_OK;
+    if (!cx || !cy || !coct || !cangle || !cdesc || !lu || !lv || !loct || !langle || !ldesc) return mfail(EAOF_ERR_ARG, "null array");
+    for (int i = 0; i < nL; ++i) if (loct[i] < 0 || loct[i] >= nLevels) return mfail(EAOF_ERR_ARG, "last_octave[%d] out of range", i);
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+#define UP(dst, src, n, T) MCK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(n), cudaMemcpyHostToDevice, s))
+    UP(m->cx, cx, nC, float); UP(m->cy, cy, nC, float); UP(m->coct, coct, nC, int); UP(m->cangle, cangle, nC, float);
+    if (curight) UP(m->curight, curight, nC, float);
+    if (ctaken) UP(m->ctaken, ctaken, nC, uint8_t);
+    UP(m->lu, lu, nL, float); UP(m->lv, lv, nL, float); UP(m->loct, loct, nL, int); UP(m->langle, langle, nL, float);
+    if (linvz) UP(m->linvz, linvz, nL, float);
+    if (lvalid) UP(m->lvalid, lvalid, nL, uint8_t);
+    if (lobs) UP(m->lobs, lobs, nL, uint8_t);
+    UP(m->desc2, cdesc, 32 * (size_t)nC, uint8_t);
+    UP(m->desc2 + 32 * (size_t)m->maxFeat, ldesc, 32 * (size_t)nL, uint8_t);
+    const int hdr[4] = {nC, nL, 0, m->maxFeat};
+    UP(m->nC, &hdr[0], 1, int); UP(m->nL, &hdr[1], 1, int); UP(m->cRow, &hdr[2], 1, int); UP(m->lRow, &hdr[3], 1, int);
+#undef UP
+    ProjArgs A{};
+    A.cx = m->cx; A.cy = m->cy; A.coct = m->coct; A.cangle = m->cangle; A.curight = curight ? m->curight : nullptr;
+    A.ctaken = ctaken ? m->ctaken : nullptr; A.nC = m->nC; A.lu = m->lu; A.lv = m->lv; A.linvz = linvz ? m->linvz : nullptr;
+    A.loct = m->loct; A.langle = m->langle; A.lvalid = lvalid ? m->lvalid : nullptr; A.lobs = lobs ? m->lobs : nullptr;
+    A.nL = m->nL; A.desc = m->desc2; A.cRow = m->cRow; A.lRow = m->lRow; A.stride = m->maxFeat;
+    A.minX = minX; A.maxX = maxX; A.minY = minY; A.maxY = maxY; A.invW = invW; A.invH = invH;
+    for (int i = 0; i < nLevels; ++i) A.scale[i] = scaleFactors[i];
+    A.th = th; A.mbf = mbf; A.searchMode = searchMode; A.checkOri = checkOri;
+    int rc = run_projection(m, A, 1, nL, m->outMatch, m->outDist, m->outN);
+    if (rc) return rc;
+    MCK(cudaMemcpyAsync(matchCur, m->outMatch, sizeof(int) * nC, cudaMemcpyDeviceToHost, s));
+    if (distCur) MCK(cudaMemcpyAsync(distCur, m->outDist, sizeof(int) * nC, cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    return EAOF_OK;
+}
+
+// accessors implemented in eaof_orb.cu
+int eaof_internal_orb_view(eaof_orb* ex, const eaof_kp** kps, const uint8_t** desc, const int** counts, int* cap, int* w,
+                           int* h, const float** scale, int* nlevels, void** stream);
+
+int eaof_match_projection_batch_device(eaof_matcher* m, eaof_orb* ex, int nPairs, const int* lastFrame, const int* curFrame,
+                                       const float* shiftX, const float* shiftY, float th, int* dMatch, int* dDist, int* dN) {
+    if (!m || !ex || !lastFrame || !curFrame || !shiftX || !shiftY || !dMatch || !dN) return mfail(EAOF_ERR_ARG, "null argument");
+    if (nPairs < 1 || nPairs > m->maxPairs) return mfail(EAOF_ERR_ARG, "n_pairs %d outside [1,%d]", nPairs, m->maxPairs);
+    const eaof_kp* kps; const uint8_t* desc; const int* counts; const float* scale;
+    int cap, W, H, nlevels; void* exStream;
+    int rc = eaof_internal_orb_view(ex, &kps, &desc, &counts, &cap, &W, &H, &scale, &nlevels, &exStream);
+    if (rc) return rc;
+    if (cap > m->maxFeat) return mfail(EAOF_ERR_ARG, "extractor keypoint capacity %d exceeds matcher max_features %d", cap, m->maxFeat);
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    // order after the extraction that produced the keypoints
+    MCK(cudaEventRecord(m->evDep, (cudaStream_t)exStream));
+    MCK(cudaStreamWaitEvent(s, m->evDep, 0));
+    int* dLast = m->pairIdx; int* dCur = m->pairIdx + m->maxPairs;
+    float* dSx = m->pairShift; float* dSy = m->pairShift + m->maxPairs;
+    MCK(cudaMemcpyAsync(dLast, lastFrame, sizeof(int) * nPairs, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(dCur, curFrame, sizeof(int) * nPairs, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(dSx, shiftX, sizeof(float) * nPairs, cudaMemcpyHostToDevice, s));
+    MCK(cudaMemcpyAsync(dSy, shiftY, sizeof(float) * nPairs, cudaMemcpyHostToDevice, s));
+    const int stride = cap;
+    k_proj_prepare<<<dim3((cap + 127) / 128, nPairs), 128, 0, s>>>(kps, counts, cap, dLast, dCur, dSx, dSy, stride, m->cx, m->cy,
+                                                                  m->coct, m->cangle, m->lu, m->lv, m->loct, m->langle, m->nC,
+                                                                  m->nL, m->cRow, m->lRow);
+    ProjArgs A{};
+    A.cx = m->cx; A.cy = m->cy; A.coct = m->coct; A.cangle = m->cangle; A.nC = m->nC; A.lu = m->lu; A.lv = m->lv;
+    A.loct = m->loct; A.langle = m->langle; A.nL = m->nL; A.desc = desc; A.cRow = m->cRow; A.lRow = m->lRow; A.stride = stride;
+    // Frame image bounds without distortion (src/Frame.cc:1040-1046): mnMinX=0, mnMaxX=cols, grid cell inverse sizes :213-214
+    A.minX = 0.f; A.maxX = (float)W; A.minY = 0.f; A.maxY = (float)H;
+    A.invW = (float)GRID_COLS / (A.maxX - A.minX); A.invH = (float)GRID_ROWS / (A.maxY - A.minY);
+    for (int i = 0; i < nlevels; ++i) A.scale[i] = scale[i];
+    A.th = th; A.mbf = 0.f; A.searchMode = 0; A.checkOri = 1;
+    return run_projection(m, A, nPairs, cap, dMatch, dDist, dN);
+}
+
+}  // extern "C"

@@ -574,6 +574,16 @@ int eaof_orb_stage_times(eaof_orb* c, float* ms6) {
     for (int i = 0; i < 6; ++i) ms6[i] = c->stageMs[i];
     return EAOF_OK;
 }
+// ---- internal hooks for eaof_match.cu (not part of the public ABI)
+int eaof_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+int eaof_internal_orb_view(eaof_orb* c, const eaof_kp** kps, const uint8_t** desc, const int** counts, int* cap, int* w,
+                           int* h, const float** scale, int* nlevels, void** stream) {
+    if (!c) return fail(EAOF_ERR_ARG, "null extractor handle");
+    *kps = c->dKps; *desc = c->dDesc; *counts = c->dKpCount; *cap = c->kpCap; *w = c->p.width; *h = c->p.height;
+    *scale = c->scale.data(); *nlevels = c->p.nlevels; *stream = (void*)c->stream;
+    return EAOF_OK;
+}
+
 int eaof_orb_last_launch_count(const eaof_orb* c) { return c ? c->lastLaunches : 0; }
 void* eaof_orb_stream(eaof_orb* c) { return c ? (void*)c->stream : nullptr; }
 

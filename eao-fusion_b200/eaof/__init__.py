@@ -212,3 +212,142 @@ class ORBextractor:
 
     def last_launch_count(self):
         return self.L.eaof_orb_last_launch_count(self.h)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Matcher (include/eaof_match.h)
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # ORBmatcher::TH_HIGH/TH_LOW/HISTO_LENGTH, src/ORBmatcher.cc:37-39
+BOW_KF_FRAME, BOW_KF_KF = 0, 1
+_mlib_ready = False
+
+
+def _mlib():
+    global _mlib_ready
+    L = lib()
+    if not _mlib_ready:
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.eaof_matcher_create.argtypes = [ci, ci, ci, C.POINTER(vp)]
+        L.eaof_matcher_destroy.argtypes = [vp]
+        L.eaof_matcher_stream.restype = vp
+        L.eaof_matcher_stream.argtypes = [vp]
+        L.eaof_matcher_sync.argtypes = [vp]
+        L.eaof_hamming_distances.argtypes = [vp, vp, vp, ci, vp]
+        L.eaof_match_bow.argtypes = [vp, ci, cf, ci, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, vp,
+                                     C.POINTER(ci)]
+        L.eaof_match_projection.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp, vp,
+                                            vp, vp, vp, vp, vp, ci, cf, cf, ci, ci, vp, vp, C.POINTER(ci)]
+        L.eaof_match_projection_batch_device.argtypes = [vp, vp, ci, vp, vp, vp, vp, cf, vp, vp, vp]
+        L.eaof_match_bruteforce_batch_device.argtypes = [vp, ci, cf, ci, ci, vp, vp, vp, vp, vp, ci, vp, vp, vp]
+        L.eaof_matcher_last_distance_count.restype = C.c_longlong
+        L.eaof_matcher_last_distance_count.argtypes = [vp]
+        _mlib_ready = True
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def _arr(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dt)
+
+
+def csr_from_nodes(node_of_feature):
+    """DBoW2::FeatureVector for tests: feature i belongs to node node_of_feature[i] (-1 = in no node).
+    Returns (node_ids ascending, starts, idx) with features of a node in ascending index order, as
+    FeatureVector::addFeature produces them."""
+    node_of_feature = np.asarray(node_of_feature)
+    ids = np.unique(node_of_feature[node_of_feature >= 0]).astype(np.int32)
+    starts = [0]
+    idx = []
+    for nid in ids:
+        f = np.nonzero(node_of_feature == nid)[0]
+        idx.extend(f.tolist())
+        starts.append(len(idx))
+    return ids, np.asarray(starts, np.int32), np.asarray(idx, np.int32)
+
+
+class ORBmatcher:
+    """Mirror of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:37-102) over the C ABI, on plain arrays."""
+
+    TH_HIGH, TH_LOW, HISTO_LENGTH = TH_HIGH, TH_LOW, HISTO_LENGTH
+
+    def __init__(self, nnratio=0.6, checkOri=True, *, max_features=4096, max_pairs=1, device=0):
+        self.L = _mlib()
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        h = C.c_void_p()
+        _ck(self.L.eaof_matcher_create(device, max_pairs, max_features, C.byref(h)))
+        self.h = h
+        self.max_features, self.max_pairs = max_features, max_pairs
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.eaof_matcher_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def DescriptorDistance(self, a, b):
+        a = _arr(a, np.uint8).reshape(-1, 32)
+        b = _arr(b, np.uint8).reshape(-1, 32)
+        out = np.zeros(len(a), np.int32)
+        _ck(self.L.eaof_hamming_distances(self.h, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
+        return out
+
+    def SearchByBoW(self, mode, desc_q, angle_q, valid_q, nodes_q, desc_t, angle_t, valid_t, nodes_t):
+        """nodes_* = (ids, starts, idx) CSR.  Returns (nmatches, match, dist)."""
+        dq, dt = _arr(desc_q, np.uint8), _arr(desc_t, np.uint8)
+        aq, at = _arr(angle_q, np.float32), _arr(angle_t, np.float32)
+        vq, vt = _arr(valid_q, np.uint8), _arr(valid_t, np.uint8)
+        iq, sq, xq = (_arr(v, np.int32) for v in nodes_q)
+        it, st, xt = (_arr(v, np.int32) for v in nodes_t)
+        nq, nt = len(dq), len(dt)
+        nout = nt if mode == BOW_KF_FRAME else nq
+        match = np.full(max(nout, 1), -1, np.int32)
+        dist = np.full(max(nout, 1), -1, np.int32)
+        n = C.c_int()
+        _ck(self.L.eaof_match_bow(self.h, mode, self.mfNNratio, int(self.mbCheckOrientation), nq, _p(dq), _p(aq), _p(vq),
+                                  nt, _p(dt), _p(at), _p(vt), len(iq), _p(iq), _p(sq), _p(xq), len(it), _p(it), _p(st),
+                                  _p(xt), match.ctypes.data, dist.ctypes.data, C.byref(n)))
+        return n.value, match[:nout], dist[:nout]
+
+    def SearchByProjection(self, cur, last, th, *, bounds, grid_inv, scale_factors, mbf=0.0, search_mode=0):
+        """cur: dict(x,y,octave,angle,desc[,uright,taken]); last: dict(u,v,octave,angle,desc[,valid,invz,obs]).
+        bounds=(minX,maxX,minY,maxY).  Returns (nmatches, match_cur, dist_cur)."""
+        cx, cy = _arr(cur["x"], np.float32), _arr(cur["y"], np.float32)
+        co, ca, cd = _arr(cur["octave"], np.int32), _arr(cur["angle"], np.float32), _arr(cur["desc"], np.uint8)
+        cur_r, ctk = _arr(cur.get("uright"), np.float32), _arr(cur.get("taken"), np.uint8)
+        lu, lv = _arr(last["u"], np.float32), _arr(last["v"], np.float32)
+        lo, la, ld = _arr(last["octave"], np.int32), _arr(last["angle"], np.float32), _arr(last["desc"], np.uint8)
+        lval, linv, lobs = _arr(last.get("valid"), np.uint8), _arr(last.get("invz"), np.float32), _arr(last.get("obs"), np.uint8)
+        sf = _arr(scale_factors, np.float32)
+        nc, nl = len(cx), len(lu)
+        match = np.full(max(nc, 1), -1, np.int32)
+        dist = np.full(max(nc, 1), -1, np.int32)
+        n = C.c_int()
+        _ck(self.L.eaof_match_projection(self.h, nc, _p(cx), _p(cy), _p(co), _p(ca), _p(cd), _p(cur_r), _p(ctk),
+                                         bounds[0], bounds[1], bounds[2], bounds[3], grid_inv[0], grid_inv[1], nl, _p(lval),
+                                         _p(lu), _p(lv), _p(linv), _p(lo), _p(la), _p(ld), _p(lobs), _p(sf), len(sf),
+                                         float(th), float(mbf), search_mode, int(self.mbCheckOrientation),
+                                         match.ctypes.data, dist.ctypes.data, C.byref(n)))
+        return n.value, match[:nc], dist[:nc]
+
+    def stream_ptr(self):
+        return self.L.eaof_matcher_stream(self.h)
+
+    def sync(self):
+        _ck(self.L.eaof_matcher_sync(self.h))
+
+    def projection_batch_device(self, ex: "ORBextractor", last_frames, cur_frames, shift_x, shift_y, th, d_match, d_dist,
+                                d_n):
+        lf, cf_ = _arr(last_frames, np.int32), _arr(cur_frames, np.int32)
+        sx, sy = _arr(shift_x, np.float32), _arr(shift_y, np.float32)
+        _ck(self.L.eaof_match_projection_batch_device(self.h, ex.h, len(lf), _p(lf), _p(cf_), _p(sx), _p(sy), float(th),
+                                                      d_match, d_dist, d_n))
+
+    def bruteforce_batch_device(self, mode, pair_q, pair_t, d_desc, d_angle, d_counts, block_stride, d_match, d_dist, d_n):
+        pq, pt = _arr(pair_q, np.int32), _arr(pair_t, np.int32)
+        _ck(self.L.eaof_match_bruteforce_batch_device(self.h, mode, self.mfNNratio, int(self.mbCheckOrientation), len(pq),
+                                                      _p(pq), _p(pt), d_desc, d_angle, d_counts, block_stride, d_match,
+                                                      d_dist, d_n))

@@ -1,0 +1,104 @@
+/*
+ * eaof_match.h — C ABI of the Hamming matcher in libeaof_orb.so (B200, sm_100a).
+ *
+ * Replaces the descriptor search loops of the reference's ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:37-102,
+ * src/ORBmatcher.cc).  MapPoint* / KeyFrame* / Frame objects stay on the reference host path; what crosses this
+ * boundary are plain arrays: 32-byte descriptors, keypoint angles/octaves/positions, validity flags in place of
+ * "has a good map point", DBoW2::FeatureVector as CSR (sorted node ids, starts, feature indices) and the projected
+ * pixel of each map point.  Results are bit-exact with the reference loops, including the TH_LOW/TH_HIGH gates,
+ * the fp32 ratio test, the greedy "already matched" exclusion (which makes results depend on query order) and the
+ * rotation-histogram pruning with each function's own histogram factor.
+ *
+ * Same conventions as eaof_orb.h: 0 / negative EAOF_ERR_*, eaof_last_error(), no CPU fallback.
+ */
+#ifndef EAOF_MATCH_H
+#define EAOF_MATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "eaof_orb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EAOF_TH_HIGH 100      /* ORBmatcher::TH_HIGH      src/ORBmatcher.cc:37 */
+#define EAOF_TH_LOW 50        /* ORBmatcher::TH_LOW       src/ORBmatcher.cc:38 */
+#define EAOF_HISTO_LENGTH 30  /* ORBmatcher::HISTO_LENGTH src/ORBmatcher.cc:39 */
+
+enum {
+    EAOF_BOW_KF_FRAME = 0, /* SearchByBoW(KeyFrame*, Frame&, ...)    src/ORBmatcher.cc:159-288: best <= TH_LOW,
+                              output per TARGET (Frame) feature = index of the matched query (KeyFrame) feature */
+    EAOF_BOW_KF_KF = 1     /* SearchByBoW(KeyFrame*, KeyFrame*, ...) src/ORBmatcher.cc:522-655: best <  TH_LOW, targets
+                              need valid_t, output per QUERY feature = index of the matched target feature */
+};
+
+typedef struct eaof_matcher eaof_matcher;
+
+/* One handle = one stream + workspace for up to max_pairs pairs of up to max_features features each. */
+int eaof_matcher_create(int device, int max_pairs, int max_features, eaof_matcher** out);
+void eaof_matcher_destroy(eaof_matcher* m);
+void* eaof_matcher_stream(eaof_matcher* m);
+int eaof_matcher_sync(eaof_matcher* m);
+
+/* static int ORBmatcher::DescriptorDistance(a, b)  src/ORBmatcher.cc:1649-1665, for n descriptor pairs (host
+ * buffers; a and b hold n x 32 bytes). */
+int eaof_hamming_distances(eaof_matcher* m, const uint8_t* a, const uint8_t* b, int n, int* dist_out);
+
+/* SearchByBoW for one pair, HOST buffers.  Q = pKF/pKF1 (outer loop), T = F/pKF2 (inner loop).
+ * valid_q / valid_t: 1 where the feature has a map point that is not bad (NULL = all valid; valid_t is only
+ * consulted in EAOF_BOW_KF_KF mode, as in the reference).  Node lists: node ids ascending, start arrays have
+ * n_nodes+1 entries, idx arrays list feature indices in FeatureVector order.  match_out / dist_out: n_t entries in
+ * KF_FRAME mode, n_q entries in KF_KF mode (-1 = no match).  *n_matches = the function's return value. */
+int eaof_match_bow(eaof_matcher* m, int mode, float nnratio, int check_orientation, int n_q, const uint8_t* desc_q,
+                   const float* angle_q, const uint8_t* valid_q, int n_t, const uint8_t* desc_t, const float* angle_t,
+                   const uint8_t* valid_t, int n_nodes_q, const int* node_id_q, const int* node_start_q,
+                   const int* node_idx_q, int n_nodes_t, const int* node_id_t, const int* node_start_t,
+                   const int* node_idx_t, int* match_out, int* dist_out, int* n_matches);
+
+/* SearchByProjection(Frame& Cur, const Frame& Last, th, bMono)  src/ORBmatcher.cc:1328-1472, one pair, HOST buffers.
+ * Cur: undistorted keypoint positions/octaves/angles, descriptors, optional mvuRight (NULL = monocular) and
+ * optional `taken` flags (Cur feature already holds a map point with observations).  The 64x48 grid of
+ * Frame::AssignFeaturesToGrid (src/Frame.cc:599-614) is rebuilt on the device from (min_x, min_y, grid_inv_w,
+ * grid_inv_h).  Last: per feature the projected pixel (u, v) and 1/z computed by the caller (src/ORBmatcher.cc:1364-1377
+ * stays on the host), validity (map point present and not an outlier), octave, angle, the map point's descriptor
+ * and obs = pMP->Observations()>0 (NULL = all).  search_mode 0: octave-1..octave+1, 1: bForward, 2: bBackward.
+ * match_cur / dist_cur: n_cur entries (index of the Last feature, -1 = none). */
+int eaof_match_projection(eaof_matcher* m, int n_cur, const float* cur_x, const float* cur_y, const int* cur_octave,
+                          const float* cur_angle, const uint8_t* cur_desc, const float* cur_uright,
+                          const uint8_t* cur_taken, float min_x, float max_x, float min_y, float max_y,
+                          float grid_inv_w, float grid_inv_h, int n_last, const uint8_t* last_valid,
+                          const float* last_u, const float* last_v, const float* last_invz, const int* last_octave,
+                          const float* last_angle, const uint8_t* last_desc, const uint8_t* last_obs,
+                          const float* scale_factors, int n_levels, float th, float mbf, int search_mode,
+                          int check_orientation, int* match_cur, int* dist_cur, int* n_matches);
+
+/* ---- batched, device-resident forms used for sequences (BASELINE.json configs[1] and [4]) ------------------ */
+
+/* Consecutive-frame SearchByProjection over the results an extractor handle holds on the device: pair p matches
+ * Cur = frame cur_frame[p] against Last = frame last_frame[p]; the "projection" of Last keypoint i is its own
+ * position shifted by (shift_x[p], shift_y[p]) (known inter-frame motion plays the role of Rcw*X+tcw), every Last
+ * feature counts as a map point with observations, monocular, search_mode 0, orientation check on.
+ * d_match / d_dist: n_pairs x cap ints on the device, d_nmatches: n_pairs ints.  Asynchronous on the matcher's
+ * stream after waiting for the extractor's stream. */
+int eaof_match_projection_batch_device(eaof_matcher* m, eaof_orb* ex, int n_pairs, const int* last_frame,
+                                       const int* cur_frame, const float* shift_x, const float* shift_y, float th,
+                                       int* d_match, int* d_dist, int* d_nmatches);
+
+/* Brute-force SearchByBoW semantics (one vocabulary node holding every feature) over pairs of descriptor blocks
+ * resident on the device: block f = d_desc + f*block_stride*32 with d_counts[f] features and angles
+ * d_angle + f*block_stride.  Pair p: queries = block pair_q[p], targets = block pair_t[p].  Outputs as
+ * eaof_match_bow, laid out [pair][block_stride].  pair_q/pair_t are host arrays. */
+int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float nnratio, int check_orientation, int n_pairs,
+                                       const int* pair_q, const int* pair_t, const uint8_t* d_desc,
+                                       const float* d_angle, const int* d_counts, int block_stride, int* d_match,
+                                       int* d_dist, int* d_nmatches);
+
+/* Number of descriptor-pair distances the last batched call evaluated (for the matches/s metric). */
+long long eaof_matcher_last_distance_count(const eaof_matcher* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAOF_MATCH_H */

@@ -1,1 +1,311 @@
-// ORACLE — test infrastructure only.  Matcher restatement (filled in below).
+// ORACLE — test infrastructure only.  Nothing here is linked into, imported by or executed from the product path.
+//
+// Line-by-line restatement, on plain arrays, of the reference's Hamming search loops
+// (/root/reference/src/ORBmatcher.cc) and of the Frame grid they query (src/Frame.cc).  MapPoint*/KeyFrame*/Frame
+// objects become arrays: "has a good map point" is a validity flag, DBoW2::FeatureVector
+// (std::map<NodeId, vector<unsigned>>) is a CSR triple (sorted node ids, starts, feature indices), and the 64x48
+// feature grid is rebuilt from the undistorted keypoints exactly as Frame::AssignFeaturesToGrid does.
+//
+// PARITY STATUS: the reference's ORBmatcher.cc cannot be compiled here (it needs Frame.h -> PCL, Eigen, g2o, DBoW2,
+// PEAC: none installed) and the reference ships no tests or golden vectors, so this restatement is checked only
+// against independent numpy restatements (tests/test_oracle_matcher.py) — "parity unpinned" for the matcher.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+const int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;  // src/ORBmatcher.cc:37-39
+const int GRID_COLS = 64, GRID_ROWS = 48;                 // include/Frame.h:89-90
+
+// ORBmatcher::DescriptorDistance  src/ORBmatcher.cc:1649-1665 (the SWAR bit hack, kept literally)
+int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t x, y;
+        memcpy(&x, a + 4 * i, 4);
+        memcpy(&y, b + 4 * i, 4);
+        unsigned int v = x ^ y;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+// ORBmatcher::ComputeThreeMaxima  src/ORBmatcher.cc:1603-1644
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; ++i) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+int rot_bin(float a1, float a2, float factor) {  // e.g. src/ORBmatcher.cc:238-244
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+struct Csr { int n; const int* id; const int* start; const int* idx; };
+
+}  // namespace
+
+extern "C" {
+
+int eaoo_hamming(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+void eaoo_three_maxima(const int* sizes, int L, int* i1, int* i2, int* i3) {
+    std::vector<std::vector<int>> h(L);
+    for (int i = 0; i < L; ++i) h[i].resize(sizes[i]);
+    *i1 = *i2 = *i3 = -1;
+    three_maxima(h.data(), L, *i1, *i2, *i3);
+}
+
+// mode 0: SearchByBoW(KeyFrame*, Frame&, ...)      src/ORBmatcher.cc:159-288   (accept best <= TH_LOW)
+//         matchOut/distOut have nT entries: index of the matched query (KF feature) per target (F feature), -1 = none
+// mode 1: SearchByBoW(KeyFrame*, KeyFrame*, ...)   src/ORBmatcher.cc:522-655   (accept best <  TH_LOW, targets need
+//         a good map point) matchOut/distOut have nQ entries: index of the matched target per query
+// Q = pKF / pKF1 side (outer loop), T = F / pKF2 side (inner loop).  validQ/validT: "map point present and not bad".
+int eaoo_search_by_bow(int mode, int nQ, const uint8_t* descQ, const float* angleQ, const uint8_t* validQ, int nT,
+                       const uint8_t* descT, const float* angleT, const uint8_t* validT, int nNodesQ,
+                       const int* nodeIdQ, const int* nodeStartQ, const int* nodeIdxQ, int nNodesT, const int* nodeIdT,
+                       const int* nodeStartT, const int* nodeIdxT, float nnratio, int checkOri, int* matchOut,
+                       int* distOut) {
+    const int nOut = mode == 0 ? nT : nQ;
+    for (int i = 0; i < nOut; ++i) { matchOut[i] = -1; if (distOut) distOut[i] = -1; }
+    std::vector<char> matchedT(nT, 0);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;  // :172 / :541 (upstream quirk)
+    int nmatches = 0;
+    int a = 0, b = 0;
+    while (a < nNodesQ && b < nNodesT) {
+        if (nodeIdQ[a] == nodeIdT[b]) {
+            for (int iq = nodeStartQ[a]; iq < nodeStartQ[a + 1]; ++iq) {
+                const int q = nodeIdxQ[iq];
+                if (validQ && !validQ[q]) continue;
+                int best1 = 256, bestIdx = -1, best2 = 256;
+                for (int it = nodeStartT[b]; it < nodeStartT[b + 1]; ++it) {
+                    const int t = nodeIdxT[it];
+                    if (matchedT[t]) continue;
+                    if (mode == 1 && validT && !validT[t]) continue;
+                    const int dist = descriptor_distance(descQ + 32 * (size_t)q, descT + 32 * (size_t)t);
+                    if (dist < best1) { best2 = best1; best1 = dist; bestIdx = t; }
+                    else if (dist < best2) { best2 = dist; }
+                }
+                const bool thOk = mode == 0 ? best1 <= TH_LOW : best1 < TH_LOW;
+                if (thOk && (float)best1 < nnratio * (float)best2) {
+                    matchedT[bestIdx] = 1;
+                    const int outIdx = mode == 0 ? bestIdx : q;
+                    matchOut[outIdx] = mode == 0 ? q : bestIdx;
+                    if (distOut) distOut[outIdx] = best1;
+                    if (checkOri) rotHist[rot_bin(angleQ[q], angleT[bestIdx], factor)].push_back(outIdx);
+                    ++nmatches;
+                }
+            }
+            ++a; ++b;
+        } else if (nodeIdQ[a] < nodeIdT[b]) {
+            while (a < nNodesQ && nodeIdQ[a] < nodeIdT[b]) ++a;  // lower_bound on a sorted map
+        } else {
+            while (b < nNodesT && nodeIdT[b] < nodeIdQ[a]) ++b;
+        }
+    }
+    if (checkOri) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int j : rotHist[i]) { matchOut[j] = -1; if (distOut) distOut[j] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchForTriangulation  src/ORBmatcher.cc:657-823 with CheckDistEpipolarLine :140-157.
+// freeQ/freeT: feature has NO map point; stereoQ/stereoT: mvuRight >= 0.  F12 row-major 3x3.  match12 has n1 entries.
+int eaoo_search_for_triangulation(int n1, const uint8_t* desc1, const float* x1, const float* y1, const float* angle1,
+                                  const uint8_t* free1, const uint8_t* stereo1, int n2, const uint8_t* desc2,
+                                  const float* x2, const float* y2, const int* oct2, const float* angle2,
+                                  const uint8_t* free2, const uint8_t* stereo2, int nNodes1, const int* nodeId1,
+                                  const int* nodeStart1, const int* nodeIdx1, int nNodes2, const int* nodeId2,
+                                  const int* nodeStart2, const int* nodeIdx2, const float* F12, float ex, float ey,
+                                  const float* scaleFactors2, const float* levelSigma2_2, int onlyStereo, int checkOri,
+                                  int* match12, int* dist12) {
+    for (int i = 0; i < n1; ++i) { match12[i] = -1; if (dist12) dist12[i] = -1; }
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;  // :684
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nNodes1 && b < nNodes2) {
+        if (nodeId1[a] == nodeId2[b]) {
+            for (int i1 = nodeStart1[a]; i1 < nodeStart1[a + 1]; ++i1) {
+                const int idx1 = nodeIdx1[i1];
+                if (!free1[idx1]) continue;
+                const bool bStereo1 = stereo1 && stereo1[idx1];
+                if (onlyStereo && !bStereo1) continue;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = nodeStart2[b]; i2 < nodeStart2[b + 1]; ++i2) {
+                    const int idx2 = nodeIdx2[i2];
+                    if (!free2[idx2]) continue;  // vbMatched2 is never set inside the loop (upstream behaviour)
+                    const bool bStereo2 = stereo2 && stereo2[idx2];
+                    if (onlyStereo && !bStereo2) continue;
+                    const int dist = descriptor_distance(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - x2[idx2], distey = ey - y2[idx2];
+                        if (distex * distex + distey * distey < 100 * scaleFactors2[oct2[idx2]]) continue;
+                    }
+                    // CheckDistEpipolarLine
+                    const float la = x1[idx1] * F12[0] + y1[idx1] * F12[3] + F12[6];
+                    const float lb = x1[idx1] * F12[1] + y1[idx1] * F12[4] + F12[7];
+                    const float lc = x1[idx1] * F12[2] + y1[idx1] * F12[5] + F12[8];
+                    const float num = la * x2[idx2] + lb * y2[idx2] + lc;
+                    const float den = la * la + lb * lb;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if (dsqr < 3.84 * levelSigma2_2[oct2[idx2]]) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[idx1] = bestIdx2;
+                    if (dist12) dist12[idx1] = bestDist;
+                    ++nmatches;
+                    if (checkOri) rotHist[rot_bin(angle1[idx1], angle2[bestIdx2], factor)].push_back(idx1);
+                }
+            }
+            ++a; ++b;
+        } else if (nodeId1[a] < nodeId2[b]) {
+            while (a < nNodes1 && nodeId1[a] < nodeId2[b]) ++a;
+        } else {
+            while (b < nNodes2 && nodeId2[b] < nodeId1[a]) ++b;
+        }
+    }
+    if (checkOri) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int j : rotHist[i]) { match12[j] = -1; if (dist12) dist12[j] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+// Frame::AssignFeaturesToGrid + PosInGrid  src/Frame.cc:599-614,751-761.  cellStart has 64*48+1 entries, cells are
+// numbered ix*48+iy (mGrid[ix][iy]); cellIdx holds feature indices in ascending order per cell.
+void eaoo_build_grid(int n, const float* x, const float* y, float minX, float minY, float invW, float invH,
+                     int* cellStart, int* cellIdx) {
+    std::vector<std::vector<int>> g(GRID_COLS * GRID_ROWS);
+    for (int i = 0; i < n; ++i) {
+        const int px = (int)roundf((x[i] - minX) * invW), py = (int)roundf((y[i] - minY) * invH);
+        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+        g[px * GRID_ROWS + py].push_back(i);
+    }
+    int o = 0;
+    for (int c = 0; c < GRID_COLS * GRID_ROWS; ++c) {
+        cellStart[c] = o;
+        for (int i : g[c]) cellIdx[o++] = i;
+    }
+    cellStart[GRID_COLS * GRID_ROWS] = o;
+}
+
+static void features_in_area(const int* cellStart, const int* cellIdx, const float* kx, const float* ky,
+                             const int* koct, float x, float y, float r, int minLevel, int maxLevel, float minX,
+                             float minY, float invW, float invH, std::vector<int>& out) {
+    // Frame::GetFeaturesInArea  src/Frame.cc:696-749
+    out.clear();
+    const int nMinCellX = std::max(0, (int)floorf((x - minX - r) * invW));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)ceilf((x - minX + r) * invW));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = std::max(0, (int)floorf((y - minY - r) * invH));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)ceilf((y - minY + r) * invH));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+        for (int iy = nMinCellY; iy <= nMaxCellY; ++iy) {
+            const int c = ix * GRID_ROWS + iy;
+            for (int j = cellStart[c]; j < cellStart[c + 1]; ++j) {
+                const int k = cellIdx[j];
+                if (bCheckLevels) {
+                    if (koct[k] < minLevel) continue;
+                    if (maxLevel >= 0 && koct[k] > maxLevel) continue;
+                }
+                const float dx = kx[k] - x, dy = ky[k] - y;
+                if (fabsf(dx) < r && fabsf(dy) < r) out.push_back(k);
+            }
+        }
+}
+
+// ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono)  src/ORBmatcher.cc:1328-1472.
+// The 3-D projection (:1364-1377) is the caller's: lu/lv are the projected pixel, linvz = 1/z (NULL: all positive).
+// lvalid: map point present and not an outlier; lobs: pMP->Observations()>0 (NULL: all true); ctaken: Cur feature
+// already holds a map point with observations (NULL: none).  searchMode 0: octave-1..octave+1, 1: forward
+// (>= octave), 2: backward (0..octave).  matchCur/distCur: nC entries, index of the Last feature / its distance.
+int eaoo_search_by_projection_last(int nC, const float* cx, const float* cy, const int* coct, const float* cangle,
+                                   const uint8_t* cdesc, const float* curight, const uint8_t* ctaken, float minX,
+                                   float maxX, float minY, float maxY, float invW, float invH, int nL,
+                                   const uint8_t* lvalid, const float* lu, const float* lv, const float* linvz,
+                                   const int* loct, const float* langle, const uint8_t* ldesc, const uint8_t* lobs,
+                                   const float* scaleFactors, float th, float mbf, int searchMode, int checkOri,
+                                   int* matchCur, int* distCur) {
+    std::vector<int> cellStart(GRID_COLS * GRID_ROWS + 1), cellIdx(nC > 0 ? nC : 1);
+    eaoo_build_grid(nC, cx, cy, minX, minY, invW, invH, cellStart.data(), cellIdx.data());
+    std::vector<char> hasObs(nC, 0);
+    for (int i = 0; i < nC; ++i) { matchCur[i] = -1; if (distCur) distCur[i] = -1; hasObs[i] = ctaken ? ctaken[i] : 0; }
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = HISTO_LENGTH / 360.0f;  // :1337
+    int nmatches = 0;
+    std::vector<int> cand;
+    for (int i = 0; i < nL; ++i) {
+        if (lvalid && !lvalid[i]) continue;
+        const float invzc = linvz ? linvz[i] : 1.f;
+        if (invzc < 0) continue;
+        const float u = lu[i], v = lv[i];
+        if (u < minX || u > maxX) continue;
+        if (v < minY || v > maxY) continue;
+        const int oct = loct[i];
+        const float radius = th * scaleFactors[oct];
+        if (searchMode == 1) features_in_area(cellStart.data(), cellIdx.data(), cx, cy, coct, u, v, radius, oct, -1, minX, minY, invW, invH, cand);
+        else if (searchMode == 2) features_in_area(cellStart.data(), cellIdx.data(), cx, cy, coct, u, v, radius, 0, oct, minX, minY, invW, invH, cand);
+        else features_in_area(cellStart.data(), cellIdx.data(), cx, cy, coct, u, v, radius, oct - 1, oct + 1, minX, minY, invW, invH, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : cand) {
+            if (hasObs[i2]) continue;
+            if (curight && curight[i2] > 0) {
+                const float ur = u - mbf * invzc;
+                const float er = fabsf(ur - curight[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(ldesc + 32 * (size_t)i, cdesc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            matchCur[bestIdx2] = i;
+            if (distCur) distCur[bestIdx2] = bestDist;
+            hasObs[bestIdx2] = lobs ? lobs[i] : 1;
+            ++nmatches;
+            if (checkOri) rotHist[rot_bin(langle[i], cangle[bestIdx2], factor)].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i != i1 && i != i2 && i != i3)
+                for (int j : rotHist[i]) { matchCur[j] = -1; if (distCur) distCur[j] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+}  // extern "C"

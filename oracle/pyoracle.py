@@ -273,3 +273,91 @@ def o_extract(img: np.ndarray, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_
         bl.append(blur[bo:bo + a * b].reshape(b, a)); bo += a * b
         cl.append(cand[co:co + ccnt[l]].copy()); co += ccnt[l]
     return kps[:n].copy(), desc[:n].copy(), pl, bl, cl
+
+
+# ------------------------------------------------------------------------------------------------
+# Matcher restatement (oracle/match_oracle.cc)
+_m_ready = False
+
+
+def _mo():
+    global _m_ready
+    L = oracle_lib()
+    if not _m_ready:
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.eaoo_hamming.restype = ci
+        L.eaoo_hamming.argtypes = [vp, vp]
+        L.eaoo_three_maxima.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
+        L.eaoo_search_by_bow.restype = ci
+        L.eaoo_search_by_bow.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, cf, ci, vp, vp]
+        L.eaoo_search_for_triangulation.restype = ci
+        L.eaoo_build_grid.argtypes = [ci, vp, vp, cf, cf, cf, cf, vp, vp]
+        L.eaoo_search_by_projection_last.restype = ci
+        L.eaoo_search_by_projection_last.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp,
+                                                     vp, vp, vp, vp, vp, vp, cf, cf, ci, ci, vp, vp]
+        _m_ready = True
+    return L
+
+
+def _a(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dt)
+
+
+def _pp(a):
+    return None if a is None else a.ctypes.data
+
+
+def o_hamming(a, b):
+    a = _a(a, np.uint8).reshape(-1, 32)
+    b = _a(b, np.uint8).reshape(-1, 32)
+    L = _mo()
+    return np.array([L.eaoo_hamming(a[i].ctypes.data, b[i].ctypes.data) for i in range(len(a))], np.int32)
+
+
+def o_three_maxima(sizes):
+    s = _a(sizes, np.int32)
+    i1, i2, i3 = C.c_int(), C.c_int(), C.c_int()
+    _mo().eaoo_three_maxima(s.ctypes.data, len(s), C.byref(i1), C.byref(i2), C.byref(i3))
+    return i1.value, i2.value, i3.value
+
+
+def o_search_by_bow(mode, nnratio, check_ori, desc_q, angle_q, valid_q, nodes_q, desc_t, angle_t, valid_t, nodes_t):
+    dq, dt = _a(desc_q, np.uint8), _a(desc_t, np.uint8)
+    aq, at = _a(angle_q, np.float32), _a(angle_t, np.float32)
+    vq, vt = _a(valid_q, np.uint8), _a(valid_t, np.uint8)
+    iq, sq, xq = (_a(v, np.int32) for v in nodes_q)
+    it, st, xt = (_a(v, np.int32) for v in nodes_t)
+    nq, nt = len(dq), len(dt)
+    nout = nt if mode == 0 else nq
+    match = np.full(max(nout, 1), -1, np.int32)
+    dist = np.full(max(nout, 1), -1, np.int32)
+    n = _mo().eaoo_search_by_bow(mode, nq, _pp(dq), _pp(aq), _pp(vq), nt, _pp(dt), _pp(at), _pp(vt), len(iq), _pp(iq), _pp(sq),
+                                 _pp(xq), len(it), _pp(it), _pp(st), _pp(xt), nnratio, int(check_ori), match.ctypes.data,
+                                 dist.ctypes.data)
+    return n, match[:nout], dist[:nout]
+
+
+def o_build_grid(x, y, min_x, min_y, inv_w, inv_h):
+    x, y = _a(x, np.float32), _a(y, np.float32)
+    cs = np.zeros(64 * 48 + 1, np.int32)
+    ci = np.zeros(max(len(x), 1), np.int32)
+    _mo().eaoo_build_grid(len(x), x.ctypes.data, y.ctypes.data, min_x, min_y, inv_w, inv_h, cs.ctypes.data, ci.ctypes.data)
+    return cs, ci[:cs[-1]]
+
+
+def o_search_by_projection(cur, last, th, check_ori, *, bounds, grid_inv, scale_factors, mbf=0.0, search_mode=0):
+    cx, cy = _a(cur["x"], np.float32), _a(cur["y"], np.float32)
+    co, ca, cd = _a(cur["octave"], np.int32), _a(cur["angle"], np.float32), _a(cur["desc"], np.uint8)
+    cur_r, ctk = _a(cur.get("uright"), np.float32), _a(cur.get("taken"), np.uint8)
+    lu, lv = _a(last["u"], np.float32), _a(last["v"], np.float32)
+    lo, la, ld = _a(last["octave"], np.int32), _a(last["angle"], np.float32), _a(last["desc"], np.uint8)
+    lval, linv, lobs = _a(last.get("valid"), np.uint8), _a(last.get("invz"), np.float32), _a(last.get("obs"), np.uint8)
+    sf = _a(scale_factors, np.float32)
+    nc, nl = len(cx), len(lu)
+    match = np.full(max(nc, 1), -1, np.int32)
+    dist = np.full(max(nc, 1), -1, np.int32)
+    n = _mo().eaoo_search_by_projection_last(nc, _pp(cx), _pp(cy), _pp(co), _pp(ca), _pp(cd), _pp(cur_r), _pp(ctk), bounds[0],
+                                             bounds[1], bounds[2], bounds[3], grid_inv[0], grid_inv[1], nl, _pp(lval), _pp(lu),
+                                             _pp(lv), _pp(linv), _pp(lo), _pp(la), _pp(ld), _pp(lobs), _pp(sf), float(th),
+                                             float(mbf), search_mode, int(check_ori), match.ctypes.data, dist.ctypes.data)
+    return n, match[:nc], dist[:nc]

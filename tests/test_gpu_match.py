@@ -1,0 +1,243 @@
+"""GPU matcher parity: libeaof_orb's Hamming search (C ABI, include/eaof_match.h) against the oracle restatement of
+src/ORBmatcher.cc — match indices, distances and match counts bit-exact, including greedy exclusion, ratio test,
+TH_LOW/TH_HIGH and rotation-histogram pruning."""
+import numpy as np
+import pytest
+
+from matchdata import frame_features, planted_pair, projected_last, random_nodes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def matcher_factory():
+    import eaof
+    made = []
+
+    def make(ratio, ori=True, max_features=4096, max_pairs=1):
+        m = eaof.ORBmatcher(ratio, ori, max_features=max_features, max_pairs=max_pairs)
+        made.append(m)
+        return m
+    yield make
+    for m in made:
+        m.close()
+
+
+def test_descriptor_distance(matcher_factory):
+    from oracle import pyoracle as po
+    rng = np.random.Generator(np.random.PCG64(1))
+    a = rng.integers(0, 256, size=(5000, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, size=(5000, 32), dtype=np.uint8)
+    a[:10] = 0; b[:5] = 255; b[5:10] = 0
+    m = matcher_factory(0.6)
+    d = m.DescriptorDistance(a, b)
+    assert np.array_equal(d, np.unpackbits(a ^ b, axis=1).sum(1))
+    assert np.array_equal(d[:200], po.o_hamming(a[:200], b[:200]))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("ratio", [0.6, 0.75, 0.9])
+def test_bow_single_node_bruteforce(matcher_factory, mode, ratio):
+    import eaof
+    from oracle import pyoracle as po
+    m = matcher_factory(ratio)
+    for seed, (nq, nt) in enumerate([(2000, 2000), (1000, 1500), (300, 7), (1, 1), (64, 129)]):
+        q, aq, t, at = planted_pair(nq, nt, seed, dup=5 if nt > 50 else 0)
+        nodes_q = eaof.csr_from_nodes(np.zeros(nq, int))
+        nodes_t = eaof.csr_from_nodes(np.zeros(nt, int))
+        rng = np.random.Generator(np.random.PCG64(100 + seed))
+        vq = (rng.random(nq) > 0.1).astype(np.uint8)
+        vt = (rng.random(nt) > 0.1).astype(np.uint8)
+        n, match, dist = m.SearchByBoW(mode, q, aq, vq, nodes_q, t, at, vt, nodes_t)
+        on, omatch, odist = po.o_search_by_bow(mode, ratio, True, q, aq, vq, nodes_q, t, at, vt, nodes_t)
+        assert n == on, (seed, n, on)
+        assert np.array_equal(match, omatch) and np.array_equal(dist, odist)
+    assert on > 0
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bow_multi_node_and_no_orientation(matcher_factory, mode):
+    import eaof
+    from oracle import pyoracle as po
+    for ori in (True, False):
+        m = matcher_factory(0.7, ori)
+        for seed in range(4):
+            q, aq, t, at = planted_pair(1200, 1100, 40 + seed, flip=0.05)
+            # give planted partners a good chance of sharing a node: nodes from a hash of the first descriptor byte pair
+            nq = (q[:, 0].astype(int) // 32) * 5 + 3
+            ntd = (t[:, 0].astype(int) // 32) * 5 + 3
+            nq[::17] = -1
+            ntd[::13] = 99 + seed  # a node only T has
+            nodes_q, nodes_t = eaof.csr_from_nodes(nq), eaof.csr_from_nodes(ntd)
+            n, match, dist = m.SearchByBoW(mode, q, aq, None, nodes_q, t, at, None, nodes_t)
+            on, omatch, odist = po.o_search_by_bow(mode, 0.7, ori, q, aq, None, nodes_q, t, at, None, nodes_t)
+            assert n == on and np.array_equal(match, omatch) and np.array_equal(dist, odist)
+        assert on > 20
+
+
+def test_bow_heavy_ties_force_the_rescan_path(matcher_factory):
+    """All-equal / all-zero / all-one descriptor sets: every query has thousands of candidates below the near-list
+    threshold, so phase 2 must take the exact re-scan path; first-wins tie-breaking and greedy exclusion decide."""
+    import eaof
+    from oracle import pyoracle as po
+    m = matcher_factory(0.9)
+    rng = np.random.Generator(np.random.PCG64(9))
+    cases = []
+    z = np.zeros((300, 32), np.uint8)
+    cases.append((z, z.copy()))
+    cases.append((np.full((200, 32), 255, np.uint8), np.full((260, 32), 255, np.uint8)))
+    base = rng.integers(0, 256, size=(1, 32), dtype=np.uint8)
+    near = np.repeat(base, 400, axis=0)
+    near[np.arange(400), rng.integers(0, 32, 400)] ^= (1 << rng.integers(0, 8, 400)).astype(np.uint8)
+    cases.append((near[:180], near[150:]))
+    for q, t in cases:
+        aq = rng.uniform(0, 360, len(q)).astype(np.float32)
+        at = rng.uniform(0, 360, len(t)).astype(np.float32)
+        for mode in (0, 1):
+            for ratio_m in (m, ):
+                nodes_q = eaof.csr_from_nodes(np.zeros(len(q), int))
+                nodes_t = eaof.csr_from_nodes(np.zeros(len(t), int))
+                n, match, dist = ratio_m.SearchByBoW(mode, q, aq, None, nodes_q, t, at, None, nodes_t)
+                on, omatch, odist = po.o_search_by_bow(mode, 0.9, True, q, aq, None, nodes_q, t, at, None, nodes_t)
+                assert n == on and np.array_equal(match, omatch) and np.array_equal(dist, odist)
+
+
+def test_bow_empty_inputs(matcher_factory):
+    import eaof
+    m = matcher_factory(0.6)
+    e = np.zeros((0, 32), np.uint8)
+    ea = np.zeros(0, np.float32)
+    q, aq, t, at = planted_pair(10, 10, 1)
+    empty_nodes = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    n, match, _ = m.SearchByBoW(0, e, ea, None, empty_nodes, t, at, None, eaof.csr_from_nodes(np.zeros(10, int)))
+    assert n == 0 and np.all(match == -1) and len(match) == 10
+    n, match, _ = m.SearchByBoW(0, q, aq, None, eaof.csr_from_nodes(np.zeros(10, int)), e, ea, None, empty_nodes)
+    assert n == 0 and len(match) == 0
+
+
+@pytest.fixture(scope="module")
+def extracted(frames640):
+    import eaof
+    ex = eaof.ORBextractor(width=640, height=480, max_batch=8)
+    res = ex.extract_batch(frames640)
+    sf = ex.GetScaleFactors()
+    yield ex, res, sf
+    ex.close()
+
+
+def _bounds():
+    return (0.0, 640.0, 0.0, 480.0), (np.float32(64) / np.float32(640), np.float32(48) / np.float32(480))
+
+
+@pytest.mark.parametrize("th", [15.0, 7.0, 30.0])
+def test_projection_consecutive_frames(matcher_factory, extracted, th):
+    """BASELINE configs[1]: consecutive frames of the synthetic sequence drift by (2,1) px, so a Last keypoint at
+    (x,y) projects to (x-2, y-1) in Cur."""
+    from oracle import pyoracle as po
+    ex, res, sf = extracted
+    bounds, ginv = _bounds()
+    m = matcher_factory(0.9)
+    tot = 0
+    for f in range(1, len(res)):
+        cur = frame_features(*res[f])
+        last = projected_last(*res[f - 1], -2.0, -1.0)
+        n, match, dist = m.SearchByProjection(cur, last, th, bounds=bounds, grid_inv=ginv, scale_factors=sf)
+        on, omatch, odist = po.o_search_by_projection(cur, last, th, True, bounds=bounds, grid_inv=ginv, scale_factors=sf)
+        assert n == on
+        assert np.array_equal(match, omatch) and np.array_equal(dist, odist)
+        tot += n
+    assert tot > 500
+
+
+def test_projection_flags_stereo_and_modes(matcher_factory, extracted):
+    from oracle import pyoracle as po
+    ex, res, sf = extracted
+    bounds, ginv = _bounds()
+    rng = np.random.Generator(np.random.PCG64(5))
+    for ori in (True, False):
+        m = matcher_factory(0.9, ori)
+        for mode in (0, 1, 2):
+            cur = frame_features(*res[2])
+            last = projected_last(*res[1], -2.0, -1.0)
+            nc, nl = len(cur["x"]), len(last["u"])
+            cur["taken"] = (rng.random(nc) < 0.2).astype(np.uint8)
+            cur["uright"] = np.where(rng.random(nc) < 0.5, cur["x"] - 30 + rng.normal(0, 8, nc), -1).astype(np.float32)
+            last["valid"] = (rng.random(nl) < 0.9).astype(np.uint8)
+            last["obs"] = (rng.random(nl) < 0.7).astype(np.uint8)
+            last["invz"] = np.where(rng.random(nl) < 0.05, -0.5, 0.75).astype(np.float32)
+            last["u"][::50] += 700  # outside the image
+            kw = dict(bounds=bounds, grid_inv=ginv, scale_factors=sf, mbf=40.0, search_mode=mode)
+            n, match, dist = m.SearchByProjection(cur, last, 15.0, **kw)
+            on, omatch, odist = po.o_search_by_projection(cur, last, 15.0, ori, **kw)
+            assert n == on and np.array_equal(match, omatch) and np.array_equal(dist, odist)
+
+
+def test_projection_crowded_window_takes_rescan_path(matcher_factory):
+    """Many identical descriptors inside one search window: the four kept candidates get taken by earlier queries."""
+    from oracle import pyoracle as po
+    rng = np.random.Generator(np.random.PCG64(3))
+    n = 300
+    cur = dict(x=(320 + rng.uniform(-6, 6, n)).astype(np.float32), y=(240 + rng.uniform(-6, 6, n)).astype(np.float32),
+               octave=np.zeros(n, np.int32), angle=rng.uniform(0, 360, n).astype(np.float32),
+               desc=np.repeat(rng.integers(0, 256, size=(1, 32), dtype=np.uint8), n, axis=0))
+    last = dict(u=(320 + rng.uniform(-3, 3, n)).astype(np.float32), v=(240 + rng.uniform(-3, 3, n)).astype(np.float32),
+                octave=np.zeros(n, np.int32), angle=rng.uniform(0, 360, n).astype(np.float32), desc=cur["desc"].copy())
+    bounds, ginv = _bounds()
+    sf = np.array([1.0, 1.2], np.float32)
+    m = matcher_factory(0.9)
+    r = m.SearchByProjection(cur, last, 15.0, bounds=bounds, grid_inv=ginv, scale_factors=sf)
+    o = po.o_search_by_projection(cur, last, 15.0, True, bounds=bounds, grid_inv=ginv, scale_factors=sf)
+    assert r[0] == o[0] and np.array_equal(r[1], o[1]) and np.array_equal(r[2], o[2])
+    assert r[0] > 4
+
+
+def test_batched_device_paths_equal_single_pair_api(matcher_factory, extracted, frames640):
+    """eaof_match_projection_batch_device / eaof_match_bruteforce_batch_device on extractor results resident on the GPU."""
+    import torch
+    import eaof
+    from oracle import pyoracle as po
+    ex, res, sf = extracted
+    nfr = len(res)
+    ex.extract_batch(frames640)  # leaves the results of all frames on the device
+    cap = ex.cap
+    m = matcher_factory(0.9, True, max_features=cap, max_pairs=16)
+    npairs = nfr - 1
+    d_match = torch.full((npairs, cap), -7, dtype=torch.int32, device="cuda")
+    d_dist = torch.full((npairs, cap), -7, dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(npairs, dtype=torch.int32, device="cuda")
+    lastf, curf = np.arange(0, nfr - 1), np.arange(1, nfr)
+    m.projection_batch_device(ex, lastf, curf, np.full(npairs, -2.0), np.full(npairs, -1.0), 15.0, d_match.data_ptr(),
+                              d_dist.data_ptr(), d_n.data_ptr())
+    m.sync()
+    bounds, ginv = _bounds()
+    hm, hd, hn = d_match.cpu().numpy(), d_dist.cpu().numpy(), d_n.cpu().numpy()
+    for p in range(npairs):
+        cur = frame_features(*res[p + 1])
+        last = projected_last(*res[p], -2.0, -1.0)
+        on, omatch, odist = po.o_search_by_projection(cur, last, 15.0, True, bounds=bounds, grid_inv=ginv, scale_factors=sf)
+        nc = len(cur["x"])
+        assert hn[p] == on
+        assert np.array_equal(hm[p, :nc], omatch) and np.array_equal(hd[p, :nc], odist)
+    # brute force over the same device-resident descriptors: all ordered pairs (i, j), i != j
+    kps_ptr, desc_ptr, cnt_ptr, cap2 = ex.device_results()
+    assert cap2 == cap
+    ang = torch.zeros((nfr, cap), dtype=torch.float32, device="cuda")
+    for f in range(nfr):
+        ang[f, :len(res[f][0])] = torch.from_numpy(res[f][0]["angle"].copy()).cuda()
+    pq = [i for i in range(nfr) for j in range(nfr) if i != j][:16]
+    pt = [j for i in range(nfr) for j in range(nfr) if i != j][:16]
+    bm = torch.full((len(pq), cap), -7, dtype=torch.int32, device="cuda")
+    bd = torch.full((len(pq), cap), -7, dtype=torch.int32, device="cuda")
+    bn = torch.zeros(len(pq), dtype=torch.int32, device="cuda")
+    for mode in (0, 1):
+        m.bruteforce_batch_device(mode, pq, pt, desc_ptr, ang.data_ptr(), cnt_ptr, cap, bm.data_ptr(), bd.data_ptr(), bn.data_ptr())
+        m.sync()
+        hm, hd, hn = bm.cpu().numpy(), bd.cpu().numpy(), bn.cpu().numpy()
+        for k, (i, j) in enumerate(zip(pq, pt)):
+            (kq, dq), (kt, dt) = res[i], res[j]
+            nodes_q = eaof.csr_from_nodes(np.zeros(len(kq), int))
+            nodes_t = eaof.csr_from_nodes(np.zeros(len(kt), int))
+            on, omatch, odist = po.o_search_by_bow(mode, 0.9, True, dq, kq["angle"], None, nodes_q, dt, kt["angle"], None, nodes_t)
+            nout = len(kt) if mode == 0 else len(kq)
+            assert hn[k] == on
+            assert np.array_equal(hm[k, :nout], omatch) and np.array_equal(hd[k, :nout], odist)
