@@ -1,0 +1,240 @@
+"""Host-side logic that needs no GPU: C-ABI surface, sharding plans (incl. a world_size-2 gloo run), matcher oracle
+against independent pure-Python restatements."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from matchdata import planted_pair, random_nodes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for hdr in ("eaof_orb.h", "eaof_match.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(eaof_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import eaof
+    if not os.path.exists(eaof.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(eaof.LIB_PATH)  # loads without a GPU; no compute calls here
+    decl = _declared_symbols()
+    assert len(decl) >= 25
+    for name in sorted(decl):
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    lib.eaof_abi_version.restype = ctypes.c_int
+    assert lib.eaof_abi_version() == 1
+
+
+def test_product_fails_loudly_without_a_gpu():
+    import eaof
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(eaof.EaofError, match="no CUDA device"):
+        eaof.ORBextractor(width=640, height=480)
+    with pytest.raises(eaof.EaofError, match="no CUDA device"):
+        eaof.ORBmatcher(0.9)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "eao-fusion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                bad = re.findall(r'#\s*include\s*[<"][^>"]*oracle|^\s*(?:from|import)\s+oracle|pyoracle|dlopen\([^)]*oracle', txt, flags=re.M)
+                assert not bad, f"{f} pulls in oracle/: {bad}"
+
+
+def test_shard_plans_cover_everything_once():
+    from eaof import shard
+    for n, world in ((1000, 1), (1000, 8), (10, 4), (7, 8), (100000, 8)):
+        blocks = [shard.frame_block(n, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        pairs = [p for r in range(world) for p in shard.consecutive_pairs(*blocks[r], n)]
+        assert pairs == [(f - 1, f) for f in range(1, n)]
+        for r in range(world):
+            hb = shard.halo_block(*blocks[r])
+            assert all(hb[0] <= a and b < hb[1] for a, b in shard.consecutive_pairs(*blocks[r], n))
+        sw = sorted(i for r in range(world) for i in shard.sweep_pairs(n, r, world))
+        assert sw == list(range(n))
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    """Two processes over gloo: each extracts its frame block with the CPU oracle (stand-in for the GPU on this box),
+    the all-gathered keypoint counts must equal the single-process result -> frame sharding is deterministic."""
+    script = tmp_path / "w2.py"
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "eao-fusion_b200"))
+import numpy as np, torch, torch.distributed as dist
+from eaof import shard, synth
+from oracle import pyoracle as po
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+tex = synth.base_texture(320, 240, seed=3)
+frames = synth.make_frames(5, 320, 240, tex=tex)
+b, e = shard.frame_block(len(frames), rank, world)
+mine = torch.zeros(len(frames), dtype=torch.int64)
+for f in range(b, e):
+    k, d = po.o_extract(frames[f], nfeatures=300)
+    mine[f] = len(k) * 1000003 + int(d.sum()) % 1000003
+dist.all_reduce(mine)
+if rank == 0:
+    full = [len(k) * 1000003 + int(d.sum()) % 1000003 for k, d in (po.o_extract(fr, nfeatures=300) for fr in frames)]
+    assert mine.tolist() == full, (mine.tolist(), full)
+    print("W2 OK")
+dist.destroy_process_group()
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert "W2 OK" in out.stdout, out.stdout + out.stderr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# matcher oracle vs. independent pure-Python restatements of the same reference loops
+
+def _ham(a, b):
+    return int(np.unpackbits(a ^ b).sum())
+
+
+def _three_maxima(sizes):
+    m1 = m2 = m3 = 0
+    i1 = i2 = i3 = -1
+    for i, s in enumerate(sizes):
+        if s > m1:
+            m3, m2, m1, i3, i2, i1 = m2, m1, s, i2, i1, i
+        elif s > m2:
+            m3, m2, i3, i2 = m2, s, i2, i
+        elif s > m3:
+            m3, i3 = s, i
+    if m2 < np.float32(0.1) * np.float32(m1):
+        i2 = i3 = -1
+    elif m3 < np.float32(0.1) * np.float32(m1):
+        i3 = -1
+    return i1, i2, i3
+
+
+def _py_bow(mode, ratio, ori, q, aq, vq, nodes_q, t, at, vt, nodes_t):
+    (iq, sq, xq), (it, st, xt) = nodes_q, nodes_t
+    nout = len(t) if mode == 0 else len(q)
+    match = np.full(nout, -1, np.int32)
+    dist = np.full(nout, -1, np.int32)
+    matched = np.zeros(len(t), bool)
+    hist = [[] for _ in range(30)]
+    n = 0
+    tmap = {int(k): j for j, k in enumerate(it)}
+    for a, nid in enumerate(iq):
+        if int(nid) not in tmap:
+            continue
+        b = tmap[int(nid)]
+        for qi in xq[sq[a]:sq[a + 1]]:
+            if vq is not None and not vq[qi]:
+                continue
+            b1, b2, bi = 256, 256, -1
+            for ti in xt[st[b]:st[b + 1]]:
+                if matched[ti] or (mode == 1 and vt is not None and not vt[ti]):
+                    continue
+                d = _ham(q[qi], t[ti])
+                if d < b1:
+                    b2, b1, bi = b1, d, ti
+                elif d < b2:
+                    b2 = d
+            ok = b1 <= 50 if mode == 0 else b1 < 50
+            if ok and np.float32(b1) < np.float32(ratio) * np.float32(b2):
+                matched[bi] = True
+                o = bi if mode == 0 else qi
+                match[o] = qi if mode == 0 else bi
+                dist[o] = b1
+                if ori:
+                    rot = np.float32(aq[qi]) - np.float32(at[bi])
+                    if rot < 0:
+                        rot = np.float32(rot + np.float32(360))
+                    v = np.float32(rot * np.float32(1.0 / 30))
+                    bn = int(np.floor(abs(v) + np.float32(0.5)) * np.sign(v))  # C round(): half away from zero
+                    hist[0 if bn == 30 else bn].append(o)
+                n += 1
+    if ori:
+        keep = _three_maxima([len(h) for h in hist])
+        for i, h in enumerate(hist):
+            if i not in keep:
+                for o in h:
+                    match[o] = -1
+                    dist[o] = -1
+                    n -= 1
+    return n, match, dist
+
+
+def test_matcher_oracle_primitives():
+    from oracle import pyoracle as po
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.Generator(np.random.PCG64(2))
+    a = rng.integers(0, 256, size=(300, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, size=(300, 32), dtype=np.uint8)
+    a[:3] = 0
+    b[:3] = 255
+    d = po.o_hamming(a, b)
+    assert np.array_equal(d, np.unpackbits(a ^ b, axis=1).sum(1))
+    assert all(d[i] == int(cv2.norm(a[i], b[i], cv2.NORM_HAMMING)) for i in range(300))
+    assert d[0] == 256
+    for _ in range(200):
+        sizes = rng.integers(0, 12, 30) * (rng.random(30) < 0.5)
+        assert po.o_three_maxima(sizes) == _three_maxima([int(s) for s in sizes])
+    assert po.o_three_maxima([0] * 30) == (-1, -1, -1)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_matcher_oracle_bow_vs_python(mode):
+    import eaof
+    from oracle import pyoracle as po
+    for seed, (nq, nt, ratio, ori) in enumerate([(120, 150, 0.9, True), (80, 80, 0.6, True), (60, 200, 0.75, False),
+                                                 (1, 5, 0.9, True), (40, 40, 0.9, True)]):
+        q, aq, t, at = planted_pair(nq, nt, 70 + seed, dup=3 if nt > 30 else 0)
+        if seed == 4:  # heavy ties
+            t[:] = t[0]
+            q[:] = t[0]
+        nodes_q = eaof.csr_from_nodes(random_nodes(nq, 3, seed) if seed % 2 else np.zeros(nq, int))
+        nodes_t = eaof.csr_from_nodes(random_nodes(nt, 3, seed + 9) if seed % 2 else np.zeros(nt, int))
+        rng = np.random.Generator(np.random.PCG64(seed))
+        vq = (rng.random(nq) > 0.1).astype(np.uint8)
+        vt = (rng.random(nt) > 0.1).astype(np.uint8)
+        got = po.o_search_by_bow(mode, ratio, ori, q, aq, vq, nodes_q, t, at, vt, nodes_t)
+        exp = _py_bow(mode, ratio, ori, q, aq, vq, nodes_q, t, at, vt, nodes_t)
+        assert got[0] == exp[0] and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+
+
+def test_matcher_oracle_grid_vs_python():
+    from oracle import pyoracle as po
+    rng = np.random.Generator(np.random.PCG64(4))
+    x = rng.uniform(-5, 645, 800).astype(np.float32)
+    y = rng.uniform(-5, 485, 800).astype(np.float32)
+    iw, ih = np.float32(64) / np.float32(640), np.float32(48) / np.float32(480)
+    cs, ci = po.o_build_grid(x, y, 0.0, 0.0, iw, ih)
+    cells = [[] for _ in range(64 * 48)]
+    for i in range(800):
+        vx, vy = np.float32(x[i] * iw), np.float32(y[i] * ih)
+        px = int(np.floor(abs(vx) + np.float32(0.5)) * np.sign(vx))
+        py = int(np.floor(abs(vy) + np.float32(0.5)) * np.sign(vy))
+        if 0 <= px < 64 and 0 <= py < 48:
+            cells[px * 48 + py].append(i)
+    flat = [i for c in cells for i in c]
+    assert list(ci) == flat
+    assert list(cs[:-1]) == list(np.cumsum([0] + [len(c) for c in cells])[:-1])
