@@ -32,6 +32,8 @@ import numpy as np  # noqa: E402
 
 W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
 SEQ_LEN = 1000
+MATCH_TH = 15.0          # TrackWithMotionModel's window, src/Tracking.cc:1749-1753
+SHIFT = (-2.0, -1.0)     # the synthetic sequence drifts by (2,1) px per frame (eaof/synth.py)
 METRIC = "ORB frames/s (pyramid+FAST+octree+rBRIEF) @640x480/1000kp"
 
 
@@ -109,15 +111,38 @@ def make_sequence(n):
     return synth.make_frames(n, W, H, tex=tex)
 
 
+def cpu_matcher_seconds_per_pair(frames, n_pairs=6):
+    """Oracle port of SearchByProjection(Cur,Last) (src/ORBmatcher.cc:1328-1472) on one host thread."""
+    from oracle import pyoracle as po
+    ref = po.RefExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, canonical=False)
+    feats = [ref.extract(frames[i]) for i in range(n_pairs + 1)]
+    sf = ref.tables()["scale"]
+    bounds = (0.0, float(W), 0.0, float(H))
+    ginv = (np.float32(64) / np.float32(W), np.float32(48) / np.float32(H))
+    t0 = time.perf_counter()
+    for i in range(1, n_pairs + 1):
+        (ck, cd), (lk, ld) = feats[i], feats[i - 1]
+        cur = dict(x=ck["x"], y=ck["y"], octave=ck["octave"], angle=ck["angle"], desc=cd)
+        last = dict(u=lk["x"] - np.float32(2), v=lk["y"] - np.float32(1), octave=lk["octave"], angle=lk["angle"], desc=ld)
+        po.o_search_by_projection(cur, last, MATCH_TH, True, bounds=bounds, grid_inv=ginv, scale_factors=sf)
+    return (time.perf_counter() - t0) / n_pairs
+
+
 def cpu_baseline_run(frames, cores, seconds_target=8.0):
-    """Reference ORBextractor.cc (oracle/_ref) on host cores: frame-parallel, one extractor instance per thread."""
+    """Reference ORBextractor.cc (oracle/_ref) on host cores, frame-parallel with one extractor instance per thread,
+    plus the oracle port of the projection matcher (timed on one thread, credited with perfect scaling over cores)."""
     from oracle import pyoracle as po
     n = min(len(frames), max(cores * 2, 8))
     sample = frames[:n]
     secs, _ = po.ref_bench(sample, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, repeat=1)
     rep = max(1, int(seconds_target / max(secs, 1e-3)))
     secs, _ = po.ref_bench(sample, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, repeat=rep)
-    return n * rep / secs, f"{n} frames x {rep} passes, frame-parallel on {cores} threads (one extractor per thread)"
+    t_extract = secs / (n * rep)                       # wall seconds per frame with all cores busy
+    t_match = cpu_matcher_seconds_per_pair(frames) / cores
+    return 1.0 / (t_extract + t_match), (f"extraction: {n} frames x {rep} passes, frame-parallel on {cores} threads, unmodified "
+                                         f"reference ORBextractor.cc + cv shim ({1.0 / t_extract:.0f} frames/s); matching: oracle "
+                                         f"port on 1 thread over 6 pairs ({t_match * cores * 1e3:.2f} ms/pair), credited with "
+                                         f"perfect {cores}-core scaling")
 
 
 def run_reference_arm(args, rank):
@@ -129,10 +154,11 @@ def run_reference_arm(args, rank):
     from oracle import pyoracle as po
     kind = "reference" if os.path.exists(po.REF_SO) else "port"
     times = []
+    t_match = cpu_matcher_seconds_per_pair(frames) / cores
     for i in range(args.warmup + args.steps):
         secs, _ = po.ref_bench(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, repeat=1)
         if i >= args.warmup:
-            times.append(secs)
+            times.append(secs + t_match * n)
     tot = sum(times)
     val = n * len(times) / tot
     line = {
@@ -141,7 +167,8 @@ def run_reference_arm(args, rank):
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"synthetic 640x480 sequence, nfeatures=1000, 8 levels, 1.2, 20/7; step = {n} frames on the host CPU"},
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{n} frames per step, frame-parallel on {cores} threads, unmodified reference ORBextractor.cc + cv shim"},
+                         "sample": f"{n} frames per step, frame-parallel on {cores} threads, unmodified reference ORBextractor.cc + cv shim; "
+                                   f"projection matching by the oracle port ({t_match * cores * 1e3:.2f} ms/pair on 1 thread, credited /{cores})"},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -185,10 +212,21 @@ def main():
     ex = eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=B, device=local_rank)
     level_sizes = [ex.level_size(l) for l in range(NLEVELS)]
     frame_bytes = W * H
+    cap = ex.cap
+    mt = eaof.ORBmatcher(0.9, True, max_features=cap, max_pairs=B, device=local_rank)
+    n_pairs = B - 1
+    pair_last, pair_cur = np.arange(0, B - 1, dtype=np.int32), np.arange(1, B, dtype=np.int32)
+    shift_x, shift_y = np.full(n_pairs, SHIFT[0], np.float32), np.full(n_pairs, SHIFT[1], np.float32)
+    d_match = torch.empty((n_pairs, cap), dtype=torch.int32, device="cuda")
+    d_dist = torch.empty((n_pairs, cap), dtype=torch.int32, device="cuda")
+    d_nm = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
 
     def dev_step(i):
         b = i % n_batches
         ex.extract_batch_device(d_frames.data_ptr() + b * B * frame_bytes, B)
+        # consecutive-frame SearchByProjection over the keypoints that just landed in HBM (waits on the extractor stream)
+        mt.projection_batch_device(ex, pair_last, pair_cur, shift_x, shift_y, MATCH_TH, d_match.data_ptr(),
+                                   d_dist.data_ptr(), d_nm.data_ptr())
 
     def barrier():
         if world > 1:
@@ -198,20 +236,24 @@ def main():
     for i in range(args.warmup):
         dev_step(i)
     ex.sync()
+    mt.sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
     # device timing: CUDA events recorded on the stream the kernels are launched on (the handle's own stream)
     xs = torch.cuda.ExternalStream(ex.stream_ptr(), device=torch.device("cuda", local_rank))
+    ms = torch.cuda.ExternalStream(mt.stream_ptr(), device=torch.device("cuda", local_rank))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(xs)
     for i in range(args.steps):
         dev_step(i)
-    ev1.record(xs)
+    ev1.record(ms)  # the matcher stream finishes last (it waits on the extractor stream every step)
     ex.sync()
+    mt.sync()
     torch.cuda.synchronize()
     dt_wall = ev0.elapsed_time(ev1) * 1e-3
+    matches_per_pair = float(d_nm.float().mean().item())
     launches_per_step = ex.last_launch_count()
     counts = ex.fetch_counts(B)
     kp_per_frame = float(counts.mean())
@@ -221,17 +263,26 @@ def main():
     ex.set_profiling(True)
     stage_acc = {}
     nprof = min(args.steps, 8)
+    me0, me1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(nprof):
-        dev_step(i)
+        b = i % n_batches
+        ex.extract_batch_device(d_frames.data_ptr() + b * B * frame_bytes, B)
         ex.sync()
         for k, v in ex.stage_times().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v / nprof
+        me0.record(ms)
+        mt.projection_batch_device(ex, pair_last, pair_cur, shift_x, shift_y, MATCH_TH, d_match.data_ptr(),
+                                   d_dist.data_ptr(), d_nm.data_ptr())
+        me1.record(ms)
+        mt.sync()
+        stage_acc["match_projection"] = stage_acc.get("match_projection", 0.0) + me0.elapsed_time(me1) / nprof
     ex.set_profiling(False)
-    step_ms_dev = stage_acc["total"]
+    step_ms_dev = stage_acc["total"] + stage_acc["match_projection"]
 
     # e2e through the public API: pinned host frames in, keypoints + descriptors out
     h_frames = torch.from_numpy(frames[:B].copy()).pin_memory()
-    cap = ex.cap
+    h_match = torch.empty((n_pairs, cap), dtype=torch.int32).pin_memory()
+    h_nm = torch.empty((n_pairs,), dtype=torch.int32).pin_memory()
     h_kps = torch.empty((B, cap, 6), dtype=torch.float32).pin_memory()
     h_desc = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
     h_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
@@ -242,6 +293,12 @@ def main():
                                          h_desc.data_ptr(), cap, h_cnt.data_ptr())
         if rc != 0:
             raise RuntimeError(ex.L.eaof_last_error().decode())
+        mt.projection_batch_device(ex, pair_last, pair_cur, shift_x, shift_y, MATCH_TH, d_match.data_ptr(),
+                                   d_dist.data_ptr(), d_nm.data_ptr())
+        mt.sync()
+        h_match.copy_(d_match, non_blocking=True)
+        h_nm.copy_(d_nm, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -291,18 +348,26 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * dt_wall / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "configs[1]: 1000-frame synthetic 640x480 sequence, nfeatures=1000, nlevels=8, "
-                                   "scaleFactor=1.2, iniThFAST=20, minThFAST=7; batched extraction",
+                                   "scaleFactor=1.2, iniThFAST=20, minThFAST=7; batched extraction + consecutive-frame "
+                                   "SearchByProjection-style matching",
                        "frames_per_step_per_gpu": B, "keypoints_per_frame": kp_per_frame,
                        "l2_policy": "each step reads a different 77 MB batch and rewrites ~0.7 GB of pyramid/blur "
                                     "workspace: working set per step exceeds the 126 MB L2",
                        "parallelism": f"frame-sharded x{world}, no collective"},
             "device_ms_per_step_events": step_ms_dev,
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
-                    "d2h_bytes_per_step": B * (cap * 56 + 4)},
-            "gpu_launches": launches_per_step * args.steps,
+                    "d2h_bytes_per_step": B * (cap * 56 + 4) + n_pairs * (cap * 4 + 4)},
+            "gpu_launches": (launches_per_step + 4) * args.steps,
+            "matching": {"kind": "consecutive-frame SearchByProjection(Cur,Last), th=15, octave+-1, rot-hist on",
+                         "pairs_per_step_per_gpu": n_pairs, "matches_per_pair": matches_per_pair,
+                         "ms_per_step": stage_acc["match_projection"]},
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    # release everything torch holds on the library's streams before the handles (and their streams) go away
+    del xs, ms, ev0, ev1, me0, me1, h_frames, h_match, h_nm, h_kps, h_desc, h_cnt, d_match, d_dist, d_nm, d_frames
+    torch.cuda.synchronize()
+    mt.close()
     ex.close()
     if world > 1:
         dist.destroy_process_group()

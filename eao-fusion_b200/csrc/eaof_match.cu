@@ -45,7 +45,7 @@ int mfail(int code, const char* fmt, ...) {
 
 constexpr int GRID_COLS = 64, GRID_ROWS = 48, GRID_CELLS = GRID_COLS * GRID_ROWS;  // include/Frame.h:89-90
 constexpr int NEAR_K = 7;                                                          // near-list entries per query
-constexpr int TOP_K = 4;                                                           // projection: best candidates kept
+constexpr int TOP_K = 6;                                                           // projection: best candidates kept
 
 __device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) {
     int d = 0;
@@ -297,15 +297,12 @@ __global__ void __launch_bounds__(32) k_bow_resolve(BowArgs A, const uint32_t* _
                     best1 = g1; bestIdx = gIdx; best2 = sec;
                 }
                 if (bestIdx >= 0 && best1 <= A.thEff && (float)best1 < __fmul_rn(A.ratio, (float)best2)) {
-                    const int outIdx = A.mode == EAOF_BOW_KF_FRAME ? bestIdx : q;
-                    int bin = 0;
-                    if (A.checkOri) bin = rot_bin(angQ[q], angT[bestIdx], factor);
                     if (lane == 0) {
+                        const int outIdx = A.mode == EAOF_BOW_KF_FRAME ? bestIdx : q;
                         smem[bestIdx >> 5] |= 1u << (bestIdx & 31);
                         mOut[outIdx] = A.mode == EAOF_BOW_KF_FRAME ? q : bestIdx;
                         if (dOut) dOut[outIdx] = best1;
-                        acc[nAcc] = (uint32_t)outIdx | ((uint32_t)bin << 24);
-                        if (A.checkOri) hist[bin]++;
+                        acc[nAcc] = (uint32_t)q | ((uint32_t)bestIdx << 16);
                     }
                     ++nAcc;
                     __syncwarp();
@@ -314,16 +311,25 @@ __global__ void __launch_bounds__(32) k_bow_resolve(BowArgs A, const uint32_t* _
         }
     }
     __syncwarp();
+    // rotation histogram over the accepted matches (bins do not influence acceptance, so they are computed here, in
+    // parallel, instead of inside the sequential loop), ComputeThreeMaxima, pruning (:266-285)
     int removed = 0;
     if (A.checkOri) {
+        for (int k = lane; k < nAcc; k += 32) {
+            const uint32_t a = acc[k];
+            atomicAdd(&hist[rot_bin(angQ[a & 0xffff], angT[a >> 16], factor)], 1);
+        }
+        __syncwarp();
         int i1, i2, i3;
         three_maxima(hist, i1, i2, i3);
         for (int k = lane; k < nAcc; k += 32) {
             const uint32_t a = acc[k];
-            const int bin = (int)(a >> 24);
+            const int q = a & 0xffff, t = a >> 16;
+            const int bin = rot_bin(angQ[q], angT[t], factor);
             if (bin != i1 && bin != i2 && bin != i3) {
-                mOut[a & 0xffffff] = -1;
-                if (dOut) dOut[a & 0xffffff] = -1;
+                const int outIdx = A.mode == EAOF_BOW_KF_FRAME ? t : q;
+                mOut[outIdx] = -1;
+                if (dOut) dOut[outIdx] = -1;
                 ++removed;
             }
         }
@@ -477,6 +483,7 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
             const uint4 a = p[0], b = p[1];
             td[0] = a.x; td[1] = a.y; td[2] = a.z; td[3] = a.w; td[4] = b.x; td[5] = b.y; td[6] = b.z; td[7] = b.w;
             const uint32_t d = (uint32_t)hamming256(qd, td);
+            if (d > EAOF_TH_HIGH) return;  // can never be accepted (:1428), so it need not be kept, counted or re-scanned
             uint32_t e = (d << 16) | (uint32_t)k;
             // insertion into the sorted top-K by distance only; ties keep the earlier arrival in front
             bool shifting = false;  // once inserted, everything behind moves down one slot
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
         });
     }
     reinterpret_cast<uint4*>(o)[0] = make_uint4(top[0], top[1], top[2], top[3]);
-    reinterpret_cast<uint4*>(o)[1] = make_uint4(0, 0, 0, (uint32_t)count);
+    reinterpret_cast<uint4*>(o)[1] = make_uint4(top[4], top[5], 0, (uint32_t)count);
 }
 
 // phase 2: one warp per pair, Last features in index order
@@ -516,12 +523,14 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
     int nAcc = 0;
     for (int i0 = 0; i0 < nL; i0 += 32) {
         const int mine = i0 + lane;
-        uint4 w0 = make_uint4(0, 0, 0, 0);
-        int myCnt = 0;
+        uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
+        int myCnt = 0, myObs = 1;
         if (mine < nL) {
             const uint4* p = reinterpret_cast<const uint4*>(topBuf + (po + mine) * 8);
             w0 = p[0];
-            myCnt = (int)p[1].w;
+            w1 = p[1];
+            myCnt = (int)w1.w;
+            if (A.lobs) myObs = A.lobs[po + mine] != 0;
         }
         unsigned rem = __ballot_sync(0xffffffffu, myCnt > 0);
         while (rem) {
@@ -530,7 +539,8 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
             const int i = i0 + j;
             const int cnt = __shfl_sync(0xffffffffu, myCnt, j);
             const uint32_t e[TOP_K] = {__shfl_sync(0xffffffffu, w0.x, j), __shfl_sync(0xffffffffu, w0.y, j),
-                                       __shfl_sync(0xffffffffu, w0.z, j), __shfl_sync(0xffffffffu, w0.w, j)};
+                                       __shfl_sync(0xffffffffu, w0.z, j), __shfl_sync(0xffffffffu, w0.w, j),
+                                       __shfl_sync(0xffffffffu, w1.x, j), __shfl_sync(0xffffffffu, w1.y, j)};
             int bestDist = 256, bestIdx = -1;
 #pragma unroll
             for (int k = 0; k < TOP_K; ++k) {
@@ -565,18 +575,16 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
                     const int d = hamming256(qd, td);
                     if (d < bestDist) { bestDist = d; bestIdx = k; }
                 });
+                if (bestDist > EAOF_TH_HIGH) bestIdx = -1;
             }
             if (bestIdx >= 0 && bestDist <= EAOF_TH_HIGH) {  // :1428
-                int bin = 0;
-                if (A.checkOri) bin = rot_bin(A.langle[po + i], A.cangle[po + bestIdx], factor);
+                const int obs = __shfl_sync(0xffffffffu, myObs, j);
                 if (lane == 0) {
                     mOut[bestIdx] = i;
                     if (dOut) dOut[bestIdx] = bestDist;
-                    const bool obs = A.lobs ? A.lobs[po + i] != 0 : true;
                     if (obs) smem[bestIdx >> 5] |= 1u << (bestIdx & 31);
                     else smem[bestIdx >> 5] &= ~(1u << (bestIdx & 31));
-                    acc[nAcc] = (uint32_t)bestIdx | ((uint32_t)bin << 24);
-                    if (A.checkOri) hist[bin]++;
+                    acc[nAcc] = (uint32_t)i | ((uint32_t)bestIdx << 16);
                 }
                 ++nAcc;
                 __syncwarp();
@@ -584,16 +592,25 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
         }
     }
     __syncwarp();
+    // rotation histogram, ComputeThreeMaxima and pruning (:1448-1469), bins computed in parallel after the loop
     int removed = 0;
     if (A.checkOri) {
-        int i1, i2, i3;
-        three_maxima(hist, i1, i2, i3);
         for (int k = lane; k < nAcc; k += 32) {
             const uint32_t a = acc[k];
-            const int bin = (int)(a >> 24);
+            atomicAdd(&hist[rot_bin(A.langle[po + (a & 0xffff)], A.cangle[po + (a >> 16)], factor)], 1);
+        }
+        __syncwarp();
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        __syncwarp();
+        // rotHist[bin] lists Cur indices; an index overwritten by a later query (only possible when the earlier map
+        // point had no observations) can sit in two bins and is cleared if either is pruned, as in the reference
+        for (int k = lane; k < nAcc; k += 32) {
+            const uint32_t a = acc[k];
+            const int bin = rot_bin(A.langle[po + (a & 0xffff)], A.cangle[po + (a >> 16)], factor);
             if (bin != i1 && bin != i2 && bin != i3) {
-                mOut[a & 0xffffff] = -1;
-                if (dOut) dOut[a & 0xffffff] = -1;
+                mOut[a >> 16] = -1;
+                if (dOut) dOut[a >> 16] = -1;
                 ++removed;
             }
         }

@@ -163,60 +163,61 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ pyr, c
     if (tid == 0) { nList = 0; nOut = 0; }
     __syncthreads();
 
-    // A: OpenCV's early-out at the lower of the two thresholds, survivors compacted with a warp ballot
-    const int tq = min(g.iniTh, g.minTh);
+    // The cell is first searched at iniThFAST; only a cell with no keypoint after NMS is searched again at
+    // minThFAST (:808-816).  Each attempt: (A) OpenCV's early-out (every 9-arc contains one pixel of each opposite
+    // ring pair) at that threshold, survivors compacted with a warp ballot; (B) exact arc score of the survivors;
+    // (C) threshold + 8-neighbour NMS restricted to the cell.  Arc scores are threshold independent, so the map
+    // written by the first attempt stays valid for the second.
     const int npx = iw * ih;
-    for (int i0 = 0; i0 < npx; i0 += 256) {
-        const int i = i0 + tid;
-        bool pass = false;
-        int x = 0, y = 0;
-        if (i < npx) {
-            y = i / iw;
-            x = i - y * iw + 3;
-            y += 3;
-            const uint8_t* p = tile + y * FAST_TP + mis + x;
-            const int v = p[0], lo = v - tq, hi = v + tq;
-            int d = fast_cls(p[RING_OFF(0, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(8, FAST_TP)], lo, hi);
-            if (d) {
-                d &= fast_cls(p[RING_OFF(4, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(12, FAST_TP)], lo, hi);
-                d &= fast_cls(p[RING_OFF(2, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(10, FAST_TP)], lo, hi);
-                d &= fast_cls(p[RING_OFF(6, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(14, FAST_TP)], lo, hi);
-                if (d) {
-                    d &= fast_cls(p[RING_OFF(1, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(9, FAST_TP)], lo, hi);
-                    d &= fast_cls(p[RING_OFF(3, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(11, FAST_TP)], lo, hi);
-                    d &= fast_cls(p[RING_OFF(5, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(13, FAST_TP)], lo, hi);
-                    d &= fast_cls(p[RING_OFF(7, FAST_TP)], lo, hi) | fast_cls(p[RING_OFF(15, FAST_TP)], lo, hi);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int th = attempt == 0 ? g.iniTh : g.minTh;
+        if (attempt == 1) {
+            __syncthreads();
+            if (tid == 0) nList = 0;
+            __syncthreads();
+        }
+        for (int i0 = 0; i0 < npx; i0 += 256) {
+            const int i = i0 + tid;
+            bool pass = false;
+            int x = 0, y = 0;
+            if (i < npx) {
+                y = i / iw;
+                x = i - y * iw + 3;
+                y += 3;
+                const uint8_t* p = tile + y * FAST_TP + mis + x;
+                const int v = p[0], lo = v - th, hi = v + th;
+                int a = p[RING_OFF(0, FAST_TP)], b = p[RING_OFF(8, FAST_TP)];
+                bool dark = min(a, b) < lo, bright = max(a, b) > hi;
+                if (dark | bright) {
+#define FAST_PAIR(k)                                                  \
+    a = p[RING_OFF(k, FAST_TP)]; b = p[RING_OFF((k) + 8, FAST_TP)]; \
+    dark = dark && (min(a, b) < lo); bright = bright && (max(a, b) > hi);
+                    FAST_PAIR(4)
+                    if (dark | bright) {
+                        FAST_PAIR(2) FAST_PAIR(6)
+                        if (dark | bright) { FAST_PAIR(1) FAST_PAIR(3) FAST_PAIR(5) FAST_PAIR(7) }
+                    }
+#undef FAST_PAIR
                 }
+                pass = dark | bright;
             }
-            pass = d != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&nList, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) lst[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 8) | x);
+            }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&nList, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) lst[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 8) | x);
+        __syncthreads();
+        const int nl = nList;
+        if (nl == 0) continue;
+        for (int i = tid; i < nl; i += 256) {
+            const int yx = lst[i], y = yx >> 8, x = yx & 255;
+            const int b = arc_best(tile + y * FAST_TP + mis + x);
+            Bm[(y - 2) * 64 + (x - 2)] = (uint8_t)max(b, 0);
         }
-    }
-    __syncthreads();
-    const int nl = nList;
-    if (nl == 0) return;
-
-    // B: exact arc score of the survivors
-    for (int i = tid; i < nl; i += 256) {
-        const int yx = lst[i], y = yx >> 8, x = yx & 255;
-        const int b = arc_best(tile + y * FAST_TP + mis + x);
-        Bm[(y - 2) * 64 + (x - 2)] = (uint8_t)max(b, 0);
-    }
-    __syncthreads();
-
-#ifdef EAOF_DEBUG_FAST
-    for (int i = tid; i < 66 * FAST_TP; i += 256) g_dbgTile[i] = tile[i + (i / FAST_TP) * 0 + 0];
-    for (int i = tid; i < 4096; i += 256) g_dbgBm[i] = Bm[i];
-#endif
-    // C: threshold + 8-neighbour NMS inside the cell; retry with minThFAST if nothing survives (:808-816)
-    for (int pass = 0; pass < 2; ++pass) {
-        const int th = pass == 0 ? g.iniTh : g.minTh;
+        __syncthreads();
         for (int i = tid; i < nl; i += 256) {
             const int yx = lst[i], y = yx >> 8, x = yx & 255;
             const uint8_t* q = Bm + (y - 2) * 64 + (x - 2);
