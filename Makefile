@@ -9,19 +9,28 @@ LIB       := $(PKG)/lib/libeaof_orb.so
 SRCS      := $(PKG)/csrc/eaof_orb.cu $(wildcard $(PKG)/csrc/eaof_match.cu)
 HDRS      := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/eaof_orb.h
 
-all: $(LIB)
+DROPIN_T  := tests/cpp/_build/libdropin_harness.so
+
+all: $(LIB) $(DROPIN_T)
 
 $(LIB): $(SRCS) $(HDRS)
 	@mkdir -p $(PKG)/lib
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) 2> $(PKG)/lib/ptxas.log || (cat $(PKG)/lib/ptxas.log; exit 1)
 	@grep -E "registers|spill|error" $(PKG)/lib/ptxas.log | sed 's/^/  /' | head -60
 
+# the drop-in ORB_SLAM2::ORBextractor compiled against the cv shim (test harness; deployment compiles
+# $(PKG)/dropin/ORBextractor.cc against the real OpenCV)
+$(DROPIN_T): tests/cpp/dropin_harness.cc $(PKG)/dropin/ORBextractor.cc $(PKG)/dropin/ORBextractor.h include/eaof_orb.h $(LIB)
+	@mkdir -p tests/cpp/_build
+	g++ -O2 -std=c++14 -fPIC -shared -Wall -Wl,-Bsymbolic -Ioracle/cvshim -I$(PKG)/dropin -Iinclude \
+	    -o $@ tests/cpp/dropin_harness.cc $(PKG)/dropin/ORBextractor.cc -L$(PKG)/lib -leaof_orb -Wl,-rpath,'$$ORIGIN/../../../$(PKG)/lib'
+
 oracle:
 	$(MAKE) -C oracle
 	$(MAKE) -C oracle ref
 
 clean:
-	rm -f $(LIB) $(PKG)/lib/ptxas.log
+	rm -f $(LIB) $(PKG)/lib/ptxas.log $(DROPIN_T)
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

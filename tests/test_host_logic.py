@@ -238,3 +238,23 @@ def test_matcher_oracle_grid_vs_python():
     flat = [i for c in cells for i in c]
     assert list(ci) == flat
     assert list(cs[:-1]) == list(np.cumsum([0] + [len(c) for c in cells])[:-1])
+
+
+def test_dropin_class_loads_and_refuses_to_run_without_cuda():
+    """The drop-in ORB_SLAM2::ORBextractor answers its getters before any frame (host restatement of
+    src/ORBextractor.cc:415-433) and throws — never falls back to a CPU path — when no CUDA device exists."""
+    import numpy as np
+    import torch
+    from dropin import DropinExtractor
+    from oracle import pyoracle as po
+    d = DropinExtractor(1000, 1.2, 8, 20, 7)
+    t, r = d.tables(), po.o_tables(1000, 1.2, 8)
+    assert np.array_equal(t["scale"], r["scale"]) and np.array_equal(t["inv_sigma2"], r["inv_sigma2"])
+    n, rows, _, _ = d.extract(None, pre_n=3)  # empty image: silent return, outputs untouched (:1046-1047)
+    assert (n, rows) == (3, 3)
+    if not torch.cuda.is_available():
+        import ctypes as C
+        img = np.zeros((240, 320), np.uint8)
+        rc = d.L.dropin_extract(d.h, img.ctypes.data, 320, 240, 320, None, None, 0, 0, None)
+        assert rc == -2
+    d.close()
