@@ -48,14 +48,12 @@ struct eaof_orb {
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
     int kpCap = 0;
-    int nBlurTiles = 0;
     // device
     uint8_t* dIn = nullptr;      // staging for host-input calls: max_batch frames
     uint8_t* dPyr = nullptr;     // max_batch pyramid blocks
     uint8_t* dBlur = nullptr;    // same layout, blurred inner levels
     int* dTabs = nullptr;        // resize coefficient tables
     CellDesc* dCells = nullptr;
-    eaof::BlurTile* dTiles = nullptr;
     uint32_t* dCand = nullptr;
     uint16_t* dLabel = nullptr;
     uint32_t* dCandCount = nullptr;  // [batch][nlevels]
@@ -108,8 +106,7 @@ void build_tables(eaof_orb* c) {
     c->quota[n - 1] = c->p.nfeatures - sum > 0 ? c->p.nfeatures - sum : 0;
 }
 
-int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& cells,
-                   std::vector<eaof::BlurTile>& tiles) {
+int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& cells) {
     Geom& g = c->g;
     memset(&g, 0, sizeof g);
     g.nlevels = c->p.nlevels;
@@ -210,8 +207,8 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
         } else {
             L.yTab = L.xTab;
         }
-        for (int ty = 0; ty * BLUR_TH < L.h; ++ty)
-            for (int tx = 0; tx * BLUR_TW < L.w; ++tx) tiles.push_back(eaof::BlurTile{(short)l, (short)tx, (short)ty, 0});
+        L.blurTaskOff = g.blurTasksPerFrame;
+        g.blurTasksPerFrame += ((L.w + 3) / 4) * ((L.h + BLUR_ROWS - 1) / BLUR_ROWS);
         if (L.winW + 3 > 4095 || L.winH + 3 > 4095) return fail(EAOF_ERR_UNSUPPORTED, "frames larger than 4096 px are not supported");
     }
     g.pyrFrameBytes = off + 4096;  // slack: tile loaders may read a few bytes past the last row
@@ -243,7 +240,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     }
     if (prof) CK(cudaEventRecord(c->ev[1], s));
     if (g.cellsPerFrame > 0) {
-        eaof::k_fast<<<dim3(g.cellsPerFrame, n), 256, 0, s>>>(c->dPyr, c->dCells, c->dCand, c->dCandCount, g);
+        eaof::k_fast<<<dim3(g.cellsPerFrame, n), FAST_THREADS, 0, s>>>(c->dPyr, c->dCells, c->dCand, c->dCandCount, g);
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[2], s));
@@ -251,7 +248,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
                                                                          c->dSlotScore, c->dLvlCount, g);
     ++launches;
     if (prof) CK(cudaEventRecord(c->ev[3], s));
-    eaof::k_blur<<<dim3(c->nBlurTiles, n), 256, 0, s>>>(c->dPyr, c->dBlur, c->dTiles, g);
+    eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, s>>>(c->dPyr, c->dBlur, g);
     ++launches;
     if (prof) CK(cudaEventRecord(c->ev[4], s));
     {
@@ -305,12 +302,10 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     build_tables(c);
     std::vector<int> tabs;
     std::vector<CellDesc> cells;
-    std::vector<eaof::BlurTile> tiles;
-    int rc = build_geometry(c, tabs, cells, tiles);
+    int rc = build_geometry(c, tabs, cells);
     if (rc != EAOF_OK) { delete c; return rc; }
     const Geom& g = c->g;
     c->kpCap = g.slotsPerFrame;
-    c->nBlurTiles = (int)tiles.size();
     const size_t B = (size_t)p.max_batch;
 #define CKD(call)                                                                                       \
     do {                                                                                                \
@@ -327,7 +322,6 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     CKD(cudaMalloc(&c->dBlur, B * g.pyrFrameBytes));
     CKD(cudaMalloc(&c->dTabs, sizeof(int) * (tabs.size() + 4)));
     CKD(cudaMalloc(&c->dCells, sizeof(CellDesc) * (cells.size() + 1)));
-    CKD(cudaMalloc(&c->dTiles, sizeof(eaof::BlurTile) * (tiles.size() + 1)));
     CKD(cudaMalloc(&c->dCand, sizeof(uint32_t) * B * (size_t)(g.candPerFrame + 64)));
     CKD(cudaMalloc(&c->dLabel, sizeof(uint16_t) * B * (size_t)(g.candPerFrame + 64)));
     CKD(cudaMalloc(&c->dCandCount, sizeof(uint32_t) * B * g.nlevels));
@@ -342,7 +336,6 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     CKD(cudaMemset(c->dKpCount, 0, sizeof(int) * B));
     CKD(cudaMemcpy(c->dTabs, tabs.data(), sizeof(int) * tabs.size(), cudaMemcpyHostToDevice));
     if (!cells.empty()) CKD(cudaMemcpy(c->dCells, cells.data(), sizeof(CellDesc) * cells.size(), cudaMemcpyHostToDevice));
-    CKD(cudaMemcpy(c->dTiles, tiles.data(), sizeof(eaof::BlurTile) * tiles.size(), cudaMemcpyHostToDevice));
     CKD(cudaMemcpyToSymbol(eaof::d_pattern, kOrbPattern31, EAOF_ORB_PATTERN_INTS));
     CKD(cudaMallocHost(&c->hIn, B * (size_t)p.width * p.height));
     CKD(cudaMallocHost(&c->hKps, sizeof(eaof_kp) * B * c->kpCap));
@@ -375,7 +368,7 @@ void eaof_orb_destroy(eaof_orb* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->dIn); cudaFree(c->dPyr); cudaFree(c->dBlur); cudaFree(c->dTabs); cudaFree(c->dCells); cudaFree(c->dTiles);
+    cudaFree(c->dIn); cudaFree(c->dPyr); cudaFree(c->dBlur); cudaFree(c->dTabs); cudaFree(c->dCells);
     cudaFree(c->dCand); cudaFree(c->dLabel); cudaFree(c->dCandCount); cudaFree(c->dSlotXY); cudaFree(c->dSlotScore);
     cudaFree(c->dLvlCount); cudaFree(c->dKps); cudaFree(c->dDesc); cudaFree(c->dKpCount);
     cudaFreeHost(c->hIn); cudaFreeHost(c->hKps); cudaFreeHost(c->hDesc); cudaFreeHost(c->hKpCount);

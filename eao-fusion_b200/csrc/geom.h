@@ -29,6 +29,7 @@ struct LevelGeom {
     int xTab, yTab;      // offsets into the resize coefficient table (ints): [xofs | alpha] per column, [yofs | beta] per row
     float scale;         // mvScaleFactor[l]
     float kpSize;        // (float)(int)(31*scale)
+    int blurTaskOff;     // first blur task (column word x row chunk) of this level inside one frame
 };
 
 struct Geom {
@@ -39,6 +40,7 @@ struct Geom {
     int cellsPerFrame;
     int slotsPerFrame;    // sum of nodeCap
     int maxNodeCap;
+    int blurTasksPerFrame;
     uint32_t candPerFrame;
     uint64_t pyrFrameBytes;  // multiple of 256
     LevelGeom L[EAOF_MAX_LEVELS];

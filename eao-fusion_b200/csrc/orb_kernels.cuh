@@ -126,17 +126,47 @@ __device__ __forceinline__ int arc_best(const uint8_t* p) {
     return lo > hi ? lo : hi;
 }
 
-__device__ __forceinline__ int fast_cls(int a, int lo, int hi) { return (a < lo ? 1 : 0) | (a > hi ? 2 : 0); }
+// ---- packed s16x2 helpers: one 32-bit register carries the same quantity for two pixels, and VIMNMX(3).S16x2 /
+// VIADD.16x2 work on both halves in one issue slot.
+__device__ __forceinline__ unsigned evn(unsigned v) { return v & 0x00ff00ffu; }              // bytes 0,2 -> lanes
+__device__ __forceinline__ unsigned odd(unsigned v) { return __byte_perm(v, 0u, 0x4341); }   // bytes 1,3 -> lanes
+__device__ __forceinline__ unsigned neg2(unsigned v) { return __vadd2(~v, 0x00010001u); }
 
-// One CTA per cell.  Candidates are appended to the (frame, level) list in arbitrary order; DistributeOctTree
-// only needs their cell-raster rank for tie-breaking, which k_octree recomputes from the coordinates.
+// Arc score of two pixels at once.  d[k] = ring_k - centre on s16x2 lanes.  Returns max(bright, dark) where
+// bright = max over the 16 arcs of min(d over 9 contiguous), dark = max over arcs of min(-d) = -(min over arcs of
+// max(d)).  Sliding 9-window as min3 of three 3-windows (VIMNMX3).
+__device__ __forceinline__ unsigned arc_best2(const unsigned (&d)[16]) {
+    unsigned lo3[16], hi3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        lo3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        hi3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    }
+    unsigned best = 0x80008000u, worst = 0x7fff7fffu;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const unsigned a = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+        const unsigned b = __vimin3_s16x2(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
+        best = __vimax3_s16x2(best, a, b);
+        const unsigned c = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+        const unsigned e = __vimax3_s16x2(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
+        worst = __vimin3_s16x2(worst, c, e);
+    }
+    return __vmaxs2(best, neg2(worst));
+}
+
+// One CTA per cell, one thread per aligned 4-pixel word of the cell tile.  Candidates are appended to the
+// (frame, level) list in arbitrary order; DistributeOctTree only needs their cell-raster rank for tie-breaking,
+// which k_octree recomputes from the coordinates.
 // cand word: x | y<<12 | score<<24 (detection-window coordinates, src/ORBextractor.cc:822-824).
-__global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ pyr, const CellDesc* __restrict__ cells,
-                                              uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount,
-                                              const __grid_constant__ Geom g) {
-    __shared__ __align__(16) uint8_t tile[66 * FAST_TP];
-    __shared__ __align__(16) uint8_t Bm[64 * 64];  // arc score, 1-px zero apron: (x-2, y-2)
-    __shared__ uint16_t lst[3600];
+#define FAST_THREADS 128
+#define FAST_PW 19  // tile/score pitch in words: 1 pad word + up to 18 data words
+__global__ void __launch_bounds__(FAST_THREADS) k_fast(const uint8_t* __restrict__ pyr, const CellDesc* __restrict__ cells,
+                                                       uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount,
+                                                       const __grid_constant__ Geom g) {
+    __shared__ __align__(16) uint32_t tile[66 * FAST_PW + 6];  // pixel (row r, tile byte column c) at byte r*76 + 4 + c
+    __shared__ __align__(16) uint32_t Bm[66 * FAST_PW + 6];    // arc score (0 = not computed / not a corner), same layout
+    __shared__ uint16_t lst[60 * 17];
     __shared__ uint32_t outl[900];
     __shared__ int nList, nOut;
     __shared__ uint32_t gBase;
@@ -146,97 +176,143 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ pyr, c
     const LevelGeom& L = g.L[c.level];
     const int tid = threadIdx.x, lane = tid & 31;
     const int cw = c.cw, ch = c.ch;
-    const int iw = cw - 6, ih = ch - 6;
-    if (iw <= 0 || ih <= 0) return;
+    const int ih = ch - 6;
+    if (cw <= 6 || ih <= 0) return;
 
     const int col0 = EAOF_INNER_X0 + c.iniX;
-    const int mis = col0 & 3;
+    const int mis = col0 & 3;  // cell pixel x sits at tile byte column mis + x
     const uint8_t* src =
         pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + c.iniY) * L.pitch + (col0 - mis);
     const int nwords = (mis + cw + 3) >> 2;
-    for (int i = tid; i < ch * nwords; i += 256) {
-        const int r = i / nwords, w = i - r * nwords;
-        *reinterpret_cast<uint32_t*>(tile + r * FAST_TP + 4 * w) =
-            __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * L.pitch + 4 * w));
+    {
+        const unsigned rcp = 65536u / (unsigned)nwords + 1u;
+        for (int i = tid; i < ch * nwords; i += FAST_THREADS) {
+            const int r = (int)(((unsigned)i * rcp) >> 16), w = i - r * nwords;
+            tile[r * FAST_PW + 1 + w] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * L.pitch) + w);
+        }
     }
-    for (int i = tid; i < 64 * 64 / 4; i += 256) reinterpret_cast<uint32_t*>(Bm)[i] = 0;
+    for (int i = tid; i < (66 * FAST_PW + 6) / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) { nList = 0; nOut = 0; }
     __syncthreads();
 
+    // words holding at least one pixel of the cell's inner area x in [3, cw-3)
+    const int cLo = mis + 3, cHi = mis + cw - 4;  // first / last valid tile byte column
+    const int wLo = cLo >> 2, nW = (cHi >> 2) - wLo + 1;
+    const int nTasks = ih * nW;
+    const unsigned rcpW = 65536u / (unsigned)nW + 1u;
+
     // The cell is first searched at iniThFAST; only a cell with no keypoint after NMS is searched again at
-    // minThFAST (:808-816).  Each attempt: (A) OpenCV's early-out (every 9-arc contains one pixel of each opposite
-    // ring pair) at that threshold, survivors compacted with a warp ballot; (B) exact arc score of the survivors;
-    // (C) threshold + 8-neighbour NMS restricted to the cell.  Arc scores are threshold independent, so the map
-    // written by the first attempt stays valid for the second.
-    const int npx = iw * ih;
+    // minThFAST (:808-816).  Each attempt: (A) a necessary condition on the 4 compass ring pixels (every 9-arc
+    // contains two adjacent compass points) at that threshold for 4 pixels at once, surviving words compacted with a
+    // warp ballot; (B) exact arc score of the survivors, 2 pixels per s16x2 op; (C) threshold + 8-neighbour NMS
+    // restricted to the cell.  Arc scores are threshold independent, so the map written by the first attempt stays
+    // valid for the second.
     for (int attempt = 0; attempt < 2; ++attempt) {
         const int th = attempt == 0 ? g.iniTh : g.minTh;
+        const unsigned th2 = (unsigned)th | ((unsigned)th << 16);
         if (attempt == 1) {
             __syncthreads();
             if (tid == 0) nList = 0;
             __syncthreads();
         }
-        for (int i0 = 0; i0 < npx; i0 += 256) {
+        // ---- (A)
+        for (int i0 = 0; i0 < nTasks; i0 += FAST_THREADS) {
             const int i = i0 + tid;
             bool pass = false;
-            int x = 0, y = 0;
-            if (i < npx) {
-                y = i / iw;
-                x = i - y * iw + 3;
-                y += 3;
-                const uint8_t* p = tile + y * FAST_TP + mis + x;
-                const int v = p[0], lo = v - th, hi = v + th;
-                int a = p[RING_OFF(0, FAST_TP)], b = p[RING_OFF(8, FAST_TP)];
-                bool dark = min(a, b) < lo, bright = max(a, b) > hi;
-                if (dark | bright) {
-#define FAST_PAIR(k)                                                  \
-    a = p[RING_OFF(k, FAST_TP)]; b = p[RING_OFF((k) + 8, FAST_TP)]; \
-    dark = dark && (min(a, b) < lo); bright = bright && (max(a, b) > hi);
-                    FAST_PAIR(4)
-                    if (dark | bright) {
-                        FAST_PAIR(2) FAST_PAIR(6)
-                        if (dark | bright) { FAST_PAIR(1) FAST_PAIR(3) FAST_PAIR(5) FAST_PAIR(7) }
-                    }
-#undef FAST_PAIR
+            int y = 0, w = 0;
+            if (i < nTasks) {
+                const int r = (int)(((unsigned)i * rcpW) >> 16);
+                w = wLo + (i - r * nW);
+                y = r + 3;
+                const uint32_t* t = tile + y * FAST_PW + 1 + w;
+                const unsigned W0 = t[0], Wm = t[-1], Wp = t[1], Wu = t[-3 * FAST_PW], Wd = t[3 * FAST_PW];
+                const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
+                unsigned res = 0x80008000u;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned nc = neg2(h ? odd(W0) : evn(W0));
+                    const unsigned d0 = __vadd2(h ? odd(Wd) : evn(Wd), nc), d4 = __vadd2(h ? odd(V4) : evn(V4), nc);
+                    const unsigned d8 = __vadd2(h ? odd(Wu) : evn(Wu), nc), d12 = __vadd2(h ? odd(V12) : evn(V12), nc);
+                    const unsigned br = __vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8),
+                                                       __vmaxs2(__vmins2(d8, d12), __vmins2(d12, d0)));
+                    const unsigned dk = __vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8),
+                                                       __vmins2(__vmaxs2(d8, d12), __vmaxs2(d12, d0)));
+                    res = __vimax3_s16x2(res, br, neg2(dk));
                 }
-                pass = dark | bright;
+                pass = __vmaxs2(res, th2) != th2;  // some lane > th
             }
             const unsigned m = __ballot_sync(0xffffffffu, pass);
             if (m) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&nList, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) lst[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 8) | x);
+                if (pass) lst[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 8) | w);
             }
         }
         __syncthreads();
         const int nl = nList;
         if (nl == 0) continue;
-        for (int i = tid; i < nl; i += 256) {
-            const int yx = lst[i], y = yx >> 8, x = yx & 255;
-            const int b = arc_best(tile + y * FAST_TP + mis + x);
-            Bm[(y - 2) * 64 + (x - 2)] = (uint8_t)max(b, 0);
+        // ---- (B)
+        for (int i = tid; i < nl; i += FAST_THREADS) {
+            const int yw = lst[i], y = yw >> 8, w = yw & 255;
+            const uint32_t* t = tile + y * FAST_PW + 1 + w;
+            unsigned V[16];
+#define ROW3(dy, m, z, p) const unsigned m = t[(dy)*FAST_PW - 1], z = t[(dy)*FAST_PW], p = t[(dy)*FAST_PW + 1];
+            ROW3(3, a3m, a3z, a3p) ROW3(2, a2m, a2z, a2p) ROW3(1, a1m, a1z, a1p) ROW3(0, c0m, c0z, c0p)
+            ROW3(-1, b1m, b1z, b1p) ROW3(-2, b2m, b2z, b2p) ROW3(-3, b3m, b3z, b3p)
+#undef ROW3
+            V[0] = a3z;                          V[1] = __byte_perm(a3z, a3p, 0x4321);
+            V[2] = __byte_perm(a2z, a2p, 0x5432); V[3] = __byte_perm(a1z, a1p, 0x6543);
+            V[4] = __byte_perm(c0z, c0p, 0x6543); V[5] = __byte_perm(b1z, b1p, 0x6543);
+            V[6] = __byte_perm(b2z, b2p, 0x5432); V[7] = __byte_perm(b3z, b3p, 0x4321);
+            V[8] = b3z;                          V[9] = __byte_perm(b3m, b3z, 0x6543);
+            V[10] = __byte_perm(b2m, b2z, 0x5432); V[11] = __byte_perm(b1m, b1z, 0x4321);
+            V[12] = __byte_perm(c0m, c0z, 0x4321); V[13] = __byte_perm(a1m, a1z, 0x4321);
+            V[14] = __byte_perm(a2m, a2z, 0x5432); V[15] = __byte_perm(a3m, a3z, 0x6543);
+            unsigned d[16];
+            const unsigned ncE = neg2(evn(c0z)), ncO = neg2(odd(c0z));
+#pragma unroll
+            for (int k = 0; k < 16; ++k) d[k] = __vadd2(evn(V[k]), ncE);
+            const unsigned bE = __vmaxs2(arc_best2(d), 0u);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) d[k] = __vadd2(odd(V[k]), ncO);
+            const unsigned bO = __vmaxs2(arc_best2(d), 0u);
+            unsigned word = __byte_perm(bE, bO, 0x6240);  // scores of pixels 4w .. 4w+3 (each <= 255)
+            // pixels outside the inner area of the cell keep score 0 (cv::FAST never scores them)
+            const int cb = 4 * w;
+            unsigned mask = 0xffffffffu;
+            if (cb < cLo) mask <<= 8 * (cLo - cb);
+            if (cb + 3 > cHi) mask &= 0xffffffffu >> (8 * (cb + 3 - cHi));
+            Bm[y * FAST_PW + 1 + w] = word & mask;
         }
         __syncthreads();
-        for (int i = tid; i < nl; i += 256) {
-            const int yx = lst[i], y = yx >> 8, x = yx & 255;
-            const uint8_t* q = Bm + (y - 2) * 64 + (x - 2);
-            const int b = q[0];
-            if (b > th) {
-                const int s = b - 1;
-                bool keep = true;
+        // ---- (C)
+        for (int i = tid; i < nl; i += FAST_THREADS) {
+            const int yw = lst[i], y = yw >> 8, w = yw & 255;
+            const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * FAST_PW + 1 + w);
+            const unsigned word = *reinterpret_cast<const uint32_t*>(q0);
+            if (word == 0) continue;
 #pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
+            for (int j = 0; j < 4; ++j) {
+                const int b = (word >> (8 * j)) & 0xff;
+                if (b > th) {
+                    const uint8_t* q = q0 + j;
+                    const int s = b - 1;
+                    bool keep = true;
 #pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        if (dx == 0 && dy == 0) continue;
-                        const int nb = q[dy * 64 + dx];
-                        keep = keep && (s > (nb > th ? nb - 1 : 0));
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            if (dx == 0 && dy == 0) continue;
+                            const int nb = q[dy * (4 * FAST_PW) + dx];
+                            keep = keep && (s > (nb > th ? nb - 1 : 0));
+                        }
+                    if (keep) {
+                        const int o = atomicAdd(&nOut, 1);
+                        const int x = 4 * w + j - mis;  // cell coordinates
+                        const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
+                        outl[o] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
                     }
-                if (keep) {
-                    const int o = atomicAdd(&nOut, 1);
-                    const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
-                    outl[o] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
                 }
             }
         }
@@ -248,7 +324,7 @@ __global__ void __launch_bounds__(256) k_fast(const uint8_t* __restrict__ pyr, c
     if (tid == 0) gBase = atomicAdd(&candCount[f * g.nlevels + c.level], (uint32_t)no);
     __syncthreads();
     uint32_t* dst = cand + (size_t)f * g.candPerFrame + L.candOff + gBase;
-    for (int i = tid; i < no; i += 256) dst[i] = outl[i];
+    for (int i = tid; i < no; i += FAST_THREADS) dst[i] = outl[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -597,63 +673,80 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
 // ------------------------------------------------------------------------------------------------
 // Gaussian blur 7x7, sigma 2 on the inner level (borders come from the REFLECT_101 pyramid border, which is
 // what cv::GaussianBlur(BORDER_REFLECT_101) on the cloned ROI sees).  Integer arithmetic, SURVEY.md A.6.
-#define BLUR_TW 64
-#define BLUR_TH 32
-struct BlurTile { short level, tx, ty, pad; };
+// One thread per (column word, chunk of BLUR_ROWS rows): it walks down its 4 columns with the last seven
+// horizontally filtered rows in registers.  The horizontal pass runs on packed 16x2 lanes (the 7-tap sum of
+// bytes times 8-bit taps is <= 255*257 = 65535, so two pixels share a register and a plain IMAD never carries from
+// one lane into the other); the vertical pass needs 25 bits and runs per pixel.
+#define BLUR_ROWS 32
+#define BLUR_THREADS 128
 
-__global__ void __launch_bounds__(256) k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
-                                              const BlurTile* __restrict__ tiles, const __grid_constant__ Geom g) {
-    __shared__ __align__(16) uint8_t in[(BLUR_TH + 6) * (BLUR_TW + 8)];
-    __shared__ uint16_t hs[(BLUR_TH + 6) * BLUR_TW];
-    const BlurTile t = tiles[blockIdx.x];
+__global__ void __launch_bounds__(BLUR_THREADS) k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
+                                                       const __grid_constant__ Geom g) {
+    const int t = blockIdx.x * BLUR_THREADS + threadIdx.x;
+    if (t >= g.blurTasksPerFrame) return;
     const int f = blockIdx.y;
-    const LevelGeom& L = g.L[t.level];
-    const int x0 = t.tx * BLUR_TW, y0 = t.ty * BLUR_TH;
-    const int tid = threadIdx.x;
-    const uint8_t* base = pyr + (size_t)f * g.pyrFrameBytes + L.off;
-    // rows y0-3 .. y0+TH+2 (clamped to the bordered buffer), columns x0-4 .. x0+TW+3 as aligned words
-    constexpr int WPR = (BLUR_TW + 8) / 4;
-    for (int i = tid; i < (BLUR_TH + 6) * WPR; i += 256) {
-        const int r = i / WPR, w = i - r * WPR;
-        const int by = min(y0 - 3 + r + EAOF_EDGE, L.rows - 1);
-        int col = EAOF_INNER_X0 + x0 - 4 + 4 * w;
-        col = min(col, L.pitch - 4);
-        reinterpret_cast<uint32_t*>(in)[i] = __ldg(reinterpret_cast<const uint32_t*>(base + (size_t)by * L.pitch + col));
-    }
-    __syncthreads();
+    int l = 0;
+    while (l + 1 < g.nlevels && t >= g.L[l + 1].blurTaskOff) ++l;
+    const LevelGeom& L = g.L[l];
+    const int nCW = (L.w + 3) >> 2;
+    const int tt = t - L.blurTaskOff;
+    const int rc = tt / nCW, cwd = tt - rc * nCW;
+    const int x = 4 * cwd, y0 = rc * BLUR_ROWS;
     const bool cv4 = g.blurMode == 1;
     const int k0 = 18, k1 = 34, k2 = cv4 ? 48 : 49, k3 = cv4 ? 56 : 55;
-    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const uint8_t* p = in + r * (BLUR_TW + 8) + c + 1;  // p[0] = pixel x-3
-        const int s = k0 * (p[0] + p[6]) + k1 * (p[1] + p[5]) + k2 * (p[2] + p[4]) + k3 * p[3];
-        hs[i] = (uint16_t)s;  // <= 255*257 = 65535
-    }
-    __syncthreads();
     const int simdW = g.blurMode == 2 ? (L.w & ~3) : 0;
-    uint8_t* outBase = blur + (size_t)f * g.pyrFrameBytes + L.off + (size_t)EAOF_EDGE * L.pitch + EAOF_INNER_X0;
-    for (int i = tid; i < BLUR_TH * (BLUR_TW / 4); i += 256) {
-        const int r = i / (BLUR_TW / 4), c4 = (i - r * (BLUR_TW / 4)) * 4;
-        const int y = y0 + r, x = x0 + c4;
-        if (y >= L.h || x >= L.w) continue;
-        uint32_t v = 0;
+    const bool halfEven = x < simdW;  // simdW is a multiple of 4, so the whole word rounds the same way
+    const size_t lvl = (size_t)f * g.pyrFrameBytes + L.off;
+    const uint8_t* in = pyr + lvl + EAOF_INNER_X0 + x;         // word-aligned
+    uint8_t* out = blur + lvl + (size_t)EAOF_EDGE * L.pitch + EAOF_INNER_X0 + x;
+
+    int h0[7], h1[7], h2[7], h3[7];  // horizontally filtered rows y-3 .. y+3 of pixels x .. x+3
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint16_t* q = hs + r * BLUR_TW + c4 + j;
-            const int acc = k0 * ((int)q[0] + q[6 * BLUR_TW]) + k1 * ((int)q[BLUR_TW] + q[5 * BLUR_TW]) +
-                            k2 * ((int)q[2 * BLUR_TW] + q[4 * BLUR_TW]) + k3 * (int)q[3 * BLUR_TW];
-            int o;
-            if (x + j < simdW) {
-                o = acc >> 16;
-                const int rem = acc & 0xffff;
-                o += (rem > 32768) || (rem == 32768 && (o & 1));
-            } else {
-                o = (acc + 32768) >> 16;
+    for (int r = 0; r < BLUR_ROWS + 6; ++r) {
+        const int by = min(y0 + r - 3 + EAOF_EDGE, L.rows - 1);
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(in + (size_t)by * L.pitch);
+        const unsigned Wm = __ldg(p - 1), W0 = __ldg(p), Wp = __ldg(p + 1);
+        // E[i] = pixels (x-3+i, x-1+i) on 16x2 lanes; the odd-pixel pair of offset i is the even pair of offset i+1
+        unsigned E[8];
+        E[0] = evn(__byte_perm(Wm, W0, 0x4321));
+        E[1] = evn(__byte_perm(Wm, W0, 0x5432));
+        E[2] = evn(__byte_perm(Wm, W0, 0x6543));
+        E[3] = evn(W0);
+        E[4] = evn(__byte_perm(W0, Wp, 0x4321));
+        E[5] = evn(__byte_perm(W0, Wp, 0x5432));
+        E[6] = evn(__byte_perm(W0, Wp, 0x6543));
+        E[7] = evn(Wp);
+        const unsigned sE = k0 * (E[0] + E[6]) + k1 * (E[1] + E[5]) + k2 * (E[2] + E[4]) + k3 * E[3];  // pixels x, x+2
+        const unsigned sO = k0 * (E[1] + E[7]) + k1 * (E[2] + E[6]) + k2 * (E[3] + E[5]) + k3 * E[4];  // pixels x+1, x+3
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { h0[i] = h0[i + 1]; h1[i] = h1[i + 1]; h2[i] = h2[i + 1]; h3[i] = h3[i + 1]; }
+        h0[6] = (int)(sE & 0xffffu); h2[6] = (int)(sE >> 16);
+        h1[6] = (int)(sO & 0xffffu); h3[6] = (int)(sO >> 16);
+        if (r >= 6) {
+            const int y = y0 + r - 6;
+            if (y < L.h) {
+                int a[4];
+                a[0] = k0 * (h0[0] + h0[6]) + k1 * (h0[1] + h0[5]) + k2 * (h0[2] + h0[4]) + k3 * h0[3];
+                a[1] = k0 * (h1[0] + h1[6]) + k1 * (h1[1] + h1[5]) + k2 * (h1[2] + h1[4]) + k3 * h1[3];
+                a[2] = k0 * (h2[0] + h2[6]) + k1 * (h2[1] + h2[5]) + k2 * (h2[2] + h2[4]) + k3 * h2[3];
+                a[3] = k0 * (h3[0] + h3[6]) + k1 * (h3[1] + h3[5]) + k2 * (h3[2] + h3[4]) + k3 * h3[3];
+                uint32_t v = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int o;
+                    if (halfEven) {
+                        o = a[j] >> 16;
+                        const int rem = a[j] & 0xffff;
+                        o += (rem > 32768) || (rem == 32768 && (o & 1));
+                    } else {
+                        o = (a[j] + 32768) >> 16;
+                    }
+                    v |= (uint32_t)min(o, 255) << (8 * j);
+                }
+                // the padded row always has room for a full word (pitch >= w + 64)
+                *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch) = v;
             }
-            v |= (uint32_t)min(o, 255) << (8 * j);
         }
-        // the padded row always has room for a full word (pitch >= w + 64)
-        *reinterpret_cast<uint32_t*>(outBase + (size_t)y * L.pitch + x) = v;
     }
 }
 
