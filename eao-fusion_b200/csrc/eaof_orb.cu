@@ -234,8 +234,13 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     }
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& L = g.L[l];
-        dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
-        eaof::k_resize<<<gr, b, 0, s>>>(c->dPyr, c->dTabs, g, l);
+        if (L.h >= 40) {
+            const int tasks = ((L.w + 43) / 4) * ((L.h + RSZ_ROWS - 1) / RSZ_ROWS);
+            eaof::k_resize<<<dim3((tasks + RSZ_THREADS - 1) / RSZ_THREADS, n), RSZ_THREADS, 0, s>>>(c->dPyr, c->dTabs, g, l);
+        } else {  // tiny levels: border rows may fold more than once
+            dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
+            eaof::k_resize_generic<<<gr, b, 0, s>>>(c->dPyr, c->dTabs, g, l);
+        }
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[1], s));

@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256) k_level0(const uint8_t* __restrict__ in, 
 // cv::resize 8UC1 INTER_LINEAR with 11-bit fixed-point coefficients; the border pixel at
 // bordered position (bx,by) equals the resized pixel at the reflected inner position, so resize and
 // copyMakeBorder are one pass.  tabs: per destination column [sx, a0|a1<<16], per row [sy, b0|b1<<16].
-__global__ void __launch_bounds__(256) k_resize(uint8_t* __restrict__ pyr, const int* __restrict__ tabs,
-                                                const __grid_constant__ Geom g, int l) {
+__global__ void __launch_bounds__(256) k_resize_generic(uint8_t* __restrict__ pyr, const int* __restrict__ tabs,
+                                                        const __grid_constant__ Geom g, int l) {
     const LevelGeom& D = g.L[l];
     const LevelGeom& S = g.L[l - 1];
     const int wi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,6 +86,80 @@ __global__ void __launch_bounds__(256) k_resize(uint8_t* __restrict__ pyr, const
         v |= (uint32_t)(d & 0xff) << (8 * j);
     }
     *reinterpret_cast<uint32_t*>(frame + D.off + (size_t)by * D.pitch + c0) = v;
+}
+
+// Same arithmetic, organised for throughput (levels with at least 40 rows): one thread owns 4 bordered columns —
+// their source word offsets, byte selectors and packed (a0, a1) coefficients are per-thread constants — and walks
+// down RSZ_ROWS inner rows.  A horizontal pass of one source row is 4 x (2 word loads + PRMT + IDP.2A); the lower
+// source row of one output row is usually the upper row of the next, so it is kept.  Rows that the REFLECT_101
+// border mirrors (inner rows 1..19 and h-20..h-2) are stored twice.
+#define RSZ_ROWS 32
+#define RSZ_THREADS 128
+__global__ void __launch_bounds__(RSZ_THREADS) k_resize(uint8_t* __restrict__ pyr, const int* __restrict__ tabs,
+                                                        const __grid_constant__ Geom g, int l) {
+    const LevelGeom& D = g.L[l];
+    const LevelGeom& S = g.L[l - 1];
+    const int nCW = (D.w + 43) >> 2;
+    const int t = blockIdx.x * RSZ_THREADS + threadIdx.x;
+    const int rc = t / nCW, cwd = t - rc * nCW;
+    const int y0 = rc * RSZ_ROWS;
+    if (y0 >= D.h) return;
+    const int f = blockIdx.y;
+    uint8_t* frame = pyr + (size_t)f * g.pyrFrameBytes;
+    const int c0 = 12 + 4 * cwd;
+    int wofs[4];
+    unsigned sel[4], coef[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = reflect101(c0 - EAOF_INNER_X0 + j, D.w);
+        const int sx = tabs[D.xTab + 2 * x];
+        coef[j] = (unsigned)tabs[D.xTab + 2 * x + 1];
+        wofs[j] = sx >> 2;
+        sel[j] = (unsigned)(sx & 3) | ((unsigned)((sx & 3) + 1) << 4);  // bytes sx, sx+1 of the word pair; a1 == 0
+    }                                                                    // whenever sx+1 would leave the image
+    const uint32_t* sIn = reinterpret_cast<const uint32_t*>(frame + S.off + (size_t)EAOF_EDGE * S.pitch + EAOF_INNER_X0);
+    const int sPitchW = S.pitch >> 2;
+    uint8_t* dOut = frame + D.off + c0;
+    int cached = -1;
+    unsigned hB[4] = {0, 0, 0, 0};
+    auto hrow = [&](int sy, unsigned (&h)[4]) {
+        const uint32_t* r = sIn + sy * sPitchW;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned lo = __ldg(r + wofs[j]), hi = __ldg(r + wofs[j] + 1);
+            h[j] = __dp2a_lo(coef[j], __byte_perm(lo, hi, sel[j]), 0u);
+        }
+    };
+    const int yEnd = min(y0 + RSZ_ROWS, D.h);
+    for (int y = y0; y < yEnd; ++y) {
+        const int sy = __ldg(tabs + D.yTab + 2 * y);
+        const int bb = __ldg(tabs + D.yTab + 2 * y + 1);
+        const int b0 = (short)(bb & 0xffff), b1 = bb >> 16;
+        const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
+        unsigned hA[4];
+        if (sy0 == cached) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hA[j] = hB[j];
+        } else {
+            hrow(sy0, hA);
+        }
+        if (sy1 != sy0) hrow(sy1, hB);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hB[j] = hA[j];
+        }
+        cached = sy1;
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = (((b0 * (int)(hA[j] >> 4)) >> 16) + ((b1 * (int)(hB[j] >> 4)) >> 16) + 2) >> 2;
+            v |= (uint32_t)(d & 0xff) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(dOut + (size_t)(y + EAOF_EDGE) * D.pitch) = v;
+        if (y >= 1 && y <= EAOF_EDGE) *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE - y) * D.pitch) = v;
+        if (y >= D.h - 1 - EAOF_EDGE && y <= D.h - 2)
+            *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE + 2 * (D.h - 1) - y) * D.pitch) = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -167,8 +241,10 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const uint8_t* __restrict
     __shared__ __align__(16) uint32_t tile[66 * FAST_PW + 6];  // pixel (row r, tile byte column c) at byte r*76 + 4 + c
     __shared__ __align__(16) uint32_t Bm[66 * FAST_PW + 6];    // arc score (0 = not computed / not a corner), same layout
     __shared__ uint16_t lst[60 * 17];
-    __shared__ uint32_t outl[900];
     __shared__ int nList, nOut;
+    // NMS survivors (<= 30*30) overwrite the tile: the first one is written only when the attempt that produced it is
+    // the last one, and phase (C) reads nothing but the score map.
+    uint32_t* outl = tile;
     __shared__ uint32_t gBase;
 
     const CellDesc c = cells[blockIdx.x];
@@ -186,9 +262,11 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const uint8_t* __restrict
     const int nwords = (mis + cw + 3) >> 2;
     {
         const unsigned rcp = 65536u / (unsigned)nwords + 1u;
+        const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
+        const int pitchW = L.pitch >> 2;
         for (int i = tid; i < ch * nwords; i += FAST_THREADS) {
             const int r = (int)(((unsigned)i * rcp) >> 16), w = i - r * nwords;
-            tile[r * FAST_PW + 1 + w] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)r * L.pitch) + w);
+            tile[r * FAST_PW + 1 + w] = __ldg(src32 + (r * pitchW + w));
         }
     }
     for (int i = tid; i < (66 * FAST_PW + 6) / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
@@ -277,7 +355,11 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const uint8_t* __restrict
 #pragma unroll
             for (int k = 0; k < 16; ++k) d[k] = __vadd2(odd(V[k]), ncO);
             const unsigned bO = __vmaxs2(arc_best2(d), 0u);
-            unsigned word = __byte_perm(bE, bO, 0x6240);  // scores of pixels 4w .. 4w+3 (each <= 255)
+            // lanes that are not corners at this threshold store 0: the NMS only ever asks "corner ? score : 0"
+            const unsigned kE = __vmaxs2(bE, th2) ^ th2, kO = __vmaxs2(bO, th2) ^ th2;  // lane != 0  <=>  b > th
+            const unsigned mE = ((kE & 0xffffu) ? 0xffffu : 0u) | ((kE >> 16) ? 0xffff0000u : 0u);
+            const unsigned mO = ((kO & 0xffffu) ? 0xffffu : 0u) | ((kO >> 16) ? 0xffff0000u : 0u);
+            unsigned word = __byte_perm(bE & mE, bO & mO, 0x6240);  // scores of pixels 4w .. 4w+3 (each <= 255)
             // pixels outside the inner area of the cell keep score 0 (cv::FAST never scores them)
             const int cb = 4 * w;
             unsigned mask = 0xffffffffu;
@@ -290,29 +372,25 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast(const uint8_t* __restrict
         for (int i = tid; i < nl; i += FAST_THREADS) {
             const int yw = lst[i], y = yw >> 8, w = yw & 255;
             const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * FAST_PW + 1 + w);
-            const unsigned word = *reinterpret_cast<const uint32_t*>(q0);
-            if (word == 0) continue;
+            unsigned word = *reinterpret_cast<const uint32_t*>(q0);
+            while (word) {
+                const int j = (__ffs(word) - 1) >> 3;
+                const int s = (int)((word >> (8 * j)) & 0xff) - 1;
+                word &= ~(0xffu << (8 * j));
+                const uint8_t* q = q0 + j;
+                int nbMax = 0;  // stored scores are either 0 or > th
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = (word >> (8 * j)) & 0xff;
-                if (b > th) {
-                    const uint8_t* q = q0 + j;
-                    const int s = b - 1;
-                    bool keep = true;
+                for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            if (dx == 0 && dy == 0) continue;
-                            const int nb = q[dy * (4 * FAST_PW) + dx];
-                            keep = keep && (s > (nb > th ? nb - 1 : 0));
-                        }
-                    if (keep) {
-                        const int o = atomicAdd(&nOut, 1);
-                        const int x = 4 * w + j - mis;  // cell coordinates
-                        const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
-                        outl[o] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dx == 0 && dy == 0) continue;
+                        nbMax = max(nbMax, (int)q[dy * (4 * FAST_PW) + dx]);
                     }
+                if (s > (nbMax > 0 ? nbMax - 1 : 0)) {  // s > (neighbour is a corner ? its score : 0) for all 8
+                    const int o = atomicAdd(&nOut, 1);
+                    const int x = 4 * w + j - mis;  // cell coordinates
+                    const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
+                    outl[o] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
                 }
             }
         }
