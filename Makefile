@@ -3,7 +3,7 @@
 #   make oracle     -> oracle/liborb_oracle.so (+ oracle/_ref/liborb_ref.so when /root/reference is present)
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 --fmad=false -Xcompiler -fPIC,-Wall -Xptxas -v
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 --fmad=false -Xcompiler -fPIC,-Wall -Xptxas -v $(EXTRA)
 PKG       := eao-fusion_b200
 LIB       := $(PKG)/lib/libeaof_orb.so
 SRCS      := $(PKG)/csrc/eaof_orb.cu $(wildcard $(PKG)/csrc/eaof_match.cu)

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -53,6 +54,7 @@ struct eaof_orb {
     uint8_t* dPyr = nullptr;     // max_batch pyramid blocks
     uint8_t* dBlur = nullptr;    // same layout, blurred inner levels
     int* dTabs = nullptr;        // resize coefficient tables
+    uint2* dAngleTab = nullptr;  // IC_Angle weights: [alignment 0..3][row*9 + word] = (u weights, v weights) as s8x4
     CellDesc* dCells = nullptr;
     uint32_t* dCand = nullptr;
     uint16_t* dLabel = nullptr;
@@ -118,6 +120,7 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
     uint64_t off = 0;
     uint32_t candOff = 0;
     int slotOff = 0;
+    int fastRows = 7, fastWords = 2, fastList = 2, fastOut = 1;
     for (int l = 0; l < g.nlevels; ++l) {
         LevelGeom& L = g.L[l];
         L.w = cv_round_f((float)g.W * c->invScale[l]);  // :1112
@@ -174,6 +177,16 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
                 if (cw < 7 || ch < 7) continue;  // cv::FAST finds nothing in fewer than 7 rows/cols
                 if (cw > 66 || ch > 66) return fail(EAOF_ERR_UNSUPPORTED, "cell larger than 66 px");
                 cells.push_back(CellDesc{(short)l, (short)iniX, (short)iniY, (short)cw, (short)ch, 0});
+                {
+                    // k_fast shared-memory extents: tile rows/words, pair-list entries, NMS survivors
+                    const int mis = (EAOF_INNER_X0 + iniX) & 3;
+                    const int nwords = (mis + cw + 3) >> 2;
+                    const int nW = ((mis + cw - 4) >> 2) - ((mis + 3) >> 2) + 1;
+                    fastRows = std::max(fastRows, ch);
+                    fastWords = std::max(fastWords, nwords);
+                    fastList = std::max(fastList, 2 * (ch - 6) * nW);
+                    fastOut = std::max(fastOut, ((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2));
+                }
                 cap += (uint32_t)(((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2));  // NMS keeps no two 8-adjacent pixels
             }
         }
@@ -211,6 +224,10 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
         g.blurTasksPerFrame += ((L.w + 3) / 4) * ((L.h + BLUR_ROWS - 1) / BLUR_ROWS);
         if (L.winW + 3 > 4095 || L.winH + 3 > 4095) return fail(EAOF_ERR_UNSUPPORTED, "frames larger than 4096 px are not supported");
     }
+    g.fastPW = (fastWords + 2) | 1;  // one pad word on the left, one spare on the right (phase A reads word w+1), odd pitch
+    g.fastMapWords = std::max(fastRows * g.fastPW + 2, fastOut);
+    g.fastMapWords = (g.fastMapWords + 3) & ~3;
+    g.fastWarpWords = (2 * g.fastMapWords + (fastList + 1) / 2 + 3) & ~3;
     g.pyrFrameBytes = off + 4096;  // slack: tile loaders may read a few bytes past the last row
     g.candPerFrame = candOff;
     g.slotsPerFrame = slotOff;
@@ -245,7 +262,9 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     }
     if (prof) CK(cudaEventRecord(c->ev[1], s));
     if (g.cellsPerFrame > 0) {
-        eaof::k_fast<<<dim3(g.cellsPerFrame, n), FAST_THREADS, 0, s>>>(c->dPyr, c->dCells, c->dCand, c->dCandCount, g);
+        const size_t smem = (size_t)FAST_WARPS * g.fastWarpWords * 4;
+        eaof::k_fast<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
+            c->dPyr, c->dCells, c->dCand, c->dCandCount, g);
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[2], s));
@@ -260,7 +279,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         const int warpsPerBlock = 8;
         dim3 gr((g.slotsPerFrame + warpsPerBlock - 1) / warpsPerBlock, n);
         eaof::k_angle_desc<<<gr, warpsPerBlock * 32, 0, s>>>(c->dPyr, c->dBlur, c->dSlotXY, c->dSlotScore, c->dLvlCount,
-                                                             c->dKps, c->dDesc, c->dKpCount, c->kpCap, g);
+                                                             c->dAngleTab, c->dKps, c->dDesc, c->dKpCount, c->kpCap, g);
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[5], s));
@@ -327,6 +346,28 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     CKD(cudaMalloc(&c->dBlur, B * g.pyrFrameBytes));
     CKD(cudaMalloc(&c->dTabs, sizeof(int) * (tabs.size() + 4)));
     CKD(cudaMalloc(&c->dCells, sizeof(CellDesc) * (cells.size() + 1)));
+    {
+        // umax as the constructor derives it for HALF_PATCH_SIZE = 15 (src/ORBextractor.cc:454-469; the oracle
+        // checks these 16 values against the reference object), then the per-alignment DP4A weights
+        static const int umax[EAOF_HALF_PATCH + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        std::vector<uint2> at(4 * EAOF_ANGLE_TASKS_PAD, make_uint2(0, 0));
+        for (int a = 0; a < 4; ++a)
+            for (int r = 0; r < 31; ++r)
+                for (int j = 0; j < 9; ++j) {
+                    const int v = r - EAOF_HALF_PATCH;
+                    uint32_t uw = 0, vw = 0;
+                    for (int b = 0; b < 4; ++b) {
+                        const int u = 4 * j - a - EAOF_HALF_PATCH + b;
+                        if (abs(u) <= EAOF_HALF_PATCH && abs(u) <= umax[abs(v)]) {
+                            uw |= (uint32_t)(uint8_t)(int8_t)u << (8 * b);
+                            vw |= (uint32_t)(uint8_t)(int8_t)v << (8 * b);
+                        }
+                    }
+                    at[(size_t)a * EAOF_ANGLE_TASKS_PAD + r * 9 + j] = make_uint2(uw, vw);
+                }
+        CKD(cudaMalloc(&c->dAngleTab, sizeof(uint2) * at.size()));
+        CKD(cudaMemcpy(c->dAngleTab, at.data(), sizeof(uint2) * at.size(), cudaMemcpyHostToDevice));
+    }
     CKD(cudaMalloc(&c->dCand, sizeof(uint32_t) * B * (size_t)(g.candPerFrame + 64)));
     CKD(cudaMalloc(&c->dLabel, sizeof(uint16_t) * B * (size_t)(g.candPerFrame + 64)));
     CKD(cudaMalloc(&c->dCandCount, sizeof(uint32_t) * B * g.nlevels));
@@ -354,6 +395,14 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
         eaof_orb_destroy(c);
         return EAOF_ERR_UNSUPPORTED;
     }
+    // k_fast: a few KB of shared memory per warp — ask for the largest carve-out so that shared memory does not cap the
+    // resident warps below what the register file allows
+    cudaFuncSetAttribute(eaof::k_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if ((size_t)FAST_WARPS * g.fastWarpWords * 4 > 48 * 1024) {
+        static std::mutex muF;
+        std::lock_guard<std::mutex> lk(muF);
+        CKD(cudaFuncSetAttribute(eaof::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
     {
         // the attribute is per function, not per handle: only ever raise it (handles with different nfeatures coexist)
         static std::mutex mu;
@@ -373,7 +422,7 @@ void eaof_orb_destroy(eaof_orb* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->dIn); cudaFree(c->dPyr); cudaFree(c->dBlur); cudaFree(c->dTabs); cudaFree(c->dCells);
+    cudaFree(c->dIn); cudaFree(c->dPyr); cudaFree(c->dBlur); cudaFree(c->dTabs); cudaFree(c->dAngleTab); cudaFree(c->dCells);
     cudaFree(c->dCand); cudaFree(c->dLabel); cudaFree(c->dCandCount); cudaFree(c->dSlotXY); cudaFree(c->dSlotScore);
     cudaFree(c->dLvlCount); cudaFree(c->dKps); cudaFree(c->dDesc); cudaFree(c->dKpCount);
     cudaFreeHost(c->hIn); cudaFreeHost(c->hKps); cudaFreeHost(c->hDesc); cudaFreeHost(c->hKpCount);

@@ -41,6 +41,9 @@ struct Geom {
     int slotsPerFrame;    // sum of nodeCap
     int maxNodeCap;
     int blurTasksPerFrame;
+    int fastPW;           // k_fast: tile pitch in words (1 pad word + widest cell row), odd
+    int fastMapWords;     // k_fast: words of one tile / score map (multiple of 4)
+    int fastWarpWords;    // k_fast: shared-memory words per warp (tile + score map + pair list)
     uint32_t candPerFrame;
     uint64_t pyrFrameBytes;  // multiple of 256
     LevelGeom L[EAOF_MAX_LEVELS];

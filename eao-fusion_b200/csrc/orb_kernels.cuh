@@ -200,209 +200,240 @@ __device__ __forceinline__ int arc_best(const uint8_t* p) {
     return lo > hi ? lo : hi;
 }
 
-// ---- packed s16x2 helpers: one 32-bit register carries the same quantity for two pixels, and VIMNMX(3).S16x2 /
-// VIADD.16x2 work on both halves in one issue slot.
+// ---- packed 16x2 helpers: one 32-bit register carries the same quantity for two pixels, and VIMNMX(3).U16x2
+// works on both halves in one issue slot.  Differences ring - centre are kept biased by +256 (range 1..511) so that
+// they are formed by a plain 32-bit add (no borrow can cross the lanes) and compare as unsigned.
 __device__ __forceinline__ unsigned evn(unsigned v) { return v & 0x00ff00ffu; }              // bytes 0,2 -> lanes
 __device__ __forceinline__ unsigned odd(unsigned v) { return __byte_perm(v, 0u, 0x4341); }   // bytes 1,3 -> lanes
-__device__ __forceinline__ unsigned neg2(unsigned v) { return __vadd2(~v, 0x00010001u); }
+#define FAST_BIAS2 0x01000100u
 
-// Arc score of two pixels at once.  d[k] = ring_k - centre on s16x2 lanes.  Returns max(bright, dark) where
-// bright = max over the 16 arcs of min(d over 9 contiguous), dark = max over arcs of min(-d) = -(min over arcs of
-// max(d)).  Sliding 9-window as min3 of three 3-windows (VIMNMX3).
+// Arc score of two pixels at once.  d[k] = 256 + ring_k - centre on u16x2 lanes.  Returns 256 + max(bright, dark)
+// where bright = max over the 16 arcs of min(ring - centre over 9 contiguous) and dark = max over arcs of
+// min(centre - ring) = -(min over arcs of max(ring - centre)).  Sliding 9-window = min3 of three 3-windows.
 __device__ __forceinline__ unsigned arc_best2(const unsigned (&d)[16]) {
     unsigned lo3[16], hi3[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        lo3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        hi3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        lo3[k] = __vimin3_u16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        hi3[k] = __vimax3_u16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
     }
-    unsigned best = 0x80008000u, worst = 0x7fff7fffu;
+    unsigned best = 0u, worst = 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
-        const unsigned a = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
-        const unsigned b = __vimin3_s16x2(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
-        best = __vimax3_s16x2(best, a, b);
-        const unsigned c = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
-        const unsigned e = __vimax3_s16x2(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
-        worst = __vimin3_s16x2(worst, c, e);
+        const unsigned a = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+        const unsigned b = __vimin3_u16x2(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
+        best = __vimax3_u16x2(best, a, b);
+        const unsigned c = __vimax3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+        const unsigned e = __vimax3_u16x2(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
+        worst = __vimin3_u16x2(worst, c, e);
     }
-    return __vmaxs2(best, neg2(worst));
+    return __vmaxu2(best, 2u * FAST_BIAS2 - worst);  // worst <= 511 per lane: no borrow
 }
 
-// One CTA per cell, one thread per aligned 4-pixel word of the cell tile.  Candidates are appended to the
-// (frame, level) list in arbitrary order; DistributeOctTree only needs their cell-raster rank for tie-breaking,
-// which k_octree recomputes from the coordinates.
+// One WARP per cell (no CTA-wide barrier anywhere: the warps of a CTA only share the launch).  Candidates are
+// appended to the (frame, level) list in arbitrary order; DistributeOctTree only needs their cell-raster rank for
+// tie-breaking, which k_octree recomputes from the coordinates.
 // cand word: x | y<<12 | score<<24 (detection-window coordinates, src/ORBextractor.cc:822-824).
-#define FAST_THREADS 128
-#define FAST_PW 19  // tile/score pitch in words: 1 pad word + up to 18 data words
-__global__ void __launch_bounds__(FAST_THREADS) k_fast(const uint8_t* __restrict__ pyr, const CellDesc* __restrict__ cells,
-                                                       uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount,
-                                                       const __grid_constant__ Geom g) {
-    __shared__ __align__(16) uint32_t tile[66 * FAST_PW + 6];  // pixel (row r, tile byte column c) at byte r*76 + 4 + c
-    __shared__ __align__(16) uint32_t Bm[66 * FAST_PW + 6];    // arc score (0 = not computed / not a corner), same layout
-    __shared__ uint16_t lst[60 * 17];
-    __shared__ int nList, nOut;
-    // NMS survivors (<= 30*30) overwrite the tile: the first one is written only when the attempt that produced it is
-    // the last one, and phase (C) reads nothing but the score map.
+// Shared memory per warp (sized for the largest cell of the handle, Geom::fast*): the cell tile, the score map in
+// the same layout, and the list of surviving pixel pairs.
+#ifndef FAST_WARPS
+#define FAST_WARPS 4
+#endif
+#ifndef FAST_MINB
+#define FAST_MINB 8
+#endif
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8_t* __restrict__ pyr,
+                                                                     const CellDesc* __restrict__ cells,
+                                                                     uint32_t* __restrict__ cand,
+                                                                     uint32_t* __restrict__ candCount,
+                                                                     const __grid_constant__ Geom g) {
+    extern __shared__ __align__(16) uint32_t fastSmem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cell = blockIdx.x * FAST_WARPS + warp;
+    if (cell >= g.cellsPerFrame) return;
+    const int PW = g.fastPW;                     // tile / score pitch in words: 1 pad word + data words
+    const int mapWords = g.fastMapWords;         // multiple of 4
+    uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;  // pixel (row r, tile byte column c) at byte (r*PW + 1)*4 + c
+    uint32_t* Bm = tile + mapWords;              // arc score of corners (0 elsewhere), same layout
+    uint16_t* lst = reinterpret_cast<uint16_t*>(Bm + mapWords);  // surviving (row, word, even/odd pixel pair)
+    // NMS survivors overwrite the tile: the first one is written only when the attempt that produced it is the last
+    // one, and phase (C) reads nothing but the score map.
     uint32_t* outl = tile;
-    __shared__ uint32_t gBase;
 
-    const CellDesc c = cells[blockIdx.x];
+    const CellDesc c = cells[cell];
     const int f = blockIdx.y;
     const LevelGeom& L = g.L[c.level];
-    const int tid = threadIdx.x, lane = tid & 31;
     const int cw = c.cw, ch = c.ch;
     const int ih = ch - 6;
     if (cw <= 6 || ih <= 0) return;
 
     const int col0 = EAOF_INNER_X0 + c.iniX;
     const int mis = col0 & 3;  // cell pixel x sits at tile byte column mis + x
-    const uint8_t* src =
-        pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + c.iniY) * L.pitch + (col0 - mis);
     const int nwords = (mis + cw + 3) >> 2;
     {
-        const unsigned rcp = 65536u / (unsigned)nwords + 1u;
-        const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
+        const uint32_t* src32 = reinterpret_cast<const uint32_t*>(
+            pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + c.iniY) * L.pitch + (col0 - mis));
         const int pitchW = L.pitch >> 2;
-        for (int i = tid; i < ch * nwords; i += FAST_THREADS) {
-            const int r = (int)(((unsigned)i * rcp) >> 16), w = i - r * nwords;
-            tile[r * FAST_PW + 1 + w] = __ldg(src32 + (r * pitchW + w));
+        if (2 * nwords <= 32) {  // two rows per pass
+            const int half = lane >= 16, wl = lane & 15;
+            if (wl < nwords)
+                for (int r = half; r < ch; r += 2) tile[r * PW + 1 + wl] = __ldg(src32 + r * pitchW + wl);
+        } else if (lane < nwords) {
+            for (int r = 0; r < ch; ++r) tile[r * PW + 1 + lane] = __ldg(src32 + r * pitchW + lane);
         }
     }
-    for (int i = tid; i < (66 * FAST_PW + 6) / 4; i += FAST_THREADS) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { nList = 0; nOut = 0; }
-    __syncthreads();
+    for (int i = lane; i < mapWords / 4; i += 32) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
 
     // words holding at least one pixel of the cell's inner area x in [3, cw-3)
     const int cLo = mis + 3, cHi = mis + cw - 4;  // first / last valid tile byte column
     const int wLo = cLo >> 2, nW = (cHi >> 2) - wLo + 1;
     const int nTasks = ih * nW;
     const unsigned rcpW = 65536u / (unsigned)nW + 1u;
+    const unsigned below = (1u << lane) - 1;
 
     // The cell is first searched at iniThFAST; only a cell with no keypoint after NMS is searched again at
     // minThFAST (:808-816).  Each attempt: (A) a necessary condition on the 4 compass ring pixels (every 9-arc
-    // contains two adjacent compass points) at that threshold for 4 pixels at once, surviving words compacted with a
-    // warp ballot; (B) exact arc score of the survivors, 2 pixels per s16x2 op; (C) threshold + 8-neighbour NMS
-    // restricted to the cell.  Arc scores are threshold independent, so the map written by the first attempt stays
-    // valid for the second.
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    // contains two adjacent compass points) at that threshold, one lane per aligned 4-pixel word, the surviving
+    // even/odd pixel pairs compacted with warp ballots; (B) exact arc score of the survivors, 2 pixels per u16x2 op;
+    // (C) 8-neighbour NMS restricted to the cell.  Arc scores are threshold independent, so what the first attempt
+    // wrote into the score map stays valid for the second.
+    int no = 0;
+    for (int attempt = 0; attempt < 2 && no == 0; ++attempt) {
         const int th = attempt == 0 ? g.iniTh : g.minTh;
-        const unsigned th2 = (unsigned)th | ((unsigned)th << 16);
-        if (attempt == 1) {
-            __syncthreads();
-            if (tid == 0) nList = 0;
-            __syncthreads();
-        }
+        const unsigned thB2 = (unsigned)(th + 256) * 0x00010001u;
         // ---- (A)
-        for (int i0 = 0; i0 < nTasks; i0 += FAST_THREADS) {
-            const int i = i0 + tid;
-            bool pass = false;
+        int nl = 0;
+        for (int i0 = 0; i0 < nTasks; i0 += 32) {
+            const int i = i0 + lane;
+            bool passE = false, passO = false;
             int y = 0, w = 0;
             if (i < nTasks) {
                 const int r = (int)(((unsigned)i * rcpW) >> 16);
                 w = wLo + (i - r * nW);
                 y = r + 3;
-                const uint32_t* t = tile + y * FAST_PW + 1 + w;
-                const unsigned W0 = t[0], Wm = t[-1], Wp = t[1], Wu = t[-3 * FAST_PW], Wd = t[3 * FAST_PW];
+                const uint32_t* t = tile + y * PW + 1 + w;
+                const unsigned W0 = t[0], Wm = t[-1], Wp = t[1], Wu = t[-3 * PW], Wd = t[3 * PW];
                 const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
-                unsigned res = 0x80008000u;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const unsigned nc = neg2(h ? odd(W0) : evn(W0));
-                    const unsigned d0 = __vadd2(h ? odd(Wd) : evn(Wd), nc), d4 = __vadd2(h ? odd(V4) : evn(V4), nc);
-                    const unsigned d8 = __vadd2(h ? odd(Wu) : evn(Wu), nc), d12 = __vadd2(h ? odd(V12) : evn(V12), nc);
-                    const unsigned br = __vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8),
-                                                       __vmaxs2(__vmins2(d8, d12), __vmins2(d12, d0)));
-                    const unsigned dk = __vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8),
-                                                       __vmins2(__vmaxs2(d8, d12), __vmaxs2(d12, d0)));
-                    res = __vimax3_s16x2(res, br, neg2(dk));
+                    const unsigned nc = FAST_BIAS2 - (h ? odd(W0) : evn(W0));
+                    const unsigned d0 = (h ? odd(Wd) : evn(Wd)) + nc, d4 = (h ? odd(V4) : evn(V4)) + nc;
+                    const unsigned d8 = (h ? odd(Wu) : evn(Wu)) + nc, d12 = (h ? odd(V12) : evn(V12)) + nc;
+                    const unsigned br = __vimax3_u16x2(__vminu2(d0, d4), __vminu2(d4, d8),
+                                                       __vmaxu2(__vminu2(d8, d12), __vminu2(d12, d0)));
+                    const unsigned dk = __vimin3_u16x2(__vmaxu2(d0, d4), __vmaxu2(d4, d8),
+                                                       __vminu2(__vmaxu2(d8, d12), __vmaxu2(d12, d0)));
+                    const bool p = __vimax3_u16x2(br, 2u * FAST_BIAS2 - dk, thB2) != thB2;  // some lane > th
+                    if (h) passO = p; else passE = p;
                 }
-                pass = __vmaxs2(res, th2) != th2;  // some lane > th
             }
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&nList, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) lst[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)((y << 8) | w);
-            }
+            const unsigned mE = __ballot_sync(0xffffffffu, passE), mO = __ballot_sync(0xffffffffu, passO);
+            const int nE = __popc(mE);
+            const unsigned e = (unsigned)((y << 8) | (w << 1));
+            if (passE) lst[nl + __popc(mE & below)] = (uint16_t)e;
+            if (passO) lst[nl + nE + __popc(mO & below)] = (uint16_t)(e | 1u);
+            nl += nE + __popc(mO);
         }
-        __syncthreads();
-        const int nl = nList;
         if (nl == 0) continue;
+        __syncwarp();
         // ---- (B)
-        for (int i = tid; i < nl; i += FAST_THREADS) {
-            const int yw = lst[i], y = yw >> 8, w = yw & 255;
-            const uint32_t* t = tile + y * FAST_PW + 1 + w;
-            unsigned V[16];
-#define ROW3(dy, m, z, p) const unsigned m = t[(dy)*FAST_PW - 1], z = t[(dy)*FAST_PW], p = t[(dy)*FAST_PW + 1];
-            ROW3(3, a3m, a3z, a3p) ROW3(2, a2m, a2z, a2p) ROW3(1, a1m, a1z, a1p) ROW3(0, c0m, c0z, c0p)
-            ROW3(-1, b1m, b1z, b1p) ROW3(-2, b2m, b2z, b2p) ROW3(-3, b3m, b3z, b3p)
-#undef ROW3
-            V[0] = a3z;                          V[1] = __byte_perm(a3z, a3p, 0x4321);
-            V[2] = __byte_perm(a2z, a2p, 0x5432); V[3] = __byte_perm(a1z, a1p, 0x6543);
-            V[4] = __byte_perm(c0z, c0p, 0x6543); V[5] = __byte_perm(b1z, b1p, 0x6543);
-            V[6] = __byte_perm(b2z, b2p, 0x5432); V[7] = __byte_perm(b3z, b3p, 0x4321);
-            V[8] = b3z;                          V[9] = __byte_perm(b3m, b3z, 0x6543);
-            V[10] = __byte_perm(b2m, b2z, 0x5432); V[11] = __byte_perm(b1m, b1z, 0x4321);
-            V[12] = __byte_perm(c0m, c0z, 0x4321); V[13] = __byte_perm(a1m, a1z, 0x4321);
-            V[14] = __byte_perm(a2m, a2z, 0x5432); V[15] = __byte_perm(a3m, a3z, 0x6543);
+        for (int i = lane; i < nl; i += 32) {
+            const int e = lst[i], y = e >> 8, w = (e & 255) >> 1;
+            const bool od = e & 1;
+            const uint32_t* t = tile + y * PW + 1 + w;
             unsigned d[16];
-            const unsigned ncE = neg2(evn(c0z)), ncO = neg2(odd(c0z));
-#pragma unroll
-            for (int k = 0; k < 16; ++k) d[k] = __vadd2(evn(V[k]), ncE);
-            const unsigned bE = __vmaxs2(arc_best2(d), 0u);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) d[k] = __vadd2(odd(V[k]), ncO);
-            const unsigned bO = __vmaxs2(arc_best2(d), 0u);
-            // lanes that are not corners at this threshold store 0: the NMS only ever asks "corner ? score : 0"
-            const unsigned kE = __vmaxs2(bE, th2) ^ th2, kO = __vmaxs2(bO, th2) ^ th2;  // lane != 0  <=>  b > th
-            const unsigned mE = ((kE & 0xffffu) ? 0xffffu : 0u) | ((kE >> 16) ? 0xffff0000u : 0u);
-            const unsigned mO = ((kO & 0xffffu) ? 0xffffu : 0u) | ((kO >> 16) ? 0xffff0000u : 0u);
-            unsigned word = __byte_perm(bE & mE, bO & mO, 0x6240);  // scores of pixels 4w .. 4w+3 (each <= 255)
-            // pixels outside the inner area of the cell keep score 0 (cv::FAST never scores them)
-            const int cb = 4 * w;
-            unsigned mask = 0xffffffffu;
-            if (cb < cLo) mask <<= 8 * (cLo - cb);
-            if (cb + 3 > cHi) mask &= 0xffffffffu >> (8 * (cb + 3 - cHi));
-            Bm[y * FAST_PW + 1 + w] = word & mask;
-        }
-        __syncthreads();
-        // ---- (C)
-        for (int i = tid; i < nl; i += FAST_THREADS) {
-            const int yw = lst[i], y = yw >> 8, w = yw & 255;
-            const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * FAST_PW + 1 + w);
-            unsigned word = *reinterpret_cast<const uint32_t*>(q0);
-            while (word) {
-                const int j = (__ffs(word) - 1) >> 3;
-                const int s = (int)((word >> (8 * j)) & 0xff) - 1;
-                word &= ~(0xffu << (8 * j));
-                const uint8_t* q = q0 + j;
-                int nbMax = 0;  // stored scores are either 0 or > th
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        if (dx == 0 && dy == 0) continue;
-                        nbMax = max(nbMax, (int)q[dy * (4 * FAST_PW) + dx]);
-                    }
-                if (s > (nbMax > 0 ? nbMax - 1 : 0)) {  // s > (neighbour is a corner ? its score : 0) for all 8
-                    const int o = atomicAdd(&nOut, 1);
-                    const int x = 4 * w + j - mis;  // cell coordinates
-                    const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
-                    outl[o] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
+            {
+#define LANES(v) (od ? odd(v) : evn(v))
+#define ROW3(dy, m, z, p) const unsigned m = t[(dy)*PW - 1], z = t[(dy)*PW], p = t[(dy)*PW + 1];
+                ROW3(0, c0m, c0z, c0p)
+                const unsigned nc = FAST_BIAS2 - LANES(c0z);
+                d[4] = LANES(__byte_perm(c0z, c0p, 0x6543)) + nc;
+                d[12] = LANES(__byte_perm(c0m, c0z, 0x4321)) + nc;
+                {
+                    ROW3(3, a3m, a3z, a3p)
+                    d[0] = LANES(a3z) + nc;
+                    d[1] = LANES(__byte_perm(a3z, a3p, 0x4321)) + nc;
+                    d[15] = LANES(__byte_perm(a3m, a3z, 0x6543)) + nc;
                 }
+                {
+                    ROW3(2, a2m, a2z, a2p)
+                    d[2] = LANES(__byte_perm(a2z, a2p, 0x5432)) + nc;
+                    d[14] = LANES(__byte_perm(a2m, a2z, 0x5432)) + nc;
+                }
+                {
+                    ROW3(1, a1m, a1z, a1p)
+                    d[3] = LANES(__byte_perm(a1z, a1p, 0x6543)) + nc;
+                    d[13] = LANES(__byte_perm(a1m, a1z, 0x4321)) + nc;
+                }
+                {
+                    ROW3(-1, b1m, b1z, b1p)
+                    d[5] = LANES(__byte_perm(b1z, b1p, 0x6543)) + nc;
+                    d[11] = LANES(__byte_perm(b1m, b1z, 0x4321)) + nc;
+                }
+                {
+                    ROW3(-2, b2m, b2z, b2p)
+                    d[6] = LANES(__byte_perm(b2z, b2p, 0x5432)) + nc;
+                    d[10] = LANES(__byte_perm(b2m, b2z, 0x5432)) + nc;
+                }
+                {
+                    ROW3(-3, b3m, b3z, b3p)
+                    d[7] = LANES(__byte_perm(b3z, b3p, 0x4321)) + nc;
+                    d[8] = LANES(b3z) + nc;
+                    d[9] = LANES(__byte_perm(b3m, b3z, 0x6543)) + nc;
+                }
+#undef ROW3
+#undef LANES
+            }
+            const unsigned b2 = arc_best2(d);
+            // a pixel that is not a corner at this threshold, or lies outside the inner area of the cell (cv::FAST
+            // never scores those), keeps 0: the NMS only ever asks "corner ? score : 0"
+            uint8_t* q = reinterpret_cast<uint8_t*>(Bm + y * PW + 1 + w) + (od ? 1 : 0);
+            const int cb = 4 * w + (od ? 1 : 0);
+            const int bLo = (int)(b2 & 0xffffu) - 256, bHi = (int)(b2 >> 16) - 256;
+            if (bLo > th && cb >= cLo && cb <= cHi) q[0] = (uint8_t)bLo;
+            if (bHi > th && cb + 2 >= cLo && cb + 2 <= cHi) q[2] = (uint8_t)bHi;
+        }
+        __syncwarp();
+        // ---- (C)
+        const int pitchB = 4 * PW;
+        for (int i0 = 0; i0 < nl; i0 += 32) {
+            const int i = i0 + lane;
+            const int e = i < nl ? lst[i] : 0, y = e >> 8, w = (e & 255) >> 1;
+            const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * PW + 1 + w) + (e & 1);
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                const uint8_t* q = q0 + j;
+                const int s = (i < nl ? (int)q[0] : 0) - 1;
+                bool keep = false;
+                if (s >= 0) {
+                    int nbMax = 0;  // stored scores are either 0 or > th
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            if (dx == 0 && dy == 0) continue;
+                            nbMax = max(nbMax, (int)q[dy * pitchB + dx]);
+                        }
+                    keep = s > (nbMax > 0 ? nbMax - 1 : 0);  // s > (neighbour is a corner ? its score : 0) for all 8
+                }
+                const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int x = 4 * w + (e & 1) + j - mis;  // cell coordinates
+                    const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
+                    outl[no + __popc(mk & below)] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
+                }
+                no += __popc(mk);
             }
         }
-        __syncthreads();
-        if (nOut > 0) break;
+        __syncwarp();
     }
-    const int no = nOut;
     if (no == 0) return;
-    if (tid == 0) gBase = atomicAdd(&candCount[f * g.nlevels + c.level], (uint32_t)no);
-    __syncthreads();
+    uint32_t gBase = 0;
+    if (lane == 0) gBase = atomicAdd(&candCount[f * g.nlevels + c.level], (uint32_t)no);
+    gBase = __shfl_sync(0xffffffffu, gBase, 0);
     uint32_t* dst = cand + (size_t)f * g.candPerFrame + L.candOff + gBase;
-    for (int i = tid; i < no; i += FAST_THREADS) dst[i] = outl[i];
+    for (int i = lane; i < no; i += 32) dst[i] = outl[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -901,14 +932,17 @@ __global__ void k_debug_sincosf(uint32_t firstBits, uint32_t stride, uint32_t n,
     glibc_sincosf(__uint_as_float(firstBits + i * stride), &s[i], &c[i]);
 }
 
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // src/ORBextractor.cc:454-469
+#define EAOF_HALF_PATCH 15                  // HALF_PATCH_SIZE, src/ORBextractor.cc:73
+#define EAOF_ANGLE_TASKS (31 * 9)           // (row, aligned word) pairs covering the 31x31 patch at any alignment
+#define EAOF_ANGLE_TASKS_PAD 288
 __device__ __align__(16) signed char d_pattern[EAOF_ORB_PATTERN_INTS];
 
 // One warp per keypoint slot.  IC_Angle on the unblurred bordered level, descriptor on the blurred level.
 __global__ void __launch_bounds__(256) k_angle_desc(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                                                     const uint32_t* __restrict__ slotXY,
                                                     const uint8_t* __restrict__ slotScore,
-                                                    const int* __restrict__ lvlCount, void* __restrict__ kpsOut,
+                                                    const int* __restrict__ lvlCount, const uint2* __restrict__ angleTab,
+                                                    void* __restrict__ kpsOut,
                                                     uint8_t* __restrict__ descOut, int* __restrict__ kpCount,
                                                     int kpCap, const __grid_constant__ Geom g) {
     const int f = blockIdx.y;
@@ -933,16 +967,25 @@ __global__ void __launch_bounds__(256) k_angle_desc(const uint8_t* __restrict__ 
     const size_t lvlBase = (size_t)f * g.pyrFrameBytes + L.off + (size_t)EAOF_EDGE * L.pitch + EAOF_INNER_X0;
     const uint8_t* ctr = pyr + lvlBase + (size_t)Y * L.pitch + X;
 
-    // IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc
+    // IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc (749 pixels).  The 31 rows are read as 9 aligned
+    // words each; for every (row, word) the table holds the four u weights and the four v weights as signed bytes
+    // (0 outside the disc), one table per alignment of the patch, so a task is one pixel load and two DP4As.
     int m10 = 0, m01 = 0;
-    const int u = lane - 15;
-    if (lane < 31) {
-#pragma unroll 1
-        for (int v = -15; v <= 15; ++v) {
-            if (abs(u) <= c_umax[abs(v)]) {
-                const int val = ctr[v * L.pitch + u];
-                m10 += u * val;
-                m01 += v * val;
+    {
+        const int cx = EAOF_INNER_X0 + X - EAOF_HALF_PATCH;  // byte column of u = -15 inside the padded row
+        const int a = cx & 3;
+        const uint2* wt = angleTab + a * EAOF_ANGLE_TASKS_PAD;
+        const uint8_t* base = pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + Y) * L.pitch + (cx - a);
+#pragma unroll
+        for (int k = 0; k < (EAOF_ANGLE_TASKS + 31) / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i < EAOF_ANGLE_TASKS) {
+                const int r = (i * 57) >> 9;  // i / 9 for i < 288
+                const int j = i - 9 * r;
+                const unsigned pix = __ldg(reinterpret_cast<const uint32_t*>(base + (r - EAOF_HALF_PATCH) * L.pitch) + j);
+                const uint2 w = __ldg(wt + i);
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(pix), "r"(w.x));
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m01) : "r"(pix), "r"(w.y));
             }
         }
     }
