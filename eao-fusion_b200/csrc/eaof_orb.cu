@@ -227,7 +227,7 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
     g.fastPW = (fastWords + 2) | 1;  // one pad word on the left, one spare on the right (phase A reads word w+1), odd pitch
     g.fastMapWords = std::max(fastRows * g.fastPW + 2, fastOut);
     g.fastMapWords = (g.fastMapWords + 3) & ~3;
-    g.fastWarpWords = (2 * g.fastMapWords + (fastList + 1) / 2 + 3) & ~3;
+    g.fastWarpWords = (2 * g.fastMapWords + FAST_CLST / 2 + (fastList + 1) / 2 + 3) & ~3;
     g.pyrFrameBytes = off + 4096;  // slack: tile loaders may read a few bytes past the last row
     g.candPerFrame = candOff;
     g.slotsPerFrame = slotOff;

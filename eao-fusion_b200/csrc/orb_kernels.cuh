@@ -242,6 +242,7 @@ __device__ __forceinline__ unsigned arc_best2(const unsigned (&d)[16]) {
 #ifndef FAST_MINB
 #define FAST_MINB 8
 #endif
+#define FAST_CLST 128
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8_t* __restrict__ pyr,
                                                                      const CellDesc* __restrict__ cells,
                                                                      uint32_t* __restrict__ cand,
@@ -255,7 +256,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     const int mapWords = g.fastMapWords;         // multiple of 4
     uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;  // pixel (row r, tile byte column c) at byte (r*PW + 1)*4 + c
     uint32_t* Bm = tile + mapWords;              // arc score of corners (0 elsewhere), same layout
-    uint16_t* lst = reinterpret_cast<uint16_t*>(Bm + mapWords);  // surviving (row, word, even/odd pixel pair)
+    uint16_t* clst = reinterpret_cast<uint16_t*>(Bm + mapWords);  // corners found by (B): (row, tile byte column)
+    uint16_t* lst = clst + FAST_CLST;                             // surviving (row, word, even/odd pixel pair)
     // NMS survivors overwrite the tile: the first one is written only when the attempt that produced it is the last
     // one, and phase (C) reads nothing but the score map.
     uint32_t* outl = tile;
@@ -338,50 +340,57 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
         if (nl == 0) continue;
         __syncwarp();
         // ---- (B)
-        for (int i = lane; i < nl; i += 32) {
-            const int e = lst[i], y = e >> 8, w = (e & 255) >> 1;
+        int ncorn = 0;  // corners found by (B); the first FAST_CLST of them are listed for (C)
+        for (int i0 = 0; i0 < nl; i0 += 32) {
+            const bool act = i0 + lane < nl;
+            const int e = lst[act ? i0 + lane : 0], y = e >> 8, w = (e & 255) >> 1;
             const bool od = e & 1;
             const uint32_t* t = tile + y * PW + 1 + w;
             unsigned d[16];
             {
-#define LANES(v) (od ? odd(v) : evn(v))
+                // lanes = bytes (b, b+2) of the 8-byte pool (lo, hi) for the even pair, (b+1, b+3) for the odd pair:
+                // PRMT selector 0x2200 + 0x1111*(b + od), upper byte of each lane masked off
+                const unsigned sb0 = 0x2200u + (od ? 0x1111u : 0u), sb1 = sb0 + 0x1111u, sb2 = sb1 + 0x1111u, sb3 = sb2 + 0x1111u;
+#define LANES(v) (__byte_perm(v, 0u, sb0) & 0x00ff00ffu)
+#define LANES2(lo, hi, sb) (__byte_perm(lo, hi, sb) & 0x00ff00ffu)
 #define ROW3(dy, m, z, p) const unsigned m = t[(dy)*PW - 1], z = t[(dy)*PW], p = t[(dy)*PW + 1];
                 ROW3(0, c0m, c0z, c0p)
                 const unsigned nc = FAST_BIAS2 - LANES(c0z);
-                d[4] = LANES(__byte_perm(c0z, c0p, 0x6543)) + nc;
-                d[12] = LANES(__byte_perm(c0m, c0z, 0x4321)) + nc;
+                d[4] = LANES2(c0z, c0p, sb3) + nc;
+                d[12] = LANES2(c0m, c0z, sb1) + nc;
                 {
                     ROW3(3, a3m, a3z, a3p)
                     d[0] = LANES(a3z) + nc;
-                    d[1] = LANES(__byte_perm(a3z, a3p, 0x4321)) + nc;
-                    d[15] = LANES(__byte_perm(a3m, a3z, 0x6543)) + nc;
+                    d[1] = LANES2(a3z, a3p, sb1) + nc;
+                    d[15] = LANES2(a3m, a3z, sb3) + nc;
                 }
                 {
                     ROW3(2, a2m, a2z, a2p)
-                    d[2] = LANES(__byte_perm(a2z, a2p, 0x5432)) + nc;
-                    d[14] = LANES(__byte_perm(a2m, a2z, 0x5432)) + nc;
+                    d[2] = LANES2(a2z, a2p, sb2) + nc;
+                    d[14] = LANES2(a2m, a2z, sb2) + nc;
                 }
                 {
                     ROW3(1, a1m, a1z, a1p)
-                    d[3] = LANES(__byte_perm(a1z, a1p, 0x6543)) + nc;
-                    d[13] = LANES(__byte_perm(a1m, a1z, 0x4321)) + nc;
+                    d[3] = LANES2(a1z, a1p, sb3) + nc;
+                    d[13] = LANES2(a1m, a1z, sb1) + nc;
                 }
                 {
                     ROW3(-1, b1m, b1z, b1p)
-                    d[5] = LANES(__byte_perm(b1z, b1p, 0x6543)) + nc;
-                    d[11] = LANES(__byte_perm(b1m, b1z, 0x4321)) + nc;
+                    d[5] = LANES2(b1z, b1p, sb3) + nc;
+                    d[11] = LANES2(b1m, b1z, sb1) + nc;
                 }
                 {
                     ROW3(-2, b2m, b2z, b2p)
-                    d[6] = LANES(__byte_perm(b2z, b2p, 0x5432)) + nc;
-                    d[10] = LANES(__byte_perm(b2m, b2z, 0x5432)) + nc;
+                    d[6] = LANES2(b2z, b2p, sb2) + nc;
+                    d[10] = LANES2(b2m, b2z, sb2) + nc;
                 }
                 {
                     ROW3(-3, b3m, b3z, b3p)
-                    d[7] = LANES(__byte_perm(b3z, b3p, 0x4321)) + nc;
+                    d[7] = LANES2(b3z, b3p, sb1) + nc;
                     d[8] = LANES(b3z) + nc;
-                    d[9] = LANES(__byte_perm(b3m, b3z, 0x6543)) + nc;
+                    d[9] = LANES2(b3m, b3z, sb3) + nc;
                 }
+#undef LANES2
 #undef ROW3
 #undef LANES
             }
@@ -391,12 +400,44 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
             uint8_t* q = reinterpret_cast<uint8_t*>(Bm + y * PW + 1 + w) + (od ? 1 : 0);
             const int cb = 4 * w + (od ? 1 : 0);
             const int bLo = (int)(b2 & 0xffffu) - 256, bHi = (int)(b2 >> 16) - 256;
-            if (bLo > th && cb >= cLo && cb <= cHi) q[0] = (uint8_t)bLo;
-            if (bHi > th && cb + 2 >= cLo && cb + 2 <= cHi) q[2] = (uint8_t)bHi;
+            const bool k0 = act && bLo > th && cb >= cLo && cb <= cHi;
+            const bool k2 = act && bHi > th && cb + 2 >= cLo && cb + 2 <= cHi;
+            if (k0) q[0] = (uint8_t)bLo;
+            if (k2) q[2] = (uint8_t)bHi;
+            const unsigned m0 = __ballot_sync(0xffffffffu, k0), m2 = __ballot_sync(0xffffffffu, k2);
+            const int p0 = ncorn + __popc(m0 & below), p2 = ncorn + __popc(m0) + __popc(m2 & below);
+            if (k0 && p0 < FAST_CLST) clst[p0] = (uint16_t)((y << 8) | cb);
+            if (k2 && p2 < FAST_CLST) clst[p2] = (uint16_t)((y << 8) | (cb + 2));
+            ncorn += __popc(m0) + __popc(m2);
         }
         __syncwarp();
+        if (ncorn == 0) continue;
         // ---- (C)
         const int pitchB = 4 * PW;
+        if (ncorn <= FAST_CLST) {
+            for (int i0 = 0; i0 < ncorn; i0 += 32) {
+                const bool act = i0 + lane < ncorn;
+                const int e = clst[act ? i0 + lane : 0], y = e >> 8, col = e & 255;
+                const uint8_t* q = reinterpret_cast<const uint8_t*>(Bm + y * PW + 1) + col;
+                const int s = (int)q[0] - 1;
+                int nbMax = 0;  // stored scores are either 0 or > th
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dx == 0 && dy == 0) continue;
+                        nbMax = max(nbMax, (int)q[dy * pitchB + dx]);
+                    }
+                const bool keep = act && s > (nbMax > 0 ? nbMax - 1 : 0);  // s > (neighbour corner ? its score : 0), all 8
+                const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int x = col - mis;  // cell coordinates
+                    const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
+                    outl[no + __popc(mk & below)] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
+                }
+                no += __popc(mk);
+            }
+        } else  // more corners than the list holds (noise-like cells): scan every surviving pair
         for (int i0 = 0; i0 < nl; i0 += 32) {
             const int i = i0 + lane;
             const int e = i < nl ? lst[i] : 0, y = e >> 8, w = (e & 255) >> 1;
