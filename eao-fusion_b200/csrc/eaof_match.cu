@@ -520,73 +520,107 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
         for (int i = lane; i < nC; i += 32) if (A.ctaken[po + i]) atomicOr(&smem[i >> 5], 1u << (i & 31));
     __syncwarp();
     const float factor = EAOF_HISTO_LENGTH / 360.0f;  // :1337
+    // The reference walks the Last features in index order and each accepted match may make its Cur feature
+    // unavailable to every later query (:1405-1407).  32 queries are resolved at a time: every lane proposes the
+    // first candidate of its list that is still free, all lanes below the first lane whose proposal collides with a
+    // lower lane's exclusive claim commit (their choice cannot depend on anything still undecided), and the rest
+    // propose again against the updated bitmap.  The bitmap only ever gains bits, so a candidate seen taken stays
+    // ruled out; a fixed point of this is exactly the sequential result.
+    const unsigned below = (1u << lane) - 1;
     int nAcc = 0;
     for (int i0 = 0; i0 < nL; i0 += 32) {
         const int mine = i0 + lane;
-        uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);
+        uint32_t e[TOP_K];
+#pragma unroll
+        for (int k = 0; k < TOP_K; ++k) e[k] = 0xffffffffu;
         int myCnt = 0, myObs = 1;
         if (mine < nL) {
             const uint4* p = reinterpret_cast<const uint4*>(topBuf + (po + mine) * 8);
-            w0 = p[0];
-            w1 = p[1];
+            const uint4 w0 = p[0], w1 = p[1];
+            e[0] = w0.x; e[1] = w0.y; e[2] = w0.z; e[3] = w0.w; e[4] = w1.x; e[5] = w1.y;
             myCnt = (int)w1.w;
             if (A.lobs) myObs = A.lobs[po + mine] != 0;
         }
-        unsigned rem = __ballot_sync(0xffffffffu, myCnt > 0);
-        while (rem) {
-            const int j = __ffs(rem) - 1;
-            rem &= rem - 1;
-            const int i = i0 + j;
-            const int cnt = __shfl_sync(0xffffffffu, myCnt, j);
-            const uint32_t e[TOP_K] = {__shfl_sync(0xffffffffu, w0.x, j), __shfl_sync(0xffffffffu, w0.y, j),
-                                       __shfl_sync(0xffffffffu, w0.z, j), __shfl_sync(0xffffffffu, w0.w, j),
-                                       __shfl_sync(0xffffffffu, w1.x, j), __shfl_sync(0xffffffffu, w1.y, j)};
-            int bestDist = 256, bestIdx = -1;
+        bool pending = myCnt > 0;
+        int next = 0;  // entries before `next` are known to be taken
+        while (__ballot_sync(0xffffffffu, pending)) {
+            int prop = -1, propDist = 256;
+            bool needScan = false;
+            if (pending) {
 #pragma unroll
-            for (int k = 0; k < TOP_K; ++k) {
-                if (bestIdx < 0 && k < cnt) {
-                    const int t = e[k] & 0xffff;
-                    if (!((smem[t >> 5] >> (t & 31)) & 1u)) { bestIdx = t; bestDist = (int)(e[k] >> 16); }
+                for (int k = 0; k < TOP_K; ++k) {
+                    if (prop < 0 && k >= next && k < myCnt) {
+                        const int t = e[k] & 0xffff;
+                        if (!((smem[t >> 5] >> (t & 31)) & 1u)) { prop = t; propDist = (int)(e[k] >> 16); }
+                        next = k + (prop < 0);
+                    }
+                }
+                if (prop < 0) {
+                    if (myCnt > TOP_K) needScan = true;  // every kept candidate is taken: exact re-scan when it is my turn
+                    else pending = false;                // no candidate left: this query stays unmatched
                 }
             }
-            if (bestIdx < 0 && cnt > TOP_K) {
-                // every kept candidate is taken: exact sequential re-scan of this query (uniform across the warp)
-                const float u = A.lu[po + i], v = A.lv[po + i];
-                const float invz = A.linvz ? A.linvz[po + i] : 1.f;
-                const int oct = A.loct[po + i];
-                const float r = __fmul_rn(A.th, A.scale[oct]);
-                int minLevel, maxLevel;
-                level_window(A.searchMode, oct, minLevel, maxLevel);
-                uint32_t qd[8];
-                const uint4* p = reinterpret_cast<const uint4*>(A.desc + 32 * ((size_t)A.lRow[pair] + i));
-                const uint4 a = p[0], b = p[1];
-                qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
-                const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
-                const float* cur = A.curight ? A.curight + po : nullptr;
-                const float ur = __fsub_rn(u, __fmul_rn(A.mbf, invz));
-                for_each_candidate(A, cellStart + (size_t)pair * (GRID_CELLS + 1), cellIdx + po, A.cx + po, A.cy + po,
-                                   A.coct + po, u, v, r, minLevel, maxLevel, [&](int k) {
-                    if ((smem[k >> 5] >> (k & 31)) & 1u) return;
-                    if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) return;
-                    uint32_t td[8];
-                    const uint4* pp = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
-                    const uint4 a2 = pp[0], b2 = pp[1];
-                    td[0] = a2.x; td[1] = a2.y; td[2] = a2.z; td[3] = a2.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
-                    const int d = hamming256(qd, td);
-                    if (d < bestDist) { bestDist = d; bestIdx = k; }
-                });
-                if (bestDist > EAOF_TH_HIGH) bestIdx = -1;
-            }
-            if (bestIdx >= 0 && bestDist <= EAOF_TH_HIGH) {  // :1428
-                const int obs = __shfl_sync(0xffffffffu, myObs, j);
-                if (lane == 0) {
-                    mOut[bestIdx] = i;
-                    if (dOut) dOut[bestIdx] = bestDist;
-                    if (obs) smem[bestIdx >> 5] |= 1u << (bestIdx & 31);
-                    else smem[bestIdx >> 5] &= ~(1u << (bestIdx & 31));
-                    acc[nAcc] = (uint32_t)i | ((uint32_t)bestIdx << 16);
+            const bool proposing = pending && prop >= 0;
+            const unsigned same = __match_any_sync(0xffffffffu, proposing ? prop : -1 - lane);
+            const unsigned excl = __ballot_sync(0xffffffffu, proposing && myObs);
+            const bool conflict = (proposing && (same & below & excl)) || (pending && needScan);
+            const unsigned cm = __ballot_sync(0xffffffffu, conflict);
+            const int c = cm ? __ffs(cm) - 1 : 32;
+            const bool commit = proposing && lane < c;
+            const unsigned cmask = __ballot_sync(0xffffffffu, commit);
+            if (commit) {
+                // several non-exclusive claims of one target: the reference lets the last query overwrite the earlier ones
+                const unsigned grp = same & cmask;
+                if ((grp >> lane) <= 1u) {
+                    mOut[prop] = mine;
+                    if (dOut) dOut[prop] = propDist;
                 }
-                ++nAcc;
+                if (myObs) atomicOr(&smem[prop >> 5], 1u << (prop & 31));
+                acc[nAcc + __popc(cmask & below)] = (uint32_t)mine | ((uint32_t)prop << 16);
+                pending = false;
+            }
+            nAcc += __popc(cmask);
+            __syncwarp();
+            const unsigned scanMask = __ballot_sync(0xffffffffu, pending && needScan);
+            if (c < 32 && ((scanMask >> c) & 1u)) {
+                // lane c is now the lowest undecided query and the bitmap is final for it: exact sequential re-scan
+                int bestDist = 256, bestIdx = -1;
+                if (lane == c) {
+                    const int i = mine;
+                    const float u = A.lu[po + i], v = A.lv[po + i];
+                    const float invz = A.linvz ? A.linvz[po + i] : 1.f;
+                    const int oct = A.loct[po + i];
+                    const float r = __fmul_rn(A.th, A.scale[oct]);
+                    int minLevel, maxLevel;
+                    level_window(A.searchMode, oct, minLevel, maxLevel);
+                    uint32_t qd[8];
+                    const uint4* p = reinterpret_cast<const uint4*>(A.desc + 32 * ((size_t)A.lRow[pair] + i));
+                    const uint4 a = p[0], b = p[1];
+                    qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+                    const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
+                    const float* cur = A.curight ? A.curight + po : nullptr;
+                    const float ur = __fsub_rn(u, __fmul_rn(A.mbf, invz));
+                    for_each_candidate(A, cellStart + (size_t)pair * (GRID_CELLS + 1), cellIdx + po, A.cx + po, A.cy + po,
+                                       A.coct + po, u, v, r, minLevel, maxLevel, [&](int k) {
+                        if ((smem[k >> 5] >> (k & 31)) & 1u) return;
+                        if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) return;
+                        uint32_t td[8];
+                        const uint4* pp = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
+                        const uint4 a2 = pp[0], b2 = pp[1];
+                        td[0] = a2.x; td[1] = a2.y; td[2] = a2.z; td[3] = a2.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
+                        const int d = hamming256(qd, td);
+                        if (d < bestDist) { bestDist = d; bestIdx = k; }
+                    });
+                    if (bestDist > EAOF_TH_HIGH) bestIdx = -1;  // :1428
+                    if (bestIdx >= 0) {
+                        mOut[bestIdx] = i;
+                        if (dOut) dOut[bestIdx] = bestDist;
+                        if (myObs) smem[bestIdx >> 5] |= 1u << (bestIdx & 31);
+                        acc[nAcc] = (uint32_t)i | ((uint32_t)bestIdx << 16);
+                    }
+                    pending = false;
+                }
+                nAcc += __popc(__ballot_sync(0xffffffffu, lane == c && bestIdx >= 0));
                 __syncwarp();
             }
         }

@@ -45,6 +45,8 @@ struct eaof_orb {
     eaof_orb_params p{};
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // side stream: the blur runs beside FAST + quadtree (both only need the pyramid)
+    cudaEvent_t evPyr = nullptr, evBlur = nullptr;
     Geom g{};
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
@@ -261,6 +263,16 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[1], s));
+    // FAST is bound by the integer ALU pipe, the blur by the FMA pipe, the quadtree by latency: outside profiling mode
+    // (which serialises the stages to time them) the blur runs on the side stream beside FAST + quadtree.
+    cudaStream_t sb = prof ? s : c->stream2;
+    if (!prof) {
+        CK(cudaEventRecord(c->evPyr, s));
+        CK(cudaStreamWaitEvent(sb, c->evPyr, 0));
+        eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, sb>>>(c->dPyr, c->dBlur, g);
+        ++launches;
+        CK(cudaEventRecord(c->evBlur, sb));
+    }
     if (g.cellsPerFrame > 0) {
         const size_t smem = (size_t)FAST_WARPS * g.fastWarpWords * 4;
         eaof::k_fast<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
@@ -272,8 +284,12 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
                                                                          c->dSlotScore, c->dLvlCount, g);
     ++launches;
     if (prof) CK(cudaEventRecord(c->ev[3], s));
-    eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, s>>>(c->dPyr, c->dBlur, g);
-    ++launches;
+    if (prof) {
+        eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, s>>>(c->dPyr, c->dBlur, g);
+        ++launches;
+    } else {
+        CK(cudaStreamWaitEvent(s, c->evBlur, 0));
+    }
     if (prof) CK(cudaEventRecord(c->ev[4], s));
     {
         const int warpsPerBlock = 8;
@@ -341,6 +357,9 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
         }                                                                                               \
     } while (0)
     CKD(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKD(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CKD(cudaEventCreateWithFlags(&c->evPyr, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->evBlur, cudaEventDisableTiming));
     CKD(cudaMalloc(&c->dIn, B * (size_t)p.width * p.height));
     CKD(cudaMalloc(&c->dPyr, B * g.pyrFrameBytes));
     CKD(cudaMalloc(&c->dBlur, B * g.pyrFrameBytes));
@@ -427,6 +446,9 @@ void eaof_orb_destroy(eaof_orb* c) {
     cudaFree(c->dLvlCount); cudaFree(c->dKps); cudaFree(c->dDesc); cudaFree(c->dKpCount);
     cudaFreeHost(c->hIn); cudaFreeHost(c->hKps); cudaFreeHost(c->hDesc); cudaFreeHost(c->hKpCount);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->evPyr) cudaEventDestroy(c->evPyr);
+    if (c->evBlur) cudaEventDestroy(c->evBlur);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
