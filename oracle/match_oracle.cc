@@ -6,9 +6,11 @@
 // (std::map<NodeId, vector<unsigned>>) is a CSR triple (sorted node ids, starts, feature indices), and the 64x48
 // feature grid is rebuilt from the undistorted keypoints exactly as Frame::AssignFeaturesToGrid does.
 //
-// PARITY STATUS: the reference's ORBmatcher.cc cannot be compiled here (it needs Frame.h -> PCL, Eigen, g2o, DBoW2,
-// PEAC: none installed) and the reference ships no tests or golden vectors, so this restatement is checked only
-// against independent numpy restatements (tests/test_oracle_matcher.py) — "parity unpinned" for the matcher.
+// PARITY STATUS: pinned.  The reference ships no tests or golden vectors, but its ORBmatcher.cc compiles here
+// unmodified against oracle/matchshim (array-backed Frame/KeyFrame/MapPoint stand-ins) into oracle/_ref/libmatch_ref.so;
+// tests/test_oracle_matcher_vs_ref.py drives both with the same arrays and requires identical match indices and
+// counts for every loop restated below.  (Distances are not an output of the reference methods; the restatement's
+// distances are checked against DescriptorDistance separately.)
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

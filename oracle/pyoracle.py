@@ -361,3 +361,126 @@ def o_search_by_projection(cur, last, th, check_ori, *, bounds, grid_inv, scale_
                                              _pp(lv), _pp(linv), _pp(lo), _pp(la), _pp(ld), _pp(lobs), _pp(sf), float(th),
                                              float(mbf), search_mode, int(check_ori), match.ctypes.data, dist.ctypes.data)
     return n, match[:nc], dist[:nc]
+
+
+def o_search_for_triangulation(k1, k2, F12, epipole, scale_factors, level_sigma2, only_stereo, check_ori):
+    """k1: dict(desc,x,y,angle,free[,stereo],nodes); k2: dict(desc,x,y,octave,angle,free[,stereo],nodes).
+    Returns (nmatches, match12, dist12).  src/ORBmatcher.cc:657-823."""
+    d1, d2 = _a(k1["desc"], np.uint8), _a(k2["desc"], np.uint8)
+    x1, y1, a1 = (_a(k1[k], np.float32) for k in ("x", "y", "angle"))
+    x2, y2, a2 = (_a(k2[k], np.float32) for k in ("x", "y", "angle"))
+    o2 = _a(k2["octave"], np.int32)
+    f1, f2 = _a(k1["free"], np.uint8), _a(k2["free"], np.uint8)
+    s1, s2 = _a(k1.get("stereo"), np.uint8), _a(k2.get("stereo"), np.uint8)
+    i1, st1, ix1 = (_a(v, np.int32) for v in k1["nodes"])
+    i2, st2, ix2 = (_a(v, np.int32) for v in k2["nodes"])
+    F = _a(F12, np.float32).reshape(9)
+    sf, ls = _a(scale_factors, np.float32), _a(level_sigma2, np.float32)
+    n1, n2 = len(d1), len(d2)
+    match = np.full(max(n1, 1), -1, np.int32)
+    dist = np.full(max(n1, 1), -1, np.int32)
+    L = _mo()
+    L.eaoo_search_for_triangulation.argtypes = ([C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 7 +
+                                                [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 3 +
+                                                [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.c_int, C.c_void_p, C.c_void_p])
+    n = L.eaoo_search_for_triangulation(n1, _pp(d1), _pp(x1), _pp(y1), _pp(a1), _pp(f1), _pp(s1), n2, _pp(d2), _pp(x2),
+                                        _pp(y2), _pp(o2), _pp(a2), _pp(f2), _pp(s2), len(i1), _pp(i1), _pp(st1), _pp(ix1),
+                                        len(i2), _pp(i2), _pp(st2), _pp(ix2), _pp(F), float(epipole[0]), float(epipole[1]),
+                                        _pp(sf), _pp(ls), int(only_stereo), int(check_ori), match.ctypes.data,
+                                        dist.ctypes.data)
+    return n, match[:n1], dist[:n1]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The UNMODIFIED reference ORBmatcher.cc (oracle/_ref/libmatch_ref.so, built by `make -C oracle matchref`), driven
+# through oracle/match_ref_harness.cc with the same arrays as the o_* restatements above.
+MATCH_REF_SO = os.path.join(HERE, "_ref", "libmatch_ref.so")
+_mref = None
+
+
+def match_ref_lib():
+    global _mref
+    if _mref is None:
+        if not os.path.exists(MATCH_REF_SO):
+            subprocess.check_call(["make", "-s", "-C", HERE, "matchref"])
+        L = C.CDLL(MATCH_REF_SO)
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.mref_hamming.argtypes = [vp, vp]
+        L.mref_predict_scale.argtypes = [cf, cf, cf]
+        L.mref_norm3.restype = cf
+        L.mref_norm3.argtypes = [cf, cf, cf]
+        L.mref_search_by_bow.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, cf, ci, vp]
+        L.mref_search_for_triangulation.argtypes = ([ci] + [vp] * 6 + [ci] + [vp] * 7 + [ci] + [vp] * 3 + [ci] + [vp] * 3 +
+                                                    [vp, cf, cf, vp, vp, ci, ci, ci, cf, vp])
+        L.mref_search_by_projection_last.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp,
+                                                     vp, vp, vp, vp, vp, vp, ci, cf, cf, ci, ci, cf, vp]
+        L.mref_search_by_projection_mappoints.argtypes = [ci, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp,
+                                                          vp, vp, vp, vp, vp, vp, vp, ci, cf, cf, vp]
+        L.mref_search_for_initialization.argtypes = [ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci,
+                                                     cf, ci, vp]
+        L.mref_search_by_projection_kf.argtypes = [ci, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp, vp,
+                                                   vp, vp, vp, vp, vp, ci, cf, cf, ci, ci, cf, vp]
+        _mref = L
+    return _mref
+
+
+def r_hamming(a, b):
+    a = _a(a, np.uint8).reshape(-1, 32)
+    b = _a(b, np.uint8).reshape(-1, 32)
+    L = match_ref_lib()
+    return np.array([L.mref_hamming(a[i].ctypes.data, b[i].ctypes.data) for i in range(len(a))], np.int32)
+
+
+def r_search_by_bow(mode, nnratio, check_ori, desc_q, angle_q, valid_q, nodes_q, desc_t, angle_t, valid_t, nodes_t):
+    dq, dt = _a(desc_q, np.uint8), _a(desc_t, np.uint8)
+    aq, at = _a(angle_q, np.float32), _a(angle_t, np.float32)
+    vq, vt = _a(valid_q, np.uint8), _a(valid_t, np.uint8)
+    iq, sq, xq = (_a(v, np.int32) for v in nodes_q)
+    it, st, xt = (_a(v, np.int32) for v in nodes_t)
+    nq, nt = len(dq), len(dt)
+    nout = nt if mode == 0 else nq
+    match = np.full(max(nout, 1), -1, np.int32)
+    n = match_ref_lib().mref_search_by_bow(mode, nq, _pp(dq), _pp(aq), _pp(vq), nt, _pp(dt), _pp(at), _pp(vt), len(iq),
+                                           _pp(iq), _pp(sq), _pp(xq), len(it), _pp(it), _pp(st), _pp(xt), nnratio,
+                                           int(check_ori), match.ctypes.data)
+    return n, match[:nout]
+
+
+def r_search_for_triangulation(k1, k2, F12, epipole, scale_factors, level_sigma2, only_stereo, check_ori):
+    d1, d2 = _a(k1["desc"], np.uint8), _a(k2["desc"], np.uint8)
+    x1, y1, a1 = (_a(k1[k], np.float32) for k in ("x", "y", "angle"))
+    x2, y2, a2 = (_a(k2[k], np.float32) for k in ("x", "y", "angle"))
+    o2 = _a(k2["octave"], np.int32)
+    f1, f2 = _a(k1["free"], np.uint8), _a(k2["free"], np.uint8)
+    s1, s2 = _a(k1.get("stereo"), np.uint8), _a(k2.get("stereo"), np.uint8)
+    i1, st1, ix1 = (_a(v, np.int32) for v in k1["nodes"])
+    i2, st2, ix2 = (_a(v, np.int32) for v in k2["nodes"])
+    F = _a(F12, np.float32).reshape(9)
+    sf, ls = _a(scale_factors, np.float32), _a(level_sigma2, np.float32)
+    n1, n2 = len(d1), len(d2)
+    match = np.full(max(n1, 1), -1, np.int32)
+    n = match_ref_lib().mref_search_for_triangulation(n1, _pp(d1), _pp(x1), _pp(y1), _pp(a1), _pp(f1), _pp(s1), n2, _pp(d2),
+                                                      _pp(x2), _pp(y2), _pp(o2), _pp(a2), _pp(f2), _pp(s2), len(i1), _pp(i1),
+                                                      _pp(st1), _pp(ix1), len(i2), _pp(i2), _pp(st2), _pp(ix2), _pp(F),
+                                                      float(epipole[0]), float(epipole[1]), _pp(sf), _pp(ls), len(sf),
+                                                      int(only_stereo), int(check_ori), 0.6, match.ctypes.data)
+    return n, match[:n1]
+
+
+def r_search_by_projection(cur, last, th, check_ori, *, bounds, grid_inv, scale_factors, mbf=0.0, search_mode=0):
+    cx, cy = _a(cur["x"], np.float32), _a(cur["y"], np.float32)
+    co, ca, cd = _a(cur["octave"], np.int32), _a(cur["angle"], np.float32), _a(cur["desc"], np.uint8)
+    cur_r, ctk = _a(cur.get("uright"), np.float32), _a(cur.get("taken"), np.uint8)
+    lu, lv = _a(last["u"], np.float32), _a(last["v"], np.float32)
+    lo, la, ld = _a(last["octave"], np.int32), _a(last["angle"], np.float32), _a(last["desc"], np.uint8)
+    lval, linv, lobs = _a(last.get("valid"), np.uint8), _a(last.get("invz"), np.float32), _a(last.get("obs"), np.uint8)
+    sf = _a(scale_factors, np.float32)
+    nc, nl = len(cx), len(lu)
+    match = np.full(max(nc, 1), -1, np.int32)
+    n = match_ref_lib().mref_search_by_projection_last(nc, _pp(cx), _pp(cy), _pp(co), _pp(ca), _pp(cd), _pp(cur_r), _pp(ctk),
+                                                       bounds[0], bounds[1], bounds[2], bounds[3], grid_inv[0], grid_inv[1],
+                                                       nl, _pp(lval), _pp(lu), _pp(lv), _pp(linv), _pp(lo), _pp(la), _pp(ld),
+                                                       _pp(lobs), _pp(sf), len(sf), float(th), float(mbf), search_mode,
+                                                       int(check_ori), 0.9, match.ctypes.data)
+    return n, match[:nc]

@@ -1,0 +1,137 @@
+"""Pins oracle/match_oracle.cc (the restatement the CUDA matcher is diffed against) to the reference's own code:
+oracle/_ref/libmatch_ref.so is the UNMODIFIED /root/reference/src/ORBmatcher.cc compiled against oracle/matchshim and
+driven with the same arrays.  Match indices and match counts must agree exactly."""
+import os
+
+import numpy as np
+import pytest
+
+from matchdata import planted_pair, random_nodes
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(po.MATCH_REF_SO) or os.path.exists("/root/reference/src/ORBmatcher.cc")),
+                                reason="reference matcher binary not built and /root/reference absent")
+
+
+def _csr(node):
+    import eaof
+    return eaof.csr_from_nodes(node)
+
+
+def test_constants_and_distance():
+    L = po.match_ref_lib()
+    assert (L.mref_th_low(), L.mref_th_high(), L.mref_histo_length()) == (50, 100, 30)
+    rng = np.random.Generator(np.random.PCG64(3))
+    a = rng.integers(0, 256, size=(500, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, size=(500, 32), dtype=np.uint8)
+    a[:3] = 0; b[:3] = 255; b[3:6] = a[3:6]
+    r = po.r_hamming(a, b)
+    assert np.array_equal(r, po.o_hamming(a, b))
+    assert np.array_equal(r, np.unpackbits(a ^ b, axis=1).sum(1))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("ratio", [0.6, 0.75, 0.9])
+@pytest.mark.parametrize("ori", [True, False])
+def test_search_by_bow(mode, ratio, ori):
+    total = 0
+    for seed, (nq, nt, nn) in enumerate([(400, 500, 1), (600, 600, 12), (300, 7, 2), (1, 1, 1), (64, 129, 5), (500, 500, 60)]):
+        q, aq, t, at = planted_pair(nq, nt, 10 + seed, dup=5 if nt > 50 else 0)
+        nodes_q = _csr(random_nodes(nq, nn, 20 + seed) if nn > 1 else np.zeros(nq, int))
+        nodes_t = _csr(random_nodes(nt, nn, 30 + seed) if nn > 1 else np.zeros(nt, int))
+        rng = np.random.Generator(np.random.PCG64(100 + seed))
+        vq = (rng.random(nq) > 0.1).astype(np.uint8)
+        vt = (rng.random(nt) > 0.1).astype(np.uint8)
+        on, omatch, _ = po.o_search_by_bow(mode, ratio, ori, q, aq, vq, nodes_q, t, at, vt, nodes_t)
+        rn, rmatch = po.r_search_by_bow(mode, ratio, ori, q, aq, vq, nodes_q, t, at, vt, nodes_t)
+        assert rn == on, (seed, rn, on)
+        assert np.array_equal(rmatch, omatch), seed
+        total += on
+    assert total > 0
+
+
+def _tri_inputs(seed, n1=500, n2=600, nn=8):
+    """Two keyframes whose planted pairs share a vocabulary node and lie on each other's epipolar line
+    (F12 = [e_x]_x for a pure x-translation: the line of (x1, y1) is y = y1), plus ties and distractors."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    d1 = rng.integers(0, 256, size=(n1, 32), dtype=np.uint8)
+    d2 = rng.integers(0, 256, size=(n2, 32), dtype=np.uint8)
+    a1 = rng.uniform(0, 360, n1).astype(np.float32)
+    a2 = rng.uniform(0, 360, n2).astype(np.float32)
+    x1, y1 = rng.uniform(0, 640, n1).astype(np.float32), rng.uniform(0, 480, n1).astype(np.float32)
+    x2, y2 = rng.uniform(0, 640, n2).astype(np.float32), rng.uniform(0, 480, n2).astype(np.float32)
+    node1, node2 = random_nodes(n1, nn, seed + 1), random_nodes(n2, nn, seed + 2)
+    m = int(0.7 * min(n1, n2))
+    src, dst = rng.permutation(n1)[:m], rng.permutation(n2)[:m]
+    d2[dst] = d1[src] ^ np.packbits((rng.random((m, 256)) < 0.06).astype(np.uint8), axis=1)
+    a2[dst] = np.mod(a1[src] + rng.normal(0, 5, m), 360).astype(np.float32)
+    y2[dst] = (y1[src] + rng.normal(0, 1.5, m)).astype(np.float32)
+    node2[dst] = node1[src]
+    # exact duplicates of some planted targets inside the same node: equal distance, the LATER candidate must win (:738)
+    extra = rng.permutation(n2)[:20]
+    twin = dst[:20]
+    d2[extra] = d2[twin]; y2[extra] = y2[twin]; node2[extra] = node2[twin]; a2[extra] = a2[twin]
+    k1 = dict(desc=d1, angle=a1, x=x1, y=y1, free=(rng.random(n1) > 0.2).astype(np.uint8),
+              stereo=(rng.random(n1) > 0.5).astype(np.uint8), nodes=_csr(node1))
+    k2 = dict(desc=d2, angle=a2, x=x2, y=y2, octave=rng.integers(0, 8, n2).astype(np.int32),
+              free=(rng.random(n2) > 0.2).astype(np.uint8), stereo=(rng.random(n2) > 0.5).astype(np.uint8), nodes=_csr(node2))
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32) + rng.normal(0, 1e-5, (3, 3)).astype(np.float32)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    return k1, k2, F12, sf, (sf * sf).astype(np.float32)
+
+
+@pytest.mark.parametrize("only_stereo", [False, True])
+@pytest.mark.parametrize("ori", [True, False])
+def test_search_for_triangulation(only_stereo, ori):
+    total = 0
+    for seed in range(4):
+        k1, k2, F12, sf, ls = _tri_inputs(50 + seed)
+        for epipole in ((320.0, 240.0), (-1e4, -1e4)):  # inside the image (the epipole-distance test bites) / far away
+            on, om, _ = po.o_search_for_triangulation(k1, k2, F12, epipole, sf, ls, only_stereo, ori)
+            rn, rm = po.r_search_for_triangulation(k1, k2, F12, epipole, sf, ls, only_stereo, ori)
+            assert rn == on and np.array_equal(rm, om), (seed, rn, on)
+            total += int((om >= 0).sum())
+    assert total > 100
+
+
+def _proj_inputs(seed, n=900, stereo=False, flags=False):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    q, aq, t, at = planted_pair(n, n, seed, flip=0.06, frac=0.8, dup=8)
+    x = rng.uniform(-5, 645, n).astype(np.float32)
+    y = rng.uniform(-5, 485, n).astype(np.float32)
+    octv = rng.integers(0, 8, n).astype(np.int32)
+    cur = dict(x=x, y=y, octave=octv, angle=at, desc=t)
+    # Last feature i projects near Cur feature perm[i]
+    perm = rng.permutation(n)
+    last = dict(u=(x[perm] + rng.normal(0, 3, n)).astype(np.float32), v=(y[perm] + rng.normal(0, 3, n)).astype(np.float32),
+                octave=np.clip(octv[perm] + rng.integers(-1, 2, n), 0, 7).astype(np.int32), angle=aq, desc=q)
+    # make descriptors of the planted partner line up with the geometry for half of the rows
+    half = perm[: n // 2]
+    cur["desc"][half] = q[: n // 2] ^ np.packbits((rng.random((n // 2, 256)) < 0.05).astype(np.uint8), axis=1)
+    if stereo:
+        cur["uright"] = np.where(rng.random(n) > 0.3, x - 20 + rng.normal(0, 4, n), -1).astype(np.float32)
+        last["invz"] = rng.choice(np.array([1, 0.5, 0.25, 2, -1], np.float32), n, p=[0.5, 0.2, 0.1, 0.15, 0.05])
+    if flags:
+        cur["taken"] = (rng.random(n) < 0.1).astype(np.uint8)
+        last["valid"] = (rng.random(n) > 0.1).astype(np.uint8)
+        last["obs"] = (rng.random(n) > 0.2).astype(np.uint8)
+    return cur, last
+
+
+@pytest.mark.parametrize("th", [7.0, 15.0, 30.0])
+@pytest.mark.parametrize("case", ["plain", "flags", "stereo", "stereo_fwd", "stereo_bwd", "no_ori"])
+def test_search_by_projection_last(th, case):
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    ginv = (np.float32(64) / np.float32(640), np.float32(48) / np.float32(480))
+    total = 0
+    for seed in range(3):
+        cur, last = _proj_inputs(200 + seed, stereo=case.startswith("stereo"), flags=case in ("flags", "stereo"))
+        mode = {"stereo_fwd": 1, "stereo_bwd": 2}.get(case, 0)
+        kw = dict(bounds=bounds, grid_inv=ginv, scale_factors=sf, mbf=40.0 if case.startswith("stereo") else 0.0, search_mode=mode)
+        on, om, _ = po.o_search_by_projection(cur, last, th, case != "no_ori", **kw)
+        rn, rm = po.r_search_by_projection(cur, last, th, case != "no_ori", **kw)
+        assert rn == on, (seed, rn, on)
+        assert np.array_equal(rm, om), seed
+        total += on
+    assert total > 0
