@@ -340,6 +340,126 @@ __global__ void __launch_bounds__(32) k_bow_resolve(BowArgs A, const uint32_t* _
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// SearchForTriangulation  src/ORBmatcher.cc:657-823 (+ CheckDistEpipolarLine :140-157).  There is no greedy exclusion
+// in this loop (vbMatched2 is never set inside it), so every query is independent: one thread per KF1 feature of a
+// shared vocabulary node scans the node's KF2 features staged in shared memory.  bestDist starts at TH_LOW and a
+// candidate replaces the best when dist <= bestDist, i.e. on equal distance the LATER candidate wins.
+struct TriArgs {
+    const uint8_t* desc;  // block 0 = KF1 rows, block 1 = KF2 rows (blockStride rows apart)
+    int blockStride;
+    const float* x1; const float* y1; const float* angle1; const uint8_t* free1; const uint8_t* stereo1;
+    const float* x2; const float* y2; const int* oct2; const float* angle2; const uint8_t* free2; const uint8_t* stereo2;
+    const int* idx1; const int* idx2;
+    const BowSeg* segs;
+    float F[9];
+    float ex, ey;
+    float scale2[EAOF_MAX_LEVELS], sigma2[EAOF_MAX_LEVELS];
+    int onlyStereo, checkOri, n1;
+};
+
+struct TriCand { float x, y; int idx; int flags; };  // flags: bit0 stereo, bits 8.. octave
+
+__global__ void __launch_bounds__(BOW_QT) k_tri_dense(TriArgs A, const int2* __restrict__ tiles, int* __restrict__ match12,
+                                                      int* __restrict__ dist12) {
+    __shared__ __align__(16) uint32_t sT[BOW_TT][8];
+    __shared__ TriCand sC[BOW_TT];
+    const int2 tile = tiles[blockIdx.x];
+    const BowSeg s = A.segs[tile.x];
+    const int qpos = tile.y + threadIdx.x;
+    const int qEnd = min(s.qOff + s.qCnt, tile.y + BOW_QT);
+    const int q = qpos < qEnd ? A.idx1[qpos] : -1;
+    const uint8_t* d1 = A.desc;
+    const uint8_t* d2 = A.desc + (size_t)A.blockStride * 32;
+    bool active = q >= 0 && A.free1[q];                       // :697-701 a feature that already has a map point is skipped
+    const bool bStereo1 = active && A.stereo1 && A.stereo1[q];
+    if (A.onlyStereo && !bStereo1) active = false;            // :705-707
+    uint32_t qd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float la = 0.f, lb = 0.f, lc = 0.f, den = 0.f;
+    if (active) {
+        const uint4* p = reinterpret_cast<const uint4*>(d1 + 32 * (size_t)q);
+        const uint4 a = p[0], b = p[1];
+        qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+        const float x = A.x1[q], y = A.y1[q];                 // epipolar line l = x1' F12, :143-145
+        la = __fadd_rn(__fadd_rn(__fmul_rn(x, A.F[0]), __fmul_rn(y, A.F[3])), A.F[6]);
+        lb = __fadd_rn(__fadd_rn(__fmul_rn(x, A.F[1]), __fmul_rn(y, A.F[4])), A.F[7]);
+        lc = __fadd_rn(__fadd_rn(__fmul_rn(x, A.F[2]), __fmul_rn(y, A.F[5])), A.F[8]);
+        den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    }
+    int bestDist = EAOF_TH_LOW, bestIdx = -1;
+    for (int t0 = s.tOff; t0 < s.tOff + s.tCnt; t0 += BOW_TT) {
+        const int tt = min(BOW_TT, s.tOff + s.tCnt - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tt * 2; i += BOW_QT) {
+            const int j = i >> 1, h = i & 1;
+            const int t = A.idx2[t0 + j];
+            reinterpret_cast<uint4*>(&sT[j][0])[h] = reinterpret_cast<const uint4*>(d2 + 32 * (size_t)t)[h];
+            if (h == 0) {
+                const bool st = A.stereo2 && A.stereo2[t];
+                // a KF2 feature that has a map point is never a candidate (:725); idx -1 marks it
+                const bool usable = A.free2[t] && !(A.onlyStereo && !st);
+                sC[j] = TriCand{A.x2[t], A.y2[t], usable ? t : -1, (st ? 1 : 0) | (A.oct2[t] << 8)};
+            }
+        }
+        __syncthreads();
+        if (active) {
+            for (int j = 0; j < tt; ++j) {
+                const TriCand c = sC[j];
+                if (c.idx < 0) continue;
+                const int d = hamming256(qd, sT[j]);
+                if (d > EAOF_TH_LOW || d > bestDist) continue;   // :738
+                const int oct = c.flags >> 8;
+                if (!bStereo1 && !(c.flags & 1)) {               // :743-749 too close to the epipole
+                    const float dx = __fsub_rn(A.ex, c.x), dy = __fsub_rn(A.ey, c.y);
+                    if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, A.scale2[oct])) continue;
+                }
+                const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, c.x), __fmul_rn(lb, c.y)), lc);   // :147-156
+                if (den == 0.f) continue;
+                const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                if ((double)dsqr < __dmul_rn(3.84, (double)A.sigma2[oct])) { bestIdx = c.idx; bestDist = d; }
+            }
+        }
+    }
+    if (q >= 0 && bestIdx >= 0) {  // every feature sits in at most one node, so q is written by one thread only
+        match12[q] = bestIdx;
+        dist12[q] = bestDist;
+    }
+}
+
+// rotation histogram (factor 1/HISTO_LENGTH, :684), ComputeThreeMaxima, pruning and the match count (:786-808)
+__global__ void __launch_bounds__(256) k_tri_finish(TriArgs A, int* __restrict__ match12, int* __restrict__ dist12,
+                                                    int* __restrict__ nMatches) {
+    __shared__ int hist[EAOF_HISTO_LENGTH];
+    __shared__ int total, keep[3];
+    const float factor = 1.0f / EAOF_HISTO_LENGTH;
+    if (threadIdx.x < EAOF_HISTO_LENGTH) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < A.n1; i += blockDim.x) {
+        const int t = match12[i];
+        if (t < 0) continue;
+        ++mine;
+        if (A.checkOri) atomicAdd(&hist[rot_bin(A.angle1[i], A.angle2[t], factor)], 1);
+    }
+    atomicAdd(&total, mine);
+    __syncthreads();
+    if (A.checkOri) {
+        if (threadIdx.x == 0) three_maxima(hist, keep[0], keep[1], keep[2]);
+        __syncthreads();
+        int removed = 0;
+        for (int i = threadIdx.x; i < A.n1; i += blockDim.x) {
+            const int t = match12[i];
+            if (t < 0) continue;
+            const int bin = rot_bin(A.angle1[i], A.angle2[t], factor);
+            if (bin != keep[0] && bin != keep[1] && bin != keep[2]) { match12[i] = -1; dist12[i] = -1; ++removed; }
+        }
+        atomicSub(&total, removed);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nMatches = total;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // SearchByProjection(Cur, Last)
 struct ProjArgs {
     // Cur side, [pair][stride]
@@ -853,6 +973,79 @@ int eaof_match_bow(eaof_matcher* m, int mode, float ratio, int checkOri, int nQ,
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(matchOut, m->outMatch, sizeof(int) * nOut, cudaMemcpyDeviceToHost, s));
     if (distOut) MCK(cudaMemcpyAsync(distOut, m->outDist, sizeof(int) * nOut, cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    m->lastDistances = dists;
+    return EAOF_OK;
+}
+
+int eaof_match_triangulation(eaof_matcher* m, int checkOri, int onlyStereo, int n1, const uint8_t* desc1, const float* x1,
+                             const float* y1, const float* angle1, const uint8_t* free1, const uint8_t* stereo1, int n2,
+                             const uint8_t* desc2, const float* x2, const float* y2, const int* oct2, const float* angle2,
+                             const uint8_t* free2, const uint8_t* stereo2, int nNodes1, const int* nodeId1,
+                             const int* nodeStart1, const int* nodeIdx1, int nNodes2, const int* nodeId2,
+                             const int* nodeStart2, const int* nodeIdx2, const float* F12, float ex, float ey,
+                             const float* scaleFactors2, const float* levelSigma2, int nLevels, int* match12, int* dist12,
+                             int* nMatches) {
+    if (!m || !match12 || !nMatches || n1 < 0 || n2 < 0) return mfail(EAOF_ERR_ARG, "bad argument");
+    if (n1 > m->maxFeat || n2 > m->maxFeat) return mfail(EAOF_ERR_ARG, "feature count exceeds max_features=%d", m->maxFeat);
+    if (nLevels < 1 || nLevels > EAOF_MAX_LEVELS || !scaleFactors2 || !levelSigma2 || !F12) return mfail(EAOF_ERR_ARG, "bad scale table / F12");
+    *nMatches = 0;
+    for (int i = 0; i < n1; ++i) { match12[i] = -1; if (dist12) dist12[i] = -1; }
+    if (n1 == 0 || n2 == 0) return EAOF_OK;
+    if (!desc1 || !x1 || !y1 || !angle1 || !free1 || !desc2 || !x2 || !y2 || !oct2 || !angle2 || !free2) return mfail(EAOF_ERR_ARG, "null array");
+    for (int i = 0; i < n2; ++i) if (oct2[i] < 0 || oct2[i] >= nLevels) return mfail(EAOF_ERR_ARG, "octave2[%d] out of range", i);
+    std::vector<BowSeg> segs;
+    std::vector<int2> tiles;
+    long long dists = 0;
+    {
+        int a = 0, b = 0;  // merge-walk of the two feature vectors, :690-783
+        while (a < nNodes1 && b < nNodes2) {
+            if (nodeId1[a] == nodeId2[b]) {
+                BowSeg s{nodeStart1[a], nodeStart1[a + 1] - nodeStart1[a], nodeStart2[b], nodeStart2[b + 1] - nodeStart2[b]};
+                if (s.qCnt > 0 && s.tCnt > 0) {
+                    for (int q0 = s.qOff; q0 < s.qOff + s.qCnt; q0 += BOW_QT) tiles.push_back(make_int2((int)segs.size(), q0));
+                    segs.push_back(s);
+                    dists += (long long)s.qCnt * s.tCnt;
+                }
+                ++a; ++b;
+            } else if (nodeId1[a] < nodeId2[b]) ++a;
+            else ++b;
+        }
+    }
+    if (segs.empty()) return EAOF_OK;
+    const int nIdx1 = nodeStart1[nNodes1], nIdx2 = nodeStart2[nNodes2];
+    if (nIdx1 > m->maxFeat || nIdx2 > m->maxFeat || (int)segs.size() > m->maxFeat || (int)tiles.size() > 2 * m->maxFeat)
+        return mfail(EAOF_ERR_ARG, "feature vector larger than max_features");
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+#define UP(dst, src, n, T) MCK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(n), cudaMemcpyHostToDevice, s))
+    UP(m->desc2, desc1, 32 * (size_t)n1, uint8_t);
+    UP(m->desc2 + 32 * (size_t)m->maxFeat, desc2, 32 * (size_t)n2, uint8_t);
+    UP(m->cx, x1, n1, float); UP(m->cy, y1, n1, float); UP(m->cangle, angle1, n1, float); UP(m->validQ, free1, n1, uint8_t);
+    if (stereo1) UP(m->ctaken, stereo1, n1, uint8_t);
+    UP(m->lu, x2, n2, float); UP(m->lv, y2, n2, float); UP(m->loct, oct2, n2, int); UP(m->langle, angle2, n2, float);
+    UP(m->validT, free2, n2, uint8_t);
+    if (stereo2) UP(m->lvalid, stereo2, n2, uint8_t);
+    UP(m->idxQ, nodeIdx1, nIdx1, int); UP(m->idxT, nodeIdx2, nIdx2, int);
+    UP(m->segs, segs.data(), segs.size(), BowSeg); UP(m->tiles, tiles.data(), tiles.size(), int2);
+#undef UP
+    TriArgs A{};
+    A.desc = m->desc2; A.blockStride = m->maxFeat;
+    A.x1 = m->cx; A.y1 = m->cy; A.angle1 = m->cangle; A.free1 = m->validQ; A.stereo1 = stereo1 ? m->ctaken : nullptr;
+    A.x2 = m->lu; A.y2 = m->lv; A.oct2 = m->loct; A.angle2 = m->langle; A.free2 = m->validT; A.stereo2 = stereo2 ? m->lvalid : nullptr;
+    A.idx1 = m->idxQ; A.idx2 = m->idxT; A.segs = m->segs;
+    for (int i = 0; i < 9; ++i) A.F[i] = F12[i];
+    A.ex = ex; A.ey = ey;
+    for (int i = 0; i < nLevels; ++i) { A.scale2[i] = scaleFactors2[i]; A.sigma2[i] = levelSigma2[i]; }
+    A.onlyStereo = onlyStereo; A.checkOri = checkOri; A.n1 = n1;
+    MCK(cudaMemsetAsync(m->outMatch, 0xff, sizeof(int) * (size_t)n1, s));
+    MCK(cudaMemsetAsync(m->outDist, 0xff, sizeof(int) * (size_t)n1, s));
+    k_tri_dense<<<(unsigned)tiles.size(), BOW_QT, 0, s>>>(A, m->tiles, m->outMatch, m->outDist);
+    k_tri_finish<<<1, 256, 0, s>>>(A, m->outMatch, m->outDist, m->outN);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(match12, m->outMatch, sizeof(int) * n1, cudaMemcpyDeviceToHost, s));
+    if (dist12) MCK(cudaMemcpyAsync(dist12, m->outDist, sizeof(int) * n1, cudaMemcpyDeviceToHost, s));
     MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
     MCK(cudaStreamSynchronize(s));
     m->lastDistances = dists;

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -47,6 +48,12 @@ struct eaof_orb {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // side stream: the blur runs beside FAST + quadtree (both only need the pyramid)
     cudaEvent_t evPyr = nullptr, evBlur = nullptr;
+    // host-buffer pipeline: upload, kernels and download of consecutive chunks of a batch overlap on three streams
+    cudaStream_t streamIn = nullptr, streamOut = nullptr;
+    static const int kMaxChunks = 64;
+    cudaEvent_t evIn[kMaxChunks] = {}, evDone[kMaxChunks] = {};
+    cudaEvent_t evOutIdle = nullptr;
+    int chunkFrames = 0;
     Geom g{};
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
@@ -238,27 +245,40 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
     return EAOF_OK;
 }
 
-int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t framePitch) {
+// Issues the kernel sequence for frames [f0, f0+n) of the workspace; dImgs points at frame f0's image.
+int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t framePitch, int f0 = 0) {
     const Geom& g = c->g;
     cudaStream_t s = c->stream;
+    // every per-frame array is frame-major, so a chunk is addressed by offsetting the base pointers
+    uint8_t* const dPyr = c->dPyr + (size_t)f0 * g.pyrFrameBytes;
+    uint8_t* const dBlur = c->dBlur + (size_t)f0 * g.pyrFrameBytes;
+    uint32_t* const dCand = c->dCand + (size_t)f0 * g.candPerFrame;
+    uint16_t* const dLabel = c->dLabel + (size_t)f0 * g.candPerFrame;
+    uint32_t* const dCandCount = c->dCandCount + (size_t)f0 * g.nlevels;
+    uint32_t* const dSlotXY = c->dSlotXY + (size_t)f0 * g.slotsPerFrame;
+    uint8_t* const dSlotScore = c->dSlotScore + (size_t)f0 * g.slotsPerFrame;
+    int* const dLvlCount = c->dLvlCount + (size_t)f0 * g.nlevels;
+    eaof_kp* const dKps = c->dKps + (size_t)f0 * c->kpCap;
+    uint8_t* const dDesc = c->dDesc + (size_t)f0 * c->kpCap * 32;
+    int* const dKpCount = c->dKpCount + f0;
     int launches = 0;
     const bool prof = c->profiling;
     if (prof) CK(cudaEventRecord(c->ev[0], s));
-    CK(cudaMemsetAsync(c->dCandCount, 0, sizeof(uint32_t) * (size_t)n * g.nlevels, s));
+    CK(cudaMemsetAsync(dCandCount, 0, sizeof(uint32_t) * (size_t)n * g.nlevels, s));
     {
         const LevelGeom& L = g.L[0];
         dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
-        eaof::k_level0<<<gr, b, 0, s>>>(dImgs, framePitch, stride, c->dPyr, g);
+        eaof::k_level0<<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g);
         ++launches;
     }
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& L = g.L[l];
         if (L.h >= 40) {
             const int tasks = ((L.w + 43) / 4) * ((L.h + RSZ_ROWS - 1) / RSZ_ROWS);
-            eaof::k_resize<<<dim3((tasks + RSZ_THREADS - 1) / RSZ_THREADS, n), RSZ_THREADS, 0, s>>>(c->dPyr, c->dTabs, g, l);
+            eaof::k_resize<<<dim3((tasks + RSZ_THREADS - 1) / RSZ_THREADS, n), RSZ_THREADS, 0, s>>>(dPyr, c->dTabs, g, l);
         } else {  // tiny levels: border rows may fold more than once
             dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
-            eaof::k_resize_generic<<<gr, b, 0, s>>>(c->dPyr, c->dTabs, g, l);
+            eaof::k_resize_generic<<<gr, b, 0, s>>>(dPyr, c->dTabs, g, l);
         }
         ++launches;
     }
@@ -269,23 +289,23 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     if (!prof) {
         CK(cudaEventRecord(c->evPyr, s));
         CK(cudaStreamWaitEvent(sb, c->evPyr, 0));
-        eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, sb>>>(c->dPyr, c->dBlur, g);
+        eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, sb>>>(dPyr, dBlur, g);
         ++launches;
         CK(cudaEventRecord(c->evBlur, sb));
     }
     if (g.cellsPerFrame > 0) {
         const size_t smem = (size_t)FAST_WARPS * g.fastWarpWords * 4;
         eaof::k_fast<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
-            c->dPyr, c->dCells, c->dCand, c->dCandCount, g);
+            dPyr, c->dCells, dCand, dCandCount, g);
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[2], s));
-    eaof::k_octree<<<dim3(g.nlevels, n), OCT_THREADS, c->octSmem, s>>>(c->dCand, c->dCandCount, c->dLabel, c->dSlotXY,
-                                                                         c->dSlotScore, c->dLvlCount, g);
+    eaof::k_octree<<<dim3(g.nlevels, n), OCT_THREADS, c->octSmem, s>>>(dCand, dCandCount, dLabel, dSlotXY,
+                                                                         dSlotScore, dLvlCount, g);
     ++launches;
     if (prof) CK(cudaEventRecord(c->ev[3], s));
     if (prof) {
-        eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, s>>>(c->dPyr, c->dBlur, g);
+        eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, s>>>(dPyr, dBlur, g);
         ++launches;
     } else {
         CK(cudaStreamWaitEvent(s, c->evBlur, 0));
@@ -294,14 +314,14 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     {
         const int warpsPerBlock = 8;
         dim3 gr((g.slotsPerFrame + warpsPerBlock - 1) / warpsPerBlock, n);
-        eaof::k_angle_desc<<<gr, warpsPerBlock * 32, 0, s>>>(c->dPyr, c->dBlur, c->dSlotXY, c->dSlotScore, c->dLvlCount,
-                                                             c->dAngleTab, c->dKps, c->dDesc, c->dKpCount, c->kpCap, g);
+        eaof::k_angle_desc<<<gr, warpsPerBlock * 32, 0, s>>>(dPyr, dBlur, dSlotXY, dSlotScore, dLvlCount,
+                                                             c->dAngleTab, dKps, dDesc, dKpCount, c->kpCap, g);
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[5], s));
     CK(cudaGetLastError());
-    c->lastLaunches = launches;
-    c->lastFrames = n;
+    c->lastLaunches = (f0 == 0 ? 0 : c->lastLaunches) + launches;
+    c->lastFrames = f0 + n;
     return EAOF_OK;
 }
 
@@ -360,6 +380,22 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     CKD(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CKD(cudaEventCreateWithFlags(&c->evPyr, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->evBlur, cudaEventDisableTiming));
+    CKD(cudaStreamCreateWithFlags(&c->streamIn, cudaStreamNonBlocking));
+    CKD(cudaStreamCreateWithFlags(&c->streamOut, cudaStreamNonBlocking));
+    CKD(cudaEventCreateWithFlags(&c->evOutIdle, cudaEventDisableTiming));
+    for (int i = 0; i < eaof_orb::kMaxChunks; ++i) {
+        CKD(cudaEventCreateWithFlags(&c->evIn[i], cudaEventDisableTiming));
+        CKD(cudaEventCreateWithFlags(&c->evDone[i], cudaEventDisableTiming));
+    }
+    {
+        // chunk size of the host-buffer pipeline: large enough to fill the GPU (the quadtree launches nlevels CTAs per
+        // frame, ~3 resident per SM), small enough that the first upload and last download are a small share
+        const char* e = getenv("EAOF_CHUNK");
+        int cf = e && *e ? atoi(e) : 0;
+        if (cf < 1) cf = std::max(8, 444 / std::max(1, p.nlevels));
+        cf = std::max(cf, (p.max_batch + eaof_orb::kMaxChunks - 1) / eaof_orb::kMaxChunks);
+        c->chunkFrames = std::min(cf, p.max_batch);
+    }
     CKD(cudaMalloc(&c->dIn, B * (size_t)p.width * p.height));
     CKD(cudaMalloc(&c->dPyr, B * g.pyrFrameBytes));
     CKD(cudaMalloc(&c->dBlur, B * g.pyrFrameBytes));
@@ -449,6 +485,13 @@ void eaof_orb_destroy(eaof_orb* c) {
     if (c->evPyr) cudaEventDestroy(c->evPyr);
     if (c->evBlur) cudaEventDestroy(c->evBlur);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    for (int i = 0; i < eaof_orb::kMaxChunks; ++i) {
+        if (c->evIn[i]) cudaEventDestroy(c->evIn[i]);
+        if (c->evDone[i]) cudaEventDestroy(c->evDone[i]);
+    }
+    if (c->evOutIdle) cudaEventDestroy(c->evOutIdle);
+    if (c->streamIn) { cudaStreamSynchronize(c->streamIn); cudaStreamDestroy(c->streamIn); }
+    if (c->streamOut) { cudaStreamSynchronize(c->streamOut); cudaStreamDestroy(c->streamOut); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -531,17 +574,56 @@ int eaof_orb_extract_batch(eaof_orb* c, const uint8_t* imgs, int n, int width, i
     if (rc) return rc;
     if (!imgs || !nOut || stride < (size_t)width) return fail(EAOF_ERR_ARG, "bad argument");
     CK(cudaSetDevice(c->device));
-    // H2D straight from the caller's buffer (true async only when it is pinned)
-    if (stride == (size_t)width && framePitch == (size_t)width * height) {
-        CK(cudaMemcpyAsync(c->dIn, imgs, (size_t)n * width * height, cudaMemcpyHostToDevice, c->stream));
-    } else {
-        for (int f = 0; f < n; ++f)
-            CK(cudaMemcpy2DAsync(c->dIn + (size_t)f * width * height, (size_t)width, imgs + (size_t)f * framePitch, stride,
-                                 (size_t)width, (size_t)height, cudaMemcpyHostToDevice, c->stream));
+    const size_t frameBytes = (size_t)width * height;
+    const bool packed = stride == (size_t)width && framePitch == frameBytes;
+    // When the caller's output layout is the device layout (cap == eaof_orb_max_keypoints) results are downloaded
+    // straight into the caller's buffers; otherwise through the pinned staging buffers and compacted on the host.
+    const bool direct = cap == c->kpCap;
+    eaof_kp* hK = kps ? (direct ? kps : c->hKps) : nullptr;
+    uint8_t* hD = desc ? (direct ? desc : c->hDesc) : nullptr;
+    const bool pipelined = !c->profiling && n > c->chunkFrames;
+    const int chunk = pipelined ? c->chunkFrames : n;
+    // the download stream may still be busy with the previous call's copies out of the same device buffers
+    CK(cudaEventRecord(c->evOutIdle, c->streamOut));
+    CK(cudaStreamWaitEvent(c->stream, c->evOutIdle, 0));
+    int ci = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, ++ci) {
+        const int m = std::min(chunk, n - f0);
+        // upload (H2D straight from the caller's buffer: truly asynchronous only when it is pinned)
+        uint8_t* dst = c->dIn + (size_t)f0 * frameBytes;
+        if (packed) {
+            CK(cudaMemcpyAsync(dst, imgs + (size_t)f0 * framePitch, (size_t)m * frameBytes, cudaMemcpyHostToDevice, c->streamIn));
+        } else {
+            for (int f = 0; f < m; ++f)
+                CK(cudaMemcpy2DAsync(dst + (size_t)f * frameBytes, (size_t)width, imgs + (size_t)(f0 + f) * framePitch, stride,
+                                     (size_t)width, (size_t)height, cudaMemcpyHostToDevice, c->streamIn));
+        }
+        CK(cudaEventRecord(c->evIn[ci], c->streamIn));
+        CK(cudaStreamWaitEvent(c->stream, c->evIn[ci], 0));
+        rc = run_batch(c, dst, m, (size_t)width, frameBytes, f0);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->evDone[ci], c->stream));
+        // download
+        CK(cudaStreamWaitEvent(c->streamOut, c->evDone[ci], 0));
+        CK(cudaMemcpyAsync(c->hKpCount + f0, c->dKpCount + f0, sizeof(int) * m, cudaMemcpyDeviceToHost, c->streamOut));
+        if (hK) CK(cudaMemcpyAsync(hK + (size_t)f0 * c->kpCap, c->dKps + (size_t)f0 * c->kpCap, sizeof(eaof_kp) * (size_t)m * c->kpCap,
+                                   cudaMemcpyDeviceToHost, c->streamOut));
+        if (hD) CK(cudaMemcpyAsync(hD + (size_t)f0 * c->kpCap * 32, c->dDesc + (size_t)f0 * c->kpCap * 32, 32 * (size_t)m * c->kpCap,
+                                   cudaMemcpyDeviceToHost, c->streamOut));
     }
-    rc = run_batch(c, c->dIn, n, (size_t)width, (size_t)width * height);
+    CK(cudaStreamSynchronize(c->streamOut));
+    rc = eaof_orb_sync(c);
     if (rc) return rc;
-    return eaof_orb_fetch_results(c, n, kps, desc, cap, nOut);
+    for (int f = 0; f < n; ++f) {
+        const int k = c->hKpCount[f];
+        nOut[f] = k;
+        if (k > cap && (kps || desc)) return fail(EAOF_ERR_ARG, "frame %d has %d keypoints but cap is %d", f, k, cap);
+        if (!direct) {
+            if (kps) memcpy(kps + (size_t)f * cap, c->hKps + (size_t)f * c->kpCap, sizeof(eaof_kp) * k);
+            if (desc) memcpy(desc + (size_t)f * cap * 32, c->hDesc + (size_t)f * c->kpCap * 32, 32 * (size_t)k);
+        }
+    }
+    return EAOF_OK;
 }
 
 int eaof_orb_extract(eaof_orb* c, const uint8_t* img, int width, int height, size_t stride, eaof_kp* kps, uint8_t* desc,

@@ -238,6 +238,8 @@ def _mlib():
                                             vp, vp, vp, vp, vp, ci, cf, cf, ci, ci, vp, vp, C.POINTER(ci)]
         L.eaof_match_projection_batch_device.argtypes = [vp, vp, ci, vp, vp, vp, vp, cf, vp, vp, vp]
         L.eaof_match_bruteforce_batch_device.argtypes = [vp, ci, cf, ci, ci, vp, vp, vp, vp, vp, ci, vp, vp, vp]
+        L.eaof_match_triangulation.argtypes = ([vp, ci, ci] + [ci] + [vp] * 6 + [ci] + [vp] * 7 + [ci] + [vp] * 3 + [ci] +
+                                               [vp] * 3 + [vp, cf, cf, vp, vp, ci, vp, vp, C.POINTER(ci)])
         L.eaof_matcher_last_distance_count.restype = C.c_longlong
         L.eaof_matcher_last_distance_count.argtypes = [vp]
         _mlib_ready = True
@@ -332,6 +334,30 @@ class ORBmatcher:
                                          float(th), float(mbf), search_mode, int(self.mbCheckOrientation),
                                          match.ctypes.data, dist.ctypes.data, C.byref(n)))
         return n.value, match[:nc], dist[:nc]
+
+    def SearchForTriangulation(self, k1, k2, F12, epipole, scale_factors, level_sigma2, only_stereo=False):
+        """k1: dict(desc,x,y,angle,free[,stereo],nodes); k2: the same plus octave.  free = feature has no map point.
+        Returns (nmatches, match12, dist12); vMatchedPairs = [(i, match12[i]) for match12[i] >= 0]."""
+        d1, d2 = _arr(k1["desc"], np.uint8), _arr(k2["desc"], np.uint8)
+        x1, y1, a1 = (_arr(k1[k], np.float32) for k in ("x", "y", "angle"))
+        x2, y2, a2 = (_arr(k2[k], np.float32) for k in ("x", "y", "angle"))
+        o2 = _arr(k2["octave"], np.int32)
+        f1, f2 = _arr(k1["free"], np.uint8), _arr(k2["free"], np.uint8)
+        s1, s2 = _arr(k1.get("stereo"), np.uint8), _arr(k2.get("stereo"), np.uint8)
+        i1, st1, ix1 = (_arr(v, np.int32) for v in k1["nodes"])
+        i2, st2, ix2 = (_arr(v, np.int32) for v in k2["nodes"])
+        F = _arr(F12, np.float32).reshape(9)
+        sf, ls = _arr(scale_factors, np.float32), _arr(level_sigma2, np.float32)
+        n1, n2 = len(d1), len(d2)
+        match = np.full(max(n1, 1), -1, np.int32)
+        dist = np.full(max(n1, 1), -1, np.int32)
+        n = C.c_int()
+        _ck(self.L.eaof_match_triangulation(self.h, int(self.mbCheckOrientation), int(only_stereo), n1, _p(d1), _p(x1),
+                                            _p(y1), _p(a1), _p(f1), _p(s1), n2, _p(d2), _p(x2), _p(y2), _p(o2), _p(a2),
+                                            _p(f2), _p(s2), len(i1), _p(i1), _p(st1), _p(ix1), len(i2), _p(i2), _p(st2),
+                                            _p(ix2), _p(F), float(epipole[0]), float(epipole[1]), _p(sf), _p(ls), len(sf),
+                                            match.ctypes.data, dist.ctypes.data, C.byref(n)))
+        return n.value, match[:n1], dist[:n1]
 
     def stream_ptr(self):
         return self.L.eaof_matcher_stream(self.h)

@@ -57,6 +57,21 @@ int eaof_match_bow(eaof_matcher* m, int mode, float nnratio, int check_orientati
                    const int* node_idx_q, int n_nodes_t, const int* node_id_t, const int* node_start_t,
                    const int* node_idx_t, int* match_out, int* dist_out, int* n_matches);
 
+/* SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)  src/ORBmatcher.cc:657-823 (with
+ * CheckDistEpipolarLine :140-157), one pair, HOST buffers.  free1/free2: 1 where the feature has NO map point
+ * (only those are matched); stereo1/stereo2: mvuRight >= 0 (NULL = monocular).  Feature vectors as CSR like
+ * eaof_match_bow.  F12: 3x3 row-major; (ex, ey): epipole of KF1's centre in KF2 (:664-670, computed by the caller);
+ * scale_factors2 / level_sigma2_2: mvScaleFactors / mvLevelSigma2 of KF2.  match12 / dist12: n1 entries (index of
+ * the KF2 feature, -1 = none) — vMatchedPairs is the list of (i, match12[i]) with match12[i] >= 0 in ascending i. */
+int eaof_match_triangulation(eaof_matcher* m, int check_orientation, int only_stereo, int n1, const uint8_t* desc1,
+                             const float* x1, const float* y1, const float* angle1, const uint8_t* free1,
+                             const uint8_t* stereo1, int n2, const uint8_t* desc2, const float* x2, const float* y2,
+                             const int* octave2, const float* angle2, const uint8_t* free2, const uint8_t* stereo2,
+                             int n_nodes1, const int* node_id1, const int* node_start1, const int* node_idx1,
+                             int n_nodes2, const int* node_id2, const int* node_start2, const int* node_idx2,
+                             const float* F12, float ex, float ey, const float* scale_factors2,
+                             const float* level_sigma2_2, int n_levels, int* match12, int* dist12, int* n_matches);
+
 /* SearchByProjection(Frame& Cur, const Frame& Last, th, bMono)  src/ORBmatcher.cc:1328-1472, one pair, HOST buffers.
  * Cur: undistorted keypoint positions/octaves/angles, descriptors, optional mvuRight (NULL = monocular) and
  * optional `taken` flags (Cur feature already holds a map point with observations).  The 64x48 grid of

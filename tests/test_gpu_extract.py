@@ -138,6 +138,44 @@ def test_batch_equals_single(ex640, frames640):
         assert np.array_equal(k, res[fi][0]) and np.array_equal(d, res[fi][1])
 
 
+def test_chunked_host_pipeline_and_staged_outputs(frames640, monkeypatch):
+    """eaof_orb_extract_batch overlaps upload / kernels / download of consecutive chunks (EAOF_CHUNK frames each);
+    results must not depend on the chunking, nor on whether the caller's cap equals the device capacity (direct
+    download) or is larger (pinned staging + host compaction)."""
+    import ctypes as C
+    import eaof
+    monkeypatch.setenv("EAOF_CHUNK", "2")
+    ex = eaof.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480, max_batch=6)
+    monkeypatch.delenv("EAOF_CHUNK")
+    one = eaof.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480, max_batch=6)
+    a = ex.extract_batch(frames640)          # 3 chunks of 2 frames
+    b = one.extract_batch(frames640)         # single chunk
+    for f in range(len(frames640)):
+        assert np.array_equal(a[f][0], b[f][0]) and np.array_equal(a[f][1], b[f][1])
+    a2 = ex.extract_batch(frames640[:5])     # ragged last chunk, workspace reused
+    for f in range(5):
+        assert np.array_equal(a2[f][0], b[f][0]) and np.array_equal(a2[f][1], b[f][1])
+    cap = ex.cap + 7
+    n = len(frames640)
+    kps = np.zeros((n, cap), eaof.KP_DTYPE)
+    desc = np.zeros((n, cap, 32), np.uint8)
+    cnt = np.zeros(n, np.int32)
+    fr = np.ascontiguousarray(frames640)
+    rc = ex.L.eaof_orb_extract_batch(ex.h, fr.ctypes.data, n, 640, 480, 640, 640 * 480, kps.ctypes.data, desc.ctypes.data,
+                                     cap, cnt.ctypes.data)
+    assert rc == 0, ex.L.eaof_last_error()
+    for f in range(n):
+        assert cnt[f] == len(b[f][0])
+        assert np.array_equal(kps[f, :cnt[f]], b[f][0]) and np.array_equal(desc[f, :cnt[f]], b[f][1])
+    # a cap that cannot hold the result is an argument error, not a truncation
+    small = 16
+    rc = ex.L.eaof_orb_extract_batch(ex.h, fr.ctypes.data, n, 640, 480, 640, 640 * 480, kps.ctypes.data, desc.ctypes.data,
+                                     small, cnt.ctypes.data)
+    assert rc == -1
+    ex.close()
+    one.close()
+
+
 def test_device_sincosf_sweep():
     """The device restatement of glibc sinf/cosf against the host's libm, all floats in [0, 6.4] (strided)."""
     import eaof

@@ -4,7 +4,7 @@ TH_LOW/TH_HIGH and rotation-histogram pruning."""
 import numpy as np
 import pytest
 
-from matchdata import frame_features, planted_pair, projected_last, random_nodes
+from matchdata import frame_features, planted_pair, projected_last, random_nodes, tri_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -241,3 +241,27 @@ def test_batched_device_paths_equal_single_pair_api(matcher_factory, extracted, 
             nout = len(kt) if mode == 0 else len(kq)
             assert hn[k] == on
             assert np.array_equal(hm[k, :nout], omatch) and np.array_equal(hd[k, :nout], odist)
+
+
+@pytest.mark.parametrize("only_stereo", [False, True])
+@pytest.mark.parametrize("ori", [True, False])
+def test_triangulation(matcher_factory, only_stereo, ori):
+    """SearchForTriangulation (src/ORBmatcher.cc:657-823): later-candidate-wins ties, epipole and epipolar-line gates."""
+    from oracle import pyoracle as po
+    m = matcher_factory(0.6, ori)
+    total = 0
+    for seed, (n1, n2, nn) in enumerate([(500, 600, 8), (2000, 2000, 40), (300, 900, 1), (5, 3, 1)]):
+        k1, k2, F12, sf, ls = tri_inputs(70 + seed, n1, n2, nn)
+        for epipole in ((320.0, 240.0), (-1e4, -1e4)):
+            n, match, dist = m.SearchForTriangulation(k1, k2, F12, epipole, sf, ls, only_stereo)
+            on, om, od = po.o_search_for_triangulation(k1, k2, F12, epipole, sf, ls, only_stereo, ori)
+            assert n == on, (seed, n, on)
+            assert np.array_equal(match, om) and np.array_equal(dist, od)
+            total += on
+    assert total > 100
+    # empty sides
+    k1, k2, F12, sf, ls = tri_inputs(1, 10, 10, 1)
+    e = dict(k1, desc=k1["desc"][:0], x=k1["x"][:0], y=k1["y"][:0], angle=k1["angle"][:0], free=k1["free"][:0],
+             stereo=k1["stereo"][:0], nodes=(np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32)))
+    n, match, _ = m.SearchForTriangulation(e, k2, F12, (0.0, 0.0), sf, ls)
+    assert n == 0 and len(match) == 0
