@@ -45,6 +45,71 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(stage, frames_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json), scaled to this run's frames per launch; None when no capture exists."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)[stage]
+        return t["dram_bytes_per_launch"] * frames_per_launch / t["frames_per_launch"]
+    except Exception:
+        return None
+
+
+def hamming_sweep(eaof, torch, device, n_blocks=64, n_feat=2000, n_pairs=1024, reps=5):
+    """BASELINE.json configs[4] on one GPU: brute-force SearchByBoW semantics (one node holding every feature, TH_LOW=50,
+    ratio 0.9, rotation histogram) over pairs of 2000-descriptor blocks resident in HBM.  Reports descriptor-pair
+    distances/s against the POPC issue rate measured on this device (8 POPC32 per distance)."""
+    import ctypes as C
+    rng = np.random.Generator(np.random.PCG64(77))
+    base = rng.integers(0, 256, size=(n_feat, 32), dtype=np.uint8)
+    desc = np.empty((n_blocks, n_feat, 32), np.uint8)
+    ang = np.empty((n_blocks, n_feat), np.float32)
+    a0 = rng.uniform(0, 360, n_feat).astype(np.float32)
+    for b in range(n_blocks):  # every block: 70 % noisy copies of the base rows (8 % bit flips), 30 % random rows
+        d = rng.integers(0, 256, size=(n_feat, 32), dtype=np.uint8)
+        keep = rng.permutation(n_feat)[: int(0.7 * n_feat)]
+        flips = np.packbits((rng.random((len(keep), 256)) < 0.08).astype(np.uint8), axis=1)
+        d[keep] = base[keep] ^ flips
+        desc[b] = d
+        ang[b] = np.mod(a0 + rng.normal(0, 5, n_feat), 360).astype(np.float32)
+    d_desc = torch.from_numpy(desc).cuda(device)
+    d_ang = torch.from_numpy(ang).cuda(device)
+    d_cnt = torch.full((n_blocks,), n_feat, dtype=torch.int32, device="cuda")
+    pq = (np.arange(n_pairs) % n_blocks).astype(np.int32)
+    pt = ((np.arange(n_pairs) * 7 + 1 + np.arange(n_pairs) // n_blocks) % n_blocks).astype(np.int32)
+    mt = eaof.ORBmatcher(0.9, True, max_features=n_feat, max_pairs=n_pairs, device=device)
+    d_match = torch.empty((n_pairs, n_feat), dtype=torch.int32, device="cuda")
+    d_dist = torch.empty((n_pairs, n_feat), dtype=torch.int32, device="cuda")
+    d_nm = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    st = torch.cuda.ExternalStream(mt.stream_ptr(), device=torch.device("cuda", device))
+
+    def run():
+        mt.bruteforce_batch_device(0, pq, pt, d_desc.data_ptr(), d_ang.data_ptr(), d_cnt.data_ptr(), n_feat,
+                                   d_match.data_ptr(), d_dist.data_ptr(), d_nm.data_ptr())
+    run(); run(); mt.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        run()
+    e1.record(st)
+    mt.sync()
+    secs = e0.elapsed_time(e1) * 1e-3 / reps
+    L = eaof.lib()
+    L.eaof_debug_popc_rate.restype = C.c_double
+    L.eaof_debug_popc_rate.argtypes = [C.c_int]
+    popc = float(L.eaof_debug_popc_rate(device))
+    dists = float(n_pairs) * n_feat * n_feat
+    out = {"workload": f"configs[4]: {n_pairs} pairs of {n_feat}x{n_feat} descriptors, TH_LOW=50, ratio 0.9, rot-hist, device-resident",
+           "distances_per_s": dists / secs, "pairs_per_s": n_pairs / secs, "ms_per_sweep": secs * 1e3,
+           "matches_per_pair": float(d_nm.float().mean().item()),
+           "popc_peak_per_s": popc, "popc_frac": (8.0 * dists / secs) / popc if popc > 0 else None}
+    del st, e0, e1
+    mt.close()
+    return out
+
+
 def algorithmic_bytes(level_sizes, kp_per_frame, cand_per_frame):
     """Per-frame algorithmic bytes per stage, SURVEY.md §8(d)."""
     P = sum(w * h for w, h in level_sizes)
@@ -279,36 +344,59 @@ def main():
     ex.set_profiling(False)
     step_ms_dev = stage_acc["total"] + stage_acc["match_projection"]
 
-    # e2e through the public API: pinned host frames in, keypoints + descriptors out
-    h_frames = torch.from_numpy(frames[:B].copy()).pin_memory()
-    h_match = torch.empty((n_pairs, cap), dtype=torch.int32).pin_memory()
-    h_nm = torch.empty((n_pairs,), dtype=torch.int32).pin_memory()
-    h_kps = torch.empty((B, cap, 6), dtype=torch.float32).pin_memory()
-    h_desc = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
-    h_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
-    import ctypes as C
+    # e2e through the public C-ABI calls with HOST buffers: every step uploads its own 250 frames from pinned host memory
+    # (eaof_orb_extract_batch_async), extracts, matches, and downloads keypoints + descriptors + matches
+    # (eaof_orb_extract_batch_wait).  Two handles alternate so that the upload of one step overlaps the kernels of the
+    # previous one — the way a caller streams a sequence; nothing is skipped or reused between steps.
+    h_all = torch.from_numpy(frames).pin_memory()
+    slots = []
+    for sl in range(2):
+        exs = ex if sl == 0 else eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=B,
+                                                   device=local_rank)
+        mts = mt if sl == 0 else eaof.ORBmatcher(0.9, True, max_features=cap, max_pairs=B, device=local_rank)
+        slots.append(dict(
+            ex=exs, mt=mts, mstream=torch.cuda.ExternalStream(mts.stream_ptr(), device=torch.device("cuda", local_rank)),
+            d_match=torch.empty((n_pairs, cap), dtype=torch.int32, device="cuda"),
+            d_dist=torch.empty((n_pairs, cap), dtype=torch.int32, device="cuda"),
+            d_nm=torch.zeros(n_pairs, dtype=torch.int32, device="cuda"),
+            h_match=torch.empty((n_pairs, cap), dtype=torch.int32).pin_memory(),
+            h_nm=torch.empty((n_pairs,), dtype=torch.int32).pin_memory(),
+            h_kps=torch.empty((B, cap, 6), dtype=torch.float32).pin_memory(),
+            h_desc=torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()))
 
-    def e2e_step():
-        rc = ex.L.eaof_orb_extract_batch(ex.h, h_frames.data_ptr(), B, W, H, W, W * H, h_kps.data_ptr(),
-                                         h_desc.data_ptr(), cap, h_cnt.data_ptr())
-        if rc != 0:
-            raise RuntimeError(ex.L.eaof_last_error().decode())
-        mt.projection_batch_device(ex, pair_last, pair_cur, shift_x, shift_y, MATCH_TH, d_match.data_ptr(),
-                                   d_dist.data_ptr(), d_nm.data_ptr())
-        mt.sync()
-        h_match.copy_(d_match, non_blocking=True)
-        h_nm.copy_(d_nm, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def e2e_issue(k):
+        S = slots[k % 2]
+        b = k % n_batches
+        S["ex"].extract_batch_async(h_all.data_ptr() + b * B * frame_bytes, B, S["h_kps"].data_ptr(), S["h_desc"].data_ptr())
+        S["mt"].projection_batch_device(S["ex"], pair_last, pair_cur, shift_x, shift_y, MATCH_TH, S["d_match"].data_ptr(),
+                                        S["d_dist"].data_ptr(), S["d_nm"].data_ptr())
+        with torch.cuda.stream(S["mstream"]):
+            S["h_match"].copy_(S["d_match"], non_blocking=True)
+            S["h_nm"].copy_(S["d_nm"], non_blocking=True)
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
+    def e2e_finish(k):
+        S = slots[k % 2]
+        cnt = S["ex"].extract_batch_wait()
+        S["mt"].sync()
+        return cnt
+
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_issue(0); e2e_issue(1); e2e_finish(0); e2e_finish(1)  # warm both slots
     barrier()
-    t1 = time.perf_counter()  # host clock: the call is synchronous and includes the copies by construction
-    for _ in range(e2e_steps):
-        e2e_step()
+    t1 = time.perf_counter()  # host clock: the region ends when the last step's results are in host memory
+    e2e_issue(0)
+    for k in range(1, e2e_steps):
+        e2e_issue(k)
+        e2e_finish(k - 1)
+    last_cnt = e2e_finish(e2e_steps - 1)
     torch.cuda.synchronize()
     dt_e2e = time.perf_counter() - t1
+    assert int(last_cnt.sum()) > 0 and int(slots[(e2e_steps - 1) % 2]["h_nm"].sum()) > 0
+    e2e_launches = e2e_steps * (slots[0]["ex"].last_launch_count() + 4)
+
+    hamming = None
+    if rank == 0 or world > 1:
+        hamming = hamming_sweep(eaof, torch, local_rank)
     clocks = sampler.finish()
 
     # max over ranks
@@ -330,7 +418,9 @@ def main():
             stages[k] = {"ms_per_step": ms, "alg_bytes_per_frame": alg[k], "achieved_gbs": gbs, "frac": gbs / hbm_peak}
         dom = max(("pyramid", "fast", "octree", "blur", "angle_desc"), key=lambda k: stage_acc[k])
         roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": stages[dom]["frac"], "traffic": ncu_traffic(dom, B), "peak_source": peak_src,
+                    "alu_pipe_note": "k_fast is bound by the INT ALU issue pipe (ncu: sm__inst_executed_pipe_alu 82 % of peak, "
+                                     "dram 4 %), see profiles/",
                     "whole_path": {"alg_bytes_per_frame": sum(alg.values()),
                                    "achieved": sum(alg.values()) * value / 1e9, "frac": sum(alg.values()) * value / 1e9 / hbm_peak}}
         cores = os.cpu_count() or 1
@@ -358,6 +448,10 @@ def main():
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
                     "d2h_bytes_per_step": B * (cap * 56 + 4) + n_pairs * (cap * 4 + 4)},
             "gpu_launches": (launches_per_step + 4) * args.steps,
+            "e2e_detail": {"steps": e2e_steps, "pipeline": "2 handles alternate: upload of step k+1 under the kernels of step k",
+                           "gpu_launches": e2e_launches, "api": "eaof_orb_extract_batch_async/_wait + "
+                           "eaof_match_projection_batch_device, pinned host buffers"},
+            "hamming": hamming,
             "matching": {"kind": "consecutive-frame SearchByProjection(Cur,Last), th=15, octave+-1, rot-hist on",
                          "pairs_per_step_per_gpu": n_pairs, "matches_per_pair": matches_per_pair,
                          "ms_per_step": stage_acc["match_projection"]},
@@ -365,10 +459,15 @@ def main():
         }
         print(json.dumps(line), flush=True)
     # release everything torch holds on the library's streams before the handles (and their streams) go away
-    del xs, ms, ev0, ev1, me0, me1, h_frames, h_match, h_nm, h_kps, h_desc, h_cnt, d_match, d_dist, d_nm, d_frames
     torch.cuda.synchronize()
-    mt.close()
-    ex.close()
+    for S in slots:
+        S.pop("mstream")
+    del xs, ms, ev0, ev1, me0, me1, h_all, d_match, d_dist, d_nm, d_frames
+    torch.cuda.synchronize()
+    for S in slots:
+        S["mt"].close()
+        S["ex"].close()
+    slots.clear()
     if world > 1:
         dist.destroy_process_group()
 

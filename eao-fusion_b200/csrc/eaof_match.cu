@@ -795,6 +795,22 @@ __global__ void k_proj_prepare(const eaof_kp* __restrict__ kps, const int* __res
     }
 }
 
+
+// POPC issue-rate probe (the roofline of the Hamming kernels): 8 independent XOR+POPC+ADD chains per
+// thread, enough warps to saturate every scheduler.
+__global__ void __launch_bounds__(256) k_popc_probe(uint32_t seed, int iters, uint32_t* out) {
+    uint32_t a[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = seed * (threadIdx.x + 1u) + 0x9e3779b9u * (i + 1u); acc[i] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __popc(a[i] ^ acc[i]);
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= acc[i];
+    if (r == 0x12345678u) out[0] = r;  // never true in practice; keeps the chains alive
+}
 }  // namespace
 
 struct eaof_matcher {
@@ -1050,6 +1066,33 @@ int eaof_match_triangulation(eaof_matcher* m, int checkOri, int onlyStereo, int 
     MCK(cudaStreamSynchronize(s));
     m->lastDistances = dists;
     return EAOF_OK;
+}
+
+// Measured POPC32 thread-instructions per second on `device` (all SMs busy), or a negative value on error.
+double eaof_debug_popc_rate(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, iters = 4096;
+    k_popc_probe<<<blocks, 256>>>(1u, 64, d);
+    double best = -1.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_popc_probe<<<blocks, 256>>>(2u + rep, iters, d);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double rate = (double)blocks * 256 * 8.0 * iters / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
 }
 
 int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, int checkOri, int nPairs, const int* pairQ,

@@ -54,6 +54,11 @@ struct eaof_orb {
     cudaEvent_t evIn[kMaxChunks] = {}, evDone[kMaxChunks] = {};
     cudaEvent_t evOutIdle = nullptr;
     int chunkFrames = 0;
+    // batch issued by eaof_orb_extract_batch_async and not yet collected
+    int pendN = 0, pendCap = 0;
+    eaof_kp* pendKps = nullptr;
+    uint8_t* pendDesc = nullptr;
+    bool pendDirect = false;
     Geom g{};
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
@@ -568,11 +573,12 @@ int eaof_orb_fetch_results(eaof_orb* c, int n, eaof_kp* kps, uint8_t* desc, int 
     return EAOF_OK;
 }
 
-int eaof_orb_extract_batch(eaof_orb* c, const uint8_t* imgs, int n, int width, int height, size_t stride,
-                           size_t framePitch, eaof_kp* kps, uint8_t* desc, int cap, int* nOut) {
+int eaof_orb_extract_batch_async(eaof_orb* c, const uint8_t* imgs, int n, int width, int height, size_t stride,
+                                 size_t framePitch, eaof_kp* kps, uint8_t* desc, int cap) {
     int rc = check_shape(c, width, height, n);
     if (rc) return rc;
-    if (!imgs || !nOut || stride < (size_t)width) return fail(EAOF_ERR_ARG, "bad argument");
+    if (!imgs || stride < (size_t)width) return fail(EAOF_ERR_ARG, "bad argument");
+    if (c->pendN) return fail(EAOF_ERR_ARG, "a batch is already in flight on this handle: call eaof_orb_extract_batch_wait first");
     CK(cudaSetDevice(c->device));
     const size_t frameBytes = (size_t)width * height;
     const bool packed = stride == (size_t)width && framePitch == frameBytes;
@@ -611,8 +617,21 @@ int eaof_orb_extract_batch(eaof_orb* c, const uint8_t* imgs, int n, int width, i
         if (hD) CK(cudaMemcpyAsync(hD + (size_t)f0 * c->kpCap * 32, c->dDesc + (size_t)f0 * c->kpCap * 32, 32 * (size_t)m * c->kpCap,
                                    cudaMemcpyDeviceToHost, c->streamOut));
     }
+    c->pendN = n; c->pendCap = cap; c->pendKps = kps; c->pendDesc = desc; c->pendDirect = direct;
+    return EAOF_OK;
+}
+
+int eaof_orb_extract_batch_wait(eaof_orb* c, int* nOut) {
+    if (!c || !nOut) return fail(EAOF_ERR_ARG, "null argument");
+    if (!c->pendN) return fail(EAOF_ERR_ARG, "no batch in flight on this handle");
+    const int n = c->pendN, cap = c->pendCap;
+    eaof_kp* kps = c->pendKps;
+    uint8_t* desc = c->pendDesc;
+    const bool direct = c->pendDirect;
+    c->pendN = 0;
+    CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->streamOut));
-    rc = eaof_orb_sync(c);
+    int rc = eaof_orb_sync(c);
     if (rc) return rc;
     for (int f = 0; f < n; ++f) {
         const int k = c->hKpCount[f];
@@ -623,6 +642,22 @@ int eaof_orb_extract_batch(eaof_orb* c, const uint8_t* imgs, int n, int width, i
             if (desc) memcpy(desc + (size_t)f * cap * 32, c->hDesc + (size_t)f * c->kpCap * 32, 32 * (size_t)k);
         }
     }
+    return EAOF_OK;
+}
+
+int eaof_orb_extract_batch(eaof_orb* c, const uint8_t* imgs, int n, int width, int height, size_t stride,
+                           size_t framePitch, eaof_kp* kps, uint8_t* desc, int cap, int* nOut) {
+    if (!nOut) return fail(EAOF_ERR_ARG, "bad argument");
+    int rc = eaof_orb_extract_batch_async(c, imgs, n, width, height, stride, framePitch, kps, desc, cap);
+    if (rc) return rc;
+    return eaof_orb_extract_batch_wait(c, nOut);
+}
+
+int eaof_orb_set_pipeline_chunk(eaof_orb* c, int frames) {
+    if (!c || frames < 0) return fail(EAOF_ERR_ARG, "bad argument");
+    if (frames == 0) frames = std::max(8, 444 / std::max(1, c->p.nlevels));
+    frames = std::max(frames, (c->p.max_batch + eaof_orb::kMaxChunks - 1) / eaof_orb::kMaxChunks);
+    c->chunkFrames = std::min(frames, c->p.max_batch);
     return EAOF_OK;
 }
 

@@ -47,6 +47,9 @@ def lib():
         L.eaof_orb_level_size.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
         L.eaof_orb_extract.argtypes = [vp, vp, ci, ci, sz, vp, vp, ci, C.POINTER(ci)]
         L.eaof_orb_extract_batch.argtypes = [vp, vp, ci, ci, ci, sz, sz, vp, vp, ci, vp]
+        L.eaof_orb_extract_batch_async.argtypes = [vp, vp, ci, ci, ci, sz, sz, vp, vp, ci]
+        L.eaof_orb_extract_batch_wait.argtypes = [vp, vp]
+        L.eaof_orb_set_pipeline_chunk.argtypes = [vp, ci]
         L.eaof_orb_extract_batch_device.argtypes = [vp, vp, ci, ci, ci, sz, sz]
         L.eaof_orb_sync.argtypes = [vp]
         L.eaof_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ci)]
@@ -150,6 +153,21 @@ class ORBextractor:
         _ck(self.L.eaof_orb_extract_batch(self.h, frames.ctypes.data, n, w, h, w, w * h, kps.ctypes.data,
                                           desc.ctypes.data, self.cap, cnt.ctypes.data))
         return [(kps[f, :cnt[f]].copy(), desc[f, :cnt[f]].copy()) for f in range(n)]
+
+    def extract_batch_async(self, frames_ptr: int, n: int, kps_ptr: int, desc_ptr: int):
+        """Enqueue upload + kernels + download of n packed frames at host address frames_ptr (pinned); outputs laid
+        out [n][cap] at kps_ptr / desc_ptr.  Collect with extract_batch_wait()."""
+        _ck(self.L.eaof_orb_extract_batch_async(self.h, frames_ptr, n, self.width, self.height, self.width,
+                                                self.width * self.height, kps_ptr, desc_ptr, self.cap))
+        self._pending_n = n
+
+    def extract_batch_wait(self):
+        cnt = np.zeros(self._pending_n, np.int32)
+        _ck(self.L.eaof_orb_extract_batch_wait(self.h, cnt.ctypes.data))
+        return cnt
+
+    def set_pipeline_chunk(self, frames: int):
+        _ck(self.L.eaof_orb_set_pipeline_chunk(self.h, frames))
 
     def extract_batch_device(self, d_ptr: int, n: int, stride=None, frame_pitch=None):
         stride = stride or self.width

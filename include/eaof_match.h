@@ -110,6 +110,10 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float nnratio,
                                        const float* d_angle, const int* d_counts, int block_stride, int* d_match,
                                        int* d_dist, int* d_nmatches);
 
+/* Micro-benchmark: POPC32 thread-instructions per second this device sustains with every SM busy (the issue-rate
+ * roofline of the Hamming kernels); negative on error. */
+double eaof_debug_popc_rate(int device);
+
 /* Number of descriptor-pair distances the last batched call evaluated (for the matches/s metric). */
 long long eaof_matcher_last_distance_count(const eaof_matcher* m);
 

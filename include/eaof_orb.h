@@ -95,6 +95,16 @@ int eaof_orb_extract(eaof_orb* ctx, const uint8_t* img, int width, int height, s
 int eaof_orb_extract_batch(eaof_orb* ctx, const uint8_t* imgs, int n_frames, int width, int height, size_t stride,
                            size_t frame_pitch, eaof_kp* kps, uint8_t* desc, int cap, int* n_out);
 
+/* The same call in two halves, so that a caller can keep several handles busy (upload of one batch under the kernels of
+ * another): _async enqueues upload, kernels and download and returns; _wait blocks until the outputs passed to _async
+ * are complete and delivers the per-frame counts.  One batch in flight per handle.  Buffers should be pinned. */
+int eaof_orb_extract_batch_async(eaof_orb* ctx, const uint8_t* imgs, int n_frames, int width, int height, size_t stride,
+                                 size_t frame_pitch, eaof_kp* kps, uint8_t* desc, int cap);
+int eaof_orb_extract_batch_wait(eaof_orb* ctx, int* n_out);
+/* Frames per chunk of the upload / kernels / download pipeline inside the host-buffer calls (0 = default heuristic;
+ * >= n_frames disables chunking).  Also settable at create time through $EAOF_CHUNK. */
+int eaof_orb_set_pipeline_chunk(eaof_orb* ctx, int frames);
+
 /* Same, with the frames already resident in device memory (d_imgs, tightly packed rows of `stride` bytes); results
  * stay on the device.  Asynchronous on the handle's stream; use eaof_orb_sync or the accessors below. */
 int eaof_orb_extract_batch_device(eaof_orb* ctx, const uint8_t* d_imgs, int n_frames, int width, int height,

@@ -61,8 +61,9 @@ def tri_inputs(seed, n1=500, n2=600, nn=8):
     y2[dst] = (y1[src] + rng.normal(0, 1.5, m)).astype(np.float32)
     node2[dst] = node1[src]
     # exact duplicates of some planted targets inside the same node: equal distance, the LATER candidate must win (:738)
-    extra = rng.permutation(n2)[:20]
-    twin = dst[:20]
+    ntw = min(20, m)
+    extra = rng.permutation(n2)[:ntw]
+    twin = dst[:ntw]
     d2[extra] = d2[twin]; y2[extra] = y2[twin]; node2[extra] = node2[twin]; a2[extra] = a2[twin]
     k1 = dict(desc=d1, angle=a1, x=x1, y=y1, free=(rng.random(n1) > 0.2).astype(np.uint8),
               stereo=(rng.random(n1) > 0.5).astype(np.uint8), nodes=_csr(node1))
