@@ -459,15 +459,18 @@ def main():
         }
         print(json.dumps(line), flush=True)
     # release everything torch holds on the library's streams before the handles (and their streams) go away
+    # release everything torch holds on the library's streams (pinned tensors record an event on every stream that
+    # used them when they are freed) before the handles, and with them the streams, go away
     torch.cuda.synchronize()
-    for S in slots:
-        S.pop("mstream")
-    del xs, ms, ev0, ev1, me0, me1, h_all, d_match, d_dist, d_nm, d_frames
-    torch.cuda.synchronize()
-    for S in slots:
-        S["mt"].close()
-        S["ex"].close()
+    handles = [(S["ex"], S["mt"]) for S in slots]
     slots.clear()
+    del xs, ms, ev0, ev1, me0, me1, h_all, d_match, d_dist, d_nm, d_frames
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    for ex_, mt_ in handles:
+        mt_.close()
+        ex_.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -109,6 +109,50 @@ dist.destroy_process_group()
     assert "W2 OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_sweep_block_gather_world_size_2_gloo(tmp_path):
+    """The one exchange step of the path (all-gather of descriptor blocks for the cross-frame sweep) over gloo with CPU
+    tensors: gathered blocks land at global_block(frame), padding blocks are empty, and the round-robin pair shares of
+    the two ranks cover the global pair list exactly once."""
+    script = tmp_path / "sw2.py"
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "eao-fusion_b200"))
+import numpy as np, torch, torch.distributed as dist
+from eaof import shard, sweep
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n_frames, stride = 7, 5                      # ragged: rank 0 owns 4 frames, rank 1 owns 3 (+1 padding block)
+b, e = shard.frame_block(n_frames, rank, world)
+def block(f):
+    rng = np.random.Generator(np.random.PCG64(f))
+    return rng.integers(0, 256, (stride, 32), dtype=np.uint8), rng.uniform(0, 360, stride).astype(np.float32), 1 + f % stride
+loc = [block(f) for f in range(b, e)]
+desc = torch.from_numpy(np.stack([x[0] for x in loc])); ang = torch.from_numpy(np.stack([x[1] for x in loc]))
+cnt = torch.tensor([x[2] for x in loc], dtype=torch.int32)
+gd, ga, gc = sweep.gather_blocks(desc, ang, cnt, n_frames, dist)
+per = sweep.padded_blocks(n_frames, world)
+assert gd.shape == (world * per, stride, 32) and gc.shape == (world * per,)
+for f in range(n_frames):
+    g = sweep.global_block(f, n_frames, world)
+    d, a, c = block(f)
+    assert np.array_equal(gd[g].numpy(), d) and np.array_equal(ga[g].numpy(), a) and int(gc[g]) == c, f
+assert int(gc[world * per - 1]) == 0          # padding block of the last rank
+pairs = np.array([(i, j) for i in range(n_frames) for j in range(n_frames) if i != j])
+sel, pq, pt = sweep.my_pairs(pairs, n_frames, rank, world)
+assert all(pq[k] == sweep.global_block(pairs[i, 0], n_frames, world) for k, i in enumerate(sel))
+mine = torch.zeros(len(pairs), dtype=torch.int64); mine[torch.from_numpy(sel)] = 1
+dist.all_reduce(mine)
+assert mine.tolist() == [1] * len(pairs)
+if rank == 0: print("SW2 OK")
+dist.destroy_process_group()
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert "SW2 OK" in out.stdout, out.stdout + out.stderr
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # matcher oracle vs. independent pure-Python restatements of the same reference loops
 
