@@ -15,6 +15,7 @@
 // candidates than the list holds, phase 2 re-scans that query exactly.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -461,6 +462,7 @@ __global__ void __launch_bounds__(256) k_tri_finish(TriArgs A, int* __restrict__
 
 // ---------------------------------------------------------------------------------------------------------
 // SearchByProjection(Cur, Last)
+__device__ __forceinline__ void level_window(int searchMode, int oct, int& minLevel, int& maxLevel);
 struct ProjArgs {
     // Cur side, [pair][stride]
     const float* cx; const float* cy; const int* coct; const float* cangle; const float* curight; const uint8_t* ctaken;
@@ -476,7 +478,37 @@ struct ProjArgs {
     float scale[EAOF_MAX_LEVELS];
     float th, mbf;
     int searchMode, checkOri;
+    // generalised window queries (eaof_match_windows): per-query radius / level window / predicted right coordinate
+    // replace th*scale[octave], the searchMode window and u - mbf/z; NULL = SearchByProjection(Cur,Last) behaviour
+    const float* qRadius; const int* qMinL; const int* qMaxL; const float* qUr;
+    int thAccept;      // accept best <= thAccept (TH_HIGH, or ORBdist of SearchByProjection(Cur,KF))
+    int cut;           // phase 1 keeps candidates with dist <= cut
+    int histMode;      // 0: no rotation check, 1: factor 1/HISTO_LENGTH, 2: factor HISTO_LENGTH/360
+    int checkBounds;   // skip queries projected outside [minX,maxX]x[minY,maxY]
+    float ratio;       // rule EAOF_WIN_RATIO_SAME_LEVEL
 };
+
+// window of query i of pair `pair`; false when the query is skipped before the search
+__device__ __forceinline__ bool query_window(const ProjArgs& A, size_t po, int i, float& u, float& v, float& r, int& minLevel,
+                                             int& maxLevel, float& ur) {
+    const float invz = A.linvz ? A.linvz[po + i] : 1.f;
+    u = A.lu[po + i];
+    v = A.lv[po + i];
+    if (A.lvalid && !A.lvalid[po + i]) return false;
+    if (invz < 0) return false;
+    if (A.checkBounds && ((u < A.minX || u > A.maxX) || (v < A.minY || v > A.maxY))) return false;
+    if (A.qRadius) {
+        r = A.qRadius[po + i];
+        minLevel = A.qMinL[po + i];
+        maxLevel = A.qMaxL[po + i];
+    } else {
+        const int oct = A.loct[po + i];
+        r = __fmul_rn(A.th, A.scale[oct]);
+        level_window(A.searchMode, oct, minLevel, maxLevel);
+    }
+    ur = A.qUr ? A.qUr[po + i] : __fsub_rn(u, __fmul_rn(A.mbf, invz));
+    return true;
+}
 
 // Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:599-614,751-761): one CTA per pair builds the CSR grid of
 // the Cur frame; cell lists are sorted ascending so they equal the reference's push_back order.
@@ -577,14 +609,10 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
     uint32_t top[TOP_K];
 #pragma unroll
     for (int k = 0; k < TOP_K; ++k) top[k] = 0xffffffffu;
-    const float invz = A.linvz ? A.linvz[po + i] : 1.f;
-    const float u = A.lu[po + i], v = A.lv[po + i];
-    const bool ok = (!A.lvalid || A.lvalid[po + i]) && !(invz < 0) && !(u < A.minX || u > A.maxX) && !(v < A.minY || v > A.maxY);
+    float u, v, r, ur;
+    int minLevel, maxLevel;
+    const bool ok = query_window(A, po, i, u, v, r, minLevel, maxLevel, ur);
     if (ok) {
-        const int oct = A.loct[po + i];
-        const float r = __fmul_rn(A.th, A.scale[oct]);
-        int minLevel, maxLevel;
-        level_window(A.searchMode, oct, minLevel, maxLevel);
         uint32_t qd[8];
         {
             const uint4* p = reinterpret_cast<const uint4*>(A.desc + 32 * ((size_t)A.lRow[pair] + i));
@@ -593,7 +621,6 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
         }
         const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
         const float* cur = A.curight ? A.curight + po : nullptr;
-        const float ur = __fsub_rn(u, __fmul_rn(A.mbf, invz));
         count = 0;
         for_each_candidate(A, cellStart + (size_t)pair * (GRID_CELLS + 1), cellIdx + po, A.cx + po, A.cy + po, A.coct + po,
                            u, v, r, minLevel, maxLevel, [&](int k) {
@@ -603,7 +630,7 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
             const uint4 a = p[0], b = p[1];
             td[0] = a.x; td[1] = a.y; td[2] = a.z; td[3] = a.w; td[4] = b.x; td[5] = b.y; td[6] = b.z; td[7] = b.w;
             const uint32_t d = (uint32_t)hamming256(qd, td);
-            if (d > EAOF_TH_HIGH) return;  // can never be accepted (:1428), so it need not be kept, counted or re-scanned
+            if (d > (uint32_t)A.cut) return;  // can never influence the outcome, so it need not be kept, counted or re-scanned
             uint32_t e = (d << 16) | (uint32_t)k;
             // insertion into the sorted top-K by distance only; ties keep the earlier arrival in front
             bool shifting = false;  // once inserted, everything behind moves down one slot
@@ -639,7 +666,7 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
     if (A.ctaken)
         for (int i = lane; i < nC; i += 32) if (A.ctaken[po + i]) atomicOr(&smem[i >> 5], 1u << (i & 31));
     __syncwarp();
-    const float factor = EAOF_HISTO_LENGTH / 360.0f;  // :1337
+    const float factor = A.histMode == 2 ? EAOF_HISTO_LENGTH / 360.0f : 1.0f / EAOF_HISTO_LENGTH;  // :1337 vs :1486
     // The reference walks the Last features in index order and each accepted match may make its Cur feature
     // unavailable to every later query (:1405-1407).  32 queries are resolved at a time: every lane proposes the
     // first candidate of its list that is still free, all lanes below the first lane whose proposal collides with a
@@ -707,19 +734,15 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
                 int bestDist = 256, bestIdx = -1;
                 if (lane == c) {
                     const int i = mine;
-                    const float u = A.lu[po + i], v = A.lv[po + i];
-                    const float invz = A.linvz ? A.linvz[po + i] : 1.f;
-                    const int oct = A.loct[po + i];
-                    const float r = __fmul_rn(A.th, A.scale[oct]);
+                    float u, v, r, ur;
                     int minLevel, maxLevel;
-                    level_window(A.searchMode, oct, minLevel, maxLevel);
+                    query_window(A, po, i, u, v, r, minLevel, maxLevel, ur);
                     uint32_t qd[8];
                     const uint4* p = reinterpret_cast<const uint4*>(A.desc + 32 * ((size_t)A.lRow[pair] + i));
                     const uint4 a = p[0], b = p[1];
                     qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
                     const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
                     const float* cur = A.curight ? A.curight + po : nullptr;
-                    const float ur = __fsub_rn(u, __fmul_rn(A.mbf, invz));
                     for_each_candidate(A, cellStart + (size_t)pair * (GRID_CELLS + 1), cellIdx + po, A.cx + po, A.cy + po,
                                        A.coct + po, u, v, r, minLevel, maxLevel, [&](int k) {
                         if ((smem[k >> 5] >> (k & 31)) & 1u) return;
@@ -731,7 +754,7 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
                         const int d = hamming256(qd, td);
                         if (d < bestDist) { bestDist = d; bestIdx = k; }
                     });
-                    if (bestDist > EAOF_TH_HIGH) bestIdx = -1;  // :1428
+                    if (bestDist > A.thAccept) bestIdx = -1;  // :1428 / :1558
                     if (bestIdx >= 0) {
                         mOut[bestIdx] = i;
                         if (dOut) dOut[bestIdx] = bestDist;
@@ -748,7 +771,7 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
     __syncwarp();
     // rotation histogram, ComputeThreeMaxima and pruning (:1448-1469), bins computed in parallel after the loop
     int removed = 0;
-    if (A.checkOri) {
+    if (A.checkOri && A.histMode) {
         for (int k = lane; k < nAcc; k += 32) {
             const uint32_t a = acc[k];
             atomicAdd(&hist[rot_bin(A.langle[po + (a & 0xffff)], A.cangle[po + (a >> 16)], factor)], 1);
@@ -772,6 +795,105 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
         for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
     }
     if (lane == 0) nMatches[pair] = nAcc - removed;
+}
+
+// phase 2 of the ratio rule (SearchByProjection(Frame&, vector<MapPoint*>&, th), src/ORBmatcher.cc:45-129): one warp,
+// queries strictly in order.  Phase 1 left, per query, the candidates with dist <= cut sorted by (dist, arrival) —
+// exactly the order in which the reference's best / second-best bookkeeping ranks them — so best and second are the
+// first two entries whose target is still free.  A second that phase 1 did not keep is > cut and passes the ratio test
+// for every acceptable best.  A match is rejected only when best and second lie on the same pyramid level and
+// best > ratio*second (:118-121).
+__global__ void __launch_bounds__(32) k_win_resolve_ratio(ProjArgs A, const int* __restrict__ cellStart,
+                                                          const int* __restrict__ cellIdx, const uint32_t* __restrict__ topBuf,
+                                                          int* __restrict__ matchOut, int* __restrict__ distOut,
+                                                          int* __restrict__ nMatches) {
+    extern __shared__ uint32_t smem[];  // taken bitmap
+    const int pair = blockIdx.x, lane = threadIdx.x;
+    const size_t po = (size_t)pair * A.stride;
+    const int nC = A.nC[pair], nL = A.nL[pair];
+    int* mOut = matchOut + po;
+    int* dOut = distOut ? distOut + po : nullptr;
+    const int* coct = A.coct + po;
+    const int words = (A.stride + 31) >> 5;
+    for (int i = lane; i < words; i += 32) smem[i] = 0;
+    for (int i = lane; i < nC; i += 32) { mOut[i] = -1; if (dOut) dOut[i] = -1; }
+    __syncwarp();
+    if (A.ctaken)
+        for (int i = lane; i < nC; i += 32) if (A.ctaken[po + i]) atomicOr(&smem[i >> 5], 1u << (i & 31));
+    __syncwarp();
+    int nAcc = 0;
+    for (int i0 = 0; i0 < nL; i0 += 32) {
+        const int mine = i0 + lane;
+        uint4 w0 = make_uint4(~0u, ~0u, ~0u, ~0u), w1 = make_uint4(~0u, ~0u, 0u, 0u);
+        if (mine < nL) {
+            const uint4* p = reinterpret_cast<const uint4*>(topBuf + (po + mine) * 8);
+            w0 = p[0];
+            w1 = p[1];
+        }
+        const int myCnt = mine < nL ? (int)w1.w : 0;
+        unsigned rem = __ballot_sync(0xffffffffu, myCnt > 0);
+        while (rem) {
+            const int j = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const int q = i0 + j;
+            const int cnt = __shfl_sync(0xffffffffu, myCnt, j);
+            const uint32_t e[TOP_K] = {__shfl_sync(0xffffffffu, w0.x, j), __shfl_sync(0xffffffffu, w0.y, j),
+                                       __shfl_sync(0xffffffffu, w0.z, j), __shfl_sync(0xffffffffu, w0.w, j),
+                                       __shfl_sync(0xffffffffu, w1.x, j), __shfl_sync(0xffffffffu, w1.y, j)};
+            int best = 256, best2 = 256, bestIdx = -1, lvl = -1, lvl2 = -1, found = 0;
+#pragma unroll
+            for (int k = 0; k < TOP_K; ++k) {
+                if (k < cnt && found < 2) {
+                    const int t = e[k] & 0xffff, d = (int)(e[k] >> 16);
+                    if (!((smem[t >> 5] >> (t & 31)) & 1u)) {
+                        if (found == 0) { best = d; bestIdx = t; lvl = coct[t]; }
+                        else { best2 = d; lvl2 = coct[t]; }
+                        ++found;
+                    }
+                }
+            }
+            if (cnt > TOP_K && found < 2) {
+                // more near candidates than the list holds and too many of the kept ones are taken: exact sequential
+                // re-scan of this query (rare), every lane redundantly so the result is warp-uniform
+                float u, v, r, ur;
+                int minLevel, maxLevel;
+                query_window(A, po, q, u, v, r, minLevel, maxLevel, ur);
+                uint32_t qd[8];
+                const uint4* p = reinterpret_cast<const uint4*>(A.desc + 32 * ((size_t)A.lRow[pair] + q));
+                const uint4 a = p[0], b = p[1];
+                qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+                const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
+                const float* cur = A.curight ? A.curight + po : nullptr;
+                best = 256; best2 = 256; bestIdx = -1; lvl = -1; lvl2 = -1;
+                for_each_candidate(A, cellStart + (size_t)pair * (GRID_CELLS + 1), cellIdx + po, A.cx + po, A.cy + po, coct,
+                                   u, v, r, minLevel, maxLevel, [&](int k) {
+                    if ((smem[k >> 5] >> (k & 31)) & 1u) return;
+                    if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) return;
+                    uint32_t td[8];
+                    const uint4* pp = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
+                    const uint4 a2 = pp[0], b2 = pp[1];
+                    td[0] = a2.x; td[1] = a2.y; td[2] = a2.z; td[3] = a2.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
+                    const int d = hamming256(qd, td);
+                    if (d < best) { best2 = best; best = d; lvl2 = lvl; lvl = coct[k]; bestIdx = k; }
+                    else if (d < best2) { lvl2 = coct[k]; best2 = d; }
+                });
+            }
+            if (bestIdx >= 0 && best <= A.thAccept) {
+                if (!(lvl == lvl2 && (float)best > __fmul_rn(A.ratio, (float)best2))) {
+                    const int obs = A.lobs ? (A.lobs[po + q] != 0) : 1;
+                    if (lane == 0) {
+                        mOut[bestIdx] = q;
+                        if (dOut) dOut[bestIdx] = best;
+                        if (obs) smem[bestIdx >> 5] |= 1u << (bestIdx & 31);
+                    }
+                    ++nAcc;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    // the reference counts accepted queries (nmatches++ per assignment, :123-124), also when a later query overwrites
+    if (lane == 0) nMatches[pair] = nAcc;
 }
 
 // Queries of the consecutive-frame path: Last keypoints of an extractor batch shifted by the known motion.
@@ -824,6 +946,8 @@ struct eaof_matcher {
           *linvz = nullptr, *langle = nullptr;
     int *coct = nullptr, *loct = nullptr, *nC = nullptr, *nL = nullptr, *cRow = nullptr, *lRow = nullptr;
     uint8_t *ctaken = nullptr, *lvalid = nullptr, *lobs = nullptr;
+    float* qRadius = nullptr;   // eaof_match_windows: per-query radius and upper level
+    int* qMaxL = nullptr;
     // single-pair host API staging
     uint8_t* desc2 = nullptr;   // 2 blocks of maxFeat descriptors
     float* angle2 = nullptr;    // 2 blocks of maxFeat angles
@@ -872,6 +996,7 @@ int eaof_matcher_create(int device, int maxPairs, int maxFeat, eaof_matcher** ou
     A_(dalloc(&m->coct, PF)); A_(dalloc(&m->loct, PF));
     A_(dalloc(&m->nC, maxPairs)); A_(dalloc(&m->nL, maxPairs)); A_(dalloc(&m->cRow, maxPairs)); A_(dalloc(&m->lRow, maxPairs));
     A_(dalloc(&m->ctaken, PF)); A_(dalloc(&m->lvalid, PF)); A_(dalloc(&m->lobs, PF));
+    A_(dalloc(&m->qRadius, (size_t)maxFeat)); A_(dalloc(&m->qMaxL, (size_t)maxFeat));
     A_(dalloc(&m->desc2, (size_t)2 * maxFeat * 32)); A_(dalloc(&m->angle2, (size_t)2 * maxFeat));
     A_(dalloc(&m->validQ, maxFeat)); A_(dalloc(&m->validT, maxFeat)); A_(dalloc(&m->idxQ, maxFeat)); A_(dalloc(&m->idxT, maxFeat));
     A_(dalloc(&m->segs, maxFeat)); A_(dalloc(&m->segStart, 2)); A_(dalloc(&m->tiles, (size_t)2 * maxFeat));
@@ -894,7 +1019,7 @@ void eaof_matcher_destroy(eaof_matcher* m) {
     void* ptrs[] = {m->nearBuf, m->accBuf, m->cellStart, m->cellIdx, m->cx, m->cy, m->cangle, m->curight, m->lu, m->lv,
                     m->linvz, m->langle, m->coct, m->loct, m->nC, m->nL, m->cRow, m->lRow, m->ctaken, m->lvalid, m->lobs,
                     m->desc2, m->angle2, m->validQ, m->validT, m->idxQ, m->idxT, m->segs, m->segStart, m->tiles,
-                    m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN};
+                    m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN, m->qRadius, m->qMaxL};
     for (void* p : ptrs) cudaFree(p);
     if (m->evDep) cudaEventDestroy(m->evDep);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -1166,6 +1291,7 @@ int eaof_match_projection(eaof_matcher* m, int nC, const float* cx, const float*
     A.minX = minX; A.maxX = maxX; A.minY = minY; A.maxY = maxY; A.invW = invW; A.invH = invH;
     for (int i = 0; i < nLevels; ++i) A.scale[i] = scaleFactors[i];
     A.th = th; A.mbf = mbf; A.searchMode = searchMode; A.checkOri = checkOri;
+    A.thAccept = EAOF_TH_HIGH; A.cut = EAOF_TH_HIGH; A.histMode = 2; A.checkBounds = 1;
     int rc = run_projection(m, A, 1, nL, m->outMatch, m->outDist, m->outN);
     if (rc) return rc;
     MCK(cudaMemcpyAsync(matchCur, m->outMatch, sizeof(int) * nC, cudaMemcpyDeviceToHost, s));
@@ -1175,9 +1301,77 @@ int eaof_match_projection(eaof_matcher* m, int nC, const float* cx, const float*
     return EAOF_OK;
 }
 
+int eaof_match_windows(eaof_matcher* m, int rule, int nT, const float* tx, const float* ty, const int* toct,
+                       const float* tangle, const uint8_t* tdesc, const float* turight, const uint8_t* ttaken, float minX,
+                       float maxX, float minY, float maxY, float invW, float invH, int nQ, const uint8_t* qValid,
+                       const float* qU, const float* qV, const float* qRadius, const int* qMinLevel, const int* qMaxLevel,
+                       const float* qUr, const float* qAngle, const uint8_t* qDesc, const uint8_t* qObs, int thAccept,
+                       float nnratio, int histMode, int checkBounds, int* matchT, int* distT, int* nMatches) {
+    if (!m || !matchT || !nMatches || nT < 0 || nQ < 0) return mfail(EAOF_ERR_ARG, "bad argument");
+    if (rule != EAOF_WIN_BEST && rule != EAOF_WIN_RATIO_SAME_LEVEL) return mfail(EAOF_ERR_ARG, "unknown rule");
+    if (nT > m->maxFeat || nQ > m->maxFeat) return mfail(EAOF_ERR_ARG, "feature count exceeds max_features=%d", m->maxFeat);
+    if (histMode < 0 || histMode > 2 || thAccept < 0 || thAccept > 256) return mfail(EAOF_ERR_ARG, "bad hist_mode / th_accept");
+    *nMatches = 0;
+    for (int i = 0; i < nT; ++i) { matchT[i] = -1; if (distT) distT[i] = -1; }
+    if (nT == 0 || nQ == 0) return EAOF_OK;
+    if (!tx || !ty || !toct || !tdesc || !qU || !qV || !qRadius || !qMinLevel || !qMaxLevel || !qDesc) return mfail(EAOF_ERR_ARG, "null array");
+    if (histMode && (!tangle || !qAngle)) return mfail(EAOF_ERR_ARG, "rotation check needs angles");
+    if (turight && !qUr) return mfail(EAOF_ERR_ARG, "t_uright given without q_ur");
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+#define UP(dst, src, n, T) MCK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(n), cudaMemcpyHostToDevice, s))
+    UP(m->cx, tx, nT, float); UP(m->cy, ty, nT, float); UP(m->coct, toct, nT, int);
+    if (tangle) UP(m->cangle, tangle, nT, float);
+    if (turight) UP(m->curight, turight, nT, float);
+    if (ttaken) UP(m->ctaken, ttaken, nT, uint8_t);
+    UP(m->lu, qU, nQ, float); UP(m->lv, qV, nQ, float); UP(m->qRadius, qRadius, nQ, float);
+    UP(m->loct, qMinLevel, nQ, int); UP(m->qMaxL, qMaxLevel, nQ, int);
+    if (qUr) UP(m->linvz, qUr, nQ, float);
+    if (qAngle) UP(m->langle, qAngle, nQ, float);
+    if (qValid) UP(m->lvalid, qValid, nQ, uint8_t);
+    if (qObs) UP(m->lobs, qObs, nQ, uint8_t);
+    UP(m->desc2, tdesc, 32 * (size_t)nT, uint8_t);
+    UP(m->desc2 + 32 * (size_t)m->maxFeat, qDesc, 32 * (size_t)nQ, uint8_t);
+    const int hdr[4] = {nT, nQ, 0, m->maxFeat};
+    UP(m->nC, &hdr[0], 1, int); UP(m->nL, &hdr[1], 1, int); UP(m->cRow, &hdr[2], 1, int); UP(m->lRow, &hdr[3], 1, int);
+#undef UP
+    ProjArgs A{};
+    A.cx = m->cx; A.cy = m->cy; A.coct = m->coct; A.cangle = m->cangle; A.curight = turight ? m->curight : nullptr;
+    A.ctaken = ttaken ? m->ctaken : nullptr; A.nC = m->nC; A.lu = m->lu; A.lv = m->lv; A.linvz = nullptr;
+    A.loct = m->loct; A.langle = m->langle; A.lvalid = qValid ? m->lvalid : nullptr; A.lobs = qObs ? m->lobs : nullptr;
+    A.nL = m->nL; A.desc = m->desc2; A.cRow = m->cRow; A.lRow = m->lRow; A.stride = m->maxFeat;
+    A.minX = minX; A.maxX = maxX; A.minY = minY; A.maxY = maxY; A.invW = invW; A.invH = invH;
+    A.qRadius = m->qRadius; A.qMinL = m->loct; A.qMaxL = m->qMaxL; A.qUr = qUr ? m->linvz : m->lu;  // without a stereo
+    A.checkOri = histMode != 0; A.histMode = histMode; A.checkBounds = checkBounds;                  // prediction qUr is never read
+    A.thAccept = thAccept; A.ratio = nnratio;
+    if (rule == EAOF_WIN_BEST) {
+        A.cut = thAccept;
+    } else {
+        int sMin = 0;  // smallest second-best that passes "best <= ratio*second" for every best <= thAccept
+        while (sMin <= 256 && (float)thAccept > nnratio * (float)sMin) ++sMin;
+        A.cut = std::min(256, std::max(sMin, thAccept + 1)) - 1;
+        if (A.cut < thAccept) A.cut = thAccept;
+    }
+    if (!turight) A.curight = nullptr;
+    k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx);
+    k_proj_dense<<<dim3((nQ + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
+    const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
+    if (rule == EAOF_WIN_BEST)
+        k_proj_resolve<<<1, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->accBuf, m->outMatch, m->outDist, m->outN);
+    else
+        k_win_resolve_ratio<<<1, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->outMatch, m->outDist, m->outN);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(matchT, m->outMatch, sizeof(int) * nT, cudaMemcpyDeviceToHost, s));
+    if (distT) MCK(cudaMemcpyAsync(distT, m->outDist, sizeof(int) * nT, cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    return EAOF_OK;
+}
+
 // accessors implemented in eaof_orb.cu
 int eaof_internal_orb_view(eaof_orb* ex, const eaof_kp** kps, const uint8_t** desc, const int** counts, int* cap, int* w,
                            int* h, const float** scale, int* nlevels, void** stream);
+int eaof_internal_orb_note_reader(eaof_orb* ex, void* readerStream);
 
 int eaof_match_projection_batch_device(eaof_matcher* m, eaof_orb* ex, int nPairs, const int* lastFrame, const int* curFrame,
                                        const float* shiftX, const float* shiftY, float th, int* dMatch, int* dDist, int* dN) {
@@ -1211,7 +1405,10 @@ int eaof_match_projection_batch_device(eaof_matcher* m, eaof_orb* ex, int nPairs
     A.invW = (float)GRID_COLS / (A.maxX - A.minX); A.invH = (float)GRID_ROWS / (A.maxY - A.minY);
     for (int i = 0; i < nlevels; ++i) A.scale[i] = scale[i];
     A.th = th; A.mbf = 0.f; A.searchMode = 0; A.checkOri = 1;
-    return run_projection(m, A, nPairs, cap, dMatch, dDist, dN);
+    A.thAccept = EAOF_TH_HIGH; A.cut = EAOF_TH_HIGH; A.histMode = 2; A.checkBounds = 1;
+    rc = run_projection(m, A, nPairs, cap, dMatch, dDist, dN);
+    if (rc) return rc;
+    return eaof_internal_orb_note_reader(ex, (void*)s);  // the extractor must not overwrite what these kernels still read
 }
 
 }  // extern "C"

@@ -54,6 +54,10 @@ struct eaof_orb {
     cudaEvent_t evIn[kMaxChunks] = {}, evDone[kMaxChunks] = {};
     cudaEvent_t evOutIdle = nullptr;
     int chunkFrames = 0;
+    // a matcher that reads dKps/dDesc/dKpCount in place on its own stream leaves this event behind; the next batch's
+    // k_angle_desc (the only writer of those buffers) waits for it
+    cudaEvent_t evReader = nullptr;
+    bool readerPending = false;
     // batch issued by eaof_orb_extract_batch_async and not yet collected
     int pendN = 0, pendCap = 0;
     eaof_kp* pendKps = nullptr;
@@ -316,6 +320,10 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         CK(cudaStreamWaitEvent(s, c->evBlur, 0));
     }
     if (prof) CK(cudaEventRecord(c->ev[4], s));
+    if (c->readerPending) {
+        CK(cudaStreamWaitEvent(s, c->evReader, 0));
+        c->readerPending = false;
+    }
     {
         const int warpsPerBlock = 8;
         dim3 gr((g.slotsPerFrame + warpsPerBlock - 1) / warpsPerBlock, n);
@@ -388,6 +396,7 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     CKD(cudaStreamCreateWithFlags(&c->streamIn, cudaStreamNonBlocking));
     CKD(cudaStreamCreateWithFlags(&c->streamOut, cudaStreamNonBlocking));
     CKD(cudaEventCreateWithFlags(&c->evOutIdle, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->evReader, cudaEventDisableTiming));
     for (int i = 0; i < eaof_orb::kMaxChunks; ++i) {
         CKD(cudaEventCreateWithFlags(&c->evIn[i], cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&c->evDone[i], cudaEventDisableTiming));
@@ -495,6 +504,7 @@ void eaof_orb_destroy(eaof_orb* c) {
         if (c->evDone[i]) cudaEventDestroy(c->evDone[i]);
     }
     if (c->evOutIdle) cudaEventDestroy(c->evOutIdle);
+    if (c->evReader) cudaEventDestroy(c->evReader);
     if (c->streamIn) { cudaStreamSynchronize(c->streamIn); cudaStreamDestroy(c->streamIn); }
     if (c->streamOut) { cudaStreamSynchronize(c->streamOut); cudaStreamDestroy(c->streamOut); }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -767,6 +777,14 @@ int eaof_internal_orb_view(eaof_orb* c, const eaof_kp** kps, const uint8_t** des
     if (!c) return fail(EAOF_ERR_ARG, "null extractor handle");
     *kps = c->dKps; *desc = c->dDesc; *counts = c->dKpCount; *cap = c->kpCap; *w = c->p.width; *h = c->p.height;
     *scale = c->scale.data(); *nlevels = c->p.nlevels; *stream = (void*)c->stream;
+    return EAOF_OK;
+}
+
+// called by a consumer right after it enqueued its last read of the result buffers on `readerStream`
+int eaof_internal_orb_note_reader(eaof_orb* c, void* readerStream) {
+    if (!c) return fail(EAOF_ERR_ARG, "null extractor handle");
+    CK(cudaEventRecord(c->evReader, (cudaStream_t)readerStream));
+    c->readerPending = true;
     return EAOF_OK;
 }
 

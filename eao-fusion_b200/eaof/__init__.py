@@ -258,6 +258,8 @@ def _mlib():
         L.eaof_match_bruteforce_batch_device.argtypes = [vp, ci, cf, ci, ci, vp, vp, vp, vp, vp, ci, vp, vp, vp]
         L.eaof_match_triangulation.argtypes = ([vp, ci, ci] + [ci] + [vp] * 6 + [ci] + [vp] * 7 + [ci] + [vp] * 3 + [ci] +
                                                [vp] * 3 + [vp, cf, cf, vp, vp, ci, vp, vp, C.POINTER(ci)])
+        L.eaof_match_windows.argtypes = ([vp, ci, ci] + [vp] * 7 + [cf] * 6 + [ci] + [vp] * 10 + [ci, cf, ci, ci, vp, vp,
+                                                                                               C.POINTER(ci)])
         L.eaof_matcher_last_distance_count.restype = C.c_longlong
         L.eaof_matcher_last_distance_count.argtypes = [vp]
         _mlib_ready = True
@@ -352,6 +354,60 @@ class ORBmatcher:
                                          float(th), float(mbf), search_mode, int(self.mbCheckOrientation),
                                          match.ctypes.data, dist.ctypes.data, C.byref(n)))
         return n.value, match[:nc], dist[:nc]
+
+    def SearchWindows(self, rule, F, q, th_accept, hist_mode, check_bounds, *, bounds, grid_inv):
+        """eaof_match_windows.  F: dict(x,y,octave,desc[,angle,uright,taken]); q: dict(u,v,radius,min_level,max_level,desc
+        [,valid,ur,angle,obs]).  Returns (nmatches, match_t, dist_t)."""
+        tx, ty, to = _arr(F["x"], np.float32), _arr(F["y"], np.float32), _arr(F["octave"], np.int32)
+        ta, td = _arr(F.get("angle"), np.float32), _arr(F["desc"], np.uint8)
+        tr, tt = _arr(F.get("uright"), np.float32), _arr(F.get("taken"), np.uint8)
+        qu, qv, qr = _arr(q["u"], np.float32), _arr(q["v"], np.float32), _arr(q["radius"], np.float32)
+        ql0, ql1 = _arr(q["min_level"], np.int32), _arr(q["max_level"], np.int32)
+        qval, qur, qa = _arr(q.get("valid"), np.uint8), _arr(q.get("ur"), np.float32), _arr(q.get("angle"), np.float32)
+        qd, qo = _arr(q["desc"], np.uint8), _arr(q.get("obs"), np.uint8)
+        nt, nq = len(tx), len(qu)
+        match = np.full(max(nt, 1), -1, np.int32)
+        dist = np.full(max(nt, 1), -1, np.int32)
+        n = C.c_int()
+        _ck(self.L.eaof_match_windows(self.h, rule, nt, _p(tx), _p(ty), _p(to), _p(ta), _p(td), _p(tr), _p(tt), bounds[0],
+                                      bounds[1], bounds[2], bounds[3], grid_inv[0], grid_inv[1], nq, _p(qval), _p(qu), _p(qv),
+                                      _p(qr), _p(ql0), _p(ql1), _p(qur), _p(qa), _p(qd), _p(qo), int(th_accept),
+                                      self.mfNNratio, hist_mode, int(check_bounds), match.ctypes.data, dist.ctypes.data,
+                                      C.byref(n)))
+        return n.value, match[:nt], dist[:nt]
+
+    def SearchByProjectionMapPoints(self, F, mp, th, *, bounds, grid_inv, scale_factors):
+        """SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:45-129.  mp: dict(x,y,level,desc
+        [,in_view,bad,xr,cos,obs]).  The window radius (RadiusByViewingCos * th * scale[level]) is the caller's."""
+        sf = _arr(scale_factors, np.float32)
+        lvl = _arr(mp["level"], np.int32)
+        cos = _arr(mp.get("cos"), np.float32)
+        r = np.where((cos if cos is not None else np.ones(len(lvl), np.float32)).astype(np.float64) > 0.998,
+                     np.float32(2.5), np.float32(4.0)).astype(np.float32)      # RadiusByViewingCos :131-137
+        if th != 1.0:
+            r = (r * np.float32(th)).astype(np.float32)
+        valid = np.ones(len(lvl), np.uint8)
+        if mp.get("in_view") is not None:
+            valid &= _arr(mp["in_view"], np.uint8)
+        if mp.get("bad") is not None:
+            valid &= (1 - _arr(mp["bad"], np.uint8))
+        q = dict(u=mp["x"], v=mp["y"], radius=(r * sf[lvl]).astype(np.float32), min_level=lvl - 1, max_level=lvl,
+                 desc=mp["desc"], valid=valid, ur=mp.get("xr"), obs=mp.get("obs"))
+        if F.get("uright") is not None and q["ur"] is None:
+            q["ur"] = np.zeros(len(lvl), np.float32)
+        return self.SearchWindows(1, F, q, TH_HIGH, 0, False, bounds=bounds, grid_inv=grid_inv)
+
+    def SearchByProjectionKF(self, cur, kq, th, orb_dist, *, bounds, grid_inv, scale_factors):
+        """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:1474-1601, after the
+        caller's projection.  kq: dict(valid,u,v,level,angle,desc)."""
+        sf = _arr(scale_factors, np.float32)
+        lvl = _arr(kq["level"], np.int32)
+        q = dict(u=kq["u"], v=kq["v"], radius=(np.float32(th) * sf[lvl]).astype(np.float32), min_level=lvl - 1,
+                 max_level=lvl + 1, desc=kq["desc"], valid=kq["valid"], angle=kq["angle"])
+        F = dict(cur)
+        F.pop("uright", None)
+        return self.SearchWindows(0, F, q, orb_dist, 1 if self.mbCheckOrientation else 0, True, bounds=bounds,
+                                  grid_inv=grid_inv)
 
     def SearchForTriangulation(self, k1, k2, F12, epipole, scale_factors, level_sigma2, only_stereo=False):
         """k1: dict(desc,x,y,angle,free[,stereo],nodes); k2: the same plus octave.  free = feature has no map point.

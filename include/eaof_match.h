@@ -89,6 +89,34 @@ int eaof_match_projection(eaof_matcher* m, int n_cur, const float* cur_x, const 
                           const float* scale_factors, int n_levels, float th, float mbf, int search_mode,
                           int check_orientation, int* match_cur, int* dist_cur, int* n_matches);
 
+/* Window search on the 64x48 feature grid — the common shape of the projection matchers other than (Cur,Last)
+ * (SURVEY.md §8 a14), one call, HOST buffers.  Targets = the features of a Frame (undistorted position, octave, angle,
+ * descriptor, optional mvuRight and `taken` flags); queries = map points already projected by the caller: pixel
+ * (q_u, q_v), search radius, level window [q_min_level, q_max_level] as passed to Frame::GetFeaturesInArea
+ * (src/Frame.cc:696-749), optional predicted right coordinate q_ur (stereo gate |q_ur - mvuRight| > radius), angle,
+ * descriptor, q_obs = pMP->Observations()>0.  Queries are processed in index order with the reference's greedy
+ * exclusion (a target that received a map point with observations is no longer a candidate).
+ *   rule EAOF_WIN_BEST: best distance only, accept best <= th_accept.
+ *        SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist)  src/ORBmatcher.cc:1474-1601:
+ *        q_valid = map point present, not bad, not already found, distance inside the scale pyramid; radius =
+ *        th*mvScaleFactors[level]; levels level-1..level+1; ttaken = mvpMapPoints[i] != NULL; th_accept = ORBdist;
+ *        hist_mode 1; check_bounds 1.
+ *   rule EAOF_WIN_RATIO_SAME_LEVEL: best and second best; rejected when both lie on the same level and
+ *        best > nnratio*second.  SearchByProjection(Frame&, const vector<MapPoint*>&, th)  src/ORBmatcher.cc:45-129:
+ *        q_valid = mbTrackInView && !isBad(); radius = RadiusByViewingCos(mTrackViewCos)*th*mvScaleFactors[level];
+ *        levels level-1..level; q_ur = mTrackProjXR; th_accept = TH_HIGH; hist_mode 0; check_bounds 0.  *n_matches
+ *        counts accepted queries like the reference's return value.
+ * hist_mode: 0 none, 1 factor 1/HISTO_LENGTH, 2 factor HISTO_LENGTH/360.
+ * match_t / dist_t: n_t entries (index of the query matched to the target, -1 = none). */
+enum { EAOF_WIN_BEST = 0, EAOF_WIN_RATIO_SAME_LEVEL = 1 };
+int eaof_match_windows(eaof_matcher* m, int rule, int n_t, const float* t_x, const float* t_y, const int* t_octave,
+                       const float* t_angle, const uint8_t* t_desc, const float* t_uright, const uint8_t* t_taken,
+                       float min_x, float max_x, float min_y, float max_y, float grid_inv_w, float grid_inv_h, int n_q,
+                       const uint8_t* q_valid, const float* q_u, const float* q_v, const float* q_radius,
+                       const int* q_min_level, const int* q_max_level, const float* q_ur, const float* q_angle,
+                       const uint8_t* q_desc, const uint8_t* q_obs, int th_accept, float nnratio, int hist_mode,
+                       int check_bounds, int* match_t, int* dist_t, int* n_matches);
+
 /* ---- batched, device-resident forms used for sequences (BASELINE.json configs[1] and [4]) ------------------ */
 
 /* Consecutive-frame SearchByProjection over the results an extractor handle holds on the device: pair p matches

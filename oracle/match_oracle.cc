@@ -310,4 +310,105 @@ int eaoo_search_by_projection_last(int nC, const float* cx, const float* cy, con
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th)  src/ORBmatcher.cc:45-129.
+// Per map point: inView (mbTrackInView), bad, projection (px, py, pxr), predicted level, view cosine, descriptor,
+// pobs = Observations()>0.  Frame: undistorted keypoints, descriptors, mvuRight (NULL: all -1), ftaken = feature
+// already holds a map point with observations.  matchF: nF entries, index of the map point assigned to the feature.
+int eaoo_search_by_projection_mappoints(int nF, const float* fx, const float* fy, const int* foct, const uint8_t* fdesc,
+                                        const float* furight, const uint8_t* ftaken, float minX, float minY, float invW,
+                                        float invH, int nMP, const uint8_t* inView, const uint8_t* bad, const float* px,
+                                        const float* py, const float* pxr, const int* plevel, const float* pcos,
+                                        const uint8_t* pdesc, const uint8_t* pobs, const float* scaleFactors, float th,
+                                        float nnratio, int* matchF, int* distF) {
+    std::vector<int> cellStart(GRID_COLS * GRID_ROWS + 1), cellIdx(nF > 0 ? nF : 1);
+    eaoo_build_grid(nF, fx, fy, minX, minY, invW, invH, cellStart.data(), cellIdx.data());
+    std::vector<char> hasObs(nF, 0);
+    for (int i = 0; i < nF; ++i) { matchF[i] = -1; if (distF) distF[i] = -1; hasObs[i] = ftaken ? ftaken[i] : 0; }
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<int> cand;
+    for (int iMP = 0; iMP < nMP; ++iMP) {
+        if (inView && !inView[iMP]) continue;
+        if (bad && bad[iMP]) continue;
+        const int nPredictedLevel = plevel[iMP];
+        float r = (pcos ? pcos[iMP] : 1.f) > 0.998 ? 2.5 : 4.0;  // RadiusByViewingCos :131-137 (double compare)
+        if (bFactor) r *= th;
+        const float rr = r * scaleFactors[nPredictedLevel];
+        features_in_area(cellStart.data(), cellIdx.data(), fx, fy, foct, px[iMP], py[iMP], rr, nPredictedLevel - 1,
+                         nPredictedLevel, minX, minY, invW, invH, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : cand) {
+            if (hasObs[idx]) continue;
+            if (furight && furight[idx] > 0) {
+                const float er = fabsf((pxr ? pxr[iMP] : 0.f) - furight[idx]);
+                if (er > r * scaleFactors[nPredictedLevel]) continue;
+            }
+            const int dist = descriptor_distance(pdesc + 32 * (size_t)iMP, fdesc + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = foct[idx]; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = foct[idx]; bestDist2 = dist; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            matchF[bestIdx] = iMP;
+            if (distF) distF[bestIdx] = bestDist;
+            hasObs[bestIdx] = pobs ? pobs[iMP] : 1;
+            ++nmatches;
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist)  src/ORBmatcher.cc:1474-1601, after
+// the caller's projection (:1497-1525): per KF feature kvalid (map point present, not bad, not already found, distance
+// inside the scale pyramid), projected pixel (ku, kv), predicted level, keypoint angle, map-point descriptor.
+// ctaken: Cur feature already holds a map point.  matchCur: nC entries, index of the KF feature.
+int eaoo_search_by_projection_kf(int nC, const float* cx, const float* cy, const int* coct, const float* cangle,
+                                 const uint8_t* cdesc, const uint8_t* ctaken, float minX, float maxX, float minY,
+                                 float maxY, float invW, float invH, int nK, const uint8_t* kvalid, const float* ku,
+                                 const float* kv, const int* klevel, const float* kangle, const uint8_t* kdesc,
+                                 const float* scaleFactors, float th, int orbDist, int checkOri, int* matchCur,
+                                 int* distCur) {
+    std::vector<int> cellStart(GRID_COLS * GRID_ROWS + 1), cellIdx(nC > 0 ? nC : 1);
+    eaoo_build_grid(nC, cx, cy, minX, minY, invW, invH, cellStart.data(), cellIdx.data());
+    std::vector<char> has(nC, 0);
+    for (int i = 0; i < nC; ++i) { matchCur[i] = -1; if (distCur) distCur[i] = -1; has[i] = ctaken ? ctaken[i] : 0; }
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;  // :1486
+    int nmatches = 0;
+    std::vector<int> cand;
+    for (int i = 0; i < nK; ++i) {
+        if (!kvalid[i]) continue;
+        const float u = ku[i], v = kv[i];
+        if (u < minX || u > maxX) continue;
+        if (v < minY || v > maxY) continue;
+        const int nPredictedLevel = klevel[i];
+        const float radius = th * scaleFactors[nPredictedLevel];
+        features_in_area(cellStart.data(), cellIdx.data(), cx, cy, coct, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1,
+                         minX, minY, invW, invH, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : cand) {
+            if (has[i2]) continue;
+            const int dist = descriptor_distance(kdesc + 32 * (size_t)i, cdesc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orbDist) {
+            matchCur[bestIdx2] = i;
+            if (distCur) distCur[bestIdx2] = bestDist;
+            has[bestIdx2] = 1;
+            ++nmatches;
+            if (checkOri) rotHist[rot_bin(kangle[i], cangle[bestIdx2], factor)].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != i1 && i != i2 && i != i3)
+                for (int j : rotHist[i]) { matchCur[j] = -1; if (distCur) distCur[j] = -1; --nmatches; }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

@@ -484,3 +484,103 @@ def r_search_by_projection(cur, last, th, check_ori, *, bounds, grid_inv, scale_
                                                        _pp(lobs), _pp(sf), len(sf), float(th), float(mbf), search_mode,
                                                        int(check_ori), 0.9, match.ctypes.data)
     return n, match[:nc]
+
+
+def _frame_arrays(F):
+    return (_a(F["x"], np.float32), _a(F["y"], np.float32), _a(F["octave"], np.int32), _a(F.get("angle"), np.float32),
+            _a(F["desc"], np.uint8), _a(F.get("uright"), np.float32), _a(F.get("taken"), np.uint8))
+
+
+def o_search_by_projection_mappoints(F, mp, th, nnratio, *, bounds, grid_inv, scale_factors):
+    """F: dict(x,y,octave,desc[,uright,taken]); mp: dict(x,y,level,desc[,in_view,bad,xr,cos,obs]).
+    Returns (nmatches, matchF, distF).  src/ORBmatcher.cc:45-129."""
+    fx, fy, fo, _, fd, fr, ft = _frame_arrays(F)
+    px, py, pl, pd = _a(mp["x"], np.float32), _a(mp["y"], np.float32), _a(mp["level"], np.int32), _a(mp["desc"], np.uint8)
+    iv, bad, pxr = _a(mp.get("in_view"), np.uint8), _a(mp.get("bad"), np.uint8), _a(mp.get("xr"), np.float32)
+    pc, po_ = _a(mp.get("cos"), np.float32), _a(mp.get("obs"), np.uint8)
+    sf = _a(scale_factors, np.float32)
+    nF, nM = len(fx), len(px)
+    match, dist = np.full(max(nF, 1), -1, np.int32), np.full(max(nF, 1), -1, np.int32)
+    L = _mo()
+    ci, cf, vp = C.c_int, C.c_float, C.c_void_p
+    L.eaoo_search_by_projection_mappoints.argtypes = [ci, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, ci, vp, vp, vp, vp, vp, vp,
+                                                      vp, vp, vp, vp, cf, cf, vp, vp]
+    n = L.eaoo_search_by_projection_mappoints(nF, _pp(fx), _pp(fy), _pp(fo), _pp(fd), _pp(fr), _pp(ft), bounds[0], bounds[2],
+                                              grid_inv[0], grid_inv[1], nM, _pp(iv), _pp(bad), _pp(px), _pp(py), _pp(pxr),
+                                              _pp(pl), _pp(pc), _pp(pd), _pp(po_), _pp(sf), float(th), float(nnratio),
+                                              match.ctypes.data, dist.ctypes.data)
+    return n, match[:nF], dist[:nF]
+
+
+def r_search_by_projection_mappoints(F, mp, th, nnratio, *, bounds, grid_inv, scale_factors):
+    fx, fy, fo, _, fd, fr, ft = _frame_arrays(F)
+    px, py, pl, pd = _a(mp["x"], np.float32), _a(mp["y"], np.float32), _a(mp["level"], np.int32), _a(mp["desc"], np.uint8)
+    iv, bad, pxr = _a(mp.get("in_view"), np.uint8), _a(mp.get("bad"), np.uint8), _a(mp.get("xr"), np.float32)
+    pc, po_ = _a(mp.get("cos"), np.float32), _a(mp.get("obs"), np.uint8)
+    sf = _a(scale_factors, np.float32)
+    nF, nM = len(fx), len(px)
+    match = np.full(max(nF, 1), -1, np.int32)
+    n = match_ref_lib().mref_search_by_projection_mappoints(nF, _pp(fx), _pp(fy), _pp(fo), _pp(fd), _pp(fr), _pp(ft),
+                                                            bounds[0], bounds[1], bounds[2], bounds[3], grid_inv[0],
+                                                            grid_inv[1], nM, _pp(iv), _pp(bad), _pp(px), _pp(py), _pp(pxr),
+                                                            _pp(pl), _pp(pc), _pp(pd), _pp(po_), _pp(sf), len(sf), float(th),
+                                                            float(nnratio), match.ctypes.data)
+    return n, match[:nF]
+
+
+def kf_projection(kf, log_scale_factor, n_levels):
+    """What the caller of SearchByProjection(Cur,KF) derives per KF map point before the search (:1497-1525), computed
+    with the reference binary's own helpers: pixel (u, v) for an identity pose with fx=fy=1, cx=cy=0 and wz=1, the 3-D
+    distance gate and MapPoint::PredictScale.  Returns (valid, u, v, level)."""
+    L = match_ref_lib()
+    st, wx, wy, wz = _a(kf["state"], np.uint8), _a(kf["wx"], np.float32), _a(kf["wy"], np.float32), _a(kf["wz"], np.float32)
+    mx, mn = _a(kf["max_dist"], np.float32), _a(kf["min_dist"], np.float32)
+    n = len(st)
+    valid, u, v, lvl = np.zeros(n, np.uint8), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+    for i in range(n):
+        assert wz[i] == 1.0
+        u[i], v[i] = wx[i], wy[i]
+        d = np.float32(L.mref_norm3(float(wx[i]), float(wy[i]), float(wz[i])))
+        inside = not (d < np.float32(0.8) * mn[i] or d > np.float32(1.2) * mx[i])
+        valid[i] = st[i] == 3 and inside
+        lvl[i] = L.mref_predict_scale(float(mx[i]), float(d), float(log_scale_factor)) if inside else 0
+        if valid[i]:
+            assert 0 <= lvl[i] < n_levels, "test data must keep the predicted level inside the pyramid"
+    return valid, u, v, lvl
+
+
+def o_search_by_projection_kf(cur, kq, th, orb_dist, check_ori, *, bounds, grid_inv, scale_factors):
+    """cur: dict(x,y,octave,angle,desc[,taken]); kq: dict(valid,u,v,level,angle,desc) (see kf_projection).
+    Returns (nmatches, matchCur, distCur).  src/ORBmatcher.cc:1474-1601."""
+    cx, cy, co, ca, cd, _, ct = _frame_arrays(cur)
+    kv, ku, kvv, kl = _a(kq["valid"], np.uint8), _a(kq["u"], np.float32), _a(kq["v"], np.float32), _a(kq["level"], np.int32)
+    ka, kd = _a(kq["angle"], np.float32), _a(kq["desc"], np.uint8)
+    sf = _a(scale_factors, np.float32)
+    nC, nK = len(cx), len(ku)
+    match, dist = np.full(max(nC, 1), -1, np.int32), np.full(max(nC, 1), -1, np.int32)
+    L = _mo()
+    ci, cf, vp = C.c_int, C.c_float, C.c_void_p
+    L.eaoo_search_by_projection_kf.argtypes = [ci, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp, vp, vp, vp,
+                                               vp, cf, ci, ci, vp, vp]
+    n = L.eaoo_search_by_projection_kf(nC, _pp(cx), _pp(cy), _pp(co), _pp(ca), _pp(cd), _pp(ct), bounds[0], bounds[1],
+                                       bounds[2], bounds[3], grid_inv[0], grid_inv[1], nK, _pp(kv), _pp(ku), _pp(kvv),
+                                       _pp(kl), _pp(ka), _pp(kd), _pp(sf), float(th), int(orb_dist), int(check_ori),
+                                       match.ctypes.data, dist.ctypes.data)
+    return n, match[:nC], dist[:nC]
+
+
+def r_search_by_projection_kf(cur, kf, th, orb_dist, check_ori, *, bounds, grid_inv, scale_factors, log_scale_factor):
+    """kf: dict(state,wx,wy,wz,max_dist,min_dist,angle,desc); state 0 none, 1 bad, 2 already found, 3 usable."""
+    cx, cy, co, ca, cd, _, ct = _frame_arrays(cur)
+    st, wx, wy, wz = _a(kf["state"], np.uint8), _a(kf["wx"], np.float32), _a(kf["wy"], np.float32), _a(kf["wz"], np.float32)
+    mx, mn = _a(kf["max_dist"], np.float32), _a(kf["min_dist"], np.float32)
+    ka, kd = _a(kf["angle"], np.float32), _a(kf["desc"], np.uint8)
+    sf = _a(scale_factors, np.float32)
+    nC, nK = len(cx), len(st)
+    match = np.full(max(nC, 1), -1, np.int32)
+    n = match_ref_lib().mref_search_by_projection_kf(nC, _pp(cx), _pp(cy), _pp(co), _pp(ca), _pp(cd), _pp(ct), bounds[0],
+                                                     bounds[1], bounds[2], bounds[3], grid_inv[0], grid_inv[1], nK, _pp(st),
+                                                     _pp(wx), _pp(wy), _pp(wz), _pp(mx), _pp(mn), _pp(ka), _pp(kd), _pp(sf),
+                                                     len(sf), float(log_scale_factor), float(th), int(orb_dist),
+                                                     int(check_ori), 0.9, match.ctypes.data)
+    return n, match[:nC]

@@ -72,3 +72,56 @@ def tri_inputs(seed, n1=500, n2=600, nn=8):
     F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32) + rng.normal(0, 1e-5, (3, 3)).astype(np.float32)
     sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
     return k1, k2, F12, sf, (sf * sf).astype(np.float32)
+
+
+def window_scene(seed, n=900, stereo=False, flags=False):
+    """A frame of n features and n projected map points, half of which land next to a feature whose descriptor is a
+    noisy copy of theirs, with ties, crowded windows and (optionally) stereo / taken / validity flags."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    q, aq, t, at = planted_pair(n, n, seed, flip=0.06, frac=0.8, dup=8)
+    x = rng.uniform(-5, 645, n).astype(np.float32)
+    y = rng.uniform(-5, 485, n).astype(np.float32)
+    octv = rng.integers(0, 8, n).astype(np.int32)
+    F = dict(x=x, y=y, octave=octv, angle=at, desc=t)
+    perm = rng.permutation(n)
+    mp = dict(x=(x[perm] + rng.normal(0, 2, n)).astype(np.float32), y=(y[perm] + rng.normal(0, 2, n)).astype(np.float32),
+              level=np.clip(octv[perm] + rng.integers(0, 2, n), 0, 7).astype(np.int32), angle=aq, desc=q,
+              cos=rng.choice(np.array([0.9, 0.999, 0.9985], np.float32), n))
+    half = perm[: n // 2]
+    F["desc"][half] = q[: n // 2] ^ np.packbits((rng.random((n // 2, 256)) < 0.05).astype(np.uint8), axis=1)
+    # near-ties on the same level: a second feature right next to some planted ones with an almost equal descriptor
+    twins = half[:60]
+    extra = perm[n // 2: n // 2 + 60]
+    F["x"][extra] = F["x"][twins] + 1; F["y"][extra] = F["y"][twins]; F["octave"][extra] = F["octave"][twins]
+    F["desc"][extra] = F["desc"][twins] ^ np.packbits((rng.random((60, 256)) < 0.01).astype(np.uint8), axis=1)
+    if stereo:
+        F["uright"] = np.where(rng.random(n) > 0.3, x - 20 + rng.normal(0, 4, n), -1).astype(np.float32)
+        mp["xr"] = (mp["x"] - 20 + rng.normal(0, 3, n)).astype(np.float32)
+    if flags:
+        F["taken"] = (rng.random(n) < 0.1).astype(np.uint8)
+        mp["in_view"] = (rng.random(n) > 0.1).astype(np.uint8)
+        mp["bad"] = (rng.random(n) < 0.05).astype(np.uint8)
+        mp["obs"] = (rng.random(n) > 0.2).astype(np.uint8)
+    return F, mp
+
+
+def kf_scene(seed, n=900, flags=False):
+    """Cur frame + keyframe map points for SearchByProjection(Cur,KF): world points (u, v, 1) seen from an identity
+    pose, distance gates and predicted levels spread over the pyramid."""
+    F, mp = window_scene(seed, n)
+    rng = np.random.Generator(np.random.PCG64(seed + 7))
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    d = np.sqrt(mp["x"].astype(np.float64) ** 2 + mp["y"].astype(np.float64) ** 2 + 1.0)
+    lvl = mp["level"]
+    # mfMaxDistance so that ceil(log(max/d)/log(1.2)) == lvl with margin: max = d * 1.2^(lvl-0.5)
+    max_dist = (d * 1.2 ** (lvl - 0.5)).astype(np.float32)
+    min_dist = (max_dist / sf[7]).astype(np.float32)
+    state = np.full(n, 3, np.uint8)
+    if flags:
+        state = rng.choice(np.array([0, 1, 2, 3], np.uint8), n, p=[0.05, 0.05, 0.1, 0.8])
+        F["taken"] = (rng.random(n) < 0.1).astype(np.uint8)
+        far = rng.random(n) < 0.05
+        max_dist[far] = (d[far] * 0.5).astype(np.float32)  # outside the scale pyramid -> skipped by the distance gate
+    kf = dict(state=state, wx=mp["x"], wy=mp["y"], wz=np.ones(n, np.float32), max_dist=max_dist, min_dist=min_dist,
+              angle=mp["angle"], desc=mp["desc"])
+    return F, kf

@@ -265,3 +265,73 @@ def test_triangulation(matcher_factory, only_stereo, ori):
              stereo=k1["stereo"][:0], nodes=(np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32)))
     n, match, _ = m.SearchForTriangulation(e, k2, F12, (0.0, 0.0), sf, ls)
     assert n == 0 and len(match) == 0
+
+
+_SF = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+_BOUNDS = (0.0, 640.0, 0.0, 480.0)
+_GINV = (np.float32(64) / np.float32(640), np.float32(48) / np.float32(480))
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0, 5.0])
+@pytest.mark.parametrize("ratio", [0.8, 0.6])
+@pytest.mark.parametrize("case", ["plain", "flags", "stereo"])
+def test_projection_mappoints(matcher_factory, th, ratio, case):
+    """SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129) through eaof_match_windows:
+    same-level ratio rule, stereo gate, greedy exclusion, match count."""
+    from matchdata import window_scene
+    from oracle import pyoracle as po
+    m = matcher_factory(ratio)
+    total = 0
+    for seed in range(3):
+        F, mp = window_scene(300 + seed, stereo=case == "stereo", flags=case != "plain")
+        kw = dict(bounds=_BOUNDS, grid_inv=_GINV, scale_factors=_SF)
+        n, match, dist = m.SearchByProjectionMapPoints(F, mp, th, **kw)
+        on, om, od = po.o_search_by_projection_mappoints(F, mp, th, ratio, **kw)
+        assert n == on, (seed, n, on)
+        assert np.array_equal(match, om) and np.array_equal(dist, od)
+        total += on
+    assert total > 100
+
+
+def test_projection_mappoints_crowded_windows_rescan(matcher_factory):
+    """Dozens of near-identical features inside every window and most of them taken: the kept list runs dry and the
+    exact re-scan decides."""
+    from oracle import pyoracle as po
+    rng = np.random.Generator(np.random.PCG64(9))
+    n_f, n_q = 600, 120
+    base = rng.integers(0, 256, size=(1, 32), dtype=np.uint8)
+    desc = np.repeat(base, n_f, 0) ^ np.packbits((rng.random((n_f, 256)) < 0.02).astype(np.uint8), axis=1)
+    F = dict(x=rng.uniform(300, 340, n_f).astype(np.float32), y=rng.uniform(220, 260, n_f).astype(np.float32),
+             octave=rng.integers(0, 2, n_f).astype(np.int32), desc=desc, taken=(rng.random(n_f) < 0.5).astype(np.uint8))
+    mp = dict(x=rng.uniform(300, 340, n_q).astype(np.float32), y=rng.uniform(220, 260, n_q).astype(np.float32),
+              level=np.ones(n_q, np.int32), desc=np.repeat(base, n_q, 0), cos=np.full(n_q, 0.9, np.float32))
+    kw = dict(bounds=_BOUNDS, grid_inv=_GINV, scale_factors=_SF)
+    for ratio in (0.8, 1.0):
+        m = matcher_factory(ratio)
+        n, match, dist = m.SearchByProjectionMapPoints(F, mp, 5.0, **kw)
+        on, om, od = po.o_search_by_projection_mappoints(F, mp, 5.0, ratio, **kw)
+        assert n == on and np.array_equal(match, om) and np.array_equal(dist, od), (ratio, n, on)
+    assert on > 20
+
+
+@pytest.mark.parametrize("th", [7.0, 15.0])
+@pytest.mark.parametrize("orb_dist", [50, 100])
+@pytest.mark.parametrize("case", ["plain", "flags", "no_ori"])
+def test_projection_keyframe(matcher_factory, th, orb_dist, case):
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1474-1601)."""
+    from matchdata import kf_scene
+    from oracle import pyoracle as po
+    m = matcher_factory(0.9, case != "no_ori")
+    lsf = float(np.log(np.float32(1.2)))
+    total = 0
+    for seed in range(3):
+        F, kf = kf_scene(400 + seed, flags=case == "flags")
+        valid, u, v, lvl = po.kf_projection(kf, lsf, 8)
+        kq = dict(valid=valid, u=u, v=v, level=lvl, angle=kf["angle"], desc=kf["desc"])
+        kw = dict(bounds=_BOUNDS, grid_inv=_GINV, scale_factors=_SF)
+        n, match, dist = m.SearchByProjectionKF(F, kq, th, orb_dist, **kw)
+        on, om, od = po.o_search_by_projection_kf(F, kq, th, orb_dist, case != "no_ori", **kw)
+        assert n == on, (seed, n, on)
+        assert np.array_equal(match, om) and np.array_equal(dist, od)
+        total += on
+    assert total > 30

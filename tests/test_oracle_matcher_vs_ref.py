@@ -105,3 +105,46 @@ def test_search_by_projection_last(th, case):
         assert np.array_equal(rm, om), seed
         total += on
     assert total > 0
+
+
+_SF = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+_BOUNDS = (0.0, 640.0, 0.0, 480.0)
+_GINV = (np.float32(64) / np.float32(640), np.float32(48) / np.float32(480))
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0, 5.0])
+@pytest.mark.parametrize("ratio", [0.8, 0.6])
+@pytest.mark.parametrize("case", ["plain", "flags", "stereo"])
+def test_search_by_projection_mappoints(th, ratio, case):
+    from matchdata import window_scene
+    total = rejected = 0
+    for seed in range(3):
+        F, mp = window_scene(300 + seed, stereo=case == "stereo", flags=case != "plain")
+        kw = dict(bounds=_BOUNDS, grid_inv=_GINV, scale_factors=_SF)
+        on, om, _ = po.o_search_by_projection_mappoints(F, mp, th, ratio, **kw)
+        rn, rm = po.r_search_by_projection_mappoints(F, mp, th, ratio, **kw)
+        assert rn == on, (seed, rn, on)
+        assert np.array_equal(rm, om), seed
+        total += on
+        rejected += po.o_search_by_projection_mappoints(F, mp, th, 1e9, **kw)[0] - on
+    assert total > 100 and (rejected > 0 or th == 1.0)  # the same-level ratio test must have bitten somewhere
+
+
+@pytest.mark.parametrize("th", [7.0, 15.0])
+@pytest.mark.parametrize("orb_dist", [50, 100])
+@pytest.mark.parametrize("case", ["plain", "flags", "no_ori"])
+def test_search_by_projection_kf(th, orb_dist, case):
+    from matchdata import kf_scene
+    lsf = float(np.log(np.float32(1.2)))
+    total = 0
+    for seed in range(3):
+        F, kf = kf_scene(400 + seed, flags=case == "flags")
+        valid, u, v, lvl = po.kf_projection(kf, lsf, 8)
+        kq = dict(valid=valid, u=u, v=v, level=lvl, angle=kf["angle"], desc=kf["desc"])
+        kw = dict(bounds=_BOUNDS, grid_inv=_GINV, scale_factors=_SF)
+        on, om, _ = po.o_search_by_projection_kf(F, kq, th, orb_dist, case != "no_ori", **kw)
+        rn, rm = po.r_search_by_projection_kf(F, kf, th, orb_dist, case != "no_ori", log_scale_factor=lsf, **kw)
+        assert rn == on, (seed, rn, on)
+        assert np.array_equal(rm, om), seed
+        total += on
+    assert total > 30
