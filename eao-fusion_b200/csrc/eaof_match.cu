@@ -896,6 +896,109 @@ __global__ void __launch_bounds__(32) k_win_resolve_ratio(ProjArgs A, const int*
     if (lane == 0) nMatches[pair] = nAcc;
 }
 
+// phase 2 of SearchForInitialization (src/ORBmatcher.cc:405-520): one warp, F1 features in index order.  A target
+// that is already matched stays a candidate for a later query whose distance is strictly smaller than the stored one
+// (:443-444), in which case the earlier match is undone (:465-469).  Phase 1 left the candidates with dist <= cut
+// sorted by (dist, arrival); best / second best are the first two that pass the matched-distance filter.
+__global__ void __launch_bounds__(32) k_init_resolve(ProjArgs A, const int* __restrict__ cellStart,
+                                                     const int* __restrict__ cellIdx, const uint32_t* __restrict__ topBuf,
+                                                     int* __restrict__ matched21, int* __restrict__ matchedDist,
+                                                     int* __restrict__ binOf, int* __restrict__ match12,
+                                                     int* __restrict__ nMatches) {
+    __shared__ int hist[EAOF_HISTO_LENGTH];
+    const int lane = threadIdx.x;
+    const int nC = A.nC[0], nL = A.nL[0];
+    const size_t po = 0;
+    for (int i = lane; i < EAOF_HISTO_LENGTH; i += 32) hist[i] = 0;
+    for (int i = lane; i < nC; i += 32) { matched21[i] = -1; matchedDist[i] = 0x7fffffff; }
+    for (int i = lane; i < nL; i += 32) { match12[i] = -1; binOf[i] = -1; }
+    __syncwarp();
+    const float factor = 1.0f / EAOF_HISTO_LENGTH;  // :413
+    int nm = 0;
+    for (int i0 = 0; i0 < nL; i0 += 32) {
+        const int mine = i0 + lane;
+        uint4 w0 = make_uint4(~0u, ~0u, ~0u, ~0u), w1 = make_uint4(~0u, ~0u, 0u, 0u);
+        if (mine < nL) {
+            const uint4* p = reinterpret_cast<const uint4*>(topBuf + (po + mine) * 8);
+            w0 = p[0];
+            w1 = p[1];
+        }
+        const int myCnt = mine < nL ? (int)w1.w : 0;
+        unsigned rem = __ballot_sync(0xffffffffu, myCnt > 0);
+        while (rem) {
+            const int j = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const int q = i0 + j;
+            const int cnt = __shfl_sync(0xffffffffu, myCnt, j);
+            const uint32_t e[TOP_K] = {__shfl_sync(0xffffffffu, w0.x, j), __shfl_sync(0xffffffffu, w0.y, j),
+                                       __shfl_sync(0xffffffffu, w0.z, j), __shfl_sync(0xffffffffu, w0.w, j),
+                                       __shfl_sync(0xffffffffu, w1.x, j), __shfl_sync(0xffffffffu, w1.y, j)};
+            int best = 0x7fffffff, best2 = 0x7fffffff, bestIdx = -1, found = 0;
+#pragma unroll
+            for (int k = 0; k < TOP_K; ++k) {
+                if (k < cnt && found < 2) {
+                    const int t = e[k] & 0xffff, d = (int)(e[k] >> 16);
+                    if (!(matchedDist[t] <= d)) {
+                        if (found == 0) { best = d; bestIdx = t; } else best2 = d;
+                        ++found;
+                    }
+                }
+            }
+            if (cnt > TOP_K && found < 2) {  // exact re-scan (rare)
+                float u, v, r, ur;
+                int minLevel, maxLevel;
+                query_window(A, po, q, u, v, r, minLevel, maxLevel, ur);
+                uint32_t qd[8];
+                const uint4* p = reinterpret_cast<const uint4*>(A.desc + 32 * ((size_t)A.lRow[0] + q));
+                const uint4 a = p[0], b = p[1];
+                qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+                const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[0];
+                best = 0x7fffffff; best2 = 0x7fffffff; bestIdx = -1;
+                for_each_candidate(A, cellStart, cellIdx, A.cx, A.cy, A.coct, u, v, r, minLevel, maxLevel, [&](int k) {
+                    uint32_t td[8];
+                    const uint4* pp = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
+                    const uint4 a2 = pp[0], b2 = pp[1];
+                    td[0] = a2.x; td[1] = a2.y; td[2] = a2.z; td[3] = a2.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
+                    const int d = hamming256(qd, td);
+                    if (matchedDist[k] <= d) return;
+                    if (d < best) { best2 = best; best = d; bestIdx = k; }
+                    else if (d < best2) best2 = d;
+                });
+            }
+            // an unseen second best is > cut, which passes the ratio test for every best <= TH_LOW
+            const float second = best2 == 0x7fffffff ? 2147483648.f : (float)best2;
+            if (bestIdx >= 0 && best <= EAOF_TH_LOW && (float)best < __fmul_rn(second, A.ratio)) {
+                const int prev = matched21[bestIdx];
+                const int bin = A.checkOri ? rot_bin(A.langle[q], A.cangle[bestIdx], factor) : -1;
+                __syncwarp();
+                if (lane == 0) {
+                    if (prev >= 0) match12[prev] = -1;
+                    match12[q] = bestIdx;
+                    matched21[bestIdx] = q;
+                    matchedDist[bestIdx] = best;
+                    if (bin >= 0) { binOf[q] = bin; ++hist[bin]; }
+                }
+                nm += prev >= 0 ? 0 : 1;
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    if (A.checkOri) {
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        int removed = 0;
+        for (int i = lane; i < nL; i += 32) {
+            const int bin = binOf[i];
+            if (bin >= 0 && bin != i1 && bin != i2 && bin != i3 && match12[i] >= 0) { match12[i] = -1; ++removed; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nm -= removed;
+    }
+    if (lane == 0) *nMatches = nm;
+}
+
 // Queries of the consecutive-frame path: Last keypoints of an extractor batch shifted by the known motion.
 __global__ void k_proj_prepare(const eaof_kp* __restrict__ kps, const int* __restrict__ counts, int cap,
                                const int* __restrict__ lastFrame, const int* __restrict__ curFrame,
@@ -948,6 +1051,7 @@ struct eaof_matcher {
     uint8_t *ctaken = nullptr, *lvalid = nullptr, *lobs = nullptr;
     float* qRadius = nullptr;   // eaof_match_windows: per-query radius and upper level
     int* qMaxL = nullptr;
+    int* initBin = nullptr;     // eaof_match_initialization: rotation bin per accepted F1 feature
     // single-pair host API staging
     uint8_t* desc2 = nullptr;   // 2 blocks of maxFeat descriptors
     float* angle2 = nullptr;    // 2 blocks of maxFeat angles
@@ -996,7 +1100,7 @@ int eaof_matcher_create(int device, int maxPairs, int maxFeat, eaof_matcher** ou
     A_(dalloc(&m->coct, PF)); A_(dalloc(&m->loct, PF));
     A_(dalloc(&m->nC, maxPairs)); A_(dalloc(&m->nL, maxPairs)); A_(dalloc(&m->cRow, maxPairs)); A_(dalloc(&m->lRow, maxPairs));
     A_(dalloc(&m->ctaken, PF)); A_(dalloc(&m->lvalid, PF)); A_(dalloc(&m->lobs, PF));
-    A_(dalloc(&m->qRadius, (size_t)maxFeat)); A_(dalloc(&m->qMaxL, (size_t)maxFeat));
+    A_(dalloc(&m->qRadius, (size_t)maxFeat)); A_(dalloc(&m->qMaxL, (size_t)maxFeat)); A_(dalloc(&m->initBin, (size_t)maxFeat));
     A_(dalloc(&m->desc2, (size_t)2 * maxFeat * 32)); A_(dalloc(&m->angle2, (size_t)2 * maxFeat));
     A_(dalloc(&m->validQ, maxFeat)); A_(dalloc(&m->validT, maxFeat)); A_(dalloc(&m->idxQ, maxFeat)); A_(dalloc(&m->idxT, maxFeat));
     A_(dalloc(&m->segs, maxFeat)); A_(dalloc(&m->segStart, 2)); A_(dalloc(&m->tiles, (size_t)2 * maxFeat));
@@ -1019,7 +1123,7 @@ void eaof_matcher_destroy(eaof_matcher* m) {
     void* ptrs[] = {m->nearBuf, m->accBuf, m->cellStart, m->cellIdx, m->cx, m->cy, m->cangle, m->curight, m->lu, m->lv,
                     m->linvz, m->langle, m->coct, m->loct, m->nC, m->nL, m->cRow, m->lRow, m->ctaken, m->lvalid, m->lobs,
                     m->desc2, m->angle2, m->validQ, m->validT, m->idxQ, m->idxT, m->segs, m->segStart, m->tiles,
-                    m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN, m->qRadius, m->qMaxL};
+                    m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN, m->qRadius, m->qMaxL, m->initBin};
     for (void* p : ptrs) cudaFree(p);
     if (m->evDep) cudaEventDestroy(m->evDep);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -1365,6 +1469,58 @@ int eaof_match_windows(eaof_matcher* m, int rule, int nT, const float* tx, const
     if (distT) MCK(cudaMemcpyAsync(distT, m->outDist, sizeof(int) * nT, cudaMemcpyDeviceToHost, s));
     MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
     MCK(cudaStreamSynchronize(s));
+    return EAOF_OK;
+}
+
+int eaof_match_initialization(eaof_matcher* m, float nnratio, int checkOri, int n1, const int* oct1, const float* angle1,
+                              const uint8_t* desc1, float* prevMatched, int n2, const float* x2, const float* y2,
+                              const int* oct2, const float* angle2, const uint8_t* desc2, float minX, float maxX, float minY,
+                              float maxY, float invW, float invH, int windowSize, int* matches12, int* nMatches) {
+    if (!m || !matches12 || !nMatches || n1 < 0 || n2 < 0) return mfail(EAOF_ERR_ARG, "bad argument");
+    if (n1 > m->maxFeat || n2 > m->maxFeat) return mfail(EAOF_ERR_ARG, "feature count exceeds max_features=%d", m->maxFeat);
+    *nMatches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return EAOF_OK;
+    if (!oct1 || !angle1 || !desc1 || !prevMatched || !x2 || !y2 || !oct2 || !angle2 || !desc2) return mfail(EAOF_ERR_ARG, "null array");
+    (void)maxX; (void)maxY;
+    std::vector<float> qu(n1), qv(n1), qr(n1, (float)windowSize);
+    std::vector<int> ql(n1);
+    std::vector<uint8_t> qval(n1);
+    for (int i = 0; i < n1; ++i) {
+        qu[i] = prevMatched[2 * i]; qv[i] = prevMatched[2 * i + 1];
+        ql[i] = oct1[i];                 // GetFeaturesInArea(x, y, windowSize, level1, level1), :425
+        qval[i] = oct1[i] > 0 ? 0 : 1;   // only level-0 features of F1 are matched (:421-423)
+    }
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+#define UP(dst, src, n, T) MCK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(n), cudaMemcpyHostToDevice, s))
+    UP(m->cx, x2, n2, float); UP(m->cy, y2, n2, float); UP(m->coct, oct2, n2, int); UP(m->cangle, angle2, n2, float);
+    UP(m->lu, qu.data(), n1, float); UP(m->lv, qv.data(), n1, float); UP(m->qRadius, qr.data(), n1, float);
+    UP(m->loct, ql.data(), n1, int); UP(m->qMaxL, ql.data(), n1, int); UP(m->langle, angle1, n1, float);
+    UP(m->lvalid, qval.data(), n1, uint8_t);
+    UP(m->desc2, desc2, 32 * (size_t)n2, uint8_t);
+    UP(m->desc2 + 32 * (size_t)m->maxFeat, desc1, 32 * (size_t)n1, uint8_t);
+    const int hdr[4] = {n2, n1, 0, m->maxFeat};
+    UP(m->nC, &hdr[0], 1, int); UP(m->nL, &hdr[1], 1, int); UP(m->cRow, &hdr[2], 1, int); UP(m->lRow, &hdr[3], 1, int);
+#undef UP
+    MCK(cudaStreamSynchronize(s));  // the staging vectors above live on this stack frame
+    ProjArgs A{};
+    A.cx = m->cx; A.cy = m->cy; A.coct = m->coct; A.cangle = m->cangle; A.nC = m->nC; A.lu = m->lu; A.lv = m->lv;
+    A.loct = m->loct; A.langle = m->langle; A.lvalid = m->lvalid; A.nL = m->nL; A.desc = m->desc2; A.cRow = m->cRow;
+    A.lRow = m->lRow; A.stride = m->maxFeat; A.minX = minX; A.maxX = maxX; A.minY = minY; A.maxY = maxY; A.invW = invW;
+    A.invH = invH; A.qRadius = m->qRadius; A.qMinL = m->loct; A.qMaxL = m->qMaxL; A.qUr = m->lu; A.checkOri = checkOri;
+    A.histMode = 1; A.checkBounds = 0; A.thAccept = EAOF_TH_LOW; A.ratio = nnratio;
+    A.cut = near_threshold(EAOF_TH_LOW, nnratio) - 1;
+    if (A.cut > 256) A.cut = 256;
+    k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx);
+    k_proj_dense<<<dim3((n1 + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
+    k_init_resolve<<<1, 32, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->idxQ, m->idxT, m->initBin, m->outMatch, m->outN);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(matches12, m->outMatch, sizeof(int) * n1, cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n1; ++i)  // :515-517 update prev matched
+        if (matches12[i] >= 0) { prevMatched[2 * i] = x2[matches12[i]]; prevMatched[2 * i + 1] = y2[matches12[i]]; }
     return EAOF_OK;
 }
 

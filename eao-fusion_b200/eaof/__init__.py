@@ -260,6 +260,8 @@ def _mlib():
                                                [vp] * 3 + [vp, cf, cf, vp, vp, ci, vp, vp, C.POINTER(ci)])
         L.eaof_match_windows.argtypes = ([vp, ci, ci] + [vp] * 7 + [cf] * 6 + [ci] + [vp] * 10 + [ci, cf, ci, ci, vp, vp,
                                                                                                C.POINTER(ci)])
+        L.eaof_match_initialization.argtypes = [vp, cf, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci,
+                                                vp, C.POINTER(ci)]
         L.eaof_matcher_last_distance_count.restype = C.c_longlong
         L.eaof_matcher_last_distance_count.argtypes = [vp]
         _mlib_ready = True
@@ -354,6 +356,21 @@ class ORBmatcher:
                                          float(th), float(mbf), search_mode, int(self.mbCheckOrientation),
                                          match.ctypes.data, dist.ctypes.data, C.byref(n)))
         return n.value, match[:nc], dist[:nc]
+
+    def SearchForInitialization(self, F1, F2, prev_matched, window_size=10, *, bounds, grid_inv):
+        """src/ORBmatcher.cc:405-520.  F1: dict(octave,angle,desc); F2: dict(x,y,octave,angle,desc); prev_matched (n1,2).
+        Returns (nmatches, vnMatches12, updated vbPrevMatched)."""
+        o1, a1, d1 = _arr(F1["octave"], np.int32), _arr(F1["angle"], np.float32), _arr(F1["desc"], np.uint8)
+        pm = np.ascontiguousarray(prev_matched, np.float32).copy()
+        x2, y2, o2 = _arr(F2["x"], np.float32), _arr(F2["y"], np.float32), _arr(F2["octave"], np.int32)
+        a2, d2 = _arr(F2["angle"], np.float32), _arr(F2["desc"], np.uint8)
+        m12 = np.full(max(len(o1), 1), -1, np.int32)
+        n = C.c_int()
+        _ck(self.L.eaof_match_initialization(self.h, self.mfNNratio, int(self.mbCheckOrientation), len(o1), _p(o1), _p(a1),
+                                             _p(d1), pm.ctypes.data, len(x2), _p(x2), _p(y2), _p(o2), _p(a2), _p(d2),
+                                             bounds[0], bounds[1], bounds[2], bounds[3], grid_inv[0], grid_inv[1],
+                                             int(window_size), m12.ctypes.data, C.byref(n)))
+        return n.value, m12[:len(o1)], pm
 
     def SearchWindows(self, rule, F, q, th_accept, hist_mode, check_bounds, *, bounds, grid_inv):
         """eaof_match_windows.  F: dict(x,y,octave,desc[,angle,uright,taken]); q: dict(u,v,radius,min_level,max_level,desc

@@ -117,6 +117,17 @@ int eaof_match_windows(eaof_matcher* m, int rule, int n_t, const float* t_x, con
                        const uint8_t* q_desc, const uint8_t* q_obs, int th_accept, float nnratio, int hist_mode,
                        int check_bounds, int* match_t, int* dist_t, int* n_matches);
 
+/* SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  src/ORBmatcher.cc:405-520, HOST buffers.
+ * F1: octave, angle, descriptor of every feature (only level-0 features are matched) and prev_matched (x,y pairs, in/out:
+ * updated to the matched F2 position like vbPrevMatched).  F2: undistorted positions, octaves, angles, descriptors; its
+ * 64x48 grid is rebuilt on the device.  A later F1 feature takes over an F2 feature when its distance is strictly
+ * smaller (the earlier match is undone).  matches12: n1 entries. */
+int eaof_match_initialization(eaof_matcher* m, float nnratio, int check_orientation, int n1, const int* octave1,
+                              const float* angle1, const uint8_t* desc1, float* prev_matched, int n2, const float* x2,
+                              const float* y2, const int* octave2, const float* angle2, const uint8_t* desc2, float min_x,
+                              float max_x, float min_y, float max_y, float grid_inv_w, float grid_inv_h, int window_size,
+                              int* matches12, int* n_matches);
+
 /* ---- batched, device-resident forms used for sequences (BASELINE.json configs[1] and [4]) ------------------ */
 
 /* Consecutive-frame SearchByProjection over the results an extractor handle holds on the device: pair p matches

@@ -411,4 +411,54 @@ int eaoo_search_by_projection_kf(int nC, const float* cx, const float* cy, const
     return nmatches;
 }
 
+// ORBmatcher::SearchForInitialization  src/ORBmatcher.cc:405-520.  prev: vbPrevMatched as (x,y) pairs, in/out.
+int eaoo_search_for_initialization(int n1, const int* oct1, const float* angle1, const uint8_t* desc1, float* prev, int n2,
+                                   const float* x2, const float* y2, const int* oct2, const float* angle2,
+                                   const uint8_t* desc2, float minX, float minY, float invW, float invH, int windowSize,
+                                   float nnratio, int checkOri, int* matches12) {
+    std::vector<int> cellStart(GRID_COLS * GRID_ROWS + 1), cellIdx(n2 > 0 ? n2 : 1);
+    eaoo_build_grid(n2, x2, y2, minX, minY, invW, invH, cellStart.data(), cellIdx.data());
+    int nmatches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;  // :413
+    std::vector<int> vMatchedDistance(n2, 0x7fffffff), vnMatches21(n2, -1), cand;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int level1 = oct1[i1];
+        if (level1 > 0) continue;
+        features_in_area(cellStart.data(), cellIdx.data(), x2, y2, oct2, prev[2 * i1], prev[2 * i1 + 1], (float)windowSize,
+                         level1, level1, minX, minY, invW, invH, cand);
+        if (cand.empty()) continue;
+        int bestDist = 0x7fffffff, bestDist2 = 0x7fffffff, bestIdx2 = -1;
+        for (int i2 : cand) {
+            const int dist = descriptor_distance(desc1 + 32 * (size_t)i1, desc2 + 32 * (size_t)i2);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { matches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                matches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOri) rotHist[rot_bin(angle1[i1], angle2[bestIdx2], factor)].push_back(i1);
+            }
+        }
+    }
+    if (checkOri) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int idx1 : rotHist[i])
+                if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; ++i1)
+        if (matches12[i1] >= 0) { prev[2 * i1] = x2[matches12[i1]]; prev[2 * i1 + 1] = y2[matches12[i1]]; }
+    return nmatches;
+}
+
 }  // extern "C"

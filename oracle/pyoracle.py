@@ -584,3 +584,32 @@ def r_search_by_projection_kf(cur, kf, th, orb_dist, check_ori, *, bounds, grid_
                                                      len(sf), float(log_scale_factor), float(th), int(orb_dist),
                                                      int(check_ori), 0.9, match.ctypes.data)
     return n, match[:nC]
+
+
+def _init_args(F1, F2, prev):
+    return (_a(F1["octave"], np.int32), _a(F1["angle"], np.float32), _a(F1["desc"], np.uint8),
+            np.ascontiguousarray(prev, np.float32).copy(), _a(F2["x"], np.float32), _a(F2["y"], np.float32),
+            _a(F2["octave"], np.int32), _a(F2["angle"], np.float32), _a(F2["desc"], np.uint8))
+
+
+def o_search_for_initialization(F1, F2, prev, window, nnratio, check_ori, *, bounds, grid_inv):
+    """Returns (nmatches, matches12, updated prev).  src/ORBmatcher.cc:405-520."""
+    o1, a1, d1, pm, x2, y2, o2, a2, d2 = _init_args(F1, F2, prev)
+    m = np.full(max(len(o1), 1), -1, np.int32)
+    L = _mo()
+    ci, cf, vp = C.c_int, C.c_float, C.c_void_p
+    L.eaoo_search_for_initialization.argtypes = [ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, ci, cf, ci, vp]
+    n = L.eaoo_search_for_initialization(len(o1), _pp(o1), _pp(a1), _pp(d1), _pp(pm), len(x2), _pp(x2), _pp(y2), _pp(o2),
+                                         _pp(a2), _pp(d2), bounds[0], bounds[2], grid_inv[0], grid_inv[1], int(window),
+                                         float(nnratio), int(check_ori), m.ctypes.data)
+    return n, m[:len(o1)], pm
+
+
+def r_search_for_initialization(F1, F2, prev, window, nnratio, check_ori, *, bounds, grid_inv):
+    o1, a1, d1, pm, x2, y2, o2, a2, d2 = _init_args(F1, F2, prev)
+    m = np.full(max(len(o1), 1), -1, np.int32)
+    n = match_ref_lib().mref_search_for_initialization(len(o1), _pp(o1), _pp(a1), _pp(d1), _pp(pm), len(x2), _pp(x2), _pp(y2),
+                                                       _pp(o2), _pp(a2), _pp(d2), bounds[0], bounds[1], bounds[2], bounds[3],
+                                                       grid_inv[0], grid_inv[1], int(window), float(nnratio), int(check_ori),
+                                                       m.ctypes.data)
+    return n, m[:len(o1)], pm

@@ -125,3 +125,30 @@ def kf_scene(seed, n=900, flags=False):
     kf = dict(state=state, wx=mp["x"], wy=mp["y"], wz=np.ones(n, np.float32), max_dist=max_dist, min_dist=min_dist,
               angle=mp["angle"], desc=mp["desc"])
     return F, kf
+
+
+def init_scene(seed, n=1200):
+    """Two monocular frames for SearchForInitialization: F2 = F1 moved by a few pixels, descriptors noisy copies, with
+    clusters of look-alike F2 features so that later F1 features steal earlier matches (:443-469)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    d1 = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a1 = rng.uniform(0, 360, n).astype(np.float32)
+    x1, y1 = rng.uniform(0, 640, n).astype(np.float32), rng.uniform(0, 480, n).astype(np.float32)
+    o1 = rng.choice(np.arange(3), n, p=[0.7, 0.2, 0.1]).astype(np.int32)
+    d2 = d1 ^ np.packbits((rng.random((n, 256)) < 0.05).astype(np.uint8), axis=1)
+    a2 = np.mod(a1 + rng.normal(0, 4, n), 360).astype(np.float32)
+    x2, y2 = (x1 + rng.normal(0, 3, n)).astype(np.float32), (y1 + rng.normal(0, 3, n)).astype(np.float32)
+    o2 = o1.copy()
+    # look-alike groups: several F1 features close together share (almost) one descriptor
+    for g in range(40):
+        idx = rng.permutation(n)[:4]
+        x1[idx] = x1[idx[0]] + rng.uniform(-4, 4, 4); y1[idx] = y1[idx[0]] + rng.uniform(-4, 4, 4)
+        x2[idx] = x1[idx] + 1; y2[idx] = y1[idx]
+        o1[idx] = 0; o2[idx] = 0
+        d1[idx] = d1[idx[0]] ^ np.packbits((rng.random((4, 256)) < 0.01).astype(np.uint8), axis=1)
+        d2[idx] = d1[idx[0]] ^ np.packbits((rng.random((4, 256)) < 0.02).astype(np.uint8), axis=1)
+    perm = rng.permutation(n)  # F2 in a different order
+    F1 = dict(octave=o1, angle=a1, desc=d1)
+    F2 = dict(x=x2[perm], y=y2[perm], octave=o2[perm], angle=a2[perm], desc=d2[perm])
+    prev = np.stack([x1, y1], 1).astype(np.float32)
+    return F1, F2, prev

@@ -335,3 +335,22 @@ def test_projection_keyframe(matcher_factory, th, orb_dist, case):
         assert np.array_equal(match, om) and np.array_equal(dist, od)
         total += on
     assert total > 30
+
+
+@pytest.mark.parametrize("window", [10, 100])
+@pytest.mark.parametrize("ratio", [0.9, 0.6])
+@pytest.mark.parametrize("ori", [True, False])
+def test_initialization(matcher_factory, window, ratio, ori):
+    """SearchForInitialization (src/ORBmatcher.cc:405-520) incl. match stealing and the vbPrevMatched update."""
+    from matchdata import init_scene
+    from oracle import pyoracle as po
+    m = matcher_factory(ratio, ori)
+    total = 0
+    for seed in range(3):
+        F1, F2, prev = init_scene(500 + seed)
+        n, m12, pm = m.SearchForInitialization(F1, F2, prev, window, bounds=_BOUNDS, grid_inv=_GINV)
+        on, om, op = po.o_search_for_initialization(F1, F2, prev, window, ratio, ori, bounds=_BOUNDS, grid_inv=_GINV)
+        assert n == on, (seed, n, on)
+        assert np.array_equal(m12, om) and np.array_equal(pm, op)
+        total += on
+    assert total > 300

@@ -148,3 +148,18 @@ def test_search_by_projection_kf(th, orb_dist, case):
         assert np.array_equal(rm, om), seed
         total += on
     assert total > 30
+
+
+@pytest.mark.parametrize("window", [10, 100])
+@pytest.mark.parametrize("ratio", [0.9, 0.6])
+@pytest.mark.parametrize("ori", [True, False])
+def test_search_for_initialization(window, ratio, ori):
+    from matchdata import init_scene
+    total = 0
+    for seed in range(3):
+        F1, F2, prev = init_scene(500 + seed)
+        on, om, op = po.o_search_for_initialization(F1, F2, prev, window, ratio, ori, bounds=_BOUNDS, grid_inv=_GINV)
+        rn, rm, rp = po.r_search_for_initialization(F1, F2, prev, window, ratio, ori, bounds=_BOUNDS, grid_inv=_GINV)
+        assert rn == on and np.array_equal(rm, om) and np.array_equal(rp, op), (seed, rn, on)
+        total += on
+    assert total > 300
