@@ -55,6 +55,19 @@ __device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) 
     return d;
 }
 
+// The same distance with 5 POPC instead of 8: POPC issues at a quarter of the ALU rate (it is the pipe the brute-force
+// kernels saturate, profiles/r01_bowdense_full_summary.txt), so three carry-save adders (sum = a^b^c, carry = maj(a,b,c),
+// two LOP3 each) fold seven of the eight XOR words into one weight-1 word and three weight-2 words first.
+__device__ __forceinline__ int hamming256_csa(const uint32_t* a, const uint32_t* b) {
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = a[i] ^ b[i];
+    const uint32_t s1 = x[0] ^ x[1] ^ x[2], c1 = (x[0] & x[1]) | (x[2] & (x[0] ^ x[1]));
+    const uint32_t s2 = x[3] ^ x[4] ^ x[5], c2 = (x[3] & x[4]) | (x[5] & (x[3] ^ x[4]));
+    const uint32_t s3 = s1 ^ s2 ^ x[6], c3 = (s1 & s2) | (x[6] & (s1 ^ s2));
+    return __popc(s3) + __popc(x[7]) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+
 __global__ void k_hamming_pairs(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -147,8 +160,9 @@ __global__ void __launch_bounds__(BOW_QT) k_bow_dense(BowArgs A, const int2* __r
         }
         __syncthreads();
         if (active) {
+#pragma unroll 4
             for (int j = 0; j < tt; ++j) {
-                const int d = hamming256(qd, sT[j]);
+                const int d = hamming256_csa(qd, sT[j]);
                 if (d < A.D) {
                     if (cnt < NEAR_K) {
                         const uint32_t e = (uint32_t)sIdx[j] | ((uint32_t)d << 16);
@@ -406,7 +420,7 @@ __global__ void __launch_bounds__(BOW_QT) k_tri_dense(TriArgs A, const int2* __r
             for (int j = 0; j < tt; ++j) {
                 const TriCand c = sC[j];
                 if (c.idx < 0) continue;
-                const int d = hamming256(qd, sT[j]);
+                const int d = hamming256_csa(qd, sT[j]);
                 if (d > EAOF_TH_LOW || d > bestDist) continue;   // :738
                 const int oct = c.flags >> 8;
                 if (!bStereo1 && !(c.flags & 1)) {               // :743-749 too close to the epipole

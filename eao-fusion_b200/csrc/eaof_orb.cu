@@ -283,8 +283,16 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& L = g.L[l];
         if (L.h >= 40) {
-            const int tasks = ((L.w + 43) / 4) * ((L.h + RSZ_ROWS - 1) / RSZ_ROWS);
-            eaof::k_resize<<<dim3((tasks + RSZ_THREADS - 1) / RSZ_THREADS, n), RSZ_THREADS, 0, s>>>(dPyr, c->dTabs, g, l);
+            // rows per thread: long walks reuse source rows, but small levels / small batches need the threads
+            const long long want = 600000;
+            const int nCW = (L.w + 43) / 4;
+            int rows = 32;
+            while (rows > 8 && (long long)nCW * ((L.h + rows - 1) / rows) * n < want) rows >>= 1;
+            const int tasks = nCW * ((L.h + rows - 1) / rows);
+            const dim3 gr((tasks + RSZ_THREADS - 1) / RSZ_THREADS, n);
+            if (rows == 32) eaof::k_resize<32><<<gr, RSZ_THREADS, 0, s>>>(dPyr, c->dTabs, g, l);
+            else if (rows == 16) eaof::k_resize<16><<<gr, RSZ_THREADS, 0, s>>>(dPyr, c->dTabs, g, l);
+            else eaof::k_resize<8><<<gr, RSZ_THREADS, 0, s>>>(dPyr, c->dTabs, g, l);
         } else {  // tiny levels: border rows may fold more than once
             dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
             eaof::k_resize_generic<<<gr, b, 0, s>>>(dPyr, c->dTabs, g, l);
