@@ -104,7 +104,10 @@ def hamming_sweep(eaof, torch, device, n_blocks=64, n_feat=2000, n_pairs=1024, r
     out = {"workload": f"configs[4]: {n_pairs} pairs of {n_feat}x{n_feat} descriptors, TH_LOW=50, ratio 0.9, rot-hist, device-resident",
            "distances_per_s": dists / secs, "pairs_per_s": n_pairs / secs, "ms_per_sweep": secs * 1e3,
            "matches_per_pair": float(d_nm.float().mean().item()),
-           "popc_peak_per_s": popc, "popc_frac": (8.0 * dists / secs) / popc if popc > 0 else None}
+           "popc_peak_per_s": popc,
+           # 8 XOR words per distance; three carry-save adders fold them so that 5 POPC are executed per distance
+           "popc_executed_per_distance": 5, "xu_pipe_frac": (5.0 * dists / secs) / popc if popc > 0 else None,
+           "frac_of_naive_popc_roofline": (8.0 * dists / secs) / popc if popc > 0 else None}
     del st, e0, e1
     mt.close()
     return out
@@ -346,14 +349,18 @@ def main():
 
     # e2e through the public C-ABI calls with HOST buffers: every step uploads its own 250 frames from pinned host memory
     # (eaof_orb_extract_batch_async), extracts, matches, and downloads keypoints + descriptors + matches
-    # (eaof_orb_extract_batch_wait).  Two handles alternate so that the upload of one step overlaps the kernels of the
-    # previous one — the way a caller streams a sequence; nothing is skipped or reused between steps.
+    # (eaof_orb_extract_batch_wait).  Three handles rotate so that the upload of a step overlaps the kernels of the
+    # previous ones — the way a caller streams a sequence; nothing is skipped or reused between steps.
     h_all = torch.from_numpy(frames).pin_memory()
     slots = []
-    for sl in range(2):
+    n_slots = int(os.environ.get("EAOF_E2E_SLOTS", 3))
+    for sl in range(n_slots):
         exs = ex if sl == 0 else eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=B,
                                                    device=local_rank)
         mts = mt if sl == 0 else eaof.ORBmatcher(0.9, True, max_features=cap, max_pairs=B, device=local_rank)
+        # with two handles in flight the upload of a whole batch already hides under the other handle's kernels:
+        # no chunking inside a call (EAOF_E2E_CHUNK overrides, 0 = the library's default chunk)
+        exs.set_pipeline_chunk(int(os.environ.get("EAOF_E2E_CHUNK", B)))
         slots.append(dict(
             ex=exs, mt=mts, mstream=torch.cuda.ExternalStream(mts.stream_ptr(), device=torch.device("cuda", local_rank)),
             d_match=torch.empty((n_pairs, cap), dtype=torch.int32, device="cuda"),
@@ -365,7 +372,7 @@ def main():
             h_desc=torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()))
 
     def e2e_issue(k):
-        S = slots[k % 2]
+        S = slots[k % n_slots]
         b = k % n_batches
         S["ex"].extract_batch_async(h_all.data_ptr() + b * B * frame_bytes, B, S["h_kps"].data_ptr(), S["h_desc"].data_ptr())
         S["mt"].projection_batch_device(S["ex"], pair_last, pair_cur, shift_x, shift_y, MATCH_TH, S["d_match"].data_ptr(),
@@ -375,23 +382,27 @@ def main():
             S["h_nm"].copy_(S["d_nm"], non_blocking=True)
 
     def e2e_finish(k):
-        S = slots[k % 2]
+        S = slots[k % n_slots]
         cnt = S["ex"].extract_batch_wait()
         S["mt"].sync()
         return cnt
 
     e2e_steps = max(3, min(args.steps, 20))
-    e2e_issue(0); e2e_issue(1); e2e_finish(0); e2e_finish(1)  # warm both slots
+    for k in range(n_slots):  # warm every slot
+        e2e_issue(k)
+    for k in range(n_slots):
+        e2e_finish(k)
     barrier()
     t1 = time.perf_counter()  # host clock: the region ends when the last step's results are in host memory
-    e2e_issue(0)
-    for k in range(1, e2e_steps):
+    for k in range(min(n_slots - 1, e2e_steps)):
         e2e_issue(k)
-        e2e_finish(k - 1)
-    last_cnt = e2e_finish(e2e_steps - 1)
+    for k in range(e2e_steps):
+        if k + n_slots - 1 < e2e_steps:
+            e2e_issue(k + n_slots - 1)
+        last_cnt = e2e_finish(k)
     torch.cuda.synchronize()
     dt_e2e = time.perf_counter() - t1
-    assert int(last_cnt.sum()) > 0 and int(slots[(e2e_steps - 1) % 2]["h_nm"].sum()) > 0
+    assert int(last_cnt.sum()) > 0 and int(slots[(e2e_steps - 1) % n_slots]["h_nm"].sum()) > 0
     e2e_launches = e2e_steps * (slots[0]["ex"].last_launch_count() + 4)
 
     hamming = None
@@ -448,7 +459,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
                     "d2h_bytes_per_step": B * (cap * 56 + 4) + n_pairs * (cap * 4 + 4)},
             "gpu_launches": (launches_per_step + 4) * args.steps,
-            "e2e_detail": {"steps": e2e_steps, "pipeline": "2 handles alternate: upload of step k+1 under the kernels of step k",
+            "e2e_detail": {"steps": e2e_steps, "pipeline": f"{n_slots} handles in rotation: uploads of the next steps under the kernels of step k",
                            "gpu_launches": e2e_launches, "api": "eaof_orb_extract_batch_async/_wait + "
                            "eaof_match_projection_batch_device, pinned host buffers"},
             "hamming": hamming,

@@ -1078,6 +1078,22 @@ struct eaof_matcher {
     float* pairShift = nullptr; // [2][maxPairs]
     int *outMatch = nullptr, *outDist = nullptr, *outN = nullptr;
     long long lastDistances = 0;
+    // Small per-call host arrays (pair lists, shifts) go through a pinned staging buffer: cudaMemcpyAsync from pageable
+    // memory would synchronise the stream first and stall the caller behind the extraction the stream waits for.
+    // Unchanged arrays (a sequence matched batch after batch) are not uploaded again.
+    int* hStage = nullptr;            // [4][maxPairs] words
+    cudaEvent_t evStage = nullptr;    // last upload out of hStage has completed
+    std::vector<int> lastUp[4];
+    int upload_words(int slot, const void* src, int n, void* dst) {
+        const int* w = static_cast<const int*>(src);
+        if ((int)lastUp[slot].size() == n && memcmp(lastUp[slot].data(), w, sizeof(int) * (size_t)n) == 0) return 0;
+        if (cudaEventSynchronize(evStage) != cudaSuccess) return -1;
+        memcpy(hStage + (size_t)slot * maxPairs, w, sizeof(int) * (size_t)n);
+        if (cudaMemcpyAsync(dst, hStage + (size_t)slot * maxPairs, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, stream) != cudaSuccess) return -1;
+        if (cudaEventRecord(evStage, stream) != cudaSuccess) return -1;
+        lastUp[slot].assign(w, w + n);
+        return 0;
+    }
 };
 
 namespace {
@@ -1107,6 +1123,8 @@ int eaof_matcher_create(int device, int maxPairs, int maxFeat, eaof_matcher** ou
 #define A_(x) if (e == cudaSuccess) e = (x)
     A_(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     A_(cudaEventCreateWithFlags(&m->evDep, cudaEventDisableTiming));
+    A_(cudaEventCreateWithFlags(&m->evStage, cudaEventDisableTiming));
+    A_(cudaMallocHost(&m->hStage, sizeof(int) * 4 * (size_t)maxPairs));
     A_(dalloc(&m->nearBuf, PF * 8)); A_(dalloc(&m->accBuf, PF));
     A_(dalloc(&m->cellStart, (size_t)maxPairs * (GRID_CELLS + 1))); A_(dalloc(&m->cellIdx, PF));
     A_(dalloc(&m->cx, PF)); A_(dalloc(&m->cy, PF)); A_(dalloc(&m->cangle, PF)); A_(dalloc(&m->curight, PF));
@@ -1140,6 +1158,8 @@ void eaof_matcher_destroy(eaof_matcher* m) {
                     m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN, m->qRadius, m->qMaxL, m->initBin};
     for (void* p : ptrs) cudaFree(p);
     if (m->evDep) cudaEventDestroy(m->evDep);
+    if (m->evStage) cudaEventDestroy(m->evStage);
+    cudaFreeHost(m->hStage);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -1347,8 +1367,8 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, i
     if (mode != EAOF_BOW_KF_FRAME && mode != EAOF_BOW_KF_KF) return mfail(EAOF_ERR_ARG, "unknown mode");
     MCK(cudaSetDevice(m->device));
     cudaStream_t s = m->stream;
-    MCK(cudaMemcpyAsync(m->pairIdx, pairQ, sizeof(int) * nPairs, cudaMemcpyHostToDevice, s));
-    MCK(cudaMemcpyAsync(m->pairIdx + m->maxPairs, pairT, sizeof(int) * nPairs, cudaMemcpyHostToDevice, s));
+    if (m->upload_words(0, pairQ, nPairs, m->pairIdx) || m->upload_words(1, pairT, nPairs, m->pairIdx + m->maxPairs))
+        return mfail(EAOF_ERR_CUDA, "pair list upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     BowArgs A{};
     A.desc = dDesc; A.angle = dAngle; A.counts = dCounts; A.pairQ = m->pairIdx; A.pairT = m->pairIdx + m->maxPairs;
     A.blockStride = blockStride; A.stride = blockStride; A.mode = mode;
@@ -1554,15 +1574,14 @@ int eaof_match_projection_batch_device(eaof_matcher* m, eaof_orb* ex, int nPairs
     if (cap > m->maxFeat) return mfail(EAOF_ERR_ARG, "extractor keypoint capacity %d exceeds matcher max_features %d", cap, m->maxFeat);
     MCK(cudaSetDevice(m->device));
     cudaStream_t s = m->stream;
+    int* dLast = m->pairIdx; int* dCur = m->pairIdx + m->maxPairs;
+    float* dSx = m->pairShift; float* dSy = m->pairShift + m->maxPairs;
+    if (m->upload_words(0, lastFrame, nPairs, dLast) || m->upload_words(1, curFrame, nPairs, dCur) ||
+        m->upload_words(2, shiftX, nPairs, dSx) || m->upload_words(3, shiftY, nPairs, dSy))
+        return mfail(EAOF_ERR_CUDA, "pair list upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     // order after the extraction that produced the keypoints
     MCK(cudaEventRecord(m->evDep, (cudaStream_t)exStream));
     MCK(cudaStreamWaitEvent(s, m->evDep, 0));
-    int* dLast = m->pairIdx; int* dCur = m->pairIdx + m->maxPairs;
-    float* dSx = m->pairShift; float* dSy = m->pairShift + m->maxPairs;
-    MCK(cudaMemcpyAsync(dLast, lastFrame, sizeof(int) * nPairs, cudaMemcpyHostToDevice, s));
-    MCK(cudaMemcpyAsync(dCur, curFrame, sizeof(int) * nPairs, cudaMemcpyHostToDevice, s));
-    MCK(cudaMemcpyAsync(dSx, shiftX, sizeof(float) * nPairs, cudaMemcpyHostToDevice, s));
-    MCK(cudaMemcpyAsync(dSy, shiftY, sizeof(float) * nPairs, cudaMemcpyHostToDevice, s));
     const int stride = cap;
     k_proj_prepare<<<dim3((cap + 127) / 128, nPairs), 128, 0, s>>>(kps, counts, cap, dLast, dCur, dSx, dSy, stride, m->cx, m->cy,
                                                                   m->coct, m->cangle, m->lu, m->lv, m->loct, m->langle, m->nC,

@@ -255,6 +255,14 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
 }
 
 // Issues the kernel sequence for frames [f0, f0+n) of the workspace; dImgs points at frame f0's image.
+// Kernels of different handles that run at the same time slow each other down on B200 (measured: two handles
+// alternating full batches reach 115 k frames/s against 132 k for one, tools/lanes_experiment.py), while uploads and
+// downloads overlap with kernels for free.  The host-buffer pipeline therefore passes a per-device token from batch to
+// batch: a batch's kernels start only after the kernels of the batch issued before it, whichever handle issued it.
+std::mutex g_tokMu;
+cudaEvent_t g_tok[64] = {};
+bool g_tokSet[64] = {};
+
 int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t framePitch, int f0 = 0) {
     const Geom& g = c->g;
     cudaStream_t s = c->stream;
@@ -610,6 +618,9 @@ int eaof_orb_extract_batch_async(eaof_orb* c, const uint8_t* imgs, int n, int wi
     // the download stream may still be busy with the previous call's copies out of the same device buffers
     CK(cudaEventRecord(c->evOutIdle, c->streamOut));
     CK(cudaStreamWaitEvent(c->stream, c->evOutIdle, 0));
+    const int dev = c->device < 64 ? c->device : 63;
+    std::lock_guard<std::mutex> tokLock(g_tokMu);
+    if (g_tokSet[dev]) CK(cudaStreamWaitEvent(c->stream, g_tok[dev], 0));
     int ci = 0;
     for (int f0 = 0; f0 < n; f0 += chunk, ++ci) {
         const int m = std::min(chunk, n - f0);
@@ -635,6 +646,9 @@ int eaof_orb_extract_batch_async(eaof_orb* c, const uint8_t* imgs, int n, int wi
         if (hD) CK(cudaMemcpyAsync(hD + (size_t)f0 * c->kpCap * 32, c->dDesc + (size_t)f0 * c->kpCap * 32, 32 * (size_t)m * c->kpCap,
                                    cudaMemcpyDeviceToHost, c->streamOut));
     }
+    if (!g_tok[dev]) CK(cudaEventCreateWithFlags(&g_tok[dev], cudaEventDisableTiming));
+    CK(cudaEventRecord(g_tok[dev], c->stream));
+    g_tokSet[dev] = true;
     c->pendN = n; c->pendCap = cap; c->pendKps = kps; c->pendDesc = desc; c->pendDirect = direct;
     return EAOF_OK;
 }

@@ -230,17 +230,6 @@ __device__ __forceinline__ unsigned arc_best2(const unsigned (&d)[16]) {
     return __vmaxu2(best, 2u * FAST_BIAS2 - worst);  // worst <= 511 per lane: no borrow
 }
 
-// Byte-lane unsigned compare on bit 7 of every byte (the other bits are garbage): a > b.  gt7_b: b fixed — nb7 =
-// ~b & 0x7f.. and b as given are precomputed; gt7_a: a fixed — a7 = a & 0x7f.. precomputed.
-__device__ __forceinline__ unsigned gt7_b(unsigned a, unsigned nb7, unsigned b) {
-    const unsigned s = (a & 0x7f7f7f7fu) + nb7;   // bit 7 = carry of the low 7 bits of a - b - 1 >= 0, i.e. a7.. > b7..
-    return (a & ~b) | (~(a ^ b) & s);
-}
-__device__ __forceinline__ unsigned gt7_a(unsigned a, unsigned a7, unsigned b) {
-    const unsigned s = a7 + (~b & 0x7f7f7f7fu);
-    return (a & ~b) | (~(a ^ b) & s);
-}
-
 // One WARP per cell (no CTA-wide barrier anywhere: the warps of a CTA only share the launch).  Candidates are
 // appended to the (frame, level) list in arbitrary order; DistributeOctTree only needs their cell-raster rank for
 // tie-breaking, which k_octree recomputes from the coordinates.
@@ -315,7 +304,6 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     for (int attempt = 0; attempt < 2 && no == 0; ++attempt) {
         const int th = attempt == 0 ? g.iniTh : g.minTh;
         const unsigned thB2 = (unsigned)(th + 256) * 0x00010001u;
-        const unsigned th4 = (unsigned)th * 0x01010101u;
         // ---- (A)
         int nl = 0;
         for (int i0 = 0; i0 < nTasks; i0 += 32) {
@@ -329,16 +317,18 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                 const uint32_t* t = tile + y * PW + 1 + w;
                 const unsigned W0 = t[0], Wm = t[-1], Wp = t[1], Wu = t[-3 * PW], Wd = t[3 * PW];
                 const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
-                // all four pixels of the word at once on byte lanes: B_k = ring_k > min(v+t,255), D_k = ring_k < max(v-t,0)
-                // (bit 7 of every byte; the saturation cannot change either comparison).  "Two adjacent compass points
-                // both brighter" over the 4-cycle 0-4-8-12 is (B0|B8)&(B4|B12), likewise for darker.
-                const unsigned hi = __vaddus4(W0, th4), nhi7 = ~hi & 0x7f7f7f7fu;
-                const unsigned lo = __vsubus4(W0, th4), lo7 = lo & 0x7f7f7f7fu;
-                const unsigned b0 = gt7_b(Wd, nhi7, hi), b4 = gt7_b(V4, nhi7, hi), b8 = gt7_b(Wu, nhi7, hi), b12 = gt7_b(V12, nhi7, hi);
-                const unsigned d0 = gt7_a(lo, lo7, Wd), d4 = gt7_a(lo, lo7, V4), d8 = gt7_a(lo, lo7, Wu), d12 = gt7_a(lo, lo7, V12);
-                const unsigned pass = (((b0 | b8) & (b4 | b12)) | ((d0 | d8) & (d4 | d12))) & 0x80808080u;
-                passE = (pass & 0x00800080u) != 0;
-                passO = (pass & 0x80008000u) != 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned nc = FAST_BIAS2 - (h ? odd(W0) : evn(W0));
+                    const unsigned d0 = (h ? odd(Wd) : evn(Wd)) + nc, d4 = (h ? odd(V4) : evn(V4)) + nc;
+                    const unsigned d8 = (h ? odd(Wu) : evn(Wu)) + nc, d12 = (h ? odd(V12) : evn(V12)) + nc;
+                    const unsigned br = __vimax3_u16x2(__vminu2(d0, d4), __vminu2(d4, d8),
+                                                       __vmaxu2(__vminu2(d8, d12), __vminu2(d12, d0)));
+                    const unsigned dk = __vimin3_u16x2(__vmaxu2(d0, d4), __vmaxu2(d4, d8),
+                                                       __vminu2(__vmaxu2(d8, d12), __vmaxu2(d12, d0)));
+                    const bool p = __vimax3_u16x2(br, 2u * FAST_BIAS2 - dk, thB2) != thB2;  // some lane > th
+                    if (h) passO = p; else passE = p;
+                }
             }
             const unsigned mE = __ballot_sync(0xffffffffu, passE), mO = __ballot_sync(0xffffffffu, passO);
             const int nE = __popc(mE);
