@@ -310,8 +310,10 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     if (prof) CK(cudaEventRecord(c->ev[1], s));
     // FAST is bound by the integer ALU pipe, the blur by the FMA pipe, the quadtree by latency: outside profiling mode
     // (which serialises the stages to time them) the blur runs on the side stream beside FAST + quadtree.
-    cudaStream_t sb = prof ? s : c->stream2;
-    if (!prof) {
+    static const bool serialBlur = getenv("EAOF_SERIAL_BLUR") != nullptr;  // experiment knob
+    const bool side = !prof && !serialBlur;
+    cudaStream_t sb = side ? c->stream2 : s;
+    if (side) {
         CK(cudaEventRecord(c->evPyr, s));
         CK(cudaStreamWaitEvent(sb, c->evPyr, 0));
         eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, sb>>>(dPyr, dBlur, g);
@@ -329,7 +331,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
                                                                          dSlotScore, dLvlCount, g);
     ++launches;
     if (prof) CK(cudaEventRecord(c->ev[3], s));
-    if (prof) {
+    if (!side) {
         eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, s>>>(dPyr, dBlur, g);
         ++launches;
     } else {
