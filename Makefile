@@ -10,8 +10,10 @@ SRCS      := $(PKG)/csrc/eaof_orb.cu $(wildcard $(PKG)/csrc/eaof_match.cu)
 HDRS      := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/eaof_orb.h
 
 DROPIN_T  := tests/cpp/_build/libdropin_harness.so
+DROPIN_M  := tests/cpp/_build/libmatch_dropin.so
+REF       ?= /root/reference
 
-all: $(LIB) $(DROPIN_T)
+all: $(LIB) $(DROPIN_T) matchdropin
 
 $(LIB): $(SRCS) $(HDRS)
 	@mkdir -p $(PKG)/lib
@@ -25,12 +27,25 @@ $(DROPIN_T): tests/cpp/dropin_harness.cc $(PKG)/dropin/ORBextractor.cc $(PKG)/dr
 	g++ -O2 -std=c++14 -fPIC -shared -Wall -Wl,-Bsymbolic -Ioracle/cvshim -I$(PKG)/dropin -Iinclude \
 	    -o $@ tests/cpp/dropin_harness.cc $(PKG)/dropin/ORBextractor.cc -L$(PKG)/lib -leaof_orb -Wl,-rpath,'$$ORIGIN/../../../$(PKG)/lib'
 
+# the drop-in ORB_SLAM2::ORBmatcher methods ($(PKG)/dropin/ORBmatcher.cc, compiled against the reference's own
+# include/ORBmatcher.h) behind the same C harness that drives the unmodified reference ORBmatcher.cc
+# (oracle/match_ref_harness.cc, oracle/matchshim); needs the reference tree for that header and DBoW2's FeatureVector —
+# on the GPU box the prebuilt file shipped by gpurun is used
+matchdropin: $(LIB)
+	@if [ -f $(REF)/include/ORBmatcher.h ]; then \
+	  mkdir -p tests/cpp/_build && \
+	  g++ -O2 -std=c++14 -fPIC -shared -w -ffp-contract=off -Wl,-Bsymbolic -include oracle/matchshim/slam_types.h -Ioracle/matchshim \
+	      -I$(REF)/include -I$(REF)/Thirdparty/DBoW2/DBoW2 -Iinclude -o $(DROPIN_M) oracle/match_ref_harness.cc \
+	      $(PKG)/dropin/ORBmatcher.cc $(REF)/Thirdparty/DBoW2/DBoW2/FeatureVector.cpp \
+	      -L$(PKG)/lib -leaof_orb -Wl,-rpath,'$$ORIGIN/../../../$(PKG)/lib' ; \
+	else echo "reference tree $(REF) not present: keeping prebuilt $(DROPIN_M) (if any)"; fi
+
 oracle:
 	$(MAKE) -C oracle
 	$(MAKE) -C oracle ref
 
 clean:
-	rm -f $(LIB) $(PKG)/lib/ptxas.log $(DROPIN_T)
+	rm -f $(LIB) $(PKG)/lib/ptxas.log $(DROPIN_T) $(DROPIN_M)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean matchdropin

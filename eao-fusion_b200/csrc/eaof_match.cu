@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
             const int bin = rot_bin(A.langle[po + (a & 0xffff)], A.cangle[po + (a >> 16)], factor);
             if (bin != i1 && bin != i2 && bin != i3) {
                 mOut[a >> 16] = -1;
-                if (dOut) dOut[a >> 16] = -1;
+                if (dOut) dOut[a >> 16] = -2;  // matched, then pruned: the reference leaves NULL here, not the old pointer
                 ++removed;
             }
         }

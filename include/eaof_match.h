@@ -79,7 +79,8 @@ int eaof_match_triangulation(eaof_matcher* m, int check_orientation, int only_st
  * grid_inv_h).  Last: per feature the projected pixel (u, v) and 1/z computed by the caller (src/ORBmatcher.cc:1364-1377
  * stays on the host), validity (map point present and not an outlier), octave, angle, the map point's descriptor
  * and obs = pMP->Observations()>0 (NULL = all).  search_mode 0: octave-1..octave+1, 1: bForward, 2: bBackward.
- * match_cur / dist_cur: n_cur entries (index of the Last feature, -1 = none). */
+ * match_cur / dist_cur: n_cur entries (index of the Last feature, -1 = none).  dist_cur is -2 where a match was made and
+ * then removed by the rotation check: the reference leaves NULL in mvpMapPoints there (:1463), not the previous pointer. */
 int eaof_match_projection(eaof_matcher* m, int n_cur, const float* cur_x, const float* cur_y, const int* cur_octave,
                           const float* cur_angle, const uint8_t* cur_desc, const float* cur_uright,
                           const uint8_t* cur_taken, float min_x, float max_x, float min_y, float max_y,
@@ -107,7 +108,8 @@ int eaof_match_projection(eaof_matcher* m, int n_cur, const float* cur_x, const 
  *        levels level-1..level; q_ur = mTrackProjXR; th_accept = TH_HIGH; hist_mode 0; check_bounds 0.  *n_matches
  *        counts accepted queries like the reference's return value.
  * hist_mode: 0 none, 1 factor 1/HISTO_LENGTH, 2 factor HISTO_LENGTH/360.
- * match_t / dist_t: n_t entries (index of the query matched to the target, -1 = none). */
+ * match_t / dist_t: n_t entries (index of the query matched to the target, -1 = none; dist_t -2 = matched, then pruned
+ * by the rotation check). */
 enum { EAOF_WIN_BEST = 0, EAOF_WIN_RATIO_SAME_LEVEL = 1 };
 int eaof_match_windows(eaof_matcher* m, int rule, int n_t, const float* t_x, const float* t_y, const int* t_octave,
                        const float* t_angle, const uint8_t* t_desc, const float* t_uright, const uint8_t* t_taken,

@@ -304,7 +304,7 @@ int eaoo_search_by_projection_last(int nC, const float* cx, const float* cy, con
         three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
         for (int i = 0; i < HISTO_LENGTH; ++i) {
             if (i != i1 && i != i2 && i != i3)
-                for (int j : rotHist[i]) { matchCur[j] = -1; if (distCur) distCur[j] = -1; --nmatches; }
+                for (int j : rotHist[i]) { matchCur[j] = -1; if (distCur) distCur[j] = -2; --nmatches; }  // -2: matched, then pruned
         }
     }
     return nmatches;
@@ -406,7 +406,7 @@ int eaoo_search_by_projection_kf(int nC, const float* cx, const float* cy, const
         three_maxima(rotHist, HISTO_LENGTH, i1, i2, i3);
         for (int i = 0; i < HISTO_LENGTH; ++i)
             if (i != i1 && i != i2 && i != i3)
-                for (int j : rotHist[i]) { matchCur[j] = -1; if (distCur) distCur[j] = -1; --nmatches; }
+                for (int j : rotHist[i]) { matchCur[j] = -1; if (distCur) distCur[j] = -2; --nmatches; }  // -2: matched, then pruned
     }
     return nmatches;
 }

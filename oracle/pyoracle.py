@@ -399,40 +399,49 @@ MATCH_REF_SO = os.path.join(HERE, "_ref", "libmatch_ref.so")
 _mref = None
 
 
+def _setup_mref(L):
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    L.mref_hamming.argtypes = [vp, vp]
+    L.mref_predict_scale.argtypes = [cf, cf, cf]
+    L.mref_norm3.restype = cf
+    L.mref_norm3.argtypes = [cf, cf, cf]
+    L.mref_search_by_bow.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, cf, ci, vp]
+    L.mref_search_for_triangulation.argtypes = ([ci] + [vp] * 6 + [ci] + [vp] * 7 + [ci] + [vp] * 3 + [ci] + [vp] * 3 +
+                                                [vp, cf, cf, vp, vp, ci, ci, ci, cf, vp])
+    L.mref_search_by_projection_last.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp,
+                                                 vp, vp, vp, vp, vp, vp, ci, cf, cf, ci, ci, cf, vp]
+    L.mref_search_by_projection_mappoints.argtypes = [ci, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp,
+                                                      vp, vp, vp, vp, vp, vp, vp, ci, cf, cf, vp]
+    L.mref_search_for_initialization.argtypes = [ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci,
+                                                 cf, ci, vp]
+    L.mref_search_by_projection_kf.argtypes = [ci, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp, vp,
+                                               vp, vp, vp, vp, vp, ci, cf, cf, ci, ci, cf, vp]
+    return L
+
+
 def match_ref_lib():
     global _mref
     if _mref is None:
         if not os.path.exists(MATCH_REF_SO):
             subprocess.check_call(["make", "-s", "-C", HERE, "matchref"])
-        L = C.CDLL(MATCH_REF_SO)
-        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
-        L.mref_hamming.argtypes = [vp, vp]
-        L.mref_predict_scale.argtypes = [cf, cf, cf]
-        L.mref_norm3.restype = cf
-        L.mref_norm3.argtypes = [cf, cf, cf]
-        L.mref_search_by_bow.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, cf, ci, vp]
-        L.mref_search_for_triangulation.argtypes = ([ci] + [vp] * 6 + [ci] + [vp] * 7 + [ci] + [vp] * 3 + [ci] + [vp] * 3 +
-                                                    [vp, cf, cf, vp, vp, ci, ci, ci, cf, vp])
-        L.mref_search_by_projection_last.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp,
-                                                     vp, vp, vp, vp, vp, vp, ci, cf, cf, ci, ci, cf, vp]
-        L.mref_search_by_projection_mappoints.argtypes = [ci, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp,
-                                                          vp, vp, vp, vp, vp, vp, vp, ci, cf, cf, vp]
-        L.mref_search_for_initialization.argtypes = [ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci,
-                                                     cf, ci, vp]
-        L.mref_search_by_projection_kf.argtypes = [ci, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp, vp,
-                                                   vp, vp, vp, vp, vp, ci, cf, cf, ci, ci, cf, vp]
-        _mref = L
+        _mref = _setup_mref(C.CDLL(MATCH_REF_SO))
     return _mref
 
 
-def r_hamming(a, b):
+def match_harness_lib(path):
+    """The same C harness (oracle/match_ref_harness.cc) linked against another implementation of ORB_SLAM2::ORBmatcher,
+    e.g. the drop-in class over the C ABI (tests/cpp/_build/libmatch_dropin.so).  Use as r_*(..., L=lib)."""
+    return _setup_mref(C.CDLL(path))
+
+
+def r_hamming(a, b, L=None):
     a = _a(a, np.uint8).reshape(-1, 32)
     b = _a(b, np.uint8).reshape(-1, 32)
-    L = match_ref_lib()
+    L = L or match_ref_lib()
     return np.array([L.mref_hamming(a[i].ctypes.data, b[i].ctypes.data) for i in range(len(a))], np.int32)
 
 
-def r_search_by_bow(mode, nnratio, check_ori, desc_q, angle_q, valid_q, nodes_q, desc_t, angle_t, valid_t, nodes_t):
+def r_search_by_bow(mode, nnratio, check_ori, desc_q, angle_q, valid_q, nodes_q, desc_t, angle_t, valid_t, nodes_t, L=None):
     dq, dt = _a(desc_q, np.uint8), _a(desc_t, np.uint8)
     aq, at = _a(angle_q, np.float32), _a(angle_t, np.float32)
     vq, vt = _a(valid_q, np.uint8), _a(valid_t, np.uint8)
@@ -441,13 +450,13 @@ def r_search_by_bow(mode, nnratio, check_ori, desc_q, angle_q, valid_q, nodes_q,
     nq, nt = len(dq), len(dt)
     nout = nt if mode == 0 else nq
     match = np.full(max(nout, 1), -1, np.int32)
-    n = match_ref_lib().mref_search_by_bow(mode, nq, _pp(dq), _pp(aq), _pp(vq), nt, _pp(dt), _pp(at), _pp(vt), len(iq),
+    n = (L or match_ref_lib()).mref_search_by_bow(mode, nq, _pp(dq), _pp(aq), _pp(vq), nt, _pp(dt), _pp(at), _pp(vt), len(iq),
                                            _pp(iq), _pp(sq), _pp(xq), len(it), _pp(it), _pp(st), _pp(xt), nnratio,
                                            int(check_ori), match.ctypes.data)
     return n, match[:nout]
 
 
-def r_search_for_triangulation(k1, k2, F12, epipole, scale_factors, level_sigma2, only_stereo, check_ori):
+def r_search_for_triangulation(k1, k2, F12, epipole, scale_factors, level_sigma2, only_stereo, check_ori, L=None):
     d1, d2 = _a(k1["desc"], np.uint8), _a(k2["desc"], np.uint8)
     x1, y1, a1 = (_a(k1[k], np.float32) for k in ("x", "y", "angle"))
     x2, y2, a2 = (_a(k2[k], np.float32) for k in ("x", "y", "angle"))
@@ -460,7 +469,7 @@ def r_search_for_triangulation(k1, k2, F12, epipole, scale_factors, level_sigma2
     sf, ls = _a(scale_factors, np.float32), _a(level_sigma2, np.float32)
     n1, n2 = len(d1), len(d2)
     match = np.full(max(n1, 1), -1, np.int32)
-    n = match_ref_lib().mref_search_for_triangulation(n1, _pp(d1), _pp(x1), _pp(y1), _pp(a1), _pp(f1), _pp(s1), n2, _pp(d2),
+    n = (L or match_ref_lib()).mref_search_for_triangulation(n1, _pp(d1), _pp(x1), _pp(y1), _pp(a1), _pp(f1), _pp(s1), n2, _pp(d2),
                                                       _pp(x2), _pp(y2), _pp(o2), _pp(a2), _pp(f2), _pp(s2), len(i1), _pp(i1),
                                                       _pp(st1), _pp(ix1), len(i2), _pp(i2), _pp(st2), _pp(ix2), _pp(F),
                                                       float(epipole[0]), float(epipole[1]), _pp(sf), _pp(ls), len(sf),
@@ -468,7 +477,7 @@ def r_search_for_triangulation(k1, k2, F12, epipole, scale_factors, level_sigma2
     return n, match[:n1]
 
 
-def r_search_by_projection(cur, last, th, check_ori, *, bounds, grid_inv, scale_factors, mbf=0.0, search_mode=0):
+def r_search_by_projection(cur, last, th, check_ori, *, bounds, grid_inv, scale_factors, mbf=0.0, search_mode=0, L=None):
     cx, cy = _a(cur["x"], np.float32), _a(cur["y"], np.float32)
     co, ca, cd = _a(cur["octave"], np.int32), _a(cur["angle"], np.float32), _a(cur["desc"], np.uint8)
     cur_r, ctk = _a(cur.get("uright"), np.float32), _a(cur.get("taken"), np.uint8)
@@ -478,7 +487,7 @@ def r_search_by_projection(cur, last, th, check_ori, *, bounds, grid_inv, scale_
     sf = _a(scale_factors, np.float32)
     nc, nl = len(cx), len(lu)
     match = np.full(max(nc, 1), -1, np.int32)
-    n = match_ref_lib().mref_search_by_projection_last(nc, _pp(cx), _pp(cy), _pp(co), _pp(ca), _pp(cd), _pp(cur_r), _pp(ctk),
+    n = (L or match_ref_lib()).mref_search_by_projection_last(nc, _pp(cx), _pp(cy), _pp(co), _pp(ca), _pp(cd), _pp(cur_r), _pp(ctk),
                                                        bounds[0], bounds[1], bounds[2], bounds[3], grid_inv[0], grid_inv[1],
                                                        nl, _pp(lval), _pp(lu), _pp(lv), _pp(linv), _pp(lo), _pp(la), _pp(ld),
                                                        _pp(lobs), _pp(sf), len(sf), float(th), float(mbf), search_mode,
@@ -512,7 +521,7 @@ def o_search_by_projection_mappoints(F, mp, th, nnratio, *, bounds, grid_inv, sc
     return n, match[:nF], dist[:nF]
 
 
-def r_search_by_projection_mappoints(F, mp, th, nnratio, *, bounds, grid_inv, scale_factors):
+def r_search_by_projection_mappoints(F, mp, th, nnratio, *, bounds, grid_inv, scale_factors, L=None):
     fx, fy, fo, _, fd, fr, ft = _frame_arrays(F)
     px, py, pl, pd = _a(mp["x"], np.float32), _a(mp["y"], np.float32), _a(mp["level"], np.int32), _a(mp["desc"], np.uint8)
     iv, bad, pxr = _a(mp.get("in_view"), np.uint8), _a(mp.get("bad"), np.uint8), _a(mp.get("xr"), np.float32)
@@ -520,7 +529,7 @@ def r_search_by_projection_mappoints(F, mp, th, nnratio, *, bounds, grid_inv, sc
     sf = _a(scale_factors, np.float32)
     nF, nM = len(fx), len(px)
     match = np.full(max(nF, 1), -1, np.int32)
-    n = match_ref_lib().mref_search_by_projection_mappoints(nF, _pp(fx), _pp(fy), _pp(fo), _pp(fd), _pp(fr), _pp(ft),
+    n = (L or match_ref_lib()).mref_search_by_projection_mappoints(nF, _pp(fx), _pp(fy), _pp(fo), _pp(fd), _pp(fr), _pp(ft),
                                                             bounds[0], bounds[1], bounds[2], bounds[3], grid_inv[0],
                                                             grid_inv[1], nM, _pp(iv), _pp(bad), _pp(px), _pp(py), _pp(pxr),
                                                             _pp(pl), _pp(pc), _pp(pd), _pp(po_), _pp(sf), len(sf), float(th),
@@ -569,7 +578,7 @@ def o_search_by_projection_kf(cur, kq, th, orb_dist, check_ori, *, bounds, grid_
     return n, match[:nC], dist[:nC]
 
 
-def r_search_by_projection_kf(cur, kf, th, orb_dist, check_ori, *, bounds, grid_inv, scale_factors, log_scale_factor):
+def r_search_by_projection_kf(cur, kf, th, orb_dist, check_ori, *, bounds, grid_inv, scale_factors, log_scale_factor, L=None):
     """kf: dict(state,wx,wy,wz,max_dist,min_dist,angle,desc); state 0 none, 1 bad, 2 already found, 3 usable."""
     cx, cy, co, ca, cd, _, ct = _frame_arrays(cur)
     st, wx, wy, wz = _a(kf["state"], np.uint8), _a(kf["wx"], np.float32), _a(kf["wy"], np.float32), _a(kf["wz"], np.float32)
@@ -578,7 +587,7 @@ def r_search_by_projection_kf(cur, kf, th, orb_dist, check_ori, *, bounds, grid_
     sf = _a(scale_factors, np.float32)
     nC, nK = len(cx), len(st)
     match = np.full(max(nC, 1), -1, np.int32)
-    n = match_ref_lib().mref_search_by_projection_kf(nC, _pp(cx), _pp(cy), _pp(co), _pp(ca), _pp(cd), _pp(ct), bounds[0],
+    n = (L or match_ref_lib()).mref_search_by_projection_kf(nC, _pp(cx), _pp(cy), _pp(co), _pp(ca), _pp(cd), _pp(ct), bounds[0],
                                                      bounds[1], bounds[2], bounds[3], grid_inv[0], grid_inv[1], nK, _pp(st),
                                                      _pp(wx), _pp(wy), _pp(wz), _pp(mx), _pp(mn), _pp(ka), _pp(kd), _pp(sf),
                                                      len(sf), float(log_scale_factor), float(th), int(orb_dist),
@@ -605,10 +614,10 @@ def o_search_for_initialization(F1, F2, prev, window, nnratio, check_ori, *, bou
     return n, m[:len(o1)], pm
 
 
-def r_search_for_initialization(F1, F2, prev, window, nnratio, check_ori, *, bounds, grid_inv):
+def r_search_for_initialization(F1, F2, prev, window, nnratio, check_ori, *, bounds, grid_inv, L=None):
     o1, a1, d1, pm, x2, y2, o2, a2, d2 = _init_args(F1, F2, prev)
     m = np.full(max(len(o1), 1), -1, np.int32)
-    n = match_ref_lib().mref_search_for_initialization(len(o1), _pp(o1), _pp(a1), _pp(d1), _pp(pm), len(x2), _pp(x2), _pp(y2),
+    n = (L or match_ref_lib()).mref_search_for_initialization(len(o1), _pp(o1), _pp(a1), _pp(d1), _pp(pm), len(x2), _pp(x2), _pp(y2),
                                                        _pp(o2), _pp(a2), _pp(d2), bounds[0], bounds[1], bounds[2], bounds[3],
                                                        grid_inv[0], grid_inv[1], int(window), float(nnratio), int(check_ori),
                                                        m.ctypes.data)

@@ -302,3 +302,31 @@ def test_dropin_class_loads_and_refuses_to_run_without_cuda():
         rc = d.L.dropin_extract(d.h, img.ctypes.data, 320, 240, 320, None, None, 0, 0, None)
         assert rc == -2
     d.close()
+
+
+def test_matcher_dropin_loads_and_refuses_to_run_without_cuda():
+    """tests/cpp/_build/libmatch_dropin.so = the drop-in ORBmatcher.cc behind the reference harness: on a box without a
+    GPU every search must throw (no CPU fallback) — the harness lets the C++ exception terminate a child process."""
+    so = os.path.join(ROOT, "tests", "cpp", "_build", "libmatch_dropin.so")
+    if not os.path.exists(so):
+        pytest.skip("drop-in matcher harness not built (needs /root/reference headers)")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    code = f"""
+import sys
+sys.path[:0] = [{ROOT!r}, {os.path.join(ROOT, 'eao-fusion_b200')!r}, {os.path.join(ROOT, 'tests')!r}]
+import numpy as np
+from oracle import pyoracle as po
+from matchdata import planted_pair
+import eaof
+D = po.match_harness_lib({so!r})
+assert D.mref_th_low() == 50
+q, aq, t, at = planted_pair(50, 60, 1)
+n0 = eaof.csr_from_nodes(np.zeros(50, int)); n1 = eaof.csr_from_nodes(np.zeros(60, int))
+po.r_search_by_bow(0, 0.9, True, q, aq, None, n0, t, at, None, n1, L=D)
+print("RETURNED")
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert "RETURNED" not in out.stdout and out.returncode != 0
+    assert "no CUDA device" in out.stderr or "eaof_matcher_create" in out.stderr, out.stderr[-2000:]
