@@ -612,17 +612,23 @@ __device__ __forceinline__ void level_window(int searchMode, int oct, int& minLe
     else { minLevel = oct - 1; maxLevel = oct + 1; }               // :1391
 }
 
-// phase 1: one thread per Last feature: TOP_K best candidates (dist asc, candidate order asc) + candidate count
+// phase 1: PROJ_LANES lanes per query.  The candidate sequence of Frame::GetFeaturesInArea (cells in (ix, iy) order,
+// features of a cell in insertion order) is dealt round-robin to the lanes by its running ordinal, so that the scattered
+// position / descriptor loads of different candidates are in flight together; every lane keeps its TOP_K best
+// (distance, then ordinal), and the lanes' sorted lists are merged by PROJ_LANES-way selection.  Output per query: the
+// TOP_K best candidates by (dist asc, arrival asc) + the number of candidates with dist <= cut.
+#define PROJ_LANES 4
 __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __restrict__ cellStart,
                                                     const int* __restrict__ cellIdx, uint32_t* __restrict__ topBuf) {
-    const int pair = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.nL[pair]) return;
+    const int pair = blockIdx.y;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / PROJ_LANES, sub = threadIdx.x & (PROJ_LANES - 1);
+    const unsigned grp = 0xfu << (threadIdx.x & 28);  // the lanes of this query inside the warp
+    if (i >= A.nL[pair]) return;                      // whole groups leave together
     const size_t po = (size_t)pair * A.stride;
-    uint32_t* o = topBuf + (po + i) * 8;
-    int count = -1;
-    uint32_t top[TOP_K];
+    int count = 0;
+    uint32_t top[TOP_K], ordv[TOP_K];
 #pragma unroll
-    for (int k = 0; k < TOP_K; ++k) top[k] = 0xffffffffu;
+    for (int k = 0; k < TOP_K; ++k) { top[k] = 0xffffffffu; ordv[k] = 0xffffffffu; }
     float u, v, r, ur;
     int minLevel, maxLevel;
     const bool ok = query_window(A, po, i, u, v, r, minLevel, maxLevel, ur);
@@ -635,28 +641,84 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
         }
         const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
         const float* cur = A.curight ? A.curight + po : nullptr;
-        count = 0;
-        for_each_candidate(A, cellStart + (size_t)pair * (GRID_CELLS + 1), cellIdx + po, A.cx + po, A.cy + po, A.coct + po,
-                           u, v, r, minLevel, maxLevel, [&](int k) {
-            if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) return;  // :1409-1415
-            uint32_t td[8];
-            const uint4* p = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
-            const uint4 a = p[0], b = p[1];
-            td[0] = a.x; td[1] = a.y; td[2] = a.z; td[3] = a.w; td[4] = b.x; td[5] = b.y; td[6] = b.z; td[7] = b.w;
-            const uint32_t d = (uint32_t)hamming256(qd, td);
-            if (d > (uint32_t)A.cut) return;  // can never influence the outcome, so it need not be kept, counted or re-scanned
-            uint32_t e = (d << 16) | (uint32_t)k;
-            // insertion into the sorted top-K by distance only; ties keep the earlier arrival in front
-            bool shifting = false;  // once inserted, everything behind moves down one slot
+        const int* cs = cellStart + (size_t)pair * (GRID_CELLS + 1);
+        const int* ci = cellIdx + po;
+        const float* cx = A.cx + po;
+        const float* cy = A.cy + po;
+        const int* coct = A.coct + po;
+        // Frame::GetFeaturesInArea, src/Frame.cc:696-749
+        const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, A.minX), r), A.invW)));
+        const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, A.minX), r), A.invW)));
+        const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, A.minY), r), A.invH)));
+        const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, A.minY), r), A.invH)));
+        const bool any = !(nMinCellX >= GRID_COLS || nMaxCellX < 0 || nMinCellY >= GRID_ROWS || nMaxCellY < 0);
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        int ord = 0;
+        if (any)
+            for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
+                const int c0 = ix * GRID_ROWS + nMinCellY;
+                for (int c = c0; c <= c0 + (nMaxCellY - nMinCellY); ++c) {
+                    const int b = cs[c], e = cs[c + 1];
+                    for (int j = b + ((sub - ord) & (PROJ_LANES - 1)); j < e; j += PROJ_LANES) {
+                        const int k = ci[j];
+                        if (bCheckLevels) {
+                            const int o = coct[k];
+                            if (o < minLevel) continue;
+                            if (maxLevel >= 0 && o > maxLevel) continue;
+                        }
+                        const float dx = __fsub_rn(cx[k], u), dy = __fsub_rn(cy[k], v);
+                        if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
+                        if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) continue;  // :1409-1415
+                        uint32_t td[8];
+                        const uint4* p = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
+                        const uint4 a = p[0], b2 = p[1];
+                        td[0] = a.x; td[1] = a.y; td[2] = a.z; td[3] = a.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
+                        const uint32_t d = (uint32_t)hamming256(qd, td);
+                        if (d > (uint32_t)A.cut) continue;  // can never influence the outcome: not kept, counted or re-scanned
+                        uint32_t e2 = (d << 16) | (uint32_t)k, o2 = (uint32_t)(ord + (j - b));
+                        // sorted insertion by distance; this lane's candidates arrive in ordinal order, ties keep the earlier
+                        bool shifting = false;
 #pragma unroll
-            for (int s = 0; s < TOP_K; ++s) {
-                if (shifting || (e >> 16) < (top[s] >> 16)) { const uint32_t t = top[s]; top[s] = e; e = t; shifting = true; }
+                        for (int s2 = 0; s2 < TOP_K; ++s2) {
+                            if (shifting || (e2 >> 16) < (top[s2] >> 16)) {
+                                const uint32_t t = top[s2], to = ordv[s2];
+                                top[s2] = e2; ordv[s2] = o2; e2 = t; o2 = to; shifting = true;
+                            }
+                        }
+                        ++count;
+                    }
+                    ord += e - b;
+                }
             }
-            ++count;
-        });
     }
-    reinterpret_cast<uint4*>(o)[0] = make_uint4(top[0], top[1], top[2], top[3]);
-    reinterpret_cast<uint4*>(o)[1] = make_uint4(top[4], top[5], 0, (uint32_t)count);
+    // merge: TOP_K rounds, each takes the smallest (dist, ordinal) head among the lanes of the group
+    uint32_t out[TOP_K];
+    int head = 0;
+#pragma unroll
+    for (int round = 0; round < TOP_K; ++round) {
+        uint32_t hv = 0xffffffffu, ho = 0xffffffffu;
+#pragma unroll
+        for (int s2 = 0; s2 < TOP_K; ++s2)
+            if (s2 == head) { hv = top[s2]; ho = ordv[s2]; }
+        unsigned long long key = hv == 0xffffffffu ? ~0ull : (((unsigned long long)(hv >> 16)) << 40) | ((unsigned long long)ho << 8) | sub;
+        unsigned long long best = key;
+#pragma unroll
+        for (int o = 1; o < PROJ_LANES; o <<= 1) {
+            const unsigned long long other = __shfl_xor_sync(grp, best, o);
+            best = other < best ? other : best;
+        }
+        const int winner = (int)(best & 0xff);
+        const uint32_t wv = __shfl_sync(grp, hv, (threadIdx.x & 28) | (winner & (PROJ_LANES - 1)));
+        out[round] = best == ~0ull ? 0xffffffffu : wv;
+        if (best != ~0ull && winner == sub) ++head;
+    }
+#pragma unroll
+    for (int o = 1; o < PROJ_LANES; o <<= 1) count += __shfl_xor_sync(grp, count, o);
+    if (sub == 0) {
+        uint32_t* o = topBuf + (po + i) * 8;
+        reinterpret_cast<uint4*>(o)[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        reinterpret_cast<uint4*>(o)[1] = make_uint4(out[4], out[5], 0, ok ? (uint32_t)count : 0xffffffffu);
+    }
 }
 
 // phase 2: one warp per pair, Last features in index order
@@ -1385,7 +1447,7 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, i
 static int run_projection(eaof_matcher* m, ProjArgs& A, int nPairs, int maxL, int* dMatch, int* dDist, int* dN) {
     cudaStream_t s = m->stream;
     k_build_grid<<<nPairs, 256, 0, s>>>(A, m->cellStart, m->cellIdx);
-    k_proj_dense<<<dim3((maxL + 127) / 128, nPairs), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
+    k_proj_dense<<<dim3((maxL * PROJ_LANES + 127) / 128, nPairs), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
     const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
     k_proj_resolve<<<nPairs, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->accBuf, dMatch, dDist, dN);
     MCK(cudaGetLastError());
@@ -1492,7 +1554,7 @@ int eaof_match_windows(eaof_matcher* m, int rule, int nT, const float* tx, const
     }
     if (!turight) A.curight = nullptr;
     k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx);
-    k_proj_dense<<<dim3((nQ + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
+    k_proj_dense<<<dim3((nQ * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
     const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
     if (rule == EAOF_WIN_BEST)
         k_proj_resolve<<<1, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->accBuf, m->outMatch, m->outDist, m->outN);
@@ -1547,7 +1609,7 @@ int eaof_match_initialization(eaof_matcher* m, float nnratio, int checkOri, int 
     A.cut = near_threshold(EAOF_TH_LOW, nnratio) - 1;
     if (A.cut > 256) A.cut = 256;
     k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx);
-    k_proj_dense<<<dim3((n1 + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
+    k_proj_dense<<<dim3((n1 * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
     k_init_resolve<<<1, 32, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->idxQ, m->idxT, m->initBin, m->outMatch, m->outN);
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(matches12, m->outMatch, sizeof(int) * n1, cudaMemcpyDeviceToHost, s));
