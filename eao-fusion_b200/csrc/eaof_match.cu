@@ -526,7 +526,8 @@ __device__ __forceinline__ bool query_window(const ProjArgs& A, size_t po, int i
 
 // Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:599-614,751-761): one CTA per pair builds the CSR grid of
 // the Cur frame; cell lists are sorted ascending so they equal the reference's push_back order.
-__global__ void __launch_bounds__(256) k_build_grid(ProjArgs A, int* __restrict__ cellStart, int* __restrict__ cellIdx) {
+__global__ void __launch_bounds__(256) k_build_grid(ProjArgs A, int* __restrict__ cellStart, int* __restrict__ cellIdx,
+                                                    float4* __restrict__ cellPack) {
     __shared__ int cnt[GRID_CELLS];
     __shared__ int warpTot[8];
     const int pair = blockIdx.x, tid = threadIdx.x;
@@ -574,6 +575,16 @@ __global__ void __launch_bounds__(256) k_build_grid(ProjArgs A, int* __restrict_
             ci[j + 1] = v;
         }
     }
+    __syncthreads();
+    // the same lists with the fields phase 1 filters on next to each other: (x, y, octave, feature index) per entry, so
+    // that a query streams over one contiguous run per grid column instead of chasing cellIdx -> x/y/octave
+    float4* pk = cellPack + (size_t)pair * A.stride;
+    const int* oct = A.coct + (size_t)pair * A.stride;
+    const int total = cs[GRID_CELLS];
+    for (int j = tid; j < total; j += 256) {
+        const int k = ci[j];
+        pk[j] = make_float4(x[k], y[k], __int_as_float(oct[k]), __int_as_float(k));
+    }
 }
 
 // Walks Frame::GetFeaturesInArea (src/Frame.cc:696-749) for one query and calls f(k) for every candidate, in the
@@ -619,7 +630,7 @@ __device__ __forceinline__ void level_window(int searchMode, int oct, int& minLe
 // TOP_K best candidates by (dist asc, arrival asc) + the number of candidates with dist <= cut.
 #define PROJ_LANES 4
 __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __restrict__ cellStart,
-                                                    const int* __restrict__ cellIdx, uint32_t* __restrict__ topBuf) {
+                                                    const float4* __restrict__ cellPack, uint32_t* __restrict__ topBuf) {
     const int pair = blockIdx.y;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / PROJ_LANES, sub = threadIdx.x & (PROJ_LANES - 1);
     const unsigned grp = 0xfu << (threadIdx.x & 28);  // the lanes of this query inside the warp
@@ -642,11 +653,9 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
         const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
         const float* cur = A.curight ? A.curight + po : nullptr;
         const int* cs = cellStart + (size_t)pair * (GRID_CELLS + 1);
-        const int* ci = cellIdx + po;
-        const float* cx = A.cx + po;
-        const float* cy = A.cy + po;
-        const int* coct = A.coct + po;
-        // Frame::GetFeaturesInArea, src/Frame.cc:696-749
+        const float4* pk = cellPack + po;
+        // Frame::GetFeaturesInArea, src/Frame.cc:696-749.  Cells (ix, iy0..iy1) are adjacent in the CSR order, so one grid
+        // column is one contiguous run of entries, in the reference's visiting order.
         const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, A.minX), r), A.invW)));
         const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, A.minX), r), A.invW)));
         const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, A.minY), r), A.invH)));
@@ -656,17 +665,17 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
         int ord = 0;
         if (any)
             for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
-                const int c0 = ix * GRID_ROWS + nMinCellY;
-                for (int c = c0; c <= c0 + (nMaxCellY - nMinCellY); ++c) {
-                    const int b = cs[c], e = cs[c + 1];
+                {
+                    const int b = cs[ix * GRID_ROWS + nMinCellY], e = cs[ix * GRID_ROWS + nMaxCellY + 1];
                     for (int j = b + ((sub - ord) & (PROJ_LANES - 1)); j < e; j += PROJ_LANES) {
-                        const int k = ci[j];
+                        const float4 ent = __ldg(pk + j);
+                        const int k = __float_as_int(ent.w);
                         if (bCheckLevels) {
-                            const int o = coct[k];
+                            const int o = __float_as_int(ent.z);
                             if (o < minLevel) continue;
                             if (maxLevel >= 0 && o > maxLevel) continue;
                         }
-                        const float dx = __fsub_rn(cx[k], u), dy = __fsub_rn(cy[k], v);
+                        const float dx = __fsub_rn(ent.x, u), dy = __fsub_rn(ent.y, v);
                         if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
                         if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) continue;  // :1409-1415
                         uint32_t td[8];
@@ -1120,6 +1129,7 @@ struct eaof_matcher {
     cudaEvent_t evDep = nullptr;
     uint32_t *nearBuf = nullptr, *accBuf = nullptr;
     int *cellStart = nullptr, *cellIdx = nullptr;
+    float4* cellPack = nullptr;  // grid lists as (x, y, octave, index) entries
     // SoA staging, [maxPairs][maxFeat]
     float *cx = nullptr, *cy = nullptr, *cangle = nullptr, *curight = nullptr, *lu = nullptr, *lv = nullptr,
           *linvz = nullptr, *langle = nullptr;
@@ -1188,7 +1198,7 @@ int eaof_matcher_create(int device, int maxPairs, int maxFeat, eaof_matcher** ou
     A_(cudaEventCreateWithFlags(&m->evStage, cudaEventDisableTiming));
     A_(cudaMallocHost(&m->hStage, sizeof(int) * 4 * (size_t)maxPairs));
     A_(dalloc(&m->nearBuf, PF * 8)); A_(dalloc(&m->accBuf, PF));
-    A_(dalloc(&m->cellStart, (size_t)maxPairs * (GRID_CELLS + 1))); A_(dalloc(&m->cellIdx, PF));
+    A_(dalloc(&m->cellStart, (size_t)maxPairs * (GRID_CELLS + 1))); A_(dalloc(&m->cellIdx, PF)); A_(dalloc(&m->cellPack, PF));
     A_(dalloc(&m->cx, PF)); A_(dalloc(&m->cy, PF)); A_(dalloc(&m->cangle, PF)); A_(dalloc(&m->curight, PF));
     A_(dalloc(&m->lu, PF)); A_(dalloc(&m->lv, PF)); A_(dalloc(&m->linvz, PF)); A_(dalloc(&m->langle, PF));
     A_(dalloc(&m->coct, PF)); A_(dalloc(&m->loct, PF));
@@ -1217,7 +1227,7 @@ void eaof_matcher_destroy(eaof_matcher* m) {
     void* ptrs[] = {m->nearBuf, m->accBuf, m->cellStart, m->cellIdx, m->cx, m->cy, m->cangle, m->curight, m->lu, m->lv,
                     m->linvz, m->langle, m->coct, m->loct, m->nC, m->nL, m->cRow, m->lRow, m->ctaken, m->lvalid, m->lobs,
                     m->desc2, m->angle2, m->validQ, m->validT, m->idxQ, m->idxT, m->segs, m->segStart, m->tiles,
-                    m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN, m->qRadius, m->qMaxL, m->initBin};
+                    m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN, m->qRadius, m->qMaxL, m->initBin, m->cellPack};
     for (void* p : ptrs) cudaFree(p);
     if (m->evDep) cudaEventDestroy(m->evDep);
     if (m->evStage) cudaEventDestroy(m->evStage);
@@ -1446,8 +1456,8 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, i
 
 static int run_projection(eaof_matcher* m, ProjArgs& A, int nPairs, int maxL, int* dMatch, int* dDist, int* dN) {
     cudaStream_t s = m->stream;
-    k_build_grid<<<nPairs, 256, 0, s>>>(A, m->cellStart, m->cellIdx);
-    k_proj_dense<<<dim3((maxL * PROJ_LANES + 127) / 128, nPairs), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
+    k_build_grid<<<nPairs, 256, 0, s>>>(A, m->cellStart, m->cellIdx, m->cellPack);
+    k_proj_dense<<<dim3((maxL * PROJ_LANES + 127) / 128, nPairs), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
     const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
     k_proj_resolve<<<nPairs, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->accBuf, dMatch, dDist, dN);
     MCK(cudaGetLastError());
@@ -1553,8 +1563,8 @@ int eaof_match_windows(eaof_matcher* m, int rule, int nT, const float* tx, const
         if (A.cut < thAccept) A.cut = thAccept;
     }
     if (!turight) A.curight = nullptr;
-    k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx);
-    k_proj_dense<<<dim3((nQ * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
+    k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx, m->cellPack);
+    k_proj_dense<<<dim3((nQ * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
     const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
     if (rule == EAOF_WIN_BEST)
         k_proj_resolve<<<1, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->accBuf, m->outMatch, m->outDist, m->outN);
@@ -1608,8 +1618,8 @@ int eaof_match_initialization(eaof_matcher* m, float nnratio, int checkOri, int 
     A.histMode = 1; A.checkBounds = 0; A.thAccept = EAOF_TH_LOW; A.ratio = nnratio;
     A.cut = near_threshold(EAOF_TH_LOW, nnratio) - 1;
     if (A.cut > 256) A.cut = 256;
-    k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx);
-    k_proj_dense<<<dim3((n1 * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf);
+    k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx, m->cellPack);
+    k_proj_dense<<<dim3((n1 * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
     k_init_resolve<<<1, 32, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->idxQ, m->idxT, m->initBin, m->outMatch, m->outN);
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(matches12, m->outMatch, sizeof(int) * n1, cudaMemcpyDeviceToHost, s));
