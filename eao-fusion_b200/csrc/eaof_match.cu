@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
 
 // phase 2: one warp per pair, Last features in index order
 __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __restrict__ cellStart,
-                                                     const int* __restrict__ cellIdx, const uint32_t* __restrict__ topBuf,
+                                                     const float4* __restrict__ cellPack, const uint32_t* __restrict__ topBuf,
                                                      uint32_t* __restrict__ accBuf, int* __restrict__ matchOut,
                                                      int* __restrict__ distOut, int* __restrict__ nMatches) {
     extern __shared__ uint32_t smem[];  // taken bitmap
@@ -760,19 +760,23 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
     // ruled out; a fixed point of this is exactly the sequential result.
     const unsigned below = (1u << lane) - 1;
     int nAcc = 0;
+    // the lists of the next 32 queries are fetched while the current 32 are being resolved
+    uint4 nw0 = make_uint4(~0u, ~0u, ~0u, ~0u), nw1 = make_uint4(~0u, ~0u, 0u, 0u);
+    int nObs = 1;
+    auto fetch = [&](int q) {
+        nw0 = make_uint4(~0u, ~0u, ~0u, ~0u); nw1 = make_uint4(~0u, ~0u, 0u, 0u); nObs = 1;
+        if (q < nL) {
+            const uint4* p = reinterpret_cast<const uint4*>(topBuf + (po + q) * 8);
+            nw0 = p[0]; nw1 = p[1];
+            if (A.lobs) nObs = A.lobs[po + q] != 0;
+        }
+    };
+    fetch(lane);
     for (int i0 = 0; i0 < nL; i0 += 32) {
         const int mine = i0 + lane;
-        uint32_t e[TOP_K];
-#pragma unroll
-        for (int k = 0; k < TOP_K; ++k) e[k] = 0xffffffffu;
-        int myCnt = 0, myObs = 1;
-        if (mine < nL) {
-            const uint4* p = reinterpret_cast<const uint4*>(topBuf + (po + mine) * 8);
-            const uint4 w0 = p[0], w1 = p[1];
-            e[0] = w0.x; e[1] = w0.y; e[2] = w0.z; e[3] = w0.w; e[4] = w1.x; e[5] = w1.y;
-            myCnt = (int)w1.w;
-            if (A.lobs) myObs = A.lobs[po + mine] != 0;
-        }
+        const uint32_t e[TOP_K] = {nw0.x, nw0.y, nw0.z, nw0.w, nw1.x, nw1.y};
+        const int myCnt = mine < nL ? (int)nw1.w : 0, myObs = nObs;
+        fetch(mine + 32);
         bool pending = myCnt > 0;
         int next = 0;  // entries before `next` are known to be taken
         while (__ballot_sync(0xffffffffu, pending)) {
@@ -815,31 +819,63 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
             __syncwarp();
             const unsigned scanMask = __ballot_sync(0xffffffffu, pending && needScan);
             if (c < 32 && ((scanMask >> c) & 1u)) {
-                // lane c is now the lowest undecided query and the bitmap is final for it: exact sequential re-scan
-                int bestDist = 256, bestIdx = -1;
-                if (lane == c) {
-                    const int i = mine;
-                    float u, v, r, ur;
-                    int minLevel, maxLevel;
-                    query_window(A, po, i, u, v, r, minLevel, maxLevel, ur);
-                    uint32_t qd[8];
+                // lane c's query is now the lowest undecided one and the bitmap is final for it: exact re-scan of its window,
+                // the whole warp sharing the candidate runs; the winner is the smallest (distance, arrival ordinal)
+                const int i = i0 + c;
+                float u, v, r, ur;
+                int minLevel, maxLevel;
+                query_window(A, po, i, u, v, r, minLevel, maxLevel, ur);
+                uint32_t qd[8];
+                {
                     const uint4* p = reinterpret_cast<const uint4*>(A.desc + 32 * ((size_t)A.lRow[pair] + i));
                     const uint4 a = p[0], b = p[1];
                     qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
-                    const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
-                    const float* cur = A.curight ? A.curight + po : nullptr;
-                    for_each_candidate(A, cellStart + (size_t)pair * (GRID_CELLS + 1), cellIdx + po, A.cx + po, A.cy + po,
-                                       A.coct + po, u, v, r, minLevel, maxLevel, [&](int k) {
-                        if ((smem[k >> 5] >> (k & 31)) & 1u) return;
-                        if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) return;
-                        uint32_t td[8];
-                        const uint4* pp = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
-                        const uint4 a2 = pp[0], b2 = pp[1];
-                        td[0] = a2.x; td[1] = a2.y; td[2] = a2.z; td[3] = a2.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
-                        const int d = hamming256(qd, td);
-                        if (d < bestDist) { bestDist = d; bestIdx = k; }
-                    });
-                    if (bestDist > A.thAccept) bestIdx = -1;  // :1428 / :1558
+                }
+                const uint8_t* cd = A.desc + 32 * (size_t)A.cRow[pair];
+                const float* cur = A.curight ? A.curight + po : nullptr;
+                const int* cs = cellStart + (size_t)pair * (GRID_CELLS + 1);
+                const float4* pk = cellPack + po;
+                const int nMinCellX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(u, A.minX), r), A.invW)));
+                const int nMaxCellX = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(u, A.minX), r), A.invW)));
+                const int nMinCellY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(v, A.minY), r), A.invH)));
+                const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, A.minY), r), A.invH)));
+                const bool any = !(nMinCellX >= GRID_COLS || nMaxCellX < 0 || nMinCellY >= GRID_ROWS || nMaxCellY < 0);
+                const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+                unsigned long long bestKey = ~0ull;  // dist << 40 | ordinal << 16 | candidate index
+                int ord = 0;
+                if (any)
+                    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
+                        const int b = cs[ix * GRID_ROWS + nMinCellY], e = cs[ix * GRID_ROWS + nMaxCellY + 1];
+                        for (int jj = b + lane; jj < e; jj += 32) {
+                            const float4 ent = __ldg(pk + jj);
+                            const int k = __float_as_int(ent.w);
+                            if (bCheckLevels) {
+                                const int o = __float_as_int(ent.z);
+                                if (o < minLevel) continue;
+                                if (maxLevel >= 0 && o > maxLevel) continue;
+                            }
+                            const float dx = __fsub_rn(ent.x, u), dy = __fsub_rn(ent.y, v);
+                            if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
+                            if ((smem[k >> 5] >> (k & 31)) & 1u) continue;
+                            if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) continue;
+                            uint32_t td[8];
+                            const uint4* pp = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
+                            const uint4 a2 = pp[0], b2 = pp[1];
+                            td[0] = a2.x; td[1] = a2.y; td[2] = a2.z; td[3] = a2.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
+                            const unsigned long long key = ((unsigned long long)hamming256(qd, td) << 40) |
+                                                           ((unsigned long long)(ord + (jj - b)) << 16) | (unsigned long long)k;
+                            bestKey = key < bestKey ? key : bestKey;
+                        }
+                        ord += e - b;
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, bestKey, o);
+                    bestKey = other < bestKey ? other : bestKey;
+                }
+                int bestDist = bestKey == ~0ull ? 256 : (int)(bestKey >> 40), bestIdx = bestKey == ~0ull ? -1 : (int)(bestKey & 0xffff);
+                if (bestDist > A.thAccept) bestIdx = -1;  // :1428 / :1558
+                if (lane == c) {
                     if (bestIdx >= 0) {
                         mOut[bestIdx] = i;
                         if (dOut) dOut[bestIdx] = bestDist;
@@ -848,7 +884,7 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
                     }
                     pending = false;
                 }
-                nAcc += __popc(__ballot_sync(0xffffffffu, lane == c && bestIdx >= 0));
+                nAcc += bestIdx >= 0 ? 1 : 0;
                 __syncwarp();
             }
         }
@@ -1459,7 +1495,7 @@ static int run_projection(eaof_matcher* m, ProjArgs& A, int nPairs, int maxL, in
     k_build_grid<<<nPairs, 256, 0, s>>>(A, m->cellStart, m->cellIdx, m->cellPack);
     k_proj_dense<<<dim3((maxL * PROJ_LANES + 127) / 128, nPairs), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
     const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
-    k_proj_resolve<<<nPairs, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->accBuf, dMatch, dDist, dN);
+    k_proj_resolve<<<nPairs, 32, bm, s>>>(A, m->cellStart, m->cellPack, m->nearBuf, m->accBuf, dMatch, dDist, dN);
     MCK(cudaGetLastError());
     return EAOF_OK;
 }
@@ -1567,7 +1603,7 @@ int eaof_match_windows(eaof_matcher* m, int rule, int nT, const float* tx, const
     k_proj_dense<<<dim3((nQ * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
     const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
     if (rule == EAOF_WIN_BEST)
-        k_proj_resolve<<<1, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->accBuf, m->outMatch, m->outDist, m->outN);
+        k_proj_resolve<<<1, 32, bm, s>>>(A, m->cellStart, m->cellPack, m->nearBuf, m->accBuf, m->outMatch, m->outDist, m->outN);
     else
         k_win_resolve_ratio<<<1, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->outMatch, m->outDist, m->outN);
     MCK(cudaGetLastError());
