@@ -843,55 +843,61 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const uint8_t* __restrict
     const int rc = tt / nCW, cwd = tt - rc * nCW;
     const int x = 4 * cwd, y0 = rc * BLUR_ROWS;
     const bool cv4 = g.blurMode == 1;
-    const int k0 = 18, k1 = 34, k2 = cv4 ? 48 : 49, k3 = cv4 ? 56 : 55;
+    const unsigned k0 = 18, k1 = 34, k2 = cv4 ? 48 : 49, k3 = cv4 ? 56 : 55;
+    // taps as byte vectors for the integer dot-product instructions
+    const unsigned TL = k0 | (k1 << 8) | (k2 << 16) | (k3 << 24);  // pixels x-3 .. x
+    const unsigned TR = k2 | (k1 << 8) | (k0 << 16);                // pixels x+1 .. x+3
+    const unsigned TV = k2 | (k1 << 8);                              // rows y+1, y+2 (TL's halves serve rows y-3..y)
     const int simdW = g.blurMode == 2 ? (L.w & ~3) : 0;
     const bool halfEven = x < simdW;  // simdW is a multiple of 4, so the whole word rounds the same way
     const size_t lvl = (size_t)f * g.pyrFrameBytes + L.off;
     const uint8_t* in = pyr + lvl + EAOF_INNER_X0 + x;         // word-aligned
     uint8_t* out = blur + lvl + (size_t)EAOF_EDGE * L.pitch + EAOF_INNER_X0 + x;
 
-    int h0[7], h1[7], h2[7], h3[7];  // horizontally filtered rows y-3 .. y+3 of pixels x .. x+3
+    // Horizontal pass: 7 taps of one pixel = two DP4A over byte groups picked by PRMT (sum <= 255*257 fits 16 bits).
+    // Vertical pass: the horizontally filtered values of vertically adjacent rows are kept as 16x2 pairs
+    // pr[r] = (h[r-1], h[r]); an output row is three DP2A over the pairs created 5, 3 and 1 rows ago plus k0 times the
+    // newest value (25 bits).
+    unsigned prA[4] = {0, 0, 0, 0}, prB[4] = {0, 0, 0, 0}, prC[4] = {0, 0, 0, 0}, prD[4] = {0, 0, 0, 0}, prE[4] = {0, 0, 0, 0};
+    unsigned hPrev[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int r = 0; r < BLUR_ROWS + 6; ++r) {
         const int by = min(y0 + r - 3 + EAOF_EDGE, L.rows - 1);
         const uint32_t* p = reinterpret_cast<const uint32_t*>(in + (size_t)by * L.pitch);
         const unsigned Wm = __ldg(p - 1), W0 = __ldg(p), Wp = __ldg(p + 1);
-        // E[i] = pixels (x-3+i, x-1+i) on 16x2 lanes; the odd-pixel pair of offset i is the even pair of offset i+1
-        unsigned E[8];
-        E[0] = evn(__byte_perm(Wm, W0, 0x4321));
-        E[1] = evn(__byte_perm(Wm, W0, 0x5432));
-        E[2] = evn(__byte_perm(Wm, W0, 0x6543));
-        E[3] = evn(W0);
-        E[4] = evn(__byte_perm(W0, Wp, 0x4321));
-        E[5] = evn(__byte_perm(W0, Wp, 0x5432));
-        E[6] = evn(__byte_perm(W0, Wp, 0x6543));
-        E[7] = evn(Wp);
-        const unsigned sE = k0 * (E[0] + E[6]) + k1 * (E[1] + E[5]) + k2 * (E[2] + E[4]) + k3 * E[3];  // pixels x, x+2
-        const unsigned sO = k0 * (E[1] + E[7]) + k1 * (E[2] + E[6]) + k2 * (E[3] + E[5]) + k3 * E[4];  // pixels x+1, x+3
+        unsigned h[4];
+        h[0] = __dp4a(__byte_perm(Wm, W0, 0x4321), TL, __dp4a(__byte_perm(W0, Wp, 0x4321), TR, 0u));
+        h[1] = __dp4a(__byte_perm(Wm, W0, 0x5432), TL, __dp4a(__byte_perm(W0, Wp, 0x5432), TR, 0u));
+        h[2] = __dp4a(__byte_perm(Wm, W0, 0x6543), TL, __dp4a(__byte_perm(W0, Wp, 0x6543), TR, 0u));
+        h[3] = __dp4a(W0, TL, __dp4a(Wp, TR, 0u));
+        // pairs created at rows r-5 (prA) .. r-1 (prE); shift the history and append (h[r-1], h[r])
+        unsigned a[4];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { h0[i] = h0[i + 1]; h1[i] = h1[i + 1]; h2[i] = h2[i + 1]; h3[i] = h3[i + 1]; }
-        h0[6] = (int)(sE & 0xffffu); h2[6] = (int)(sE >> 16);
-        h1[6] = (int)(sO & 0xffffu); h3[6] = (int)(sO >> 16);
+        for (int j = 0; j < 4; ++j) {
+            const unsigned prNew = hPrev[j] | (h[j] << 16);
+            // window rows r-6..r: (r-6, r-5) = prA, (r-4, r-3) = prC, (r-2, r-1) = prE, single r
+            a[j] = __dp2a_lo(prA[j], TL, __dp2a_hi(prC[j], TL, __dp2a_lo(prE[j], TV, k0 * h[j])));
+            prA[j] = prB[j]; prB[j] = prC[j]; prC[j] = prD[j]; prD[j] = prE[j]; prE[j] = prNew;
+            hPrev[j] = h[j];
+        }
         if (r >= 6) {
             const int y = y0 + r - 6;
             if (y < L.h) {
-                int a[4];
-                a[0] = k0 * (h0[0] + h0[6]) + k1 * (h0[1] + h0[5]) + k2 * (h0[2] + h0[4]) + k3 * h0[3];
-                a[1] = k0 * (h1[0] + h1[6]) + k1 * (h1[1] + h1[5]) + k2 * (h1[2] + h1[4]) + k3 * h1[3];
-                a[2] = k0 * (h2[0] + h2[6]) + k1 * (h2[1] + h2[5]) + k2 * (h2[2] + h2[4]) + k3 * h2[3];
-                a[3] = k0 * (h3[0] + h3[6]) + k1 * (h3[1] + h3[5]) + k2 * (h3[2] + h3[4]) + k3 * h3[3];
-                uint32_t v = 0;
+                uint32_t v;
+                if (halfEven) {
+                    v = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int o;
-                    if (halfEven) {
-                        o = a[j] >> 16;
-                        const int rem = a[j] & 0xffff;
+                    for (int j = 0; j < 4; ++j) {
+                        int o = (int)(a[j] >> 16);
+                        const int rem = (int)(a[j] & 0xffff);
                         o += (rem > 32768) || (rem == 32768 && (o & 1));
-                    } else {
-                        o = (a[j] + 32768) >> 16;
+                        v |= (uint32_t)min(o, 255) << (8 * j);
                     }
-                    v |= (uint32_t)min(o, 255) << (8 * j);
+                } else {
+                    // (a + 2^15) >> 16 saturated to 255 = byte 2 of min(a + 2^15, 0xffffff)
+                    const unsigned b0 = min(a[0] + 32768u, 0xffffffu), b1 = min(a[1] + 32768u, 0xffffffu);
+                    const unsigned b2 = min(a[2] + 32768u, 0xffffffu), b3 = min(a[3] + 32768u, 0xffffffu);
+                    v = __byte_perm(__byte_perm(b0, b1, 0x0062), __byte_perm(b2, b3, 0x0062), 0x5410);
                 }
                 // the padded row always has room for a full word (pitch >= w + 64)
                 *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch) = v;
