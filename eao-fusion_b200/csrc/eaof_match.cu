@@ -500,6 +500,7 @@ struct ProjArgs {
     int histMode;      // 0: no rotation check, 1: factor 1/HISTO_LENGTH, 2: factor HISTO_LENGTH/360
     int checkBounds;   // skip queries projected outside [minX,maxX]x[minY,maxY]
     float ratio;       // rule EAOF_WIN_RATIO_SAME_LEVEL
+    float invSigma2[EAOF_MAX_LEVELS];  // gate EAOF_GATE_FUSE_CHI2: mvInvLevelSigma2 of the target keyframe
 };
 
 // window of query i of pair `pair`; false when the query is skipped before the search
@@ -628,7 +629,11 @@ __device__ __forceinline__ void level_window(int searchMode, int oct, int& minLe
 // position / descriptor loads of different candidates are in flight together; every lane keeps its TOP_K best
 // (distance, then ordinal), and the lanes' sorted lists are merged by PROJ_LANES-way selection.  Output per query: the
 // TOP_K best candidates by (dist asc, arrival asc) + the number of candidates with dist <= cut.
+// GATE selects the per-candidate test between the window test and the distance: 0 = the stereo gate of the Frame
+// searches (src/ORBmatcher.cc:1409-1415, :93-98), 1 = the reprojection chi-square of Fuse(KeyFrame*, vpMapPoints, th)
+// (:901-929).
 #define PROJ_LANES 4
+template <int GATE>
 __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __restrict__ cellStart,
                                                     const float4* __restrict__ cellPack, uint32_t* __restrict__ topBuf) {
     const int pair = blockIdx.y;
@@ -677,7 +682,18 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
                         }
                         const float dx = __fsub_rn(ent.x, u), dy = __fsub_rn(ent.y, v);
                         if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
-                        if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) continue;  // :1409-1415
+                        if (GATE == 0) {
+                            if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) continue;  // :1409-1415
+                        } else {
+                            const float kr = cur ? cur[k] : -1.f, inv = A.invSigma2[__float_as_int(ent.z)];
+                            const float ex = __fsub_rn(u, ent.x), ey = __fsub_rn(v, ent.y);
+                            float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                            if (kr >= 0) {  // :901-914
+                                const float er = __fsub_rn(ur, kr);
+                                e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                                if ((double)__fmul_rn(e2, inv) > 7.8) continue;
+                            } else if ((double)__fmul_rn(e2, inv) > 5.99) continue;  // :915-925
+                        }
                         uint32_t td[8];
                         const uint4* p = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
                         const uint4 a = p[0], b2 = p[1];
@@ -727,6 +743,87 @@ __global__ void __launch_bounds__(128) k_proj_dense(ProjArgs A, const int* __res
         uint32_t* o = topBuf + (po + i) * 8;
         reinterpret_cast<uint4*>(o)[0] = make_uint4(out[0], out[1], out[2], out[3]);
         reinterpret_cast<uint4*>(o)[1] = make_uint4(out[4], out[5], 0, ok ? (uint32_t)count : 0xffffffffu);
+    }
+}
+
+// Independent window queries (Fuse x2, SearchBySim3: no "already matched" exclusion inside the loop, so the result of a
+// query is the head of its phase-1 list): thread = query.
+__global__ void __launch_bounds__(128) k_win_pick(int nQ, int thAccept, const uint32_t* __restrict__ topBuf,
+                                                  int* __restrict__ matchQ, int* __restrict__ distQ, int* __restrict__ nMatches) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nQ) return;
+    const uint32_t head = topBuf[(size_t)i * 8], cnt = topBuf[(size_t)i * 8 + 7];
+    const bool hit = cnt != 0xffffffffu && head != 0xffffffffu && (int)(head >> 16) <= thAccept;
+    matchQ[i] = hit ? (int)(head & 0xffffu) : -1;
+    distQ[i] = hit ? (int)(head >> 16) : -1;
+    const unsigned b = __ballot_sync(__activemask(), hit);
+    if (hit && (threadIdx.x & 31) == __ffs(b) - 1) atomicAdd(nMatches, __popc(b));
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307), batched: CTA = map point, warp = one row of its
+// N x N distance matrix at a time.  The row median (element int(0.5*(N-1)) of the sorted row) is read off a 257-bin
+// histogram of the row's distances instead of sorting; rows compete by (median, row index), so the first row with the
+// smallest median wins as in :293-297.
+__global__ void __launch_bounds__(128) k_distinctive(const int* __restrict__ start, const uint8_t* __restrict__ desc,
+                                                     int* __restrict__ bestOut, int* __restrict__ medOut) {
+    __shared__ int hist[4][288];
+    __shared__ unsigned long long warpBest[4];
+    const int p = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = start[p], n = start[p + 1] - s;
+    if (n <= 0) {
+        if (threadIdx.x == 0) { bestOut[p] = -1; medOut[p] = -1; }
+        return;
+    }
+    const int k = (n - 1) >> 1;
+    const uint8_t* D = desc + 32 * (size_t)s;
+    unsigned long long best = ~0ull;
+    for (int row = w; row < n; row += 4) {
+#pragma unroll
+        for (int b = 0; b < 9; ++b) hist[w][lane * 9 + b] = 0;
+        __syncwarp();
+        uint32_t qd[8];
+        {
+            const uint4* q = reinterpret_cast<const uint4*>(D + 32 * (size_t)row);
+            const uint4 a = q[0], b = q[1];
+            qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+        }
+        for (int j = lane; j < n; j += 32) {
+            uint32_t td[8];
+            const uint4* t = reinterpret_cast<const uint4*>(D + 32 * (size_t)j);
+            const uint4 a = t[0], b = t[1];
+            td[0] = a.x; td[1] = a.y; td[2] = a.z; td[3] = a.w; td[4] = b.x; td[5] = b.y; td[6] = b.z; td[7] = b.w;
+            atomicAdd(&hist[w][hamming256_csa(qd, td)], 1);
+        }
+        __syncwarp();
+        int bins[9], sum = 0;
+#pragma unroll
+        for (int b = 0; b < 9; ++b) { bins[b] = hist[w][lane * 9 + b]; sum += bins[b]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int owner = __ffs(__ballot_sync(0xffffffffu, incl > k)) - 1;  // some lane always qualifies: total = n > k
+        int med = 0;
+        if (lane == owner) {
+            int c = incl - sum;
+            bool found = false;
+#pragma unroll
+            for (int b = 0; b < 9; ++b) {
+                c += bins[b];
+                if (!found && c > k) { med = lane * 9 + b; found = true; }
+            }
+        }
+        med = __shfl_sync(0xffffffffu, med, owner);
+        const unsigned long long key = ((unsigned long long)med << 32) | (unsigned)row;
+        best = key < best ? key : best;
+        __syncwarp();
+    }
+    if (lane == 0) warpBest[w] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long b = warpBest[0];
+        for (int i = 1; i < 4; ++i) b = warpBest[i] < b ? warpBest[i] : b;
+        bestOut[p] = (int)(b & 0xffffffffu);
+        medOut[p] = (int)(b >> 32);
     }
 }
 
@@ -1493,7 +1590,7 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, i
 static int run_projection(eaof_matcher* m, ProjArgs& A, int nPairs, int maxL, int* dMatch, int* dDist, int* dN) {
     cudaStream_t s = m->stream;
     k_build_grid<<<nPairs, 256, 0, s>>>(A, m->cellStart, m->cellIdx, m->cellPack);
-    k_proj_dense<<<dim3((maxL * PROJ_LANES + 127) / 128, nPairs), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
+    k_proj_dense<0><<<dim3((maxL * PROJ_LANES + 127) / 128, nPairs), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
     const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
     k_proj_resolve<<<nPairs, 32, bm, s>>>(A, m->cellStart, m->cellPack, m->nearBuf, m->accBuf, dMatch, dDist, dN);
     MCK(cudaGetLastError());
@@ -1600,7 +1697,7 @@ int eaof_match_windows(eaof_matcher* m, int rule, int nT, const float* tx, const
     }
     if (!turight) A.curight = nullptr;
     k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx, m->cellPack);
-    k_proj_dense<<<dim3((nQ * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
+    k_proj_dense<0><<<dim3((nQ * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
     const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
     if (rule == EAOF_WIN_BEST)
         k_proj_resolve<<<1, 32, bm, s>>>(A, m->cellStart, m->cellPack, m->nearBuf, m->accBuf, m->outMatch, m->outDist, m->outN);
@@ -1611,6 +1708,94 @@ int eaof_match_windows(eaof_matcher* m, int rule, int nT, const float* tx, const
     if (distT) MCK(cudaMemcpyAsync(distT, m->outDist, sizeof(int) * nT, cudaMemcpyDeviceToHost, s));
     MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
     MCK(cudaStreamSynchronize(s));
+    return EAOF_OK;
+}
+
+int eaof_match_windows_independent(eaof_matcher* m, int gate, int nT, const float* tx, const float* ty, const int* toct,
+                                   const uint8_t* tdesc, const float* turight, float minX, float minY, float invW,
+                                   float invH, const float* invLevelSigma2, int nLevels, int nQ, const uint8_t* qValid,
+                                   const float* qU, const float* qV, const float* qRadius, const int* qMinLevel,
+                                   const int* qMaxLevel, const float* qUr, const uint8_t* qDesc, int thAccept,
+                                   int* matchQ, int* distQ, int* nMatches) {
+    if (!m || !matchQ || !nMatches || nT < 0 || nQ < 0) return mfail(EAOF_ERR_ARG, "bad argument");
+    if (gate != EAOF_GATE_NONE && gate != EAOF_GATE_FUSE_CHI2) return mfail(EAOF_ERR_ARG, "unknown gate");
+    if (nT > m->maxFeat || nQ > m->maxFeat) return mfail(EAOF_ERR_ARG, "feature count exceeds max_features=%d", m->maxFeat);
+    if (thAccept < 0 || thAccept > 256) return mfail(EAOF_ERR_ARG, "bad th_accept");
+    *nMatches = 0;
+    for (int i = 0; i < nQ; ++i) { matchQ[i] = -1; if (distQ) distQ[i] = -1; }
+    if (nT == 0 || nQ == 0) return EAOF_OK;
+    if (!tx || !ty || !toct || !tdesc || !qU || !qV || !qRadius || !qMinLevel || !qMaxLevel || !qDesc) return mfail(EAOF_ERR_ARG, "null array");
+    if (gate == EAOF_GATE_FUSE_CHI2) {
+        if (!invLevelSigma2 || !qUr || nLevels < 1 || nLevels > EAOF_MAX_LEVELS) return mfail(EAOF_ERR_ARG, "chi-square gate needs inv_level_sigma2 and q_ur");
+        for (int i = 0; i < nT; ++i) if (toct[i] < 0 || toct[i] >= nLevels) return mfail(EAOF_ERR_ARG, "t_octave[%d] out of range", i);
+    }
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+#define UP(dst, src, n, T) MCK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(n), cudaMemcpyHostToDevice, s))
+    UP(m->cx, tx, nT, float); UP(m->cy, ty, nT, float); UP(m->coct, toct, nT, int);
+    const bool useRight = gate == EAOF_GATE_FUSE_CHI2 && turight;
+    if (useRight) UP(m->curight, turight, nT, float);
+    UP(m->lu, qU, nQ, float); UP(m->lv, qV, nQ, float); UP(m->qRadius, qRadius, nQ, float);
+    UP(m->loct, qMinLevel, nQ, int); UP(m->qMaxL, qMaxLevel, nQ, int);
+    if (qUr) UP(m->linvz, qUr, nQ, float);
+    if (qValid) UP(m->lvalid, qValid, nQ, uint8_t);
+    UP(m->desc2, tdesc, 32 * (size_t)nT, uint8_t);
+    UP(m->desc2 + 32 * (size_t)m->maxFeat, qDesc, 32 * (size_t)nQ, uint8_t);
+    const int hdr[4] = {nT, nQ, 0, m->maxFeat};
+    UP(m->nC, &hdr[0], 1, int); UP(m->nL, &hdr[1], 1, int); UP(m->cRow, &hdr[2], 1, int); UP(m->lRow, &hdr[3], 1, int);
+#undef UP
+    ProjArgs A{};
+    A.cx = m->cx; A.cy = m->cy; A.coct = m->coct; A.curight = useRight ? m->curight : nullptr; A.nC = m->nC;
+    A.lu = m->lu; A.lv = m->lv; A.loct = m->loct; A.lvalid = qValid ? m->lvalid : nullptr; A.nL = m->nL;
+    A.desc = m->desc2; A.cRow = m->cRow; A.lRow = m->lRow; A.stride = m->maxFeat;
+    A.minX = minX; A.minY = minY; A.invW = invW; A.invH = invH;
+    A.qRadius = m->qRadius; A.qMinL = m->loct; A.qMaxL = m->qMaxL; A.qUr = qUr ? m->linvz : m->lu;
+    A.thAccept = thAccept; A.cut = thAccept;
+    if (gate == EAOF_GATE_FUSE_CHI2) for (int i = 0; i < nLevels; ++i) A.invSigma2[i] = invLevelSigma2[i];
+    MCK(cudaMemsetAsync(m->outN, 0, sizeof(int), s));
+    k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx, m->cellPack);
+    if (gate == EAOF_GATE_FUSE_CHI2)
+        k_proj_dense<1><<<dim3((nQ * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
+    else
+        k_proj_dense<0><<<dim3((nQ * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
+    k_win_pick<<<(nQ + 127) / 128, 128, 0, s>>>(nQ, thAccept, m->nearBuf, m->outMatch, m->outDist, m->outN);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(matchQ, m->outMatch, sizeof(int) * nQ, cudaMemcpyDeviceToHost, s));
+    if (distQ) MCK(cudaMemcpyAsync(distQ, m->outDist, sizeof(int) * nQ, cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MCK(cudaStreamSynchronize(s));
+    return EAOF_OK;
+}
+
+int eaof_distinctive_descriptors(eaof_matcher* m, int nPoints, const int* start, const uint8_t* desc, int* bestOut,
+                                 int* medianOut) {
+    if (!m || nPoints < 0 || !bestOut) return mfail(EAOF_ERR_ARG, "bad argument");
+    if (nPoints == 0) return EAOF_OK;
+    if (!start || !desc) return mfail(EAOF_ERR_ARG, "null array");
+    const int rowCap = 2 * m->maxFeat, ptCap = m->maxFeat - 1;  // staging: desc2 holds 2*maxFeat rows, idxQ maxFeat starts
+    for (int p = 0; p < nPoints; ++p) {
+        if (start[p + 1] < start[p]) return mfail(EAOF_ERR_ARG, "start[] must be non-decreasing");
+        if (start[p + 1] - start[p] > rowCap) return mfail(EAOF_ERR_ARG, "map point %d has more than %d observations", p, rowCap);
+    }
+    if (ptCap < 1) return mfail(EAOF_ERR_ARG, "matcher too small");
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    std::vector<int> rel;
+    for (int p0 = 0; p0 < nPoints;) {
+        int p1 = p0;  // largest chunk of points whose rows fit the staging buffers
+        while (p1 < nPoints && p1 - p0 < ptCap && start[p1 + 1] - start[p0] <= rowCap) ++p1;
+        const int np = p1 - p0, rows = start[p1] - start[p0];
+        rel.resize(np + 1);
+        for (int i = 0; i <= np; ++i) rel[i] = start[p0 + i] - start[p0];
+        MCK(cudaMemcpyAsync(m->idxQ, rel.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice, s));
+        if (rows) MCK(cudaMemcpyAsync(m->desc2, desc + 32 * (size_t)start[p0], 32 * (size_t)rows, cudaMemcpyHostToDevice, s));
+        k_distinctive<<<np, 128, 0, s>>>(m->idxQ, m->desc2, m->outMatch, m->outDist);
+        MCK(cudaGetLastError());
+        MCK(cudaMemcpyAsync(bestOut + p0, m->outMatch, sizeof(int) * np, cudaMemcpyDeviceToHost, s));
+        if (medianOut) MCK(cudaMemcpyAsync(medianOut + p0, m->outDist, sizeof(int) * np, cudaMemcpyDeviceToHost, s));
+        MCK(cudaStreamSynchronize(s));  // rel / staging are reused by the next chunk
+        p0 = p1;
+    }
     return EAOF_OK;
 }
 
@@ -1655,7 +1840,7 @@ int eaof_match_initialization(eaof_matcher* m, float nnratio, int checkOri, int 
     A.cut = near_threshold(EAOF_TH_LOW, nnratio) - 1;
     if (A.cut > 256) A.cut = 256;
     k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx, m->cellPack);
-    k_proj_dense<<<dim3((n1 * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
+    k_proj_dense<0><<<dim3((n1 * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
     k_init_resolve<<<1, 32, 0, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->idxQ, m->idxT, m->initBin, m->outMatch, m->outN);
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(matches12, m->outMatch, sizeof(int) * n1, cudaMemcpyDeviceToHost, s));

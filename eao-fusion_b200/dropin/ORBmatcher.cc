@@ -12,11 +12,14 @@
  *   SearchForTriangulation(...)                                          (:657-823)
  *   SearchByProjection(Frame&, const Frame&, th, bMono)                  (:1328-1472)
  *   SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, d)  (:1474-1601)
- * The map-mutating loops of the LocalMapping / LoopClosing threads (Fuse x2, SearchBySim3,
- * SearchByProjection(KeyFrame*, Scw, ...), :290-403, :825-1326) and the two helpers only they use stay in the reference's
- * ORBmatcher.cc: a maintainer deletes the definitions listed above from it and adds this file to the build
+ *   SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)          (:290-403)
+ *   Fuse(KeyFrame*, const vector<MapPoint*>&, th)                        (:825-961)
+ *   Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)                   (:963-1100)
+ *   SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)             (:1102-1326)
+ * i.e. every definition of the reference's ORBmatcher.cc: a maintainer replaces that file by this one in the build
  * (INTEGRATION.md §3).  Every method marshals the fields the reference loop reads into plain arrays, calls the
- * library, and applies the result to the host objects exactly where the reference does; projections
+ * library, and applies the result to the host objects exactly where the reference does (the map mutations of Fuse run
+ * on the host, in candidate order, with the skip tests re-read at each turn); projections
  * (Rcw*x3Dw+tcw, PredictScale, ...) stay on the host with the reference's own expressions.  There is no CPU search path:
  * a library failure throws.
  *
@@ -453,6 +456,307 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set
         if(match[k] >= 0)
             CurrentFrame.mvpMapPoints[k] = vpMPs[match[k]];
     return n;
+}
+
+namespace
+{
+
+// Candidate map points seen from a keyframe: what the map-side loops derive per point before the descriptor search
+// (:318-360, :852-887, :1001-1047, :1160-1194): projected pixel, predicted level, search radius.
+struct Projected
+{
+    vector<unsigned char> valid, desc;
+    vector<float> u, v, ur, radius;
+    vector<int> minL, maxL;
+    explicit Projected(size_t n) : valid(n, 0), desc(32 * (n ? n : 1)), u(n, 0.f), v(n, 0.f), ur(n, 0.f), radius(n, 0.f), minL(n, 0), maxL(n, 0) {}
+    void Set(size_t i, float u_, float v_, float ur_, float r, int level, MapPoint* pMP)
+    {
+        valid[i] = 1;
+        u[i] = u_;
+        v[i] = v_;
+        ur[i] = ur_;
+        radius[i] = r;
+        minL[i] = level - 1;
+        maxL[i] = level;
+        const cv::Mat d = pMP->GetDescriptor();
+        memcpy(&desc[32 * i], d.ptr<unsigned char>(), 32);
+    }
+};
+
+// Points given in the world frame, keyframe pose (Rcw, tcw, Ow): shared by SearchByProjection(KF,Scw), Fuse and Fuse(Scw)
+bool ProjectWorld(KeyFrame* pKF, MapPoint* pMP, const cv::Mat& Rcw, const cv::Mat& tcw, const cv::Mat& Ow, float th, float bf,
+                  float& u, float& v, float& ur, float& radius, int& level)
+{
+    cv::Mat p3Dw = pMP->GetWorldPos();
+    cv::Mat p3Dc = Rcw*p3Dw+tcw;
+    if(p3Dc.at<float>(2)<0.0f)
+        return false;
+    const float invz = 1/p3Dc.at<float>(2);
+    const float x = p3Dc.at<float>(0)*invz;
+    const float y = p3Dc.at<float>(1)*invz;
+    u = pKF->fx*x+pKF->cx;
+    v = pKF->fy*y+pKF->cy;
+    if(!pKF->IsInImage(u,v))
+        return false;
+    ur = u-bf*invz;
+    const float maxDistance = pMP->GetMaxDistanceInvariance();
+    const float minDistance = pMP->GetMinDistanceInvariance();
+    cv::Mat PO = p3Dw-Ow;
+    const float dist3D = cv::norm(PO);
+    if(dist3D<minDistance || dist3D>maxDistance)
+        return false;
+    cv::Mat Pn = pMP->GetNormal();
+    if(PO.dot(Pn)<0.5*dist3D)
+        return false;
+    level = pMP->PredictScale(dist3D,pKF->mfLogScaleFactor);
+    radius = th*pKF->mvScaleFactors[level];
+    return true;
+}
+
+struct KeyFrameArrays
+{
+    KeyArrays keys;
+    vector<unsigned char> desc;
+    explicit KeyFrameArrays(KeyFrame* pKF) : keys(pKF->mvKeysUn), desc(Rows(pKF->mDescriptors, pKF->mvKeysUn.size())) {}
+};
+
+// best keyframe feature per projected point, no exclusion between points
+void SearchIndependent(KeyFrame* pKF, const Projected& q, int gate, int thAccept, vector<int>& match)
+{
+    const size_t nT = pKF->mvKeysUn.size(), nQ = q.valid.size();
+    match.assign(nQ, -1);
+    if(nT == 0 || nQ == 0)
+        return;
+    KeyFrameArrays t(pKF);
+    int n = 0;
+    const bool chi2 = gate == EAOF_GATE_FUSE_CHI2;
+    if(eaof_match_windows_independent(Matcher(max(nT, nQ)), gate, (int)nT, P(t.keys.x), P(t.keys.y), P(t.keys.octave), P(t.desc),
+                                      chi2 ? P(pKF->mvuRight) : NULL, pKF->mnMinX, pKF->mnMinY, pKF->mfGridElementWidthInv,
+                                      pKF->mfGridElementHeightInv, chi2 ? P(pKF->mvInvLevelSigma2) : NULL,
+                                      (int)pKF->mvScaleFactors.size(), (int)nQ, P(q.valid), P(q.u), P(q.v), P(q.radius), P(q.minL),
+                                      P(q.maxL), P(q.ur), P(q.desc), thAccept, P(match), NULL, &n) != EAOF_OK)
+        Throw("eaof_match_windows_independent");
+}
+
+void DecomposeSim3(const cv::Mat& Scw, cv::Mat& Rcw, cv::Mat& tcw, cv::Mat& Ow)
+{
+    cv::Mat sRcw = Scw.rowRange(0,3).colRange(0,3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    Rcw = sRcw/scw;
+    tcw = Scw.rowRange(0,3).col(3)/scw;
+    Ow = -Rcw.t()*tcw;
+}
+
+}  // namespace
+
+int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th)
+{
+    cv::Mat Rcw, tcw, Ow;
+    DecomposeSim3(Scw, Rcw, tcw, Ow);
+    set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(NULL));
+
+    const size_t nQ = vpPoints.size(), nT = pKF->mvKeysUn.size();
+    if(nQ == 0 || nT == 0)
+        return 0;
+    Projected q(nQ);
+    for(size_t i = 0; i < nQ; i++)
+    {
+        MapPoint* pMP = vpPoints[i];
+        if(pMP->isBad() || spAlreadyFound.count(pMP))
+            continue;
+        float u, v, ur, radius;
+        int level;
+        if(ProjectWorld(pKF, pMP, Rcw, tcw, Ow, th, 0.f, u, v, ur, radius, level))
+            q.Set(i, u, v, ur, radius, level, pMP);
+    }
+    KeyFrameArrays t(pKF);
+    vector<unsigned char> taken(nT, 0);
+    for(size_t k = 0; k < nT; k++)
+        taken[k] = vpMatched[k] != NULL;
+    vector<int> match(nT, -1);
+    int n = 0;
+    // a matched feature is closed for the later points (:375-376, :396): the greedy window search
+    if(eaof_match_windows(Matcher(max(nT, nQ)), EAOF_WIN_BEST, (int)nT, P(t.keys.x), P(t.keys.y), P(t.keys.octave), NULL, P(t.desc),
+                          NULL, P(taken), pKF->mnMinX, pKF->mnMaxX, pKF->mnMinY, pKF->mnMaxY, pKF->mfGridElementWidthInv,
+                          pKF->mfGridElementHeightInv, (int)nQ, P(q.valid), P(q.u), P(q.v), P(q.radius), P(q.minL), P(q.maxL), NULL,
+                          NULL, P(q.desc), NULL, TH_LOW, mfNNratio, 0, 0, P(match), NULL, &n) != EAOF_OK)
+        Throw("eaof_match_windows");
+    for(size_t k = 0; k < nT; k++)
+        if(match[k] >= 0)
+            vpMatched[k] = vpPoints[match[k]];
+    return n;
+}
+
+int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th)
+{
+    cv::Mat Rcw = pKF->GetRotation();
+    cv::Mat tcw = pKF->GetTranslation();
+    cv::Mat Ow = pKF->GetCameraCenter();
+
+    const size_t nQ = vpMapPoints.size();
+    Projected q(nQ);
+    for(size_t i = 0; i < nQ; i++)
+    {
+        MapPoint* pMP = vpMapPoints[i];
+        if(!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF))  // neither state is ever left again
+            continue;
+        float u, v, ur, radius;
+        int level;
+        if(ProjectWorld(pKF, pMP, Rcw, tcw, Ow, th, pKF->mbf, u, v, ur, radius, level))
+            q.Set(i, u, v, ur, radius, level, pMP);
+    }
+    vector<int> match;
+    SearchIndependent(pKF, q, EAOF_GATE_FUSE_CHI2, TH_LOW, match);
+
+    // the reference's bookkeeping, in candidate order; isBad / IsInKeyFrame change while the loop runs (:846-849)
+    int nFused = 0;
+    for(size_t i = 0; i < nQ; i++)
+    {
+        MapPoint* pMP = vpMapPoints[i];
+        if(!pMP || match[i] < 0)
+            continue;
+        if(pMP->isBad() || pMP->IsInKeyFrame(pKF))
+            continue;
+        const int bestIdx = match[i];
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+        if(!pMPinKF)
+        {
+            pMP->AddObservation(pKF,bestIdx);
+            pKF->AddMapPoint(pMP,bestIdx);
+        }
+        else if(!pMPinKF->isBad())
+        {
+            if(pMPinKF->Observations()>pMP->Observations())
+                pMP->Replace(pMPinKF);
+            else
+                pMPinKF->Replace(pMP);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint)
+{
+    cv::Mat Rcw, tcw, Ow;
+    DecomposeSim3(Scw, Rcw, tcw, Ow);
+    const set<MapPoint*> spAlreadyFound = pKF->GetMapPoints();
+
+    const size_t nQ = vpPoints.size();
+    Projected q(nQ);
+    for(size_t i = 0; i < nQ; i++)
+    {
+        MapPoint* pMP = vpPoints[i];
+        if(pMP->isBad() || spAlreadyFound.count(pMP))
+            continue;
+        float u, v, ur, radius;
+        int level;
+        if(ProjectWorld(pKF, pMP, Rcw, tcw, Ow, th, 0.f, u, v, ur, radius, level))
+            q.Set(i, u, v, ur, radius, level, pMP);
+    }
+    vector<int> match;
+    SearchIndependent(pKF, q, EAOF_GATE_NONE, TH_LOW, match);
+
+    int nFused = 0;
+    for(size_t i = 0; i < nQ; i++)
+    {
+        if(match[i] < 0)
+            continue;
+        MapPoint* pMP = vpPoints[i];
+        const int bestIdx = match[i];
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+        if(!pMPinKF)
+        {
+            pMP->AddObservation(pKF,bestIdx);
+            pKF->AddMapPoint(pMP,bestIdx);
+        }
+        else if(!pMPinKF->isBad())
+            vpReplacePoint[i] = pMPinKF;
+        nFused++;
+    }
+    return nFused;
+}
+
+int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                             const cv::Mat& t12, const float th)
+{
+    cv::Mat R1w = pKF1->GetRotation();
+    cv::Mat t1w = pKF1->GetTranslation();
+    cv::Mat R2w = pKF2->GetRotation();
+    cv::Mat t2w = pKF2->GetTranslation();
+    cv::Mat sR12 = s12*R12;
+    cv::Mat sR21 = (1.0/s12)*R12.t();
+    cv::Mat t21 = -sR21*t12;
+
+    const vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const vector<MapPoint*> vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N1 = vpMapPoints1.size(), N2 = vpMapPoints2.size();
+    vector<bool> vbAlreadyMatched1(N1,false), vbAlreadyMatched2(N2,false);
+    for(int i = 0; i < N1; i++)
+    {
+        MapPoint* pMP = vpMatches12[i];
+        if(!pMP)
+            continue;
+        vbAlreadyMatched1[i] = true;
+        const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+        if(idx2>=0 && idx2<N2)
+            vbAlreadyMatched2[idx2] = true;
+    }
+
+    // one direction: the points of keyframe A moved into keyframe B's camera and searched among B's features
+    struct Dir
+    {
+        static void Run(const vector<MapPoint*>& vpA, const vector<bool>& vbDoneA, const cv::Mat& RAw, const cv::Mat& tAw,
+                        const cv::Mat& sRBA, const cv::Mat& tBA, KeyFrame* pKFB, float fx, float fy, float cx, float cy, float th,
+                        vector<int>& vnMatch)
+        {
+            const size_t n = vpA.size();
+            Projected q(n);
+            for(size_t i = 0; i < n; i++)
+            {
+                MapPoint* pMP = vpA[i];
+                if(!pMP || vbDoneA[i] || pMP->isBad())
+                    continue;
+                cv::Mat p3Dw = pMP->GetWorldPos();
+                cv::Mat p3DcA = RAw*p3Dw + tAw;
+                cv::Mat p3DcB = sRBA*p3DcA + tBA;
+                if(p3DcB.at<float>(2)<0.0)
+                    continue;
+                const float invz = 1.0/p3DcB.at<float>(2);
+                const float x = p3DcB.at<float>(0)*invz;
+                const float y = p3DcB.at<float>(1)*invz;
+                const float u = fx*x+cx;
+                const float v = fy*y+cy;
+                if(!pKFB->IsInImage(u,v))
+                    continue;
+                const float maxDistance = pMP->GetMaxDistanceInvariance();
+                const float minDistance = pMP->GetMinDistanceInvariance();
+                const float dist3D = cv::norm(p3DcB);
+                if(dist3D<minDistance || dist3D>maxDistance)
+                    continue;
+                const int level = pMP->PredictScale(dist3D,pKFB->mfLogScaleFactor);
+                q.Set(i, u, v, 0.f, th*pKFB->mvScaleFactors[level], level, pMP);
+            }
+            SearchIndependent(pKFB, q, EAOF_GATE_NONE, TH_HIGH, vnMatch);
+        }
+    };
+    // both directions project with pKF1's intrinsics, as the reference does (:1105-1108)
+    vector<int> vnMatch1, vnMatch2;
+    Dir::Run(vpMapPoints1, vbAlreadyMatched1, R1w, t1w, sR21, t21, pKF2, pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy, th, vnMatch1);
+    Dir::Run(vpMapPoints2, vbAlreadyMatched2, R2w, t2w, sR12, t12, pKF1, pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy, th, vnMatch2);
+
+    int nFound = 0;
+    for(int i1 = 0; i1 < N1; i1++)
+    {
+        const int idx2 = vnMatch1[i1];
+        if(idx2 >= 0 && vnMatch2[idx2] == i1)
+        {
+            vpMatches12[i1] = vpMapPoints2[idx2];
+            nFound++;
+        }
+    }
+    return nFound;
 }
 
 } //namespace ORB_SLAM

@@ -262,6 +262,9 @@ def _mlib():
                                                                                                C.POINTER(ci)])
         L.eaof_match_initialization.argtypes = [vp, cf, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci,
                                                 vp, C.POINTER(ci)]
+        L.eaof_match_windows_independent.argtypes = ([vp, ci, ci] + [vp] * 5 + [cf] * 4 + [vp, ci, ci] + [vp] * 8 +
+                                                     [ci, vp, vp, C.POINTER(ci)])
+        L.eaof_distinctive_descriptors.argtypes = [vp, ci, vp, vp, vp, vp]
         L.eaof_matcher_last_distance_count.restype = C.c_longlong
         L.eaof_matcher_last_distance_count.argtypes = [vp]
         _mlib_ready = True
@@ -425,6 +428,36 @@ class ORBmatcher:
         F.pop("uright", None)
         return self.SearchWindows(0, F, q, orb_dist, 1 if self.mbCheckOrientation else 0, True, bounds=bounds,
                                   grid_inv=grid_inv)
+
+    def SearchWindowsIndependent(self, gate, KF, q, th_accept, *, bounds, grid_inv, inv_level_sigma2=None):
+        """eaof_match_windows_independent: the search step of Fuse x2 / SearchBySim3 (src/ORBmatcher.cc:825-1326).
+        KF: dict(x,y,octave,desc[,uright]); q: dict(u,v,radius,min_level,max_level,desc[,valid,ur]).
+        Returns (naccepted, match_q, dist_q)."""
+        tx, ty, to = _arr(KF["x"], np.float32), _arr(KF["y"], np.float32), _arr(KF["octave"], np.int32)
+        td, tr = _arr(KF["desc"], np.uint8), _arr(KF.get("uright"), np.float32)
+        qu, qv, qr = _arr(q["u"], np.float32), _arr(q["v"], np.float32), _arr(q["radius"], np.float32)
+        ql0, ql1 = _arr(q["min_level"], np.int32), _arr(q["max_level"], np.int32)
+        qval, qur, qd = _arr(q.get("valid"), np.uint8), _arr(q.get("ur"), np.float32), _arr(q["desc"], np.uint8)
+        inv = _arr(inv_level_sigma2, np.float32)
+        nt, nq = len(tx), len(qu)
+        match = np.full(max(nq, 1), -1, np.int32)
+        dist = np.full(max(nq, 1), -1, np.int32)
+        n = C.c_int()
+        _ck(self.L.eaof_match_windows_independent(self.h, int(gate), nt, _p(tx), _p(ty), _p(to), _p(td), _p(tr), bounds[0],
+                                                  bounds[2], grid_inv[0], grid_inv[1], _p(inv), 0 if inv is None else len(inv),
+                                                  nq, _p(qval), _p(qu), _p(qv), _p(qr), _p(ql0), _p(ql1), _p(qur), _p(qd),
+                                                  int(th_accept), match.ctypes.data, dist.ctypes.data, C.byref(n)))
+        return n.value, match[:nq], dist[:nq]
+
+    def DistinctiveDescriptors(self, starts, desc):
+        """Batched MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307): point p owns rows
+        starts[p]:starts[p+1] of desc.  Returns (best row per point relative to its start, its median distance)."""
+        st, d = _arr(starts, np.int32), _arr(desc, np.uint8)
+        npts = len(st) - 1
+        best = np.full(max(npts, 1), -1, np.int32)
+        med = np.full(max(npts, 1), -1, np.int32)
+        _ck(self.L.eaof_distinctive_descriptors(self.h, npts, _p(st), _p(d), best.ctypes.data, med.ctypes.data))
+        return best[:npts], med[:npts]
 
     def SearchForTriangulation(self, k1, k2, F12, epipole, scale_factors, level_sigma2, only_stereo=False):
         """k1: dict(desc,x,y,angle,free[,stereo],nodes); k2: the same plus octave.  free = feature has no map point.

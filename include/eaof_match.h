@@ -119,6 +119,38 @@ int eaof_match_windows(eaof_matcher* m, int rule, int n_t, const float* t_x, con
                        const uint8_t* q_desc, const uint8_t* q_obs, int th_accept, float nnratio, int hist_mode,
                        int check_bounds, int* match_t, int* dist_t, int* n_matches);
 
+/* Independent window queries on the 64x48 grid of a KeyFrame (KeyFrame::GetFeaturesInArea, src/KeyFrame.cc:608-647) —
+ * the search step of the map-side matchers whose loop never excludes a target because an earlier query took it, one
+ * call, HOST buffers.  Per query (a map point projected by the caller): the best target by Hamming distance among
+ * the window candidates on levels [q_min_level, q_max_level], first candidate in the reference's visiting order on
+ * ties, accepted when best <= th_accept.  match_q / dist_q: n_q entries (index of the target, -1 = none); *n_matches
+ * = number of accepted queries.  The caller applies the map mutations in query order.
+ *   Fuse(KeyFrame*, const vector<MapPoint*>&, th)            src/ORBmatcher.cc:825-961: gate EAOF_GATE_FUSE_CHI2 (a
+ *        candidate is dropped when its reprojection error e2*mvInvLevelSigma2[level] exceeds 7.8 with mvuRight >= 0 —
+ *        e2 includes (q_ur - mvuRight)^2 — or 5.99 without, :901-925), levels level-1..level, th_accept = TH_LOW.
+ *   Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)       :963-1100: no gate, th_accept = TH_LOW.
+ *   SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) :1102-1326: once per direction, no gate, th_accept =
+ *        TH_HIGH; the mutual-agreement pass (:1308-1323) is the caller's.
+ * (SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) :290-403 does exclude matched targets: it is
+ * eaof_match_windows with rule EAOF_WIN_BEST, t_taken = vpMatched[idx] != NULL, hist_mode 0, check_bounds 0.)
+ * t_uright (mvuRight, NULL = all monocular) and inv_level_sigma2 / q_ur are only read by the chi-square gate. */
+enum { EAOF_GATE_NONE = 0, EAOF_GATE_FUSE_CHI2 = 1 };
+int eaof_match_windows_independent(eaof_matcher* m, int gate, int n_t, const float* t_x, const float* t_y,
+                                   const int* t_octave, const uint8_t* t_desc, const float* t_uright, float min_x,
+                                   float min_y, float grid_inv_w, float grid_inv_h, const float* inv_level_sigma2,
+                                   int n_levels, int n_q, const uint8_t* q_valid, const float* q_u, const float* q_v,
+                                   const float* q_radius, const int* q_min_level, const int* q_max_level,
+                                   const float* q_ur, const uint8_t* q_desc, int th_accept, int* match_q, int* dist_q,
+                                   int* n_matches);
+
+/* Batched MapPoint::ComputeDistinctiveDescriptors  src/MapPoint.cc:242-307, HOST buffers: map point p owns the
+ * observation descriptors rows [start[p], start[p+1]) of `desc`; for each point the N x N Hamming distances, the
+ * median of every row (sorted row, element 0.5*(N-1) truncated, :288-291) and the FIRST row with the smallest median
+ * (:293-297).  best_out[p] = index of that row relative to start[p] (-1 for a point without observations);
+ * median_out (optional) = its median. */
+int eaof_distinctive_descriptors(eaof_matcher* m, int n_points, const int* start, const uint8_t* desc, int* best_out,
+                                 int* median_out);
+
 /* SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  src/ORBmatcher.cc:405-520, HOST buffers.
  * F1: octave, angle, descriptor of every feature (only level-0 features are matched) and prev_matched (x,y pairs, in/out:
  * updated to the matched F2 position like vbPrevMatched).  F2: undistorted positions, octaves, angles, descriptors; its

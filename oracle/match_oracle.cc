@@ -461,4 +461,186 @@ int eaoo_search_for_initialization(int n1, const int* oct1, const float* angle1,
     return nmatches;
 }
 
+// ---- map-side window matchers: KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:608-647, the Frame walk without a level
+// filter) and a best-distance loop with the level window [predicted-1, predicted] applied by the caller -------------
+
+// ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)  src/ORBmatcher.cc:290-403, after the
+// caller's projection (:318-360): per candidate map point qvalid (not bad, not already found, positive depth, inside
+// the image, inside the scale-invariance range, viewing angle below 60 deg), pixel (qu, qv), predicted level, descriptor.
+// tmatched: vpMatched[idx] != NULL on entry.  matchT/distT: nT entries, index of the map point newly assigned to the
+// keyframe feature (-1: unchanged).
+int eaoo_search_by_projection_sim3kf(int nT, const float* tx, const float* ty, const int* toct, const uint8_t* tdesc,
+                                     const uint8_t* tmatched, float minX, float minY, float invW, float invH, int nQ,
+                                     const uint8_t* qvalid, const float* qu, const float* qv, const int* qlevel,
+                                     const uint8_t* qdesc, const float* scaleFactors, int th, int* matchT, int* distT) {
+    std::vector<int> cellStart(GRID_COLS * GRID_ROWS + 1), cellIdx(nT > 0 ? nT : 1), cand;
+    eaoo_build_grid(nT, tx, ty, minX, minY, invW, invH, cellStart.data(), cellIdx.data());
+    std::vector<uint8_t> matched(nT, 0);
+    for (int k = 0; k < nT; ++k) { matched[k] = tmatched && tmatched[k]; matchT[k] = -1; if (distT) distT[k] = -1; }
+    int nmatches = 0;
+    for (int iMP = 0; iMP < nQ; ++iMP) {
+        if (qvalid && !qvalid[iMP]) continue;
+        const int nPredictedLevel = qlevel[iMP];
+        const float radius = th * scaleFactors[nPredictedLevel];  // int * float, :358
+        features_in_area(cellStart.data(), cellIdx.data(), tx, ty, toct, qu[iMP], qv[iMP], radius, -1, -1, minX, minY, invW,
+                         invH, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            if (matched[idx]) continue;                                                    // :375-376
+            if (toct[idx] < nPredictedLevel - 1 || toct[idx] > nPredictedLevel) continue;  // :380-381
+            const int dist = descriptor_distance(qdesc + 32 * (size_t)iMP, tdesc + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) {  // :394-398
+            matched[bestIdx] = 1;
+            matchT[bestIdx] = iMP;
+            if (distT) distT[bestIdx] = bestDist;
+            ++nmatches;
+        }
+    }
+    return nmatches;
+}
+
+// The search step shared by Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:887-936, gate 1: the reprojection
+// chi-square :901-925), Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (:1049-1075, gate 0) and both directions of
+// SearchBySim3 (:1196-1223, :1276-1303, gate 0): best target of every query, independent of the other queries.
+// Returns the number of queries with best <= thAccept.
+int eaoo_window_best(int gate, int nT, const float* tx, const float* ty, const int* toct, const uint8_t* tdesc,
+                     const float* turight, const float* invLevelSigma2, float minX, float minY, float invW, float invH,
+                     int nQ, const uint8_t* qvalid, const float* qu, const float* qv, const float* qur, const int* qlevel,
+                     const uint8_t* qdesc, const float* scaleFactors, float th, int thAccept, int* matchQ, int* distQ) {
+    std::vector<int> cellStart(GRID_COLS * GRID_ROWS + 1), cellIdx(nT > 0 ? nT : 1), cand;
+    eaoo_build_grid(nT, tx, ty, minX, minY, invW, invH, cellStart.data(), cellIdx.data());
+    int n = 0;
+    for (int i = 0; i < nQ; ++i) {
+        matchQ[i] = -1;
+        if (distQ) distQ[i] = -1;
+        if (qvalid && !qvalid[i]) continue;
+        const int nPredictedLevel = qlevel[i];
+        const float u = qu[i], v = qv[i];
+        const float radius = th * scaleFactors[nPredictedLevel];
+        features_in_area(cellStart.data(), cellIdx.data(), tx, ty, toct, u, v, radius, -1, -1, minX, minY, invW, invH, cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            const int kpLevel = toct[idx];
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            if (gate == 1) {
+                const float kpx = tx[idx], kpy = ty[idx];
+                if (turight && turight[idx] >= 0) {  // :901-914
+                    const float kpr = turight[idx];
+                    const float ex = u - kpx, ey = v - kpy, er = qur[i] - kpr;
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * invLevelSigma2[kpLevel] > 7.8) continue;
+                } else {  // :915-925
+                    const float ex = u - kpx, ey = v - kpy;
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * invLevelSigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = descriptor_distance(qdesc + 32 * (size_t)i, tdesc + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= thAccept) {
+            matchQ[i] = bestIdx;
+            if (distQ) distQ[i] = bestDist;
+            ++n;
+        }
+    }
+    return n;
+}
+
+// What Fuse(KeyFrame*, vpMapPoints, th) does with the search result, in query order (src/ORBmatcher.cc:846-849 re-read
+// at each turn, :938-957), on array state.  Map points are numbered: candidate i -> qid[i] (its first occurrence when
+// the same MapPoint* is listed twice), the point a keyframe feature holds on entry -> nQ+idx.  Per point: bad, obs
+// (Observations()), inKF (IsInKeyFrame(pKF)); slot[idx] = point held by feature idx (-1 none).  Replace(a by b) marks a
+// bad and records replacedBy[a] = b (the stand-in MapPoint of oracle/matchshim).  matchQ = the search result of the
+// candidates that pass the static skip tests (projection, distance, viewing angle); qnull = vpMapPoints[i] == NULL.
+int eaoo_fuse_apply(int nT, int nQ, const int* matchQ, const uint8_t* qnull, const int* qid, int* slot, uint8_t* bad,
+                    int* obs, uint8_t* inKF, int* replacedBy, int* addedAt) {
+    int nFused = 0;
+    for (int i = 0; i < nQ; ++i) {
+        addedAt[i] = -1;
+        if (qnull && qnull[i]) continue;
+        const int p = qid ? qid[i] : i;
+        if (bad[p] || inKF[p]) continue;
+        const int bestIdx = matchQ[i];
+        if (bestIdx < 0) continue;
+        const int inKFpt = slot[bestIdx];
+        if (inKFpt >= 0) {
+            if (!bad[inKFpt]) {
+                if (obs[inKFpt] > obs[p]) { bad[p] = 1; replacedBy[p] = inKFpt; }
+                else { bad[inKFpt] = 1; replacedBy[inKFpt] = p; }
+            }
+        } else {
+            inKF[p] = 1; ++obs[p]; addedAt[i] = bestIdx;  // AddObservation
+            slot[bestIdx] = p;                             // AddMapPoint
+        }
+        ++nFused;
+    }
+    (void)nT;
+    return nFused;
+}
+
+// Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint): the result step :1078-1093.  replacePoint[i] = point to be
+// replaced (numbering as above, -1 none).
+int eaoo_fuse_sim3_apply(int nT, int nQ, const int* matchQ, int* slot, const uint8_t* bad, int* replacePoint, int* addedAt) {
+    int nFused = 0;
+    for (int i = 0; i < nQ; ++i) {
+        addedAt[i] = -1;
+        replacePoint[i] = -1;
+        const int bestIdx = matchQ[i];
+        if (bestIdx < 0) continue;
+        const int inKFpt = slot[bestIdx];
+        if (inKFpt >= 0) {
+            if (!bad[inKFpt]) replacePoint[i] = inKFpt;
+        } else {
+            addedAt[i] = bestIdx;
+            slot[bestIdx] = i;
+        }
+        ++nFused;
+    }
+    (void)nT;
+    return nFused;
+}
+
+// SearchBySim3: the agreement pass src/ORBmatcher.cc:1308-1323.  match12out[i1] = idx2 for the mutual matches.
+int eaoo_sim3_agreement(int n1, const int* vnMatch1, int n2, const int* vnMatch2, int* match12out) {
+    int nFound = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        match12out[i1] = -1;
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && idx2 < n2) {
+            const int idx1 = vnMatch2[idx2];
+            if (idx1 == i1) { match12out[i1] = idx2; ++nFound; }
+        }
+    }
+    return nFound;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors  src/MapPoint.cc:273-301 for one map point with n observation descriptors:
+// returns the index of the descriptor with the least median distance to the others (first on ties), -1 when n == 0.
+int eaoo_distinctive_descriptor(int n, const uint8_t* desc, int* medianOut) {
+    if (n <= 0) return -1;
+    std::vector<float> D((size_t)n * n);
+    for (int i = 0; i < n; ++i) {
+        D[(size_t)i * n + i] = 0;
+        for (int j = i + 1; j < n; ++j) {
+            const int d = descriptor_distance(desc + 32 * (size_t)i, desc + 32 * (size_t)j);
+            D[(size_t)i * n + j] = d;
+            D[(size_t)j * n + i] = d;
+        }
+    }
+    int BestMedian = 0x7fffffff, BestIdx = 0;
+    for (int i = 0; i < n; ++i) {
+        std::vector<int> vDists(D.begin() + (size_t)i * n, D.begin() + (size_t)(i + 1) * n);
+        std::sort(vDists.begin(), vDists.end());
+        const int median = vDists[(size_t)(0.5 * (n - 1))];
+        if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    if (medianOut) *medianOut = BestMedian;
+    return BestIdx;
+}
+
 }  // extern "C"

@@ -357,4 +357,222 @@ int mref_search_by_projection_kf(int nC, const float* cx, const float* cy, const
     return n;
 }
 
+// ---- map-side matchers of the LocalMapping / LoopClosing threads ------------------------------------------------------
+// Geometry as above: keyframe pose identity, fx=fy=1, cx=cy=0, world points (wx, wy, wz) with wz = +-1, so that the
+// projection is (wx, wy) exactly; the distance gate, viewing-angle gate and MapPoint::PredictScale run inside the
+// reference on (maxDist, minDist, normal).
+
+double mref_dot3(float ax, float ay, float az, float bx, float by, float bz) { return vec3(ax, ay, az).dot(vec3(bx, by, bz)); }
+
+}  // extern "C"
+
+namespace {
+void assign_grid(KeyFrame& kf) {  // KeyFrame copies the Frame's grid (src/KeyFrame.cc:52-58); Frame::AssignFeaturesToGrid
+    for (int i = 0; i < kf.N; i++) {
+        const cv::KeyPoint& kp = kf.mvKeysUn[i];
+        const int posX = round((kp.pt.x - kf.mnMinX) * kf.mfGridElementWidthInv);
+        const int posY = round((kp.pt.y - kf.mnMinY) * kf.mfGridElementHeightInv);
+        if (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) continue;
+        kf.mGrid[posX][posY].push_back(i);
+    }
+}
+void setup_kf(KeyFrame& kf, int n, const float* x, const float* y, const int* oct, const uint8_t* desc, const float* uright,
+              int minX, int maxX, int minY, int maxY, float invW, float invH, const float* scaleFactors,
+              const float* invSigma2, int nLevels, float logScaleFactor) {
+    kf.N = n;
+    fill_keys(kf.mvKeysUn, n, x, y, oct, nullptr);
+    kf.mvKeys = kf.mvKeysUn;
+    kf.mDescriptors = desc_rows(desc, n);
+    kf.mvuRight.resize(n);
+    for (int i = 0; i < n; ++i) kf.mvuRight[i] = uright ? uright[i] : -1.f;
+    kf.mvpMapPoints.assign(n, nullptr);
+    kf.mnMinX = minX; kf.mnMaxX = maxX; kf.mnMinY = minY; kf.mnMaxY = maxY;
+    kf.mfGridElementWidthInv = invW; kf.mfGridElementHeightInv = invH;
+    assign_grid(kf);
+    kf.mvScaleFactors.assign(scaleFactors, scaleFactors + nLevels);
+    if (invSigma2) kf.mvInvLevelSigma2.assign(invSigma2, invSigma2 + nLevels);
+    kf.mfLogScaleFactor = logScaleFactor;
+    kf.mnScaleLevels = nLevels;
+    kf.Tcw = eye4();
+    kf.Ow = vec3(0.f, 0.f, 0.f);
+}
+void setup_point(MapPoint* p, int i, const float* wx, const float* wy, const float* wz, const float* maxDist,
+                 const float* minDist, const float* normal, const uint8_t* desc) {
+    p->pos = vec3(wx[i], wy[i], wz[i]);
+    p->mfMaxDistance = maxDist[i];
+    p->maxDist = maxDist[i];
+    p->minDist = minDist[i];
+    p->normal = normal ? vec3(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]) : vec3(wx[i], wy[i], wz[i]);
+    p->desc = desc_row(desc + 32 * (size_t)i);
+}
+const int SLOT_TAG = 100000;  // tag of the map point a keyframe feature holds on entry = SLOT_TAG + feature index
+}  // namespace
+
+extern "C" {
+
+// SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)  src/ORBmatcher.cc:290-403.  Scw = scwScale * identity.
+// tmatched[k]: -1 = vpMatched[k] NULL, -2 = a map point that is not among vpPoints, i >= 0 = vpPoints[i] (so that point
+// counts as already found).  qbad[i]: isBad().  matchT[k] = index of the map point in vpMatched[k] afterwards.
+int mref_search_by_projection_sim3kf(int nT, const float* tx, const float* ty, const int* toct, const uint8_t* tdesc,
+                                     const int* tmatched, int minX, int maxX, int minY, int maxY, float invW, float invH,
+                                     int nQ, const uint8_t* qbad, const float* wx, const float* wy, const float* wz,
+                                     const float* maxDist, const float* minDist, const float* normal, const uint8_t* qdesc,
+                                     const float* scaleFactors, int nLevels, float logScaleFactor, float scwScale, int th,
+                                     int* matchT) {
+    Pool pool;
+    ORBmatcher matcher(0.75f, true);
+    KeyFrame kf;
+    setup_kf(kf, nT, tx, ty, toct, tdesc, nullptr, minX, maxX, minY, maxY, invW, invH, scaleFactors, nullptr, nLevels, logScaleFactor);
+    std::vector<MapPoint*> pts(nQ);
+    for (int i = 0; i < nQ; ++i) {
+        pts[i] = pool.make(i);
+        pts[i]->bad = qbad && qbad[i];
+        setup_point(pts[i], i, wx, wy, wz, maxDist, minDist, normal, qdesc);
+    }
+    std::vector<MapPoint*> matched(nT, nullptr);
+    for (int k = 0; k < nT; ++k) {
+        if (tmatched[k] >= 0) matched[k] = pts[tmatched[k]];
+        else if (tmatched[k] == -2) matched[k] = pool.make(-2);
+    }
+    cv::Mat Scw = eye4();
+    for (int i = 0; i < 3; ++i) Scw.at<float>(i, i) = scwScale;
+    const int n = matcher.SearchByProjection(&kf, Scw, pts, matched, th);
+    for (int k = 0; k < nT; ++k) matchT[k] = pool.of(matched[k]);
+    return n;
+}
+
+// Fuse(KeyFrame*, const vector<MapPoint*>&, th)  src/ORBmatcher.cc:825-961.  Keyframe features: slotState 0 = no map
+// point, 1 = a good one, 2 = a bad one (Observations() = slotObs).  Candidates: qstate 0 = NULL, 1 = bad, 2 = already in
+// the keyframe, 3 = usable; qid[i] = canonical index when the same MapPoint* appears more than once (qid[i] <= i).
+// Outputs (stand-in MapPoint semantics of matchshim): per candidate addedAt (AddObservation index or -1), replacedBy (tag
+// of the point it was replaced by, -1 none); per keyframe feature slotReplacedBy (same for the point held on entry) and
+// slotHolder (tag of the point held afterwards).  Tags: candidate i -> qid, entry point of feature k -> 100000+k.
+int mref_fuse(int nT, const float* tx, const float* ty, const int* toct, const uint8_t* tdesc, const float* turight,
+              const uint8_t* slotState, const int* slotObs, int minX, int maxX, int minY, int maxY, float invW, float invH,
+              const float* invSigma2, const float* scaleFactors, int nLevels, float logScaleFactor, float mbf, int nQ,
+              const uint8_t* qstate, const int* qid, const float* wx, const float* wy, const float* wz, const float* maxDist,
+              const float* minDist, const float* normal, const int* qobs, const uint8_t* qdesc, float th, int* addedAt,
+              int* replacedBy, int* slotReplacedBy, int* slotHolder) {
+    Pool pool;
+    ORBmatcher matcher(0.6f, true);
+    KeyFrame kf, other;
+    setup_kf(kf, nT, tx, ty, toct, tdesc, turight, minX, maxX, minY, maxY, invW, invH, scaleFactors, invSigma2, nLevels, logScaleFactor);
+    kf.mbf = mbf;
+    std::vector<MapPoint*> entry(nT, nullptr);
+    for (int k = 0; k < nT; ++k) {
+        if (!slotState[k]) continue;
+        entry[k] = pool.make(SLOT_TAG + k);
+        entry[k]->bad = slotState[k] == 2;
+        entry[k]->nObs = slotObs[k];
+        entry[k]->obs[&kf] = k;
+        kf.mvpMapPoints[k] = entry[k];
+    }
+    std::vector<MapPoint*> pts(nQ, nullptr);
+    for (int i = 0; i < nQ; ++i) {
+        if (qstate[i] == 0) continue;
+        if (qid && qid[i] != i) { pts[i] = pts[qid[i]]; continue; }
+        pts[i] = pool.make(i);
+        pts[i]->bad = qstate[i] == 1;
+        pts[i]->nObs = qobs[i];
+        if (qstate[i] == 2) pts[i]->obs[&kf] = 0;
+        else pts[i]->obs[&other] = 0;
+        setup_point(pts[i], i, wx, wy, wz, maxDist, minDist, normal, qdesc);
+    }
+    const int n = matcher.Fuse(&kf, pts, th);
+    for (int i = 0; i < nQ; ++i) {
+        addedAt[i] = -1;
+        replacedBy[i] = -1;
+        if (!pts[i]) continue;
+        if (qstate[i] != 2 && pts[i]->obs.count(&kf)) addedAt[i] = (int)pts[i]->obs[&kf];
+        replacedBy[i] = pool.of(pts[i]->replaced);
+    }
+    for (int k = 0; k < nT; ++k) {
+        slotReplacedBy[k] = entry[k] ? pool.of(entry[k]->replaced) : -1;
+        slotHolder[k] = pool.of(kf.mvpMapPoints[k]);
+    }
+    return n;
+}
+
+// Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)  src/ORBmatcher.cc:963-1100.  slotState as mref_fuse, except
+// slotQuery[k] >= 0: the feature holds vpPoints[slotQuery[k]] (so that candidate is "already found").  replacePoint[i] =
+// tag of vpReplacePoint[i] afterwards.
+int mref_fuse_sim3(int nT, const float* tx, const float* ty, const int* toct, const uint8_t* tdesc, const uint8_t* slotState,
+                   const int* slotQuery, int minX, int maxX, int minY, int maxY, float invW, float invH,
+                   const float* scaleFactors, int nLevels, float logScaleFactor, float scwScale, int nQ, const uint8_t* qbad,
+                   const float* wx, const float* wy, const float* wz, const float* maxDist, const float* minDist,
+                   const float* normal, const uint8_t* qdesc, float th, int* addedAt, int* replacePoint, int* slotHolder) {
+    Pool pool;
+    ORBmatcher matcher(0.8f, true);
+    KeyFrame kf;
+    setup_kf(kf, nT, tx, ty, toct, tdesc, nullptr, minX, maxX, minY, maxY, invW, invH, scaleFactors, nullptr, nLevels, logScaleFactor);
+    std::vector<MapPoint*> pts(nQ);
+    for (int i = 0; i < nQ; ++i) {
+        pts[i] = pool.make(i);
+        pts[i]->bad = qbad && qbad[i];
+        setup_point(pts[i], i, wx, wy, wz, maxDist, minDist, normal, qdesc);
+    }
+    for (int k = 0; k < nT; ++k) {
+        if (slotQuery && slotQuery[k] >= 0) { kf.mvpMapPoints[k] = pts[slotQuery[k]]; continue; }
+        if (!slotState[k]) continue;
+        kf.mvpMapPoints[k] = pool.make(SLOT_TAG + k);
+        kf.mvpMapPoints[k]->bad = slotState[k] == 2;
+    }
+    cv::Mat Scw = eye4();
+    for (int i = 0; i < 3; ++i) Scw.at<float>(i, i) = scwScale;
+    std::vector<MapPoint*> repl(nQ, nullptr);
+    const int n = matcher.Fuse(&kf, Scw, pts, th, repl);
+    for (int i = 0; i < nQ; ++i) {
+        replacePoint[i] = pool.of(repl[i]);
+        addedAt[i] = pts[i]->obs.count(&kf) ? (int)pts[i]->obs[&kf] : -1;
+    }
+    for (int k = 0; k < nT; ++k) slotHolder[k] = pool.of(kf.mvpMapPoints[k]);
+    return n;
+}
+
+// SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)  src/ORBmatcher.cc:1102-1326 with R12 = I, t12 = 0 and both
+// keyframe poses identity.  Per keyframe a (a = 1, 2): features (x, y, octave, descriptor) and per feature the map point
+// it holds: state 0 = none, 1 = bad, 3 = good, with world point / distance range / descriptor.  pre12[i1] = index of the
+// KF2 feature whose map point vpMatches12[i1] holds on entry (-1 none).  match12[i1] = KF2 feature index of
+// vpMatches12[i1] afterwards.
+int mref_search_by_sim3(int n1, const float* x1, const float* y1, const int* oct1, const uint8_t* kdesc1,
+                        const uint8_t* state1, const float* wx1, const float* wy1, const float* wz1, const float* maxDist1,
+                        const float* minDist1, const uint8_t* pdesc1, int n2, const float* x2, const float* y2,
+                        const int* oct2, const uint8_t* kdesc2, const uint8_t* state2, const float* wx2, const float* wy2,
+                        const float* wz2, const float* maxDist2, const float* minDist2, const uint8_t* pdesc2,
+                        const int* pre12, int minX, int maxX, int minY, int maxY, float invW, float invH,
+                        const float* scaleFactors, int nLevels, float logScaleFactor, float s12, float th, int* match12) {
+    Pool pool;
+    ORBmatcher matcher(0.75f, true);
+    KeyFrame k1, k2;
+    setup_kf(k1, n1, x1, y1, oct1, kdesc1, nullptr, minX, maxX, minY, maxY, invW, invH, scaleFactors, nullptr, nLevels, logScaleFactor);
+    setup_kf(k2, n2, x2, y2, oct2, kdesc2, nullptr, minX, maxX, minY, maxY, invW, invH, scaleFactors, nullptr, nLevels, logScaleFactor);
+    for (int i = 0; i < n1; ++i) {
+        if (!state1[i]) continue;
+        MapPoint* p = pool.make(i);
+        p->bad = state1[i] == 1;
+        setup_point(p, i, wx1, wy1, wz1, maxDist1, minDist1, nullptr, pdesc1);
+        p->obs[&k1] = i;
+        k1.mvpMapPoints[i] = p;
+    }
+    for (int i = 0; i < n2; ++i) {
+        if (!state2[i]) continue;
+        MapPoint* p = pool.make(SLOT_TAG + i);
+        p->bad = state2[i] == 1;
+        setup_point(p, i, wx2, wy2, wz2, maxDist2, minDist2, nullptr, pdesc2);
+        p->obs[&k2] = i;
+        k2.mvpMapPoints[i] = p;
+    }
+    std::vector<MapPoint*> m12(n1, nullptr);
+    for (int i = 0; i < n1; ++i)
+        if (pre12 && pre12[i] >= 0) m12[i] = k2.mvpMapPoints[pre12[i]];
+    cv::Mat R12 = eye4().rowRange(0, 3).colRange(0, 3).clone();
+    cv::Mat t12 = vec3(0.f, 0.f, 0.f);
+    const int n = matcher.SearchBySim3(&k1, &k2, m12, s12, R12, t12, th);
+    for (int i = 0; i < n1; ++i) {
+        const int t = pool.of(m12[i]);
+        match12[i] = t >= SLOT_TAG ? t - SLOT_TAG : -1;
+    }
+    return n;
+}
+
 }  // extern "C"

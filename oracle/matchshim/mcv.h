@@ -87,6 +87,8 @@ public:
     template <typename T> T* ptr(int y = 0) { return (T*)(data + (size_t)y * step); }
     template <typename T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step); }
 
+    void copyTo(Mat& dst) const { dst = clone(); }
+    static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
     Mat t() const {
         assert(depth_ == CV_32F);
         Mat m(cols, rows, CV_32F);

@@ -7,13 +7,23 @@
 //   Frame::GetFeaturesInArea / PosInGrid / AssignFeaturesToGrid   src/Frame.cc:599-614,696-761
 //   KeyFrame::GetFeaturesInArea / IsInImage                        src/KeyFrame.cc:608-652
 //   MapPoint::PredictScale / Get{Min,Max}DistanceInvariance       src/MapPoint.cc:373-394
+//
+// Second mode, -DEAOF_REAL_MAPPOINT (oracle/Makefile target `mappointref`): MapPoint is NOT replaced — the reference's
+// own include/MapPoint.h + src/MapPoint.cc are compiled unmodified on top of the KeyFrame / Frame stand-ins below plus a
+// Map stand-in, so that MapPoint::ComputeDistinctiveDescriptors, Replace, AddObservation, PredictScale ... are the
+// reference's code (oracle/mappoint_ref_harness.cc).
 #pragma once
+#ifndef EAOF_REAL_MAPPOINT
 #define MAPPOINT_H
+#else
+#define MAP_H
+#endif
 #define KEYFRAME_H
 #define FRAME_H
 
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <set>
 #include <vector>
 
@@ -29,6 +39,15 @@ using namespace std;  // the reference headers do the same (include/Frame.h), an
 class KeyFrame;
 class Frame;
 
+#ifdef EAOF_REAL_MAPPOINT
+class MapPoint;
+class Map {  // include/Map.h: what src/MapPoint.cc touches
+public:
+    std::mutex mMutexPointCreation;
+    void EraseMapPoint(MapPoint* pMP) { erased.push_back(pMP); }
+    std::vector<MapPoint*> erased;
+};
+#else
 class MapPoint {
 public:
     MapPoint() : mbTrackInView(false), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mnTrackScaleLevel(0),
@@ -62,6 +81,7 @@ public:
     std::map<KeyFrame*, size_t> obs;
     MapPoint* replaced = nullptr;
 };
+#endif
 
 struct GridOwner {
     std::vector<size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
@@ -116,6 +136,10 @@ public:
         return vIndices;
     }
 
+    cv::Mat GetCameraCenter() { return mOw.clone(); }
+    long unsigned int mnId = 0;
+    cv::Mat mOw;
+
     int N;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     std::vector<float> mvuRight, mvDepth;
@@ -163,12 +187,13 @@ public:
     bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
-    std::set<MapPoint*> GetMapPoints() {
-        std::set<MapPoint*> s;
-        for (MapPoint* p : mvpMapPoints) if (p && !p->isBad()) s.insert(p);
-        return s;
-    }
+    std::set<MapPoint*> GetMapPoints();  // src/KeyFrame.cc:252-265, defined below (needs the complete MapPoint)
     void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
+    void EraseMapPointMatch(const size_t& idx) { mvpMapPoints[idx] = static_cast<MapPoint*>(NULL); }
+    void ReplaceMapPointMatch(const size_t& idx, MapPoint* pMP) { mvpMapPoints[idx] = pMP; }
+    bool isBad() { return mbBad; }
+    long unsigned int mnId = 0, mnFrameId = 0;
+    bool mbBad = false;
     cv::Mat GetRotation() { return Tcw.rowRange(0, 3).colRange(0, 3).clone(); }
     cv::Mat GetTranslation() { return Tcw.rowRange(0, 3).col(3).clone(); }
     cv::Mat GetCameraCenter() { return Ow.clone(); }
@@ -190,4 +215,17 @@ public:
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
 };
 
+}  // namespace ORB_SLAM2
+
+#ifdef EAOF_REAL_MAPPOINT
+#include <mutex>
+#include "MapPoint.h"  // the reference's own include/MapPoint.h; its KeyFrame.h / Frame.h / Map.h includes are claimed above
+#endif
+
+namespace ORB_SLAM2 {
+inline std::set<MapPoint*> KeyFrame::GetMapPoints() {
+    std::set<MapPoint*> s;
+    for (MapPoint* p : mvpMapPoints) if (p && !p->isBad()) s.insert(p);
+    return s;
+}
 }  // namespace ORB_SLAM2

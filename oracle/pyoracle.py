@@ -416,6 +416,12 @@ def _setup_mref(L):
                                                  cf, ci, vp]
     L.mref_search_by_projection_kf.argtypes = [ci, vp, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, ci, vp, vp, vp, vp,
                                                vp, vp, vp, vp, vp, ci, cf, cf, ci, ci, cf, vp]
+    L.mref_dot3.restype = C.c_double
+    L.mref_dot3.argtypes = [cf] * 6
+    L.mref_search_by_projection_sim3kf.argtypes = [ci] + [vp] * 5 + [ci] * 4 + [cf, cf, ci] + [vp] * 9 + [ci, cf, cf, ci, vp]
+    L.mref_fuse.argtypes = ([ci] + [vp] * 7 + [ci] * 4 + [cf, cf, vp, vp, ci, cf, cf, ci] + [vp] * 10 + [cf] + [vp] * 4)
+    L.mref_fuse_sim3.argtypes = [ci] + [vp] * 6 + [ci] * 4 + [cf, cf, vp, ci, cf, cf, ci] + [vp] * 8 + [cf] + [vp] * 3
+    L.mref_search_by_sim3.argtypes = ([ci] + [vp] * 11 + [ci] + [vp] * 11 + [vp] + [ci] * 4 + [cf, cf, vp, ci, cf, cf, cf, vp])
     return L
 
 
@@ -622,3 +628,217 @@ def r_search_for_initialization(F1, F2, prev, window, nnratio, check_ori, *, bou
                                                        grid_inv[0], grid_inv[1], int(window), float(nnratio), int(check_ori),
                                                        m.ctypes.data)
     return n, m[:len(o1)], pm
+
+
+# ---- map-side matchers (LocalMapping / LoopClosing): SearchByProjection(KF,Scw), Fuse x2, SearchBySim3 -------------------
+
+def map_projection(pts, log_scale_factor, n_levels, *, bounds, check_normal=True, scale=1.0, L=None):
+    """What the map-side loops derive per map point before the descriptor search (src/ORBmatcher.cc:318-356, :852-885,
+    :1160-1190), for the harness geometry (identity pose, fx=fy=1, cx=cy=0, wz=+-1, camera-frame point = scale * world
+    point), computed with the reference binary's own helpers (cv::norm, Mat::dot, MapPoint::PredictScale as compiled
+    into libmatch_ref.so).  pts: dict(wx,wy,wz,max_dist,min_dist[,normal]).  Returns (valid, u, v, level): valid = passes
+    depth, image bounds, distance range and viewing angle."""
+    L = L or match_ref_lib()
+    wx, wy, wz = _a(pts["wx"], np.float32), _a(pts["wy"], np.float32), _a(pts["wz"], np.float32)
+    mx, mn = _a(pts["max_dist"], np.float32), _a(pts["min_dist"], np.float32)
+    nrm = _a(pts.get("normal"), np.float32)
+    n = len(wx)
+    sc = np.float32(scale)
+    valid, u, v, lvl = np.zeros(n, np.uint8), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+    for i in range(n):
+        assert abs(wz[i]) == 1.0
+        if wz[i] < 0:
+            continue
+        u[i], v[i] = wx[i], wy[i]
+        if not (u[i] >= bounds[0] and u[i] < bounds[1] and v[i] >= bounds[2] and v[i] < bounds[3]):  # KeyFrame::IsInImage
+            continue
+        d = np.float32(L.mref_norm3(float(sc * wx[i]), float(sc * wy[i]), float(sc * wz[i])))
+        if d < np.float32(0.8) * mn[i] or d > np.float32(1.2) * mx[i]:
+            continue
+        if check_normal:
+            nx, ny, nz = (nrm[i] if nrm is not None else (wx[i], wy[i], wz[i]))
+            if L.mref_dot3(float(wx[i]), float(wy[i]), float(wz[i]), float(nx), float(ny), float(nz)) < 0.5 * float(d):
+                continue
+        lvl[i] = L.mref_predict_scale(float(mx[i]), float(d), float(log_scale_factor))
+        assert 0 <= lvl[i] < n_levels, "test data must keep the predicted level inside the pyramid"
+        valid[i] = 1
+    return valid, u, v, lvl
+
+
+def _kf_arrays(KF):
+    return (_a(KF["x"], np.float32), _a(KF["y"], np.float32), _a(KF["octave"], np.int32), _a(KF["desc"], np.uint8),
+            _a(KF.get("uright"), np.float32))
+
+
+def _pt_arrays(pts):
+    return (_a(pts["wx"], np.float32), _a(pts["wy"], np.float32), _a(pts["wz"], np.float32), _a(pts["max_dist"], np.float32),
+            _a(pts["min_dist"], np.float32), _a(pts.get("normal"), np.float32), _a(pts["desc"], np.uint8))
+
+
+def o_search_by_projection_sim3kf(KF, q, th, *, bounds, grid_inv, scale_factors):
+    """KF: dict(x,y,octave,desc, matched = flags vpMatched[k] != NULL); q: dict(valid,u,v,level,desc).
+    Returns (nmatches, matchT, distT).  src/ORBmatcher.cc:290-403."""
+    tx, ty, to, td, _ = _kf_arrays(KF)
+    tm = _a(KF.get("matched"), np.uint8)
+    qv, qu, qvv, ql, qd = (_a(q["valid"], np.uint8), _a(q["u"], np.float32), _a(q["v"], np.float32), _a(q["level"], np.int32),
+                           _a(q["desc"], np.uint8))
+    sf = _a(scale_factors, np.float32)
+    nT, nQ = len(tx), len(qu)
+    match, dist = np.full(max(nT, 1), -1, np.int32), np.full(max(nT, 1), -1, np.int32)
+    L = _mo()
+    ci, cf, vp = C.c_int, C.c_float, C.c_void_p
+    L.eaoo_search_by_projection_sim3kf.argtypes = [ci] + [vp] * 5 + [cf] * 4 + [ci] + [vp] * 6 + [ci, vp, vp]
+    n = L.eaoo_search_by_projection_sim3kf(nT, _pp(tx), _pp(ty), _pp(to), _pp(td), _pp(tm), bounds[0], bounds[2], grid_inv[0],
+                                           grid_inv[1], nQ, _pp(qv), _pp(qu), _pp(qvv), _pp(ql), _pp(qd), _pp(sf), int(th),
+                                           match.ctypes.data, dist.ctypes.data)
+    return n, match[:nT], dist[:nT]
+
+
+def r_search_by_projection_sim3kf(KF, pts, th, *, bounds, grid_inv, scale_factors, log_scale_factor, scw_scale=1.0, L=None):
+    """KF as above with matched_q (int per feature: -1 none, -2 foreign point, i = vpPoints[i]); pts: dict(wx,wy,wz,
+    max_dist,min_dist,normal,desc,bad).  Returns (nmatches, tag of vpMatched[k] afterwards)."""
+    tx, ty, to, td, _ = _kf_arrays(KF)
+    tm = _a(KF["matched_q"], np.int32)
+    wx, wy, wz, mx, mn, nrm, qd = _pt_arrays(pts)
+    bad = _a(pts.get("bad"), np.uint8)
+    sf = _a(scale_factors, np.float32)
+    nT, nQ = len(tx), len(wx)
+    match = np.full(max(nT, 1), -1, np.int32)
+    n = (L or match_ref_lib()).mref_search_by_projection_sim3kf(
+        nT, _pp(tx), _pp(ty), _pp(to), _pp(td), _pp(tm), int(bounds[0]), int(bounds[1]), int(bounds[2]), int(bounds[3]),
+        grid_inv[0], grid_inv[1], nQ, _pp(bad), _pp(wx), _pp(wy), _pp(wz), _pp(mx), _pp(mn), _pp(nrm), _pp(qd), _pp(sf), len(sf),
+        float(log_scale_factor), float(scw_scale), int(th), match.ctypes.data)
+    return n, match[:nT]
+
+
+def o_window_best(gate, KF, q, th, th_accept, *, bounds, grid_inv, scale_factors, inv_level_sigma2=None):
+    """The search step of Fuse x2 / SearchBySim3.  q: dict(valid,u,v,level,desc[,ur]).  Returns (n, matchQ, distQ)."""
+    tx, ty, to, td, tr = _kf_arrays(KF)
+    qv, qu, qvv, ql, qd = (_a(q["valid"], np.uint8), _a(q["u"], np.float32), _a(q["v"], np.float32), _a(q["level"], np.int32),
+                           _a(q["desc"], np.uint8))
+    qur, inv, sf = _a(q.get("ur"), np.float32), _a(inv_level_sigma2, np.float32), _a(scale_factors, np.float32)
+    nT, nQ = len(tx), len(qu)
+    match, dist = np.full(max(nQ, 1), -1, np.int32), np.full(max(nQ, 1), -1, np.int32)
+    L = _mo()
+    ci, cf, vp = C.c_int, C.c_float, C.c_void_p
+    L.eaoo_window_best.argtypes = [ci, ci] + [vp] * 6 + [cf] * 4 + [ci] + [vp] * 7 + [cf, ci, vp, vp]
+    n = L.eaoo_window_best(int(gate), nT, _pp(tx), _pp(ty), _pp(to), _pp(td), _pp(tr), _pp(inv), bounds[0], bounds[2],
+                           grid_inv[0], grid_inv[1], nQ, _pp(qv), _pp(qu), _pp(qvv), _pp(qur), _pp(ql), _pp(qd), _pp(sf),
+                           float(th), int(th_accept), match.ctypes.data, dist.ctypes.data)
+    return n, match[:nQ], dist[:nQ]
+
+
+def o_fuse_apply(match_q, qstate, qid, qobs, slot_state, slot_obs):
+    """Bookkeeping of Fuse(KeyFrame*, vpMapPoints, th) on array state (eaoo_fuse_apply).  Returns (nFused, addedAt,
+    replacedBy, slotReplacedBy, slotHolder) in the tag convention of mref_fuse (candidate -> qid, entry point of feature
+    k -> 100000+k)."""
+    nQ, nT = len(match_q), len(slot_state)
+    TAG = 100000
+    qstate, slot_state, qid = np.asarray(qstate), np.asarray(slot_state), _a(qid, np.int32)
+    slot = np.where(slot_state > 0, nQ + np.arange(nT), -1).astype(np.int32)
+    bad = np.zeros(nQ + nT, np.uint8); obs = np.zeros(nQ + nT, np.int32); inkf = np.zeros(nQ + nT, np.uint8)
+    bad[:nQ] = qstate == 1; inkf[:nQ] = qstate == 2; obs[:nQ] = qobs
+    bad[nQ:] = slot_state == 2; obs[nQ:] = slot_obs; inkf[nQ:] = slot_state > 0
+    repl = np.full(nQ + nT, -1, np.int32)
+    added = np.full(max(nQ, 1), -1, np.int32)
+    qnull = (qstate == 0).astype(np.uint8)
+    L = _mo()
+    L.eaoo_fuse_apply.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 9
+    n = L.eaoo_fuse_apply(nT, nQ, _pp(_a(match_q, np.int32)), _pp(qnull), _pp(qid), _pp(slot), _pp(bad), _pp(obs), _pp(inkf),
+                          _pp(repl), _pp(added))
+    tag = lambda p: -1 if p < 0 else (int(p) if p < nQ else TAG + int(p) - nQ)
+    replaced_by = np.array([-1 if qnull[i] else tag(repl[qid[i]]) for i in range(nQ)], np.int32)
+    added_at = np.full(nQ, -1, np.int32)   # the AddObservation index is a property of the point: every alias reports it
+    for i in range(nQ):
+        if added[i] >= 0:
+            added_at[(qid == qid[i]) & (qnull == 0)] = added[i]
+    slot_replaced_by = np.array([tag(repl[nQ + k]) if slot_state[k] else -1 for k in range(nT)], np.int32)
+    slot_holder = np.array([tag(p) for p in slot], np.int32)
+    return n, added_at, replaced_by, slot_replaced_by, slot_holder
+
+
+def r_fuse(KF, pts, th, *, bounds, grid_inv, scale_factors, inv_level_sigma2, log_scale_factor, mbf, L=None):
+    """KF: dict(x,y,octave,desc,uright,slot_state,slot_obs); pts: dict(wx,..,desc,state,qid,obs).
+    Returns (nFused, addedAt, replacedBy, slotReplacedBy, slotHolder)."""
+    tx, ty, to, td, tr = _kf_arrays(KF)
+    ss, so = _a(KF["slot_state"], np.uint8), _a(KF["slot_obs"], np.int32)
+    wx, wy, wz, mx, mn, nrm, qd = _pt_arrays(pts)
+    qs, qid, qo = _a(pts["state"], np.uint8), _a(pts["qid"], np.int32), _a(pts["obs"], np.int32)
+    sf, inv = _a(scale_factors, np.float32), _a(inv_level_sigma2, np.float32)
+    nT, nQ = len(tx), len(wx)
+    added, repl = np.full(max(nQ, 1), -1, np.int32), np.full(max(nQ, 1), -1, np.int32)
+    srep, shold = np.full(max(nT, 1), -1, np.int32), np.full(max(nT, 1), -1, np.int32)
+    n = (L or match_ref_lib()).mref_fuse(
+        nT, _pp(tx), _pp(ty), _pp(to), _pp(td), _pp(tr), _pp(ss), _pp(so), int(bounds[0]), int(bounds[1]), int(bounds[2]),
+        int(bounds[3]), grid_inv[0], grid_inv[1], _pp(inv), _pp(sf), len(sf), float(log_scale_factor), float(mbf), nQ, _pp(qs),
+        _pp(qid), _pp(wx), _pp(wy), _pp(wz), _pp(mx), _pp(mn), _pp(nrm), _pp(qo), _pp(qd), float(th), added.ctypes.data,
+        repl.ctypes.data, srep.ctypes.data, shold.ctypes.data)
+    return n, added[:nQ], repl[:nQ], srep[:nT], shold[:nT]
+
+
+def o_fuse_sim3_apply(match_q, slot_state, slot_query):
+    """Result step of Fuse(KeyFrame*, Scw, ...) (eaoo_fuse_sim3_apply).  Returns (nFused, addedAt, replacePoint, slotHolder)."""
+    nQ, nT = len(match_q), len(slot_state)
+    TAG = 100000
+    slot = np.where(np.asarray(slot_query) >= 0, slot_query, np.where(np.asarray(slot_state) > 0, nQ + np.arange(nT), -1)).astype(np.int32)
+    bad = np.zeros(nQ + nT, np.uint8)
+    bad[nQ:] = np.asarray(slot_state) == 2
+    repl, added = np.full(max(nQ, 1), -1, np.int32), np.full(max(nQ, 1), -1, np.int32)
+    L = _mo()
+    ci, vp = C.c_int, C.c_void_p
+    L.eaoo_fuse_sim3_apply.argtypes = [ci, ci] + [vp] * 5
+    n = L.eaoo_fuse_sim3_apply(nT, nQ, _pp(_a(match_q, np.int32)), _pp(slot), _pp(bad), _pp(repl), _pp(added))
+    tag = lambda p: -1 if p < 0 else (int(p) if p < nQ else TAG + int(p) - nQ)
+    return n, added[:nQ], np.array([tag(p) for p in repl[:nQ]], np.int32), np.array([tag(p) for p in slot], np.int32)
+
+
+def r_fuse_sim3(KF, pts, th, *, bounds, grid_inv, scale_factors, log_scale_factor, scw_scale=1.0, L=None):
+    """KF: dict(x,y,octave,desc,slot_state,slot_query); pts: dict(wx,..,desc,bad).
+    Returns (nFused, addedAt, replacePoint, slotHolder)."""
+    tx, ty, to, td, _ = _kf_arrays(KF)
+    ss, sq = _a(KF["slot_state"], np.uint8), _a(KF["slot_query"], np.int32)
+    wx, wy, wz, mx, mn, nrm, qd = _pt_arrays(pts)
+    bad = _a(pts.get("bad"), np.uint8)
+    sf = _a(scale_factors, np.float32)
+    nT, nQ = len(tx), len(wx)
+    added, repl = np.full(max(nQ, 1), -1, np.int32), np.full(max(nQ, 1), -1, np.int32)
+    shold = np.full(max(nT, 1), -1, np.int32)
+    n = (L or match_ref_lib()).mref_fuse_sim3(
+        nT, _pp(tx), _pp(ty), _pp(to), _pp(td), _pp(ss), _pp(sq), int(bounds[0]), int(bounds[1]), int(bounds[2]), int(bounds[3]),
+        grid_inv[0], grid_inv[1], _pp(sf), len(sf), float(log_scale_factor), float(scw_scale), nQ, _pp(bad), _pp(wx), _pp(wy),
+        _pp(wz), _pp(mx), _pp(mn), _pp(nrm), _pp(qd), float(th), added.ctypes.data, repl.ctypes.data, shold.ctypes.data)
+    return n, added[:nQ], repl[:nQ], shold[:nT]
+
+
+def o_sim3_agreement(m1, m2):
+    m1, m2 = _a(m1, np.int32), _a(m2, np.int32)
+    out = np.full(max(len(m1), 1), -1, np.int32)
+    L = _mo()
+    L.eaoo_sim3_agreement.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    n = L.eaoo_sim3_agreement(len(m1), _pp(m1), len(m2), _pp(m2), out.ctypes.data)
+    return n, out[:len(m1)]
+
+
+def r_search_by_sim3(K1, K2, pre12, th, *, bounds, grid_inv, scale_factors, log_scale_factor, s12=1.0, L=None):
+    """Ka: dict(x,y,octave,desc, state, wx,wy,wz,max_dist,min_dist, pdesc).  Returns (nFound, match12)."""
+    def arrs(K):
+        return (_a(K["x"], np.float32), _a(K["y"], np.float32), _a(K["octave"], np.int32), _a(K["desc"], np.uint8),
+                _a(K["state"], np.uint8), _a(K["wx"], np.float32), _a(K["wy"], np.float32), _a(K["wz"], np.float32),
+                _a(K["max_dist"], np.float32), _a(K["min_dist"], np.float32), _a(K["pdesc"], np.uint8))
+    a1, a2 = arrs(K1), arrs(K2)
+    pre = _a(pre12, np.int32)
+    sf = _a(scale_factors, np.float32)
+    n1, n2 = len(a1[0]), len(a2[0])
+    m12 = np.full(max(n1, 1), -1, np.int32)
+    n = (L or match_ref_lib()).mref_search_by_sim3(
+        n1, *[_pp(a) for a in a1], n2, *[_pp(a) for a in a2], _pp(pre), int(bounds[0]), int(bounds[1]), int(bounds[2]),
+        int(bounds[3]), grid_inv[0], grid_inv[1], _pp(sf), len(sf), float(log_scale_factor), float(s12), float(th), m12.ctypes.data)
+    return n, m12[:n1]
+
+
+def o_distinctive_descriptor(desc):
+    d = _a(desc, np.uint8).reshape(-1, 32)
+    L = _mo()
+    L.eaoo_distinctive_descriptor.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    med = C.c_int(-1)
+    return L.eaoo_distinctive_descriptor(len(d), _pp(d), C.byref(med)), med.value

@@ -152,3 +152,112 @@ def init_scene(seed, n=1200):
     F2 = dict(x=x2[perm], y=y2[perm], octave=o2[perm], angle=a2[perm], desc=d2[perm])
     prev = np.stack([x1, y1], 1).astype(np.float32)
     return F1, F2, prev
+
+
+def _dist_range(x, y, lvl, scale=1.0):
+    """mfMaxDistance / mfMinDistance so that MapPoint::PredictScale gives lvl for the point (x, y, 1)*scale seen from
+    the origin (margin half a level), as kf_scene does."""
+    sf7 = np.float32(1.2) ** 7
+    d = scale * np.sqrt(np.asarray(x, np.float64) ** 2 + np.asarray(y, np.float64) ** 2 + 1.0)
+    max_dist = (d * 1.2 ** (np.asarray(lvl) - 0.5)).astype(np.float32)
+    return max_dist, (max_dist / sf7).astype(np.float32)
+
+
+def map_scene(seed, n=900, flags=False, stereo=False, noise=2.0):
+    """A keyframe of n features and n candidate map points given as world points (u, v, +-1) seen from an identity
+    pose, for the map-side matchers (SearchByProjection(KF,Scw), Fuse x2): distance ranges that put the predicted
+    level on or one above the paired feature's octave, viewing normals (some turned away), points behind the camera,
+    outside the image and outside their scale range."""
+    F, mp = window_scene(seed, n, stereo=stereo)
+    rng = np.random.Generator(np.random.PCG64(seed + 11))
+    if noise != 2.0:  # re-draw the projection noise around the paired features
+        mp["x"] = (mp["x"] + rng.normal(0, noise, n)).astype(np.float32)
+        mp["y"] = (mp["y"] + rng.normal(0, noise, n)).astype(np.float32)
+    wx, wy, wz = mp["x"].copy(), mp["y"].copy(), np.ones(n, np.float32)
+    max_dist, min_dist = _dist_range(wx, wy, mp["level"])
+    normal = np.stack([wx, wy, wz], 1).astype(np.float32)
+    bad = np.zeros(n, np.uint8)
+    if flags:
+        wz[rng.random(n) < 0.05] = -1.0
+        away = rng.random(n) < 0.08
+        normal[away] *= -1.0
+        far = rng.random(n) < 0.05
+        max_dist[far] = (max_dist[far] * 0.2).astype(np.float32)
+        bad = (rng.random(n) < 0.05).astype(np.uint8)
+    KF = dict(x=F["x"], y=F["y"], octave=F["octave"], desc=F["desc"])
+    if stereo:
+        KF["uright"] = F["uright"]
+    pts = dict(wx=wx, wy=wy, wz=wz, max_dist=max_dist, min_dist=min_dist, normal=normal, desc=mp["desc"], bad=bad)
+    return KF, pts
+
+
+def fuse_scene(seed, n=900, flags=True, stereo=False):
+    """map_scene + the keyframe's own map points (slot_state / slot_obs) and candidate states for
+    Fuse(KeyFrame*, vpMapPoints, th): NULL / bad / already-in-keyframe candidates, the same MapPoint* listed twice,
+    several candidates landing on one feature."""
+    KF, pts = map_scene(seed, n, flags=flags, stereo=stereo, noise=1.0)
+    rng = np.random.Generator(np.random.PCG64(seed + 13))
+    KF["slot_state"] = rng.choice(np.array([0, 1, 2], np.uint8), n, p=[0.5, 0.42, 0.08])
+    KF["slot_obs"] = rng.integers(1, 6, n).astype(np.int32)
+    state = np.where(pts["bad"] > 0, 1, 3).astype(np.uint8)
+    if flags:
+        state[rng.random(n) < 0.05] = 0
+        state[rng.random(n) < 0.05] = 2
+    qid = np.arange(n, dtype=np.int32)
+    dup = rng.permutation(np.arange(n // 2, n))[:40]           # later entries repeating an earlier MapPoint*
+    src = rng.integers(0, n // 2, 40)
+    for d, s in zip(dup, src):
+        qid[d] = s
+        for k in ("wx", "wy", "wz", "max_dist", "min_dist", "normal", "desc"):
+            pts[k][d] = pts[k][s]
+        state[d] = state[s]
+    # crowds: a few candidates copied next to another candidate so that they compete for one feature
+    crowd = rng.permutation(n // 2)[:40]
+    for c in crowd:
+        t = (c + 1) % (n // 2)
+        if qid[t] != t or qid[c] != c or np.any(qid[n // 2:] == t):
+            continue
+        for k in ("wx", "wy", "wz", "max_dist", "min_dist", "normal"):
+            pts[k][t] = pts[k][c]
+        pts["desc"][t] = pts["desc"][c] ^ np.packbits((rng.random(256) < 0.01).astype(np.uint8))
+    pts["state"], pts["qid"], pts["obs"] = state, qid, rng.integers(1, 6, n).astype(np.int32)
+    return KF, pts
+
+
+def sim3_scene(seed, n=800, flags=True):
+    """Two keyframes for SearchBySim3: KF2's features are KF1's moved by a few pixels (in another order) with noisy
+    descriptors; the map point held by a feature projects next to the paired feature of the other keyframe, so that
+    most pairs agree in both directions, some only in one, some on neither."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x1, y1 = rng.uniform(5, 635, n).astype(np.float32), rng.uniform(5, 475, n).astype(np.float32)
+    o1 = rng.integers(0, 7, n).astype(np.int32)
+    d1 = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    perm = rng.permutation(n)               # KF2 feature j pairs with KF1 feature perm[j]
+    x2 = (x1[perm] + rng.normal(0, 2, n)).astype(np.float32)
+    y2 = (y1[perm] + rng.normal(0, 2, n)).astype(np.float32)
+    o2 = o1[perm].copy()
+    flip = lambda d, p: d ^ np.packbits((rng.random((len(d), 256)) < p).astype(np.uint8), axis=1)
+    d2 = flip(d1[perm], 0.06)
+    inv = np.argsort(perm)                  # KF1 feature i pairs with KF2 feature inv[i]
+    def points(xo, yo, lvl_of_pair, dk):
+        wx = (xo + rng.normal(0, 1.5, n)).astype(np.float32)
+        wy = (yo + rng.normal(0, 1.5, n)).astype(np.float32)
+        lvl = np.clip(lvl_of_pair + rng.integers(0, 2, n), 0, 7)
+        mx, mn = _dist_range(wx, wy, lvl)
+        return dict(wx=wx, wy=wy, wz=np.ones(n, np.float32), max_dist=mx, min_dist=mn, pdesc=flip(dk, 0.03))
+    K1 = dict(x=x1, y=y1, octave=o1, desc=d1, **points(x2[inv], y2[inv], o2[inv], d1))
+    K2 = dict(x=x2, y=y2, octave=o2, desc=d2, **points(x1[perm], y1[perm], o1[perm], d2))
+    K1["state"] = np.full(n, 3, np.uint8)
+    K2["state"] = np.full(n, 3, np.uint8)
+    pre12 = np.full(n, -1, np.int32)
+    if flags:
+        K1["state"] = rng.choice(np.array([0, 1, 3], np.uint8), n, p=[0.1, 0.05, 0.85])
+        K2["state"] = rng.choice(np.array([0, 1, 3], np.uint8), n, p=[0.1, 0.05, 0.85])
+        pre = rng.permutation(n)[:60]
+        ok = K2["state"][inv[pre]] > 0
+        pre12[pre[ok]] = inv[pre[ok]]
+        # one-sided pairs: move the KF2 point of some pairs far away
+        lost = rng.permutation(n)[:80]
+        K2["wx"][lost] = rng.uniform(5, 635, 80).astype(np.float32)
+        K2["max_dist"][lost], K2["min_dist"][lost] = _dist_range(K2["wx"][lost], K2["wy"][lost], np.clip(o1[perm][lost], 0, 7))
+    return K1, K2, pre12

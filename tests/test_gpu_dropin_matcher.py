@@ -117,3 +117,55 @@ def test_search_for_initialization(libs, window):
         dn, dm, dp = po.r_search_for_initialization(F1, F2, prev, window, 0.9, True, bounds=_BOUNDS, grid_inv=_GINV, L=D)
         assert dn == rn and np.array_equal(dm, rm) and np.array_equal(dp, rp), (seed, dn, rn)
     assert rn > 0
+
+
+# ---- map-side matchers through the class interface: Fuse x2, SearchBySim3, SearchByProjection(KF,Scw) ---------------------
+@pytest.mark.parametrize("flags", [False, True])
+def test_search_by_projection_sim3kf(libs, flags):
+    from test_oracle_matcher_vs_ref import _KW, _LSF, sim3kf_case
+    po, D = libs
+    for seed in range(3):
+        KF, pts, _ = sim3kf_case(600 + seed, flags)
+        kw = dict(log_scale_factor=_LSF, scw_scale=2.0 if seed else 1.0, **_KW)
+        rn, rm = po.r_search_by_projection_sim3kf(KF, pts, 10, **kw)
+        dn, dm = po.r_search_by_projection_sim3kf(KF, pts, 10, L=D, **kw)
+        assert dn == rn and np.array_equal(dm, rm), (seed, dn, rn)
+    assert rn > 0
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_fuse(libs, stereo):
+    from test_oracle_matcher_vs_ref import _INV_SIGMA2, _KW, _LSF, fuse_case
+    po, D = libs
+    for seed in range(3):
+        KF, pts, _ = fuse_case(700 + seed, stereo)
+        kw = dict(inv_level_sigma2=_INV_SIGMA2, log_scale_factor=_LSF, mbf=20.0, **_KW)
+        r = po.r_fuse(KF, pts, 3.0, **kw)
+        d = po.r_fuse(KF, pts, 3.0, L=D, **kw)
+        assert d[0] == r[0] and all(np.array_equal(a, b) for a, b in zip(d[1:], r[1:])), (seed, d[0], r[0])
+    assert r[0] > 0
+
+
+def test_fuse_sim3(libs):
+    from test_oracle_matcher_vs_ref import _KW, _LSF, fuse_sim3_case
+    po, D = libs
+    for seed in range(3):
+        KF, pts, _ = fuse_sim3_case(800 + seed)
+        kw = dict(log_scale_factor=_LSF, scw_scale=4.0 if seed else 1.0, **_KW)
+        r = po.r_fuse_sim3(KF, pts, 4.0, **kw)
+        d = po.r_fuse_sim3(KF, pts, 4.0, L=D, **kw)
+        assert d[0] == r[0] and all(np.array_equal(a, b) for a, b in zip(d[1:], r[1:])), (seed, d[0], r[0])
+    assert r[0] > 0
+
+
+@pytest.mark.parametrize("flags", [False, True])
+def test_search_by_sim3(libs, flags):
+    from matchdata import sim3_scene
+    from test_oracle_matcher_vs_ref import _KW, _LSF
+    po, D = libs
+    for seed in range(3):
+        K1, K2, pre12 = sim3_scene(900 + seed, flags=flags)
+        rn, rm = po.r_search_by_sim3(K1, K2, pre12, 7.5, log_scale_factor=_LSF, **_KW)
+        dn, dm = po.r_search_by_sim3(K1, K2, pre12, 7.5, log_scale_factor=_LSF, L=D, **_KW)
+        assert dn == rn and np.array_equal(dm, rm), (seed, dn, rn)
+    assert rn > 0

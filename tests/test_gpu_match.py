@@ -354,3 +354,122 @@ def test_initialization(matcher_factory, window, ratio, ori):
         assert np.array_equal(m12, om) and np.array_equal(pm, op)
         total += on
     assert total > 300
+
+
+# ---- map-side matchers (src/ORBmatcher.cc:290-403, :825-1326) and ComputeDistinctiveDescriptors ---------------------------
+def _win_query(q, th, sf):
+    lvl = q["level"].astype(np.int32)
+    out = dict(u=q["u"], v=q["v"], radius=(np.float32(th) * sf[lvl]).astype(np.float32), min_level=lvl - 1, max_level=lvl,
+               desc=q["desc"], valid=q["valid"])
+    if "ur" in q:
+        out["ur"] = q["ur"]
+    return out
+
+
+@pytest.mark.parametrize("th", [5, 10])
+@pytest.mark.parametrize("flags", [False, True])
+def test_projection_sim3_keyframe(matcher_factory, th, flags):
+    """SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) = greedy window search, TH_LOW, no rotation check."""
+    from oracle import pyoracle as po
+    from test_oracle_matcher_vs_ref import _KW, _SF, sim3kf_case
+    m = matcher_factory(0.75)
+    total = 0
+    for seed in range(3):
+        KF, pts, q = sim3kf_case(600 + seed, flags)
+        on, om, od = po.o_search_by_projection_sim3kf(KF, q, th, **_KW)
+        F = dict(x=KF["x"], y=KF["y"], octave=KF["octave"], desc=KF["desc"], taken=KF["matched"])
+        n, match, dist = m.SearchWindows(0, F, _win_query(q, th, _SF), 50, 0, False, bounds=_KW["bounds"], grid_inv=_KW["grid_inv"])
+        assert n == on, (seed, n, on)
+        assert np.array_equal(match, om) and np.array_equal(dist, od), seed
+        total += on
+    assert total > 100
+
+
+@pytest.mark.parametrize("th", [3.0, 6.0])
+@pytest.mark.parametrize("stereo", [False, True])
+def test_fuse_search(matcher_factory, th, stereo):
+    """The search step of Fuse(KeyFrame*, vpMapPoints, th) with the reprojection chi-square gate."""
+    from oracle import pyoracle as po
+    from test_oracle_matcher_vs_ref import _INV_SIGMA2, _KW, _SF, fuse_case
+    m = matcher_factory(0.6)
+    total = 0
+    for seed in range(3):
+        KF, pts, q = fuse_case(700 + seed, stereo)
+        on, om, od = po.o_window_best(1, KF, q, th, 50, inv_level_sigma2=_INV_SIGMA2, **_KW)
+        n, match, dist = m.SearchWindowsIndependent(1, KF, _win_query(q, th, _SF), 50, bounds=_KW["bounds"],
+                                                    grid_inv=_KW["grid_inv"], inv_level_sigma2=_INV_SIGMA2)
+        assert n == on, (seed, n, on)
+        assert np.array_equal(match, om) and np.array_equal(dist, od), seed
+        total += on
+    assert total > 100
+
+
+@pytest.mark.parametrize("th,accept", [(4.0, 50), (10.0, 50), (7.5, 100)])
+def test_independent_windows_no_gate(matcher_factory, th, accept):
+    """The search step of Fuse(KeyFrame*, Scw, ...) (TH_LOW) and of one SearchBySim3 direction (TH_HIGH)."""
+    from oracle import pyoracle as po
+    from test_oracle_matcher_vs_ref import _KW, _SF, fuse_sim3_case
+    m = matcher_factory(0.6)
+    total = 0
+    for seed in range(3):
+        KF, pts, q = fuse_sim3_case(800 + seed)
+        on, om, od = po.o_window_best(0, KF, q, th, accept, **_KW)
+        n, match, dist = m.SearchWindowsIndependent(0, KF, _win_query(q, th, _SF), accept, bounds=_KW["bounds"], grid_inv=_KW["grid_inv"])
+        assert n == on and np.array_equal(match, om) and np.array_equal(dist, od), (seed, n, on)
+        total += on
+    assert total > 100
+
+
+def test_search_by_sim3_both_directions(matcher_factory):
+    from matchdata import sim3_scene
+    from oracle import pyoracle as po
+    from test_oracle_matcher_vs_ref import _KW, _SF, sim3_queries
+    m = matcher_factory(0.75)
+    for seed in range(2):
+        K1, K2, pre12 = sim3_scene(900 + seed, flags=True)
+        q1, q2 = sim3_queries(K1, K2, pre12)
+        g1 = m.SearchWindowsIndependent(0, K2, _win_query(q1, 7.5, _SF), 100, bounds=_KW["bounds"], grid_inv=_KW["grid_inv"])[1]
+        g2 = m.SearchWindowsIndependent(0, K1, _win_query(q2, 7.5, _SF), 100, bounds=_KW["bounds"], grid_inv=_KW["grid_inv"])[1]
+        o1 = po.o_window_best(0, K2, q1, 7.5, 100, **_KW)[1]
+        o2 = po.o_window_best(0, K1, q2, 7.5, 100, **_KW)[1]
+        assert np.array_equal(g1, o1) and np.array_equal(g2, o2), seed
+        assert po.o_sim3_agreement(g1, g2)[0] > 100
+
+
+def test_independent_windows_edge_cases(matcher_factory):
+    m = matcher_factory(0.6)
+    e = np.zeros(0, np.float32)
+    KF = dict(x=e, y=e, octave=np.zeros(0, np.int32), desc=np.zeros((0, 32), np.uint8))
+    q = dict(u=np.float32([10]), v=np.float32([10]), radius=np.float32([5]), min_level=np.int32([0]), max_level=np.int32([1]),
+             desc=np.zeros((1, 32), np.uint8))
+    n, match, dist = m.SearchWindowsIndependent(0, KF, q, 50, bounds=(0, 640, 0, 480), grid_inv=(0.1, 0.1))
+    assert n == 0 and match.tolist() == [-1]
+    # two identical targets in one cell: the first in grid order wins; a target exactly at the radius is outside
+    KF = dict(x=np.float32([10, 10, 15]), y=np.float32([10, 10, 10]), octave=np.int32([0, 0, 0]), desc=np.zeros((3, 32), np.uint8))
+    KF["desc"][2] = 0
+    n, match, dist = m.SearchWindowsIndependent(0, KF, q, 50, bounds=(0, 640, 0, 480), grid_inv=(0.1, 0.1))
+    assert n == 1 and match.tolist() == [0] and dist.tolist() == [0]
+    q["u"] = np.float32([20])  # only target 2 at |dx| = 5 = r: not < r
+    n, match, _ = m.SearchWindowsIndependent(0, KF, q, 50, bounds=(0, 640, 0, 480), grid_inv=(0.1, 0.1))
+    assert n == 0 and match.tolist() == [-1]
+
+
+def test_distinctive_descriptors(matcher_factory):
+    from oracle import pyoracle as po
+    rng = np.random.Generator(np.random.PCG64(5))
+    sizes = [0, 1, 2, 3, 4, 5, 8, 31, 32, 33, 64, 100, 257, 600] + rng.integers(1, 40, 400).tolist()
+    descs = []
+    for n in sizes:
+        base = rng.integers(0, 256, size=(1, 32), dtype=np.uint8)
+        d = base ^ np.packbits((rng.random((n, 256)) < rng.uniform(0.0, 0.3, (n, 1))).astype(np.uint8), axis=1)
+        if n > 3:
+            d[n - 1] = d[0]
+        descs.append(d)
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    allrows = np.concatenate(descs)
+    for max_features in (4096, 400):  # the small handle forces the chunked path
+        m = matcher_factory(0.6, max_features=max_features)
+        best, med = m.DistinctiveDescriptors(starts, allrows)
+        for p, d in enumerate(descs):
+            ob, om = po.o_distinctive_descriptor(d)
+            assert best[p] == ob and (ob < 0 or med[p] == om), (p, len(d), best[p], ob)

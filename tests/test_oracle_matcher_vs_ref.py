@@ -163,3 +163,148 @@ def test_search_for_initialization(window, ratio, ori):
         assert rn == on and np.array_equal(rm, om) and np.array_equal(rp, op), (seed, rn, on)
         total += on
     assert total > 300
+
+
+# ---- map-side matchers: SearchByProjection(KF,Scw), Fuse x2, SearchBySim3 (src/ORBmatcher.cc:290-403, :825-1326) ----------
+_LSF = float(np.log(np.float32(1.2)))
+_INV_SIGMA2 = (np.float32(1.0) / (_SF * _SF)).astype(np.float32)
+_KW = dict(bounds=_BOUNDS, grid_inv=_GINV, scale_factors=_SF)
+
+
+def sim3kf_case(seed, flags):
+    """(KF with matched / matched_q, pts, q) for SearchByProjection(KF,Scw)."""
+    from matchdata import map_scene
+    KF, pts = map_scene(seed, flags=flags)
+    n = len(KF["x"])
+    rng = np.random.Generator(np.random.PCG64(seed + 17))
+    mq = np.full(n, -1, np.int32)
+    if flags:
+        k = rng.permutation(n)
+        mq[k[:40]] = -2
+        mq[k[40:80]] = rng.permutation(n)[:40]
+    KF["matched_q"], KF["matched"] = mq, (mq != -1).astype(np.uint8)
+    valid, u, v, lvl = po.map_projection(pts, _LSF, 8, bounds=_BOUNDS)
+    valid &= (1 - pts["bad"])
+    valid[mq[mq >= 0]] = 0
+    return KF, pts, dict(valid=valid, u=u, v=v, level=lvl, desc=pts["desc"])
+
+
+@pytest.mark.parametrize("th", [5, 10])
+@pytest.mark.parametrize("flags", [False, True])
+def test_search_by_projection_sim3kf(th, flags):
+    total = 0
+    for seed in range(3):
+        KF, pts, q = sim3kf_case(600 + seed, flags)
+        on, om, _ = po.o_search_by_projection_sim3kf(KF, q, th, **_KW)
+        rn, rm = po.r_search_by_projection_sim3kf(KF, pts, th, log_scale_factor=_LSF, scw_scale=2.0 if seed else 1.0, **_KW)
+        assert rn == on, (seed, rn, on)
+        assert np.array_equal(rm, np.where(om >= 0, om, KF["matched_q"])), seed
+        total += on
+    assert total > 100
+
+
+def fuse_case(seed, stereo, mbf=20.0):
+    from matchdata import fuse_scene
+    KF, pts = fuse_scene(seed, stereo=stereo)
+    valid, u, v, lvl = po.map_projection(pts, _LSF, 8, bounds=_BOUNDS)
+    valid &= (pts["state"] == 3)
+    q = dict(valid=valid, u=u, v=v, level=lvl, desc=pts["desc"], ur=(u - np.float32(mbf)).astype(np.float32))
+    return KF, pts, q
+
+
+@pytest.mark.parametrize("th", [3.0, 6.0])
+@pytest.mark.parametrize("stereo", [False, True])
+def test_fuse(th, stereo):
+    total = replaced = gated = 0
+    for seed in range(3):
+        KF, pts, q = fuse_case(700 + seed, stereo)
+        _, mq, _ = po.o_window_best(1, KF, q, th, 50, inv_level_sigma2=_INV_SIGMA2, **_KW)
+        gated += int(np.sum(po.o_window_best(0, KF, q, th, 50, **_KW)[1] != mq))
+        o = po.o_fuse_apply(mq, pts["state"], pts["qid"], pts["obs"], KF["slot_state"], KF["slot_obs"])
+        r = po.r_fuse(KF, pts, th, inv_level_sigma2=_INV_SIGMA2, log_scale_factor=_LSF, mbf=20.0, **_KW)
+        assert r[0] == o[0], (seed, r[0], o[0])
+        for a, b, name in zip(r[1:], o[1:], ("addedAt", "replacedBy", "slotReplacedBy", "slotHolder")):
+            assert np.array_equal(a, b), (seed, name)
+        total += o[0]
+        replaced += int(np.sum(o[2] >= 0) + np.sum(o[3] >= 0))
+    assert total > 100 and replaced > 10 and gated > 0  # the chi-square gate and both Replace directions were exercised
+
+
+def fuse_sim3_case(seed):
+    from matchdata import map_scene
+    KF, pts = map_scene(seed, flags=True, noise=1.0)
+    n = len(KF["x"])
+    rng = np.random.Generator(np.random.PCG64(seed + 19))
+    KF["slot_state"] = rng.choice(np.array([0, 1, 2], np.uint8), n, p=[0.5, 0.42, 0.08])
+    sq = np.full(n, -1, np.int32)
+    k = rng.permutation(n)[:40]
+    sq[k] = rng.permutation(n)[:40]
+    sq[k[pts["bad"][sq[k]] > 0]] = -1  # KeyFrame::GetMapPoints leaves bad points out; keep the case unambiguous
+    KF["slot_query"] = sq
+    valid, u, v, lvl = po.map_projection(pts, _LSF, 8, bounds=_BOUNDS)
+    valid &= (1 - pts["bad"])
+    valid[sq[sq >= 0]] = 0
+    return KF, pts, dict(valid=valid, u=u, v=v, level=lvl, desc=pts["desc"])
+
+
+@pytest.mark.parametrize("th", [4.0, 10.0])
+def test_fuse_sim3(th):
+    total = repl = 0
+    for seed in range(3):
+        KF, pts, q = fuse_sim3_case(800 + seed)
+        _, mq, _ = po.o_window_best(0, KF, q, th, 50, **_KW)
+        o = po.o_fuse_sim3_apply(mq, KF["slot_state"], KF["slot_query"])
+        r = po.r_fuse_sim3(KF, pts, th, log_scale_factor=_LSF, scw_scale=4.0 if seed else 1.0, **_KW)
+        assert r[0] == o[0], (seed, r[0], o[0])
+        for a, b, name in zip(r[1:], o[1:], ("addedAt", "replacePoint", "slotHolder")):
+            assert np.array_equal(a, b), (seed, name)
+        total += o[0]
+        repl += int(np.sum(o[2] >= 0))
+    assert total > 100 and repl > 10
+
+
+def sim3_queries(K1, K2, pre12):
+    """Post-projection query arrays of both directions of SearchBySim3 (s12 = 1, R12 = I, t12 = 0)."""
+    def direction(K, done):
+        valid, u, v, lvl = po.map_projection(K, _LSF, 8, bounds=_BOUNDS, check_normal=False)
+        valid &= (K["state"] == 3) & ~done
+        return dict(valid=valid, u=u, v=v, level=lvl, desc=K["pdesc"])
+    done1 = pre12 >= 0
+    done2 = np.zeros(len(K2["x"]), bool)
+    done2[pre12[done1]] = True
+    return direction(K1, done1), direction(K2, done2)
+
+
+@pytest.mark.parametrize("th", [7.5, 3.0])
+@pytest.mark.parametrize("flags", [False, True])
+def test_search_by_sim3(th, flags):
+    from matchdata import sim3_scene
+    total = onesided = 0
+    for seed in range(3):
+        K1, K2, pre12 = sim3_scene(900 + seed, flags=flags)
+        q1, q2 = sim3_queries(K1, K2, pre12)
+        _, m1, _ = po.o_window_best(0, K2, q1, th, 100, **_KW)
+        _, m2, _ = po.o_window_best(0, K1, q2, th, 100, **_KW)
+        on, om = po.o_sim3_agreement(m1, m2)
+        rn, rm = po.r_search_by_sim3(K1, K2, pre12, th, log_scale_factor=_LSF, **_KW)
+        assert rn == on, (seed, rn, on)
+        assert np.array_equal(rm, np.where(om >= 0, om, pre12)), seed
+        total += on
+        onesided += int(np.sum(m1 >= 0)) - on
+    assert total > 300 and (onesided > 0 or not flags)
+
+
+def test_distinctive_descriptor_restatement():
+    """eaoo_distinctive_descriptor (src/MapPoint.cc:273-301) against a numpy restatement: N x N distances, row medians at
+    index int(0.5*(N-1)) of the sorted row, first minimum."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    for n in [1, 2, 3, 4, 7, 20, 33, 64, 150]:
+        base = rng.integers(0, 256, size=(1, 32), dtype=np.uint8)
+        d = base ^ np.packbits((rng.random((n, 256)) < rng.uniform(0.02, 0.3, (n, 1))).astype(np.uint8), axis=1)
+        if n > 3:
+            d[n // 2] = d[0]  # ties between rows
+        D = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2)
+        med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
+        best, m = po.o_distinctive_descriptor(d)
+        assert best == int(np.argmin(med)) and m == int(med.min()), n
+    assert po.o_distinctive_descriptor(np.zeros((0, 32), np.uint8))[0] == -1
