@@ -6,7 +6,9 @@
 // Float products accumulate in double and round once, like cv::gemm's GEMMSingleMul<float,double>; the parity tests
 // use identity rotations / zero translations on the paths they pin, so no result depends on that choice.
 #pragma once
+#include <algorithm>  // <opencv2/core/core.hpp> brings these in; src/MapPoint.cc relies on it (sort, INT_MAX)
 #include <cassert>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>

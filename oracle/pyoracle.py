@@ -842,3 +842,29 @@ def o_distinctive_descriptor(desc):
     L.eaoo_distinctive_descriptor.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_int)]
     med = C.c_int(-1)
     return L.eaoo_distinctive_descriptor(len(d), _pp(d), C.byref(med)), med.value
+
+
+MAPPOINT_REF_SO = os.path.join(HERE, "_ref", "libmappoint_ref.so")
+_mpref = None
+
+
+def mappoint_ref_lib():
+    """The unmodified reference MapPoint.cc (+ ORBmatcher.cc) behind oracle/mappoint_ref_harness.cc."""
+    global _mpref
+    if _mpref is None:
+        if not os.path.exists(MAPPOINT_REF_SO):
+            subprocess.check_call(["make", "-s", "-C", HERE, "mappointref"])
+        _mpref = C.CDLL(MAPPOINT_REF_SO)
+        _mpref.mpref_distinctive_descriptor.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _mpref.mpref_predict_scale.argtypes = [C.c_float] * 4
+    return _mpref
+
+
+def r_distinctive_descriptor(desc, kf_bad=None):
+    """MapPoint::ComputeDistinctiveDescriptors of the reference on n observations.  Returns (index of the chosen
+    observation or -1, the 32 descriptor bytes the map point holds afterwards)."""
+    d = _a(desc, np.uint8).reshape(-1, 32)
+    bad = _a(kf_bad, np.uint8)
+    out = np.zeros(32, np.uint8)
+    i = mappoint_ref_lib().mpref_distinctive_descriptor(len(d), _pp(d), _pp(bad), out.ctypes.data)
+    return i, out

@@ -308,3 +308,33 @@ def test_distinctive_descriptor_restatement():
         best, m = po.o_distinctive_descriptor(d)
         assert best == int(np.argmin(med)) and m == int(med.min()), n
     assert po.o_distinctive_descriptor(np.zeros((0, 32), np.uint8))[0] == -1
+
+
+def test_distinctive_descriptor_vs_reference_mappoint():
+    """The restatement against the UNMODIFIED reference MapPoint.cc (oracle/_ref/libmappoint_ref.so): same chosen
+    observation, with ties between rows, duplicate descriptors and bad keyframes (skipped at src/MapPoint.cc:265)."""
+    rng = np.random.Generator(np.random.PCG64(78))
+    for trial, n in enumerate([1, 2, 3, 4, 5, 6, 9, 16, 31, 32, 33, 64, 101, 200] * 3):
+        base = rng.integers(0, 256, size=(1, 32), dtype=np.uint8)
+        d = base ^ np.packbits((rng.random((n, 256)) < rng.uniform(0.0, 0.3, (n, 1))).astype(np.uint8), axis=1)
+        if n > 3:
+            d[n - 1] = d[1]
+        bad = (rng.random(n) < 0.2).astype(np.uint8) if trial % 3 == 2 else np.zeros(n, np.uint8)
+        ri, rdesc = po.r_distinctive_descriptor(d, bad)
+        good = np.nonzero(bad == 0)[0]
+        ob, _ = po.o_distinctive_descriptor(d[good])
+        if ob < 0:
+            assert ri == -1 and np.all(rdesc == 0xA5), (trial, n)  # no usable observation: descriptor untouched
+        else:
+            assert ri == good[ob] and np.array_equal(rdesc, d[good[ob]]), (trial, n, ri, good[ob])
+
+
+def test_predict_scale_of_the_real_mappoint_equals_the_standin():
+    """matchshim's MapPoint::PredictScale (used by libmatch_ref.so) against the reference's own MapPoint.cc."""
+    L, M = po.match_ref_lib(), po.mappoint_ref_lib()
+    rng = np.random.Generator(np.random.PCG64(79))
+    lsf = float(np.log(np.float32(1.2)))
+    for _ in range(2000):
+        d0, sc, cur = (float(np.float32(v)) for v in (rng.uniform(0.5, 20), rng.uniform(1, 3.6), rng.uniform(0.3, 40)))
+        max_dist = float(np.float32(d0) * np.float32(sc))  # MapPoint(Pos, pMap, pFrame, idxF): mfMaxDistance = dist*levelScaleFactor
+        assert M.mpref_predict_scale(d0, sc, cur, lsf) == L.mref_predict_scale(max_dist, cur, lsf)
