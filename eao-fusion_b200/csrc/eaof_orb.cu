@@ -69,6 +69,10 @@ struct eaof_orb {
     int kpCap = 0;
     // device
     uint8_t* dIn = nullptr;      // staging for host-input calls: max_batch frames
+    uint8_t* dAux = nullptr;     // lazily allocated staging for host colour frames / host depth maps
+    size_t auxBytes = 0;
+    float *dURight = nullptr, *dDepthKp = nullptr;  // ComputeStereoFromRGBD outputs, [max_batch][kpCap], lazily allocated
+    int colorCh = 0, colorK[3] = {0, 0, 0}, colorShift = 0;  // set by the colour entry points around run_batch
     uint8_t* dPyr = nullptr;     // max_batch pyramid blocks
     uint8_t* dBlur = nullptr;    // same layout, blurred inner levels
     int* dTabs = nullptr;        // resize coefficient tables
@@ -285,7 +289,12 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     {
         const LevelGeom& L = g.L[0];
         dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
-        eaof::k_level0<<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g);
+        if (c->colorCh == 3)
+            eaof::k_level0_color<3><<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g, c->colorK[0], c->colorK[1], c->colorK[2], c->colorShift);
+        else if (c->colorCh == 4)
+            eaof::k_level0_color<4><<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g, c->colorK[0], c->colorK[1], c->colorK[2], c->colorShift);
+        else
+            eaof::k_level0<<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g);
         ++launches;
     }
     for (int l = 1; l < g.nlevels; ++l) {
@@ -509,6 +518,7 @@ void eaof_orb_destroy(eaof_orb* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->dAux); cudaFree(c->dURight); cudaFree(c->dDepthKp);
     cudaFree(c->dIn); cudaFree(c->dPyr); cudaFree(c->dBlur); cudaFree(c->dTabs); cudaFree(c->dAngleTab); cudaFree(c->dCells);
     cudaFree(c->dCand); cudaFree(c->dLabel); cudaFree(c->dCandCount); cudaFree(c->dSlotXY); cudaFree(c->dSlotScore);
     cudaFree(c->dLvlCount); cudaFree(c->dKps); cudaFree(c->dDesc); cudaFree(c->dKpCount);
@@ -557,6 +567,106 @@ int eaof_orb_extract_batch_device(eaof_orb* c, const uint8_t* dImgs, int n, int 
     if (!dImgs || stride < (size_t)width) return fail(EAOF_ERR_ARG, "bad image pointer/stride");
     CK(cudaSetDevice(c->device));
     return run_batch(c, dImgs, n, stride, framePitch);
+}
+
+namespace {
+int set_color(eaof_orb* c, int color, int grayMode) {
+    if (color < EAOF_COLOR_BGR || color > EAOF_COLOR_RGBA) return fail(EAOF_ERR_ARG, "unknown colour layout");
+    if (grayMode != EAOF_GRAY_CV331 && grayMode != EAOF_GRAY_CV4) return fail(EAOF_ERR_ARG, "unknown gray_mode");
+    // OpenCV RGB2Gray<uchar>: B2Y, G2Y, R2Y at yuv_shift 14 (3.3.1) / BY15, GY15, RY15 at 15 bits (4.x)
+    const int kB = grayMode == EAOF_GRAY_CV331 ? 1868 : 3735, kG = grayMode == EAOF_GRAY_CV331 ? 9617 : 19235,
+              kR = grayMode == EAOF_GRAY_CV331 ? 4899 : 9798;
+    const bool rgb = color == EAOF_COLOR_RGB || color == EAOF_COLOR_RGBA;
+    c->colorCh = (color == EAOF_COLOR_BGRA || color == EAOF_COLOR_RGBA) ? 4 : 3;
+    c->colorK[0] = rgb ? kR : kB; c->colorK[1] = kG; c->colorK[2] = rgb ? kB : kR;
+    c->colorShift = grayMode == EAOF_GRAY_CV331 ? 14 : 15;
+    return EAOF_OK;
+}
+int need_aux(eaof_orb* c, size_t bytes) {
+    if (c->auxBytes >= bytes) return EAOF_OK;
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(c->dAux);
+    c->dAux = nullptr; c->auxBytes = 0;
+    CK(cudaMalloc(&c->dAux, bytes));
+    c->auxBytes = bytes;
+    return EAOF_OK;
+}
+}  // namespace
+
+int eaof_orb_extract_batch_device_color(eaof_orb* c, const uint8_t* dImgs, int n, int width, int height, size_t stride,
+                                        size_t framePitch, int color, int grayMode) {
+    int rc = check_shape(c, width, height, n);
+    if (rc) return rc;
+    if ((rc = set_color(c, color, grayMode))) return rc;
+    if (!dImgs || stride < (size_t)width * c->colorCh) { c->colorCh = 0; return fail(EAOF_ERR_ARG, "bad image pointer/stride"); }
+    CK(cudaSetDevice(c->device));
+    rc = run_batch(c, dImgs, n, stride, framePitch);
+    c->colorCh = 0;
+    return rc;
+}
+
+int eaof_orb_extract_batch_color(eaof_orb* c, const uint8_t* imgs, int n, int width, int height, size_t stride,
+                                 size_t framePitch, int color, int grayMode, eaof_kp* kps, uint8_t* desc, int cap, int* nOut) {
+    int rc = check_shape(c, width, height, n);
+    if (rc) return rc;
+    if (!imgs || !nOut) return fail(EAOF_ERR_ARG, "bad argument");
+    const int ch = (color == EAOF_COLOR_BGRA || color == EAOF_COLOR_RGBA) ? 4 : 3;
+    if (stride < (size_t)width * ch) return fail(EAOF_ERR_ARG, "bad stride");
+    CK(cudaSetDevice(c->device));
+    const size_t rowBytes = (size_t)width * ch, tight = rowBytes * height;
+    if ((rc = need_aux(c, tight * n))) return rc;
+    for (int f = 0; f < n; ++f)
+        CK(cudaMemcpy2DAsync(c->dAux + (size_t)f * tight, rowBytes, imgs + (size_t)f * framePitch, stride, rowBytes, height,
+                             cudaMemcpyHostToDevice, c->stream));
+    if ((rc = eaof_orb_extract_batch_device_color(c, c->dAux, n, width, height, rowBytes, tight, color, grayMode))) return rc;
+    return eaof_orb_fetch_results(c, n, kps, desc, cap, nOut);
+}
+
+int eaof_orb_stereo_from_rgbd_device(eaof_orb* c, int n, const void* dDepth, int depthType, float depthScale,
+                                     size_t strideBytes, size_t framePitchBytes, const float* dXUn, float mbf,
+                                     float* dURight, float* dDepthOut) {
+    if (!c || !dDepth || !dURight || !dDepthOut || n < 1 || n > c->p.max_batch) return fail(EAOF_ERR_ARG, "bad argument");
+    if (depthType != EAOF_DEPTH_F32 && depthType != EAOF_DEPTH_U16) return fail(EAOF_ERR_ARG, "unknown depth_type");
+    CK(cudaSetDevice(c->device));
+    const dim3 gr((c->kpCap + 255) / 256, n);
+    if (depthType == EAOF_DEPTH_U16)
+        eaof::k_stereo_from_rgbd<true><<<gr, 256, 0, c->stream>>>(c->dKps, c->dKpCount, c->kpCap, dDepth, strideBytes, framePitchBytes,
+                                                                  depthScale, c->p.width, c->p.height, dXUn, mbf, dURight, dDepthOut);
+    else
+        eaof::k_stereo_from_rgbd<false><<<gr, 256, 0, c->stream>>>(c->dKps, c->dKpCount, c->kpCap, dDepth, strideBytes, framePitchBytes,
+                                                                   depthScale, c->p.width, c->p.height, dXUn, mbf, dURight, dDepthOut);
+    CK(cudaGetLastError());
+    return EAOF_OK;
+}
+
+int eaof_orb_stereo_from_rgbd(eaof_orb* c, int n, const void* depth, int depthType, float depthScale, size_t strideBytes,
+                              size_t framePitchBytes, float mbf, float* uRight, float* depthOut, int cap) {
+    if (!c || !depth || !uRight || !depthOut || n < 1 || n > c->p.max_batch) return fail(EAOF_ERR_ARG, "bad argument");
+    if (depthType != EAOF_DEPTH_F32 && depthType != EAOF_DEPTH_U16) return fail(EAOF_ERR_ARG, "unknown depth_type");
+    const size_t px = depthType == EAOF_DEPTH_U16 ? 2 : 4, rowBytes = px * c->p.width, tight = rowBytes * c->p.height;
+    if (strideBytes < rowBytes) return fail(EAOF_ERR_ARG, "bad stride");
+    CK(cudaSetDevice(c->device));
+    int rc = need_aux(c, tight * n);
+    if (rc) return rc;
+    const size_t outN = (size_t)c->p.max_batch * c->kpCap;
+    if (!c->dURight) { CK(cudaMalloc(&c->dURight, sizeof(float) * outN)); CK(cudaMalloc(&c->dDepthKp, sizeof(float) * outN)); }
+    for (int f = 0; f < n; ++f)
+        CK(cudaMemcpy2DAsync(c->dAux + (size_t)f * tight, rowBytes, static_cast<const uint8_t*>(depth) + (size_t)f * framePitchBytes,
+                             strideBytes, rowBytes, c->p.height, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = eaof_orb_stereo_from_rgbd_device(c, n, c->dAux, depthType, depthScale, rowBytes, tight, nullptr, mbf, c->dURight, c->dDepthKp)))
+        return rc;
+    std::vector<float> hu((size_t)n * c->kpCap), hd((size_t)n * c->kpCap);
+    std::vector<int> cnt(n);
+    CK(cudaMemcpyAsync(hu.data(), c->dURight, sizeof(float) * hu.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(hd.data(), c->dDepthKp, sizeof(float) * hd.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(cnt.data(), c->dKpCount, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int f = 0; f < n; ++f) {
+        if (cnt[f] > cap) return fail(EAOF_ERR_ARG, "frame %d has %d keypoints but cap is %d", f, cnt[f], cap);
+        memcpy(uRight + (size_t)f * cap, hu.data() + (size_t)f * c->kpCap, sizeof(float) * cnt[f]);
+        memcpy(depthOut + (size_t)f * cap, hd.data() + (size_t)f * c->kpCap, sizeof(float) * cnt[f]);
+    }
+    return EAOF_OK;
 }
 
 int eaof_orb_sync(eaof_orb* c) {

@@ -51,6 +51,77 @@ __global__ void __launch_bounds__(256) k_level0(const uint8_t* __restrict__ in, 
     *reinterpret_cast<uint32_t*>(pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)by * L.pitch + c0) = v;
 }
 
+// Colour ingest: cv::cvtColor(RGB/BGR/RGBA/BGRA -> GRAY) on 8U (src/Tracking.cc:324-337, OpenCV RGB2Gray<uchar>) fused
+// with the level-0 copyMakeBorder.  gray = (c0*k0 + c1*k1 + c2*k2 + 2^(shift-1)) >> shift with the coefficients in
+// channel order (the caller swaps them for RGB vs BGR); alpha is ignored.  Same work decomposition as k_level0.
+template <int CH>
+__global__ void __launch_bounds__(256) k_level0_color(const uint8_t* __restrict__ in, size_t framePitch, size_t stride,
+                                                      uint8_t* __restrict__ pyr, const __grid_constant__ Geom g, int k0,
+                                                      int k1, int k2, int shift) {
+    const LevelGeom& L = g.L[0];
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int by = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.z;
+    const int c0 = 12 + 4 * wi;
+    if (by >= L.rows || c0 >= L.w + 52) return;
+    const int y = reflect101(by - EAOF_EDGE, L.h);
+    const uint8_t* src = in + (size_t)f * framePitch + (size_t)y * stride;
+    const int bx = c0 - EAOF_INNER_X0;
+    const int rnd = 1 << (shift - 1);
+    uint32_t v = 0;
+    if (bx >= 0 && bx + 3 < L.w && ((reinterpret_cast<uintptr_t>(src + (size_t)bx * CH) & (CH == 4 ? 15 : 3)) == 0)) {
+        uint32_t w[CH];  // 4 pixels = CH aligned words
+        if (CH == 4) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)bx * 4));
+            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[CH - 1] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) w[j] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)bx * 3) + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int c[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int b = j * CH + k;
+                c[k] = (w[b >> 2] >> (8 * (b & 3))) & 0xff;
+            }
+            v |= (uint32_t)((c[0] * k0 + c[1] * k1 + c[2] * k2 + rnd) >> shift) << (8 * j);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint8_t* p = src + (size_t)reflect101(bx + j, L.w) * CH;
+            v |= (uint32_t)(((int)__ldg(p) * k0 + (int)__ldg(p + 1) * k1 + (int)__ldg(p + 2) * k2 + rnd) >> shift) << (8 * j);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)by * L.pitch + c0) = v;
+}
+
+// Frame::ComputeStereoFromRGBD (src/Frame.cc:1016-1037) over the keypoints a handle holds on the device: depth at the
+// (truncated) raw keypoint position, mvDepth = d and mvuRight = x_undistorted - mbf/d where d > 0, -1 elsewhere.
+// U16: raw sensor depth converted like Tracking's imDepth.convertTo(CV_32F, mDepthMapFactor) (src/Tracking.cc:340-341).
+template <bool U16>
+__global__ void __launch_bounds__(256) k_stereo_from_rgbd(const eaof_kp* __restrict__ kps, const int* __restrict__ counts,
+                                                          int cap, const void* __restrict__ depth, size_t strideBytes,
+                                                          size_t framePitchBytes, float depthScale, int w, int h,
+                                                          const float* __restrict__ xUn, float mbf,
+                                                          float* __restrict__ uRight, float* __restrict__ depthOut) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[f]) return;
+    const size_t o = (size_t)f * cap + i;
+    const eaof_kp kp = kps[o];
+    const int u = (int)kp.x, v = (int)kp.y;  // cv::Mat::at<float>(float, float): implicit conversion, truncation
+    float d = -1.f;
+    if (u >= 0 && u < w && v >= 0 && v < h) {
+        const uint8_t* row = static_cast<const uint8_t*>(depth) + (size_t)f * framePitchBytes + (size_t)v * strideBytes;
+        d = U16 ? __fmul_rn((float)reinterpret_cast<const uint16_t*>(row)[u], depthScale) : reinterpret_cast<const float*>(row)[u];
+    }
+    const bool ok = d > 0;
+    depthOut[o] = ok ? d : -1.f;
+    uRight[o] = ok ? __fsub_rn(xUn ? xUn[o] : kp.x, __fdiv_rn(mbf, d)) : -1.f;
+}
+
 // cv::resize 8UC1 INTER_LINEAR with 11-bit fixed-point coefficients; the border pixel at
 // bordered position (bx,by) equals the resized pixel at the reflected inner position, so resize and
 // copyMakeBorder are one pass.  tabs: per destination column [sx, a0|a1<<16], per row [sy, b0|b1<<16].

@@ -52,6 +52,10 @@ def lib():
         L.eaof_orb_set_pipeline_chunk.argtypes = [vp, ci]
         L.eaof_orb_extract_batch_device.argtypes = [vp, vp, ci, ci, ci, sz, sz]
         L.eaof_orb_sync.argtypes = [vp]
+        L.eaof_orb_extract_batch_device_color.argtypes = [vp, vp, ci, ci, ci, sz, sz, ci, ci]
+        L.eaof_orb_extract_batch_color.argtypes = [vp, vp, ci, ci, ci, sz, sz, ci, ci, vp, vp, ci, vp]
+        L.eaof_orb_stereo_from_rgbd_device.argtypes = [vp, ci, vp, ci, C.c_float, sz, sz, vp, C.c_float, vp, vp]
+        L.eaof_orb_stereo_from_rgbd.argtypes = [vp, ci, vp, ci, C.c_float, sz, sz, C.c_float, vp, vp, ci]
         L.eaof_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ci)]
         L.eaof_orb_fetch_results.argtypes = [vp, ci, vp, vp, ci, vp]
         L.eaof_orb_pyramid_level.argtypes = [vp, ci, ci, ci, vp, sz]
@@ -154,6 +158,33 @@ class ORBextractor:
                                           desc.ctypes.data, self.cap, cnt.ctypes.data))
         return [(kps[f, :cnt[f]].copy(), desc[f, :cnt[f]].copy()) for f in range(n)]
 
+    def extract_batch_color(self, frames: np.ndarray, color=0, gray_mode=0):
+        """frames (n,h,w,3|4) u8 interleaved colour on the host; color = COLOR_BGR/RGB/BGRA/RGBA, gray_mode = GRAY_CV331 /
+        GRAY_CV4: cvtColor (src/Tracking.cc:324-337) + extraction.  Returns a list of (keypoints, descriptors)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w, ch = frames.shape
+        assert ch == (4 if color >= 2 else 3)
+        kps = np.zeros((n, self.cap), KP_DTYPE)
+        desc = np.zeros((n, self.cap, 32), np.uint8)
+        cnt = np.zeros(n, np.int32)
+        _ck(self.L.eaof_orb_extract_batch_color(self.h, frames.ctypes.data, n, w, h, w * ch, w * h * ch, int(color),
+                                                int(gray_mode), kps.ctypes.data, desc.ctypes.data, self.cap, cnt.ctypes.data))
+        return [(kps[f, :cnt[f]].copy(), desc[f, :cnt[f]].copy()) for f in range(n)]
+
+    def stereo_from_rgbd(self, depth: np.ndarray, mbf: float, depth_scale=1.0):
+        """Frame::ComputeStereoFromRGBD (src/Frame.cc:1016-1037) for the keypoints of the last batch.  depth (n,h,w)
+        float32 (the CV_32F map) or uint16 (raw map, d = raw*depth_scale).  Returns (mvuRight, mvDepth) as (n, cap)."""
+        depth = np.ascontiguousarray(depth)
+        assert depth.dtype in (np.float32, np.uint16)
+        n, h, w = depth.shape
+        px = depth.dtype.itemsize
+        ur = np.full((n, self.cap), -1, np.float32)
+        dd = np.full((n, self.cap), -1, np.float32)
+        _ck(self.L.eaof_orb_stereo_from_rgbd(self.h, n, depth.ctypes.data, 1 if depth.dtype == np.uint16 else 0,
+                                             float(depth_scale), w * px, w * h * px, float(mbf), ur.ctypes.data,
+                                             dd.ctypes.data, self.cap))
+        return ur, dd
+
     def extract_batch_async(self, frames_ptr: int, n: int, kps_ptr: int, desc_ptr: int):
         """Enqueue upload + kernels + download of n packed frames at host address frames_ptr (pinned); outputs laid
         out [n][cap] at kps_ptr / desc_ptr.  Collect with extract_batch_wait()."""
@@ -233,6 +264,9 @@ class ORBextractor:
 
 
 # ------------------------------------------------------------------------------------------------------------
+COLOR_BGR, COLOR_RGB, COLOR_BGRA, COLOR_RGBA = 0, 1, 2, 3
+GRAY_CV331, GRAY_CV4 = 0, 1
+
 # Matcher (include/eaof_match.h)
 TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # ORBmatcher::TH_HIGH/TH_LOW/HISTO_LENGTH, src/ORBmatcher.cc:37-39
 BOW_KF_FRAME, BOW_KF_KF = 0, 1

@@ -110,6 +110,40 @@ int eaof_orb_set_pipeline_chunk(eaof_orb* ctx, int frames);
 int eaof_orb_extract_batch_device(eaof_orb* ctx, const uint8_t* d_imgs, int n_frames, int width, int height,
                                   size_t stride, size_t frame_pitch);
 int eaof_orb_sync(eaof_orb* ctx);
+
+/* Colour ingest: Tracking::GrabImageRGBD / GrabImageMonocular convert the camera image with
+ * cv::cvtColor(CV_RGB2GRAY | CV_BGR2GRAY | CV_RGBA2GRAY | CV_BGRA2GRAY) before the Frame constructor calls the extractor
+ * (src/Tracking.cc:324-337).  These entry points take the interleaved 8-bit colour frames and do that conversion on the
+ * device inside the level-0 pass; everything after it is the gray path.  The gray image (mImGray) is pyramid level 0,
+ * eaof_orb_pyramid_level(ctx, frame, 0, 0, ...).  `stride` / `frame_pitch` in bytes.  gray_mode: the integer formula of
+ * OpenCV's RGB2Gray<uchar>, which changed between versions like the blur taps did. */
+enum { EAOF_COLOR_BGR = 0, EAOF_COLOR_RGB = 1, EAOF_COLOR_BGRA = 2, EAOF_COLOR_RGBA = 3 };
+enum {
+    EAOF_GRAY_CV331 = 0, /* OpenCV 3.3.1: (B*1868 + G*9617 + R*4899 + 2^13) >> 14 [the reference's pinned version] */
+    EAOF_GRAY_CV4 = 1    /* OpenCV 4.x:   (B*3735 + G*19235 + R*9798 + 2^14) >> 15 (verified against cv2 4.13) */
+};
+int eaof_orb_extract_batch_device_color(eaof_orb* ctx, const uint8_t* d_imgs, int n_frames, int width, int height,
+                                        size_t stride, size_t frame_pitch, int color, int gray_mode);
+int eaof_orb_extract_batch_color(eaof_orb* ctx, const uint8_t* imgs, int n_frames, int width, int height, size_t stride,
+                                 size_t frame_pitch, int color, int gray_mode, eaof_kp* kps, uint8_t* desc, int cap,
+                                 int* n_out);
+
+/* Frame::ComputeStereoFromRGBD(imDepth)  src/Frame.cc:1016-1037 for the keypoints of the last batch:
+ * per keypoint the depth d at its raw position (coordinates truncated like cv::Mat::at<float>(float, float)); where
+ * d > 0: mvDepth = d, mvuRight = x_undistorted - mbf/d; -1 elsewhere.  depth_type EAOF_DEPTH_F32: the CV_32F map the
+ * reference holds; EAOF_DEPTH_U16: the raw 16-bit sensor map, converted as Tracking does with
+ * imDepth.convertTo(CV_32F, mDepthMapFactor) (src/Tracking.cc:340-341): d = (float)raw * depth_scale.
+ * _device: depth map and outputs in device memory ([n_frames][eaof_orb_max_keypoints()] floats), asynchronous on the
+ * handle's stream; d_x_undistorted = mvKeysUn x per keypoint in the same layout, NULL when the camera has no distortion
+ * (mvKeysUn = mvKeys, src/Frame.cc:775-779).  Host form: depth maps and outputs ([n_frames][cap]) in host memory. */
+enum { EAOF_DEPTH_F32 = 0, EAOF_DEPTH_U16 = 1 };
+int eaof_orb_stereo_from_rgbd_device(eaof_orb* ctx, int n_frames, const void* d_depth, int depth_type, float depth_scale,
+                                     size_t stride_bytes, size_t frame_pitch_bytes, const float* d_x_undistorted,
+                                     float mbf, float* d_uright, float* d_depth_out);
+int eaof_orb_stereo_from_rgbd(eaof_orb* ctx, int n_frames, const void* depth, int depth_type, float depth_scale,
+                              size_t stride_bytes, size_t frame_pitch_bytes, float mbf, float* uright, float* depth_out,
+                              int cap);
+
 /* Device-resident results of the last batch: kps[f*cap_out + i], desc[(f*cap_out + i)*32], counts[f].
  * cap_out == eaof_orb_max_keypoints(). */
 int eaof_orb_device_results(eaof_orb* ctx, const eaof_kp** d_kps, const uint8_t** d_desc, const int** d_counts,

@@ -868,3 +868,33 @@ def r_distinctive_descriptor(desc, kf_bad=None):
     out = np.zeros(32, np.uint8)
     i = mappoint_ref_lib().mpref_distinctive_descriptor(len(d), _pp(d), _pp(bad), out.ctypes.data)
     return i, out
+
+
+# ---- frame ingest either side of the extractor ------------------------------------------------
+
+def o_cvt_gray(img, color=0, mode=0):
+    """cv::cvtColor(..., CV_BGR2GRAY | CV_RGB2GRAY | CV_BGRA2GRAY | CV_RGBA2GRAY) on 8U as Tracking calls it
+    (src/Tracking.cc:324-337): OpenCV's RGB2Gray<uchar> integer formula.  color 0 BGR, 1 RGB, 2 BGRA, 3 RGBA; mode 0 =
+    OpenCV 3.3.1 (coefficients 1868/9617/4899, shift 14), 1 = OpenCV 4.x (3735/19235/9798, shift 15; checked against cv2
+    in tests/test_oracle_primitives.py)."""
+    img = np.asarray(img, np.uint8)
+    kb, kg, kr, sh = (1868, 9617, 4899, 14) if mode == 0 else (3735, 19235, 9798, 15)
+    c0, c1, c2 = (img[..., i].astype(np.int64) for i in range(3))
+    b, r = (c2, c0) if color in (1, 3) else (c0, c2)
+    return ((b * kb + c1 * kg + r * kr + (1 << (sh - 1))) >> sh).astype(np.uint8)
+
+
+def o_stereo_from_rgbd(kps, depth, mbf, depth_scale=1.0):
+    """Frame::ComputeStereoFromRGBD (src/Frame.cc:1016-1037) with mvKeysUn = mvKeys: returns (mvuRight, mvDepth).
+    depth float32, or uint16 converted like imDepth.convertTo(CV_32F, mDepthMapFactor) (src/Tracking.cc:340-341)."""
+    if depth.dtype == np.uint16:
+        depth = (depth.astype(np.float32) * np.float32(depth_scale)).astype(np.float32)
+    n = len(kps)
+    ur, dd = np.full(n, -1, np.float32), np.full(n, -1, np.float32)
+    for i in range(n):
+        u, v = int(kps["x"][i]), int(kps["y"][i])  # cv::Mat::at<float>(float v, float u): truncation
+        d = depth[v, u]
+        if d > 0:
+            dd[i] = d
+            ur[i] = np.float32(kps["x"][i]) - np.float32(mbf) / d
+    return ur, dd

@@ -184,3 +184,76 @@ def test_device_sincosf_sweep():
     L.eaof_debug_sincosf_mismatches.restype = C.c_long
     L.eaof_debug_sincosf_mismatches.argtypes = [C.c_float, C.c_uint32]
     assert L.eaof_debug_sincosf_mismatches(6.4, 7) == 0
+
+
+def _color_frames(frames, color, seed=9):
+    """Interleaved colour frames whose channels are different textures (so the conversion matters)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n, h, w = frames.shape
+    ch = 4 if color >= 2 else 3
+    out = np.empty((n, h, w, ch), np.uint8)
+    out[..., 0] = frames
+    out[..., 1] = np.roll(frames, 7, axis=2)
+    out[..., 2] = 255 - np.roll(frames, 5, axis=1)
+    if ch == 4:
+        out[..., 3] = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    return out
+
+
+@pytest.mark.parametrize("color", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_color_ingest(frames640, color, mode):
+    """cvtColor + extraction on the device == the oracle's gray conversion followed by the reference extraction."""
+    import eaof
+    from oracle import pyoracle as po
+    col = _color_frames(frames640[:3], color)
+    ex = eaof.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480, max_batch=3)
+    res = ex.extract_batch_color(col, color, mode)
+    for f in range(3):
+        gray = po.o_cvt_gray(col[f], color, mode)
+        assert np.array_equal(ex.pyramid_level(0, frame=f), gray), f
+        ok, od = po.o_extract(gray)
+        k, d = res[f]
+        assert len(k) == len(ok) and np.array_equal(k, ok) and np.array_equal(d, od), f
+    ex.close()
+
+
+def test_color_ingest_odd_width_takes_the_unaligned_path():
+    import eaof
+    from eaof import synth
+    from oracle import pyoracle as po
+    fr = synth.make_frames(2, 322, 241, tex=synth.base_texture(322, 241, seed=3))
+    ex = eaof.ORBextractor(500, 1.2, 8, 20, 7, width=322, height=241, max_batch=2)
+    for color in (0, 3):
+        col = _color_frames(fr, color)
+        res = ex.extract_batch_color(col, color, 0)
+        for f in range(2):
+            gray = po.o_cvt_gray(col[f], color, 0)
+            assert np.array_equal(ex.pyramid_level(0, frame=f), gray)
+            ok, od = po.o_extract(gray, nfeatures=500)
+            assert np.array_equal(res[f][0], ok) and np.array_equal(res[f][1], od)
+    ex.close()
+
+
+@pytest.mark.parametrize("kind", ["f32", "u16"])
+def test_stereo_from_rgbd(ex640, frames640, kind):
+    from oracle import pyoracle as po
+    rng = np.random.Generator(np.random.PCG64(12))
+    n = 3
+    res = ex640.extract_batch(frames640[:n])
+    if kind == "u16":
+        depth = rng.integers(0, 40000, (n, 480, 640)).astype(np.uint16)
+        depth[rng.random(depth.shape) < 0.2] = 0          # holes
+        scale = 1.0 / 5000.0                               # TUM DepthMapFactor
+    else:
+        depth = rng.uniform(-0.5, 8.0, (n, 480, 640)).astype(np.float32)
+        depth[rng.random(depth.shape) < 0.1] = 0
+        scale = 1.0
+    ur, dd = ex640.stereo_from_rgbd(depth, 40.0, scale)
+    tot = 0
+    for f in range(n):
+        k = res[f][0]
+        our, odd = po.o_stereo_from_rgbd(k, depth[f], 40.0, np.float32(scale))
+        assert np.array_equal(ur[f, :len(k)], our) and np.array_equal(dd[f, :len(k)], odd), f
+        tot += int(np.sum(odd > 0))
+    assert tot > 1000

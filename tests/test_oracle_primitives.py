@@ -121,3 +121,19 @@ def test_ctor_tables_match_reference():
     t = po.o_tables(1000, 1.2, 8)
     assert list(t["quotas"]) == [217, 181, 151, 126, 105, 87, 73, 60]
     assert list(t["umax"]) == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+
+
+@pytest.mark.parametrize("code,color", [("COLOR_BGR2GRAY", 0), ("COLOR_RGB2GRAY", 1), ("COLOR_BGRA2GRAY", 2), ("COLOR_RGBA2GRAY", 3)])
+def test_cvt_gray_cv4_formula_equals_cv2(code, color):
+    """The 15-bit RGB2Gray<uchar> formula (EAOF_GRAY_CV4) is what cv2 4.x computes; the 14-bit one (EAOF_GRAY_CV331, the
+    reference's pinned OpenCV 3.3.1) differs from it on a small fraction of pixels and cannot be checked here."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.Generator(np.random.PCG64(4))
+    ch = 4 if color >= 2 else 3
+    img = rng.integers(0, 256, (240, 321, ch), dtype=np.uint8)
+    img[:16, :16] = 255
+    img[16:32, :16] = 0
+    want = cv2.cvtColor(img, getattr(cv2, code))
+    assert np.array_equal(po.o_cvt_gray(img, color, 1), want)
+    diff = po.o_cvt_gray(img, color, 0).astype(int) - want
+    assert 0 < np.count_nonzero(diff) < 0.02 * diff.size and np.abs(diff).max() == 1
