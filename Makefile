@@ -6,14 +6,15 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 --fmad=false -Xcompiler -fPIC,-Wall -Xptxas -v $(EXTRA)
 PKG       := eao-fusion_b200
 LIB       := $(PKG)/lib/libeaof_orb.so
-SRCS      := $(PKG)/csrc/eaof_orb.cu $(wildcard $(PKG)/csrc/eaof_match.cu)
-HDRS      := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/eaof_orb.h
+SRCS      := $(PKG)/csrc/eaof_orb.cu $(PKG)/csrc/eaof_match.cu $(PKG)/csrc/eaof_voc.cu
+HDRS      := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/eaof_orb.h include/eaof_match.h include/eaof_voc.h
 
 DROPIN_T  := tests/cpp/_build/libdropin_harness.so
 DROPIN_M  := tests/cpp/_build/libmatch_dropin.so
+DROPIN_V  := tests/cpp/_build/libvoc_dropin.so
 REF       ?= /root/reference
 
-all: $(LIB) $(DROPIN_T) matchdropin
+all: $(LIB) $(DROPIN_T) matchdropin vocdropin
 
 $(LIB): $(SRCS) $(HDRS)
 	@mkdir -p $(PKG)/lib
@@ -40,12 +41,25 @@ matchdropin: $(LIB)
 	      -L$(PKG)/lib -leaof_orb -Wl,-rpath,'$$ORIGIN/../../../$(PKG)/lib' ; \
 	else echo "reference tree $(REF) not present: keeping prebuilt $(DROPIN_M) (if any)"; fi
 
+# the drop-in ORBVocabulary ($(PKG)/dropin/ORBVocabulary.h, a subclass of the reference's vendored DBoW2 vocabulary whose
+# batch transform runs on the GPU) behind the harness that drives the unmodified DBoW2 (oracle/voc_ref_harness.cc)
+DBOW := $(REF)/Thirdparty/DBoW2
+vocdropin: $(LIB)
+	@if [ -f $(DBOW)/DBoW2/TemplatedVocabulary.h ]; then \
+	  mkdir -p tests/cpp/_build && \
+	  /usr/bin/g++ -O2 -std=c++14 -fPIC -shared -w -Wl,-Bsymbolic -DEAOF_VOC_DROPIN -I$(PKG)/dropin -Ioracle/matchshim \
+	      -I$(DBOW)/DBoW2 -I$(DBOW) -Iinclude -o $(DROPIN_V) oracle/voc_ref_harness.cc $(DBOW)/DBoW2/FORB.cpp \
+	      $(DBOW)/DBoW2/BowVector.cpp $(DBOW)/DBoW2/FeatureVector.cpp $(DBOW)/DBoW2/ScoringObject.cpp \
+	      $(DBOW)/DUtils/Random.cpp $(DBOW)/DUtils/Timestamp.cpp \
+	      -L$(PKG)/lib -leaof_orb -Wl,-rpath,'$$ORIGIN/../../../$(PKG)/lib' ; \
+	else echo "reference tree $(REF) not present: keeping prebuilt $(DROPIN_V) (if any)"; fi
+
 oracle:
 	$(MAKE) -C oracle
 	$(MAKE) -C oracle ref
 
 clean:
-	rm -f $(LIB) $(PKG)/lib/ptxas.log $(DROPIN_T) $(DROPIN_M)
+	rm -f $(LIB) $(PKG)/lib/ptxas.log $(DROPIN_T) $(DROPIN_M) $(DROPIN_V)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean matchdropin
+.PHONY: all oracle clean matchdropin vocdropin

@@ -535,3 +535,76 @@ class ORBmatcher:
         _ck(self.L.eaof_match_bruteforce_batch_device(self.h, mode, self.mfNNratio, int(self.mbCheckOrientation), len(pq),
                                                       _p(pq), _p(pt), d_desc, d_angle, d_counts, block_stride, d_match,
                                                       d_dist, d_n))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Vocabulary (include/eaof_voc.h)
+_vlib_ready = False
+
+
+def _vlib():
+    global _vlib_ready
+    L = lib()
+    if not _vlib_ready:
+        vp, ci = C.c_void_p, C.c_int
+        L.eaof_voc_create.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, ci, ci, ci, ci, C.POINTER(vp)]
+        L.eaof_voc_destroy.argtypes = [vp]
+        L.eaof_voc_transform.argtypes = [vp, ci, vp, vp, ci] + [vp] * 7
+        L.eaof_voc_transform_orb_device.argtypes = [vp, vp, ci, ci] + [vp] * 7
+        L.eaof_voc_sync.argtypes = [vp]
+        L.eaof_voc_stream.restype = vp
+        L.eaof_voc_stream.argtypes = [vp]
+        _vlib_ready = True
+    return L
+
+
+class ORBVocabulary:
+    """ORBVocabulary::transform(features, BowVector, FeatureVector, levelsup) over the C ABI.  tree: dict(L, child_start,
+    child_idx, desc[n,32], weight[n] f64, word_id[n], weighting, scoring) — the arrays a loaded DBoW2 vocabulary holds."""
+
+    def __init__(self, tree, *, max_features=4096, max_sets=1, device=0):
+        self.L = _vlib()
+        self.h = C.c_void_p()
+        cs, ci_, d = _arr(tree["child_start"], np.int32), _arr(tree["child_idx"], np.int32), _arr(tree["desc"], np.uint8)
+        w, wid = _arr(tree["weight"], np.float64), _arr(tree["word_id"], np.int32)
+        _ck(self.L.eaof_voc_create(device, int(tree["L"]), len(w), _p(cs), _p(ci_), _p(d), _p(w), _p(wid), int(tree["weighting"]),
+                                   int(tree["scoring"]), int(max_features), int(max_sets), C.byref(self.h)))
+        self.max_features, self.max_sets = max_features, max_sets
+
+    def close(self):
+        if self.h:
+            self.L.eaof_voc_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def transform_sets(self, sets, levelsup=4):
+        """sets: list of (n_i, 32) u8 arrays.  Returns one (word_ids, word_vals, node_ids, node_starts, feat_idx) per set."""
+        cnt = [len(s) for s in sets]
+        start = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+        tot = int(start[-1])
+        desc = np.concatenate([np.asarray(s, np.uint8).reshape(-1, 32) for s in sets]) if tot else np.zeros((0, 32), np.uint8)
+        desc = np.ascontiguousarray(desc)
+        ns = len(sets)
+        nw, nn = np.zeros(ns, np.int32), np.zeros(ns, np.int32)
+        wi, wv = np.zeros(tot + 1, np.uint32), np.zeros(tot + 1, np.float64)
+        ni, nst, fi = np.zeros(tot + 1, np.uint32), np.zeros(tot + ns + 1, np.int32), np.zeros(tot + 1, np.uint32)
+        _ck(self.L.eaof_voc_transform(self.h, ns, start.ctypes.data, desc.ctypes.data, int(levelsup), nw.ctypes.data,
+                                      wi.ctypes.data, wv.ctypes.data, nn.ctypes.data, ni.ctypes.data, nst.ctypes.data,
+                                      fi.ctypes.data))
+        out = []
+        for s in range(ns):
+            o = int(start[s])
+            st = nst[o + s:o + s + nn[s] + 1].copy()
+            out.append((wi[o:o + nw[s]].copy(), wv[o:o + nw[s]].copy(), ni[o:o + nn[s]].copy(), st, fi[o:o + st[-1]].copy()))
+        return out
+
+    def transform(self, feats, levelsup=4):
+        return self.transform_sets([feats], levelsup)[0]
+
+    def transform_orb_device(self, ex: "ORBextractor", n_frames, levelsup, d_nw, d_wi, d_wv, d_nn, d_ni, d_ns, d_fi):
+        _ck(self.L.eaof_voc_transform_orb_device(self.h, ex.h, n_frames, int(levelsup), d_nw, d_wi, d_wv, d_nn, d_ni, d_ns, d_fi))
+
+    def sync(self):
+        _ck(self.L.eaof_voc_sync(self.h))
+
+    def stream_ptr(self):
+        return self.L.eaof_voc_stream(self.h)

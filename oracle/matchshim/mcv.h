@@ -12,7 +12,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 typedef unsigned char uchar;
@@ -90,6 +93,7 @@ public:
     template <typename T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step); }
 
     void copyTo(Mat& dst) const { dst = clone(); }
+    void release() { buf_.reset(); data = nullptr; rows = cols = 0; step = 0; }
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
     Mat t() const {
         assert(depth_ == CV_32F);
@@ -111,6 +115,27 @@ private:
     int depth_;
     std::shared_ptr<uchar> buf_;
 };
+
+// cv::FileStorage / cv::FileNode: only named by TemplatedVocabulary::save/load(cv::FileStorage&) (Thirdparty/DBoW2/DBoW2/
+// TemplatedVocabulary.h:1534-1740), which the harnesses never call — the vocabulary is read with loadFromTextFile.  The
+// stand-ins make those members compile; reaching them aborts.
+struct FileNode {
+    FileNode operator[](const char*) const { std::abort(); }
+    FileNode operator[](const std::string&) const { std::abort(); }
+    FileNode operator[](int) const { std::abort(); }
+    size_t size() const { std::abort(); }
+    operator int() const { std::abort(); }
+    operator double() const { std::abort(); }
+    operator std::string() const { std::abort(); }
+};
+struct FileStorage {
+    enum { READ = 0, WRITE = 1 };
+    FileStorage(const char*, int) {}
+    bool isOpened() const { return false; }
+    FileNode operator[](const std::string&) const { std::abort(); }
+    FileNode operator[](const char*) const { std::abort(); }
+};
+template <typename T> static inline FileStorage& operator<<(FileStorage& f, const T&) { std::abort(); return f; }
 
 static inline Mat operator*(const Mat& a, const Mat& b) {
     assert(a.cols == b.rows);

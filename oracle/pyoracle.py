@@ -898,3 +898,97 @@ def o_stereo_from_rgbd(kps, depth, mbf, depth_scale=1.0):
             dd[i] = d
             ur[i] = np.float32(kps["x"][i]) - np.float32(mbf) / d
     return ur, dd
+
+
+# ---- DBoW2 vocabulary: ORBVocabulary::transform ------------------------------------------------------
+VOC_REF_SO = os.path.join(HERE, "_ref", "libvoc_ref.so")
+_vref = None
+
+
+def _setup_vref(L):
+    vp, ci = C.c_void_p, C.c_int
+    L.vref_load.restype = vp
+    L.vref_load.argtypes = [C.c_char_p]
+    L.vref_free.argtypes = [vp]
+    L.vref_info.argtypes = [vp, vp]
+    L.vref_tree.argtypes = [vp] * 7
+    L.vref_transform.argtypes = [vp, ci, vp, ci] + [vp] * 6
+    L.vref_score.restype = C.c_double
+    L.vref_score.argtypes = [vp, ci, vp, vp, ci, vp, vp]
+    return L
+
+
+def voc_ref_lib():
+    global _vref
+    if _vref is None:
+        if not os.path.exists(VOC_REF_SO):
+            subprocess.check_call(["make", "-s", "-C", HERE, "vocref"])
+        _vref = _setup_vref(C.CDLL(VOC_REF_SO))
+    return _vref
+
+
+def voc_harness_lib(path):
+    """The same harness (oracle/voc_ref_harness.cc) built around the drop-in vocabulary class."""
+    return _setup_vref(C.CDLL(path))
+
+
+class RefVocabulary:
+    """A vocabulary loaded by the reference's own TemplatedVocabulary::loadFromTextFile."""
+
+    def __init__(self, path, L=None):
+        self.L = L or voc_ref_lib()
+        self.h = self.L.vref_load(path.encode())
+        if not self.h:
+            raise RuntimeError(f"vocabulary {path} did not load")
+        info = np.zeros(6, np.int32)
+        self.L.vref_info(self.h, info.ctypes.data)
+        self.k, self.depth, self.n_nodes, self.n_words, self.scoring, self.weighting = (int(v) for v in info)
+
+    def close(self):
+        if self.h:
+            self.L.vref_free(self.h)
+            self.h = None
+
+    def tree(self):
+        """dict(parent, desc, weight, word_id, child_start, child_idx) as the reference holds the tree."""
+        n = self.n_nodes
+        t = dict(parent=np.zeros(n, np.int32), desc=np.zeros((n, 32), np.uint8), weight=np.zeros(n, np.float64),
+                 word_id=np.zeros(n, np.int32), child_start=np.zeros(n + 1, np.int32), child_idx=np.zeros(max(n - 1, 1), np.int32))
+        self.L.vref_tree(self.h, *[t[k].ctypes.data for k in ("parent", "desc", "weight", "word_id", "child_start", "child_idx")])
+        t.update(L=self.depth, k=self.k, scoring=self.scoring, weighting=self.weighting)
+        return t
+
+    def transform(self, feats, levelsup=4):
+        """Returns (word_ids, word_values, node_ids, node_starts, feat_idx)."""
+        f = _a(feats, np.uint8).reshape(-1, 32)
+        n = len(f)
+        cnt = np.zeros(2, np.int32)
+        wi, wv = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float64)
+        ni, ns, fi = np.zeros(max(n, 1), np.uint32), np.zeros(n + 1, np.int32), np.zeros(max(n, 1), np.uint32)
+        self.L.vref_transform(self.h, n, _pp(f), int(levelsup), cnt.ctypes.data, wi.ctypes.data, wv.ctypes.data, ni.ctypes.data,
+                              ns.ctypes.data, fi.ctypes.data)
+        return wi[:cnt[0]], wv[:cnt[0]], ni[:cnt[1]], ns[:cnt[1] + 1], fi[:ns[cnt[1]]]
+
+    def score(self, a, b):
+        ia, va, ib, vb = _a(a[0], np.uint32), _a(a[1], np.float64), _a(b[0], np.uint32), _a(b[1], np.float64)
+        return self.L.vref_score(self.h, len(ia), _pp(ia), _pp(va), len(ib), _pp(ib), _pp(vb))
+
+
+def o_voc_transform(tree, feats, levelsup=4):
+    """oracle/voc_oracle.cc on the tree arrays of RefVocabulary.tree().  Same return layout as RefVocabulary.transform."""
+    f = _a(feats, np.uint8).reshape(-1, 32)
+    n = len(f)
+    L = oracle_lib()
+    ci, vp = C.c_int, C.c_void_p
+    L.eaoo_voc_transform.restype = None
+    L.eaoo_voc_transform.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, ci, ci, vp, ci] + [vp] * 6
+    cnt = np.zeros(2, np.int32)
+    wi, wv = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float64)
+    ni, ns, fi = np.zeros(max(n, 1), np.uint32), np.zeros(n + 1, np.int32), np.zeros(max(n, 1), np.uint32)
+    cs, cx, nd = _a(tree["child_start"], np.int32), _a(tree["child_idx"], np.int32), _a(tree["desc"], np.uint8)
+    wt, wd = _a(tree["weight"], np.float64), _a(tree["word_id"], np.int32)
+    L.eaoo_voc_transform(int(tree["L"]), len(wt), _pp(cs), _pp(cx), _pp(nd), _pp(wt), _pp(wd), int(tree["weighting"]),
+                         int(tree["scoring"]), n, _pp(f),
+                         int(levelsup), cnt.ctypes.data, wi.ctypes.data, wv.ctypes.data, ni.ctypes.data, ns.ctypes.data,
+                         fi.ctypes.data)
+    return wi[:cnt[0]], wv[:cnt[0]], ni[:cnt[1]], ns[:cnt[1] + 1], fi[:ns[cnt[1]]]

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for hdr in ("eaof_orb.h", "eaof_match.h"):
+    for hdr in ("eaof_orb.h", "eaof_match.h", "eaof_voc.h"):
         src = open(os.path.join(ROOT, "include", hdr)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(eaof_[a-z0-9_]+)\s*\(", src))
