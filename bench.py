@@ -113,6 +113,106 @@ def hamming_sweep(eaof, torch, device, n_blocks=64, n_feat=2000, n_pairs=1024, r
     return out
 
 
+def next_rows(eaof, torch, device, ex, d_frames, B, W, H):
+    """SURVEY.md §8(f) rows built so far, each timed on its own (device-resident where the entry point is; CUDA events on
+    the library's streams): bag-of-words conversion of a batch, colour ingest, ComputeStereoFromRGBD, the map-side window
+    search and ComputeDistinctiveDescriptors.  Reported beside the headline, not part of it."""
+    import time as _t
+    from eaof import synth
+    out = {}
+    dev = torch.device("cuda", device)
+    cap = ex.cap
+
+    def timed(stream_ptr, fn, sync, reps=5):
+        st = torch.cuda.ExternalStream(stream_ptr, device=dev)
+        fn(); sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            fn()
+        e1.record(st)
+        sync()
+        return e0.elapsed_time(e1) / reps
+
+    # f-2: ORBVocabulary::transform over the descriptors of a batch, vocabulary of the ORBvoc shape (k=10, L=6)
+    tree = synth.vocabulary(10, 6)
+    voc = eaof.ORBVocabulary(tree, max_features=cap, max_sets=B, device=device)
+    ex.extract_batch_device(d_frames.data_ptr(), B)
+    ex.sync()
+    kp = float(ex.fetch_counts(B).mean())
+    nw, nn = torch.zeros(B, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)
+    wi, ni, fi = (torch.zeros(B * cap, dtype=torch.int32, device=dev) for _ in range(3))
+    wv = torch.zeros(B * cap, dtype=torch.float64, device=dev)
+    ns = torch.zeros(B * (cap + 1), dtype=torch.int32, device=dev)
+    ms = timed(voc.stream_ptr(), lambda: voc.transform_orb_device(ex, B, 4, nw.data_ptr(), wi.data_ptr(), wv.data_ptr(),
+                                                                 nn.data_ptr(), ni.data_ptr(), ns.data_ptr(), fi.data_ptr()), voc.sync)
+    out["bow_transform"] = {"workload": f"{B} frames x {kp:.0f} descriptors, synthetic vocabulary k=10 L=6 (1,111,111 nodes), levelsup=4",
+                            "ms_per_batch": ms, "frames_per_s": B / (ms * 1e-3), "descriptors_per_s": B * kp / (ms * 1e-3),
+                            "words_per_frame": float(nw.float().mean().item()),
+                            "alg_bytes_per_descriptor": 6 * 10 * 32 + 32,
+                            "achieved_gbs": B * kp * (6 * 10 * 32 + 32) / (ms * 1e-3) / 1e9}
+    voc.sync()
+    voc.close()
+
+    # f-4: colour ingest (cvtColor BGR->gray fused into the level-0 pass) against the gray entry point
+    d_col = d_frames[:B].unsqueeze(-1).expand(B, H, W, 3).contiguous()
+    L = eaof.lib()
+    ms_gray = timed(ex.stream_ptr(), lambda: ex.extract_batch_device(d_frames.data_ptr(), B), ex.sync)
+    ms_col = timed(ex.stream_ptr(), lambda: eaof._ck(L.eaof_orb_extract_batch_device_color(ex.h, d_col.data_ptr(), B, W, H, W * 3,
+                                                                                      W * H * 3, 0, 0)), ex.sync)
+    out["color_ingest"] = {"workload": f"{B} BGR frames {W}x{H}: cvtColor + extraction, device-resident",
+                           "ms_per_batch_bgr": ms_col, "ms_per_batch_gray": ms_gray, "frames_per_s_bgr": B / (ms_col * 1e-3)}
+    del d_col
+
+    # f-1: Frame::ComputeStereoFromRGBD over the keypoints of the batch (raw 16-bit depth, TUM factor)
+    d_depth = torch.randint(0, 40000, (B, H, W), dtype=torch.int32, device=dev).to(torch.uint16)
+    ur = torch.zeros(B * cap, dtype=torch.float32, device=dev)
+    dd = torch.zeros(B * cap, dtype=torch.float32, device=dev)
+    ms = timed(ex.stream_ptr(), lambda: eaof._ck(L.eaof_orb_stereo_from_rgbd_device(ex.h, B, d_depth.data_ptr(), 1, 1.0 / 5000.0,
+                                                                                   W * 2, W * H * 2, None, 40.0, ur.data_ptr(),
+                                                                                   dd.data_ptr())), ex.sync)
+    out["stereo_from_rgbd"] = {"workload": f"{B} frames x {kp:.0f} keypoints, u16 depth", "ms_per_batch": ms,
+                               "keypoints_per_s": B * kp / (ms * 1e-3)}
+    del d_depth, ur, dd
+
+    # a14: the search step of Fuse / SearchBySim3 (one keyframe, host buffers in and out: a latency number)
+    rng = np.random.Generator(np.random.PCG64(3))
+    n = 1000
+    KF = dict(x=rng.uniform(0, W, n).astype(np.float32), y=rng.uniform(0, H, n).astype(np.float32),
+              octave=rng.integers(0, 8, n).astype(np.int32), desc=rng.integers(0, 256, (n, 32), dtype=np.uint8))
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    lvl = np.clip(KF["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+    q = dict(u=(KF["x"] + rng.normal(0, 2, n)).astype(np.float32), v=(KF["y"] + rng.normal(0, 2, n)).astype(np.float32),
+             radius=(np.float32(3.0) * sf[lvl]).astype(np.float32), min_level=lvl - 1, max_level=lvl,
+             desc=KF["desc"] ^ np.packbits((rng.random((n, 256)) < 0.05).astype(np.uint8), axis=1))
+    mt = eaof.ORBmatcher(0.6, True, max_features=4096, device=device)
+    kw = dict(bounds=(0.0, float(W), 0.0, float(H)), grid_inv=(np.float32(64) / np.float32(W), np.float32(48) / np.float32(H)))
+    mt.SearchWindowsIndependent(0, KF, q, 50, **kw)
+    t0 = _t.perf_counter()
+    for _ in range(20):
+        nacc, _, _ = mt.SearchWindowsIndependent(0, KF, q, 50, **kw)
+    us = (_t.perf_counter() - t0) / 20 * 1e6
+    out["fuse_search"] = {"workload": f"{n} projected map points against {n} keyframe features, host buffers (upload + 3 kernels + download)",
+                          "us_per_call": us, "accepted": int(nacc)}
+
+    # f-3: MapPoint::ComputeDistinctiveDescriptors batched over map points (host buffers)
+    npts, nobs = 20000, 8
+    base = rng.integers(0, 256, (npts, 1, 32), dtype=np.uint8)
+    desc = (base ^ np.packbits((rng.random((npts, nobs, 256)) < 0.08).astype(np.uint8), axis=2)).reshape(-1, 32)
+    starts = (np.arange(npts + 1) * nobs).astype(np.int32)
+    mt2 = eaof.ORBmatcher(0.6, True, max_features=65535, device=device)
+    mt2.DistinctiveDescriptors(starts, desc)
+    t0 = _t.perf_counter()
+    for _ in range(3):
+        mt2.DistinctiveDescriptors(starts, desc)
+    sec = (_t.perf_counter() - t0) / 3
+    out["distinctive_descriptors"] = {"workload": f"{npts} map points x {nobs} observations, host buffers", "ms_per_call": sec * 1e3,
+                                      "map_points_per_s": npts / sec}
+    mt.close()
+    mt2.close()
+    return out
+
+
 def algorithmic_bytes(level_sizes, kp_per_frame, cand_per_frame):
     """Per-frame algorithmic bytes per stage, SURVEY.md §8(d)."""
     P = sum(w * h for w, h in level_sizes)
@@ -251,6 +351,7 @@ def main():
     ap.add_argument("--batch", type=int, default=250)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -409,6 +510,12 @@ def main():
     if rank == 0 or world > 1:
         hamming = hamming_sweep(eaof, torch, local_rank)
     clocks = sampler.finish()
+    extras = None
+    if rank == 0 and not args.no_next_rows:  # after the clock sampler: these rows have host-side phases
+        try:
+            extras = next_rows(eaof, torch, local_rank, ex, d_frames, B, W, H)
+        except Exception as e:  # reported beside the headline, never required for it
+            extras = {"failed": repr(e)}
 
     # max over ranks
     t = torch.tensor([dt_wall, dt_e2e, step_ms_dev], dtype=torch.float64, device="cuda")
@@ -466,6 +573,7 @@ def main():
             "matching": {"kind": "consecutive-frame SearchByProjection(Cur,Last), th=15, octave+-1, rot-hist on",
                          "pairs_per_step_per_gpu": n_pairs, "matches_per_pair": matches_per_pair,
                          "ms_per_step": stage_acc["match_projection"]},
+            "next_rows": extras,
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
