@@ -71,6 +71,9 @@ public:
     void SetBlurMode(int eaofBlurMode);      // EAOF_BLUR_* of eaof_orb.h; default OpenCV 3.3.1 taps or $EAOF_BLUR_MODE
     void SetPyramidDownload(bool on);        // default on; off skips the device->host copy of mvImagePyramid
                                              // (only Frame::ComputeStereoMatches reads it) or $EAOF_PYRAMID=0
+    // The library handle holding this extractor's last frame on the device (NULL before the first frame): what the
+    // device-side Frame helpers take (eaof_orb_stereo_from_rgbd, eaof_stereo_matches, eaof_voc_transform_orb_device).
+    eaof_orb* Handle() const { return mpCtx; }
 
 protected:
 
