@@ -644,3 +644,109 @@ int eaoo_distinctive_descriptor(int n, const uint8_t* desc, int* medianOut) {
 }
 
 }  // extern "C"
+
+// ---- Frame::ComputeStereoMatches  src/Frame.cc:841-1013 -------------------------------------------------------------------
+// Left / right keypoints (level-0 coordinates, octave), descriptors, both image pyramids as bordered level buffers back
+// to back (level l at off[l], (w[l]+38) x (h[l]+38) bytes, the level image at (19,19): src/ORBextractor.cc:1114-1116).
+// Outputs mvuRight / mvDepth (-1 where unmatched).  sadOut (optional): the SAD of the accepted matches (-1 elsewhere), before
+// the median filter.
+extern "C" void eaoo_stereo_matches(int nL, const float* xL, const float* yL, const int* octL, const uint8_t* descL, int nR,
+                                    const float* xR, const float* yR, const int* octR, const uint8_t* descR, int nLevels,
+                                    const float* scale, const float* invScale, const uint8_t* pyrL, const uint8_t* pyrR,
+                                    const int* off, const int* w, const int* h, float mb, float mbf, float* uRight,
+                                    float* depth, int* sadOut) {
+    (void)nLevels;
+    for (int i = 0; i < nL; ++i) { uRight[i] = -1.0f; depth[i] = -1.0f; if (sadOut) sadOut[i] = -1; }
+    const int nRows = h[0];
+    std::vector<std::vector<int>> vRowIndices(nRows);
+    for (int iR = 0; iR < nR; ++iR) {  // :855-866
+        const float kpY = yR[iR];
+        const float r = 2.0f * scale[octR[iR]];
+        const int maxr = (int)ceilf(kpY + r);
+        const int minr = (int)floorf(kpY - r);
+        for (int yi = minr; yi <= maxr; ++yi)
+            if (yi >= 0 && yi < nRows) vRowIndices[yi].push_back(iR);  // the reference indexes unchecked
+    }
+    const float minZ = mb;
+    const float minD = -3;
+    const float maxD = mbf / minZ;
+    auto px = [&](const uint8_t* pyr, int l, int y, int x) -> float {  // mvImagePyramid[l].at<uchar>(y, x) as float
+        return (float)pyr[off[l] + (size_t)(y + 19) * (w[l] + 38) + (x + 19)];
+    };
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int iL = 0; iL < nL; ++iL) {
+        const int levelL = octL[iL];
+        const float vL = yL[iL], uL = xL[iL];
+        const std::vector<int>& vCandidates = vRowIndices[(size_t)vL];
+        if (vCandidates.empty()) continue;
+        const float minU = uL - maxD;
+        const float maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        int bestIdxR = 0;
+        for (int iR : vCandidates) {
+            if (octR[iR] < levelL - 1 || octR[iR] > levelL + 1) continue;
+            const float uR = xR[iR];
+            if (uR >= minU && uR <= maxU) {
+                const int dist = descriptor_distance(descL + 32 * (size_t)iL, descR + 32 * (size_t)iR);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < TH_HIGH) {  // subpixel match by correlation, :913-1000
+            const float uR0 = xR[bestIdxR];
+            const float scaleFactor = invScale[levelL];
+            const float scaleduL = roundf(uL * scaleFactor);
+            const float scaledvL = roundf(vL * scaleFactor);
+            const float scaleduR0 = roundf(uR0 * scaleFactor);
+            const int wp = 5;
+            float IL[11][11];
+            const int y0 = (int)(scaledvL - wp), x0 = (int)(scaleduL - wp);
+            for (int a = 0; a < 11; ++a)
+                for (int b = 0; b < 11; ++b) IL[a][b] = px(pyrL, levelL, y0 + a, x0 + b);
+            const float cL = IL[wp][wp];
+            for (int a = 0; a < 11; ++a)
+                for (int b = 0; b < 11; ++b) IL[a][b] = IL[a][b] - cL * 1.0f;
+            int bestDistS = 0x7fffffff;
+            int bestincR = 0;
+            const int L = 5;
+            float vDists[11];
+            const float iniu = scaleduR0 + L - wp;
+            const float endu = scaleduR0 + L + wp + 1;
+            if (iniu < 0 || endu >= w[levelL]) continue;
+            for (int incR = -L; incR <= +L; ++incR) {
+                const int xr0 = (int)(scaleduR0 + incR - wp);
+                const float cR = px(pyrR, levelL, y0 + wp, xr0 + wp);
+                double acc = 0;  // cv::norm(IL, IR, NORM_L1): double accumulator over exact integers
+                for (int a = 0; a < 11; ++a)
+                    for (int b = 0; b < 11; ++b) acc += fabs((double)IL[a][b] - (double)(px(pyrR, levelL, y0 + a, xr0 + b) - cR * 1.0f));
+                const float dist = (float)acc;
+                if (dist < bestDistS) { bestDistS = dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1];
+            const float dist2 = vDists[L + bestincR];
+            const float dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = scale[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= 0 && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+                depth[iL] = mbf / disparity;
+                uRight[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(bestDistS, iL));
+                if (sadOut) sadOut[iL] = bestDistS;
+            }
+        }
+    }
+    if (vDistIdx.empty()) return;  // the reference reads vDistIdx[0] of an empty vector here
+    std::sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {
+        if (vDistIdx[i].first < thDist) break;
+        uRight[vDistIdx[i].second] = -1;
+        depth[vDistIdx[i].second] = -1;
+    }
+}

@@ -95,6 +95,22 @@ public:
     void copyTo(Mat& dst) const { dst = clone(); }
     void release() { buf_.reset(); data = nullptr; rows = cols = 0; step = 0; }
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+    static Mat ones(int r, int c, int type) {
+        Mat m(r, c, type);
+        for (int y = 0; y < r; ++y)
+            for (int x = 0; x < c; ++x) {
+                if (type == CV_32F) m.at<float>(y, x) = 1.f; else m.at<uchar>(y, x) = 1;
+            }
+        return m;
+    }
+    // 8U -> 32F / 32F -> 32F without scaling (Frame::ComputeStereoMatches converts its 11x11 patches, src/Frame.cc:939,957)
+    void convertTo(Mat& dst, int type) const {
+        assert(type == CV_32F);
+        Mat m(rows, cols, CV_32F);
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) m.at<float>(y, x) = depth_ == CV_32F ? at<float>(y, x) : (float)at<uchar>(y, x);
+        dst = m;
+    }
     Mat t() const {
         assert(depth_ == CV_32F);
         Mat m(cols, rows, CV_32F);
@@ -168,5 +184,13 @@ static inline Mat addw(const Mat& a, const Mat& b, float sb) {
 static inline Mat operator+(const Mat& a, const Mat& b) { return addw(a, b, 1.f); }
 static inline Mat operator-(const Mat& a, const Mat& b) { return addw(a, b, -1.f); }
 static inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
+enum { NORM_L1 = 2 };
+static inline double norm(const Mat& a, const Mat& b, int normType) {  // normDiffL1_32f: double accumulator
+    assert(normType == NORM_L1 && a.type() == CV_32F && b.type() == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    double s = 0;
+    for (int y = 0; y < a.rows; ++y)
+        for (int x = 0; x < a.cols; ++x) s += std::fabs((double)a.at<float>(y, x) - (double)b.at<float>(y, x));
+    return s;
+}
 
 }  // namespace cv

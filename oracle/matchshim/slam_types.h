@@ -83,6 +83,12 @@ public:
 };
 #endif
 
+// include/ORBextractor.h:85 — the one member Frame::ComputeStereoMatches reads
+class ORBextractor {
+public:
+    std::vector<cv::Mat> mvImagePyramid;
+};
+
 struct GridOwner {
     std::vector<size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
 };
@@ -139,6 +145,13 @@ public:
     cv::Mat GetCameraCenter() { return mOw.clone(); }
     long unsigned int mnId = 0;
     cv::Mat mOw;
+    // stereo / RGB-D members; the two methods are the reference's own text (src/Frame.cc:841-1037), cut out at build time
+    // by `make -C oracle stereoref` and compiled in oracle/stereo_ref_harness.cc
+    void ComputeStereoMatches();
+    void ComputeStereoFromRGBD(const cv::Mat& imDepth);
+    std::vector<cv::KeyPoint> mvKeysRight;
+    cv::Mat mDescriptorsRight;
+    ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
 
     int N;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;

@@ -992,3 +992,82 @@ def o_voc_transform(tree, feats, levelsup=4):
                          int(levelsup), cnt.ctypes.data, wi.ctypes.data, wv.ctypes.data, ni.ctypes.data, ns.ctypes.data,
                          fi.ctypes.data)
     return wi[:cnt[0]], wv[:cnt[0]], ni[:cnt[1]], ns[:cnt[1] + 1], fi[:ns[cnt[1]]]
+
+
+# ---- Frame::ComputeStereoMatches / ComputeStereoFromRGBD -------------------------------------
+STEREO_REF_SO = os.path.join(HERE, "_ref", "libstereo_ref.so")
+_sref = None
+
+
+def stereo_ref_lib():
+    """The text of Frame::ComputeStereoMatches / ComputeStereoFromRGBD cut out of the reference's src/Frame.cc at build
+    time and compiled unmodified (oracle/stereo_ref_harness.cc)."""
+    global _sref
+    if _sref is None:
+        if not os.path.exists(STEREO_REF_SO):
+            subprocess.check_call(["make", "-s", "-C", HERE, "stereoref"])
+        _sref = C.CDLL(STEREO_REF_SO)
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        _sref.sref_stereo_matches.restype = None
+        _sref.sref_stereo_matches.argtypes = [ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, cf, cf, vp, vp]
+        _sref.sref_stereo_from_rgbd.restype = None
+        _sref.sref_stereo_from_rgbd.argtypes = [ci, vp, vp, vp, vp, ci, ci, cf, vp, vp]
+    return _sref
+
+
+def pack_pyramid(levels):
+    """Bordered level images [(h+38, w+38) u8] -> (buffer, off[], w[], h[]) as the stereo oracles take them."""
+    off, ws, hs, o = [], [], [], 0
+    for im in levels:
+        off.append(o); hs.append(im.shape[0] - 38); ws.append(im.shape[1] - 38)
+        o += im.size
+    buf = np.concatenate([np.ascontiguousarray(im, np.uint8).ravel() for im in levels])
+    return buf, np.asarray(off, np.int32), np.asarray(ws, np.int32), np.asarray(hs, np.int32)
+
+
+def _stereo_args(kL, dL, kR, dR, pyrL, pyrR, scale, inv_scale):
+    xL, yL, oL = _a(kL["x"], np.float32), _a(kL["y"], np.float32), _a(kL["octave"], np.int32)
+    xR, yR, oR = _a(kR["x"], np.float32), _a(kR["y"], np.float32), _a(kR["octave"], np.int32)
+    bL, off, w, h = pack_pyramid(pyrL)
+    bR, off2, _, _ = pack_pyramid(pyrR)
+    assert np.array_equal(off, off2)
+    sf, isf = _a(scale, np.float32), _a(inv_scale, np.float32)
+    keep = (xL, yL, oL, _a(dL, np.uint8), xR, yR, oR, _a(dR, np.uint8), sf, isf, bL, bR, off, w, h)
+    return keep
+
+
+def o_stereo_matches(kL, dL, kR, dR, pyrL, pyrR, scale, inv_scale, mb, mbf):
+    """oracle/match_oracle.cc eaoo_stereo_matches.  kL/kR: keypoint records (x, y, octave); pyrL/pyrR: lists of bordered
+    level images.  Returns (mvuRight, mvDepth, sad)."""
+    xL, yL, oL, dL, xR, yR, oR, dR, sf, isf, bL, bR, off, w, h = _stereo_args(kL, dL, kR, dR, pyrL, pyrR, scale, inv_scale)
+    n = len(xL)
+    ur, dp, sad = np.full(max(n, 1), -1, np.float32), np.full(max(n, 1), -1, np.float32), np.full(max(n, 1), -1, np.int32)
+    L = oracle_lib()
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    L.eaoo_stereo_matches.restype = None
+    L.eaoo_stereo_matches.argtypes = [ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, cf, cf, vp, vp, vp]
+    L.eaoo_stereo_matches(n, _pp(xL), _pp(yL), _pp(oL), _pp(dL), len(xR), _pp(xR), _pp(yR), _pp(oR), _pp(dR), len(sf), _pp(sf),
+                          _pp(isf), _pp(bL), _pp(bR), _pp(off), _pp(w), _pp(h), float(mb), float(mbf), ur.ctypes.data,
+                          dp.ctypes.data, sad.ctypes.data)
+    return ur[:n], dp[:n], sad[:n]
+
+
+def r_stereo_matches(kL, dL, kR, dR, pyrL, pyrR, scale, inv_scale, mb, mbf):
+    xL, yL, oL, dL, xR, yR, oR, dR, sf, isf, bL, bR, off, w, h = _stereo_args(kL, dL, kR, dR, pyrL, pyrR, scale, inv_scale)
+    n = len(xL)
+    ur, dp = np.full(max(n, 1), -1, np.float32), np.full(max(n, 1), -1, np.float32)
+    stereo_ref_lib().sref_stereo_matches(n, _pp(xL), _pp(yL), _pp(oL), _pp(dL), len(xR), _pp(xR), _pp(yR), _pp(oR), _pp(dR),
+                                         len(sf), _pp(sf), _pp(isf), _pp(bL), _pp(bR), _pp(off), _pp(w), _pp(h), float(mb),
+                                         float(mbf), ur.ctypes.data, dp.ctypes.data)
+    return ur[:n], dp[:n]
+
+
+def r_stereo_from_rgbd(kps, depth, mbf, x_un=None):
+    x, y = _a(kps["x"], np.float32), _a(kps["y"], np.float32)
+    xu = _a(x_un, np.float32)
+    d = np.ascontiguousarray(depth, np.float32)
+    n = len(x)
+    ur, dp = np.full(max(n, 1), -1, np.float32), np.full(max(n, 1), -1, np.float32)
+    stereo_ref_lib().sref_stereo_from_rgbd(n, _pp(x), _pp(y), _pp(xu), d.ctypes.data, d.shape[1], d.shape[0], float(mbf),
+                                           ur.ctypes.data, dp.ctypes.data)
+    return ur[:n], dp[:n]

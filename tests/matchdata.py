@@ -261,3 +261,20 @@ def sim3_scene(seed, n=800, flags=True):
         K2["wx"][lost] = rng.uniform(5, 635, 80).astype(np.float32)
         K2["max_dist"][lost], K2["min_dist"][lost] = _dist_range(K2["wx"][lost], K2["wy"][lost], np.clip(o1[perm][lost], 0, 7))
     return K1, K2, pre12
+
+
+def stereo_pair(seed=0, width=640, height=480, disparity=14, half_pixel=True, tex=None):
+    """A rectified pair cut from one texture: the right image is the left one shifted by `disparity` px (a fronto-parallel
+    plane), optionally blended with the next shift so that the SAD parabola lands between pixels, plus a little noise."""
+    from eaof import synth
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if tex is None:
+        tex = synth.base_texture(width, height, seed=40 + seed)
+    ox, oy = synth.frame_offset(3 * seed)
+    left = tex[oy:oy + height, ox:ox + width].copy()
+    a = tex[oy:oy + height, ox + disparity:ox + disparity + width].astype(np.int32)
+    if half_pixel:
+        b = tex[oy:oy + height, ox + disparity + 1:ox + disparity + 1 + width].astype(np.int32)
+        a = (a + b + 1) >> 1
+    right = np.clip(a + rng.integers(-2, 3, a.shape), 0, 255).astype(np.uint8)
+    return left, right
