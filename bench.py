@@ -175,6 +175,21 @@ def next_rows(eaof, torch, device, ex, d_frames, B, W, H):
                                "keypoints_per_s": B * kp / (ms * 1e-3)}
     del d_depth, ur, dd
 
+    # f-3: Frame::ComputeStereoMatches between two handles (the right camera sees the sequence 7 frames later: a moving
+    # disparity field, enough to exercise band search + SAD refinement)
+    exR = eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=B, device=device)
+    exR.extract_batch_device(d_frames.data_ptr() + 7 * W * H, B)
+    exR.sync()
+    ur = torch.zeros(B * cap, dtype=torch.float32, device=dev)
+    dd = torch.zeros(B * cap, dtype=torch.float32, device=dev)
+    ms = timed(ex.stream_ptr(), lambda: eaof._ck(L.eaof_stereo_matches_device(ex.h, exR.h, B, 0.1, 40.0, ur.data_ptr(), dd.data_ptr())),
+               ex.sync)
+    out["stereo_matches"] = {"workload": f"{B} stereo pairs x {kp:.0f} keypoints, row-band Hamming + 11x11 SAD over 11 shifts on the device pyramids",
+                             "ms_per_batch": ms, "pairs_per_s": B / (ms * 1e-3), "matched_per_pair": float((ur >= 0).sum().item()) / B}
+    ex.sync()
+    exR.close()
+    del ur, dd
+
     # a14: the search step of Fuse / SearchBySim3 (one keyframe, host buffers in and out: a latency number)
     rng = np.random.Generator(np.random.PCG64(3))
     n = 1000

@@ -58,6 +58,11 @@ struct eaof_orb {
     // k_angle_desc (the only writer of those buffers) waits for it
     cudaEvent_t evReader = nullptr;
     bool readerPending = false;
+    // the same for a consumer of the pyramid block (eaof_stereo_matches reads both cameras' level images): the next
+    // batch's level-0 pass waits for it
+    cudaEvent_t evPyrReader = nullptr;
+    bool pyrReaderPending = false;
+    int* dSad = nullptr;  // eaof_stereo_matches scratch, [max_batch][kpCap], lazily allocated
     // batch issued by eaof_orb_extract_batch_async and not yet collected
     int pendN = 0, pendCap = 0;
     eaof_kp* pendKps = nullptr;
@@ -286,6 +291,10 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     const bool prof = c->profiling;
     if (prof) CK(cudaEventRecord(c->ev[0], s));
     CK(cudaMemsetAsync(dCandCount, 0, sizeof(uint32_t) * (size_t)n * g.nlevels, s));
+    if (c->pyrReaderPending) {
+        CK(cudaStreamWaitEvent(s, c->evPyrReader, 0));
+        c->pyrReaderPending = false;
+    }
     {
         const LevelGeom& L = g.L[0];
         dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
@@ -424,6 +433,7 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     CKD(cudaStreamCreateWithFlags(&c->streamOut, cudaStreamNonBlocking));
     CKD(cudaEventCreateWithFlags(&c->evOutIdle, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->evReader, cudaEventDisableTiming));
+    CKD(cudaEventCreateWithFlags(&c->evPyrReader, cudaEventDisableTiming));
     for (int i = 0; i < eaof_orb::kMaxChunks; ++i) {
         CKD(cudaEventCreateWithFlags(&c->evIn[i], cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&c->evDone[i], cudaEventDisableTiming));
@@ -533,6 +543,8 @@ void eaof_orb_destroy(eaof_orb* c) {
     }
     if (c->evOutIdle) cudaEventDestroy(c->evOutIdle);
     if (c->evReader) cudaEventDestroy(c->evReader);
+    if (c->evPyrReader) cudaEventDestroy(c->evPyrReader);
+    cudaFree(c->dSad);
     if (c->streamIn) { cudaStreamSynchronize(c->streamIn); cudaStreamDestroy(c->streamIn); }
     if (c->streamOut) { cudaStreamSynchronize(c->streamOut); cudaStreamDestroy(c->streamOut); }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -665,6 +677,58 @@ int eaof_orb_stereo_from_rgbd(eaof_orb* c, int n, const void* depth, int depthTy
         if (cnt[f] > cap) return fail(EAOF_ERR_ARG, "frame %d has %d keypoints but cap is %d", f, cnt[f], cap);
         memcpy(uRight + (size_t)f * cap, hu.data() + (size_t)f * c->kpCap, sizeof(float) * cnt[f]);
         memcpy(depthOut + (size_t)f * cap, hd.data() + (size_t)f * c->kpCap, sizeof(float) * cnt[f]);
+    }
+    return EAOF_OK;
+}
+
+int eaof_stereo_matches_device(eaof_orb* l, eaof_orb* r, int n, float mb, float mbf, float* dURight, float* dDepth) {
+    if (!l || !r || !dURight || !dDepth || n < 1) return fail(EAOF_ERR_ARG, "bad argument");
+    if (l == r) return fail(EAOF_ERR_ARG, "left and right must be two extractor handles");
+    if (l->device != r->device) return fail(EAOF_ERR_ARG, "both handles must live on one device");
+    if (l->p.width != r->p.width || l->p.height != r->p.height || l->p.nlevels != r->p.nlevels ||
+        l->p.scale_factor != r->p.scale_factor)
+        return fail(EAOF_ERR_ARG, "left and right handles must share frame size and pyramid parameters");
+    if (n > l->lastFrames || n > r->lastFrames) return fail(EAOF_ERR_ARG, "n_frames exceeds the last batch of a handle");
+    if (!(mb > 0)) return fail(EAOF_ERR_ARG, "mb must be positive");
+    CK(cudaSetDevice(l->device));
+    if (!l->dSad) CK(cudaMalloc(&l->dSad, sizeof(int) * (size_t)l->p.max_batch * l->kpCap));
+    cudaStream_t s = l->stream;
+    CK(cudaEventRecord(r->evPyr, r->stream));  // the right camera's batch is complete
+    CK(cudaStreamWaitEvent(s, r->evPyr, 0));
+    eaof::StereoArgs A{};
+    A.kpL = l->dKps; A.descL = l->dDesc; A.cntL = l->dKpCount; A.pyrL = l->dPyr;
+    A.kpR = r->dKps; A.descR = r->dDesc; A.cntR = r->dKpCount; A.pyrR = r->dPyr;
+    A.capL = l->kpCap; A.capR = r->kpCap;
+    for (int i = 0; i < l->p.nlevels; ++i) A.invScale[i] = l->invScale[i];
+    A.mb = mb; A.mbf = mbf;
+    eaof::k_stereo_match<<<dim3((l->kpCap + 7) / 8, n), 256, 0, s>>>(A, dURight, dDepth, l->dSad, l->g);
+    eaof::k_stereo_filter<<<n, 1024, sizeof(int) * (size_t)l->kpCap, s>>>(l->dKpCount, l->kpCap, dURight, dDepth, l->dSad);
+    CK(cudaGetLastError());
+    // the right handle's next batch must not overwrite what these kernels read
+    CK(cudaEventRecord(r->evReader, s));
+    r->readerPending = true;
+    CK(cudaEventRecord(r->evPyrReader, s));
+    r->pyrReaderPending = true;
+    return EAOF_OK;
+}
+
+int eaof_stereo_matches(eaof_orb* l, eaof_orb* r, int n, float mb, float mbf, float* uRight, float* depthOut, int cap) {
+    if (!l || !r || !uRight || !depthOut || n < 1 || n > l->p.max_batch) return fail(EAOF_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(l->device));
+    const size_t outN = (size_t)l->p.max_batch * l->kpCap;
+    if (!l->dURight) { CK(cudaMalloc(&l->dURight, sizeof(float) * outN)); CK(cudaMalloc(&l->dDepthKp, sizeof(float) * outN)); }
+    int rc = eaof_stereo_matches_device(l, r, n, mb, mbf, l->dURight, l->dDepthKp);
+    if (rc) return rc;
+    std::vector<float> hu((size_t)n * l->kpCap), hd((size_t)n * l->kpCap);
+    std::vector<int> cnt(n);
+    CK(cudaMemcpyAsync(hu.data(), l->dURight, sizeof(float) * hu.size(), cudaMemcpyDeviceToHost, l->stream));
+    CK(cudaMemcpyAsync(hd.data(), l->dDepthKp, sizeof(float) * hd.size(), cudaMemcpyDeviceToHost, l->stream));
+    CK(cudaMemcpyAsync(cnt.data(), l->dKpCount, sizeof(int) * n, cudaMemcpyDeviceToHost, l->stream));
+    CK(cudaStreamSynchronize(l->stream));
+    for (int f = 0; f < n; ++f) {
+        if (cnt[f] > cap) return fail(EAOF_ERR_ARG, "frame %d has %d keypoints but cap is %d", f, cnt[f], cap);
+        memcpy(uRight + (size_t)f * cap, hu.data() + (size_t)f * l->kpCap, sizeof(float) * cnt[f]);
+        memcpy(depthOut + (size_t)f * cap, hd.data() + (size_t)f * l->kpCap, sizeof(float) * cnt[f]);
     }
     return EAOF_OK;
 }

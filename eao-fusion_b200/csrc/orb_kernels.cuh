@@ -122,6 +122,145 @@ __global__ void __launch_bounds__(256) k_stereo_from_rgbd(const eaof_kp* __restr
     uRight[o] = ok ? __fsub_rn(xUn ? xUn[o] : kp.x, __fdiv_rn(mbf, d)) : -1.f;
 }
 
+// Frame::ComputeStereoMatches (src/Frame.cc:841-1013) over the results two extractor handles (left / right camera) hold on
+// the device.  k_stereo_match: warp = one left keypoint.  (1) the lanes sweep the right keypoints: row band of the right
+// keypoint contains the left row (:855-866, :885), octave within +-1, u inside [uL - maxD, uL + 3], Hamming distance;
+// warp argmin by (distance, right index) = the reference's first-minimum over ascending iR, accepted below TH_HIGH.
+// (2) sub-pixel refinement on the level images: the 121 pixels of the 11x11 patch are dealt to the lanes, the 11 SADs of
+// (patch - its centre) against the right patches at shifts -5..5 are integer sums reduced across the warp; lane 0 picks
+// the first smallest, fits the parabola (fp32, same operation order) and applies the disparity gates.  sad = -1 where no
+// match survives.  k_stereo_filter: CTA = frame, median of the SADs by rank counting, matches at or above
+// 1.5f*1.4f*median are removed (:1002-1012).
+struct StereoArgs {
+    const eaof_kp* kpL; const uint8_t* descL; const int* cntL; const uint8_t* pyrL;
+    const eaof_kp* kpR; const uint8_t* descR; const int* cntR; const uint8_t* pyrR;
+    int capL, capR;
+    float invScale[EAOF_MAX_LEVELS];
+    float mb, mbf;
+};
+
+__global__ void __launch_bounds__(256) k_stereo_match(StereoArgs A, float* __restrict__ uRight, float* __restrict__ depth,
+                                                      int* __restrict__ sad, const __grid_constant__ Geom g) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (iL >= A.cntL[f]) return;
+    const size_t oL = (size_t)f * A.capL + iL;
+    const eaof_kp kL = A.kpL[oL];
+    const int levelL = kL.octave;
+    const float uL = kL.x, vL = kL.y;
+    const float maxD = __fdiv_rn(A.mbf, A.mb);
+    const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, -3.f);
+    const int row = (int)vL;
+    uint32_t q[8];
+    {
+        const uint4* p = reinterpret_cast<const uint4*>(A.descL + 32 * oL);
+        const uint4 a = p[0], b = p[1];
+        q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+    }
+    unsigned best = 0xffffffffu;  // (distance << 16) | iR
+    const int nR = A.cntR[f];
+    if (!(maxU < 0))
+        for (int iR = lane; iR < nR; iR += 32) {
+            const eaof_kp kR = A.kpR[(size_t)f * A.capR + iR];
+            const float r = __fmul_rn(2.0f, g.L[kR.octave].scale);
+            if (row > (int)ceilf(__fadd_rn(kR.y, r)) || row < (int)floorf(__fsub_rn(kR.y, r))) continue;
+            if (kR.octave < levelL - 1 || kR.octave > levelL + 1) continue;
+            if (!(kR.x >= minU && kR.x <= maxU)) continue;
+            const uint4* p = reinterpret_cast<const uint4*>(A.descR + 32 * ((size_t)f * A.capR + iR));
+            const uint4 a = p[0], b = p[1];
+            const int d = __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
+                          __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+            const unsigned key = ((unsigned)d << 16) | (unsigned)iR;
+            best = key < best ? key : best;
+        }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { const unsigned t = __shfl_xor_sync(0xffffffffu, best, o); best = t < best ? t : best; }
+    float outU = -1.f, outD = -1.f;
+    int outS = -1;
+    if (best != 0xffffffffu && (int)(best >> 16) < 100) {  // bestDist < ORBmatcher::TH_HIGH, :913
+        const LevelGeom& L = g.L[levelL];
+        const float uR0 = A.kpR[(size_t)f * A.capR + (best & 0xffffu)].x;
+        const float sc = A.invScale[levelL];
+        const float scaleduL = roundf(__fmul_rn(uL, sc)), scaledvL = roundf(__fmul_rn(vL, sc)), scaleduR0 = roundf(__fmul_rn(uR0, sc));
+        const float iniu = scaleduR0, endu = __fadd_rn(scaleduR0, 11.f);  // scaleduR0+L-w, scaleduR0+L+w+1 with L = w = 5
+        if (!(iniu < 0 || endu >= (float)L.w)) {
+            const int y0 = (int)(scaledvL - 5.f), x0 = (int)(scaleduL - 5.f), xr = (int)(scaleduR0 - 5.f);
+            const uint8_t* bL = A.pyrL + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(y0 + EAOF_EDGE) * L.pitch + EAOF_INNER_X0;
+            const uint8_t* bR = A.pyrR + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(y0 + EAOF_EDGE) * L.pitch + EAOF_INNER_X0;
+            const int cL = bL[5 * L.pitch + x0 + 5];
+            int acc[11], cR[11];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) { acc[k] = 0; cR[k] = bR[5 * L.pitch + xr + k]; }  // centre of the patch at shift k-5
+            for (int p = lane; p < 121; p += 32) {
+                const int a = p / 11, b = p - a * 11;
+                const int il = (int)bL[a * L.pitch + x0 + b] - cL;
+                const uint8_t* rr = bR + a * L.pitch + xr + b - 5;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) acc[k] += abs(il - ((int)rr[k] - cR[k]));
+            }
+#pragma unroll
+            for (int k = 0; k < 11; ++k)
+#pragma unroll
+                for (int o = 16; o; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            if (lane == 0) {
+                int bestS = 0x7fffffff, bestInc = 0;
+#pragma unroll
+                for (int k = 0; k < 11; ++k)
+                    if ((float)acc[k] < (float)bestS) { bestS = acc[k]; bestInc = k - 5; }
+                if (bestInc != -5 && bestInc != 5) {
+                    float d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+                    for (int k = 1; k < 10; ++k)
+                        if (k - 5 == bestInc) { d1 = (float)acc[k - 1]; d2 = (float)acc[k]; d3 = (float)acc[k + 1]; }
+                    const float deltaR = __fdiv_rn(__fsub_rn(d1, d3),
+                                                   __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+                    if (!(deltaR < -1 || deltaR > 1)) {
+                        float bestuR = __fmul_rn(L.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestInc), deltaR));
+                        float disparity = __fsub_rn(uL, bestuR);
+                        if (disparity >= 0 && disparity < maxD) {
+                            if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                            outD = __fdiv_rn(A.mbf, disparity);
+                            outU = bestuR;
+                            outS = bestS;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { uRight[oL] = outU; depth[oL] = outD; sad[oL] = outS; }
+}
+
+__global__ void __launch_bounds__(1024) k_stereo_filter(const int* __restrict__ cntL, int cap, float* __restrict__ uRight,
+                                                        float* __restrict__ depth, const int* __restrict__ sad) {
+    extern __shared__ int sS[];
+    __shared__ int sMedian, sCount;
+    const int f = blockIdx.x, n = cntL[f], tid = threadIdx.x;
+    const size_t o = (size_t)f * cap;
+    if (tid == 0) { sMedian = -1; sCount = 0; }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = tid; i < n; i += 1024) { const int v = sad[o + i]; sS[i] = v; cnt += v >= 0; }
+    atomicAdd(&sCount, cnt);
+    __syncthreads();
+    const int m = sCount;
+    if (m == 0) return;
+    const int target = m / 2;  // vDistIdx[vDistIdx.size()/2] of the pairs sorted by (SAD, left index)
+    for (int i = tid; i < n; i += 1024) {
+        const int v = sS[i];
+        if (v < 0) continue;
+        int r = 0;
+        for (int j = 0; j < n; ++j) { const int u = sS[j]; r += u >= 0 && (u < v || (u == v && j < i)); }
+        if (r == target) sMedian = v;
+    }
+    __syncthreads();
+    const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)sMedian);
+    for (int i = tid; i < n; i += 1024) {
+        const int v = sS[i];
+        if (v >= 0 && !((float)v < thDist)) { uRight[o + i] = -1.f; depth[o + i] = -1.f; }
+    }
+}
+
 // cv::resize 8UC1 INTER_LINEAR with 11-bit fixed-point coefficients; the border pixel at
 // bordered position (bx,by) equals the resized pixel at the reflected inner position, so resize and
 // copyMakeBorder are one pass.  tabs: per destination column [sx, a0|a1<<16], per row [sy, b0|b1<<16].

@@ -56,6 +56,8 @@ def lib():
         L.eaof_orb_extract_batch_color.argtypes = [vp, vp, ci, ci, ci, sz, sz, ci, ci, vp, vp, ci, vp]
         L.eaof_orb_stereo_from_rgbd_device.argtypes = [vp, ci, vp, ci, C.c_float, sz, sz, vp, C.c_float, vp, vp]
         L.eaof_orb_stereo_from_rgbd.argtypes = [vp, ci, vp, ci, C.c_float, sz, sz, C.c_float, vp, vp, ci]
+        L.eaof_stereo_matches_device.argtypes = [vp, vp, ci, C.c_float, C.c_float, vp, vp]
+        L.eaof_stereo_matches.argtypes = [vp, vp, ci, C.c_float, C.c_float, vp, vp, ci]
         L.eaof_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ci)]
         L.eaof_orb_fetch_results.argtypes = [vp, ci, vp, vp, ci, vp]
         L.eaof_orb_pyramid_level.argtypes = [vp, ci, ci, ci, vp, sz]
@@ -183,6 +185,14 @@ class ORBextractor:
         _ck(self.L.eaof_orb_stereo_from_rgbd(self.h, n, depth.ctypes.data, 1 if depth.dtype == np.uint16 else 0,
                                              float(depth_scale), w * px, w * h * px, float(mbf), ur.ctypes.data,
                                              dd.ctypes.data, self.cap))
+        return ur, dd
+
+    def stereo_matches(self, right: "ORBextractor", n: int, mb: float, mbf: float):
+        """Frame::ComputeStereoMatches (src/Frame.cc:841-1013): self = left camera's extractor, right = the right one,
+        over the first n frames of their last batches.  Returns (mvuRight, mvDepth) as (n, cap)."""
+        ur = np.full((n, self.cap), -1, np.float32)
+        dd = np.full((n, self.cap), -1, np.float32)
+        _ck(self.L.eaof_stereo_matches(self.h, right.h, n, float(mb), float(mbf), ur.ctypes.data, dd.ctypes.data, self.cap))
         return ur, dd
 
     def extract_batch_async(self, frames_ptr: int, n: int, kps_ptr: int, desc_ptr: int):

@@ -144,6 +144,19 @@ int eaof_orb_stereo_from_rgbd(eaof_orb* ctx, int n_frames, const void* depth, in
                               size_t stride_bytes, size_t frame_pitch_bytes, float mbf, float* uright, float* depth_out,
                               int cap);
 
+/* Frame::ComputeStereoMatches()  src/Frame.cc:841-1013 for frames 0..n_frames-1 of the last batches of
+ * two handles, `left` = mpORBextractorLeft and `right` = mpORBextractorRight (same frame size and pyramid parameters,
+ * same device): per left keypoint the best right keypoint by Hamming distance in its row band (+-2*scale rows, octave
+ * within +-1, u in [uL - mbf/mb, uL + 3], distance < TH_HIGH), refined on the two image pyramids — the only readers of
+ * mvImagePyramid — by the 11x11 SAD over shifts -5..5 and a parabola fit; then the 1.5*1.4*median SAD filter.
+ * mvuRight / mvDepth per left keypoint, -1 where unmatched, laid out like eaof_orb_stereo_from_rgbd's outputs.
+ * _device: outputs in device memory ([n_frames][eaof_orb_max_keypoints(left)]), asynchronous on left's stream (which waits
+ * for right's batch; right's next batch waits for this call).  No pyramid ever travels to the host. */
+int eaof_stereo_matches_device(eaof_orb* left, eaof_orb* right, int n_frames, float mb, float mbf, float* d_uright,
+                               float* d_depth);
+int eaof_stereo_matches(eaof_orb* left, eaof_orb* right, int n_frames, float mb, float mbf, float* uright, float* depth_out,
+                        int cap);
+
 /* Device-resident results of the last batch: kps[f*cap_out + i], desc[(f*cap_out + i)*32], counts[f].
  * cap_out == eaof_orb_max_keypoints(). */
 int eaof_orb_device_results(eaof_orb* ctx, const eaof_kp** d_kps, const uint8_t** d_desc, const int** d_counts,

@@ -257,3 +257,47 @@ def test_stereo_from_rgbd(ex640, frames640, kind):
         assert np.array_equal(ur[f, :len(k)], our) and np.array_equal(dd[f, :len(k)], odd), f
         tot += int(np.sum(odd > 0))
     assert tot > 1000
+
+
+@pytest.mark.parametrize("disparity,half,mb,mbf", [(14, True, 0.1, 40.0), (3, False, 0.1, 40.0), (60, True, 0.5, 20.0), (0, False, 0.1, 40.0)])
+def test_stereo_matches(disparity, half, mb, mbf):
+    """Two extractor handles (left / right camera), ComputeStereoMatches on the device against the oracle fed with the
+    same keypoints and the handles' own pyramids (which are the oracle's, test_stages_match_oracle)."""
+    import eaof
+    from matchdata import stereo_pair
+    from oracle import pyoracle as po
+    n = 3
+    pairs = [stereo_pair(seed, disparity=disparity, half_pixel=half) for seed in range(n)]
+    exL = eaof.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480, max_batch=n)
+    exR = eaof.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480, max_batch=n)
+    resL = exL.extract_batch(np.stack([p[0] for p in pairs]))
+    resR = exR.extract_batch(np.stack([p[1] for p in pairs]))
+    ur, dd = exL.stereo_matches(exR, n, mb, mbf)
+    sf, isf = exL.GetScaleFactors(), exL.GetInverseScaleFactors()
+    total = 0
+    for f in range(n):
+        pL = [exL.pyramid_level(l, frame=f, with_border=True) for l in range(8)]
+        pR = [exR.pyramid_level(l, frame=f, with_border=True) for l in range(8)]
+        kL, dL = resL[f]
+        kR, dR = resR[f]
+        ou, od, _ = po.o_stereo_matches(kL, dL, kR, dR, pL, pR, sf, isf, mb, mbf)
+        assert np.array_equal(ur[f, :len(kL)], ou) and np.array_equal(dd[f, :len(kL)], od), (f, int(np.sum(ur[f, :len(kL)] != ou)))
+        total += int(np.sum(ou >= 0))
+    assert total > 600 or disparity >= mbf / mb - 2
+    # the next batches of both handles (writers of what the stereo kernels read) still produce the right results
+    again = exR.extract_batch(np.stack([p[0] for p in pairs]))
+    assert all(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) for a, b in zip(again, resL))
+    exL.close()
+    exR.close()
+
+
+def test_stereo_matches_rejects_mismatched_handles():
+    import eaof
+    a = eaof.ORBextractor(500, 1.2, 8, 20, 7, width=320, height=240, max_batch=1)
+    b = eaof.ORBextractor(500, 1.2, 8, 20, 7, width=322, height=240, max_batch=1)
+    with pytest.raises(eaof.EaofError):
+        a.stereo_matches(b, 1, 0.1, 40.0)
+    with pytest.raises(eaof.EaofError):
+        a.stereo_matches(a, 1, 0.1, 40.0)
+    a.close()
+    b.close()
