@@ -151,6 +151,21 @@ def next_rows(eaof, torch, device, ex, d_frames, B, W, H):
                             "words_per_frame": float(nw.float().mean().item()),
                             "alg_bytes_per_descriptor": 6 * 10 * 32 + 32,
                             "achieved_gbs": B * kp * (6 * 10 * 32 + 32) / (ms * 1e-3) / 1e9}
+    # f-2 -> a12: SearchByBoW between consecutive frames on the FeatureVectors that just landed in HBM (the
+    # TrackReferenceKeyFrame shape: nodes at level L - 4, about ten features per node and frame)
+    mtb = eaof.ORBmatcher(0.7, True, max_features=cap, max_pairs=B, device=device)
+    pq, pt = np.arange(0, B - 1, dtype=np.int32), np.arange(1, B, dtype=np.int32)
+    bm_ = torch.empty((B - 1, cap), dtype=torch.int32, device=dev)
+    bd_ = torch.empty((B - 1, cap), dtype=torch.int32, device=dev)
+    bn_ = torch.zeros(B - 1, dtype=torch.int32, device=dev)
+    voc.sync()
+    ms = timed(mtb.stream_ptr(), lambda: mtb.bow_orb_device(ex, B, 0, pq, pt, nn.data_ptr(), ni.data_ptr(), ns.data_ptr(),
+                                                            fi.data_ptr(), bm_.data_ptr(), bd_.data_ptr(), bn_.data_ptr()), mtb.sync)
+    out["search_by_bow_device"] = {"workload": f"{B - 1} consecutive-frame pairs, SearchByBoW(KF,F) on device-resident FeatureVectors, ratio 0.7, rot-hist",
+                                   "ms_per_batch": ms, "pairs_per_s": (B - 1) / (ms * 1e-3),
+                                   "matches_per_pair": float(bn_.float().mean().item()),
+                                   "fv_nodes_per_frame": float(nn.float().mean().item())}
+    mtb.close()
     voc.sync()
     voc.close()
 

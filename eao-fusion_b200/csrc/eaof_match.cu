@@ -26,6 +26,10 @@
 #include "../../include/eaof_match.h"
 
 extern "C" int eaof_internal_fail(int code, const char* msg);  // sets eaof_last_error (eaof_orb.cu)
+// device-resident results of an extractor handle, and the hook that makes its next batch wait for a reader (eaof_orb.cu)
+extern "C" int eaof_internal_orb_view(eaof_orb* ex, const eaof_kp** kps, const uint8_t** desc, const int** counts, int* cap,
+                                      int* w, int* h, const float** scale, int* nlevels, void** stream);
+extern "C" int eaof_internal_orb_note_reader(eaof_orb* ex, void* readerStream);
 
 namespace {
 
@@ -96,6 +100,11 @@ struct BowArgs {
     const int* idxT;
     const BowSeg* segs;       // segments of all pairs (NULL = one segment covering everything)
     const int* segStart;      // [pair+1] (NULL with segs)
+    // device-built plans (eaof_match_bow_orb_device): segments laid out [pair][stride] with segCount[pair] entries, and
+    // node-sorted feature lists per block (FeatureVector of every frame) from which idxQ / idxT derive through pairQ / pairT
+    const int* segCount;
+    const uint32_t* featIdx;
+    int featStride;
     int nQhost, nThost;       // used when counts == NULL
     int stride;               // per-pair stride of the workspace arrays (= max_features)
     int mode;
@@ -181,6 +190,96 @@ __global__ void __launch_bounds__(BOW_QT) k_bow_dense(BowArgs A, const int2* __r
     }
 }
 
+// Device-built plan of a SearchByBoW pair (src/ORBmatcher.cc:182-264: the merge-walk of the two FeatureVectors): warp =
+// pair; lanes take the query frame's nodes 32 at a time, look each one up in the target frame's ascending node list and
+// the hits are appended in node order.  FeatureVectors in the layout eaof_voc_transform_orb_device leaves.
+__global__ void __launch_bounds__(32) k_bow_plan(BowArgs A, const int* __restrict__ nFNodes, const uint32_t* __restrict__ nodeIds,
+                                                 const int* __restrict__ nodeStart, BowSeg* __restrict__ segs,
+                                                 int* __restrict__ segCount) {
+    const int pair = blockIdx.x, lane = threadIdx.x;
+    const int bq = A.pairQ[pair], bt = A.pairT[pair];
+    const int nNQ = nFNodes[bq], nNT = nFNodes[bt];
+    const uint32_t* idQ = nodeIds + (size_t)bq * A.featStride;
+    const uint32_t* idT = nodeIds + (size_t)bt * A.featStride;
+    const int* stQ = nodeStart + (size_t)bq * (A.featStride + 1);
+    const int* stT = nodeStart + (size_t)bt * (A.featStride + 1);
+    BowSeg* out = segs + (size_t)pair * A.stride;
+    const unsigned below = (1u << lane) - 1;
+    int n = 0;
+    for (int a0 = 0; a0 < nNQ; a0 += 32) {
+        const int a = a0 + lane;
+        BowSeg s{0, 0, 0, 0};
+        bool hit = false;
+        if (a < nNQ) {
+            const uint32_t id = idQ[a];
+            int lo = 0, hi = nNT;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (idT[mid] < id) lo = mid + 1; else hi = mid; }
+            if (lo < nNT && idT[lo] == id) {
+                s = BowSeg{stQ[a], stQ[a + 1] - stQ[a], stT[lo], stT[lo + 1] - stT[lo]};
+                hit = s.qCnt > 0 && s.tCnt > 0;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) out[n + __popc(m & below)] = s;
+        n += __popc(m);
+    }
+    if (lane == 0) segCount[pair] = n;
+}
+
+// phase 1 for planned pairs: thread = one position of the query frame's node-sorted feature list; the thread finds the
+// segment its position falls in and scans that node's target features straight from global memory (a vocabulary node
+// holds about ten features of a frame: nothing to stage).  Same near-list output as k_bow_dense.
+__global__ void __launch_bounds__(BOW_QT) k_bow_dense_nodes(BowArgs A, uint32_t* __restrict__ nearBuf) {
+    const int pair = blockIdx.y, p = blockIdx.x * BOW_QT + threadIdx.x;
+    const int nSeg = A.segCount[pair];
+    const BowSeg* segs = A.segs + (size_t)pair * A.stride;
+    int lo = 0, hi = nSeg;  // last segment with qOff <= p
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (segs[mid].qOff <= p) lo = mid + 1; else hi = mid; }
+    if (lo == 0) return;
+    const BowSeg s = segs[lo - 1];
+    if (p >= s.qOff + s.qCnt) return;
+    const int bq = A.pairQ[pair], bt = A.pairT[pair];
+    const uint8_t* dQ = A.desc + (size_t)bq * A.blockStride * 32;
+    const uint8_t* dT = A.desc + (size_t)bt * A.blockStride * 32;
+    const int* idxQ = reinterpret_cast<const int*>(A.featIdx + (size_t)bq * A.featStride);
+    const int* idxT = reinterpret_cast<const int*>(A.featIdx + (size_t)bt * A.featStride);
+    const int q = idxQ[p];
+    uint32_t qd[8];
+    {
+        const uint4* pq = reinterpret_cast<const uint4*>(dQ + 32 * (size_t)q);
+        const uint4 a = pq[0], b = pq[1];
+        qd[0] = a.x; qd[1] = a.y; qd[2] = a.z; qd[3] = a.w; qd[4] = b.x; qd[5] = b.y; qd[6] = b.z; qd[7] = b.w;
+    }
+    uint32_t near[NEAR_K];
+#pragma unroll
+    for (int i = 0; i < NEAR_K; ++i) near[i] = 0xffffffffu;
+    int cnt = 0;
+    for (int tp = s.tOff; tp < s.tOff + s.tCnt; ++tp) {
+        const int t = idxT[tp];
+        uint32_t td[8];
+        const uint4* pt = reinterpret_cast<const uint4*>(dT + 32 * (size_t)t);
+        const uint4 a = __ldg(pt), b = __ldg(pt + 1);
+        td[0] = a.x; td[1] = a.y; td[2] = a.z; td[3] = a.w; td[4] = b.x; td[5] = b.y; td[6] = b.z; td[7] = b.w;
+        const int d = hamming256_csa(qd, td);
+        if (d < A.D) {
+            if (cnt < NEAR_K) {
+                const uint32_t e = (uint32_t)t | ((uint32_t)d << 16);
+#pragma unroll
+                for (int i = 0; i < NEAR_K; ++i) if (i == cnt) near[i] = e;
+            }
+            ++cnt;
+        }
+    }
+    uint32_t* o = nearBuf + ((size_t)pair * A.stride + q) * 8;
+    reinterpret_cast<uint4*>(o)[0] = make_uint4(near[0], near[1], near[2], near[3]);
+    reinterpret_cast<uint4*>(o)[1] = make_uint4(near[4], near[5], near[6], (uint32_t)cnt);
+}
+
+__global__ void __launch_bounds__(256) k_kp_angles(const eaof_kp* __restrict__ kps, int n, float* __restrict__ angle) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) angle[i] = kps[i].angle;
+}
+
 // ComputeThreeMaxima, src/ORBmatcher.cc:1603-1644
 __device__ void three_maxima(const int* hist, int& i1, int& i2, int& i3) {
     int max1 = 0, max2 = 0, max3 = 0;
@@ -216,8 +315,10 @@ __global__ void __launch_bounds__(32) k_bow_resolve(BowArgs A, const uint32_t* _
     const uint8_t* dT = A.desc + (size_t)bt * A.blockStride * 32;
     const float* angQ = A.angle + (size_t)bq * A.blockStride;
     const float* angT = A.angle + (size_t)bt * A.blockStride;
-    const int* idxQ = A.idxQ ? A.idxQ + (size_t)pair * A.stride : nullptr;
-    const int* idxT = A.idxT ? A.idxT + (size_t)pair * A.stride : nullptr;
+    const int* idxQ = A.featIdx ? reinterpret_cast<const int*>(A.featIdx + (size_t)bq * A.featStride)
+                                : (A.idxQ ? A.idxQ + (size_t)pair * A.stride : nullptr);
+    const int* idxT = A.featIdx ? reinterpret_cast<const int*>(A.featIdx + (size_t)bt * A.featStride)
+                                : (A.idxT ? A.idxT + (size_t)pair * A.stride : nullptr);
     const uint8_t* validQ = A.validQ ? A.validQ + (size_t)pair * A.stride : nullptr;
     const uint8_t* validT = (A.validT && A.mode == EAOF_BOW_KF_KF) ? A.validT + (size_t)pair * A.stride : nullptr;
     const int nOut = A.mode == EAOF_BOW_KF_FRAME ? nt : nq;
@@ -237,10 +338,11 @@ __global__ void __launch_bounds__(32) k_bow_resolve(BowArgs A, const uint32_t* _
 
     const float factor = 1.0f / EAOF_HISTO_LENGTH;  // :172, :541
     int nAcc = 0;
-    const int nSeg = A.segs ? (A.segStart[pair + 1] - A.segStart[pair]) : 1;
+    const int nSeg = A.segCount ? A.segCount[pair] : (A.segs ? (A.segStart[pair + 1] - A.segStart[pair]) : 1);
+    const size_t segBase = A.segCount ? (size_t)pair * A.stride : (A.segs ? (size_t)A.segStart[pair] : 0);
     for (int si = 0; si < nSeg; ++si) {
         BowSeg s;
-        if (A.segs) s = A.segs[A.segStart[pair] + si];
+        if (A.segs) s = A.segs[segBase + si];
         else s = BowSeg{0, nq, 0, nt};
         for (int q0 = s.qOff; q0 < s.qOff + s.qCnt; q0 += 32) {
             const int myPos = q0 + lane;
@@ -1282,6 +1384,10 @@ struct eaof_matcher {
     int *pairIdx = nullptr;     // [4][maxPairs] device copies of pair arrays / shifts
     float* pairShift = nullptr; // [2][maxPairs]
     int *outMatch = nullptr, *outDist = nullptr, *outN = nullptr;
+    // eaof_match_bow_orb_device: per-pair plans and the extractor's keypoint angles as a plain array (lazily allocated)
+    BowSeg* segsBatch = nullptr;  // [maxPairs][maxFeat]
+    int* segCountBatch = nullptr; // [maxPairs]
+    float* orbAngle = nullptr;    // [(maxPairs+1) * maxFeat]
     long long lastDistances = 0;
     // Small per-call host arrays (pair lists, shifts) go through a pinned staging buffer: cudaMemcpyAsync from pageable
     // memory would synchronise the stream first and stall the caller behind the extraction the stream waits for.
@@ -1360,7 +1466,8 @@ void eaof_matcher_destroy(eaof_matcher* m) {
     void* ptrs[] = {m->nearBuf, m->accBuf, m->cellStart, m->cellIdx, m->cx, m->cy, m->cangle, m->curight, m->lu, m->lv,
                     m->linvz, m->langle, m->coct, m->loct, m->nC, m->nL, m->cRow, m->lRow, m->ctaken, m->lvalid, m->lobs,
                     m->desc2, m->angle2, m->validQ, m->validT, m->idxQ, m->idxT, m->segs, m->segStart, m->tiles,
-                    m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN, m->qRadius, m->qMaxL, m->initBin, m->cellPack};
+                    m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN, m->qRadius, m->qMaxL, m->initBin, m->cellPack,
+                    m->segsBatch, m->segCountBatch, m->orbAngle};
     for (void* p : ptrs) cudaFree(p);
     if (m->evDep) cudaEventDestroy(m->evDep);
     if (m->evStage) cudaEventDestroy(m->evStage);
@@ -1585,6 +1692,49 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, i
     MCK(cudaGetLastError());
     m->lastDistances = -1;  // counts live on the device; the caller knows nQ*nT per pair
     return EAOF_OK;
+}
+
+int eaof_match_bow_orb_device(eaof_matcher* m, eaof_orb* ex, int nFrames, int mode, float ratio, int checkOri, int nPairs,
+                              const int* pairQ, const int* pairT, const int* dNFNodes, const uint32_t* dNodeIds,
+                              const int* dNodeStart, const uint32_t* dFeatIdx, int* dMatch, int* dDist, int* dN) {
+    if (!m || !ex || !pairQ || !pairT || !dNFNodes || !dNodeIds || !dNodeStart || !dFeatIdx || !dMatch || !dN)
+        return mfail(EAOF_ERR_ARG, "null argument");
+    if (nPairs < 1 || nPairs > m->maxPairs) return mfail(EAOF_ERR_ARG, "n_pairs %d outside [1,%d]", nPairs, m->maxPairs);
+    if (mode != EAOF_BOW_KF_FRAME && mode != EAOF_BOW_KF_KF) return mfail(EAOF_ERR_ARG, "unknown mode");
+    const eaof_kp* kps; const uint8_t* desc; const int* counts; const float* scale;
+    int cap, W, H, nlevels; void* exStream;
+    int rc = eaof_internal_orb_view(ex, &kps, &desc, &counts, &cap, &W, &H, &scale, &nlevels, &exStream);
+    if (rc) return rc;
+    if (cap > m->maxFeat) return mfail(EAOF_ERR_ARG, "extractor keypoint capacity %d exceeds matcher max_features %d", cap, m->maxFeat);
+    if (nFrames < 1 || (size_t)nFrames * cap > (size_t)(m->maxPairs + 1) * m->maxFeat)
+        return mfail(EAOF_ERR_ARG, "n_frames %d does not fit a matcher of %d pairs", nFrames, m->maxPairs);
+    for (int p = 0; p < nPairs; ++p)
+        if (pairQ[p] < 0 || pairQ[p] >= nFrames || pairT[p] < 0 || pairT[p] >= nFrames) return mfail(EAOF_ERR_ARG, "pair %d names a frame outside [0,%d)", p, nFrames);
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    if (!m->segsBatch) {
+        MCK(cudaMalloc(&m->segsBatch, sizeof(BowSeg) * (size_t)m->maxPairs * m->maxFeat));
+        MCK(cudaMalloc(&m->segCountBatch, sizeof(int) * (size_t)m->maxPairs));
+        MCK(cudaMalloc(&m->orbAngle, sizeof(float) * (size_t)(m->maxPairs + 1) * m->maxFeat));
+    }
+    if (m->upload_words(0, pairQ, nPairs, m->pairIdx) || m->upload_words(1, pairT, nPairs, m->pairIdx + m->maxPairs))
+        return mfail(EAOF_ERR_CUDA, "pair list upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    MCK(cudaEventRecord(m->evDep, (cudaStream_t)exStream));
+    MCK(cudaStreamWaitEvent(s, m->evDep, 0));
+    k_kp_angles<<<(nFrames * cap + 255) / 256, 256, 0, s>>>(kps, nFrames * cap, m->orbAngle);
+    BowArgs A{};
+    A.desc = desc; A.angle = m->orbAngle; A.counts = counts; A.pairQ = m->pairIdx; A.pairT = m->pairIdx + m->maxPairs;
+    A.blockStride = cap; A.stride = cap; A.mode = mode; A.segs = m->segsBatch; A.segCount = m->segCountBatch;
+    A.featIdx = dFeatIdx; A.featStride = cap;
+    A.thEff = mode == EAOF_BOW_KF_FRAME ? EAOF_TH_LOW : EAOF_TH_LOW - 1;
+    A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
+    k_bow_plan<<<nPairs, 32, 0, s>>>(A, dNFNodes, dNodeIds, dNodeStart, m->segsBatch, m->segCountBatch);
+    k_bow_dense_nodes<<<dim3((cap + BOW_QT - 1) / BOW_QT, nPairs), BOW_QT, 0, s>>>(A, m->nearBuf);
+    const size_t bm = sizeof(uint32_t) * ((cap + 31) / 32);
+    k_bow_resolve<<<nPairs, 32, bm, s>>>(A, m->nearBuf, m->accBuf, dMatch, dDist, dN);
+    MCK(cudaGetLastError());
+    m->lastDistances = -1;
+    return eaof_internal_orb_note_reader(ex, (void*)s);
 }
 
 static int run_projection(eaof_matcher* m, ProjArgs& A, int nPairs, int maxL, int* dMatch, int* dDist, int* dN) {

@@ -309,6 +309,7 @@ def _mlib():
         L.eaof_match_windows_independent.argtypes = ([vp, ci, ci] + [vp] * 5 + [cf] * 4 + [vp, ci, ci] + [vp] * 8 +
                                                      [ci, vp, vp, C.POINTER(ci)])
         L.eaof_distinctive_descriptors.argtypes = [vp, ci, vp, vp, vp, vp]
+        L.eaof_match_bow_orb_device.argtypes = [vp, vp, ci, ci, cf, ci, ci] + [vp] * 9
         L.eaof_matcher_last_distance_count.restype = C.c_longlong
         L.eaof_matcher_last_distance_count.argtypes = [vp]
         _mlib_ready = True
@@ -539,6 +540,12 @@ class ORBmatcher:
         sx, sy = _arr(shift_x, np.float32), _arr(shift_y, np.float32)
         _ck(self.L.eaof_match_projection_batch_device(self.h, ex.h, len(lf), _p(lf), _p(cf_), _p(sx), _p(sy), float(th),
                                                       d_match, d_dist, d_n))
+
+    def bow_orb_device(self, ex: "ORBextractor", n_frames, mode, pair_q, pair_t, d_nn, d_ni, d_ns, d_fi, d_match, d_dist, d_n):
+        """eaof_match_bow_orb_device: SearchByBoW between frames of an extractor batch with device-resident FeatureVectors."""
+        pq, pt = _arr(pair_q, np.int32), _arr(pair_t, np.int32)
+        _ck(self.L.eaof_match_bow_orb_device(self.h, ex.h, int(n_frames), int(mode), self.mfNNratio, int(self.mbCheckOrientation),
+                                             len(pq), _p(pq), _p(pt), d_nn, d_ni, d_ns, d_fi, d_match, d_dist, d_n))
 
     def bruteforce_batch_device(self, mode, pair_q, pair_t, d_desc, d_angle, d_counts, block_stride, d_match, d_dist, d_n):
         pq, pt = _arr(pair_q, np.int32), _arr(pair_t, np.int32)

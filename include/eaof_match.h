@@ -183,6 +183,18 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float nnratio,
                                        const float* d_angle, const int* d_counts, int block_stride, int* d_match,
                                        int* d_dist, int* d_nmatches);
 
+/* SearchByBoW over frames that never leave the device: descriptors and keypoint angles of the extractor handle's last
+ * batch (frames 0..n_frames-1), FeatureVectors as eaof_voc_transform_orb_device (include/eaof_voc.h) left them
+ * (d_n_fnodes[f], d_node_ids[f*cap + j], d_node_start[f*(cap+1) + j], d_feat_idx[f*cap + i], cap =
+ * eaof_orb_max_keypoints).  Pair p: queries = frame pair_q[p] (the KeyFrame side), targets = frame pair_t[p]; every
+ * feature counts as holding a good map point.  The merge-walk of the two FeatureVectors (src/ORBmatcher.cc:182-264) is
+ * planned on the device.  Outputs as eaof_match_bow, laid out [pair][cap].  Asynchronous on the matcher's stream after
+ * the extractor's; the caller orders it after the vocabulary's stream (eaof_voc_sync, or an event). */
+int eaof_match_bow_orb_device(eaof_matcher* m, eaof_orb* ex, int n_frames, int mode, float nnratio, int check_orientation,
+                              int n_pairs, const int* pair_q, const int* pair_t, const int* d_n_fnodes,
+                              const uint32_t* d_node_ids, const int* d_node_start, const uint32_t* d_feat_idx, int* d_match,
+                              int* d_dist, int* d_nmatches);
+
 /* Micro-benchmark: POPC32 thread-instructions per second this device sustains with every SM busy (the issue-rate
  * roofline of the Hamming kernels); negative on error. */
 double eaof_debug_popc_rate(int device);

@@ -118,3 +118,53 @@ def test_dropin_vocabulary_class(case):
         d.close()
     finally:
         os.unlink(path)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_search_by_bow_device_resident_end_to_end(frames640, mode):
+    """extraction -> ORBVocabulary::transform -> SearchByBoW, nothing leaving the device in between; per pair against the
+    oracle's SearchByBoW fed with the oracle's FeatureVectors (TrackReferenceKeyFrame / loop-candidate shape)."""
+    import torch
+    import eaof
+    from oracle import pyoracle as po
+    voc = make_vocabulary(10, 4, 0, 0, seed=5)
+    tree = tree_from(voc)
+    n = 5
+    ex = eaof.ORBextractor(1000, 1.2, 8, 20, 7, width=640, height=480, max_batch=n)
+    res = ex.extract_batch(frames640[:n])
+    cap = ex.cap
+    v = eaof.ORBVocabulary(tree, max_features=cap, max_sets=n)
+    mt = eaof.ORBmatcher(0.7, True, max_features=cap, max_pairs=8)
+    dev = torch.device("cuda:0")
+    nw, nn = torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n, dtype=torch.int32, device=dev)
+    wi, ni, fi = (torch.zeros(n * cap, dtype=torch.int32, device=dev) for _ in range(3))
+    wv = torch.zeros(n * cap, dtype=torch.float64, device=dev)
+    ns = torch.zeros(n * (cap + 1), dtype=torch.int32, device=dev)
+    levelsup = 2
+    v.transform_orb_device(ex, n, levelsup, nw.data_ptr(), wi.data_ptr(), wv.data_ptr(), nn.data_ptr(), ni.data_ptr(), ns.data_ptr(),
+                           fi.data_ptr())
+    v.sync()
+    pq = np.array([0, 1, 2, 3, 4, 0], np.int32)
+    pt = np.array([1, 2, 3, 4, 0, 0], np.int32)
+    d_match = torch.full((len(pq), cap), -7, dtype=torch.int32, device=dev)
+    d_dist = torch.full((len(pq), cap), -7, dtype=torch.int32, device=dev)
+    d_n = torch.zeros(len(pq), dtype=torch.int32, device=dev)
+    mt.bow_orb_device(ex, n, mode, pq, pt, nn.data_ptr(), ni.data_ptr(), ns.data_ptr(), fi.data_ptr(), d_match.data_ptr(),
+                      d_dist.data_ptr(), d_n.data_ptr())
+    mt.sync()
+    fvs = [po.o_voc_transform(tree, res[f][1], levelsup) for f in range(n)]
+    total = 0
+    for p, (q, t) in enumerate(zip(pq, pt)):
+        kq, dq = res[q]
+        kt, dt = res[t]
+        nodes_q = (fvs[q][2].astype(np.int32), fvs[q][3], fvs[q][4].astype(np.int32))
+        nodes_t = (fvs[t][2].astype(np.int32), fvs[t][3], fvs[t][4].astype(np.int32))
+        on, om, od = po.o_search_by_bow(mode, 0.7, True, dq, kq["angle"], None, nodes_q, dt, kt["angle"], None, nodes_t)
+        nout = len(kt) if mode == 0 else len(kq)
+        assert int(d_n[p]) == on, (p, int(d_n[p]), on)
+        assert np.array_equal(d_match[p, :nout].cpu().numpy(), om) and np.array_equal(d_dist[p, :nout].cpu().numpy(), od), p
+        total += on
+    assert total > 1000
+    mt.close()
+    v.close()
+    ex.close()
