@@ -701,7 +701,9 @@ int eaof_stereo_matches_device(eaof_orb* l, eaof_orb* r, int n, float mb, float 
     A.capL = l->kpCap; A.capR = r->kpCap;
     for (int i = 0; i < l->p.nlevels; ++i) A.invScale[i] = l->invScale[i];
     A.mb = mb; A.mbf = mbf;
-    eaof::k_stereo_match<<<dim3((l->kpCap + 7) / 8, n), 256, 0, s>>>(A, dURight, dDepth, l->dSad, l->g);
+    const size_t smemMatch = (size_t)r->kpCap * 9 + 16;
+    if (smemMatch > 48 * 1024) CK(cudaFuncSetAttribute(eaof::k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMatch));
+    eaof::k_stereo_match<<<dim3((l->kpCap + 15) / 16, n), 512, smemMatch, s>>>(A, dURight, dDepth, l->dSad, l->g);
     eaof::k_stereo_filter<<<n, 1024, sizeof(int) * (size_t)l->kpCap, s>>>(l->dKpCount, l->kpCap, dURight, dDepth, l->dSad);
     CK(cudaGetLastError());
     // the right handle's next batch must not overwrite what these kernels read

@@ -139,11 +139,26 @@ struct StereoArgs {
     float mb, mbf;
 };
 
-__global__ void __launch_bounds__(256) k_stereo_match(StereoArgs A, float* __restrict__ uRight, float* __restrict__ depth,
+__global__ void __launch_bounds__(512) k_stereo_match(StereoArgs A, float* __restrict__ uRight, float* __restrict__ depth,
                                                       int* __restrict__ sad, const __grid_constant__ Geom g) {
+    // the right frame's keypoints, staged once per CTA in the form the sweep tests: row band (minr | maxr << 16), u, octave
+    extern __shared__ __align__(16) unsigned char stereoSmem[];
+    const int nR = A.cntR[blockIdx.y];
+    int* sBand = reinterpret_cast<int*>(stereoSmem);
+    float* sU = reinterpret_cast<float*>(sBand + A.capR);
+    unsigned char* sOct = reinterpret_cast<unsigned char*>(sU + A.capR);
     const int f = blockIdx.y, lane = threadIdx.x & 31;
+    for (int iR = threadIdx.x; iR < nR; iR += blockDim.x) {
+        const eaof_kp kR = A.kpR[(size_t)f * A.capR + iR];
+        const float r = __fmul_rn(2.0f, g.L[kR.octave].scale);
+        const int maxr = (int)ceilf(__fadd_rn(kR.y, r)), minr = (int)floorf(__fsub_rn(kR.y, r));
+        sBand[iR] = (max(minr, 0) & 0xffff) | (max(maxr, -1) << 16);  // rows are >= 0; a band ending above row 0 holds none
+        sU[iR] = kR.x;
+        sOct[iR] = (unsigned char)kR.octave;
+    }
+    __syncthreads();
     const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (iL >= A.cntL[f]) return;
+    if (iL >= A.cntL[f]) return;  // no CTA-wide barrier below
     const size_t oL = (size_t)f * A.capL + iL;
     const eaof_kp kL = A.kpL[oL];
     const int levelL = kL.octave;
@@ -158,14 +173,14 @@ __global__ void __launch_bounds__(256) k_stereo_match(StereoArgs A, float* __res
         q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
     }
     unsigned best = 0xffffffffu;  // (distance << 16) | iR
-    const int nR = A.cntR[f];
     if (!(maxU < 0))
         for (int iR = lane; iR < nR; iR += 32) {
-            const eaof_kp kR = A.kpR[(size_t)f * A.capR + iR];
-            const float r = __fmul_rn(2.0f, g.L[kR.octave].scale);
-            if (row > (int)ceilf(__fadd_rn(kR.y, r)) || row < (int)floorf(__fsub_rn(kR.y, r))) continue;
-            if (kR.octave < levelL - 1 || kR.octave > levelL + 1) continue;
-            if (!(kR.x >= minU && kR.x <= maxU)) continue;
+            const int band = sBand[iR];
+            if (row < (band & 0xffff) || row > (band >> 16)) continue;
+            const int oR = sOct[iR];
+            if (oR < levelL - 1 || oR > levelL + 1) continue;
+            const float uR = sU[iR];
+            if (!(uR >= minU && uR <= maxU)) continue;
             const uint4* p = reinterpret_cast<const uint4*>(A.descR + 32 * ((size_t)f * A.capR + iR));
             const uint4 a = p[0], b = p[1];
             const int d = __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
