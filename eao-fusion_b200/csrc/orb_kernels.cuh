@@ -468,6 +468,9 @@ __device__ __forceinline__ unsigned arc_best2(const unsigned (&d)[16]) {
 #define FAST_MINB 8
 #endif
 #define FAST_CLST 128
+#ifndef FAST_PRETEST_SWAR
+#define FAST_PRETEST_SWAR 1  // 0: the compass test on u16x2 lanes (two adjacent compass pixels on the same side)
+#endif
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8_t* __restrict__ pyr,
                                                                      const CellDesc* __restrict__ cells,
                                                                      uint32_t* __restrict__ cand,
@@ -529,6 +532,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     for (int attempt = 0; attempt < 2 && no == 0; ++attempt) {
         const int th = attempt == 0 ? g.iniTh : g.minTh;
         const unsigned thB2 = (unsigned)(th + 256) * 0x00010001u;
+        const bool thHigh = th >= 128;
+        const unsigned thK = (unsigned)(127 - (th & 127)) * 0x01010101u;
         // ---- (A)
         int nl = 0;
         for (int i0 = 0; i0 < nTasks; i0 += 32) {
@@ -542,6 +547,20 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                 const uint32_t* t = tile + y * PW + 1 + w;
                 const unsigned W0 = t[0], Wm = t[-1], Wp = t[1], Wu = t[-3 * PW], Wd = t[3 * PW];
                 const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
+#if FAST_PRETEST_SWAR
+                // Every 9-arc of the ring holds one of the pixels {0, 8} and one of {4, 12}, so a corner at threshold th
+                // has |ring - centre| > th on one pixel of each pair.  Four pixels at once: VABSDIFF4 against the words
+                // 3 rows below / above and 3 columns right / left, "byte > th" as a carry into bit 7 of each byte
+                // (low 7 bits + 127 - th', combined with the byte's own top bit: OR for th < 128, AND for th >= 128).
+                const unsigned a0 = __vabsdiffu4(W0, Wd), a8 = __vabsdiffu4(W0, Wu);
+                const unsigned a4 = __vabsdiffu4(W0, V4), a12 = __vabsdiffu4(W0, V12);
+                const unsigned t0 = (a0 & 0x7f7f7f7fu) + thK, t8 = (a8 & 0x7f7f7f7fu) + thK;
+                const unsigned t4 = (a4 & 0x7f7f7f7fu) + thK, t12 = (a12 & 0x7f7f7f7fu) + thK;
+                const unsigned m = thHigh ? ((t0 & a0) | (t8 & a8)) & ((t4 & a4) | (t12 & a12))
+                                          : ((t0 | a0) | (t8 | a8)) & ((t4 | a4) | (t12 | a12));
+                passE = (m & 0x00800080u) != 0;  // pixels 0, 2 of the word
+                passO = (m & 0x80008000u) != 0;  // pixels 1, 3
+#else
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const unsigned nc = FAST_BIAS2 - (h ? odd(W0) : evn(W0));
@@ -554,6 +573,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                     const bool p = __vimax3_u16x2(br, 2u * FAST_BIAS2 - dk, thB2) != thB2;  // some lane > th
                     if (h) passO = p; else passE = p;
                 }
+#endif
             }
             const unsigned mE = __ballot_sync(0xffffffffu, passE), mO = __ballot_sync(0xffffffffu, passO);
             const int nE = __popc(mE);
