@@ -735,6 +735,48 @@ int eaof_stereo_matches(eaof_orb* l, eaof_orb* r, int n, float mb, float mbf, fl
     return EAOF_OK;
 }
 
+int eaof_orb_undistort_keypoints_device(eaof_orb* c, int n, float fx, float fy, float cx, float cy, const float* dist,
+                                        int nDist, int mode, float* dXUn, float* dYUn) {
+    if (!c || !dXUn || !dYUn || n < 1 || n > c->p.max_batch) return fail(EAOF_ERR_ARG, "bad argument");
+    if (nDist < 0 || nDist > 12 || (nDist && !dist)) return fail(EAOF_ERR_ARG, "0..12 distortion coefficients expected");
+    if (mode != EAOF_UNDISTORT_CV331 && mode != EAOF_UNDISTORT_CV4) return fail(EAOF_ERR_ARG, "unknown undistort mode");
+    CK(cudaSetDevice(c->device));
+    const dim3 gr((c->kpCap + 255) / 256, n);
+    if (nDist == 0 || dist[0] == 0.0f) {  // mvKeysUn = mvKeys, src/Frame.cc:775-779
+        eaof::k_copy_xy<<<gr, 256, 0, c->stream>>>(c->dKps, c->dKpCount, c->kpCap, dXUn, dYUn);
+    } else {
+        eaof::UndistortArgs U{};
+        U.fx = fx; U.fy = fy; U.cx = cx; U.cy = cy;
+        for (int i = 0; i < nDist; ++i) U.k[i] = dist[i];
+        U.guard = mode == EAOF_UNDISTORT_CV4;
+        eaof::k_undistort<<<gr, 256, 0, c->stream>>>(c->dKps, c->dKpCount, c->kpCap, U, dXUn, dYUn);
+    }
+    CK(cudaGetLastError());
+    return EAOF_OK;
+}
+
+int eaof_orb_undistort_keypoints(eaof_orb* c, int n, float fx, float fy, float cx, float cy, const float* dist, int nDist,
+                                 int mode, float* xUn, float* yUn, int cap) {
+    if (!c || !xUn || !yUn || n < 1 || n > c->p.max_batch) return fail(EAOF_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t outN = (size_t)c->p.max_batch * c->kpCap;
+    if (!c->dURight) { CK(cudaMalloc(&c->dURight, sizeof(float) * outN)); CK(cudaMalloc(&c->dDepthKp, sizeof(float) * outN)); }
+    int rc = eaof_orb_undistort_keypoints_device(c, n, fx, fy, cx, cy, dist, nDist, mode, c->dURight, c->dDepthKp);
+    if (rc) return rc;
+    std::vector<float> hx((size_t)n * c->kpCap), hy((size_t)n * c->kpCap);
+    std::vector<int> cnt(n);
+    CK(cudaMemcpyAsync(hx.data(), c->dURight, sizeof(float) * hx.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(hy.data(), c->dDepthKp, sizeof(float) * hy.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(cnt.data(), c->dKpCount, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int f = 0; f < n; ++f) {
+        if (cnt[f] > cap) return fail(EAOF_ERR_ARG, "frame %d has %d keypoints but cap is %d", f, cnt[f], cap);
+        memcpy(xUn + (size_t)f * cap, hx.data() + (size_t)f * c->kpCap, sizeof(float) * cnt[f]);
+        memcpy(yUn + (size_t)f * cap, hy.data() + (size_t)f * c->kpCap, sizeof(float) * cnt[f]);
+    }
+    return EAOF_OK;
+}
+
 int eaof_orb_sync(eaof_orb* c) {
     if (!c) return fail(EAOF_ERR_ARG, "null handle");
     CK(cudaStreamSynchronize(c->stream));

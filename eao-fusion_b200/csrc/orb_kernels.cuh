@@ -276,6 +276,49 @@ __global__ void __launch_bounds__(1024) k_stereo_filter(const int* __restrict__ 
     }
 }
 
+// Frame::UndistortKeyPoints (src/Frame.cc:773-803) = cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) over
+// the keypoints a handle holds on the device: OpenCV's cvUndistortPoints in double arithmetic (the library is built with
+// --fmad=false, double division is IEEE): normalise, five fixed-point iterations of the inverse Brown model, re-project
+// with P = mK, round to float.  thread = keypoint.
+struct UndistortArgs {
+    double fx, fy, cx, cy;
+    double k[12];
+    int guard;  // 1: OpenCV 4.x "icdist < 0" exit
+};
+
+__global__ void __launch_bounds__(256) k_undistort(const eaof_kp* __restrict__ kps, const int* __restrict__ counts, int cap,
+                                                   UndistortArgs U, float* __restrict__ xo, float* __restrict__ yo) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[f]) return;
+    const size_t o = (size_t)f * cap + i;
+    const double u = kps[o].x, v = kps[o].y;
+    const double ifx = 1. / U.fx, ify = 1. / U.fy;
+    double x = (u - U.cx) * ifx, y = (v - U.cy) * ify;
+    const double x0 = x, y0 = y;
+    const double* k = U.k;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (U.guard && icdist < 0) { x = (u - U.cx) * ifx; y = (v - U.cy) * ify; break; }
+        const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    const double xx = U.fx * x + 0.0 * y + U.cx, yy = 0.0 * x + U.fy * y + U.cy, ww = 1. / (0.0 * x + 0.0 * y + 1.0);
+    xo[o] = (float)(xx * ww);
+    yo[o] = (float)(yy * ww);
+}
+
+__global__ void __launch_bounds__(256) k_copy_xy(const eaof_kp* __restrict__ kps, const int* __restrict__ counts, int cap,
+                                                 float* __restrict__ xo, float* __restrict__ yo) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[f]) return;
+    const size_t o = (size_t)f * cap + i;
+    xo[o] = kps[o].x;
+    yo[o] = kps[o].y;
+}
+
 // cv::resize 8UC1 INTER_LINEAR with 11-bit fixed-point coefficients; the border pixel at
 // bordered position (bx,by) equals the resized pixel at the reflected inner position, so resize and
 // copyMakeBorder are one pass.  tabs: per destination column [sx, a0|a1<<16], per row [sy, b0|b1<<16].

@@ -56,6 +56,8 @@ def lib():
         L.eaof_orb_extract_batch_color.argtypes = [vp, vp, ci, ci, ci, sz, sz, ci, ci, vp, vp, ci, vp]
         L.eaof_orb_stereo_from_rgbd_device.argtypes = [vp, ci, vp, ci, C.c_float, sz, sz, vp, C.c_float, vp, vp]
         L.eaof_orb_stereo_from_rgbd.argtypes = [vp, ci, vp, ci, C.c_float, sz, sz, C.c_float, vp, vp, ci]
+        L.eaof_orb_undistort_keypoints_device.argtypes = [vp, ci] + [C.c_float] * 4 + [vp, ci, ci, vp, vp]
+        L.eaof_orb_undistort_keypoints.argtypes = [vp, ci] + [C.c_float] * 4 + [vp, ci, ci, vp, vp, ci]
         L.eaof_stereo_matches_device.argtypes = [vp, vp, ci, C.c_float, C.c_float, vp, vp]
         L.eaof_stereo_matches.argtypes = [vp, vp, ci, C.c_float, C.c_float, vp, vp, ci]
         L.eaof_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ci)]
@@ -186,6 +188,15 @@ class ORBextractor:
                                              float(depth_scale), w * px, w * h * px, float(mbf), ur.ctypes.data,
                                              dd.ctypes.data, self.cap))
         return ur, dd
+
+    def undistort_keypoints(self, n: int, K, dist, mode=0):
+        """Frame::UndistortKeyPoints (src/Frame.cc:773-803) for the last batch.  K = (fx, fy, cx, cy).  Returns (x, y) as (n, cap)."""
+        d = np.ascontiguousarray(dist, np.float32)
+        xo, yo = np.zeros((n, self.cap), np.float32), np.zeros((n, self.cap), np.float32)
+        _ck(self.L.eaof_orb_undistort_keypoints(self.h, n, float(K[0]), float(K[1]), float(K[2]), float(K[3]),
+                                                d.ctypes.data if len(d) else None, len(d), int(mode), xo.ctypes.data,
+                                                yo.ctypes.data, self.cap))
+        return xo, yo
 
     def stereo_matches(self, right: "ORBextractor", n: int, mb: float, mbf: float):
         """Frame::ComputeStereoMatches (src/Frame.cc:841-1013): self = left camera's extractor, right = the right one,

@@ -128,6 +128,20 @@ int eaof_orb_extract_batch_color(eaof_orb* ctx, const uint8_t* imgs, int n_frame
                                  size_t frame_pitch, int color, int gray_mode, eaof_kp* kps, uint8_t* desc, int cap,
                                  int* n_out);
 
+/* Frame::UndistortKeyPoints()  src/Frame.cc:773-803 for the keypoints of the last batch: mvKeysUn
+ * positions = cv::undistortPoints(mvKeys, mK, mDistCoef, cv::Mat(), mK) with mK = (fx, fy, cx, cy) and `dist` = k1 k2 p1 p2
+ * [k3 k4 k5 k6 s1 s2 s3 s4] (n_dist of them), computed in double like OpenCV; with no coefficients or k1 == 0 the
+ * positions are copied, which is the reference's shortcut (:775-779).  mode: EAOF_UNDISTORT_CV331 = OpenCV 3.3.1 (five
+ * iterations, no exit), EAOF_UNDISTORT_CV4 = OpenCV 4.x (adds the "icdist < 0" exit; checked against cv2 4.13) — they
+ * agree wherever the distortion polynomial stays positive, i.e. for every real calibration.
+ * _device: outputs [n_frames][eaof_orb_max_keypoints()] floats in device memory (what eaof_orb_stereo_from_rgbd_device
+ * takes as d_x_undistorted), asynchronous; host form: [n_frames][cap]. */
+enum { EAOF_UNDISTORT_CV331 = 0, EAOF_UNDISTORT_CV4 = 1 };
+int eaof_orb_undistort_keypoints_device(eaof_orb* ctx, int n_frames, float fx, float fy, float cx, float cy,
+                                        const float* dist, int n_dist, int mode, float* d_x_un, float* d_y_un);
+int eaof_orb_undistort_keypoints(eaof_orb* ctx, int n_frames, float fx, float fy, float cx, float cy, const float* dist,
+                                 int n_dist, int mode, float* x_un, float* y_un, int cap);
+
 /* Frame::ComputeStereoFromRGBD(imDepth)  src/Frame.cc:1016-1037 for the keypoints of the last batch:
  * per keypoint the depth d at its raw position (coordinates truncated like cv::Mat::at<float>(float, float)); where
  * d > 0: mvDepth = d, mvuRight = x_undistorted - mbf/d; -1 elsewhere.  depth_type EAOF_DEPTH_F32: the CV_32F map the

@@ -750,3 +750,36 @@ extern "C" void eaoo_stereo_matches(int nL, const float* xL, const float* yL, co
         depth[vDistIdx[i].second] = -1;
     }
 }
+
+// ---- Frame::UndistortKeyPoints  src/Frame.cc:773-803 = cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) -----------
+// OpenCV's cvUndistortPoints in double arithmetic: normalise with the camera matrix, five fixed-point iterations of the
+// Brown model inverse (k1 k2 p1 p2 k3 [k4 k5 k6 s1 s2 s3 s4], missing coefficients are 0), re-project with P = mK, store as
+// float.  guard = 1 adds OpenCV 4.x's "icdist < 0 -> keep the normalised point" exit (verified against cv2 4.13 in
+// tests/test_oracle_primitives.py); OpenCV 3.3.1, the reference's pinned version, has no such exit (guard = 0).
+// The k1 == 0 shortcut of the reference (:775-779) is the caller's.
+extern "C" void eaoo_undistort_points(int n, const float* xs, const float* ys, float fx, float fy, float cx, float cy,
+                                      const float* dist, int nDist, int guard, float* xo, float* yo) {
+    double k[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < nDist && i < 12; ++i) k[i] = dist[i];
+    const double dfx = fx, dfy = fy, dcx = cx, dcy = cy;
+    const double ifx = 1. / dfx, ify = 1. / dfy;
+    for (int i = 0; i < n; ++i) {
+        double x = xs[i], y = ys[i];
+        const double u = x, v = y;
+        x = (x - dcx) * ifx;
+        y = (y - dcy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; ++j) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (guard && icdist < 0) { x = (u - dcx) * ifx; y = (v - dcy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = dfx * x + 0.0 * y + dcx, yy = 0.0 * x + dfy * y + dcy, ww = 1. / (0.0 * x + 0.0 * y + 1.0);
+        xo[i] = (float)(xx * ww);
+        yo[i] = (float)(yy * ww);
+    }
+}

@@ -1071,3 +1071,18 @@ def r_stereo_from_rgbd(kps, depth, mbf, x_un=None):
     stereo_ref_lib().sref_stereo_from_rgbd(n, _pp(x), _pp(y), _pp(xu), d.ctypes.data, d.shape[1], d.shape[0], float(mbf),
                                            ur.ctypes.data, dp.ctypes.data)
     return ur[:n], dp[:n]
+
+
+def o_undistort_points(x, y, K, dist, guard=0):
+    """Frame::UndistortKeyPoints' cv::undistortPoints (src/Frame.cc:773-803).  K = (fx, fy, cx, cy); dist = k1 k2 p1 p2 [k3 ...].
+    guard=1: OpenCV 4.x semantics (checked against cv2), guard=0: OpenCV 3.3.1."""
+    x, y, d = _a(x, np.float32), _a(y, np.float32), _a(dist, np.float32)
+    n = len(x)
+    xo, yo = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32)
+    L = oracle_lib()
+    cf, ci, vp = C.c_float, C.c_int, C.c_void_p
+    L.eaoo_undistort_points.restype = None
+    L.eaoo_undistort_points.argtypes = [ci, vp, vp, cf, cf, cf, cf, vp, ci, ci, vp, vp]
+    L.eaoo_undistort_points(n, _pp(x), _pp(y), float(K[0]), float(K[1]), float(K[2]), float(K[3]), _pp(d), len(d), int(guard),
+                            xo.ctypes.data, yo.ctypes.data)
+    return xo[:n], yo[:n]

@@ -301,3 +301,21 @@ def test_stereo_matches_rejects_mismatched_handles():
         a.stereo_matches(a, 1, 0.1, 40.0)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("dist", [[0.2624, -0.9531, -0.0054, 0.0026, 1.1633], [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05],
+                                  [0.0, 0.1, 0.0, 0.0], [], [5.0, -30.0, 0.3, -0.2, 80.0]])
+def test_undistort_keypoints(ex640, frames640, dist):
+    from oracle import pyoracle as po
+    n = 3
+    res = ex640.extract_batch(frames640[:n])
+    K = (np.float32(517.306408), np.float32(516.469215), np.float32(318.643040), np.float32(255.313989))
+    for mode in (0, 1):
+        gx, gy = ex640.undistort_keypoints(n, K, dist, mode)
+        for f in range(n):
+            k = res[f][0]
+            if len(dist) == 0 or dist[0] == 0.0:
+                ox, oy = k["x"], k["y"]  # mvKeysUn = mvKeys
+            else:
+                ox, oy = po.o_undistort_points(k["x"], k["y"], K, dist, guard=mode)
+            assert np.array_equal(gx[f, :len(k)], ox) and np.array_equal(gy[f, :len(k)], oy), (mode, f)

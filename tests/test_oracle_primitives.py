@@ -137,3 +137,24 @@ def test_cvt_gray_cv4_formula_equals_cv2(code, color):
     assert np.array_equal(po.o_cvt_gray(img, color, 1), want)
     diff = po.o_cvt_gray(img, color, 0).astype(int) - want
     assert 0 < np.count_nonzero(diff) < 0.02 * diff.size and np.abs(diff).max() == 1
+
+
+@pytest.mark.parametrize("dist", [[0.2624, -0.9531, -0.0054, 0.0026, 1.1633],          # TUM1.yaml
+                                  [0.2312, -0.7849, -0.0033, -0.0001, 0.9172],        # TUM2.yaml
+                                  [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05],  # EuRoC, 4 coefficients
+                                  [5.0, -30.0, 0.3, -0.2, 80.0]])                      # absurd: drives icdist negative
+def test_undistort_points_equals_cv2(dist):
+    """cv::undistortPoints(mat, mat, mK, mDistCoef, cv::Mat(), mK) restated in double arithmetic == cv2 4.13 (guard = 1);
+    the OpenCV 3.3.1 form (guard = 0) differs only where icdist < 0, which real calibrations never reach."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    n = 5000
+    x = rng.uniform(-20, 660, n).astype(np.float32)
+    y = rng.uniform(-20, 500, n).astype(np.float32)
+    K = np.array([[517.306408, 0, 318.643040], [0, 516.469215, 255.313989], [0, 0, 1]], np.float32)
+    D = np.asarray(dist, np.float32)
+    want = cv2.undistortPoints(np.stack([x, y], 1).reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+    gx, gy = po.o_undistort_points(x, y, (K[0, 0], K[1, 1], K[0, 2], K[1, 2]), D, guard=1)
+    assert np.array_equal(gx, want[:, 0]) and np.array_equal(gy, want[:, 1])
+    ox, oy = po.o_undistort_points(x, y, (K[0, 0], K[1, 1], K[0, 2], K[1, 2]), D, guard=0)
+    if abs(dist[0]) < 1:
+        assert np.array_equal(ox, gx) and np.array_equal(oy, gy)
