@@ -134,6 +134,23 @@ def next_rows(eaof, torch, device, ex, d_frames, B, W, H):
         sync()
         return e0.elapsed_time(e1) / reps
 
+    # how the reference actually runs: one frame per call through the host-buffer entry point the drop-in operator() uses
+    # (upload + 13 kernels + download, synchronous), beside one SearchByProjection(Cur,Last) call on host buffers
+    ex1 = eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=1, device=device)
+    f_host = d_frames[:8].cpu().numpy()
+    for i in range(8):
+        ex1(f_host[i])
+    lat = []
+    for i in range(64):
+        t0 = _t.perf_counter()
+        k1, d1 = ex1(f_host[i % 8])
+        lat.append(_t.perf_counter() - t0)
+    lat.sort()
+    out["single_frame_latency"] = {"workload": f"ORBextractor::operator() on one {W}x{H} frame, host buffers in and out (pageable numpy arrays)",
+                                   "median_us": lat[len(lat) // 2] * 1e6, "p95_us": lat[int(len(lat) * 0.95)] * 1e6,
+                                   "keypoints": int(len(k1))}
+    ex1.close()
+
     # f-2: ORBVocabulary::transform over the descriptors of a batch, vocabulary of the ORBvoc shape (k=10, L=6)
     tree = synth.vocabulary(10, 6)
     voc = eaof.ORBVocabulary(tree, max_features=cap, max_sets=B, device=device)
