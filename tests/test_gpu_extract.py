@@ -319,3 +319,78 @@ def test_undistort_keypoints(ex640, frames640, dist):
             else:
                 ox, oy = po.o_undistort_points(k["x"], k["y"], K, dist, guard=mode)
             assert np.array_equal(gx[f, :len(k)], ox) and np.array_equal(gy[f, :len(k)], oy), (mode, f)
+
+
+@pytest.mark.parametrize("shape,nf", [((848, 480), 1200), ((1920, 1080), 4000)])
+def test_frame_helpers_at_the_other_config_sizes(shape, nf):
+    """BASELINE.json configs[2] / [3] geometry through the rows either side of the extractor: colour ingest, stereo matches
+    between two handles, RGB-D depth lookup, vocabulary transform + SearchByBoW on the device."""
+    import torch
+    import eaof
+    from eaof import synth
+    from matchdata import stereo_pair
+    from oracle import pyoracle as po
+    from vocdata import make_vocabulary, tree_from
+    w, h = shape
+    tex = synth.base_texture(w, h, seed=77 + w)
+    left, right = stereo_pair(1, width=w, height=h, disparity=21, tex=tex)
+    exL = eaof.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=2)
+    exR = eaof.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=2)
+    # colour ingest: BGR whose conversion is the identity on equal channels
+    col = np.repeat(np.stack([left, right])[..., None], 3, axis=3)
+    resC = exL.extract_batch_color(col, 0, 0)
+    resL = exL.extract_batch(np.stack([left, right]))
+    assert all(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) for a, b in zip(resC, resL))
+    resR = exR.extract_batch(np.stack([right, left]))
+    # stereo: frame 0 = (left, right), frame 1 = (right, left) (negative disparities: nothing may match)
+    ur, dd = exL.stereo_matches(exR, 2, 0.1, 60.0)
+    sf, isf = exL.GetScaleFactors(), exL.GetInverseScaleFactors()
+    for f in range(2):
+        pL = [exL.pyramid_level(l, frame=f, with_border=True) for l in range(8)]
+        pR = [exR.pyramid_level(l, frame=f, with_border=True) for l in range(8)]
+        ou, od, _ = po.o_stereo_matches(resL[f][0], resL[f][1], resR[f][0], resR[f][1], pL, pR, sf, isf, 0.1, 60.0)
+        n = len(resL[f][0])
+        assert np.array_equal(ur[f, :n], ou) and np.array_equal(dd[f, :n], od), f
+    assert np.sum(ur[0] >= 0) > nf // 5
+    # RGB-D
+    rng = np.random.Generator(np.random.PCG64(3))
+    depth = rng.uniform(0.2, 9.0, (2, h, w)).astype(np.float32)
+    gu, gd = exL.stereo_from_rgbd(depth, 40.0)
+    for f in range(2):
+        ou, od = po.o_stereo_from_rgbd(resL[f][0], depth[f], 40.0)
+        n = len(resL[f][0])
+        assert np.array_equal(gu[f, :n], ou) and np.array_equal(gd[f, :n], od)
+    # vocabulary transform + SearchByBoW, device-resident
+    voc = make_vocabulary(10, 3, 0, 0, seed=9)
+    tree = tree_from(voc)
+    cap = exL.cap
+    v = eaof.ORBVocabulary(tree, max_features=cap, max_sets=2)
+    mt = eaof.ORBmatcher(0.75, True, max_features=cap, max_pairs=2)
+    dev = torch.device("cuda:0")
+    nw, nn = torch.zeros(2, dtype=torch.int32, device=dev), torch.zeros(2, dtype=torch.int32, device=dev)
+    wi, ni, fi = (torch.zeros(2 * cap, dtype=torch.int32, device=dev) for _ in range(3))
+    wv = torch.zeros(2 * cap, dtype=torch.float64, device=dev)
+    ns = torch.zeros(2 * (cap + 1), dtype=torch.int32, device=dev)
+    v.transform_orb_device(exL, 2, 2, nw.data_ptr(), wi.data_ptr(), wv.data_ptr(), nn.data_ptr(), ni.data_ptr(), ns.data_ptr(),
+                           fi.data_ptr())
+    v.sync()
+    d_match = torch.zeros((1, cap), dtype=torch.int32, device=dev)
+    d_dist = torch.zeros((1, cap), dtype=torch.int32, device=dev)
+    d_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    mt.bow_orb_device(exL, 2, 0, [0], [1], nn.data_ptr(), ni.data_ptr(), ns.data_ptr(), fi.data_ptr(), d_match.data_ptr(),
+                      d_dist.data_ptr(), d_n.data_ptr())
+    mt.sync()
+    fv = [po.o_voc_transform(tree, resL[f][1], 2) for f in range(2)]
+    for f in range(2):
+        a = int(nw[f])
+        assert a == len(fv[f][0]) and np.array_equal(wv[f * cap:f * cap + a].cpu().numpy(), fv[f][1])
+    nodes = [(x[2].astype(np.int32), x[3], x[4].astype(np.int32)) for x in fv]
+    on, om, od = po.o_search_by_bow(0, 0.75, True, resL[0][1], resL[0][0]["angle"], None, nodes[0], resL[1][1],
+                                    resL[1][0]["angle"], None, nodes[1])
+    nt = len(resL[1][0])
+    assert int(d_n[0]) == on and np.array_equal(d_match[0, :nt].cpu().numpy(), om) and np.array_equal(d_dist[0, :nt].cpu().numpy(), od)
+    assert on > 50
+    mt.close()
+    v.close()
+    exL.close()
+    exR.close()
