@@ -1117,6 +1117,9 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
 // one lane into the other); the vertical pass needs 25 bits and runs per pixel.
 #define BLUR_ROWS 32
 #define BLUR_THREADS 128
+#ifndef BLUR_AHEAD
+#define BLUR_AHEAD 3
+#endif
 
 __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
                                                        const __grid_constant__ Geom g) {
@@ -1148,11 +1151,23 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(const uint8_t* __restrict
     // newest value (25 bits).
     unsigned prA[4] = {0, 0, 0, 0}, prB[4] = {0, 0, 0, 0}, prC[4] = {0, 0, 0, 0}, prD[4] = {0, 0, 0, 0}, prE[4] = {0, 0, 0, 0};
     unsigned hPrev[4] = {0, 0, 0, 0};
+    // The stage waits on its loads (ncu: long-scoreboard stalls dominate, issue slots half used), so the three words of
+    // a row are fetched BLUR_AHEAD rows before they are filtered.
+    unsigned qm[BLUR_AHEAD], q0[BLUR_AHEAD], qp[BLUR_AHEAD];
 #pragma unroll
-    for (int r = 0; r < BLUR_ROWS + 6; ++r) {
+    for (int r = 0; r < BLUR_AHEAD; ++r) {
         const int by = min(y0 + r - 3 + EAOF_EDGE, L.rows - 1);
         const uint32_t* p = reinterpret_cast<const uint32_t*>(in + (size_t)by * L.pitch);
-        const unsigned Wm = __ldg(p - 1), W0 = __ldg(p), Wp = __ldg(p + 1);
+        qm[r] = __ldg(p - 1); q0[r] = __ldg(p); qp[r] = __ldg(p + 1);
+    }
+#pragma unroll
+    for (int r = 0; r < BLUR_ROWS + 6; ++r) {
+        const unsigned Wm = qm[r % BLUR_AHEAD], W0 = q0[r % BLUR_AHEAD], Wp = qp[r % BLUR_AHEAD];
+        if (r + BLUR_AHEAD < BLUR_ROWS + 6) {
+            const int by = min(y0 + r + BLUR_AHEAD - 3 + EAOF_EDGE, L.rows - 1);
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(in + (size_t)by * L.pitch);
+            qm[r % BLUR_AHEAD] = __ldg(p - 1); q0[r % BLUR_AHEAD] = __ldg(p); qp[r % BLUR_AHEAD] = __ldg(p + 1);
+        }
         unsigned h[4];
         h[0] = __dp4a(__byte_perm(Wm, W0, 0x4321), TL, __dp4a(__byte_perm(W0, Wp, 0x4321), TR, 0u));
         h[1] = __dp4a(__byte_perm(Wm, W0, 0x5432), TL, __dp4a(__byte_perm(W0, Wp, 0x5432), TR, 0u));
