@@ -298,12 +298,13 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     {
         const LevelGeom& L = g.L[0];
         dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
+        const dim3 gr8(gr.x, (L.rows + 4 * LEVEL0_ROWS - 1) / (4 * LEVEL0_ROWS), n);  // k_level0: LEVEL0_ROWS rows per thread
         if (c->colorCh == 3)
             eaof::k_level0_color<3><<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g, c->colorK[0], c->colorK[1], c->colorK[2], c->colorShift);
         else if (c->colorCh == 4)
             eaof::k_level0_color<4><<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g, c->colorK[0], c->colorK[1], c->colorK[2], c->colorShift);
         else
-            eaof::k_level0<<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g);
+            eaof::k_level0<<<gr8, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g);
         ++launches;
     }
     for (int l = 1; l < g.nlevels; ++l) {

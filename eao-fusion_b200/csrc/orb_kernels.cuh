@@ -28,27 +28,39 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 // ------------------------------------------------------------------------------------------------
 // Pyramid.  A level row is `pitch` bytes; inner pixel x sits at byte EAOF_INNER_X0 + x, so the bordered
-// span is bytes [13, w+51).  Each thread produces one aligned 4-byte word of one bordered row.
+// span is bytes [13, w+51).  
+// Each thread produces one aligned 4-byte word of LEVEL0_ROWS consecutive bordered rows: the column part of the address
+// arithmetic (reflected byte offsets, alignment test) is done once per thread.
+#define LEVEL0_ROWS 8
 __global__ void __launch_bounds__(256) k_level0(const uint8_t* __restrict__ in, size_t framePitch, size_t stride,
                                                 uint8_t* __restrict__ pyr, const __grid_constant__ Geom g) {
     const LevelGeom& L = g.L[0];
     const int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int by = blockIdx.y * blockDim.y + threadIdx.y;
+    const int r0 = (blockIdx.y * blockDim.y + threadIdx.y) * LEVEL0_ROWS;
     const int f = blockIdx.z;
     const int c0 = 12 + 4 * wi;
-    if (by >= L.rows || c0 >= L.w + 52) return;
-    const int y = reflect101(by - EAOF_EDGE, L.h);
-    const uint8_t* src = in + (size_t)f * framePitch + (size_t)y * stride;
+    if (r0 >= L.rows || c0 >= L.w + 52) return;
     const int bx = c0 - EAOF_INNER_X0;
-    uint32_t v;
-    if (bx >= 0 && bx + 3 < L.w && ((reinterpret_cast<uintptr_t>(src + bx) & 3) == 0)) {
-        v = __ldg(reinterpret_cast<const uint32_t*>(src + bx));
-    } else {
-        v = 0;
+    const uint8_t* base = in + (size_t)f * framePitch;
+    const bool fast = bx >= 0 && bx + 3 < L.w && ((reinterpret_cast<uintptr_t>(base + bx) | stride) & 3) == 0;
+    int xs[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v |= (uint32_t)__ldg(src + reflect101(bx + j, L.w)) << (8 * j);
+    for (int j = 0; j < 4; ++j) xs[j] = reflect101(bx + j, L.w);
+    uint8_t* dst = pyr + (size_t)f * g.pyrFrameBytes + L.off + c0;
+#pragma unroll
+    for (int k = 0; k < LEVEL0_ROWS; ++k) {
+        const int by = r0 + k;
+        if (by >= L.rows) break;
+        const uint8_t* src = base + (size_t)reflect101(by - EAOF_EDGE, L.h) * stride;
+        uint32_t v;
+        if (fast) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(src + bx));
+        } else {
+            v = (uint32_t)__ldg(src + xs[0]) | ((uint32_t)__ldg(src + xs[1]) << 8) | ((uint32_t)__ldg(src + xs[2]) << 16) |
+                ((uint32_t)__ldg(src + xs[3]) << 24);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)by * L.pitch) = v;
     }
-    *reinterpret_cast<uint32_t*>(pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)by * L.pitch + c0) = v;
 }
 
 // Colour ingest: cv::cvtColor(RGB/BGR/RGBA/BGRA -> GRAY) on 8U (src/Tracking.cc:324-337, OpenCV RGB2Gray<uchar>) fused
