@@ -374,6 +374,11 @@ __global__ void __launch_bounds__(256) k_resize_generic(uint8_t* __restrict__ py
 // source row of one output row is usually the upper row of the next, so it is kept.  Rows that the REFLECT_101
 // border mirrors (inner rows 1..19 and h-20..h-2) are stored twice.
 #define RSZ_THREADS 128
+__device__ __forceinline__ unsigned mad_hi_u32(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 template <int RSZ_ROWS>
 __global__ void __launch_bounds__(RSZ_THREADS) k_resize(uint8_t* __restrict__ pyr, const int* __restrict__ tabs,
                                                         const __grid_constant__ Geom g, int l) {
@@ -407,14 +412,16 @@ __global__ void __launch_bounds__(RSZ_THREADS) k_resize(uint8_t* __restrict__ py
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const unsigned lo = __ldg(r + wofs[j]), hi = __ldg(r + wofs[j] + 1);
-            h[j] = __dp2a_lo(coef[j], __byte_perm(lo, hi, sel[j]), 0u);
+            h[j] = __dp2a_lo(coef[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;  // every use is (sum >> 4), A.2
         }
     };
     const int yEnd = min(y0 + RSZ_ROWS, D.h);
     for (int y = y0; y < yEnd; ++y) {
         const int sy = __ldg(tabs + D.yTab + 2 * y);
         const int bb = __ldg(tabs + D.yTab + 2 * y + 1);
-        const int b0 = (short)(bb & 0xffff), b1 = bb >> 16;
+        // (b * (S >> 4)) >> 16 == high word of (b << 16) * (S >> 4): one IMAD.HI (FMA pipe) per product, the second one
+        // adding the first and the rounding constant; b in [0, 2048]
+        const unsigned b0s = (unsigned)bb << 16, b1s = (unsigned)bb & 0xffff0000u;
         const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
         unsigned hA[4];
         if (sy0 == cached) {
@@ -429,12 +436,10 @@ __global__ void __launch_bounds__(RSZ_THREADS) k_resize(uint8_t* __restrict__ py
             for (int j = 0; j < 4; ++j) hB[j] = hA[j];
         }
         cached = sy1;
-        uint32_t v = 0;
+        unsigned d[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int d = (((b0 * (int)(hA[j] >> 4)) >> 16) + ((b1 * (int)(hB[j] >> 4)) >> 16) + 2) >> 2;
-            v |= (uint32_t)(d & 0xff) << (8 * j);
-        }
+        for (int j = 0; j < 4; ++j) d[j] = mad_hi_u32(b1s, hB[j], mad_hi_u32(b0s, hA[j], 2u)) >> 2;  // <= 255
+        const uint32_t v = ((d[3] * 256u + d[2]) * 256u + d[1]) * 256u + d[0];
         *reinterpret_cast<uint32_t*>(dOut + (size_t)(y + EAOF_EDGE) * D.pitch) = v;
         if (y >= 1 && y <= EAOF_EDGE) *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE - y) * D.pitch) = v;
         if (y >= D.h - 1 - EAOF_EDGE && y <= D.h - 2)
