@@ -33,131 +33,133 @@ static int EnvInt(const char* name, int dflt)
     return (v && *v) ? atoi(v) : dflt;
 }
 
-ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels,
-         int _iniThFAST, int _minThFAST):
-    nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels),
-    iniThFAST(_iniThFAST), minThFAST(_minThFAST),
-    mpCtx(NULL), mnCtxWidth(0), mnCtxHeight(0),
-    mnDevice(EnvInt("EAOF_DEVICE", 0)), mnBlurMode(EnvInt("EAOF_BLUR_MODE", EAOF_BLUR_CV331)),
-    mbDownloadPyramid(EnvInt("EAOF_PYRAMID", 1) != 0)
+ORBextractor::ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
 {
-    // The getters must answer before the first frame (Frame's constructor reads them right after ExtractORB, but
-    // Tracking may query earlier), so the scale tables are restated on the host exactly as
-    // src/ORBextractor.cc:415-446 computes them; the library computes the same tables for the kernels and
-    // EnsureWorkspace cross-checks the two.
-    mvScaleFactor.resize(nlevels);
-    mvLevelSigma2.resize(nlevels);
-    mvScaleFactor[0]=1.0f;
-    mvLevelSigma2[0]=1.0f;
-    for(int i=1; i<nlevels; i++)
+    mSetup.features = nfeatures;
+    mSetup.factor = scaleFactor;  // a double member initialised from the float argument, like the reference's
+    mSetup.levels = nlevels;
+    mSetup.fastHigh = iniThFAST;
+    mSetup.fastLow = minThFAST;
+    mGpu.ctx = NULL;
+    mGpu.width = mGpu.height = 0;
+    mGpu.device = EnvInt("EAOF_DEVICE", 0);
+    mGpu.blurMode = EnvInt("EAOF_BLUR_MODE", EAOF_BLUR_CV331);
+    mGpu.downloadPyramid = EnvInt("EAOF_PYRAMID", 1) != 0;
+
+    // The getters must answer before the first frame, so the scale tables are restated here with the arithmetic of
+    // src/ORBextractor.cc:415-433 (float table entry times the double factor, narrowed); the library computes the same
+    // tables for its kernels and Prepare() cross-checks the two.
+    Tables& T = mTables;
+    T.scale.assign(nlevels, 1.0f);
+    T.sigma2.assign(nlevels, 1.0f);
+    for(int l = 1; l < nlevels; ++l)
     {
-        mvScaleFactor[i]=(float)(mvScaleFactor[i-1]*scaleFactor);
-        mvLevelSigma2[i]=mvScaleFactor[i]*mvScaleFactor[i];
+        T.scale[l] = (float)(T.scale[l-1]*mSetup.factor);
+        T.sigma2[l] = T.scale[l]*T.scale[l];
     }
-    mvInvScaleFactor.resize(nlevels);
-    mvInvLevelSigma2.resize(nlevels);
-    for(int i=0; i<nlevels; i++)
+    T.invScale.resize(nlevels);
+    T.invSigma2.resize(nlevels);
+    for(int l = 0; l < nlevels; ++l)
     {
-        mvInvScaleFactor[i]=1.0f/mvScaleFactor[i];
-        mvInvLevelSigma2[i]=1.0f/mvLevelSigma2[i];
+        T.invScale[l] = 1.0f/T.scale[l];
+        T.invSigma2[l] = 1.0f/T.sigma2[l];
     }
+    T.quota.assign(nlevels, 0);
     mvImagePyramid.resize(nlevels);
-    mnFeaturesPerLevel.assign(nlevels, 0);
 }
 
 ORBextractor::~ORBextractor()
 {
-    if(mpCtx)
-        eaof_orb_destroy(mpCtx);
+    if(mGpu.ctx)
+        eaof_orb_destroy(mGpu.ctx);
 }
 
-void ORBextractor::SetDevice(int d) { mnDevice = d; }
-void ORBextractor::SetBlurMode(int m) { mnBlurMode = m; }
-void ORBextractor::SetPyramidDownload(bool on) { mbDownloadPyramid = on; }
+void ORBextractor::SetDevice(int d) { mGpu.device = d; }
+void ORBextractor::SetBlurMode(int m) { mGpu.blurMode = m; }
+void ORBextractor::SetPyramidDownload(bool on) { mGpu.downloadPyramid = on; }
 
-void ORBextractor::EnsureWorkspace(int width, int height)
+// (Re)creates the library handle for this frame size and checks its tables against the host restatement.
+void ORBextractor::Prepare(int width, int height)
 {
-    if(mpCtx && width==mnCtxWidth && height==mnCtxHeight)
+    Gpu& G = mGpu;
+    if(G.ctx && width == G.width && height == G.height)
         return;
-    if(mpCtx)
+    if(G.ctx)
     {
-        eaof_orb_destroy(mpCtx);
-        mpCtx = NULL;
+        eaof_orb_destroy(G.ctx);
+        G.ctx = NULL;
     }
     eaof_orb_params p;
-    p.nfeatures = nfeatures;
-    p.scale_factor = (float)scaleFactor;
-    p.nlevels = nlevels;
-    p.ini_th_fast = iniThFAST;
-    p.min_th_fast = minThFAST;
-    p.blur_mode = mnBlurMode;
+    p.nfeatures = mSetup.features;
+    p.scale_factor = (float)mSetup.factor;
+    p.nlevels = mSetup.levels;
+    p.ini_th_fast = mSetup.fastHigh;
+    p.min_th_fast = mSetup.fastLow;
+    p.blur_mode = G.blurMode;
     p.width = width;
     p.height = height;
     p.max_batch = 1;
-    if(eaof_orb_create(&p, mnDevice, &mpCtx)!=EAOF_OK)
+    if(eaof_orb_create(&p, G.device, &G.ctx) != EAOF_OK)
         Throw("eaof_orb_create");
-    mnCtxWidth = width;
-    mnCtxHeight = height;
+    G.width = width;
+    G.height = height;
 
-    std::vector<float> sf(nlevels), isf(nlevels), s2(nlevels), is2(nlevels);
-    if(eaof_orb_scale_tables(mpCtx, &sf[0], &isf[0], &s2[0], &is2[0], &mnFeaturesPerLevel[0])!=EAOF_OK)
+    const int n = mSetup.levels;
+    const size_t bytes = sizeof(float)*n;
+    std::vector<float> sf(n), isf(n), s2(n), is2(n);
+    if(eaof_orb_scale_tables(G.ctx, &sf[0], &isf[0], &s2[0], &is2[0], &mTables.quota[0]) != EAOF_OK)
         Throw("eaof_orb_scale_tables");
-    if(memcmp(&sf[0], &mvScaleFactor[0], sizeof(float)*nlevels) || memcmp(&isf[0], &mvInvScaleFactor[0], sizeof(float)*nlevels) ||
-       memcmp(&s2[0], &mvLevelSigma2[0], sizeof(float)*nlevels) || memcmp(&is2[0], &mvInvLevelSigma2[0], sizeof(float)*nlevels))
+    if(memcmp(&sf[0], &mTables.scale[0], bytes) || memcmp(&isf[0], &mTables.invScale[0], bytes) ||
+       memcmp(&s2[0], &mTables.sigma2[0], bytes) || memcmp(&is2[0], &mTables.invSigma2[0], bytes))
         Throw("scale tables of the library differ from the host restatement");
 
-    const int cap = eaof_orb_max_keypoints(mpCtx);
-    mvKpStage.resize(sizeof(eaof_kp)*(size_t)cap);
-    mvDescStage.resize(32*(size_t)cap);
+    const size_t cap = (size_t)eaof_orb_max_keypoints(G.ctx);
+    G.kpStage.resize(sizeof(eaof_kp)*cap);
+    G.descStage.resize(32*cap);
 }
 
-void ORBextractor::operator()( cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
-                      cv::OutputArray _descriptors)
+void ORBextractor::operator()(cv::InputArray imageArray, cv::InputArray, std::vector<cv::KeyPoint>& keypoints,
+                              cv::OutputArray descriptorArray)
 {
-    (void)_mask;
-    if(_image.empty())
-        return;
+    if(imageArray.empty())
+        return;  // the reference returns without touching its outputs (src/ORBextractor.cc:1046-1047)
+    cv::Mat image = imageArray.getMat();
+    assert(image.type() == CV_8UC1);
 
-    cv::Mat image = _image.getMat();
-    assert(image.type() == CV_8UC1 );
-
-    EnsureWorkspace(image.cols, image.rows);
-
-    const int cap = eaof_orb_max_keypoints(mpCtx);
-    eaof_kp* kps = reinterpret_cast<eaof_kp*>(&mvKpStage[0]);
+    Prepare(image.cols, image.rows);
+    Gpu& G = mGpu;
+    const int cap = eaof_orb_max_keypoints(G.ctx);
+    eaof_kp* kps = reinterpret_cast<eaof_kp*>(&G.kpStage[0]);
     int n = 0;
-    if(eaof_orb_extract(mpCtx, image.data, image.cols, image.rows, (size_t)image.step, kps, &mvDescStage[0], cap, &n)!=EAOF_OK)
+    if(eaof_orb_extract(G.ctx, image.data, image.cols, image.rows, (size_t)image.step, kps, &G.descStage[0], cap, &n) != EAOF_OK)
         Throw("eaof_orb_extract");
 
-    // mvImagePyramid: bordered host copies with the level as an ROI view, as ComputePyramid builds them
-    if(mbDownloadPyramid)
-    {
-        for(int level=0; level<nlevels; ++level)
+    if(G.downloadPyramid)  // bordered host copies with the level as an ROI view, the layout ComputePyramid leaves
+        for(int level = 0; level < mSetup.levels; ++level)
         {
-            int w=0, h=0;
-            eaof_orb_level_size(mpCtx, level, &w, &h);
-            cv::Mat temp(h+EDGE_THRESHOLD*2, w+EDGE_THRESHOLD*2, CV_8UC1);
-            if(eaof_orb_pyramid_level(mpCtx, 0, level, 1, temp.data, (size_t)temp.step)!=EAOF_OK)
+            int w = 0, h = 0;
+            eaof_orb_level_size(G.ctx, level, &w, &h);
+            cv::Mat bordered(h + 2*EDGE_THRESHOLD, w + 2*EDGE_THRESHOLD, CV_8UC1);
+            if(eaof_orb_pyramid_level(G.ctx, 0, level, 1, bordered.data, (size_t)bordered.step) != EAOF_OK)
                 Throw("eaof_orb_pyramid_level");
-            mvImagePyramid[level] = temp(cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, w, h));
+            mvImagePyramid[level] = bordered(cv::Rect(EDGE_THRESHOLD, EDGE_THRESHOLD, w, h));
         }
-    }
 
-    _keypoints.clear();
-    if(n==0)
+    keypoints.clear();
+    if(n == 0)
     {
-        _descriptors.release();
+        descriptorArray.release();
         return;
     }
-    _descriptors.create(n, 32, CV_8U);
-    cv::Mat descriptors = _descriptors.getMat();
-    _keypoints.reserve(n);
-    for(int i=0; i<n; ++i)
+    descriptorArray.create(n, 32, CV_8U);
+    cv::Mat descriptors = descriptorArray.getMat();
+    keypoints.reserve(n);
+    for(int i = 0; i < n; ++i)
     {
         const eaof_kp& k = kps[i];
-        _keypoints.push_back(cv::KeyPoint(k.x, k.y, k.size, k.angle, k.response, k.octave, -1));
-        memcpy(descriptors.ptr(i), &mvDescStage[32*(size_t)i], 32);
+        keypoints.push_back(cv::KeyPoint(k.x, k.y, k.size, k.angle, k.response, k.octave, -1));
+        memcpy(descriptors.ptr(i), &G.descStage[32*(size_t)i], 32);
     }
 }
 
-} //namespace ORB_SLAM
+}  // namespace ORB_SLAM2
