@@ -58,8 +58,13 @@ oracle:
 	$(MAKE) -C oracle
 	$(MAKE) -C oracle ref
 
+# compute-sanitizer over the GPU parity tests (run on a GPU box; logs of the last run: profiles/r01_sanitizer_*.log)
+sanitize: all
+	compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -x -q
+	compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "stages or voc or stereo or distinctive"
+
 clean:
 	rm -f $(LIB) $(PKG)/lib/ptxas.log $(DROPIN_T) $(DROPIN_M) $(DROPIN_V)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean matchdropin vocdropin
+.PHONY: all oracle clean matchdropin vocdropin sanitize

@@ -3,6 +3,7 @@
 // owns the device workspace and issues the kernel sequence of orb_kernels.cuh on the handle's stream.
 // There is deliberately no CPU implementation here: every failure to reach the GPU is an error.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges are no-ops unless a tool (ncu --nvtx, nsys) injects itself
 
 #include <cmath>
 #include <cstdarg>
@@ -290,6 +291,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     int launches = 0;
     const bool prof = c->profiling;
     if (prof) CK(cudaEventRecord(c->ev[0], s));
+    nvtxRangePushA("eaof:pyramid");
     CK(cudaMemsetAsync(dCandCount, 0, sizeof(uint32_t) * (size_t)n * g.nlevels, s));
     if (c->pyrReaderPending) {
         CK(cudaStreamWaitEvent(s, c->evPyrReader, 0));
@@ -326,7 +328,9 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         }
         ++launches;
     }
+    nvtxRangePop();
     if (prof) CK(cudaEventRecord(c->ev[1], s));
+    nvtxRangePushA("eaof:fast+blur+octree");
     // FAST is bound by the integer ALU pipe, the blur by the FMA pipe, the quadtree by latency: outside profiling mode
     // (which serialises the stages to time them) the blur runs on the side stream beside FAST + quadtree.
     static const bool serialBlur = getenv("EAOF_SERIAL_BLUR") != nullptr;  // experiment knob
@@ -356,7 +360,9 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     } else {
         CK(cudaStreamWaitEvent(s, c->evBlur, 0));
     }
+    nvtxRangePop();
     if (prof) CK(cudaEventRecord(c->ev[4], s));
+    nvtxRangePushA("eaof:angle+descriptor");
     if (c->readerPending) {
         CK(cudaStreamWaitEvent(s, c->evReader, 0));
         c->readerPending = false;
@@ -368,6 +374,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
                                                              c->dAngleTab, dKps, dDesc, dKpCount, c->kpCap, g);
         ++launches;
     }
+    nvtxRangePop();
     if (prof) CK(cudaEventRecord(c->ev[5], s));
     CK(cudaGetLastError());
     c->lastLaunches = (f0 == 0 ? 0 : c->lastLaunches) + launches;
