@@ -789,7 +789,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
 // and where their children land, (c) relabels the keys.  push_front puts children in front of the list in
 // reverse creation order, so "later created" == "smaller list position", which is also the canonical
 // tie-break for the reference's (size, pointer) sort.
-#define OCT_THREADS 512
+// 256 threads per (frame, level): the passes are barrier-bound, and twice as many resident CTAs hide more of it than
+// 512-thread CTAs do (measured 0.130 -> 0.102 ms per 250 frames; splitting small and large levels into two launches of
+// different widths was slower than one launch)
+#define OCT_THREADS 256
 
 struct OctShared {
     int n;        // list size
