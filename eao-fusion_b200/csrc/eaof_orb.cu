@@ -368,7 +368,10 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         c->readerPending = false;
     }
     {
-        const int warpsPerBlock = 8;
+#ifndef DESC_WARPS
+#define DESC_WARPS 8
+#endif
+        const int warpsPerBlock = DESC_WARPS;
         dim3 gr((g.slotsPerFrame + warpsPerBlock - 1) / warpsPerBlock, n);
         eaof::k_angle_desc<<<gr, warpsPerBlock * 32, 0, s>>>(dPyr, dBlur, dSlotXY, dSlotScore, dLvlCount,
                                                              c->dAngleTab, dKps, dDesc, dKpCount, c->kpCap, g);

@@ -373,7 +373,9 @@ __global__ void __launch_bounds__(256) k_resize_generic(uint8_t* __restrict__ py
 // down RSZ_ROWS inner rows (32, 16 or 8: the host picks the largest that still gives the launch enough threads).  A horizontal pass of one source row is 4 x (2 word loads + PRMT + IDP.2A); the lower
 // source row of one output row is usually the upper row of the next, so it is kept.  Rows that the REFLECT_101
 // border mirrors (inner rows 1..19 and h-20..h-2) are stored twice.
+#ifndef RSZ_THREADS
 #define RSZ_THREADS 128
+#endif
 __device__ __forceinline__ unsigned mad_hi_u32(unsigned a, unsigned b, unsigned c) {
     unsigned d;
     asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -1135,8 +1137,12 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
 // horizontally filtered rows in registers.  The horizontal pass runs on packed 16x2 lanes (the 7-tap sum of
 // bytes times 8-bit taps is <= 255*257 = 65535, so two pixels share a register and a plain IMAD never carries from
 // one lane into the other); the vertical pass needs 25 bits and runs per pixel.
-#define BLUR_ROWS 32
+#ifndef BLUR_ROWS
+#define BLUR_ROWS 16
+#endif
+#ifndef BLUR_THREADS
 #define BLUR_THREADS 128
+#endif
 #ifndef BLUR_AHEAD
 #define BLUR_AHEAD 3
 #endif
