@@ -530,9 +530,6 @@ __device__ __forceinline__ unsigned arc_best2(const unsigned (&d)[16]) {
 #define FAST_MINB 8
 #endif
 #define FAST_CLST 128
-#ifndef FAST_PRETEST_SWAR
-#define FAST_PRETEST_SWAR 1  // 0: the compass test on u16x2 lanes (two adjacent compass pixels on the same side)
-#endif
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8_t* __restrict__ pyr,
                                                                      const CellDesc* __restrict__ cells,
                                                                      uint32_t* __restrict__ cand,
@@ -547,7 +544,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;  // pixel (row r, tile byte column c) at byte (r*PW + 1)*4 + c
     uint32_t* Bm = tile + mapWords;              // arc score of corners (0 elsewhere), same layout
     uint16_t* clst = reinterpret_cast<uint16_t*>(Bm + mapWords);  // corners found by (B): (row, tile byte column)
-    uint16_t* lst = clst + FAST_CLST;                             // surviving (row, word, even/odd pixel pair)
+    uint16_t* lst = clst + FAST_CLST;                             // surviving (row, word, pixel pair (0,1) or (2,3))
     // NMS survivors overwrite the tile: the first one is written only when the attempt that produced it is the last
     // one, and phase (C) reads nothing but the score map.
     uint32_t* outl = tile;
@@ -587,7 +584,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     // The cell is first searched at iniThFAST; only a cell with no keypoint after NMS is searched again at
     // minThFAST (:808-816).  Each attempt: (A) a necessary condition on the 4 compass ring pixels (every 9-arc
     // contains two adjacent compass points) at that threshold, one lane per aligned 4-pixel word, the surviving
-    // even/odd pixel pairs compacted with warp ballots; (B) exact arc score of the survivors, 2 pixels per u16x2 op;
+    // pairs of adjacent pixels compacted with warp ballots; (B) exact arc score of the survivors, 2 pixels per u16x2 op;
     // (C) 8-neighbour NMS restricted to the cell.  Arc scores are threshold independent, so what the first attempt
     // wrote into the score map stays valid for the second.
     int no = 0;
@@ -609,7 +606,6 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                 const uint32_t* t = tile + y * PW + 1 + w;
                 const unsigned W0 = t[0], Wm = t[-1], Wp = t[1], Wu = t[-3 * PW], Wd = t[3 * PW];
                 const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
-#if FAST_PRETEST_SWAR
                 // Every 9-arc of the ring holds one of the pixels {0, 8} and one of {4, 12}, so a corner at threshold th
                 // has |ring - centre| > th on one pixel of each pair.  Four pixels at once: VABSDIFF4 against the words
                 // 3 rows below / above and 3 columns right / left, "byte > th" as a carry into bit 7 of each byte
@@ -620,22 +616,10 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                 const unsigned t4 = (a4 & 0x7f7f7f7fu) + thK, t12 = (a12 & 0x7f7f7f7fu) + thK;
                 const unsigned m = thHigh ? ((t0 & a0) | (t8 & a8)) & ((t4 & a4) | (t12 & a12))
                                           : ((t0 | a0) | (t8 | a8)) & ((t4 | a4) | (t12 | a12));
-                passE = (m & 0x00800080u) != 0;  // pixels 0, 2 of the word
-                passO = (m & 0x80008000u) != 0;  // pixels 1, 3
-#else
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const unsigned nc = FAST_BIAS2 - (h ? odd(W0) : evn(W0));
-                    const unsigned d0 = (h ? odd(Wd) : evn(Wd)) + nc, d4 = (h ? odd(V4) : evn(V4)) + nc;
-                    const unsigned d8 = (h ? odd(Wu) : evn(Wu)) + nc, d12 = (h ? odd(V12) : evn(V12)) + nc;
-                    const unsigned br = __vimax3_u16x2(__vminu2(d0, d4), __vminu2(d4, d8),
-                                                       __vmaxu2(__vminu2(d8, d12), __vminu2(d12, d0)));
-                    const unsigned dk = __vimin3_u16x2(__vmaxu2(d0, d4), __vmaxu2(d4, d8),
-                                                       __vminu2(__vmaxu2(d8, d12), __vmaxu2(d12, d0)));
-                    const bool p = __vimax3_u16x2(br, 2u * FAST_BIAS2 - dk, thB2) != thB2;  // some lane > th
-                    if (h) passO = p; else passE = p;
-                }
-#endif
+                // survivors go to the arc score as pairs of ADJACENT pixels (0,1) and (2,3): neighbours pass together more
+                // often than pixels two apart, so fewer half-empty pairs reach phase (B)
+                passE = (m & 0x00008080u) != 0;  // pixels 0, 1 of the word
+                passO = (m & 0x80800000u) != 0;  // pixels 2, 3
             }
             const unsigned mE = __ballot_sync(0xffffffffu, passE), mO = __ballot_sync(0xffffffffu, passO);
             const int nE = __popc(mE);
@@ -655,9 +639,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
             const uint32_t* t = tile + y * PW + 1 + w;
             unsigned d[16];
             {
-                // lanes = bytes (b, b+2) of the 8-byte pool (lo, hi) for the even pair, (b+1, b+3) for the odd pair:
-                // PRMT selector 0x2200 + 0x1111*(b + od), upper byte of each lane masked off
-                const unsigned sb0 = 0x2200u + (od ? 0x1111u : 0u), sb1 = sb0 + 0x1111u, sb2 = sb1 + 0x1111u, sb3 = sb2 + 0x1111u;
+                // lanes = bytes (b, b+1) of the 8-byte pool (lo, hi) for the pair of pixels 0,1, (b+2, b+3) for pixels 2,3:
+                // PRMT selector 0x1100 + 0x1111*(b + 2*od), upper byte of each lane masked off
+                const unsigned sb0 = 0x1100u + (od ? 0x2222u : 0u), sb1 = sb0 + 0x1111u, sb2 = sb1 + 0x1111u, sb3 = sb2 + 0x1111u;
 #define LANES(v) (__byte_perm(v, 0u, sb0) & 0x00ff00ffu)
 #define LANES2(lo, hi, sb) (__byte_perm(lo, hi, sb) & 0x00ff00ffu)
 #define ROW3(dy, m, z, p) const unsigned m = t[(dy)*PW - 1], z = t[(dy)*PW], p = t[(dy)*PW + 1];
@@ -704,17 +688,17 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
             const unsigned b2 = arc_best2(d);
             // a pixel that is not a corner at this threshold, or lies outside the inner area of the cell (cv::FAST
             // never scores those), keeps 0: the NMS only ever asks "corner ? score : 0"
-            uint8_t* q = reinterpret_cast<uint8_t*>(Bm + y * PW + 1 + w) + (od ? 1 : 0);
-            const int cb = 4 * w + (od ? 1 : 0);
+            uint8_t* q = reinterpret_cast<uint8_t*>(Bm + y * PW + 1 + w) + (od ? 2 : 0);
+            const int cb = 4 * w + (od ? 2 : 0);
             const int bLo = (int)(b2 & 0xffffu) - 256, bHi = (int)(b2 >> 16) - 256;
             const bool k0 = act && bLo > th && cb >= cLo && cb <= cHi;
-            const bool k2 = act && bHi > th && cb + 2 >= cLo && cb + 2 <= cHi;
+            const bool k2 = act && bHi > th && cb + 1 >= cLo && cb + 1 <= cHi;
             if (k0) q[0] = (uint8_t)bLo;
-            if (k2) q[2] = (uint8_t)bHi;
+            if (k2) q[1] = (uint8_t)bHi;
             const unsigned m0 = __ballot_sync(0xffffffffu, k0), m2 = __ballot_sync(0xffffffffu, k2);
             const int p0 = ncorn + __popc(m0 & below), p2 = ncorn + __popc(m0) + __popc(m2 & below);
             if (k0 && p0 < FAST_CLST) clst[p0] = (uint16_t)((y << 8) | cb);
-            if (k2 && p2 < FAST_CLST) clst[p2] = (uint16_t)((y << 8) | (cb + 2));
+            if (k2 && p2 < FAST_CLST) clst[p2] = (uint16_t)((y << 8) | (cb + 1));
             ncorn += __popc(m0) + __popc(m2);
         }
         __syncwarp();
@@ -748,9 +732,9 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
         for (int i0 = 0; i0 < nl; i0 += 32) {
             const int i = i0 + lane;
             const int e = i < nl ? lst[i] : 0, y = e >> 8, w = (e & 255) >> 1;
-            const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * PW + 1 + w) + (e & 1);
+            const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * PW + 1 + w) + 2 * (e & 1);
 #pragma unroll
-            for (int j = 0; j < 4; j += 2) {
+            for (int j = 0; j < 2; ++j) {
                 const uint8_t* q = q0 + j;
                 const int s = (i < nl ? (int)q[0] : 0) - 1;
                 bool keep = false;
@@ -767,7 +751,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                 }
                 const unsigned mk = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
-                    const int x = 4 * w + (e & 1) + j - mis;  // cell coordinates
+                    const int x = 4 * w + 2 * (e & 1) + j - mis;  // cell coordinates
                     const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
                     outl[no + __popc(mk & below)] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
                 }
