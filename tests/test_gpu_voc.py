@@ -168,3 +168,27 @@ def test_search_by_bow_device_resident_end_to_end(frames640, mode):
     mt.close()
     v.close()
     ex.close()
+
+
+def test_cuda_path_reproduces_the_frozen_reference_answers():
+    """CUDA outputs hashed straight against tests/golden/frontend_hashes.json (frozen from the reference's own code), with no
+    oracle in between: vocabulary transform and both SearchByBoW overloads."""
+    import json
+    import eaof
+    from golden_frontend import digest
+    from matchdata import planted_pair, random_nodes
+    with open(os.path.join(ROOT, "tests", "golden", "frontend_hashes.json")) as f:
+        gold = json.load(f)
+    voc = make_vocabulary(10, 3, 0, 0, seed=313)
+    v = eaof.ORBVocabulary(tree_from(voc), max_features=1024)
+    assert digest(*v.transform(features_for(voc, 1000, seed=1004), 2)) == gold["voc_transform"]["sha256"]
+    v.close()
+    for mode in (0, 1):
+        q, aq, t, at = planted_pair(600, 600, 16, dup=5)
+        nq, nt = eaof.csr_from_nodes(random_nodes(600, 12, 26)), eaof.csr_from_nodes(random_nodes(600, 12, 36))
+        rng = np.random.Generator(np.random.PCG64(106))
+        vq, vt = (rng.random(600) > 0.1).astype(np.uint8), (rng.random(600) > 0.1).astype(np.uint8)
+        m = eaof.ORBmatcher(0.75, True, max_features=1024)
+        n, match, _ = m.SearchByBoW(mode, q, aq, vq, nq, t, at, vt, nt)
+        assert digest(np.asarray([n], np.int32), match) == gold[f"search_by_bow_mode{mode}"]["sha256"], mode
+        m.close()
