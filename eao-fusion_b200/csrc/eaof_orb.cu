@@ -148,7 +148,7 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
     uint64_t off = 0;
     uint32_t candOff = 0;
     int slotOff = 0;
-    int fastRows = 7, fastWords = 2, fastList = 2, fastOut = 1;
+    int fastRows = 7, fastWords = 2, fastList = 160, fastOut = 1;
     for (int l = 0; l < g.nlevels; ++l) {
         LevelGeom& L = g.L[l];
         L.w = cv_round_f((float)g.W * c->invScale[l]);  // :1112
@@ -212,7 +212,7 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
                     const int nW = ((mis + cw - 4) >> 2) - ((mis + 3) >> 2) + 1;
                     fastRows = std::max(fastRows, ch);
                     fastWords = std::max(fastWords, nwords);
-                    fastList = std::max(fastList, 2 * (ch - 6) * nW);
+                    fastList = std::max(fastList, std::max(2 * (ch - 6) * nW, 160));  // k_fast refills it in rounds of <= 128
                     fastOut = std::max(fastOut, ((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2));
                 }
                 cap += (uint32_t)(((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2));  // NMS keeps no two 8-adjacent pixels

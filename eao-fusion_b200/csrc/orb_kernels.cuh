@@ -580,6 +580,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     const int nTasks = ih * nW;
     const unsigned rcpW = 65536u / (unsigned)nW + 1u;
     const unsigned below = (1u << lane) - 1;
+    const int lstCap = 2 * (g.fastWarpWords - 2 * mapWords) - FAST_CLST;  // entries the survivor list holds
 
     // The cell is first searched at iniThFAST; only a cell with no keypoint after NMS is searched again at
     // minThFAST (:808-816).  Each attempt: (A) a necessary condition on the 4 compass ring pixels (every 9-arc
@@ -593,118 +594,85 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
         const unsigned thB2 = (unsigned)(th + 256) * 0x00010001u;
         const bool thHigh = th >= 128;
         const unsigned thK = (unsigned)(127 - (th & 127)) * 0x01010101u;
-        // ---- (A)
-        int nl = 0;
-        for (int i0 = 0; i0 < nTasks; i0 += 32) {
-            const int i = i0 + lane;
-            bool passE = false, passO = false;
-            int y = 0, w = 0;
-            if (i < nTasks) {
-                const int r = (int)(((unsigned)i * rcpW) >> 16);
-                w = wLo + (i - r * nW);
-                y = r + 3;
-                const uint32_t* t = tile + y * PW + 1 + w;
-                const unsigned W0 = t[0], Wm = t[-1], Wp = t[1], Wu = t[-3 * PW], Wd = t[3 * PW];
-                const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
-                // Every 9-arc of the ring holds one of the pixels {0, 8} and one of {4, 12}, so a corner at threshold th
-                // has |ring - centre| > th on one pixel of each pair.  Four pixels at once: VABSDIFF4 against the words
-                // 3 rows below / above and 3 columns right / left, "byte > th" as a carry into bit 7 of each byte
-                // (low 7 bits + 127 - th', combined with the byte's own top bit: OR for th < 128, AND for th >= 128).
-                const unsigned a0 = __vabsdiffu4(W0, Wd), a8 = __vabsdiffu4(W0, Wu);
-                const unsigned a4 = __vabsdiffu4(W0, V4), a12 = __vabsdiffu4(W0, V12);
-                const unsigned t0 = (a0 & 0x7f7f7f7fu) + thK, t8 = (a8 & 0x7f7f7f7fu) + thK;
-                const unsigned t4 = (a4 & 0x7f7f7f7fu) + thK, t12 = (a12 & 0x7f7f7f7fu) + thK;
-                const unsigned m = thHigh ? ((t0 & a0) | (t8 & a8)) & ((t4 & a4) | (t12 & a12))
-                                          : ((t0 | a0) | (t8 | a8)) & ((t4 | a4) | (t12 | a12));
-                // survivors go to the arc score as pairs of ADJACENT pixels (0,1) and (2,3): neighbours pass together more
-                // often than pixels two apart, so fewer half-empty pairs reach phase (B)
-                passE = (m & 0x00008080u) != 0;  // pixels 0, 1 of the word
-                passO = (m & 0x80800000u) != 0;  // pixels 2, 3
-            }
-            const unsigned mE = __ballot_sync(0xffffffffu, passE), mO = __ballot_sync(0xffffffffu, passO);
-            const int nE = __popc(mE);
-            const unsigned e = (unsigned)((y << 8) | (w << 1));
-            if (passE) lst[nl + __popc(mE & below)] = (uint16_t)e;
-            if (passO) lst[nl + nE + __popc(mO & below)] = (uint16_t)(e | 1u);
-            nl += nE + __popc(mO);
-        }
-        if (nl == 0) continue;
-        __syncwarp();
-        // ---- (B)
+        // (A) and (B) alternate in rounds: (A) appends the surviving PIXELS (row << 8 | tile byte column) until the list
+        // could overflow, (B) drains it two pixels per lane.  One round for all but noise-like cells.
         int ncorn = 0;  // corners found by (B); the first FAST_CLST of them are listed for (C)
-        for (int i0 = 0; i0 < nl; i0 += 32) {
-            const bool act = i0 + lane < nl;
-            const int e = lst[act ? i0 + lane : 0], y = e >> 8, w = (e & 255) >> 1;
-            const bool od = e & 1;
-            const uint32_t* t = tile + y * PW + 1 + w;
-            unsigned d[16];
-            {
-                // lanes = bytes (b, b+1) of the 8-byte pool (lo, hi) for the pair of pixels 0,1, (b+2, b+3) for pixels 2,3:
-                // PRMT selector 0x1100 + 0x1111*(b + 2*od), upper byte of each lane masked off
-                const unsigned sb0 = 0x1100u + (od ? 0x2222u : 0u), sb1 = sb0 + 0x1111u, sb2 = sb1 + 0x1111u, sb3 = sb2 + 0x1111u;
-#define LANES(v) (__byte_perm(v, 0u, sb0) & 0x00ff00ffu)
-#define LANES2(lo, hi, sb) (__byte_perm(lo, hi, sb) & 0x00ff00ffu)
-#define ROW3(dy, m, z, p) const unsigned m = t[(dy)*PW - 1], z = t[(dy)*PW], p = t[(dy)*PW + 1];
-                ROW3(0, c0m, c0z, c0p)
-                const unsigned nc = FAST_BIAS2 - LANES(c0z);
-                d[4] = LANES2(c0z, c0p, sb3) + nc;
-                d[12] = LANES2(c0m, c0z, sb1) + nc;
-                {
-                    ROW3(3, a3m, a3z, a3p)
-                    d[0] = LANES(a3z) + nc;
-                    d[1] = LANES2(a3z, a3p, sb1) + nc;
-                    d[15] = LANES2(a3m, a3z, sb3) + nc;
+        const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+        uint8_t* mb = reinterpret_cast<uint8_t*>(Bm);
+        const int pitchB = 4 * PW;
+        for (int i0 = 0; i0 < nTasks;) {
+            // ---- (A)
+            int nl = 0;
+            for (; i0 < nTasks && nl + 128 <= lstCap; i0 += 32) {
+                const int i = i0 + lane;
+                unsigned m = 0;
+                int y = 0, w = 0;
+                if (i < nTasks) {
+                    const int r = (int)(((unsigned)i * rcpW) >> 16);
+                    w = wLo + (i - r * nW);
+                    y = r + 3;
+                    const uint32_t* t = tile + y * PW + 1 + w;
+                    const unsigned W0 = t[0], Wm = t[-1], Wp = t[1], Wu = t[-3 * PW], Wd = t[3 * PW];
+                    const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
+                    // Every 9-arc of the ring holds one of the pixels {0, 8} and one of {4, 12}, so a corner at threshold
+                    // th has |ring - centre| > th on one pixel of each pair.  Four pixels at once: VABSDIFF4 against the
+                    // words 3 rows below / above and 3 columns right / left, "byte > th" as a carry into bit 7 of each
+                    // byte (low 7 bits + 127 - th', combined with the byte's own top bit: OR for th < 128, AND above).
+                    const unsigned a0 = __vabsdiffu4(W0, Wd), a8 = __vabsdiffu4(W0, Wu);
+                    const unsigned a4 = __vabsdiffu4(W0, V4), a12 = __vabsdiffu4(W0, V12);
+                    const unsigned t0 = (a0 & 0x7f7f7f7fu) + thK, t8 = (a8 & 0x7f7f7f7fu) + thK;
+                    const unsigned t4 = (a4 & 0x7f7f7f7fu) + thK, t12 = (a12 & 0x7f7f7f7fu) + thK;
+                    m = thHigh ? ((t0 & a0) | (t8 & a8)) & ((t4 & a4) | (t12 & a12))
+                               : ((t0 | a0) | (t8 | a8)) & ((t4 | a4) | (t12 | a12));
+                    m &= 0x80808080u;  // bit 7 of byte j: pixel j of the word survives
                 }
-                {
-                    ROW3(2, a2m, a2z, a2p)
-                    d[2] = LANES2(a2z, a2p, sb2) + nc;
-                    d[14] = LANES2(a2m, a2z, sb2) + nc;
+                const unsigned e = (unsigned)((y << 8) | (w << 2));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool pj = (m >> (8 * j + 7)) & 1u;
+                    const unsigned mj = __ballot_sync(0xffffffffu, pj);
+                    if (pj) lst[nl + __popc(mj & below)] = (uint16_t)(e | (unsigned)j);
+                    nl += __popc(mj);
                 }
-                {
-                    ROW3(1, a1m, a1z, a1p)
-                    d[3] = LANES2(a1z, a1p, sb3) + nc;
-                    d[13] = LANES2(a1m, a1z, sb1) + nc;
-                }
-                {
-                    ROW3(-1, b1m, b1z, b1p)
-                    d[5] = LANES2(b1z, b1p, sb3) + nc;
-                    d[11] = LANES2(b1m, b1z, sb1) + nc;
-                }
-                {
-                    ROW3(-2, b2m, b2z, b2p)
-                    d[6] = LANES2(b2z, b2p, sb2) + nc;
-                    d[10] = LANES2(b2m, b2z, sb2) + nc;
-                }
-                {
-                    ROW3(-3, b3m, b3z, b3p)
-                    d[7] = LANES2(b3z, b3p, sb1) + nc;
-                    d[8] = LANES(b3z) + nc;
-                    d[9] = LANES2(b3m, b3z, sb3) + nc;
-                }
-#undef LANES2
-#undef ROW3
-#undef LANES
             }
-            const unsigned b2 = arc_best2(d);
-            // a pixel that is not a corner at this threshold, or lies outside the inner area of the cell (cv::FAST
-            // never scores those), keeps 0: the NMS only ever asks "corner ? score : 0"
-            uint8_t* q = reinterpret_cast<uint8_t*>(Bm + y * PW + 1 + w) + (od ? 2 : 0);
-            const int cb = 4 * w + (od ? 2 : 0);
-            const int bLo = (int)(b2 & 0xffffu) - 256, bHi = (int)(b2 >> 16) - 256;
-            const bool k0 = act && bLo > th && cb >= cLo && cb <= cHi;
-            const bool k2 = act && bHi > th && cb + 1 >= cLo && cb + 1 <= cHi;
-            if (k0) q[0] = (uint8_t)bLo;
-            if (k2) q[1] = (uint8_t)bHi;
-            const unsigned m0 = __ballot_sync(0xffffffffu, k0), m2 = __ballot_sync(0xffffffffu, k2);
-            const int p0 = ncorn + __popc(m0 & below), p2 = ncorn + __popc(m0) + __popc(m2 & below);
-            if (k0 && p0 < FAST_CLST) clst[p0] = (uint16_t)((y << 8) | cb);
-            if (k2 && p2 < FAST_CLST) clst[p2] = (uint16_t)((y << 8) | (cb + 1));
-            ncorn += __popc(m0) + __popc(m2);
+            if (nl == 0) continue;
+            __syncwarp();
+            // ---- (B): lane takes two list entries; their ring pixels are read as bytes (no lane extraction) and packed
+            // into u16x2 for the arc score
+            for (int p0 = 0; p0 < nl; p0 += 64) {
+                const int iA = p0 + 2 * lane;
+                const bool actA = iA < nl, actB = iA + 1 < nl;
+                const int eA = lst[actA ? iA : 0], eB = lst[actB ? iA + 1 : (actA ? iA : 0)];
+                const int oA = ((eA >> 8) * PW + 1) * 4 + (eA & 255), oB = ((eB >> 8) * PW + 1) * 4 + (eB & 255);
+                const uint8_t* pA = tb + oA;
+                const uint8_t* pB = tb + oB;
+                const unsigned nc = FAST_BIAS2 - ((unsigned)pA[0] | ((unsigned)pB[0] << 16));
+                unsigned d[16];
+#define RING2(k, off) d[k] = ((unsigned)pA[off] | ((unsigned)pB[off] << 16)) + nc;
+                RING2(0, 3 * pitchB) RING2(1, 3 * pitchB + 1) RING2(2, 2 * pitchB + 2) RING2(3, pitchB + 3)
+                RING2(4, 3) RING2(5, -pitchB + 3) RING2(6, -2 * pitchB + 2) RING2(7, -3 * pitchB + 1)
+                RING2(8, -3 * pitchB) RING2(9, -3 * pitchB - 1) RING2(10, -2 * pitchB - 2) RING2(11, -pitchB - 3)
+                RING2(12, -3) RING2(13, pitchB - 3) RING2(14, 2 * pitchB - 2) RING2(15, 3 * pitchB - 1)
+#undef RING2
+                const unsigned b2 = arc_best2(d);
+                // a pixel that is not a corner at this threshold, or lies outside the inner area of the cell (cv::FAST
+                // never scores those), keeps 0: the NMS only ever asks "corner ? score : 0"
+                const int cA = eA & 255, cB = eB & 255;
+                const int bLo = (int)(b2 & 0xffffu) - 256, bHi = (int)(b2 >> 16) - 256;
+                const bool k0 = actA && bLo > th && cA >= cLo && cA <= cHi;
+                const bool k2 = actB && bHi > th && cB >= cLo && cB <= cHi;
+                if (k0) mb[oA] = (uint8_t)bLo;
+                if (k2) mb[oB] = (uint8_t)bHi;
+                const unsigned m0 = __ballot_sync(0xffffffffu, k0), m2 = __ballot_sync(0xffffffffu, k2);
+                const int p0c = ncorn + __popc(m0 & below), p2c = ncorn + __popc(m0) + __popc(m2 & below);
+                if (k0 && p0c < FAST_CLST) clst[p0c] = (uint16_t)eA;
+                if (k2 && p2c < FAST_CLST) clst[p2c] = (uint16_t)eB;
+                ncorn += __popc(m0) + __popc(m2);
+            }
+            __syncwarp();
         }
-        __syncwarp();
         if (ncorn == 0) continue;
         // ---- (C)
-        const int pitchB = 4 * PW;
         if (ncorn <= FAST_CLST) {
             for (int i0 = 0; i0 < ncorn; i0 += 32) {
                 const bool act = i0 + lane < ncorn;
@@ -728,15 +696,16 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                 }
                 no += __popc(mk);
             }
-        } else  // more corners than the list holds (noise-like cells): scan every surviving pair
-        for (int i0 = 0; i0 < nl; i0 += 32) {
+        } else  // more corners than the list holds (noise-like cells): scan the score map of the inner area
+        for (int i0 = 0; i0 < nTasks; i0 += 32) {
             const int i = i0 + lane;
-            const int e = i < nl ? lst[i] : 0, y = e >> 8, w = (e & 255) >> 1;
-            const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * PW + 1 + w) + 2 * (e & 1);
+            const int r = (int)(((unsigned)min(i, nTasks - 1) * rcpW) >> 16);
+            const int w = wLo + (min(i, nTasks - 1) - r * nW), y = r + 3;
+            const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * PW + 1 + w);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 const uint8_t* q = q0 + j;
-                const int s = (i < nl ? (int)q[0] : 0) - 1;
+                const int s = (i < nTasks ? (int)q[0] : 0) - 1;
                 bool keep = false;
                 if (s >= 0) {
                     int nbMax = 0;  // stored scores are either 0 or > th
@@ -751,7 +720,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                 }
                 const unsigned mk = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
-                    const int x = 4 * w + 2 * (e & 1) + j - mis;  // cell coordinates
+                    const int x = 4 * w + j - mis;  // cell coordinates
                     const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
                     outl[no + __popc(mk & below)] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
                 }
