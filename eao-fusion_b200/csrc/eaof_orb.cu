@@ -212,7 +212,11 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
                     const int nW = ((mis + cw - 4) >> 2) - ((mis + 3) >> 2) + 1;
                     fastRows = std::max(fastRows, ch);
                     fastWords = std::max(fastWords, nwords);
+#ifdef FAST_LIST_CAP
+                    fastList = FAST_LIST_CAP;
+#else
                     fastList = std::max(fastList, std::max(2 * (ch - 6) * nW, 160));  // k_fast refills it in rounds of <= 128
+#endif
                     fastOut = std::max(fastOut, ((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2));
                 }
                 cap += (uint32_t)(((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2));  // NMS keeps no two 8-adjacent pixels
