@@ -317,7 +317,10 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         const LevelGeom& L = g.L[l];
         if (L.h >= 40) {
             // rows per thread: long walks reuse source rows, but small levels / small batches need the threads
-            const long long want = 600000;
+#ifndef RSZ_WANT
+#define RSZ_WANT 600000
+#endif
+            const long long want = RSZ_WANT;
             const int nCW = (L.w + 43) / 4;
             int rows = 32;
             while (rows > 8 && (long long)nCW * ((L.h + rows - 1) / rows) * n < want) rows >>= 1;
