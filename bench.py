@@ -584,8 +584,8 @@ def main():
         dom = max(("pyramid", "fast", "octree", "blur", "angle_desc"), key=lambda k: stage_acc[k])
         roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": stages[dom]["frac"], "traffic": ncu_traffic(dom, B), "peak_source": peak_src,
-                    "alu_pipe_note": "k_fast is bound by the INT ALU issue pipe (ncu: sm__inst_executed_pipe_alu 82 % of peak, "
-                                     "dram 4 %), see profiles/",
+                    "alu_pipe_note": "k_fast is bound by instruction issue, not by HBM (ncu, profiles/r01_fast_full4_summary.txt: issue "
+                                     "slots 79 %, INT ALU pipe 68 %, LSU 41 %, dram 5 %; DRAM traffic x1.11 of the algorithmic bytes)",
                     "whole_path": {"alg_bytes_per_frame": sum(alg.values()),
                                    "achieved": sum(alg.values()) * value / 1e9, "frac": sum(alg.values()) * value / 1e9 / hbm_peak}}
         cores = os.cpu_count() or 1
