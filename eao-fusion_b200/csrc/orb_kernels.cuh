@@ -586,16 +586,15 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     const int lstCap = 2 * (g.fastWarpWords - 2 * mapWords) - FAST_CLST;  // entries the survivor list holds
 
     // The cell is first searched at iniThFAST; only a cell with no keypoint after NMS is searched again at
-    // minThFAST (:808-816).  Each attempt: (A) a necessary condition on the 4 compass ring pixels (every 9-arc
-    // contains two adjacent compass points) at that threshold, one lane per aligned 4-pixel word, the surviving
-    // pairs of adjacent pixels compacted with warp ballots; (B) exact arc score of the survivors, 2 pixels per u16x2 op;
-    // (C) 8-neighbour NMS restricted to the cell.  Arc scores are threshold independent, so what the first attempt
+    // minThFAST (:808-816).  Each attempt: (A) a necessary condition on the 4 compass ring pixels (every 9-arc holds
+    // one of the pixels {0, 8} and one of {4, 12}) at that threshold, one lane per aligned 4-pixel word on byte lanes,
+    // the surviving pixels compacted with warp ballots; (B) exact arc score of the survivors, any two of them per lane
+    // on u16x2; (C) 8-neighbour NMS restricted to the cell.  Arc scores are threshold independent, so what the first attempt
     // wrote into the score map stays valid for the second.
     int no = 0;
     for (int attempt = 0; attempt < 2 && no == 0; ++attempt) {
         const int th = attempt == 0 ? g.iniTh : g.minTh;
-        const unsigned thB2 = (unsigned)(th + 256) * 0x00010001u;
-        const bool thHigh = th >= 128;
+            const bool thHigh = th >= 128;
         const unsigned thK = (unsigned)(127 - (th & 127)) * 0x01010101u;
         // (A) and (B) alternate in rounds: (A) appends the surviving PIXELS (row << 8 | tile byte column) until the list
         // could overflow, (B) drains it two pixels per lane.  One round for all but noise-like cells.
