@@ -490,8 +490,6 @@ __device__ __forceinline__ int arc_best(const uint8_t* p) {
 // ---- packed 16x2 helpers: one 32-bit register carries the same quantity for two pixels, and VIMNMX(3).U16x2
 // works on both halves in one issue slot.  Differences ring - centre are kept biased by +256 (range 1..511) so that
 // they are formed by a plain 32-bit add (no borrow can cross the lanes) and compare as unsigned.
-__device__ __forceinline__ unsigned evn(unsigned v) { return v & 0x00ff00ffu; }              // bytes 0,2 -> lanes
-__device__ __forceinline__ unsigned odd(unsigned v) { return __byte_perm(v, 0u, 0x4341); }   // bytes 1,3 -> lanes
 #define FAST_BIAS2 0x01000100u
 
 // Arc score of two pixels at once.  d[k] = 256 + ring_k - centre on u16x2 lanes.  Returns 256 + max(bright, dark)
