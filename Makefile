@@ -6,8 +6,8 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 --fmad=false -Xcompiler -fPIC,-Wall -Xptxas -v $(EXTRA)
 PKG       := eao-fusion_b200
 LIB       := $(PKG)/lib/libeaof_orb.so
-SRCS      := $(PKG)/csrc/eaof_orb.cu $(PKG)/csrc/eaof_match.cu $(PKG)/csrc/eaof_voc.cu
-HDRS      := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/eaof_orb.h include/eaof_match.h include/eaof_voc.h
+SRCS      := $(PKG)/csrc/eaof_orb.cu $(PKG)/csrc/eaof_match.cu $(PKG)/csrc/eaof_voc.cu $(PKG)/csrc/eaof_sweep.cu
+HDRS      := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/eaof_orb.h include/eaof_match.h include/eaof_voc.h include/eaof_sweep.h
 
 DROPIN_T  := tests/cpp/_build/libdropin_harness.so
 DROPIN_M  := tests/cpp/_build/libmatch_dropin.so
@@ -17,9 +17,9 @@ REF       ?= /root/reference
 all: $(LIB) $(DROPIN_T) matchdropin vocdropin
 
 $(LIB): $(SRCS) $(HDRS)
-	@mkdir -p $(PKG)/lib
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) 2> $(PKG)/lib/ptxas.log || (cat $(PKG)/lib/ptxas.log; exit 1)
-	@grep -E "registers|spill|error" $(PKG)/lib/ptxas.log | sed 's/^/  /' | head -60
+	@mkdir -p $(PKG)/lib build
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) -ldl 2> build/ptxas.log || (cat build/ptxas.log; exit 1)
+	@grep -E "registers|spill|error" build/ptxas.log | sed 's/^/  /' | head -80
 
 # the drop-in ORB_SLAM2::ORBextractor compiled against the cv shim (test harness; deployment compiles
 # $(PKG)/dropin/ORBextractor.cc against the real OpenCV)
@@ -64,7 +64,7 @@ sanitize: all
 	compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "stages or voc or stereo or distinctive"
 
 clean:
-	rm -f $(LIB) $(PKG)/lib/ptxas.log $(DROPIN_T) $(DROPIN_M) $(DROPIN_V)
+	rm -f $(LIB) build/ptxas.log $(DROPIN_T) $(DROPIN_M) $(DROPIN_V)
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean matchdropin vocdropin sanitize

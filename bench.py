@@ -1,17 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — ORB front-end throughput on B200 (BASELINE.json metric: ORB frames/s @640x480/1000kp).
+"""bench.py — ORB front-end throughput on B200 (BASELINE.json metric: ORB frames/s @640x480/1000kp; Hamming matches/s).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): a 1000-frame synthetic 640x480 sequence, nfeatures=1000, 8 levels, 1.2, 20/7.
-A "step" is one pass of the hot path over one batch of B consecutive frames of that sequence (extraction of every
-frame, plus — when the matcher is built — consecutive-frame SearchByProjection-style matching).
-  value  = frames/s with the frames already resident in HBM (device-timed, CUDA events, max over ranks);
-  e2e    = frames/s through the public C-ABI call eaof_orb_extract_batch with pinned HOST buffers: H2D of the
-           frames and D2H of keypoints+descriptors inside the timed region;
+Workload (BASELINE.json configs[1]): a 1000-frame synthetic 640x480 sequence per GPU, nfeatures=1000, 8 levels, 1.2, 20/7.
+A "step" is one pass of the hot path over that sequence: extraction of every frame plus consecutive-frame
+SearchByProjection-style matching of all its pairs, issued as 1000/B batches of B frames; a batch carries one halo frame
+in front (the last frame of the previous batch / of the previous rank's block, recomputed — eaof/shard.py) so that the
+pair across every batch and rank boundary is matched too.
+  value    = frames/s with the frames already resident in HBM (device-timed, CUDA events, max over ranks);
+  e2e      = frames/s through the C-ABI calls with pinned HOST buffers: H2D of the frames and D2H of keypoints,
+             descriptors and matches inside the timed region;
   roofline / stages = per-stage device time (CUDA events inside the library) against the measured HBM peak;
-  cpu_baseline = the reference's own ORBextractor.cc (oracle/_ref) on this box's host cores, bounded sample.
-Multi-GPU: frames are sharded across ranks, no collective on the data path (weak scaling: B frames per GPU per step).
+  sustained = the same step repeated back to back for >= 2 s;
+  sweep    = configs[4]: 100k frame pairs of 2000x2000 descriptors, blocks sharded over the ranks, one ncclAllGather
+             inside libeaof_orb.so (include/eaof_sweep.h), pair list partitioned round-robin;
+  determinism = the configs[1] sequence sharded over the ranks (block + halo) reproduces the single-GPU digests;
+  parity   = those digests against the unmodified reference ORBextractor.cc + the matcher oracle on the same frames;
+  other_configs = configs[2] (848x480/1200) and configs[3] (1920x1080/4000): frames/s, e2e, per-stage roofline;
+  cpu_baseline = the reference's own ORBextractor.cc (oracle/_ref) on this box's host cores, bounded sample, plus the
+             single-thread per-frame latency the reference really runs at (alpha) and a cv2-primitive estimate.
+Multi-GPU: rank r owns frames [1000 r, 1000 (r+1)) of a world x 1000-frame sequence (weak scaling), no collective on
+the extraction / consecutive-matching path; the sweep has the path's one exchange step.
 """
 from __future__ import annotations
 
@@ -30,11 +40,14 @@ for p in (ROOT, os.path.join(ROOT, "eao-fusion_b200")):
 
 import numpy as np  # noqa: E402
 
-W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
-SEQ_LEN = 1000
-MATCH_TH = 15.0          # TrackWithMotionModel's window, src/Tracking.cc:1749-1753
-SHIFT = (-2.0, -1.0)     # the synthetic sequence drifts by (2,1) px per frame (eaof/synth.py)
+from eaof import shard, workload  # noqa: E402
+from eaof.workload import CONFIGS, INI_TH, MATCH_TH, MIN_TH, NLEVELS, SCALE, SEQ_LEN, SHIFT  # noqa: E402
+
+CFG = CONFIGS["configs[1]"]
+W, H, NFEAT = CFG["width"], CFG["height"], CFG["nfeatures"]
 METRIC = "ORB frames/s (pyramid+FAST+octree+rBRIEF) @640x480/1000kp"
+WORKLOAD = "configs[1]: " + CFG["what"]
+STAGES = ("pyramid", "fast", "octree", "blur", "angle_desc")
 
 
 def peaks():
@@ -45,78 +58,623 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(stage, frames_per_launch):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernel from the committed `ncu --set full` capture
-    (profiles/ncu_traffic.json), scaled to this run's frames per launch; None when no capture exists."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+def ncu_capture(stage):
+    """The committed `ncu --set full` capture of the stage's kernel (profiles/ncu_traffic.json) or {}."""
     try:
-        with open(path) as f:
-            t = json.load(f)[stage]
-        return t["dram_bytes_per_launch"] * frames_per_launch / t["frames_per_launch"]
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[stage]
     except Exception:
-        return None
+        return {}
 
 
-def hamming_sweep(eaof, torch, device, n_blocks=64, n_feat=2000, n_pairs=1024, reps=5):
-    """BASELINE.json configs[4] on one GPU: brute-force SearchByBoW semantics (one node holding every feature, TH_LOW=50,
-    ratio 0.9, rotation histogram) over pairs of 2000-descriptor blocks resident in HBM.  Reports descriptor-pair
-    distances/s against the POPC issue rate measured on this device (8 POPC32 per distance)."""
-    import ctypes as C
-    rng = np.random.Generator(np.random.PCG64(77))
-    base = rng.integers(0, 256, size=(n_feat, 32), dtype=np.uint8)
-    desc = np.empty((n_blocks, n_feat, 32), np.uint8)
-    ang = np.empty((n_blocks, n_feat), np.float32)
-    a0 = rng.uniform(0, 360, n_feat).astype(np.float32)
-    for b in range(n_blocks):  # every block: 70 % noisy copies of the base rows (8 % bit flips), 30 % random rows
-        d = rng.integers(0, 256, size=(n_feat, 32), dtype=np.uint8)
-        keep = rng.permutation(n_feat)[: int(0.7 * n_feat)]
-        flips = np.packbits((rng.random((len(keep), 256)) < 0.08).astype(np.uint8), axis=1)
-        d[keep] = base[keep] ^ flips
-        desc[b] = d
-        ang[b] = np.mod(a0 + rng.normal(0, 5, n_feat), 360).astype(np.float32)
-    d_desc = torch.from_numpy(desc).cuda(device)
-    d_ang = torch.from_numpy(ang).cuda(device)
-    d_cnt = torch.full((n_blocks,), n_feat, dtype=torch.int32, device="cuda")
-    pq = (np.arange(n_pairs) % n_blocks).astype(np.int32)
-    pt = ((np.arange(n_pairs) * 7 + 1 + np.arange(n_pairs) // n_blocks) % n_blocks).astype(np.int32)
-    mt = eaof.ORBmatcher(0.9, True, max_features=n_feat, max_pairs=n_pairs, device=device)
-    d_match = torch.empty((n_pairs, n_feat), dtype=torch.int32, device="cuda")
-    d_dist = torch.empty((n_pairs, n_feat), dtype=torch.int32, device="cuda")
-    d_nm = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
-    st = torch.cuda.ExternalStream(mt.stream_ptr(), device=torch.device("cuda", device))
+def algorithmic_bytes(width, height, level_sizes, kp_per_frame, cand_per_frame):
+    """Per-frame algorithmic bytes per stage, SURVEY.md §8(d)."""
+    P = sum(w * h for w, h in level_sizes)
+    Pb = sum((w + 38) * (h + 38) for w, h in level_sizes)
+    w7, h7 = level_sizes[-1]
+    return {
+        "pyramid": width * height + (P - w7 * h7) + Pb,
+        "fast": P,
+        "octree": 12 * cand_per_frame + 20 * kp_per_frame,
+        "blur": 2 * P,
+        "angle_desc": kp_per_frame * (749 + 1369 + 52),
+    }
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        return self.summary()
+
+    def summary(self, t0=None, t1=None):
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, r in list(self.rows):
+            if (t0 is not None and ts < t0) or (t1 is not None and ts > t1):
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_mhz_min": min(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU side: the reference arm and the baselines reported beside the GPU number
+
+def cpu_match_pairs(feats, scale_factors, width, height, threads):
+    """Oracle port of SearchByProjection(Cur,Last) (src/ORBmatcher.cc:1328-1472) over the consecutive pairs of `feats`
+    on `threads` host threads (the C function releases the GIL).  Returns (wall seconds, list of (match, dist))."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po
+    bounds = (0.0, float(width), 0.0, float(height))
+    ginv = (np.float32(64) / np.float32(width), np.float32(48) / np.float32(height))
+
+    def one(i):
+        (ck, cd), (lk, ld) = feats[i], feats[i - 1]
+        cur = dict(x=ck["x"], y=ck["y"], octave=ck["octave"], angle=ck["angle"], desc=cd)
+        last = dict(u=lk["x"] + np.float32(SHIFT[0]), v=lk["y"] + np.float32(SHIFT[1]), octave=lk["octave"], angle=lk["angle"], desc=ld)
+        _, m, d = po.o_search_by_projection(cur, last, MATCH_TH, True, bounds=bounds, grid_inv=ginv, scale_factors=scale_factors)
+        return m, d
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        out = list(ex.map(one, range(1, len(feats))))
+    return time.perf_counter() - t0, out
+
+
+def cpu_reference_pass(frames, cores, nfeatures=NFEAT, canonical=False):
+    """One pass of the reference CPU path over `frames`: the unmodified ORBextractor.cc frame-parallel on `cores` threads
+    (one extractor instance per thread) + the projection matcher over all consecutive pairs on the same threads."""
+    from oracle import pyoracle as po
+    t_ex, per, feats = po.ref_extract_many(frames, nfeatures, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=canonical)
+    sf = po.o_tables(nfeatures, SCALE, NLEVELS)["scale"]
+    t_m, matches = cpu_match_pairs(feats, sf, frames.shape[2], frames.shape[1], cores)
+    return t_ex, t_m, feats, matches
+
+
+def cv2_primitive_estimate(frame, threads_note=1):
+    """What the pixel primitives of one frame cost with OpenCV's own SIMD code (cv2 wheel of this image, one thread):
+    pyramid (resize + copyMakeBorder), FAST over every level, GaussianBlur of every level.  A lower bound for those
+    stages of a reference built against a real OpenCV; the reference's own code (cell loop, quadtree, IC_Angle, rBRIEF)
+    is not in it."""
+    try:
+        import cv2
+    except Exception as e:  # reported, never required
+        return {"unavailable": repr(e)}
+    cv2.setNumThreads(1)
+    inv = [1.0]
+    sc = np.float32(1.0)
+    for _ in range(1, NLEVELS):
+        sc = np.float32(sc * np.float32(SCALE))
+        inv.append(float(np.float32(1.0) / sc))
+    h0, w0 = frame.shape
+    fast20 = cv2.FastFeatureDetector_create(threshold=INI_TH, nonmaxSuppression=True)
 
     def run():
-        mt.bruteforce_batch_device(0, pq, pt, d_desc.data_ptr(), d_ang.data_ptr(), d_cnt.data_ptr(), n_feat,
-                                   d_match.data_ptr(), d_dist.data_ptr(), d_nm.data_ptr())
-    run(); run(); mt.sync()
+        t = {}
+        a = time.perf_counter()
+        levels = [frame]
+        for l in range(1, NLEVELS):
+            sz = (int(round(w0 * inv[l])), int(round(h0 * inv[l])))
+            levels.append(cv2.resize(levels[-1], sz, interpolation=cv2.INTER_LINEAR))
+        bordered = [cv2.copyMakeBorder(im, 19, 19, 19, 19, cv2.BORDER_REFLECT_101) for im in levels]
+        t["pyramid_ms"] = (time.perf_counter() - a) * 1e3
+        a = time.perf_counter()
+        n = 0
+        for im in levels:
+            n += len(fast20.detect(im))
+        t["fast_whole_level_ms"] = (time.perf_counter() - a) * 1e3
+        a = time.perf_counter()
+        for im in bordered:
+            cv2.GaussianBlur(im, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        t["blur_ms"] = (time.perf_counter() - a) * 1e3
+        return t
+    run()
+    reps = [run() for _ in range(10)]
+    out = {k: float(np.median([r[k] for r in reps])) for k in reps[0]}
+    out["sum_ms"] = sum(out.values())
+    out["note"] = ("cv2 %s, 1 thread; FAST once per level at iniThFAST over the whole level (the reference calls it per 30-px "
+                   "cell and again at minThFAST for empty cells)" % cv2.__version__)
+    return out
+
+
+def cpu_baselines(seq, cores):
+    """cpu_baseline (beta: all cores, throughput), alpha (1 thread, per-frame latency), cv2 primitive estimate."""
+    from oracle import pyoracle as po
+    kind = "reference" if os.path.exists(po.REF_SO) else "port"
+    n = min(SEQ_LEN, max(cores * 8, 64))
+    frames = seq.frames(0, n)
+    po.ref_extract_many(frames[:cores], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, want_results=False)
+    t_ex, t_m, feats, _ = cpu_reference_pass(frames, cores)
+    beta = n / (t_ex + t_m)
+    # alpha: how the reference actually runs — one frame per call on one thread (src/Frame.cc:193,229-231 prints this time)
+    na = 220
+    fa = seq.frames(0, na)
+    _, per, _ = po.ref_extract_many(fa, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=1, canonical=False, want_results=False)
+    per = np.sort(per[20:]) * 1e3  # 20 warm-up frames
+    sf = po.o_tables(NFEAT, SCALE, NLEVELS)["scale"]
+    t_m1, _ = cpu_match_pairs(feats[:33], sf, W, H, 1)
+    alpha = {"workload": "configs[0]: one 640x480 frame per ORBextractor::operator() call, one host thread (how Tracking runs it)",
+             "frames": int(len(per)), "median_ms": float(np.median(per)), "p5_ms": float(per[int(0.05 * len(per))]),
+             "p95_ms": float(per[int(0.95 * len(per))]), "match_projection_ms_per_pair": t_m1 / 32 * 1e3, "kind": kind}
+    cpu = {"value": beta, "unit": "frames/s", "cores": cores, "kind": kind,
+           "sample": f"{n} frames of the sequence, frame-parallel on {cores} threads: unmodified reference ORBextractor.cc over the "
+                     f"cv shim ({n / t_ex:.0f} frames/s) + oracle port of SearchByProjection over the {n - 1} pairs on the same threads "
+                     f"({t_m / (n - 1) * 1e3 * 1.0:.3f} ms wall per pair)"}
+    return cpu, alpha, cv2_primitive_estimate(frames[0])
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, same config,
+    metric and unit; a step = the same 1000-frame sequence (extraction + all 999 consecutive pairs)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    from oracle import pyoracle as po
+    kind = "reference" if os.path.exists(po.REF_SO) else "port"
+    seq = workload.Sequence(W, H)
+    frames = seq.frames(0, SEQ_LEN)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t_ex, t_m, _, _ = cpu_reference_pass(frames, cores)
+        if i >= args.warmup:
+            times.append(t_ex + t_m)
+    tot = sum(times)
+    val = SEQ_LEN * len(times) / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": SEQ_LEN},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{SEQ_LEN} frames per step, frame-parallel on {cores} threads: unmodified reference ORBextractor.cc "
+                                   f"over the cv shim ({SEQ_LEN / t_ex:.0f} frames/s) + oracle port of SearchByProjection over the 999 "
+                                   f"pairs on the same threads ({t_m * 1e3:.1f} ms per step)"},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU side
+
+class Rig:
+    """One extractor + matcher pair sized for batches of B frames + 1 halo frame, and the per-batch pair lists."""
+
+    def __init__(self, eaof, torch, device, width, height, nfeatures, B):
+        self.eaof, self.torch, self.device, self.B = eaof, torch, device, B
+        self.w, self.h = width, height
+        self.ex = eaof.ORBextractor(nfeatures, SCALE, NLEVELS, INI_TH, MIN_TH, width=width, height=height, max_batch=B + 1, device=device)
+        self.cap = self.ex.cap
+        self.mt = eaof.ORBmatcher(0.9, True, max_features=self.cap, max_pairs=B, device=device)
+        self.pair_last, self.pair_cur = np.arange(0, B, dtype=np.int32), np.arange(1, B + 1, dtype=np.int32)
+        self.shift_x, self.shift_y = np.full(B, SHIFT[0], np.float32), np.full(B, SHIFT[1], np.float32)
+        self.d_match = torch.empty((B, self.cap), dtype=torch.int32, device="cuda")
+        self.d_dist = torch.empty((B, self.cap), dtype=torch.int32, device="cuda")
+        self.d_nm = torch.zeros(B, dtype=torch.int32, device="cuda")
+
+    def batch_device(self, d_ptr):
+        """d_ptr: B+1 packed frames (halo first) resident in HBM."""
+        self.ex.extract_batch_device(d_ptr, self.B + 1)
+        # consecutive-frame SearchByProjection over the keypoints that just landed in HBM (waits on the extractor stream)
+        self.mt.projection_batch_device(self.ex, self.pair_last, self.pair_cur, self.shift_x, self.shift_y, MATCH_TH,
+                                        self.d_match.data_ptr(), self.d_dist.data_ptr(), self.d_nm.data_ptr())
+
+    def streams(self):
+        dev = self.torch.device("cuda", self.device)
+        return (self.torch.cuda.ExternalStream(self.ex.stream_ptr(), device=dev),
+                self.torch.cuda.ExternalStream(self.mt.stream_ptr(), device=dev))
+
+    def close(self):
+        self.mt.close()
+        self.ex.close()
+
+
+def rank_sequence(seq, rank):
+    """(SEQ_LEN + 1, h, w): slot 0 = the halo frame (global frame rank*SEQ_LEN - 1; rank 0 has none and carries a copy of
+    frame 0 there so that every batch has the same shape — its pair is not counted), slots 1.. = the rank's block."""
+    b = rank * SEQ_LEN
+    if rank == 0:
+        fr = seq.frames(0, SEQ_LEN)
+        return np.concatenate([fr[:1], fr])
+    return seq.frames(b - 1, b + SEQ_LEN)
+
+
+def measure_config(eaof, torch, dist, rank, world, device, name, B, steps, warmup, frames_host, sustained_s=0.0, e2e_steps=None,
+                   sampler=None, want_stage_profile=True):
+    """Device-resident + e2e throughput and the per-stage table of one config on this rank's frames.
+    frames_host: (n_seq + 1, h, w) with the halo slot in front."""
+    cfg = CONFIGS[name]
+    width, height, nfeat = cfg["width"], cfg["height"], cfg["nfeatures"]
+    n_seq = frames_host.shape[0] - 1
+    assert n_seq % B == 0, "the sequence must be a whole number of batches"
+    n_batches = n_seq // B
+    frame_bytes = width * height
+    rig = Rig(eaof, torch, device, width, height, nfeat, B)
+    ex, mt, cap = rig.ex, rig.mt, rig.cap
+    d_seq = torch.from_numpy(frames_host).cuda(device)  # inputs resident in HBM before the timed region
+
+    def dev_step():
+        for b in range(n_batches):
+            rig.batch_device(d_seq.data_ptr() + b * B * frame_bytes)  # frames [bB-1, bB+B) of the block: halo + batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        dev_step()
+    ex.sync(); mt.sync()
+    xs, ms = rig.streams()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_host0 = time.perf_counter()
+    ev0.record(xs)
+    for _ in range(steps):
+        dev_step()
+    ev1.record(ms)  # the matcher stream finishes last (it waits on the extractor stream every batch)
+    ex.sync(); mt.sync()
+    torch.cuda.synchronize()
+    t_host1 = time.perf_counter()
+    dt = ev0.elapsed_time(ev1) * 1e-3
+    launches_per_batch = ex.last_launch_count() + 3  # + k_build_grid, k_proj_dense, k_proj_resolve
+    counts = ex.fetch_counts(B + 1)[1:]
+    kp_per_frame = float(counts.mean())
+    matches_per_pair = float(rig.d_nm.float().mean().item())
+    cand = []
+    for f in range(1, min(B, 8) + 1):
+        cand.append(sum(len(ex.candidates(l, frame=f)) for l in range(NLEVELS)))
+    cand_per_frame = float(np.mean(cand))
+    barrier()
+    out = {"dt": dt, "t_host": (t_host0, t_host1), "kp_per_frame": kp_per_frame, "cand_per_frame": cand_per_frame,
+           "matches_per_pair": matches_per_pair, "launches_per_step": launches_per_batch * n_batches, "n_batches": n_batches,
+           "frames_per_step": n_seq, "cap": cap, "level_sizes": [ex.level_size(l) for l in range(NLEVELS)]}
+
+    # sustained: the same step back to back for >= sustained_s seconds of device time (clock / power behaviour)
+    if sustained_s > 0:
+        n_sus = max(steps, int(np.ceil(sustained_s / max(dt / steps, 1e-6))))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ts0 = time.perf_counter()
+        s0.record(xs)
+        for _ in range(n_sus):
+            dev_step()
+        s1.record(ms)
+        ex.sync(); mt.sync()
+        torch.cuda.synchronize()
+        ts1 = time.perf_counter()
+        out["sustained"] = {"steps": n_sus, "dt": s0.elapsed_time(s1) * 1e-3, "t_host": (ts0, ts1)}
+        barrier()
+
+    # per-stage device times (CUDA events on the library's stream; profiling mode serialises blur behind the quadtree)
+    if want_stage_profile:
+        ex.set_profiling(True)
+        acc = {}
+        nprof = min(n_batches * 2, 8)
+        me0, me1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(nprof):
+            b = i % n_batches
+            ex.extract_batch_device(d_seq.data_ptr() + b * B * frame_bytes, B + 1)
+            ex.sync()
+            for k, v in ex.stage_times().items():
+                acc[k] = acc.get(k, 0.0) + v / nprof
+            me0.record(ms)
+            mt.projection_batch_device(ex, rig.pair_last, rig.pair_cur, rig.shift_x, rig.shift_y, MATCH_TH, rig.d_match.data_ptr(),
+                                       rig.d_dist.data_ptr(), rig.d_nm.data_ptr())
+            me1.record(ms)
+            mt.sync()
+            acc["match_projection"] = acc.get("match_projection", 0.0) + me0.elapsed_time(me1) / nprof
+        ex.set_profiling(False)
+        out["stage_ms_per_batch"] = acc
+        del me0, me1
+
+    # e2e through the public C-ABI calls with HOST buffers: every batch uploads its own B+1 frames from pinned host memory
+    # (eaof_orb_extract_batch_async), extracts, matches, and downloads keypoints + descriptors (eaof_orb_extract_batch_wait)
+    # and the matches.  Handles rotate so that the upload of a batch overlaps the kernels of the previous ones — the way a
+    # caller streams a sequence; nothing is skipped or reused between batches.
+    if e2e_steps:
+        h_all = torch.from_numpy(frames_host).pin_memory()
+        n_slots = int(os.environ.get("EAOF_E2E_SLOTS", 3))
+        slots = []
+        for sl in range(n_slots):
+            r = rig if sl == 0 else Rig(eaof, torch, device, width, height, nfeat, B)
+            r.ex.set_pipeline_chunk(int(os.environ.get("EAOF_E2E_CHUNK", B + 1)))
+            slots.append(dict(rig=r, mstream=r.streams()[1],
+                              h_match=torch.empty((B, cap), dtype=torch.int32).pin_memory(),
+                              h_nm=torch.empty((B,), dtype=torch.int32).pin_memory(),
+                              h_kps=torch.empty((B + 1, cap, 6), dtype=torch.float32).pin_memory(),
+                              h_desc=torch.empty((B + 1, cap, 32), dtype=torch.uint8).pin_memory()))
+
+        def issue(k):
+            S = slots[k % n_slots]
+            r = S["rig"]
+            b = k % n_batches
+            r.ex.extract_batch_async(h_all.data_ptr() + b * B * frame_bytes, B + 1, S["h_kps"].data_ptr(), S["h_desc"].data_ptr())
+            r.mt.projection_batch_device(r.ex, r.pair_last, r.pair_cur, r.shift_x, r.shift_y, MATCH_TH, r.d_match.data_ptr(),
+                                         r.d_dist.data_ptr(), r.d_nm.data_ptr())
+            with torch.cuda.stream(S["mstream"]):
+                S["h_match"].copy_(r.d_match, non_blocking=True)
+                S["h_nm"].copy_(r.d_nm, non_blocking=True)
+
+        def finish(k):
+            S = slots[k % n_slots]
+            cnt = S["rig"].ex.extract_batch_wait()
+            S["rig"].mt.sync()
+            return cnt
+
+        nb = e2e_steps * n_batches
+        for k in range(n_slots):  # warm every slot
+            issue(k)
+        for k in range(n_slots):
+            finish(k)
+        barrier()
+        t1 = time.perf_counter()  # host clock: the region ends when the last batch's results are in host memory
+        for k in range(min(n_slots - 1, nb)):
+            issue(k)
+        for k in range(nb):
+            if k + n_slots - 1 < nb:
+                issue(k + n_slots - 1)
+            last_cnt = finish(k)
+        torch.cuda.synchronize()
+        out["e2e"] = {"dt": time.perf_counter() - t1, "steps": e2e_steps, "slots": n_slots,
+                      "h2d_bytes_per_step": n_batches * (B + 1) * frame_bytes,
+                      # everything the calls bring back: all cap slots of every frame (keypoint records 24 B + descriptors
+                      # 32 B), the per-frame counts, and the match rows + counts of every pair
+                      "d2h_bytes_per_step": n_batches * ((B + 1) * (cap * 56 + 4) + B * (cap * 4 + 4)),
+                      "launches": nb * launches_per_batch}
+        assert int(last_cnt.sum()) > 0 and int(slots[(nb - 1) % n_slots]["h_nm"].sum()) > 0
+        torch.cuda.synchronize()
+        for S in slots[1:]:
+            S["rig"].close()
+        slots.clear()
+        del h_all
+    out["rig"] = rig
+    out["d_seq"] = d_seq
+    del xs, ms, ev0, ev1
+    return out
+
+
+def stage_table(m, width, height, hbm_peak, B):
+    alg = algorithmic_bytes(width, height, m["level_sizes"], m["kp_per_frame"], m["cand_per_frame"])
+    stages = {}
+    for k in STAGES:
+        ms = m["stage_ms_per_batch"][k]
+        gbs = alg[k] * (B + 1) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stages[k] = {"ms_per_batch": ms, "alg_bytes_per_frame": alg[k], "achieved_gbs": gbs, "frac": gbs / hbm_peak}
+    return alg, stages
+
+
+def digests_of(eaof, torch, device, frames, first_is_halo, B=250):
+    """Per-frame and per-pair sha256 digests of the CUDA path over `frames` (consecutive frames of one sequence; when
+    first_is_halo, frame 0 belongs to the previous rank and only serves as the Last frame of the first pair).  Returns
+    (digests of the owned frames, digests of the pairs whose Cur frame is owned), both in frame order."""
+    n = len(frames)
+    rig = Rig(eaof, torch, device, frames.shape[2], frames.shape[1], NFEAT, B)
+    fd, pd = [], []
+    own0 = 1 if first_is_halo else 0
+    while own0 < n:
+        c0 = own0 - 1 if own0 > 0 else 0      # one frame in front of the chunk's first owned frame: recomputed, not owned
+        c1 = min(n, own0 + B)
+        m = c1 - c0
+        d = torch.from_numpy(np.ascontiguousarray(frames[c0:c1])).cuda(device)
+        rig.ex.extract_batch_device(d.data_ptr(), m)
+        npair = m - 1
+        if npair > 0:
+            rig.mt.projection_batch_device(rig.ex, np.arange(0, npair, dtype=np.int32), np.arange(1, m, dtype=np.int32),
+                                           rig.shift_x[:npair], rig.shift_y[:npair], MATCH_TH, rig.d_match.data_ptr(),
+                                           rig.d_dist.data_ptr(), rig.d_nm.data_ptr())
+        res = rig.ex.fetch(m)
+        rig.mt.sync()
+        hm, hd = rig.d_match[:max(npair, 1)].cpu().numpy(), rig.d_dist[:max(npair, 1)].cpu().numpy()
+        for j in range(own0 - c0, m):
+            fd.append(workload.frame_digest(*res[j]))
+        for p in range(npair):  # pair p = (c0+p, c0+p+1): its Cur frame is always an owned one
+            ncur = len(res[p + 1][0])
+            pd.append(workload.pair_digest(hm[p, :ncur], hd[p, :ncur]))
+        own0 = c1
+        del d
+    rig.close()
+    return fd, pd
+
+
+def determinism_and_parity(eaof, torch, dist, rank, world, device, seq, cores, check_cpu=True):
+    """The configs[1] sequence (1000 frames, 999 pairs): (1) sharded over the ranks in contiguous blocks with one halo
+    frame (eaof/shard.py), digests gathered in frame order; (2) rank 0 alone over the whole sequence; (3) the CPU
+    reference (unmodified ORBextractor.cc, canonical quadtree tie-break, + matcher oracle) on rank 0's host cores."""
+    b, e = shard.frame_block(SEQ_LEN, rank, world)
+    hb, he = shard.halo_block(b, e)
+    fd, pd = digests_of(eaof, torch, device, seq.frames(hb, he), first_is_halo=hb < b)
+    assert len(fd) == e - b and len(pd) == len(shard.consecutive_pairs(b, e, SEQ_LEN))
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (fd, pd))
+    else:
+        gathered = [(fd, pd)]
+    if rank != 0:
+        return None
+    all_f = [d for g in gathered for d in g[0]]
+    all_p = [d for g in gathered for d in g[1]]
+    sharded = workload.combine(all_f + all_p)
+    out = {"workload": "configs[1] sequence, 1000 frames + 999 consecutive pairs, sha256 over keypoint records, descriptors, "
+                       "match indices and distances", "world": world, "hash": sharded}
+    if world > 1:
+        f1, p1 = digests_of(eaof, torch, device, seq.frames(0, SEQ_LEN), first_is_halo=False)
+        single = workload.combine(f1 + p1)
+        out["hash_single_gpu"] = single
+        out["equal_to_single_gpu"] = single == sharded
+    else:
+        f1, p1 = all_f, all_p
+    if check_cpu:
+        try:
+            t_ex, t_m, feats, matches = cpu_reference_pass(seq.frames(0, SEQ_LEN), cores, canonical=True)
+            cf = [workload.frame_digest(k, d) for k, d in feats]
+            cp = [workload.pair_digest(m, d) for m, d in matches]
+            bad_f = sum(a != b_ for a, b_ in zip(f1, cf)) + abs(len(f1) - len(cf))
+            bad_p = sum(a != b_ for a, b_ in zip(p1, cp)) + abs(len(p1) - len(cp))
+            out["parity_vs_cpu_reference"] = {"frames_checked": len(cf), "frames_differing": bad_f, "pairs_checked": len(cp),
+                                              "pairs_differing": bad_p, "identical": bad_f == 0 and bad_p == 0,
+                                              "hash_cpu": workload.combine(cf + cp),
+                                              "cpu_seconds": t_ex + t_m,
+                                              "checker": "unmodified reference ORBextractor.cc (oracle/_ref, quadtree ties in creation "
+                                                         "order) + oracle port of SearchByProjection"}
+        except Exception as ex_:  # reported, never required for the GPU number
+            out["parity_vs_cpu_reference"] = {"failed": repr(ex_)}
+    return out
+
+
+def make_blocks(torch, device, first, count, n_feat):
+    """Synthetic descriptor blocks first..first+count-1 of the configs[4] sweep, generated on the device, one generator per
+    block id (so a block is the same whichever rank builds it): 70 % of the rows are noisy copies of a common base row set
+    (8 % of the bits flipped), the rest random; angles = base angle + N(0, 5 degrees)."""
+    dev = torch.device("cuda", device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(77)
+    base = torch.randint(0, 256, (n_feat, 32), dtype=torch.uint8, device=dev, generator=g)
+    a0 = torch.rand(n_feat, device=dev, generator=g) * 360.0
+    desc = torch.empty((count, n_feat, 32), dtype=torch.uint8, device=dev)
+    ang = torch.empty((count, n_feat), dtype=torch.float32, device=dev)
+    bit = (2 ** torch.arange(8, device=dev, dtype=torch.int32)).view(1, 1, 8)
+    for i in range(count):
+        g.manual_seed(1000003 * (first + i) + 11)
+        d = torch.randint(0, 256, (n_feat, 32), dtype=torch.uint8, device=dev, generator=g)
+        keep = torch.rand(n_feat, device=dev, generator=g) < 0.7
+        flips = (torch.rand((n_feat, 32, 8), device=dev, generator=g) < 0.08).to(torch.int32)
+        fb = (flips * bit).sum(dim=2).to(torch.uint8)
+        desc[i] = torch.where(keep.view(-1, 1), base ^ fb, d)
+        ang[i] = torch.remainder(a0 + torch.randn(n_feat, device=dev, generator=g) * 5.0, 360.0)
+    return desc.contiguous(), ang.contiguous()
+
+
+def hamming_sweep(eaof, torch, dist, rank, world, device, n_blocks=448, n_feat=2000, n_pairs=100000):
+    """BASELINE.json configs[4]: brute-force SearchByBoW semantics (one node holding every feature, TH_LOW=50, ratio 0.9,
+    rotation histogram) over 100k pairs of 2000-descriptor blocks.  The blocks are sharded over the ranks (block f lives
+    on rank f // (n_blocks / world)), all-gathered once by ncclAllGather inside libeaof_orb.so, the pair list is
+    partitioned round-robin.  Timed on the matcher's stream: all-gather + this rank's pairs, max over ranks."""
+    import ctypes as C
+    from eaof import sweep as sweep_mod
+    assert n_blocks % world == 0
+    per = n_blocks // world
+    desc, ang = make_blocks(torch, device, rank * per, per, n_feat)
+    cnt = torch.full((per,), n_feat, dtype=torch.int32, device="cuda")
+    ids = [sweep_mod.Sweep.unique_id() if (rank == 0 and world > 1) else None]
+    if world > 1:
+        dist.broadcast_object_list(ids, src=0)
+    sw = sweep_mod.Sweep(rank, world, device, ids[0])
+    i = np.arange(n_pairs, dtype=np.int64)
+    gq = (i % n_blocks).astype(np.int32)
+    gt = ((i * 7 + 1 + i // n_blocks) % n_blocks).astype(np.int32)
+    mine = np.arange(rank, n_pairs, world)
+    pq, pt = gq[mine], gt[mine]
+    mt = eaof.ORBmatcher(0.9, True, max_features=n_feat, max_pairs=1024, device=device)
+    g_desc = torch.empty((n_blocks, n_feat, 32), dtype=torch.uint8, device="cuda")
+    g_ang = torch.empty((n_blocks, n_feat), dtype=torch.float32, device="cuda")
+    g_cnt = torch.empty((n_blocks,), dtype=torch.int32, device="cuda")
+    npm = len(mine)
+    d_match = torch.empty((npm, n_feat), dtype=torch.int32, device="cuda")
+    d_dist = torch.empty((npm, n_feat), dtype=torch.int32, device="cuda")
+    d_nm = torch.zeros(npm, dtype=torch.int32, device="cuda")
+    st = torch.cuda.ExternalStream(mt.stream_ptr(), device=torch.device("cuda", device))
+    torch.cuda.synchronize()
+
+    def run(n):
+        sw.match(mt, eaof.BOW_KF_FRAME, per, n_feat, desc.data_ptr(), ang.data_ptr(), cnt.data_ptr(), g_desc.data_ptr(),
+                 g_ang.data_ptr(), g_cnt.data_ptr(), pq[:n], pt[:n], d_match.data_ptr(), d_dist.data_ptr(), d_nm.data_ptr())
+    run(min(npm, 2048)); mt.sync()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
-    for _ in range(reps):
-        run()
+    run(npm)
     e1.record(st)
     mt.sync()
-    secs = e0.elapsed_time(e1) * 1e-3 / reps
+    secs = e0.elapsed_time(e1) * 1e-3
+    ag_ms, ag_bytes = sw.last_allgather()
+    t = torch.tensor([secs, ag_ms], dtype=torch.float64, device="cuda")
+    # matches found over the whole pair list + a position-weighted checksum (equal for every world size)
+    chk = torch.stack([d_nm.sum().to(torch.int64), (d_nm.to(torch.int64) * torch.from_numpy(mine % 9973 + 1).cuda()).sum()])
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+    secs_max, ag_max = float(t[0]), float(t[1])
+    # this GPU alone on the same number of pairs without the exchange (pairs folded onto its own blocks): the per-pair
+    # rate one GPU reaches in this run, the denominator of efficiency_vs_n1
+    lq, lt = (pq % per).astype(np.int32), (pt % per).astype(np.int32)
+    sw1 = sweep_mod.Sweep(0, 1, device)
+
+    def run_local(n):
+        sw1.match(mt, eaof.BOW_KF_FRAME, per, n_feat, desc.data_ptr(), ang.data_ptr(), cnt.data_ptr(), desc.data_ptr(),
+                  ang.data_ptr(), cnt.data_ptr(), lq[:n], lt[:n], d_match.data_ptr(), d_dist.data_ptr(), d_nm.data_ptr())
+    run_local(min(npm, 2048)); mt.sync()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(st)
+    run_local(npm)
+    e3.record(st)
+    mt.sync()
+    secs_local = e2.elapsed_time(e3) * 1e-3
     L = eaof.lib()
     L.eaof_debug_popc_rate.restype = C.c_double
     L.eaof_debug_popc_rate.argtypes = [C.c_int]
     popc = float(L.eaof_debug_popc_rate(device))
     dists = float(n_pairs) * n_feat * n_feat
-    out = {"workload": f"configs[4]: {n_pairs} pairs of {n_feat}x{n_feat} descriptors, TH_LOW=50, ratio 0.9, rot-hist, device-resident",
-           "distances_per_s": dists / secs, "pairs_per_s": n_pairs / secs, "ms_per_sweep": secs * 1e3,
-           "matches_per_pair": float(d_nm.float().mean().item()),
+    out = {"workload": f"configs[4]: {n_pairs} frame pairs of {n_feat}x{n_feat} descriptors over {n_blocks} blocks ({per} per rank), "
+                       f"TH_LOW=50, ratio 0.9, rot-hist; ncclAllGather of the blocks + round-robin pair partition",
+           "world": world, "pairs": n_pairs, "pairs_per_s": n_pairs / secs_max, "distances_per_s": dists / secs_max,
+           "matches_per_s": float(chk[0]) / secs_max, "ms_total": secs_max * 1e3,
+           "allgather_ms": ag_max, "allgather_bytes": int(ag_bytes), "allgather_frac_of_sweep": ag_max * 1e-3 / secs_max,
+           "nccl_version": sweep_mod.Sweep.nccl_version() if world > 1 else None,
+           "single_gpu_pairs_per_s": npm / secs_local, "efficiency_vs_n1": (n_pairs / secs_max) / (world * npm / secs_local),
+           "matches_total": int(chk[0]), "matches_per_pair": float(chk[0]) / n_pairs, "checksum": int(chk[1]),
            "popc_peak_per_s": popc,
            # 8 XOR words per distance; three carry-save adders fold them so that 5 POPC are executed per distance
-           "popc_executed_per_distance": 5, "xu_pipe_frac": (5.0 * dists / secs) / popc if popc > 0 else None,
-           "frac_of_naive_popc_roofline": (8.0 * dists / secs) / popc if popc > 0 else None}
-    del st, e0, e1
-    mt.close()
+           "popc_executed_per_distance": 5,
+           "xu_pipe_frac": (5.0 * dists / secs_max) / (popc * world) if popc > 0 else None,
+           "frac_of_naive_popc_roofline": (8.0 * dists / secs_max) / (popc * world) if popc > 0 else None}
+    del st, e0, e1, e2, e3
+    sw.close(); sw1.close(); mt.close()
     return out
 
 
 def next_rows(eaof, torch, device, ex, d_frames, B, W, H):
-    """SURVEY.md §8(f) rows built so far, each timed on its own (device-resident where the entry point is; CUDA events on
-    the library's streams): bag-of-words conversion of a batch, colour ingest, ComputeStereoFromRGBD, the map-side window
-    search and ComputeDistinctiveDescriptors.  Reported beside the headline, not part of it."""
+    """SURVEY.md §8(f) rows, each timed on its own (device-resident where the entry point is; CUDA events on the library's
+    streams): bag-of-words conversion of a batch, colour ingest, ComputeStereoFromRGBD, the map-side window search and
+    ComputeDistinctiveDescriptors; and the reference's real operating point — one frame per call.  Reported beside the
+    headline, not part of it."""
     import time as _t
     from eaof import synth
     out = {}
@@ -135,20 +693,22 @@ def next_rows(eaof, torch, device, ex, d_frames, B, W, H):
         return e0.elapsed_time(e1) / reps
 
     # how the reference actually runs: one frame per call through the host-buffer entry point the drop-in operator() uses
-    # (upload + 13 kernels + download, synchronous), beside one SearchByProjection(Cur,Last) call on host buffers
-    ex1 = eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=1, device=device)
-    f_host = d_frames[:8].cpu().numpy()
+    # (upload + kernels + download, synchronous), then one SearchByProjection(Cur,Last) against the previous frame
+    ex1 = eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=2, device=device)
+    f_host = d_frames[:64].cpu().numpy()
     for i in range(8):
         ex1(f_host[i])
     lat = []
-    for i in range(64):
+    for i in range(200):
         t0 = _t.perf_counter()
-        k1, d1 = ex1(f_host[i % 8])
+        k1, d1 = ex1(f_host[i % 64])
         lat.append(_t.perf_counter() - t0)
     lat.sort()
-    out["single_frame_latency"] = {"workload": f"ORBextractor::operator() on one {W}x{H} frame, host buffers in and out (pageable numpy arrays)",
-                                   "median_us": lat[len(lat) // 2] * 1e6, "p95_us": lat[int(len(lat) * 0.95)] * 1e6,
-                                   "keypoints": int(len(k1))}
+    out["single_frame_latency"] = {"workload": f"configs[0]: ORBextractor::operator() on one {W}x{H} frame, host buffers in and out "
+                                               f"(pageable numpy arrays), synchronous",
+                                   "calls": len(lat), "median_us": lat[len(lat) // 2] * 1e6, "p5_us": lat[int(len(lat) * 0.05)] * 1e6,
+                                   "p95_us": lat[int(len(lat) * 0.95)] * 1e6, "keypoints": int(len(k1)),
+                                   "launches_per_call": ex1.last_launch_count()}
     ex1.close()
 
     # f-2: ORBVocabulary::transform over the descriptors of a batch, vocabulary of the ORBvoc shape (k=10, L=6)
@@ -260,134 +820,31 @@ def next_rows(eaof, torch, device, ex, d_frames, B, W, H):
     return out
 
 
-def algorithmic_bytes(level_sizes, kp_per_frame, cand_per_frame):
-    """Per-frame algorithmic bytes per stage, SURVEY.md §8(d)."""
-    P = sum(w * h for w, h in level_sizes)
-    Pb = sum((w + 38) * (h + 38) for w, h in level_sizes)
-    w7, h7 = level_sizes[-1]
-    return {
-        "pyramid": W * H + (P - w7 * h7) + Pb,
-        "fast": P,
-        "octree": 12 * cand_per_frame + 20 * kp_per_frame,
-        "blur": 2 * P,
-        "angle_desc": kp_per_frame * (749 + 1369 + 52),
-    }
-
-
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-
-    def __init__(self, gpu_index: int):
-        super().__init__(daemon=True)
-        self.gpu = gpu_index
-        self.rows = []
-        self.stop_flag = False
-        self.proc = None
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-                if self.stop_flag:
-                    break
-        except Exception:
-            pass
-
-    def finish(self):
-        self.stop_flag = True
-        if self.proc:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
-
-
-def make_sequence(n):
-    from eaof import synth
-    tex = synth.base_texture(W, H, seed=1234 + 1)
-    return synth.make_frames(n, W, H, tex=tex)
-
-
-def cpu_matcher_seconds_per_pair(frames, n_pairs=6):
-    """Oracle port of SearchByProjection(Cur,Last) (src/ORBmatcher.cc:1328-1472) on one host thread."""
-    from oracle import pyoracle as po
-    ref = po.RefExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, canonical=False)
-    feats = [ref.extract(frames[i]) for i in range(n_pairs + 1)]
-    sf = ref.tables()["scale"]
-    bounds = (0.0, float(W), 0.0, float(H))
-    ginv = (np.float32(64) / np.float32(W), np.float32(48) / np.float32(H))
-    t0 = time.perf_counter()
-    for i in range(1, n_pairs + 1):
-        (ck, cd), (lk, ld) = feats[i], feats[i - 1]
-        cur = dict(x=ck["x"], y=ck["y"], octave=ck["octave"], angle=ck["angle"], desc=cd)
-        last = dict(u=lk["x"] - np.float32(2), v=lk["y"] - np.float32(1), octave=lk["octave"], angle=lk["angle"], desc=ld)
-        po.o_search_by_projection(cur, last, MATCH_TH, True, bounds=bounds, grid_inv=ginv, scale_factors=sf)
-    return (time.perf_counter() - t0) / n_pairs
-
-
-def cpu_baseline_run(frames, cores, seconds_target=8.0):
-    """Reference ORBextractor.cc (oracle/_ref) on host cores, frame-parallel with one extractor instance per thread,
-    plus the oracle port of the projection matcher (timed on one thread, credited with perfect scaling over cores)."""
-    from oracle import pyoracle as po
-    n = min(len(frames), max(cores * 2, 8))
-    sample = frames[:n]
-    secs, _ = po.ref_bench(sample, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, repeat=1)
-    rep = max(1, int(seconds_target / max(secs, 1e-3)))
-    secs, _ = po.ref_bench(sample, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, repeat=rep)
-    t_extract = secs / (n * rep)                       # wall seconds per frame with all cores busy
-    t_match = cpu_matcher_seconds_per_pair(frames) / cores
-    return 1.0 / (t_extract + t_match), (f"extraction: {n} frames x {rep} passes, frame-parallel on {cores} threads, unmodified "
-                                         f"reference ORBextractor.cc + cv shim ({1.0 / t_extract:.0f} frames/s); matching: oracle "
-                                         f"port on 1 thread over 6 pairs ({t_match * cores * 1e3:.2f} ms/pair), credited with "
-                                         f"perfect {cores}-core scaling")
-
-
-def run_reference_arm(args, rank):
-    if rank != 0:
-        return
-    cores = os.cpu_count() or 1
-    frames = make_sequence(max(cores * 2, 8))
-    n = len(frames)
-    from oracle import pyoracle as po
-    kind = "reference" if os.path.exists(po.REF_SO) else "port"
-    times = []
-    t_match = cpu_matcher_seconds_per_pair(frames) / cores
-    for i in range(args.warmup + args.steps):
-        secs, _ = po.ref_bench(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads=cores, canonical=False, repeat=1)
-        if i >= args.warmup:
-            times.append(secs + t_match * n)
-    tot = sum(times)
-    val = n * len(times) / tot
-    line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"synthetic 640x480 sequence, nfeatures=1000, 8 levels, 1.2, 20/7; step = {n} frames on the host CPU"},
-        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{n} frames per step, frame-parallel on {cores} threads, unmodified reference ORBextractor.cc + cv shim; "
-                                   f"projection matching by the oracle port ({t_match * cores * 1e3:.2f} ms/pair on 1 thread, credited /{cores})"},
-        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
+def other_config(eaof, torch, dist, rank, world, device, name, B, n_seq, hbm_peak):
+    """configs[2] / configs[3]: device-resident frames/s, e2e, per-stage ms and roofline fractions on a cycled set of
+    n_seq synthetic frames per rank (a cycled set stands for the 10k-frame run)."""
+    cfg = CONFIGS[name]
+    seq = workload.Sequence(cfg["width"], cfg["height"], seed=1234 + int(name[8]) + 1 + 17 * rank)
+    fr = seq.frames(0, n_seq)
+    frames_host = np.concatenate([fr[:1], fr])
+    m = measure_config(eaof, torch, dist, rank, world, device, name, B, steps=3, warmup=3, frames_host=frames_host, e2e_steps=2)
+    t = torch.tensor([m["dt"], m["e2e"]["dt"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt, dte = float(t[0]), float(t[1])
+    alg, stages = stage_table(m, cfg["width"], cfg["height"], hbm_peak, B)
+    value = world * n_seq * 3 / dt
+    out = {"workload": f"{name}: {cfg['what']}; {n_seq}-frame set per GPU, batches of {B} + halo, consecutive-frame matching on",
+           "frames_per_s": value, "ms_per_frame_per_gpu": dt / (3 * n_seq) * 1e3,
+           "e2e_frames_per_s": world * n_seq * m["e2e"]["steps"] / dte,
+           "keypoints_per_frame": m["kp_per_frame"], "fast_candidates_per_frame": m["cand_per_frame"],
+           "matches_per_pair": m["matches_per_pair"], "alg_bytes_per_frame": sum(alg.values()),
+           "whole_path_gbs_per_gpu": sum(alg.values()) * value / world / 1e9,
+           "whole_path_frac_of_hbm": sum(alg.values()) * value / world / 1e9 / hbm_peak,
+           "stages": stages, "match_projection_ms_per_batch": m["stage_ms_per_batch"]["match_projection"]}
+    m["rig"].close()
+    del m
+    return out
 
 
 def main():
@@ -399,6 +856,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-determinism", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -420,224 +881,124 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.batch
-    n_batches = SEQ_LEN // B
-    # every rank owns its own shard of the sequence (frame f -> rank f mod world would give the same work per rank;
-    # weak scaling: each rank processes B frames per step)
-    frames = make_sequence(SEQ_LEN)
-    d_frames = torch.from_numpy(frames).cuda(local_rank)  # inputs resident in HBM before the timed region
-    ex = eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=B, device=local_rank)
-    level_sizes = [ex.level_size(l) for l in range(NLEVELS)]
-    frame_bytes = W * H
-    cap = ex.cap
-    mt = eaof.ORBmatcher(0.9, True, max_features=cap, max_pairs=B, device=local_rank)
-    n_pairs = B - 1
-    pair_last, pair_cur = np.arange(0, B - 1, dtype=np.int32), np.arange(1, B, dtype=np.int32)
-    shift_x, shift_y = np.full(n_pairs, SHIFT[0], np.float32), np.full(n_pairs, SHIFT[1], np.float32)
-    d_match = torch.empty((n_pairs, cap), dtype=torch.int32, device="cuda")
-    d_dist = torch.empty((n_pairs, cap), dtype=torch.int32, device="cuda")
-    d_nm = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    if SEQ_LEN % B:
+        raise SystemExit(f"--batch must divide {SEQ_LEN}")
+    cores = os.cpu_count() or 1
+    hbm_peak, peak_src = peaks()
+    seq = workload.Sequence(W, H)
+    frames_host = rank_sequence(seq, rank)   # this rank's shard of the world x 1000-frame sequence (+ halo slot)
 
-    def dev_step(i):
-        b = i % n_batches
-        ex.extract_batch_device(d_frames.data_ptr() + b * B * frame_bytes, B)
-        # consecutive-frame SearchByProjection over the keypoints that just landed in HBM (waits on the extractor stream)
-        mt.projection_batch_device(ex, pair_last, pair_cur, shift_x, shift_y, MATCH_TH, d_match.data_ptr(),
-                                   d_dist.data_ptr(), d_nm.data_ptr())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        dev_step(i)
-    ex.sync()
-    mt.sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    # device timing: CUDA events recorded on the stream the kernels are launched on (the handle's own stream)
-    xs = torch.cuda.ExternalStream(ex.stream_ptr(), device=torch.device("cuda", local_rank))
-    ms = torch.cuda.ExternalStream(mt.stream_ptr(), device=torch.device("cuda", local_rank))
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(xs)
-    for i in range(args.steps):
-        dev_step(i)
-    ev1.record(ms)  # the matcher stream finishes last (it waits on the extractor stream every step)
-    ex.sync()
-    mt.sync()
-    torch.cuda.synchronize()
-    dt_wall = ev0.elapsed_time(ev1) * 1e-3
-    matches_per_pair = float(d_nm.float().mean().item())
-    launches_per_step = ex.last_launch_count()
-    counts = ex.fetch_counts(B)
-    kp_per_frame = float(counts.mean())
-    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    m = measure_config(eaof, torch, dist, rank, world, local_rank, "configs[1]", B, args.steps, args.warmup, frames_host,
+                       sustained_s=args.sustained_seconds, e2e_steps=e2e_steps)
+    clocks = sampler.summary(*m["t_host"])
+    if clocks["samples"] == 0:  # a timed region shorter than one nvidia-smi period: take the sustained leg's samples
+        clocks = sampler.summary(*(m["sustained"]["t_host"] if "sustained" in m else (None, None)))
+    sus_clocks = sampler.summary(*m["sustained"]["t_host"]) if "sustained" in m else None
+    rig, d_seq = m["rig"], m["d_seq"]
 
-    # per-stage device times (CUDA events on the library's stream)
-    ex.set_profiling(True)
-    stage_acc = {}
-    nprof = min(args.steps, 8)
-    me0, me1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for i in range(nprof):
-        b = i % n_batches
-        ex.extract_batch_device(d_frames.data_ptr() + b * B * frame_bytes, B)
-        ex.sync()
-        for k, v in ex.stage_times().items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v / nprof
-        me0.record(ms)
-        mt.projection_batch_device(ex, pair_last, pair_cur, shift_x, shift_y, MATCH_TH, d_match.data_ptr(),
-                                   d_dist.data_ptr(), d_nm.data_ptr())
-        me1.record(ms)
-        mt.sync()
-        stage_acc["match_projection"] = stage_acc.get("match_projection", 0.0) + me0.elapsed_time(me1) / nprof
-    ex.set_profiling(False)
-    step_ms_dev = stage_acc["total"] + stage_acc["match_projection"]
+    sweep = None
+    if not args.no_sweep:
+        sweep = hamming_sweep(eaof, torch, dist, rank, world, local_rank)
+    sampler.finish()
 
-    # e2e through the public C-ABI calls with HOST buffers: every step uploads its own 250 frames from pinned host memory
-    # (eaof_orb_extract_batch_async), extracts, matches, and downloads keypoints + descriptors + matches
-    # (eaof_orb_extract_batch_wait).  Three handles rotate so that the upload of a step overlaps the kernels of the
-    # previous ones — the way a caller streams a sequence; nothing is skipped or reused between steps.
-    h_all = torch.from_numpy(frames).pin_memory()
-    slots = []
-    n_slots = int(os.environ.get("EAOF_E2E_SLOTS", 3))
-    for sl in range(n_slots):
-        exs = ex if sl == 0 else eaof.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, width=W, height=H, max_batch=B,
-                                                   device=local_rank)
-        mts = mt if sl == 0 else eaof.ORBmatcher(0.9, True, max_features=cap, max_pairs=B, device=local_rank)
-        # with two handles in flight the upload of a whole batch already hides under the other handle's kernels:
-        # no chunking inside a call (EAOF_E2E_CHUNK overrides, 0 = the library's default chunk)
-        exs.set_pipeline_chunk(int(os.environ.get("EAOF_E2E_CHUNK", B)))
-        slots.append(dict(
-            ex=exs, mt=mts, mstream=torch.cuda.ExternalStream(mts.stream_ptr(), device=torch.device("cuda", local_rank)),
-            d_match=torch.empty((n_pairs, cap), dtype=torch.int32, device="cuda"),
-            d_dist=torch.empty((n_pairs, cap), dtype=torch.int32, device="cuda"),
-            d_nm=torch.zeros(n_pairs, dtype=torch.int32, device="cuda"),
-            h_match=torch.empty((n_pairs, cap), dtype=torch.int32).pin_memory(),
-            h_nm=torch.empty((n_pairs,), dtype=torch.int32).pin_memory(),
-            h_kps=torch.empty((B, cap, 6), dtype=torch.float32).pin_memory(),
-            h_desc=torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()))
-
-    def e2e_issue(k):
-        S = slots[k % n_slots]
-        b = k % n_batches
-        S["ex"].extract_batch_async(h_all.data_ptr() + b * B * frame_bytes, B, S["h_kps"].data_ptr(), S["h_desc"].data_ptr())
-        S["mt"].projection_batch_device(S["ex"], pair_last, pair_cur, shift_x, shift_y, MATCH_TH, S["d_match"].data_ptr(),
-                                        S["d_dist"].data_ptr(), S["d_nm"].data_ptr())
-        with torch.cuda.stream(S["mstream"]):
-            S["h_match"].copy_(S["d_match"], non_blocking=True)
-            S["h_nm"].copy_(S["d_nm"], non_blocking=True)
-
-    def e2e_finish(k):
-        S = slots[k % n_slots]
-        cnt = S["ex"].extract_batch_wait()
-        S["mt"].sync()
-        return cnt
-
-    e2e_steps = max(3, min(args.steps, 20))
-    for k in range(n_slots):  # warm every slot
-        e2e_issue(k)
-    for k in range(n_slots):
-        e2e_finish(k)
-    barrier()
-    t1 = time.perf_counter()  # host clock: the region ends when the last step's results are in host memory
-    for k in range(min(n_slots - 1, e2e_steps)):
-        e2e_issue(k)
-    for k in range(e2e_steps):
-        if k + n_slots - 1 < e2e_steps:
-            e2e_issue(k + n_slots - 1)
-        last_cnt = e2e_finish(k)
-    torch.cuda.synchronize()
-    dt_e2e = time.perf_counter() - t1
-    assert int(last_cnt.sum()) > 0 and int(slots[(e2e_steps - 1) % n_slots]["h_nm"].sum()) > 0
-    e2e_launches = e2e_steps * (slots[0]["ex"].last_launch_count() + 4)
-
-    hamming = None
-    if rank == 0 or world > 1:
-        hamming = hamming_sweep(eaof, torch, local_rank)
-    clocks = sampler.finish()
+    determinism = None
+    if not args.no_determinism:
+        determinism = determinism_and_parity(eaof, torch, dist, rank, world, local_rank, seq, cores,
+                                             check_cpu=not args.no_cpu_baseline)
+    others = None
+    if not args.no_other_configs:
+        others = {}
+        for name, ob, on in (("configs[2]", 125, 250), ("configs[3]", 32, 64)):
+            try:
+                others[name] = other_config(eaof, torch, dist, rank, world, local_rank, name, ob, on, hbm_peak)
+            except Exception as e:  # reported beside the headline, never required for it
+                others[name] = {"failed": repr(e)}
     extras = None
-    if rank == 0 and not args.no_next_rows:  # after the clock sampler: these rows have host-side phases
+    if rank == 0 and not args.no_next_rows:
         try:
-            extras = next_rows(eaof, torch, local_rank, ex, d_frames, B, W, H)
-        except Exception as e:  # reported beside the headline, never required for it
+            extras = next_rows(eaof, torch, local_rank, rig.ex, d_seq[1:], B, W, H)
+        except Exception as e:
             extras = {"failed": repr(e)}
 
     # max over ranks
-    t = torch.tensor([dt_wall, dt_e2e, step_ms_dev], dtype=torch.float64, device="cuda")
+    t = torch.tensor([m["dt"], m["e2e"]["dt"], m["sustained"]["dt"] if "sustained" in m else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt_wall, dt_e2e, step_ms_dev = (float(v) for v in t.cpu())
+    dt, dt_e2e, dt_sus = (float(v) for v in t.cpu())
 
     if rank == 0:
-        hbm_peak, peak_src = peaks()
-        value = world * B * args.steps / dt_wall
-        e2e_val = world * B * e2e_steps / dt_e2e
-        cand_per_frame = 6000.0
-        alg = algorithmic_bytes(level_sizes, kp_per_frame, cand_per_frame)
-        stages = {}
-        for k in ("pyramid", "fast", "octree", "blur", "angle_desc"):
-            ms = stage_acc[k]
-            gbs = alg[k] * B / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-            stages[k] = {"ms_per_step": ms, "alg_bytes_per_frame": alg[k], "achieved_gbs": gbs, "frac": gbs / hbm_peak}
-        dom = max(("pyramid", "fast", "octree", "blur", "angle_desc"), key=lambda k: stage_acc[k])
+        frames_step = m["frames_per_step"]
+        value = world * frames_step * args.steps / dt
+        e2e_val = world * frames_step * m["e2e"]["steps"] / dt_e2e
+        alg, stages = stage_table(m, W, H, hbm_peak, B)
+        dom = max(STAGES, key=lambda k: m["stage_ms_per_batch"][k])
+        cap_ = ncu_capture(dom)
+        traffic = cap_.get("dram_bytes_per_launch")
+        if traffic is not None:
+            traffic = traffic * (B + 1) / cap_["frames_per_launch"]
+        per_gpu = value / world
         roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": stages[dom]["frac"], "traffic": ncu_traffic(dom, B), "peak_source": peak_src,
-                    "alu_pipe_note": "k_fast is bound by instruction issue, not by HBM (ncu, profiles/r01_fast_full4_summary.txt: issue "
-                                     "slots 79 %, INT ALU pipe 68 %, LSU 41 %, dram 5 %; DRAM traffic x1.11 of the algorithmic bytes)",
-                    "whole_path": {"alg_bytes_per_frame": sum(alg.values()),
-                                   "achieved": sum(alg.values()) * value / 1e9, "frac": sum(alg.values()) * value / 1e9 / hbm_peak}}
-        cores = os.cpu_count() or 1
-        cpu = None
+                    "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    # the dominant kernel is not HBM-bound: it is limited by instruction issue (integer ALU pipe); the share of
+                    # issue slots it uses comes from the committed ncu capture named here
+                    "limiter": cap_.get("limiter"), "issue_frac": cap_.get("issue_active_frac"),
+                    "alu_pipe_frac": cap_.get("alu_pipe_frac"), "ncu_capture": cap_.get("source"),
+                    "whole_path": {"alg_bytes_per_frame": sum(alg.values()), "achieved_per_gpu": sum(alg.values()) * per_gpu / 1e9,
+                                   "frac": sum(alg.values()) * per_gpu / 1e9 / hbm_peak}}
+        cpu = alpha = cv2est = None
         if not args.no_cpu_baseline:
             try:
-                v, sample = cpu_baseline_run(frames, cores)
-                from oracle import pyoracle as po
-                cpu = {"value": v, "unit": "frames/s", "cores": cores,
-                       "kind": "reference" if os.path.exists(po.REF_SO) else "port", "sample": sample}
+                cpu, alpha, cv2est = cpu_baselines(seq, cores)
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+        pairs_step = frames_step * world - 1  # rank 0's first batch carries a dummy halo pair
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt_wall / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1000-frame synthetic 640x480 sequence, nfeatures=1000, nlevels=8, "
-                                   "scaleFactor=1.2, iniThFAST=20, minThFAST=7; batched extraction + consecutive-frame "
-                                   "SearchByProjection-style matching",
-                       "frames_per_step_per_gpu": B, "keypoints_per_frame": kp_per_frame,
-                       "l2_policy": "each step reads a different 77 MB batch and rewrites ~0.7 GB of pyramid/blur "
-                                    "workspace: working set per step exceeds the 126 MB L2",
-                       "parallelism": f"frame-sharded x{world}, no collective"},
-            "device_ms_per_step_events": step_ms_dev,
-            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
-                    "d2h_bytes_per_step": B * (cap * 56 + 4) + n_pairs * (cap * 4 + 4)},
-            "gpu_launches": (launches_per_step + 4) * args.steps,
-            "e2e_detail": {"steps": e2e_steps, "pipeline": f"{n_slots} handles in rotation: uploads of the next steps under the kernels of step k",
-                           "gpu_launches": e2e_launches, "api": "eaof_orb_extract_batch_async/_wait + "
-                           "eaof_match_projection_batch_device, pinned host buffers"},
-            "hamming": hamming,
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": frames_step, "batches_per_step": m["n_batches"],
+                       "frames_per_batch": B, "halo_frames_per_batch": 1, "keypoints_per_frame": m["kp_per_frame"],
+                       "fast_candidates_per_frame": m["cand_per_frame"],
+                       "l2_policy": "each batch reads a different 77 MB block of frames and rewrites ~0.7 GB of pyramid/blur "
+                                    "workspace: working set per batch exceeds the 126 MB L2",
+                       "parallelism": f"frame-sharded x{world} (rank r owns frames [1000r, 1000(r+1)) + 1 halo), no collective"},
+            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": m["e2e"]["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": m["e2e"]["d2h_bytes_per_step"]},
+            "gpu_launches": m["launches_per_step"] * args.steps,
+            "e2e_detail": {"steps": m["e2e"]["steps"], "pipeline": f"{m['e2e']['slots']} handles in rotation: uploads of the next batches "
+                           "under the kernels of batch k", "gpu_launches": m["e2e"]["launches"],
+                           "d2h_note": "every cap slot of every frame is downloaded (the call's output layout), not only the filled ones",
+                           "api": "eaof_orb_extract_batch_async/_wait + eaof_match_projection_batch_device, pinned host buffers"},
+            "sustained": None if "sustained" not in m else {
+                "seconds": dt_sus, "steps": m["sustained"]["steps"], "frames_per_s": world * frames_step * m["sustained"]["steps"] / dt_sus,
+                "ratio_to_value": (world * frames_step * m["sustained"]["steps"] / dt_sus) / value, "clocks": sus_clocks},
+            "hamming_matches_per_s": None if not sweep else sweep["distances_per_s"],
+            "hamming_pairs_per_s": None if not sweep else sweep["pairs_per_s"],
+            "sweep": sweep, "hamming": sweep,
             "matching": {"kind": "consecutive-frame SearchByProjection(Cur,Last), th=15, octave+-1, rot-hist on",
-                         "pairs_per_step_per_gpu": n_pairs, "matches_per_pair": matches_per_pair,
-                         "ms_per_step": stage_acc["match_projection"]},
-            "next_rows": extras,
-            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+                         "pairs_per_step": pairs_step, "matches_per_pair": m["matches_per_pair"],
+                         "ms_per_batch": m["stage_ms_per_batch"]["match_projection"],
+                         "pairs_per_s_alone": B / (m["stage_ms_per_batch"]["match_projection"] * 1e-3)},
+            "determinism": determinism, "other_configs": others, "next_rows": extras,
+            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "cpu_baseline_alpha": alpha,
+            "cpu_baseline_cv2": cv2est, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    # release everything torch holds on the library's streams before the handles (and their streams) go away
-    # release everything torch holds on the library's streams (pinned tensors record an event on every stream that
-    # used them when they are freed) before the handles, and with them the streams, go away
+    # release everything torch holds on the library's streams (pinned tensors record an event on every stream that used them
+    # when they are freed) before the handles, and with them the streams, go away
     torch.cuda.synchronize()
-    handles = [(S["ex"], S["mt"]) for S in slots]
-    slots.clear()
-    del xs, ms, ev0, ev1, me0, me1, h_all, d_match, d_dist, d_nm, d_frames
+    del d_seq
+    m.pop("d_seq", None)
     import gc
     gc.collect()
     torch.cuda.synchronize()
-    for ex_, mt_ in handles:
-        mt_.close()
-        ex_.close()
+    rig.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -1694,6 +1694,34 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, i
     return EAOF_OK;
 }
 
+// internal (eaof_sweep.cu): the same two kernels over a chunk of a pair list that already lives on the device
+int eaof_internal_bruteforce_pairs_device(eaof_matcher* m, int mode, float ratio, int checkOri, int nPairs, const int* dPairQ,
+                                          const int* dPairT, const uint8_t* dDesc, const float* dAngle, const int* dCounts,
+                                          int blockStride, int* dMatch, int* dDist, int* dN) {
+    if (!m || !dPairQ || !dPairT || !dDesc || !dAngle || !dCounts || !dMatch || !dN) return mfail(EAOF_ERR_ARG, "null argument");
+    if (nPairs < 1 || nPairs > m->maxPairs) return mfail(EAOF_ERR_ARG, "n_pairs %d outside [1,%d]", nPairs, m->maxPairs);
+    if (blockStride < 1 || blockStride > m->maxFeat) return mfail(EAOF_ERR_ARG, "block_stride exceeds max_features");
+    if (mode != EAOF_BOW_KF_FRAME && mode != EAOF_BOW_KF_KF) return mfail(EAOF_ERR_ARG, "unknown mode");
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    BowArgs A{};
+    A.desc = dDesc; A.angle = dAngle; A.counts = dCounts; A.pairQ = dPairQ; A.pairT = dPairT;
+    A.blockStride = blockStride; A.stride = blockStride; A.mode = mode;
+    A.thEff = mode == EAOF_BOW_KF_FRAME ? EAOF_TH_LOW : EAOF_TH_LOW - 1;
+    A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
+    k_bow_dense<<<dim3((blockStride + BOW_QT - 1) / BOW_QT, nPairs), BOW_QT, 0, s>>>(A, nullptr, m->nearBuf);
+    const size_t bm = sizeof(uint32_t) * ((blockStride + 31) / 32);
+    k_bow_resolve<<<nPairs, 32, bm, s>>>(A, m->nearBuf, m->accBuf, dMatch, dDist, dN);
+    MCK(cudaGetLastError());
+    m->lastDistances = -1;
+    return EAOF_OK;
+}
+int eaof_internal_matcher_limits(const eaof_matcher* m, int* maxPairs, int* maxFeat, int* device) {
+    if (!m) return mfail(EAOF_ERR_ARG, "null matcher handle");
+    *maxPairs = m->maxPairs; *maxFeat = m->maxFeat; *device = m->device;
+    return EAOF_OK;
+}
+
 int eaof_match_bow_orb_device(eaof_matcher* m, eaof_orb* ex, int nFrames, int mode, float ratio, int checkOri, int nPairs,
                               const int* pairQ, const int* pairT, const int* dNFNodes, const uint32_t* dNodeIds,
                               const int* dNodeStart, const uint32_t* dFeatIdx, int* dMatch, int* dDist, int* dN) {

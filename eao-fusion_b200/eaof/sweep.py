@@ -3,8 +3,12 @@
 Every rank holds the descriptor blocks of the frames it extracted (one block = one frame: `stride` rows of 32 bytes,
 angles, a feature count).  The only exchange step of the whole ORB path happens here: the blocks are all-gathered once
 over NCCL (NVLink/NVSwitch) so that every rank can match any (query frame, target frame) pair; the global pair list is
-then partitioned round-robin and each rank runs `eaof_match_bruteforce_batch_device` on its share.  There is no other
-collective on the data path.  `torch.distributed` is plumbing only: device buffers in, device buffers out.
+then partitioned round-robin and each rank matches its share.
+
+On GPUs the exchange and the matching go through the C ABI of include/eaof_sweep.h (`Sweep`: ncclCommInitRank /
+ncclAllGather inside libeaof_orb.so); the host program only carries the 128-byte NCCL id to the other ranks.
+`gather_blocks` is the same block layout over a `torch.distributed` process group — it exists for the world_size-2
+gloo tests of the layout on CPU boxes (tests/test_host_logic.py) and is not used by bench.py.
 """
 from __future__ import annotations
 
@@ -89,5 +93,103 @@ def sweep(matcher, mode, desc, angle, counts, pairs, n_frames, rank=0, world=1, 
         s1 = min(len(sel), s0 + matcher.max_pairs)
         matcher.bruteforce_batch_device(mode, pq[s0:s1], pt[s0:s1], gd.data_ptr(), ga.data_ptr(), gc.data_ptr(), stride,
                                         d_match[s0:].data_ptr(), d_dist[s0:].data_ptr(), d_nm[s0:].data_ptr())
+    matcher.sync()
+    return sel, d_match[:len(sel)], d_dist[:len(sel)], d_nm[:len(sel)]
+
+
+class Sweep:
+    """include/eaof_sweep.h over ctypes: one NCCL communicator owned by libeaof_orb.so.  `id_bytes`: the 128-byte id
+    made by `Sweep.unique_id()` on one rank and carried to the others by the caller (None for world == 1)."""
+
+    def __init__(self, rank=0, world=1, device=0, id_bytes=None):
+        import ctypes as C
+        from . import _ck, lib
+        self.L = lib()
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        self.L.eaof_sweep_create.argtypes = [vp, ci, ci, ci, C.POINTER(vp)]
+        self.L.eaof_sweep_destroy.argtypes = [vp]
+        self.L.eaof_sweep_allgather_blocks.argtypes = [vp, ci, ci] + [vp] * 7
+        self.L.eaof_sweep_match.argtypes = [vp, vp, ci, cf, ci, ci, ci] + [vp] * 6 + [ci] + [vp] * 5
+        self.L.eaof_sweep_last_allgather.argtypes = [vp, C.POINTER(cf), C.POINTER(C.c_longlong)]
+        h = vp()
+        buf = None
+        if world > 1:
+            assert id_bytes is not None and len(id_bytes) == 128
+            buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id_bytes))
+        _ck(self.L.eaof_sweep_create(buf, rank, world, device, C.byref(h)))
+        self.h, self.rank, self.world = h, rank, world
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import _ck, lib
+        buf = (C.c_uint8 * 128)()
+        _ck(lib().eaof_sweep_unique_id(buf))
+        return bytes(buf)
+
+    @staticmethod
+    def nccl_version() -> int:
+        import ctypes as C
+        from . import _ck, lib
+        v = C.c_int()
+        _ck(lib().eaof_sweep_nccl_version(C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.eaof_sweep_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def allgather_blocks(self, per, stride, d_desc, d_angle, d_count, g_desc, g_angle, g_count, stream_ptr=None):
+        from . import _ck
+        _ck(self.L.eaof_sweep_allgather_blocks(self.h, per, stride, d_desc, d_angle, d_count, g_desc, g_angle, g_count, stream_ptr))
+
+    def match(self, matcher, mode, per, stride, d_desc, d_angle, d_count, g_desc, g_angle, g_count, pq, pt, d_match, d_dist, d_nm):
+        """All-gather + this rank's pairs (pq / pt: int32 numpy arrays of gathered-block indices), asynchronous on the
+        matcher's stream."""
+        from . import _ck
+        pq = np.ascontiguousarray(pq, np.int32)
+        pt = np.ascontiguousarray(pt, np.int32)
+        _ck(self.L.eaof_sweep_match(self.h, matcher.h, mode, matcher.mfNNratio, int(matcher.mbCheckOrientation), per, stride,
+                                    d_desc, d_angle, d_count, g_desc, g_angle, g_count, len(pq),
+                                    pq.ctypes.data if len(pq) else None, pt.ctypes.data if len(pt) else None, d_match, d_dist, d_nm))
+
+    def last_allgather(self):
+        import ctypes as C
+        from . import _ck
+        ms, b = C.c_float(), C.c_longlong()
+        _ck(self.L.eaof_sweep_last_allgather(self.h, C.byref(ms), C.byref(b)))
+        return ms.value, b.value
+
+
+def sweep_cabi(sw: "Sweep", matcher, mode, desc, angle, counts, pairs, n_frames):
+    """The product path: desc [n_local, stride, 32] u8, angle [n_local, stride] f32, counts [n_local] i32 (torch tensors
+    on this rank's device) -> (positions of this rank's pairs in the global list, match, dist, nmatches) with the
+    exchange done by ncclAllGather inside libeaof_orb.so."""
+    import torch
+    world, rank = sw.world, sw.rank
+    per = padded_blocks(n_frames, world)
+    n_local, stride = desc.shape[0], desc.shape[1]
+
+    def pad(t):
+        if t.shape[0] == per:
+            return t.contiguous()
+        out = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        out[:n_local] = t
+        return out
+    d, a, c = pad(desc), pad(angle), pad(counts)
+    gd = torch.empty((world * per, stride, 32), dtype=torch.uint8, device=d.device)
+    ga = torch.empty((world * per, stride), dtype=torch.float32, device=d.device)
+    gc = torch.empty((world * per,), dtype=torch.int32, device=d.device)
+    sel, pq, pt = my_pairs(np.asarray(pairs), n_frames, rank, world)
+    n = max(len(sel), 1)
+    d_match = torch.full((n, stride), -1, dtype=torch.int32, device=d.device)
+    d_dist = torch.full((n, stride), -1, dtype=torch.int32, device=d.device)
+    d_nm = torch.zeros(n, dtype=torch.int32, device=d.device)
+    torch.cuda.current_stream().synchronize()  # inputs / outputs were made on torch's stream, the sweep runs on the matcher's
+    sw.match(matcher, mode, per, stride, d.data_ptr(), a.data_ptr(), c.data_ptr(), gd.data_ptr(), ga.data_ptr(), gc.data_ptr(),
+             pq, pt, d_match.data_ptr(), d_dist.data_ptr(), d_nm.data_ptr())
     matcher.sync()
     return sel, d_match[:len(sel)], d_dist[:len(sel)], d_nm[:len(sel)]

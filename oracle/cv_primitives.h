@@ -135,40 +135,130 @@ static inline int fast_arc_best(const uint8_t* p, size_t step) {
 
 struct FastPt { int x, y, score; };
 
+// The same arc score with sliding minima / maxima (2-, 4-, 8-windows, then 9 = 8 + 1): ~100 operations instead of the
+// 16 x 9 scan above; fast_arc_best stays as the plain statement the tests compare against.
+static inline int fast_arc_best_quick(const uint8_t* p, size_t step) {
+    int d[16], mn2[16], mx2[16], mn4[16], mx4[16];
+    const int v = p[0];
+    for (int k = 0; k < 16; ++k) d[k] = (int)p[(ptrdiff_t)kRingDy[k] * (ptrdiff_t)step + kRingDx[k]] - v;
+    for (int k = 0; k < 16; ++k) {
+        const int e = d[(k + 1) & 15];
+        mn2[k] = d[k] < e ? d[k] : e;
+        mx2[k] = d[k] > e ? d[k] : e;
+    }
+    for (int k = 0; k < 16; ++k) {
+        const int a = mn2[(k + 2) & 15], c = mx2[(k + 2) & 15];
+        mn4[k] = mn2[k] < a ? mn2[k] : a;
+        mx4[k] = mx2[k] > c ? mx2[k] : c;
+    }
+    int best = -256;
+    for (int k = 0; k < 16; ++k) {
+        int mn = mn4[k] < mn4[(k + 4) & 15] ? mn4[k] : mn4[(k + 4) & 15];
+        int mx = mx4[k] > mx4[(k + 4) & 15] ? mx4[k] : mx4[(k + 4) & 15];
+        const int e = d[(k + 8) & 15];
+        mn = mn < e ? mn : e;
+        mx = mx > e ? mx : e;
+        if (mn > best) best = mn;
+        if (-mx > best) best = -mx;
+    }
+    return best;
+}
+
+}  // namespace cvprim
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+namespace cvprim {
+
 // cv::FAST(img, kps, threshold, nonmaxSuppression=true, TYPE_9_16): raster order output.
+// Organised like OpenCV's FAST_t<16>: a three-row ring of score rows, the early-out on 16 pixels at a time (SSE2:
+// every 9-arc contains one pixel of each opposite pair (k, k+8), so a corner is darker-or-brighter than the threshold
+// band on one pixel of all 8 pairs), the exact arc score only for the survivors, NMS one row behind.
 static inline void fast9_nms(const uint8_t* img, int w, int h, size_t step, int threshold,
                              std::vector<FastPt>& out) {
     out.clear();
     if (w < 7 || h < 7) return;
-    std::vector<int> score((size_t)w * h, 0);
-    std::vector<uint8_t> corner((size_t)w * h, 0);
-    for (int y = 3; y < h - 3; ++y)
-        for (int x = 3; x < w - 3; ++x) {
-            // OpenCV's early-out: every 9-arc contains one pixel of each opposite pair (k, k+8)
-            const uint8_t* p = img + (size_t)y * step + x;
-            const int v = p[0], lo = v - threshold, hi = v + threshold;
-            int d = 3;
-            for (int k = 0; k < 8 && d; ++k) {
-                const int a = p[(ptrdiff_t)kRingDy[k] * (ptrdiff_t)step + kRingDx[k]];
-                const int b = p[(ptrdiff_t)kRingDy[k + 8] * (ptrdiff_t)step + kRingDx[k + 8]];
-                d &= ((a < lo) | ((a > hi) << 1)) | ((b < lo) | ((b > hi) << 1));
+    // per-call buffers (no storage may outlive the call: the reference harness recycles its allocation arena per frame);
+    // cells are at most 66 px wide, so the common case lives on the stack
+    const int rw = w + 2;
+    int stackBuf[3 * 70 + 3 * 69];
+    std::vector<int> heapBuf;
+    int* sbuf = stackBuf;
+    if (w > 68) { heapBuf.resize((size_t)3 * rw + (size_t)3 * (w + 1)); sbuf = heapBuf.data(); }
+    int* cbuf = sbuf + (size_t)3 * rw;  // corner columns of rows y-2, y-1, y; [0] = count
+    memset(sbuf, 0, sizeof(int) * (size_t)3 * rw);  // scores of those rows (column x at index x+1), 0 = not a corner
+    ptrdiff_t off[16];
+    for (int k = 0; k < 16; ++k) off[k] = (ptrdiff_t)kRingDy[k] * (ptrdiff_t)step + kRingDx[k];
+    const int t = threshold < 0 ? 0 : threshold > 255 ? 255 : threshold;
+    for (int y = 3; y < h - 2; ++y) {
+        int* cur = &sbuf[(size_t)((y - 3) % 3) * rw];
+        int* ccur = &cbuf[(size_t)((y - 3) % 3) * (w + 1)];
+        memset(cur, 0, sizeof(int) * rw);
+        int nc = 0;
+        if (y < h - 3) {
+            const uint8_t* row = img + (size_t)y * step;
+            int x = 3;
+#if defined(__SSE2__)
+            const __m128i vt = _mm_set1_epi8((char)t), zero = _mm_setzero_si128();
+            for (; x + 16 <= w - 3 || (x < w - 3 && w - 3 - 16 >= 3); ) {
+                int x0 = x;
+                if (x0 + 16 > w - 3) x0 = w - 3 - 16;  // last block overlaps the previous one
+                const uint8_t* p = row + x0;
+                const __m128i v = _mm_loadu_si128((const __m128i*)p);
+                const __m128i lo = _mm_subs_epu8(v, vt), hi = _mm_adds_epu8(v, vt);
+                __m128i dark = _mm_set1_epi8((char)0xff), bright = dark;
+                for (int k = 0; k < 8; ++k) {
+                    const __m128i a = _mm_loadu_si128((const __m128i*)(p + off[k]));
+                    const __m128i b2 = _mm_loadu_si128((const __m128i*)(p + off[k + 8]));
+                    // a < lo  <=>  subs(lo, a) != 0 ;  a > hi  <=>  subs(a, hi) != 0
+                    const __m128i da = _mm_or_si128(_mm_subs_epu8(lo, a), _mm_subs_epu8(lo, b2));
+                    const __m128i ba = _mm_or_si128(_mm_subs_epu8(a, hi), _mm_subs_epu8(b2, hi));
+                    dark = _mm_andnot_si128(_mm_cmpeq_epi8(da, zero), dark);
+                    bright = _mm_andnot_si128(_mm_cmpeq_epi8(ba, zero), bright);
+                    if (k == 1 || k == 3) {
+                        if (_mm_movemask_epi8(_mm_or_si128(dark, bright)) == 0) break;
+                    }
+                }
+                unsigned m = (unsigned)_mm_movemask_epi8(_mm_or_si128(dark, bright));
+                if (x0 < x) m &= ~0u << (x - x0);  // pixels the previous block already handled
+                while (m) {
+                    const int j = __builtin_ctz(m);
+                    m &= m - 1;
+                    const int b = fast_arc_best_quick(p + j, step);
+                    if (b > t) { cur[x0 + j + 1] = b - 1; ccur[1 + nc++] = x0 + j; }
+                }
+                x = x0 + 16;
+                if (x >= w - 3) break;
             }
-            if (!d) continue;
-            const int b = fast_arc_best(p, step);
-            if (b > threshold) {
-                score[(size_t)y * w + x] = b - 1;
-                corner[(size_t)y * w + x] = 1;
+#endif
+            for (; x < w - 3; ++x) {
+                const uint8_t* p = row + x;
+                const int v = p[0], lo = v - t, hi = v + t;
+                int d = 3;
+                for (int k = 0; k < 8 && d; ++k) {
+                    const int a = p[off[k]], b2 = p[off[k + 8]];
+                    d &= ((a < lo) | ((a > hi) << 1)) | ((b2 < lo) | ((b2 > hi) << 1));
+                }
+                if (!d) continue;
+                const int b = fast_arc_best_quick(p, step);
+                if (b > t) { cur[x + 1] = b - 1; ccur[1 + nc++] = x; }
             }
         }
-    for (int y = 3; y < h - 3; ++y)
-        for (int x = 3; x < w - 3; ++x) {
-            if (!corner[(size_t)y * w + x]) continue;
-            const int* r = &score[(size_t)y * w + x];
-            const int s = r[0];
-            if (s > r[-1] && s > r[1] && s > r[-w - 1] && s > r[-w] && s > r[-w + 1] && s > r[w - 1] &&
-                s > r[w] && s > r[w + 1])
-                out.push_back({x, y, s});
+        ccur[0] = nc;
+        if (y == 3) continue;
+        // NMS of row y-1 against rows y-2, y-1, y (rows outside [3, h-3) hold zeros)
+        const int* prev = &sbuf[(size_t)((y - 4 + 3) % 3) * rw];
+        const int* pprev = &sbuf[(size_t)((y - 5 + 6) % 3) * rw];
+        const int* cprev = &cbuf[(size_t)((y - 4 + 3) % 3) * (w + 1)];
+        const bool havePP = y - 2 >= 3;
+        for (int i = 0; i < cprev[0]; ++i) {
+            const int x = cprev[1 + i], xi = x + 1;
+            const int sc = prev[xi];
+            if (sc > prev[xi - 1] && sc > prev[xi + 1] && sc > cur[xi - 1] && sc > cur[xi] && sc > cur[xi + 1] &&
+                (!havePP || (sc > pprev[xi - 1] && sc > pprev[xi] && sc > pprev[xi + 1])))
+                out.push_back({x, y - 1, sc});
         }
+    }
 }
 
 // ---- Gaussian blur 7x7, sigma 2, 8U, reflect-101 -------------------------------------------
@@ -188,31 +278,35 @@ static inline const int* blur_taps(int mode) {
 static inline void gaussian_blur7(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst,
                                   size_t dstep, int mode) {
     const int* k = blur_taps(mode);
-    std::vector<int> rows((size_t)w * h);
+    // horizontal pass on a reflect-padded copy of the row (plain loops the compiler vectorises); sums fit 16 bits
+    std::vector<uint16_t> rows((size_t)w * h);
+    std::vector<uint8_t> pad((size_t)w + 6);
     for (int y = 0; y < h; ++y) {
         const uint8_t* s = src + (size_t)y * sstep;
-        for (int x = 0; x < w; ++x) {
-            int acc = 0;
-            for (int i = 0; i < 7; ++i) acc += k[i] * s[reflect101(x + i - 3, w)];
-            rows[(size_t)y * w + x] = acc;
-        }
+        for (int i = 0; i < 3; ++i) { pad[i] = s[reflect101(i - 3, w)]; pad[w + 3 + i] = s[reflect101(w + i, w)]; }
+        memcpy(pad.data() + 3, s, w);
+        const uint8_t* q = pad.data();
+        uint16_t* r = &rows[(size_t)y * w];
+        const int k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3];
+        for (int x = 0; x < w; ++x)
+            r[x] = (uint16_t)(k0 * (q[x] + q[x + 6]) + k1 * (q[x + 1] + q[x + 5]) + k2 * (q[x + 2] + q[x + 4]) + k3 * q[x + 3]);
     }
     const int simd_w = (mode == BLUR_CV331_SSE2) ? (w & ~3) : 0;
+    std::vector<int> acc(w);
     for (int y = 0; y < h; ++y) {
+        const uint16_t* r[7];
+        for (int j = 0; j < 7; ++j) r[j] = &rows[(size_t)reflect101(y + j - 3, h) * w];
+        const int k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3];
+        for (int x = 0; x < w; ++x)
+            acc[x] = k0 * ((int)r[0][x] + r[6][x]) + k1 * ((int)r[1][x] + r[5][x]) + k2 * ((int)r[2][x] + r[4][x]) + k3 * (int)r[3][x];
         uint8_t* d = dst + (size_t)y * dstep;
-        for (int x = 0; x < w; ++x) {
-            int acc = 0;
-            for (int j = 0; j < 7; ++j) acc += k[j] * rows[(size_t)reflect101(y + j - 3, h) * w + x];
-            int q;
-            if (x < simd_w) {
-                q = acc >> 16;
-                const int rem = acc & 0xFFFF;
-                q += (rem > 32768) || (rem == 32768 && (q & 1));
-            } else {
-                q = (acc + 32768) >> 16;
-            }
+        for (int x = 0; x < simd_w; ++x) {
+            int q = acc[x] >> 16;
+            const int rem = acc[x] & 0xFFFF;
+            q += (rem > 32768) || (rem == 32768 && (q & 1));
             d[x] = sat_u8(q);
         }
+        for (int x = simd_w; x < w; ++x) d[x] = sat_u8((acc[x] + 32768) >> 16);
     }
 }
 

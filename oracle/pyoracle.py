@@ -59,6 +59,10 @@ def ref_lib():
         L.orbref_bench.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
         L.orbref_arena_allocs.restype = C.c_long
+        L.orbref_extract_many.restype = C.c_double
+        L.orbref_extract_many.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                          C.c_void_p]
         _ref = L
     return _ref
 
@@ -127,6 +131,29 @@ def ref_bench(frames: np.ndarray, nfeatures=1000, scale_factor=1.2, nlevels=8, i
     secs = L.orbref_bench(nfeatures, scale_factor, nlevels, ini_th, min_th, frames.ctypes.data, n, w, h, threads,
                           1 if canonical else 0, repeat, C.byref(tot))
     return secs, tot.value
+
+
+def ref_extract_many(frames: np.ndarray, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, threads=1,
+                     canonical=True, blur_mode=BLUR_CV331, want_results=True):
+    """The reference extractor over frames (n,h,w), frame-parallel on `threads` host threads, results kept.
+    Returns (wall seconds, per-frame seconds [n], list of (keypoints, descriptors) or None)."""
+    L = ref_lib()
+    L.orbref_set_blur_mode(blur_mode)
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    cap = nfeatures + 4 * nlevels + 64
+    cnt = np.zeros(n, np.int32)
+    per = np.zeros(n, np.float64)
+    kps = np.zeros((n, cap), KP_DTYPE) if want_results else None
+    desc = np.zeros((n, cap, 32), np.uint8) if want_results else None
+    secs = L.orbref_extract_many(nfeatures, scale_factor, nlevels, ini_th, min_th, frames.ctypes.data, n, w, h, threads,
+                                 1 if canonical else 0, kps.ctypes.data if want_results else None,
+                                 desc.ctypes.data if want_results else None, cap, cnt.ctypes.data, per.ctypes.data)
+    res = None
+    if want_results:
+        assert int(cnt.max(initial=0)) <= cap
+        res = [(kps[i, :cnt[i]], desc[i, :cnt[i]]) for i in range(n)]
+    return secs, per, res
 
 
 # ------------------------------------------------------------------------------------------------

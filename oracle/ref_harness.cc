@@ -221,4 +221,32 @@ double orbref_bench(int nfeatures, float scaleFactor, int nlevels, int iniTh, in
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Frame-parallel extraction that keeps the results (parity checks over whole sequences, and the single-thread latency
+// distribution of the reference: per_frame_secs[i] = wall time of frame i's operator()).  Frame i runs on thread
+// i % n_threads; kps / desc are laid out [n][cap]; counts[i] = keypoints of frame i (may exceed cap: then truncated).
+double orbref_extract_many(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* frames,
+                           int n, int w, int hgt, int n_threads, int canonical, orbref_kp* kps, uint8_t* desc, int cap,
+                           int* counts, double* per_frame_secs) {
+    if (n_threads < 1) n_threads = 1;
+    std::vector<std::thread> th;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < n_threads; ++t)
+        th.emplace_back([&, t]() {
+            void* hp = orbref_create(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+            orbref_set_canonical(hp, canonical);
+            for (int i = t; i < n; i += n_threads) {
+                auto a = std::chrono::steady_clock::now();
+                const int k = orbref_extract(hp, frames + (size_t)i * w * hgt, w, hgt, (size_t)w,
+                                             kps ? kps + (size_t)i * cap : nullptr, desc ? desc + (size_t)i * cap * 32 : nullptr,
+                                             cap, 0);
+                auto b = std::chrono::steady_clock::now();
+                if (counts) counts[i] = k;
+                if (per_frame_secs) per_frame_secs[i] = std::chrono::duration<double>(b - a).count();
+            }
+            orbref_destroy(hp);
+        });
+    for (auto& x : th) x.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 }  // extern "C"

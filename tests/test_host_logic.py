@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for hdr in ("eaof_orb.h", "eaof_match.h", "eaof_voc.h"):
+    for hdr in ("eaof_orb.h", "eaof_match.h", "eaof_voc.h", "eaof_sweep.h"):
         src = open(os.path.join(ROOT, "include", hdr)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(eaof_[a-z0-9_]+)\s*\(", src))
@@ -49,6 +49,29 @@ def test_product_fails_loudly_without_a_gpu():
         eaof.ORBextractor(width=640, height=480)
     with pytest.raises(eaof.EaofError, match="no CUDA device"):
         eaof.ORBmatcher(0.9)
+    from eaof import sweep
+    with pytest.raises(eaof.EaofError, match="no CUDA device"):
+        sweep.Sweep(0, 1, 0)
+
+
+def test_sweep_cabi_argument_errors_and_nccl_binding():
+    """include/eaof_sweep.h without a GPU: argument errors come back as EAOF_ERR_ARG with a reason, NCCL is bound at run
+    time (the id call works wherever a libnccl.so.2 exists and fails with EAOF_ERR_NCCL where it does not)."""
+    import eaof
+    L = eaof.lib()
+    L.eaof_sweep_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    h = ctypes.c_void_p()
+    assert L.eaof_sweep_create(None, 2, 2, 0, ctypes.byref(h)) == -1 and b"rank 2 outside a world of 2" in L.eaof_last_error()
+    assert L.eaof_sweep_create(None, 0, 2, 0, ctypes.byref(h)) == -1 and b"unique id" in L.eaof_last_error()
+    buf = (ctypes.c_uint8 * 128)()
+    rc = L.eaof_sweep_unique_id(buf)
+    assert rc in (0, -5), L.eaof_last_error()
+    if rc == 0:
+        assert any(buf)
+        v = ctypes.c_int()
+        assert L.eaof_sweep_nccl_version(ctypes.byref(v)) == 0 and v.value >= 20000
+    else:
+        assert b"libnccl" in L.eaof_last_error()
 
 
 def test_product_package_never_imports_the_oracle():
@@ -330,3 +353,20 @@ print("RETURNED")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert "RETURNED" not in out.stdout and out.returncode != 0
     assert "no CUDA device" in out.stderr or "eaof_matcher_create" in out.stderr, out.stderr[-2000:]
+
+
+def test_workload_sequences_shard_exactly():
+    """eaof/workload.py: global frame t is the same whichever rank builds it (scene t // 1000 with its own texture), scene 0
+    is the configs[1] sequence, and a rank's block + halo is a plain slice of the whole."""
+    from eaof import shard, synth, workload
+    seq = workload.Sequence(96, 80)
+    whole = seq.frames(0, 2 * workload.SEQ_LEN)
+    assert np.array_equal(whole[:7], synth.make_frames(7, 96, 80, tex=synth.base_texture(96, 80, seed=1235)))
+    assert not np.array_equal(whole[0], whole[workload.SEQ_LEN])  # a new scene
+    for world in (2, 3):
+        for r in range(world):
+            b, e = shard.frame_block(2 * workload.SEQ_LEN, r, world)
+            hb, he = shard.halo_block(b, e)
+            assert np.array_equal(workload.Sequence(96, 80).frames(hb, he), whole[hb:he])
+    d = [workload.frame_digest(np.zeros(3, "<f4"), np.zeros((3, 32), np.uint8)), workload.pair_digest(np.arange(4))]
+    assert workload.combine(d) == workload.combine(list(d)) and len(workload.combine(d)) == 64
