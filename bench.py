@@ -459,11 +459,17 @@ def measure_config(eaof, torch, dist, rank, world, device, name, B, steps, warmu
                       "d2h_bytes_per_step": n_batches * ((B + 1) * (cap * 56 + 4) + B * (cap * 4 + 4)),
                       "launches": nb * launches_per_batch}
         assert int(last_cnt.sum()) > 0 and int(slots[(nb - 1) % n_slots]["h_nm"].sum()) > 0
+        # release what torch holds on the library's streams (pinned tensors record an event on every stream that used
+        # them when they are freed) before the extra handles, and with them their streams, go away
         torch.cuda.synchronize()
-        for S in slots[1:]:
-            S["rig"].close()
+        extra = [S["rig"] for S in slots[1:]]
         slots.clear()
-        del h_all
+        del h_all, r
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        for r_ in extra:
+            r_.close()
     out["rig"] = rig
     out["d_seq"] = d_seq
     del xs, ms, ev0, ev1

@@ -2,6 +2,7 @@
 // derives per frame (src/ORBextractor.cc:410-470 constructor tables, :1107-1118 level sizes, :773-806 cell grid),
 // owns the device workspace and issues the kernel sequence of orb_kernels.cuh on the handle's stream.
 // There is deliberately no CPU implementation here: every failure to reach the GPU is an error.
+#include <cuda.h>  // CUtensorMap and its enums; cuTensorMapEncodeTiled is fetched through the runtime (no -lcuda)
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>  // header-only; ranges are no-ops unless a tool (ncu --nvtx, nsys) injects itself
 
@@ -43,6 +44,10 @@ inline short sat_short(int v) { return (short)(v < -32768 ? -32768 : v > 32767 ?
 
 }  // namespace
 
+#ifdef EAOF_TMA_DEBUG
+static int* g_tmaDbgHost = nullptr;
+extern "C" int* eaof_debug_tma_records() { return g_tmaDbgHost; }
+#endif
 struct eaof_orb {
     eaof_orb_params p{};
     int device = 0;
@@ -99,6 +104,13 @@ struct eaof_orb {
     uint8_t* hDesc = nullptr;
     int* hKpCount = nullptr;
     size_t octSmem = 0;
+    // k_fast_tma: one tensor map per pyramid level over the handle's whole pyramid buffer, the work counter, launch shape
+    eaof::FastTmaMaps fastMaps{};
+    unsigned int* dFastCtr = nullptr;   // [kMaxChunks]
+    eaof::FastTmaArgs fastT{};
+    bool fastTma = false;
+    int fastTmaGrid = 0;
+    size_t fastTmaSmem = 0;
     bool profiling = false;
     cudaEvent_t ev[7] = {};
     float stageMs[6] = {};
@@ -277,7 +289,7 @@ std::mutex g_tokMu;
 cudaEvent_t g_tok[64] = {};
 bool g_tokSet[64] = {};
 
-int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t framePitch, int f0 = 0) {
+int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t framePitch, int f0 = 0, int chunkIdx = 0) {
     const Geom& g = c->g;
     cudaStream_t s = c->stream;
     // every per-frame array is frame-major, so a chunk is addressed by offsetting the base pointers
@@ -350,7 +362,17 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         ++launches;
         CK(cudaEventRecord(c->evBlur, sb));
     }
-    if (g.cellsPerFrame > 0) {
+    if (g.cellsPerFrame > 0 && c->fastTma) {
+        // persistent warps pulling (frame, cell) items off a counter; the tile of every item arrives by TMA
+        unsigned int* ctr = c->dFastCtr + (chunkIdx % eaof_orb::kMaxChunks);
+        CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s));
+        eaof::FastTmaArgs A = c->fastT;
+        A.f0 = f0;
+        A.nItems = n * g.cellsPerFrame;
+        const int grid = std::min(c->fastTmaGrid, (A.nItems + FASTT_WARPS - 1) / FASTT_WARPS);
+        eaof::k_fast_tma<<<grid, FASTT_WARPS * 32, c->fastTmaSmem, s>>>(c->fastMaps, A, c->dCells, dCand, dCandCount, ctr, g);
+        ++launches;
+    } else if (g.cellsPerFrame > 0) {
         const size_t smem = (size_t)FAST_WARPS * g.fastWarpWords * 4;
         eaof::k_fast<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
             dPyr, c->dCells, dCand, dCandCount, g);
@@ -528,6 +550,84 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
         CKD(cudaFuncSetAttribute(eaof::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     {
+        // k_fast_tma: tensor maps (CU_TENSOR_MAP_DATA_TYPE_UINT8, rank 3: byte column, row, frame) and shared-memory shape.
+        // EAOF_FAST_TMA=0 keeps the LDG-staged k_fast (A/B measurements).
+        const char* e = getenv("EAOF_FAST_TMA");
+        const bool want = !(e && *e == '0');
+        int maxCw = 16, maxCh = 8;
+        for (const CellDesc& cd : cells) { maxCw = std::max<int>(maxCw, cd.cw); maxCh = std::max<int>(maxCh, cd.ch); }
+        eaof::FastTmaArgs& T = c->fastT;
+        T.boxW = (maxCw + 15) & ~15;
+        T.boxH = (maxCh + 7) & ~7;
+        if (const char* v = getenv("EAOF_TMA_BOXW")) T.boxW = std::max(T.boxW, atoi(v));  // experiment knobs
+        if (const char* v = getenv("EAOF_TMA_BOXH")) T.boxH = std::max(T.boxH, atoi(v));
+        // Tile buffers are kept 256-byte aligned: with 128 (the documented minimum for cp.async.bulk.tensor destinations) the
+        // 48 x 40 box of the 640x480 geometry raised "illegal instruction" on B200 whenever a buffer sat on an odd multiple
+        // of 128 (measured: every layout with all destinations on 256 passes, every one with a 128-only destination fails).
+        T.tileBytes = (T.boxW * T.boxH + 255) & ~255;
+        T.lstCap = 248;  // phase (A) refills the list in rounds of <= 128 entries
+        T.warpBytes = (3 * T.tileBytes + 2 * FAST_CLST + 2 * T.lstCap + 16 + 255) & ~255;
+        c->fastTmaSmem = (size_t)FASTT_WARPS * T.warpBytes + 256;
+        if (const char* v = getenv("EAOF_TMA_PAD")) c->fastTmaSmem += atoi(v);  // experiment knob: fewer resident CTAs
+        if (want && !cells.empty() && T.boxW <= 256 && T.boxH <= 256 && (c->fastTmaSmem + 1024) * FASTT_MINB <= 227 * 1024) {
+            typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                            const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            CKD(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            if (!fn || qres != cudaDriverEntryPointSuccess) {
+                fail(EAOF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+                eaof_orb_destroy(c);
+                return EAOF_ERR_CUDA;
+            }
+            std::vector<CUtensorMap> maps(EAOF_MAX_LEVELS);
+            memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
+            for (int l = 0; l < g.nlevels; ++l) {
+                const LevelGeom& L = g.L[l];
+                const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)B};
+                const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.pyrFrameBytes};
+                const cuuint32_t box[3] = {(cuuint32_t)T.boxW, (cuuint32_t)T.boxH, 1};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                const CUresult r = ((EncodeTiled)fn)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->dPyr + L.off, dims, strides, box, estr,
+                                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (getenv("EAOF_TMA_DEBUG"))
+                    fprintf(stderr, "tmap level %d: base %p dims %llu x %llu x %llu strides %llu %llu box %u x %u -> %d\n", l,
+                            (void*)(c->dPyr + L.off), (unsigned long long)dims[0], (unsigned long long)dims[1],
+                            (unsigned long long)dims[2], (unsigned long long)strides[0], (unsigned long long)strides[1], box[0], box[1], (int)r);
+                if (r != CUDA_SUCCESS) {
+                    fail(EAOF_ERR_CUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+                    eaof_orb_destroy(c);
+                    return EAOF_ERR_CUDA;
+                }
+            }
+            static_assert(sizeof(CUtensorMap) == 128 && sizeof(eaof::FastTmaMaps) == 128 * EAOF_MAX_LEVELS, "tensor map size");
+            memcpy(&c->fastMaps, maps.data(), sizeof(c->fastMaps));
+            CKD(cudaMalloc(&c->dFastCtr, sizeof(unsigned int) * eaof_orb::kMaxChunks));
+            int sms = 0;
+            CKD(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            c->fastTmaGrid = sms * FASTT_MINB;
+            if (const char* v = getenv("EAOF_TMA_GRID")) c->fastTmaGrid = atoi(v);  // experiment knob
+            static std::mutex muT;
+            std::lock_guard<std::mutex> lk(muT);
+            CKD(cudaFuncSetAttribute(eaof::k_fast_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CKD(cudaFuncSetAttribute(eaof::k_fast_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            c->fastTma = true;
+#ifdef EAOF_TMA_DEBUG
+            {
+                int* h = nullptr;
+                CKD(cudaHostAlloc(&h, sizeof(int) * 8 * 8192, cudaHostAllocMapped));
+                memset(h, 0, sizeof(int) * 8 * 8192);
+                int* d = nullptr;
+                CKD(cudaHostGetDevicePointer(&d, h, 0));
+                T.dbg = d;
+                g_tmaDbgHost = h;
+            }
+#endif
+        }
+    }
+    {
         // the attribute is per function, not per handle: only ever raise it (handles with different nfeatures coexist)
         static std::mutex mu;
         static size_t maxSet[64] = {};
@@ -563,6 +663,7 @@ void eaof_orb_destroy(eaof_orb* c) {
     if (c->evReader) cudaEventDestroy(c->evReader);
     if (c->evPyrReader) cudaEventDestroy(c->evPyrReader);
     cudaFree(c->dSad);
+    cudaFree(c->dFastCtr);
     if (c->streamIn) { cudaStreamSynchronize(c->streamIn); cudaStreamDestroy(c->streamIn); }
     if (c->streamOut) { cudaStreamSynchronize(c->streamOut); cudaStreamDestroy(c->streamOut); }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -873,7 +974,7 @@ int eaof_orb_extract_batch_async(eaof_orb* c, const uint8_t* imgs, int n, int wi
         }
         CK(cudaEventRecord(c->evIn[ci], c->streamIn));
         CK(cudaStreamWaitEvent(c->stream, c->evIn[ci], 0));
-        rc = run_batch(c, dst, m, (size_t)width, frameBytes, f0);
+        rc = run_batch(c, dst, m, (size_t)width, frameBytes, f0, ci);
         if (rc) return rc;
         CK(cudaEventRecord(c->evDone[ci], c->stream));
         // download

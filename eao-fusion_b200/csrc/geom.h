@@ -49,9 +49,9 @@ struct Geom {
     LevelGeom L[EAOF_MAX_LEVELS];
 };
 
-struct CellDesc {  // one FAST cell, src/ORBextractor.cc:789-806
+struct alignas(16) CellDesc {  // one FAST cell, src/ORBextractor.cc:789-806; 16 bytes: one vector load
     short level;
     short iniX, iniY;  // top-left of the cell sub-image, inner level coordinates
     short cw, ch;      // sub-image size (<= 66)
-    short pad;
+    short pad, pad2, pad3;
 };

@@ -13,6 +13,7 @@
 // std::cos(float)/std::sin(float) (= cosf/sinf), see DESIGN.md.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <stdint.h>
 
 #include "geom.h"
@@ -531,58 +532,25 @@ __device__ __forceinline__ unsigned arc_best2(const unsigned (&d)[16]) {
 #define FAST_MINB 24
 #endif
 #define FAST_CLST 128
-__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8_t* __restrict__ pyr,
-                                                                     const CellDesc* __restrict__ cells,
-                                                                     uint32_t* __restrict__ cand,
-                                                                     uint32_t* __restrict__ candCount,
-                                                                     const __grid_constant__ Geom g) {
-    extern __shared__ __align__(16) uint32_t fastSmem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cell = blockIdx.x * FAST_WARPS + warp;
-    if (cell >= g.cellsPerFrame) return;
-    const int PW = g.fastPW;                     // tile / score pitch in words: 1 pad word + data words
-    const int mapWords = g.fastMapWords;         // multiple of 4
-    uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;  // pixel (row r, tile byte column c) at byte (r*PW + 1)*4 + c
-    uint32_t* Bm = tile + mapWords;              // arc score of corners (0 elsewhere), same layout
-    uint16_t* clst = reinterpret_cast<uint16_t*>(Bm + mapWords);  // corners found by (B): (row, tile byte column)
-    uint16_t* lst = clst + FAST_CLST;                             // surviving (row, word, pixel pair (0,1) or (2,3))
+// Phases (A), (B), (C) of one cell whose tile already sits in shared memory: pixel (row r, byte column c) at byte
+// (r*PW + PAD)*4 + c of `tile`, cell pixel x at byte column mis + x; Bm (zeroed by the caller) has the same layout.
+template <int PAD>
+__device__ __forceinline__ void fast_cell(uint32_t* tile, uint32_t* Bm, uint16_t* clst, uint16_t* lst, const int lstCap,
+                                          const CellDesc c, const int f, const int mis, const int PW, const int lane,
+                                          uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount, const Geom& g) {
     // NMS survivors overwrite the tile: the first one is written only when the attempt that produced it is the last
     // one, and phase (C) reads nothing but the score map.
     uint32_t* outl = tile;
-
-    const CellDesc c = cells[cell];
-    const int f = blockIdx.y;
     const LevelGeom& L = g.L[c.level];
     const int cw = c.cw, ch = c.ch;
     const int ih = ch - 6;
-    if (cw <= 6 || ih <= 0) return;
-
-    const int col0 = EAOF_INNER_X0 + c.iniX;
-    const int mis = col0 & 3;  // cell pixel x sits at tile byte column mis + x
-    const int nwords = (mis + cw + 3) >> 2;
-    {
-        const uint32_t* src32 = reinterpret_cast<const uint32_t*>(
-            pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + c.iniY) * L.pitch + (col0 - mis));
-        const int pitchW = L.pitch >> 2;
-        if (2 * nwords <= 32) {  // two rows per pass
-            const int half = lane >= 16, wl = lane & 15;
-            if (wl < nwords)
-                for (int r = half; r < ch; r += 2) tile[r * PW + 1 + wl] = __ldg(src32 + r * pitchW + wl);
-        } else if (lane < nwords) {
-            for (int r = 0; r < ch; ++r) tile[r * PW + 1 + lane] = __ldg(src32 + r * pitchW + lane);
-        }
-    }
-    for (int i = lane; i < mapWords / 4; i += 32) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
-    __syncwarp();
-
     // words holding at least one pixel of the cell's inner area x in [3, cw-3)
     const int cLo = mis + 3, cHi = mis + cw - 4;  // first / last valid tile byte column
     const int wLo = cLo >> 2, nW = (cHi >> 2) - wLo + 1;
     const int nTasks = ih * nW;
     const unsigned rcpW = 65536u / (unsigned)nW + 1u;
     const unsigned below = (1u << lane) - 1;
-    const int lstCap = 2 * (g.fastWarpWords - 2 * mapWords) - FAST_CLST;  // entries the survivor list holds
-
+    
     // The cell is first searched at iniThFAST; only a cell with no keypoint after NMS is searched again at
     // minThFAST (:808-816).  Each attempt: (A) a necessary condition on the 4 compass ring pixels (every 9-arc holds
     // one of the pixels {0, 8} and one of {4, 12}) at that threshold, one lane per aligned 4-pixel word on byte lanes,
@@ -611,7 +579,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                     const int r = (int)(((unsigned)i * rcpW) >> 16);
                     w = wLo + (i - r * nW);
                     y = r + 3;
-                    const uint32_t* t = tile + y * PW + 1 + w;
+                    const uint32_t* t = tile + y * PW + PAD + w;
                     const unsigned W0 = t[0], Wm = t[-1], Wp = t[1], Wu = t[-3 * PW], Wd = t[3 * PW];
                     const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
                     // Every 9-arc of the ring holds one of the pixels {0, 8} and one of {4, 12}, so a corner at threshold
@@ -643,7 +611,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                 const int iA = p0 + 2 * lane;
                 const bool actA = iA < nl, actB = iA + 1 < nl;
                 const int eA = lst[actA ? iA : 0], eB = lst[actB ? iA + 1 : (actA ? iA : 0)];
-                const int oA = ((eA >> 8) * PW + 1) * 4 + (eA & 255), oB = ((eB >> 8) * PW + 1) * 4 + (eB & 255);
+                const int oA = ((eA >> 8) * PW + PAD) * 4 + (eA & 255), oB = ((eB >> 8) * PW + PAD) * 4 + (eB & 255);
                 const uint8_t* pA = tb + oA;
                 const uint8_t* pB = tb + oB;
                 const unsigned nc = FAST_BIAS2 - ((unsigned)pA[0] | ((unsigned)pB[0] << 16));
@@ -677,7 +645,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
             for (int i0 = 0; i0 < ncorn; i0 += 32) {
                 const bool act = i0 + lane < ncorn;
                 const int e = clst[act ? i0 + lane : 0], y = e >> 8, col = e & 255;
-                const uint8_t* q = reinterpret_cast<const uint8_t*>(Bm + y * PW + 1) + col;
+                const uint8_t* q = reinterpret_cast<const uint8_t*>(Bm + y * PW + PAD) + col;
                 const int s = (int)q[0] - 1;
                 int nbMax = 0;  // stored scores are either 0 or > th
 #pragma unroll
@@ -701,7 +669,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
             const int i = i0 + lane;
             const int r = (int)(((unsigned)min(i, nTasks - 1) * rcpW) >> 16);
             const int w = wLo + (min(i, nTasks - 1) - r * nW), y = r + 3;
-            const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * PW + 1 + w);
+            const uint8_t* q0 = reinterpret_cast<const uint8_t*>(Bm + y * PW + PAD + w);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint8_t* q = q0 + j;
@@ -735,6 +703,194 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     gBase = __shfl_sync(0xffffffffu, gBase, 0);
     uint32_t* dst = cand + (size_t)f * g.candPerFrame + L.candOff + gBase;
     for (int i = lane; i < no; i += 32) dst[i] = outl[i];
+}
+
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8_t* __restrict__ pyr,
+                                                                     const CellDesc* __restrict__ cells,
+                                                                     uint32_t* __restrict__ cand,
+                                                                     uint32_t* __restrict__ candCount,
+                                                                     const __grid_constant__ Geom g) {
+    extern __shared__ __align__(16) uint32_t fastSmem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cell = blockIdx.x * FAST_WARPS + warp;
+    if (cell >= g.cellsPerFrame) return;
+    const int PW = g.fastPW;                     // tile / score pitch in words: 1 pad word + data words
+    const int mapWords = g.fastMapWords;         // multiple of 4
+    uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;  // pixel (row r, tile byte column c) at byte (r*PW + 1)*4 + c
+    uint32_t* Bm = tile + mapWords;              // arc score of corners (0 elsewhere), same layout
+    uint16_t* clst = reinterpret_cast<uint16_t*>(Bm + mapWords);  // corners found by (B): (row, tile byte column)
+    uint16_t* lst = clst + FAST_CLST;                             // surviving (row, word, pixel pair (0,1) or (2,3))
+    const CellDesc c = cells[cell];
+    const int f = blockIdx.y;
+    const LevelGeom& L = g.L[c.level];
+    const int cw = c.cw, ch = c.ch;
+    const int ih = ch - 6;
+    if (cw <= 6 || ih <= 0) return;
+
+    const int col0 = EAOF_INNER_X0 + c.iniX;
+    const int mis = col0 & 3;  // cell pixel x sits at tile byte column mis + x
+    const int nwords = (mis + cw + 3) >> 2;
+    {
+        const uint32_t* src32 = reinterpret_cast<const uint32_t*>(
+            pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + c.iniY) * L.pitch + (col0 - mis));
+        const int pitchW = L.pitch >> 2;
+        if (2 * nwords <= 32) {  // two rows per pass
+            const int half = lane >= 16, wl = lane & 15;
+            if (wl < nwords)
+                for (int r = half; r < ch; r += 2) tile[r * PW + 1 + wl] = __ldg(src32 + r * pitchW + wl);
+        } else if (lane < nwords) {
+            for (int r = 0; r < ch; ++r) tile[r * PW + 1 + lane] = __ldg(src32 + r * pitchW + lane);
+        }
+    }
+    for (int i = lane; i < mapWords / 4; i += 32) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    const int lstCap = 2 * (g.fastWarpWords - 2 * mapWords) - FAST_CLST;  // entries the survivor list holds
+    fast_cell<1>(tile, Bm, clst, lst, lstCap, c, f, mis, PW, lane, cand, candCount, g);
+}
+
+// ---- k_fast_tma: the same cell search with the tile staged by TMA --------------------------------------------------
+// Persistent warps (no CTA-wide barrier): every warp pulls (frame, cell) work items off a global counter and runs a
+// four-stage software pipeline over them — item j is claimed (atomicAdd) in iteration j-3, its CellDesc is fetched in
+// j-2, its tile is requested in j-1 with ONE cp.async.bulk.tensor (a 3-D box {FAST box width, box height, 1} of the
+// level's u8 tensor {pitch, rows, frames}, landing densely in one of the warp's two tile buffers and completing on that
+// buffer's mbarrier), and it is searched in iteration j.  The box starts at the cell's own pixel column (TMA takes
+// element coordinates, so no alignment padding: mis = 0) and replaces ~19 x (LDG + STS + address) instructions per lane
+// of k_fast; the load latency of the next cell hides under the search of the current one.
+// Shared memory per warp: 2 tile buffers + score map (box geometry), corner list, survivor list, 2 mbarriers.
+#ifndef FASTT_WARPS
+#define FASTT_WARPS 8
+#endif
+#ifndef FASTT_MINB
+#define FASTT_MINB 4
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+// One CUtensorMap (128 bytes, 64-byte aligned) per pyramid level.  The maps travel as a __grid_constant__ kernel parameter:
+// a descriptor that merely sits in global memory is read by the TMA unit through its own (non-coherent) path and needs a
+// fence.proxy.tensormap acquire first — without it the kernel raised "illegal instruction" on B200 depending on nothing but
+// the launch's shared-memory size.
+struct alignas(64) FastTmaMaps {
+    unsigned long long m[EAOF_MAX_LEVELS][16];
+};
+
+struct FastTmaArgs {
+    int boxW, boxH;      // box = tile geometry: boxW bytes per row (multiple of 16), boxH rows
+    int tileBytes;       // boxW*boxH rounded up to 256
+    int warpBytes;       // shared memory per warp (multiple of 256)
+    int lstCap;          // survivor-list entries
+    int f0;              // first frame of this launch inside the handle's pyramid buffer (chunked batches)
+    int nItems;          // frames of this launch * cells per frame
+    int* dbg;            // EAOF_TMA_DEBUG builds: host-mapped record per warp of the last request
+};
+
+__global__ void __launch_bounds__(FASTT_WARPS * 32, FASTT_MINB) k_fast_tma(const __grid_constant__ FastTmaMaps maps, const FastTmaArgs A,
+                                                                          const CellDesc* __restrict__ cells,
+                                                                          uint32_t* __restrict__ cand,
+                                                                          uint32_t* __restrict__ candCount,
+                                                                          unsigned int* __restrict__ workCounter,
+                                                                          const __grid_constant__ Geom g) {
+    extern __shared__ __align__(128) uint8_t fastTmaSmem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the dynamic shared memory window is 16-byte aligned by contract; the tile buffers are kept on 256 (see the host sizing)
+    uint8_t* base = fastTmaSmem + ((256u - (smem_u32(fastTmaSmem) & 255u)) & 255u) + (size_t)warp * A.warpBytes;
+    uint32_t* Bm = reinterpret_cast<uint32_t*>(base + 2 * A.tileBytes);
+    uint16_t* clst = reinterpret_cast<uint16_t*>(base + 3 * A.tileBytes);
+    uint16_t* lst = clst + FAST_CLST;
+    const uint32_t bar0 = smem_u32(base + 3 * A.tileBytes + 2 * FAST_CLST + 2 * A.lstCap);  // 8-byte aligned: see host sizing
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int PW = A.boxW >> 2;
+    const int mapWords4 = A.tileBytes >> 4;
+    const int nItems = A.nItems, cpf = g.cellsPerFrame;
+
+    auto claim = [&]() -> int {
+        unsigned v = 0;
+        if (lane == 0) v = atomicAdd(workCounter, 1u);
+        return (int)__shfl_sync(0xffffffffu, v, 0);
+    };
+    auto fetch = [&](int item, int& f, CellDesc& c) {
+        f = item / cpf;
+        c = cells[item - f * cpf];  // one 16-byte load
+    };
+    auto request = [&](const CellDesc& c, int f, int buf) {
+        if (lane == 0) {
+            // this buffer was read (and its head overwritten with NMS survivors) through the generic proxy two iterations
+            // ago: order those accesses before the async-proxy write of the new box
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t bar = bar0 + 8 * buf;
+#ifdef EAOF_TMA_DEBUG
+            if (A.dbg) {
+                int* r = A.dbg + 8 * (blockIdx.x * FASTT_WARPS + warp);
+                r[0] = c.level; r[1] = EAOF_INNER_X0 + c.iniX; r[2] = EAOF_EDGE + c.iniY; r[3] = A.f0 + f;
+                r[4] = (int)smem_u32(base + buf * A.tileBytes); r[5] = (int)bar; r[6] = buf; r[7] += 1;
+                __threadfence_system();
+            }
+#endif
+            mbar_expect_tx(bar, (uint32_t)(A.boxW * A.boxH));
+            tma_load_3d(smem_u32(base + buf * A.tileBytes), &maps.m[c.level][0], EAOF_INNER_X0 + c.iniX, EAOF_EDGE + c.iniY,
+                        A.f0 + f, bar);
+        }
+    };
+
+    // pipeline registers: item claimed (i3), item with descriptor (i2: c2, f2), item with tile in flight (i1: c1, f1)
+    int i1 = claim(), i2 = claim(), i3 = claim();
+    CellDesc c1{}, c2{};
+    int f1 = 0, f2 = 0;
+    if (i1 < nItems) { fetch(i1, f1, c1); request(c1, f1, 0); }
+    if (i2 < nItems) fetch(i2, f2, c2);
+    int buf = 0;
+    uint32_t phases = 0;  // bit b = parity the next wait on buffer b's mbarrier expects
+    while (i1 < nItems) {
+        const CellDesc c = c1;
+        const int f = f1;
+        // advance the pipeline before searching: tile of the next item, descriptor of the one after, claim of the third
+        i1 = i2; c1 = c2; f1 = f2;
+        if (i1 < nItems) request(c1, f1, buf ^ 1);
+        i2 = i3;
+        if (i2 < nItems) fetch(i2, f2, c2);
+        i3 = claim();
+        // score map of this cell
+        for (int i = lane; i < mapWords4; i += 32) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
+        mbar_wait(bar0 + 8 * buf, (phases >> buf) & 1u);
+        phases ^= 1u << buf;
+        __syncwarp();
+        if (c.cw > 6 && c.ch > 6)
+            fast_cell<0>(reinterpret_cast<uint32_t*>(base + buf * A.tileBytes), Bm, clst, lst, A.lstCap, c, f, 0, PW, lane, cand,
+                         candCount, g);
+        __syncwarp();
+        buf ^= 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

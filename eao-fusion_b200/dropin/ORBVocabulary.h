@@ -46,7 +46,6 @@ public:
         if(this->empty())
             return;
         const int n = (int)features.size();
-        eaof_voc* voc = Device(n);
         std::vector<unsigned char> desc(32 * (size_t)(n ? n : 1));
         for(int i = 0; i < n; i++)
             memcpy(&desc[32 * (size_t)i], features[i].ptr<unsigned char>(), 32);
@@ -56,7 +55,11 @@ public:
         std::vector<double> wordVals(n + 1);
         std::vector<int> nodeStart(n + 2);
         {
-            std::unique_lock<std::mutex> lock(mMutex);  // one stream / staging area per vocabulary
+            // Tracking (Frame::ComputeBoW) and LocalMapping / LoopClosing (KeyFrame::ComputeBoW) share the one vocabulary: the
+            // handle lookup — which may destroy and re-create the device copy for a larger frame — and the call that uses the
+            // handle (one stream / staging area per vocabulary) sit under the same lock
+            std::unique_lock<std::mutex> lock(mMutex);
+            eaof_voc* voc = DeviceLocked(n);
             if(eaof_voc_transform(voc, 1, setStart, &desc[0], levelsup, &nWords, &wordIds[0], &wordVals[0], &nNodes,
                                   &nodeIds[0], &nodeStart[0], &featIdx[0]) != EAOF_OK)
                 Throw("eaof_voc_transform");
@@ -72,7 +75,11 @@ public:
     }
 
     /// Hands the loaded tree to the device now (otherwise done by the first transform).
-    void Upload(int maxFeatures = 4096) const { Device(maxFeatures); }
+    void Upload(int maxFeatures = 4096) const
+    {
+        std::unique_lock<std::mutex> lock(mMutex);
+        DeviceLocked(maxFeatures);
+    }
 
 private:
     static void Throw(const char* what)
@@ -89,15 +96,25 @@ private:
         mpVoc = NULL;
     }
 
-    eaof_voc* Device(int nFeatures) const
+    // caller holds mMutex
+    eaof_voc* DeviceLocked(int nFeatures) const
     {
-        std::unique_lock<std::mutex> lock(mMutex);
         if(mpVoc && nFeatures <= mnCap)
             return mpVoc;
+        const int kLibraryMax = 12000;  // eaof_voc_create's max_features limit
+        if(nFeatures > kLibraryMax)
+        {
+            const std::string msg = "ORBVocabulary(eaof): a frame with " + std::to_string(nFeatures) +
+                                    " features exceeds the 12000 a device transform takes (eaof_voc_create max_features)";
+            fprintf(stderr, "%s\n", msg.c_str());
+            throw std::runtime_error(msg);
+        }
         Release();
         int cap = 4096;
         while(cap < nFeatures)
             cap *= 2;
+        if(cap > kLibraryMax)
+            cap = kLibraryMax;
         const size_t n = this->m_nodes.size();
         std::vector<int> childStart(n + 1), childIdx(n ? n - 1 : 0), wordId(n, -1);
         std::vector<unsigned char> desc(32 * n, 0);

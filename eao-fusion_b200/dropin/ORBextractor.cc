@@ -12,6 +12,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "eaof_orb.h"
 
@@ -33,6 +34,143 @@ static int EnvInt(const char* name, int dflt)
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// ---- which GaussianBlur does the OpenCV this file is compiled against compute? ---------------------------------------
+// cv::GaussianBlur(7x7, sigma 2) on 8U is integer arithmetic whose taps and rounding changed between OpenCV versions and
+// builds; the library implements the three known forms (EAOF_BLUR_*).  Instead of trusting
+// a default, the constructor blurs a fixed probe image with the maintainer's own cv::GaussianBlur, evaluates the three
+// integer formulas on the host and selects the one that reproduces it — or throws when none does (an IPP-dispatched
+// build, for instance): descriptors would silently differ from the CPU build otherwise.  $EAOF_BLUR_MODE overrides.
+namespace
+{
+
+int Reflect101(int p, int n)
+{
+    if(n == 1)
+        return 0;
+    while(p < 0 || p >= n)
+        p = p < 0 ? -p : 2*(n - 1) - p;
+    return p;
+}
+
+// the integer 7x7 formula in blur mode `mode` at one pixel; `tie` reports an exact .5 before rounding
+int BlurFormulaAt(const std::vector<unsigned char>& im, int w, int h, int x, int y, int mode, bool* tie)
+{
+    static const int t331[7] = {18, 34, 49, 55, 49, 34, 18}, t4[7] = {18, 34, 48, 56, 48, 34, 18};
+    const int* k = mode == EAOF_BLUR_CV4 ? t4 : t331;
+    int acc = 0;
+    for(int j = 0; j < 7; ++j)
+    {
+        const unsigned char* row = &im[(size_t)Reflect101(y + j - 3, h)*w];
+        int hsum = 0;
+        for(int i = 0; i < 7; ++i)
+            hsum += k[i]*row[Reflect101(x + i - 3, w)];
+        acc += k[j]*hsum;
+    }
+    const int rem = acc & 0xffff;
+    if(tie)
+        *tie = rem == 32768;
+    int q;
+    if(mode == EAOF_BLUR_CV331_SSE2 && x < (w & ~3))
+    {
+        q = acc >> 16;
+        q += (rem > 32768) || (rem == 32768 && (q & 1));  // cvtps2dq: round half to even
+    }
+    else
+        q = (acc + 32768) >> 16;
+    return q > 255 ? 255 : q;
+}
+
+// 64x64 probe: LCG noise, a saturated block, and 7x7 patches searched so that the 3.3.1 taps land exactly on .5 with an
+// even integer part — the only place where the two 3.3.1 roundings differ
+void MakeBlurProbe(std::vector<unsigned char>& im, int w, int h)
+{
+    im.assign((size_t)w*h, 0);
+    unsigned s = 12345u;
+    for(size_t i = 0; i < im.size(); ++i)
+    {
+        s = s*1664525u + 1013904223u;
+        im[i] = (unsigned char)(s >> 24);
+    }
+    for(int y = 40; y < 52; ++y)
+        for(int x = 4; x < 16; ++x)
+            im[(size_t)y*w + x] = 255;
+    int placed = 0;
+    for(int attempt = 0; attempt < 4000000 && placed < 6; ++attempt)
+    {
+        const int cx = 8 + 9*(placed % 5), cy = 8 + 9*(placed / 5);  // patch centres, 9 px apart: the 7x7 supports are disjoint
+        unsigned char patch[49];
+        for(int i = 0; i < 49; ++i)
+        {
+            s = s*1664525u + 1013904223u;
+            patch[i] = (unsigned char)(s >> 24);
+        }
+        for(int j = 0; j < 7; ++j)
+            for(int i = 0; i < 7; ++i)
+                im[(size_t)(cy + j - 3)*w + cx + i - 3] = patch[7*j + i];
+        bool tie = false;
+        const int q = BlurFormulaAt(im, w, h, cx, cy, EAOF_BLUR_CV331, &tie);
+        if(tie && ((q - 1) & 1) == 0)  // half-up gave q: the integer part q-1 is even, so half-to-even gives q-1
+            ++placed;
+    }
+}
+
+int ProbeBlurMode()
+{
+    const int w = 64, h = 64;
+    std::vector<unsigned char> probe;
+    MakeBlurProbe(probe, w, h);
+    cv::Mat src(h, w, CV_8UC1), dst;
+    for(int y = 0; y < h; ++y)
+        memcpy(src.ptr(y), &probe[(size_t)y*w], w);
+    cv::GaussianBlur(src, dst, cv::Size(7, 7), 2, 2, cv::BORDER_REFLECT_101);
+    const int order[3] = {EAOF_BLUR_CV331, EAOF_BLUR_CV331_SSE2, EAOF_BLUR_CV4};
+    for(int m = 0; m < 3; ++m)
+    {
+        bool same = true;
+        for(int y = 0; y < h && same; ++y)
+            for(int x = 0; x < w; ++x)
+                if(dst.ptr(y)[x] != BlurFormulaAt(probe, w, h, x, y, order[m], NULL))
+                {
+                    same = false;
+                    break;
+                }
+        if(same)
+            return order[m];
+    }
+    return -1;
+}
+
+}  // namespace
+
+#if defined(CV_VERSION_MAJOR) || defined(CV_MAJOR_VERSION)
+// The colour entry points of the library (eaof_orb_extract_batch_color, include/eaof_orb.h) take the integer formula of
+// cv::cvtColor(BGR2GRAY) explicitly as well; this probe tells a caller which one its OpenCV computes (-1: neither).
+// Compiled only against a real OpenCV (the test shim of this repository has no 3-channel Mat).
+int ORBextractor::ProbeGrayMode()
+{
+    cv::Mat bgr(16, 256, CV_8UC3), gray;
+    unsigned s = 777u;
+    for(int y = 0; y < bgr.rows; ++y)
+        for(int x = 0; x < bgr.cols*3; ++x)
+        {
+            s = s*1664525u + 1013904223u;
+            bgr.ptr(y)[x] = (unsigned char)(s >> 24);
+        }
+    cv::cvtColor(bgr, gray, cv::COLOR_BGR2GRAY);
+    bool ok14 = true, ok15 = true;
+    for(int y = 0; y < bgr.rows; ++y)
+        for(int x = 0; x < bgr.cols; ++x)
+        {
+            const unsigned char* p = bgr.ptr(y) + 3*x;
+            ok14 = ok14 && gray.ptr(y)[x] == ((p[0]*1868 + p[1]*9617 + p[2]*4899 + (1 << 13)) >> 14);
+            ok15 = ok15 && gray.ptr(y)[x] == ((p[0]*3735 + p[1]*19235 + p[2]*9798 + (1 << 14)) >> 15);
+        }
+    return ok14 ? EAOF_GRAY_CV331 : ok15 ? EAOF_GRAY_CV4 : -1;
+}
+#else
+int ORBextractor::ProbeGrayMode() { return -1; }
+#endif
+
 ORBextractor::ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
 {
     mSetup.features = nfeatures;
@@ -43,7 +181,19 @@ ORBextractor::ORBextractor(int nfeatures, float scaleFactor, int nlevels, int in
     mGpu.ctx = NULL;
     mGpu.width = mGpu.height = 0;
     mGpu.device = EnvInt("EAOF_DEVICE", 0);
-    mGpu.blurMode = EnvInt("EAOF_BLUR_MODE", EAOF_BLUR_CV331);
+    mGpu.blurMode = EnvInt("EAOF_BLUR_MODE", -1);
+    if(mGpu.blurMode < 0)
+    {
+        mGpu.blurMode = ProbeBlurMode();
+        if(mGpu.blurMode < 0)
+        {
+            const std::string msg = "ORBextractor(eaof): cv::GaussianBlur(7x7, sigma 2) of this OpenCV build matches none of the "
+                                    "integer formulas the library implements (EAOF_BLUR_CV331 / _CV331_SSE2 / _CV4); set "
+                                    "EAOF_BLUR_MODE to accept a documented deviation";
+            fprintf(stderr, "%s\n", msg.c_str());
+            throw std::runtime_error(msg);
+        }
+    }
     mGpu.downloadPyramid = EnvInt("EAOF_PYRAMID", 1) != 0;
 
     // The getters must answer before the first frame, so the scale tables are restated here with the arithmetic of

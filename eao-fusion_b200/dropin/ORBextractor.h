@@ -8,8 +8,9 @@
  * C ABI of include/eaof_orb.h; there is no CPU path: when the library cannot reach a CUDA device, the first frame throws.
  *
  * Not here, deliberately: class ExtractorNode and the Compute* / DistributeOctTree members of the reference header (they
- * are the implementation being replaced; nothing outside ORBextractor.cc names them).  Added: four knobs that default to
- * the reference behaviour (SetDevice, SetBlurMode, SetPyramidDownload, Handle).
+ * are the implementation being replaced; nothing outside ORBextractor.cc names them).  Added: knobs that default to
+ * the reference behaviour (SetDevice, SetBlurMode, SetPyramidDownload, Handle).  The blur arithmetic is selected by probing
+ * the cv::GaussianBlur of the OpenCV this file is compiled against (see ORBextractor.cc).
  */
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
@@ -47,7 +48,10 @@ public:
 
     // ---- not in the reference; the defaults reproduce it
     void SetDevice(int cudaDevice);      ///< before the first frame; default 0 or $EAOF_DEVICE
-    void SetBlurMode(int eaofBlurMode);  ///< EAOF_BLUR_*; default the OpenCV 3.3.1 taps or $EAOF_BLUR_MODE
+    void SetBlurMode(int eaofBlurMode);  ///< EAOF_BLUR_*; default: probed from this build's cv::GaussianBlur, or $EAOF_BLUR_MODE
+    int BlurMode() const { return mGpu.blurMode; }
+    /// EAOF_GRAY_* that reproduces this build's cv::cvtColor(BGR2GRAY) (-1: neither), for the colour entry points
+    static int ProbeGrayMode();
     void SetPyramidDownload(bool on);    ///< off: mvImagePyramid is not copied back (only stereo reads it); $EAOF_PYRAMID=0
     /// Library handle that holds the last frame on the device (NULL before the first frame): what the device-side
     /// Frame helpers take (eaof_orb_stereo_from_rgbd, eaof_stereo_matches, eaof_voc_transform_orb_device, ...).

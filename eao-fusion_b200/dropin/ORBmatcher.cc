@@ -16,6 +16,9 @@
  *   Fuse(KeyFrame*, const vector<MapPoint*>&, th)                        (:825-961)
  *   Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)                   (:963-1100)
  *   SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)             (:1102-1326)
+ *   CheckDistEpipolarLine (:140-157) and ComputeThreeMaxima (:1603-1644): the two protected helpers.  Their work happens
+ *   inside the kernels (eaof_match_triangulation's epipolar gate, the rotation-histogram pruning of every matcher); the
+ *   host definitions at the end of this file exist so that the class declared in include/ORBmatcher.h links completely.
  * i.e. every definition of the reference's ORBmatcher.cc: a maintainer replaces that file by this one in the build
  * (INTEGRATION.md §3).  Every method marshals the fields the reference loop reads into plain arrays, calls the
  * library, and applies the result to the host objects exactly where the reference does (the map mutations of Fuse run
@@ -66,6 +69,11 @@ struct TlsMatcher
     ~TlsMatcher() { if(h) eaof_matcher_destroy(h); }
 };
 
+// Map-side searches (local map in SearchByProjection(F, vpMapPoints), loop map points in Fuse / SearchByProjection(KF, Scw))
+// can hold far more points than a matcher workspace row (65535): invalid queries are dropped before upload and the valid
+// ones go through the library in chunks of this many, in order.
+const size_t kQueryChunk = 32768;
+
 eaof_matcher* Matcher(size_t nFeatures)
 {
     static thread_local TlsMatcher tls;
@@ -76,6 +84,8 @@ eaof_matcher* Matcher(size_t nFeatures)
             eaof_matcher_destroy(tls.h);
             tls.h = NULL;
         }
+        if(nFeatures > 65535)  // callers chunk their query lists (kQueryChunk); frame features never get near this
+            Throw("more than 65535 features in one frame or query chunk");
         int cap = 4096;
         while(cap < (int)nFeatures)
             cap *= 2;
@@ -158,49 +168,63 @@ float ORBmatcher::RadiusByViewingCos(const float& viewCos)
 
 int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th)
 {
-    const size_t nMP = vpMapPoints.size(), nF = (size_t)F.N;
-    if(nMP == 0 || nF == 0)
+    const size_t nAll = vpMapPoints.size(), nF = (size_t)F.N;
+    if(nAll == 0 || nF == 0)
         return 0;
     const bool bFactor = th != 1.0;
-    vector<unsigned char> valid(nMP, 0), obs(nMP, 0), qdesc(32 * nMP);
+    // only the points the reference's loop does not skip (:54-58) are uploaded, in their order
+    vector<size_t> orig;
+    orig.reserve(nAll);
+    for(size_t i = 0; i < nAll; i++)
+        if(vpMapPoints[i]->mbTrackInView && !vpMapPoints[i]->isBad())
+            orig.push_back(i);
+    const size_t nMP = orig.size();
+    if(nMP == 0)
+        return 0;
+    vector<unsigned char> obs(nMP, 0), qdesc(32 * nMP);
     vector<float> u(nMP, 0.f), v(nMP, 0.f), radius(nMP, 0.f), ur(nMP, 0.f);
     vector<int> minL(nMP, 0), maxL(nMP, 0);
-    for(size_t i = 0; i < nMP; i++)
+    for(size_t j = 0; j < nMP; j++)
     {
-        MapPoint* pMP = vpMapPoints[i];
-        if(!pMP->mbTrackInView || pMP->isBad())
-            continue;
-        valid[i] = 1;
+        MapPoint* pMP = vpMapPoints[orig[j]];
         const int nPredictedLevel = pMP->mnTrackScaleLevel;
         float r = RadiusByViewingCos(pMP->mTrackViewCos);
         if(bFactor)
             r *= th;
-        u[i] = pMP->mTrackProjX;
-        v[i] = pMP->mTrackProjY;
-        ur[i] = pMP->mTrackProjXR;
-        radius[i] = r * F.mvScaleFactors[nPredictedLevel];
-        minL[i] = nPredictedLevel - 1;
-        maxL[i] = nPredictedLevel;
-        obs[i] = pMP->Observations() > 0;
+        u[j] = pMP->mTrackProjX;
+        v[j] = pMP->mTrackProjY;
+        ur[j] = pMP->mTrackProjXR;
+        radius[j] = r * F.mvScaleFactors[nPredictedLevel];
+        minL[j] = nPredictedLevel - 1;
+        maxL[j] = nPredictedLevel;
+        obs[j] = pMP->Observations() > 0;
         const cv::Mat d = pMP->GetDescriptor();
-        memcpy(&qdesc[32 * i], d.ptr<unsigned char>(), 32);
+        memcpy(&qdesc[32 * j], d.ptr<unsigned char>(), 32);
     }
     KeyArrays keys(F.mvKeysUn);
     vector<unsigned char> tdesc = Rows(F.mDescriptors, nF), taken(nF, 0);
-    for(size_t k = 0; k < nF; k++)
-        taken[k] = F.mvpMapPoints[k] && F.mvpMapPoints[k]->Observations() > 0;
     vector<int> match(nF, -1);
-    int n = 0;
-    if(eaof_match_windows(Matcher(max(nF, nMP)), EAOF_WIN_RATIO_SAME_LEVEL, (int)nF, P(keys.x), P(keys.y), P(keys.octave), NULL,
-                          P(tdesc), P(F.mvuRight), P(taken), F.mnMinX, F.mnMaxX, F.mnMinY, F.mnMaxY,
-                          F.mfGridElementWidthInv, F.mfGridElementHeightInv, (int)nMP, P(valid), P(u), P(v), P(radius),
-                          P(minL), P(maxL), P(ur), NULL, P(qdesc), P(obs), TH_HIGH, mfNNratio, 0, 0, P(match), NULL,
-                          &n) != EAOF_OK)
-        Throw("eaof_match_windows");
-    for(size_t k = 0; k < nF; k++)
-        if(match[k] >= 0)
-            F.mvpMapPoints[k] = vpMapPoints[match[k]];
-    return n;
+    int nTotal = 0;
+    // the greedy exclusion only looks at what earlier points left in F.mvpMapPoints (:78-80), so a chunk of later points
+    // sees exactly the state the earlier chunks produced
+    for(size_t c0 = 0; c0 < nMP; c0 += kQueryChunk)
+    {
+        const size_t nc = min(kQueryChunk, nMP - c0);
+        for(size_t k = 0; k < nF; k++)
+            taken[k] = F.mvpMapPoints[k] && F.mvpMapPoints[k]->Observations() > 0;
+        int n = 0;
+        if(eaof_match_windows(Matcher(max(nF, nc)), EAOF_WIN_RATIO_SAME_LEVEL, (int)nF, P(keys.x), P(keys.y), P(keys.octave), NULL,
+                              P(tdesc), P(F.mvuRight), P(taken), F.mnMinX, F.mnMaxX, F.mnMinY, F.mnMaxY,
+                              F.mfGridElementWidthInv, F.mfGridElementHeightInv, (int)nc, NULL, &u[c0], &v[c0], &radius[c0],
+                              &minL[c0], &maxL[c0], &ur[c0], NULL, &qdesc[32 * c0], &obs[c0], TH_HIGH, mfNNratio, 0, 0, P(match),
+                              NULL, &n) != EAOF_OK)
+            Throw("eaof_match_windows");
+        for(size_t k = 0; k < nF; k++)
+            if(match[k] >= 0)
+                F.mvpMapPoints[k] = vpMapPoints[orig[c0 + match[k]]];
+        nTotal += n;
+    }
+    return nTotal;
 }
 
 int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
@@ -481,6 +505,24 @@ struct Projected
         const cv::Mat d = pMP->GetDescriptor();
         memcpy(&desc[32 * i], d.ptr<unsigned char>(), 32);
     }
+    // the valid entries only, in order (orig[j] = index in this list): what goes to the library
+    void Compact(Projected& out, vector<size_t>& orig) const
+    {
+        orig.clear();
+        for(size_t i = 0; i < valid.size(); i++)
+            if(valid[i])
+                orig.push_back(i);
+        const size_t n = orig.size();
+        out = Projected(n);
+        for(size_t j = 0; j < n; j++)
+        {
+            const size_t i = orig[j];
+            out.valid[j] = 1;
+            out.u[j] = u[i]; out.v[j] = v[i]; out.ur[j] = ur[i]; out.radius[j] = radius[i];
+            out.minL[j] = minL[i]; out.maxL[j] = maxL[i];
+            memcpy(&out.desc[32 * j], &desc[32 * i], 32);
+        }
+    }
 };
 
 // Points given in the world frame, keyframe pose (Rcw, tcw, Ow): shared by SearchByProjection(KF,Scw), Fuse and Fuse(Scw)
@@ -520,22 +562,37 @@ struct KeyFrameArrays
     explicit KeyFrameArrays(KeyFrame* pKF) : keys(pKF->mvKeysUn), desc(Rows(pKF->mDescriptors, pKF->mvKeysUn.size())) {}
 };
 
-// best keyframe feature per projected point, no exclusion between points
-void SearchIndependent(KeyFrame* pKF, const Projected& q, int gate, int thAccept, vector<int>& match)
+// best keyframe feature per projected point, no exclusion between points: the valid points are compacted and go through
+// the library in chunks (a loop-closure map can hold more points than one workspace row)
+void SearchIndependent(KeyFrame* pKF, const Projected& qAll, int gate, int thAccept, vector<int>& match)
 {
-    const size_t nT = pKF->mvKeysUn.size(), nQ = q.valid.size();
-    match.assign(nQ, -1);
-    if(nT == 0 || nQ == 0)
+    const size_t nT = pKF->mvKeysUn.size();
+    match.assign(qAll.valid.size(), -1);
+    if(nT == 0 || qAll.valid.empty())
+        return;
+    Projected q(0);
+    vector<size_t> orig;
+    qAll.Compact(q, orig);
+    const size_t nQ = orig.size();
+    if(nQ == 0)
         return;
     KeyFrameArrays t(pKF);
-    int n = 0;
     const bool chi2 = gate == EAOF_GATE_FUSE_CHI2;
-    if(eaof_match_windows_independent(Matcher(max(nT, nQ)), gate, (int)nT, P(t.keys.x), P(t.keys.y), P(t.keys.octave), P(t.desc),
-                                      chi2 ? P(pKF->mvuRight) : NULL, pKF->mnMinX, pKF->mnMinY, pKF->mfGridElementWidthInv,
-                                      pKF->mfGridElementHeightInv, chi2 ? P(pKF->mvInvLevelSigma2) : NULL,
-                                      (int)pKF->mvScaleFactors.size(), (int)nQ, P(q.valid), P(q.u), P(q.v), P(q.radius), P(q.minL),
-                                      P(q.maxL), P(q.ur), P(q.desc), thAccept, P(match), NULL, &n) != EAOF_OK)
-        Throw("eaof_match_windows_independent");
+    vector<int> part(min(nQ, kQueryChunk), -1);
+    for(size_t c0 = 0; c0 < nQ; c0 += kQueryChunk)
+    {
+        const size_t nc = min(kQueryChunk, nQ - c0);
+        int n = 0;
+        if(eaof_match_windows_independent(Matcher(max(nT, nc)), gate, (int)nT, P(t.keys.x), P(t.keys.y), P(t.keys.octave), P(t.desc),
+                                          chi2 ? P(pKF->mvuRight) : NULL, pKF->mnMinX, pKF->mnMinY, pKF->mfGridElementWidthInv,
+                                          pKF->mfGridElementHeightInv, chi2 ? P(pKF->mvInvLevelSigma2) : NULL,
+                                          (int)pKF->mvScaleFactors.size(), (int)nc, NULL, &q.u[c0], &q.v[c0], &q.radius[c0],
+                                          &q.minL[c0], &q.maxL[c0], &q.ur[c0], &q.desc[32 * c0], thAccept, P(part), NULL,
+                                          &n) != EAOF_OK)
+            Throw("eaof_match_windows_independent");
+        for(size_t j = 0; j < nc; j++)
+            match[orig[c0 + j]] = part[j];
+    }
 }
 
 void DecomposeSim3(const cv::Mat& Scw, cv::Mat& Rcw, cv::Mat& tcw, cv::Mat& Ow)
@@ -570,22 +627,36 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapP
         if(ProjectWorld(pKF, pMP, Rcw, tcw, Ow, th, 0.f, u, v, ur, radius, level))
             q.Set(i, u, v, ur, radius, level, pMP);
     }
+    Projected qc(0);
+    vector<size_t> orig;
+    q.Compact(qc, orig);
+    const size_t nV = orig.size();
+    if(nV == 0)
+        return 0;
     KeyFrameArrays t(pKF);
     vector<unsigned char> taken(nT, 0);
-    for(size_t k = 0; k < nT; k++)
-        taken[k] = vpMatched[k] != NULL;
     vector<int> match(nT, -1);
-    int n = 0;
-    // a matched feature is closed for the later points (:375-376, :396): the greedy window search
-    if(eaof_match_windows(Matcher(max(nT, nQ)), EAOF_WIN_BEST, (int)nT, P(t.keys.x), P(t.keys.y), P(t.keys.octave), NULL, P(t.desc),
-                          NULL, P(taken), pKF->mnMinX, pKF->mnMaxX, pKF->mnMinY, pKF->mnMaxY, pKF->mfGridElementWidthInv,
-                          pKF->mfGridElementHeightInv, (int)nQ, P(q.valid), P(q.u), P(q.v), P(q.radius), P(q.minL), P(q.maxL), NULL,
-                          NULL, P(q.desc), NULL, TH_LOW, mfNNratio, 0, 0, P(match), NULL, &n) != EAOF_OK)
-        Throw("eaof_match_windows");
-    for(size_t k = 0; k < nT; k++)
-        if(match[k] >= 0)
-            vpMatched[k] = vpPoints[match[k]];
-    return n;
+    int nTotal = 0;
+    // a matched feature is closed for the later points (:375-376, :396): the greedy window search; later chunks see what
+    // the earlier ones left in vpMatched
+    for(size_t c0 = 0; c0 < nV; c0 += kQueryChunk)
+    {
+        const size_t nc = min(kQueryChunk, nV - c0);
+        for(size_t k = 0; k < nT; k++)
+            taken[k] = vpMatched[k] != NULL;
+        int n = 0;
+        if(eaof_match_windows(Matcher(max(nT, nc)), EAOF_WIN_BEST, (int)nT, P(t.keys.x), P(t.keys.y), P(t.keys.octave), NULL, P(t.desc),
+                              NULL, P(taken), pKF->mnMinX, pKF->mnMaxX, pKF->mnMinY, pKF->mnMaxY, pKF->mfGridElementWidthInv,
+                              pKF->mfGridElementHeightInv, (int)nc, NULL, &qc.u[c0], &qc.v[c0], &qc.radius[c0], &qc.minL[c0],
+                              &qc.maxL[c0], NULL, NULL, &qc.desc[32 * c0], NULL, TH_LOW, mfNNratio, 0, 0, P(match), NULL,
+                              &n) != EAOF_OK)
+            Throw("eaof_match_windows");
+        for(size_t k = 0; k < nT; k++)
+            if(match[k] >= 0)
+                vpMatched[k] = vpPoints[orig[c0 + match[k]]];
+        nTotal += n;
+    }
+    return nTotal;
 }
 
 int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th)
@@ -757,6 +828,53 @@ int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& 
         }
     }
     return nFound;
+}
+
+// The two protected helpers of the class.  No method of this file calls them (the kernels apply both rules on the device),
+// they are defined for link completeness with the reference's header.
+bool ORBmatcher::CheckDistEpipolarLine(const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat& F12, const KeyFrame* pKF2)
+{
+    // l2 = kp1^T * F12 (a, b, c); squared point-line distance of kp2 against the chi-square bound at kp2's level
+    const float a = kp1.pt.x * F12.at<float>(0, 0) + kp1.pt.y * F12.at<float>(1, 0) + F12.at<float>(2, 0);
+    const float b = kp1.pt.x * F12.at<float>(0, 1) + kp1.pt.y * F12.at<float>(1, 1) + F12.at<float>(2, 1);
+    const float c = kp1.pt.x * F12.at<float>(0, 2) + kp1.pt.y * F12.at<float>(1, 2) + F12.at<float>(2, 2);
+    const float num = a * kp2.pt.x + b * kp2.pt.y + c;
+    const float den = a * a + b * b;
+    if(den == 0)
+        return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * pKF2->mvLevelSigma2[kp2.octave];
+}
+
+void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3)
+{
+    int best[3] = {0, 0, 0};
+    int where[3] = {-1, -1, -1};
+    for(int i = 0; i < L; i++)
+    {
+        const int s = (int)histo[i].size();
+        int slot = s > best[0] ? 0 : s > best[1] ? 1 : s > best[2] ? 2 : 3;  // strictly larger: earlier bins win ties
+        for(int k = 2; k > slot; k--)
+        {
+            best[k] = best[k - 1];
+            where[k] = where[k - 1];
+        }
+        if(slot < 3)
+        {
+            best[slot] = s;
+            where[slot] = i;
+        }
+    }
+    ind1 = where[0];
+    ind2 = where[1];
+    ind3 = where[2];
+    if(best[1] < 0.1f * (float)best[0])
+    {
+        ind2 = -1;
+        ind3 = -1;
+    }
+    else if(best[2] < 0.1f * (float)best[0])
+        ind3 = -1;
 }
 
 } //namespace ORB_SLAM

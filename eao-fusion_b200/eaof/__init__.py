@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libeaof_orb.so")
+LIB_PATH = os.environ.get("EAOF_LIB_PATH") or os.path.join(PKG_DIR, "lib", "libeaof_orb.so")  # override: build-variant experiments
 
 BLUR_CV331, BLUR_CV4, BLUR_CV331_SSE2 = 0, 1, 2
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),

@@ -9,8 +9,9 @@
 #include "ORBextractor.h"  // the drop-in header
 
 namespace cv {
-int eaof_shim_blur_mode() { return 0; }
-void eaof_shim_set_blur_mode(int) {}
+static int g_shim_blur_mode = 0;  // which of the three blur arithmetics the stand-in cv::GaussianBlur computes
+int eaof_shim_blur_mode() { return g_shim_blur_mode; }
+void eaof_shim_set_blur_mode(int m) { g_shim_blur_mode = m; }
 }  // namespace cv
 
 extern "C" {
@@ -24,6 +25,8 @@ void* dropin_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST
 }
 void dropin_destroy(void* h) { delete (ORB_SLAM2::ORBextractor*)h; }
 void dropin_set_blur_mode(void* h, int m) { ((ORB_SLAM2::ORBextractor*)h)->SetBlurMode(m); }
+int dropin_blur_mode(void* h) { return ((ORB_SLAM2::ORBextractor*)h)->BlurMode(); }
+void dropin_shim_set_blur_mode(int m) { cv::eaof_shim_set_blur_mode(m); }  // the "OpenCV build" the next constructor probes
 void dropin_set_pyramid(void* h, int on) { ((ORB_SLAM2::ORBextractor*)h)->SetPyramidDownload(on != 0); }
 
 void dropin_tables(void* h, float* sf, float* isf, float* s2, float* is2, int* levels, float* scale) {

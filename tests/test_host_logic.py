@@ -370,3 +370,35 @@ def test_workload_sequences_shard_exactly():
             assert np.array_equal(workload.Sequence(96, 80).frames(hb, he), whole[hb:he])
     d = [workload.frame_digest(np.zeros(3, "<f4"), np.zeros((3, 32), np.uint8)), workload.pair_digest(np.arange(4))]
     assert workload.combine(d) == workload.combine(list(d)) and len(workload.combine(d)) == 64
+
+
+def test_dropin_selects_the_blur_arithmetic_of_its_opencv():
+    """dropin/ORBextractor.cc probes the cv::GaussianBlur it is compiled against (here: the shim, switchable between the three
+    known arithmetics) and must select the matching EAOF_BLUR_* mode at construction — no GPU involved."""
+    import time
+    import dropin
+    if not os.path.exists(dropin.SO):
+        import __graft_entry__ as g
+        g.build()
+    L = dropin.lib()
+    L.dropin_blur_mode.argtypes = [ctypes.c_void_p]
+    old = os.environ.pop("EAOF_BLUR_MODE", None)
+    try:
+        for mode in (0, 1, 2):
+            L.dropin_shim_set_blur_mode(mode)
+            t0 = time.perf_counter()
+            h = L.dropin_create(1000, 1.2, 8, 20, 7)
+            dt = time.perf_counter() - t0
+            assert h and L.dropin_blur_mode(h) == mode
+            assert dt < 2.0, f"the probe took {dt:.2f} s"
+            L.dropin_destroy(h)
+        os.environ["EAOF_BLUR_MODE"] = "1"   # the override wins over the probe
+        L.dropin_shim_set_blur_mode(0)
+        h = L.dropin_create(1000, 1.2, 8, 20, 7)
+        assert L.dropin_blur_mode(h) == 1
+        L.dropin_destroy(h)
+    finally:
+        os.environ.pop("EAOF_BLUR_MODE", None)
+        if old is not None:
+            os.environ["EAOF_BLUR_MODE"] = old
+        L.dropin_shim_set_blur_mode(0)

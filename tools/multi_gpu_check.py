@@ -53,8 +53,8 @@ def main():
     if own:
         pl = np.array([a - hb for a, _ in own], np.int32)
         pc = np.array([c - hb for _, c in own], np.int32)
-        pm = torch.empty((len(own), ex.cap), dtype=torch.int32, device="cuda")
-        pd = torch.empty((len(own), ex.cap), dtype=torch.int32, device="cuda")
+        pm = torch.full((len(own), ex.cap), -1, dtype=torch.int32, device="cuda")  # rows are written up to the frame's count
+        pd = torch.full((len(own), ex.cap), -1, dtype=torch.int32, device="cuda")
         pn = torch.zeros(len(own), dtype=torch.int32, device="cuda")
         mt.projection_batch_device(ex, pl, pc, np.full(len(own), -2, np.float32), np.full(len(own), -1, np.float32), 15.0,
                                    pm.data_ptr(), pd.data_ptr(), pn.data_ptr())
@@ -94,8 +94,8 @@ def main():
         ok = bool(torch.equal(full_m, m1)) and bool(torch.equal(full_n, nm1))
         # consecutive-frame matching, single GPU over the whole sequence
         allp = shard.consecutive_pairs(0, n_frames, n_frames)
-        pm1 = torch.empty((len(allp), ex1.cap), dtype=torch.int32, device="cuda")
-        pd1 = torch.empty((len(allp), ex1.cap), dtype=torch.int32, device="cuda")
+        pm1 = torch.full((len(allp), ex1.cap), -1, dtype=torch.int32, device="cuda")
+        pd1 = torch.full((len(allp), ex1.cap), -1, dtype=torch.int32, device="cuda")
         pn1 = torch.zeros(len(allp), dtype=torch.int32, device="cuda")
         mt1 = eaof.ORBmatcher(0.9, True, max_features=ex1.cap, max_pairs=len(allp), device=local)
         mt1.projection_batch_device(ex1, np.array([a for a, _ in allp], np.int32), np.array([c for _, c in allp], np.int32),
