@@ -48,6 +48,11 @@ inline short sat_short(int v) { return (short)(v < -32768 ? -32768 : v > 32767 ?
 static int* g_tmaDbgHost = nullptr;
 extern "C" int* eaof_debug_tma_records() { return g_tmaDbgHost; }
 #endif
+// Which FAST kernel a handle uses unless $EAOF_FAST_TMA says otherwise (0 LDG-staged, 1 persistent TMA, 2 one-shot TMA);
+// the measurements behind the default are in DESIGN.md §4.
+#ifndef EAOF_FAST_TMA_DEFAULT
+#define EAOF_FAST_TMA_DEFAULT 0
+#endif
 struct eaof_orb {
     eaof_orb_params p{};
     int device = 0;
@@ -108,7 +113,7 @@ struct eaof_orb {
     eaof::FastTmaMaps fastMaps{};
     unsigned int* dFastCtr = nullptr;   // [kMaxChunks]
     eaof::FastTmaArgs fastT{};
-    bool fastTma = false;
+    int fastTma = 0;  // 0: k_fast (LDG-staged tile), 1: k_fast_tma (persistent, double-buffered TMA), 2: k_fast_tma1
     int fastTmaGrid = 0;
     size_t fastTmaSmem = 0;
     bool profiling = false;
@@ -362,7 +367,14 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         ++launches;
         CK(cudaEventRecord(c->evBlur, sb));
     }
-    if (g.cellsPerFrame > 0 && c->fastTma) {
+    if (g.cellsPerFrame > 0 && c->fastTma == 2) {
+        // one cell per one-warp CTA, tile by TMA, no persistent scheduling
+        eaof::FastTmaArgs A = c->fastT;
+        A.f0 = f0;
+        const size_t smem = (size_t)2 * A.tileBytes + 2 * FAST_CLST + 2 * A.lstCap + 16 + 128;
+        eaof::k_fast_tma1<<<dim3(g.cellsPerFrame, n), 32, smem, s>>>(c->fastMaps, A, c->dCells, dCand, dCandCount, g);
+        ++launches;
+    } else if (g.cellsPerFrame > 0 && c->fastTma) {
         // persistent warps pulling (frame, cell) items off a counter; the tile of every item arrives by TMA
         unsigned int* ctr = c->dFastCtr + (chunkIdx % eaof_orb::kMaxChunks);
         CK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), s));
@@ -553,22 +565,16 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
         // k_fast_tma: tensor maps (CU_TENSOR_MAP_DATA_TYPE_UINT8, rank 3: byte column, row, frame) and shared-memory shape.
         // EAOF_FAST_TMA=0 keeps the LDG-staged k_fast (A/B measurements).
         const char* e = getenv("EAOF_FAST_TMA");
-        const bool want = !(e && *e == '0');
+        const int want = e && *e ? atoi(e) : EAOF_FAST_TMA_DEFAULT;
         int maxCw = 16, maxCh = 8;
         for (const CellDesc& cd : cells) { maxCw = std::max<int>(maxCw, cd.cw); maxCh = std::max<int>(maxCh, cd.ch); }
         eaof::FastTmaArgs& T = c->fastT;
-        T.boxW = (maxCw + 15) & ~15;
+        T.boxW = (maxCw + 15 + 15) & ~15;  // the box starts on a 16-byte column (TMA rule), up to 15 bytes left of the cell
         T.boxH = (maxCh + 7) & ~7;
-        if (const char* v = getenv("EAOF_TMA_BOXW")) T.boxW = std::max(T.boxW, atoi(v));  // experiment knobs
-        if (const char* v = getenv("EAOF_TMA_BOXH")) T.boxH = std::max(T.boxH, atoi(v));
-        // Tile buffers are kept 256-byte aligned: with 128 (the documented minimum for cp.async.bulk.tensor destinations) the
-        // 48 x 40 box of the 640x480 geometry raised "illegal instruction" on B200 whenever a buffer sat on an odd multiple
-        // of 128 (measured: every layout with all destinations on 256 passes, every one with a 128-only destination fails).
-        T.tileBytes = (T.boxW * T.boxH + 255) & ~255;
+        T.tileBytes = (T.boxW * T.boxH + 127) & ~127;
         T.lstCap = 248;  // phase (A) refills the list in rounds of <= 128 entries
-        T.warpBytes = (3 * T.tileBytes + 2 * FAST_CLST + 2 * T.lstCap + 16 + 255) & ~255;
-        c->fastTmaSmem = (size_t)FASTT_WARPS * T.warpBytes + 256;
-        if (const char* v = getenv("EAOF_TMA_PAD")) c->fastTmaSmem += atoi(v);  // experiment knob: fewer resident CTAs
+        T.warpBytes = (3 * T.tileBytes + 2 * FAST_CLST + 2 * T.lstCap + 16 + 127) & ~127;
+        c->fastTmaSmem = (size_t)FASTT_WARPS * T.warpBytes + 128;
         if (want && !cells.empty() && T.boxW <= 256 && T.boxH <= 256 && (c->fastTmaSmem + 1024) * FASTT_MINB <= 227 * 1024) {
             typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -608,12 +614,12 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
             int sms = 0;
             CKD(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
             c->fastTmaGrid = sms * FASTT_MINB;
-            if (const char* v = getenv("EAOF_TMA_GRID")) c->fastTmaGrid = atoi(v);  // experiment knob
             static std::mutex muT;
             std::lock_guard<std::mutex> lk(muT);
             CKD(cudaFuncSetAttribute(eaof::k_fast_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CKD(cudaFuncSetAttribute(eaof::k_fast_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            c->fastTma = true;
+            CKD(cudaFuncSetAttribute(eaof::k_fast_tma1, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            c->fastTma = want;
 #ifdef EAOF_TMA_DEBUG
             {
                 int* h = nullptr;

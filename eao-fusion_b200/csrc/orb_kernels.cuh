@@ -753,15 +753,18 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
 // four-stage software pipeline over them — item j is claimed (atomicAdd) in iteration j-3, its CellDesc is fetched in
 // j-2, its tile is requested in j-1 with ONE cp.async.bulk.tensor (a 3-D box {FAST box width, box height, 1} of the
 // level's u8 tensor {pitch, rows, frames}, landing densely in one of the warp's two tile buffers and completing on that
-// buffer's mbarrier), and it is searched in iteration j.  The box starts at the cell's own pixel column (TMA takes
-// element coordinates, so no alignment padding: mis = 0) and replaces ~19 x (LDG + STS + address) instructions per lane
-// of k_fast; the load latency of the next cell hides under the search of the current one.
+// buffer's mbarrier), and it is searched in iteration j.  That replaces ~19 x (LDG + STS + address) instructions per lane
+// of k_fast, and the load latency of the next cell hides under the search of the current one.
+// TMA rule met the hard way (tools/tma_probe2.cu): the byte offset of the box's innermost start coordinate must be a
+// multiple of 16 — any other x raises "illegal instruction" (asynchronously, and not on every request).  The box
+// therefore starts at the cell's column rounded down to 16 and is 15 bytes wider than the widest cell; the cell's pixel x
+// sits at tile byte column mis + x with mis = column & 15, which fast_cell handles like k_fast's 4-byte alignment.
 // Shared memory per warp: 2 tile buffers + score map (box geometry), corner list, survivor list, 2 mbarriers.
 #ifndef FASTT_WARPS
-#define FASTT_WARPS 8
+#define FASTT_WARPS 4
 #endif
 #ifndef FASTT_MINB
-#define FASTT_MINB 4
+#define FASTT_MINB 6
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -792,18 +795,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
         : "memory");
 }
 
-// One CUtensorMap (128 bytes, 64-byte aligned) per pyramid level.  The maps travel as a __grid_constant__ kernel parameter:
-// a descriptor that merely sits in global memory is read by the TMA unit through its own (non-coherent) path and needs a
-// fence.proxy.tensormap acquire first — without it the kernel raised "illegal instruction" on B200 depending on nothing but
-// the launch's shared-memory size.
+// One CUtensorMap (128 bytes, 64-byte aligned) per pyramid level, passed as a __grid_constant__ kernel parameter (the
+// canonical way: a descriptor that merely sits in global memory would need a fence.proxy.tensormap acquire first).
 struct alignas(64) FastTmaMaps {
     unsigned long long m[EAOF_MAX_LEVELS][16];
 };
 
 struct FastTmaArgs {
     int boxW, boxH;      // box = tile geometry: boxW bytes per row (multiple of 16), boxH rows
-    int tileBytes;       // boxW*boxH rounded up to 256
-    int warpBytes;       // shared memory per warp (multiple of 256)
+    int tileBytes;       // boxW*boxH rounded up to 128
+    int warpBytes;       // shared memory per warp (multiple of 128)
     int lstCap;          // survivor-list entries
     int f0;              // first frame of this launch inside the handle's pyramid buffer (chunked batches)
     int nItems;          // frames of this launch * cells per frame
@@ -818,8 +819,8 @@ __global__ void __launch_bounds__(FASTT_WARPS * 32, FASTT_MINB) k_fast_tma(const
                                                                           const __grid_constant__ Geom g) {
     extern __shared__ __align__(128) uint8_t fastTmaSmem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // the dynamic shared memory window is 16-byte aligned by contract; the tile buffers are kept on 256 (see the host sizing)
-    uint8_t* base = fastTmaSmem + ((256u - (smem_u32(fastTmaSmem) & 255u)) & 255u) + (size_t)warp * A.warpBytes;
+    // the dynamic shared memory window is 16-byte aligned by contract; TMA destinations need 128
+    uint8_t* base = fastTmaSmem + ((128u - (smem_u32(fastTmaSmem) & 127u)) & 127u) + (size_t)warp * A.warpBytes;
     uint32_t* Bm = reinterpret_cast<uint32_t*>(base + 2 * A.tileBytes);
     uint16_t* clst = reinterpret_cast<uint16_t*>(base + 3 * A.tileBytes);
     uint16_t* lst = clst + FAST_CLST;
@@ -852,13 +853,13 @@ __global__ void __launch_bounds__(FASTT_WARPS * 32, FASTT_MINB) k_fast_tma(const
 #ifdef EAOF_TMA_DEBUG
             if (A.dbg) {
                 int* r = A.dbg + 8 * (blockIdx.x * FASTT_WARPS + warp);
-                r[0] = c.level; r[1] = EAOF_INNER_X0 + c.iniX; r[2] = EAOF_EDGE + c.iniY; r[3] = A.f0 + f;
+                r[0] = c.level; r[1] = (EAOF_INNER_X0 + c.iniX) & ~15; r[2] = EAOF_EDGE + c.iniY; r[3] = A.f0 + f;
                 r[4] = (int)smem_u32(base + buf * A.tileBytes); r[5] = (int)bar; r[6] = buf; r[7] += 1;
                 __threadfence_system();
             }
 #endif
             mbar_expect_tx(bar, (uint32_t)(A.boxW * A.boxH));
-            tma_load_3d(smem_u32(base + buf * A.tileBytes), &maps.m[c.level][0], EAOF_INNER_X0 + c.iniX, EAOF_EDGE + c.iniY,
+            tma_load_3d(smem_u32(base + buf * A.tileBytes), &maps.m[c.level][0], (EAOF_INNER_X0 + c.iniX) & ~15, EAOF_EDGE + c.iniY,
                         A.f0 + f, bar);
         }
     };
@@ -886,11 +887,40 @@ __global__ void __launch_bounds__(FASTT_WARPS * 32, FASTT_MINB) k_fast_tma(const
         phases ^= 1u << buf;
         __syncwarp();
         if (c.cw > 6 && c.ch > 6)
-            fast_cell<0>(reinterpret_cast<uint32_t*>(base + buf * A.tileBytes), Bm, clst, lst, A.lstCap, c, f, 0, PW, lane, cand,
-                         candCount, g);
+            fast_cell<0>(reinterpret_cast<uint32_t*>(base + buf * A.tileBytes), Bm, clst, lst, A.lstCap, c, f,
+                         (EAOF_INNER_X0 + c.iniX) & 15, PW, lane, cand, candCount, g);
         __syncwarp();
         buf ^= 1;
     }
+}
+
+// k_fast_tma1: the smallest TMA form — one warp and one cell per CTA like k_fast, the tile requested with one
+// cp.async.bulk.tensor (no double buffering: the other resident warps cover the latency, the score map is cleared while the
+// box is in flight).  Same occupancy as k_fast (32 one-warp CTAs per SM), minus its tile-load instructions.
+__global__ void __launch_bounds__(32, 32) k_fast_tma1(const __grid_constant__ FastTmaMaps maps, const FastTmaArgs A,
+                                                      const CellDesc* __restrict__ cells, uint32_t* __restrict__ cand,
+                                                      uint32_t* __restrict__ candCount, const __grid_constant__ Geom g) {
+    extern __shared__ __align__(128) uint8_t fastTma1Smem[];
+    const int lane = threadIdx.x;
+    uint8_t* base = fastTma1Smem + ((128u - (smem_u32(fastTma1Smem) & 127u)) & 127u);
+    uint32_t* Bm = reinterpret_cast<uint32_t*>(base + A.tileBytes);
+    uint16_t* clst = reinterpret_cast<uint16_t*>(base + 2 * A.tileBytes);
+    uint16_t* lst = clst + FAST_CLST;
+    const uint32_t bar = smem_u32(base + 2 * A.tileBytes + 2 * FAST_CLST + 2 * A.lstCap);
+    const CellDesc c = cells[blockIdx.x];
+    const int f = blockIdx.y;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)(A.boxW * A.boxH));
+        tma_load_3d(smem_u32(base), &maps.m[c.level][0], (EAOF_INNER_X0 + c.iniX) & ~15, EAOF_EDGE + c.iniY, A.f0 + f, bar);
+    }
+    for (int i = lane; i < (A.tileBytes >> 4); i += 32) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    mbar_wait(bar, 0);
+    fast_cell<0>(reinterpret_cast<uint32_t*>(base), Bm, clst, lst, A.lstCap, c, f, (EAOF_INNER_X0 + c.iniX) & 15, A.boxW >> 2, lane, cand,
+                 candCount, g);
 }
 
 // ------------------------------------------------------------------------------------------------

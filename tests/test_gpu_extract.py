@@ -394,3 +394,22 @@ def test_frame_helpers_at_the_other_config_sizes(shape, nf):
     v.close()
     exL.close()
     exR.close()
+
+
+@pytest.mark.parametrize("size", [(640, 480, 1000), (848, 480, 1200), (333, 251, 600), (1920, 1080, 4000)])
+def test_tma_staged_fast_variants_match(size, monkeypatch):
+    """The two TMA-staged forms of the FAST kernel (k_fast_tma: persistent warps, double-buffered boxes; k_fast_tma1: one
+    box per one-warp CTA) against the LDG-staged default: identical keypoints and descriptors ($EAOF_FAST_TMA selects)."""
+    import eaof
+    from eaof import synth, workload
+    w, h, nf = size
+    n = 5 if w < 1000 else 2
+    frames = synth.make_frames(n, w, h, tex=synth.base_texture(w, h, seed=77))
+    dig = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("EAOF_FAST_TMA", mode)
+        ex = eaof.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=n)
+        res = ex.extract_batch(frames)
+        ex.close()
+        dig[mode] = [workload.frame_digest(k, d) for k, d in res]
+    assert dig["1"] == dig["0"] and dig["2"] == dig["0"]

@@ -15,7 +15,7 @@ from eaof import workload
 
 
 def run(tma, d, B, W, H, nf, reps=6):
-    os.environ["EAOF_FAST_TMA"] = "1" if tma else "0"
+    os.environ["EAOF_FAST_TMA"] = str(int(tma))
     ex = eaof.ORBextractor(nf, 1.2, 8, 20, 7, width=W, height=H, max_batch=B)
     ex.extract_batch_device(d.data_ptr(), B); ex.sync()
     res = ex.fetch(B)
@@ -47,10 +47,12 @@ def main():
     W, H, nf = cfg["width"], cfg["height"], cfg["nfeatures"]
     fr = workload.Sequence(W, H).frames(0, B)
     d = torch.from_numpy(fr).cuda()
-    d0, t0, w0 = run(False, d, B, W, H, nf)
-    d1, t1, w1 = run(True, d, B, W, H, nf)
-    print(f"{os.environ.get('EAOF_LIB_PATH', 'default')} {name} B={B}: ldg fast={t0['fast']:.3f} total={t0['total']:.3f} batch={w0:.3f} | "
-          f"tma fast={t1['fast']:.3f} total={t1['total']:.3f} batch={w1:.3f} ms | same output: {d0 == d1}", flush=True)
+    d0, t0, w0 = run(0, d, B, W, H, nf)
+    d1, t1, w1 = run(1, d, B, W, H, nf)
+    d2, t2, w2 = run(2, d, B, W, H, nf)
+    print(f"{os.path.basename(os.environ.get('EAOF_LIB_PATH', 'default'))} {name} B={B}: ldg fast={t0['fast']:.3f} batch={w0:.3f} | "
+          f"tma-persistent fast={t1['fast']:.3f} batch={w1:.3f} | tma-oneshot fast={t2['fast']:.3f} batch={w2:.3f} ms | "
+          f"same output: {d0 == d1 == d2}", flush=True)
 
 
 if __name__ == "__main__":
