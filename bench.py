@@ -664,7 +664,9 @@ def hamming_sweep(eaof, torch, dist, rank, world, device, n_blocks=448, n_feat=2
            "matches_per_s": float(chk[0]) / secs_max, "ms_total": secs_max * 1e3,
            "allgather_ms": ag_max, "allgather_bytes": int(ag_bytes), "allgather_frac_of_sweep": ag_max * 1e-3 / secs_max,
            "nccl_version": sweep_mod.Sweep.nccl_version() if world > 1 else None,
-           "single_gpu_pairs_per_s": npm / secs_local, "efficiency_vs_n1": (n_pairs / secs_max) / (world * npm / secs_local),
+           # world == 1: this run IS the single-GPU run (the repeat only shows the run-to-run spread)
+           "single_gpu_pairs_per_s": npm / min(secs_local, secs) if world == 1 else npm / secs_local,
+           "efficiency_vs_n1": 1.0 if world == 1 else (n_pairs / secs_max) / (world * npm / secs_local),
            "matches_total": int(chk[0]), "matches_per_pair": float(chk[0]) / n_pairs, "checksum": int(chk[1]),
            "popc_peak_per_s": popc,
            # 8 XOR words per distance; three carry-save adders fold them so that 5 POPC are executed per distance
@@ -715,6 +717,36 @@ def next_rows(eaof, torch, device, ex, d_frames, B, W, H):
                                    "calls": len(lat), "median_us": lat[len(lat) // 2] * 1e6, "p5_us": lat[int(len(lat) * 0.05)] * 1e6,
                                    "p95_us": lat[int(len(lat) * 0.95)] * 1e6, "keypoints": int(len(k1)),
                                    "launches_per_call": ex1.last_launch_count()}
+    # the Tracking-shaped loop (src/Tracking.cc:1717-1763): extract frame t, then SearchByProjection(Cur = t, Last = t-1)
+    # through the single-pair host-buffer call the drop-in ORBmatcher makes; beside it stands cpu_baseline_alpha
+    mt1 = eaof.ORBmatcher(0.9, True, max_features=4096, device=device)
+    sf1 = ex1.GetScaleFactors()
+    bounds1 = (0.0, float(W), 0.0, float(H))
+    ginv1 = (np.float32(64) / np.float32(W), np.float32(48) / np.float32(H))
+    prev = ex1(f_host[0])
+    t_match, t_both = [], []
+    nm1 = 0
+    for i in range(1, 211):
+        t0 = _t.perf_counter()
+        k1, d1 = ex1(f_host[i % 64])
+        t1 = _t.perf_counter()
+        lk, ld = prev
+        cur = dict(x=k1["x"], y=k1["y"], octave=k1["octave"], angle=k1["angle"], desc=d1)
+        last = dict(u=lk["x"] + np.float32(SHIFT[0]), v=lk["y"] + np.float32(SHIFT[1]), octave=lk["octave"], angle=lk["angle"], desc=ld)
+        nm1, _, _ = mt1.SearchByProjection(cur, last, MATCH_TH, bounds=bounds1, grid_inv=ginv1, scale_factors=sf1)
+        t2 = _t.perf_counter()
+        prev = (k1, d1)
+        if i > 10:
+            t_match.append(t2 - t1)
+            t_both.append(t2 - t0)
+    t_match.sort(); t_both.sort()
+    out["tracking_loop"] = {"workload": "per frame: ORBextractor::operator() + SearchByProjection(Cur,Last) on host buffers, synchronous "
+                                        "(frames 63 -> 0 of the cycled set wrap around: few matches there)",
+                            "frames": len(t_both), "match_median_us": t_match[len(t_match) // 2] * 1e6,
+                            "match_p95_us": t_match[int(len(t_match) * 0.95)] * 1e6,
+                            "extract_plus_match_median_us": t_both[len(t_both) // 2] * 1e6,
+                            "extract_plus_match_p95_us": t_both[int(len(t_both) * 0.95)] * 1e6, "matches_last_pair": int(nm1)}
+    mt1.close()
     ex1.close()
 
     # f-2: ORBVocabulary::transform over the descriptors of a batch, vocabulary of the ORBvoc shape (k=10, L=6)

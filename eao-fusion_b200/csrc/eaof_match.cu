@@ -1392,6 +1392,23 @@ struct eaof_matcher {
     // Small per-call host arrays (pair lists, shifts) go through a pinned staging buffer: cudaMemcpyAsync from pageable
     // memory would synchronise the stream first and stall the caller behind the extraction the stream waits for.
     // Unchanged arrays (a sequence matched batch after batch) are not uploaded again.
+    // single-pair host API: every input array of a call is gathered in ONE pinned block and uploaded with ONE copy (a
+    // cudaMemcpyAsync per array out of pageable memory costs more than the kernels), outputs come back the same way
+    uint8_t *upH = nullptr, *upD = nullptr;
+    size_t upCap = 0, upOff = 0;
+    int *outArenaD = nullptr, *outArenaH = nullptr;  // [4 + 2*maxFeat]: n | match | dist
+    template <typename T> T* stage(const T* src, size_t n) {
+        const size_t bytes = sizeof(T) * n;
+        T* dst = reinterpret_cast<T*>(upD + upOff);
+        memcpy(upH + upOff, src, bytes);
+        upOff += (bytes + 15) & ~(size_t)15;
+        return dst;
+    }
+    cudaError_t flush_stage() {
+        const cudaError_t e = cudaMemcpyAsync(upD, upH, upOff, cudaMemcpyHostToDevice, stream);
+        upOff = 0;
+        return e;
+    }
     int* hStage = nullptr;            // [4][maxPairs] words
     cudaEvent_t evStage = nullptr;    // last upload out of hStage has completed
     std::vector<int> lastUp[4];
@@ -1449,6 +1466,9 @@ int eaof_matcher_create(int device, int maxPairs, int maxFeat, eaof_matcher** ou
     A_(dalloc(&m->segs, maxFeat)); A_(dalloc(&m->segStart, 2)); A_(dalloc(&m->tiles, (size_t)2 * maxFeat));
     A_(dalloc(&m->pairIdx, (size_t)4 * maxPairs)); A_(dalloc(&m->pairShift, (size_t)2 * maxPairs));
     A_(dalloc(&m->outMatch, PF)); A_(dalloc(&m->outDist, PF)); A_(dalloc(&m->outN, maxPairs));
+    m->upCap = (size_t)maxFeat * 160 + 4096;  // 2 x 32-byte descriptors + up to 20 4-byte arrays per feature, 16-byte aligned each
+    A_(cudaMallocHost(&m->upH, m->upCap)); A_(dalloc(&m->upD, m->upCap));
+    A_(cudaMallocHost(&m->outArenaH, sizeof(int) * (4 + 2 * (size_t)maxFeat))); A_(dalloc(&m->outArenaD, 4 + 2 * (size_t)maxFeat));
 #undef A_
     if (e != cudaSuccess) {
         mfail(EAOF_ERR_CUDA, "matcher allocation failed: %s", cudaGetErrorString(e));
@@ -1472,6 +1492,7 @@ void eaof_matcher_destroy(eaof_matcher* m) {
     if (m->evDep) cudaEventDestroy(m->evDep);
     if (m->evStage) cudaEventDestroy(m->evStage);
     cudaFreeHost(m->hStage);
+    cudaFreeHost(m->upH); cudaFree(m->upD); cudaFreeHost(m->outArenaH); cudaFree(m->outArenaD);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -1791,34 +1812,37 @@ int eaof_match_projection(eaof_matcher* m, int nC, const float* cx, const float*
     for (int i = 0; i < nL; ++i) if (loct[i] < 0 || loct[i] >= nLevels) return mfail(EAOF_ERR_ARG, "last_octave[%d] out of range", i);
     MCK(cudaSetDevice(m->device));
     cudaStream_t s = m->stream;
-#define UP(dst, src, n, T) MCK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(n), cudaMemcpyHostToDevice, s))
-    UP(m->cx, cx, nC, float); UP(m->cy, cy, nC, float); UP(m->coct, coct, nC, int); UP(m->cangle, cangle, nC, float);
-    if (curight) UP(m->curight, curight, nC, float);
-    if (ctaken) UP(m->ctaken, ctaken, nC, uint8_t);
-    UP(m->lu, lu, nL, float); UP(m->lv, lv, nL, float); UP(m->loct, loct, nL, int); UP(m->langle, langle, nL, float);
-    if (linvz) UP(m->linvz, linvz, nL, float);
-    if (lvalid) UP(m->lvalid, lvalid, nL, uint8_t);
-    if (lobs) UP(m->lobs, lobs, nL, uint8_t);
-    UP(m->desc2, cdesc, 32 * (size_t)nC, uint8_t);
-    UP(m->desc2 + 32 * (size_t)m->maxFeat, ldesc, 32 * (size_t)nL, uint8_t);
-    const int hdr[4] = {nC, nL, 0, m->maxFeat};
-    UP(m->nC, &hdr[0], 1, int); UP(m->nL, &hdr[1], 1, int); UP(m->cRow, &hdr[2], 1, int); UP(m->lRow, &hdr[3], 1, int);
-#undef UP
+    // one pinned block, one upload
+    m->upOff = 0;
     ProjArgs A{};
-    A.cx = m->cx; A.cy = m->cy; A.coct = m->coct; A.cangle = m->cangle; A.curight = curight ? m->curight : nullptr;
-    A.ctaken = ctaken ? m->ctaken : nullptr; A.nC = m->nC; A.lu = m->lu; A.lv = m->lv; A.linvz = linvz ? m->linvz : nullptr;
-    A.loct = m->loct; A.langle = m->langle; A.lvalid = lvalid ? m->lvalid : nullptr; A.lobs = lobs ? m->lobs : nullptr;
-    A.nL = m->nL; A.desc = m->desc2; A.cRow = m->cRow; A.lRow = m->lRow; A.stride = m->maxFeat;
+    A.cx = m->stage(cx, nC); A.cy = m->stage(cy, nC); A.coct = m->stage(coct, nC); A.cangle = m->stage(cangle, nC);
+    A.curight = curight ? m->stage(curight, nC) : nullptr;
+    A.ctaken = ctaken ? m->stage(ctaken, nC) : nullptr;
+    A.lu = m->stage(lu, nL); A.lv = m->stage(lv, nL); A.loct = m->stage(loct, nL); A.langle = m->stage(langle, nL);
+    A.linvz = linvz ? m->stage(linvz, nL) : nullptr;
+    A.lvalid = lvalid ? m->stage(lvalid, nL) : nullptr;
+    A.lobs = lobs ? m->stage(lobs, nL) : nullptr;
+    A.desc = m->stage(cdesc, 32 * (size_t)nC);          // Cur rows, then Last rows right behind them (32*nC is a multiple of 16)
+    m->stage(ldesc, 32 * (size_t)nL);
+    const int hdr[4] = {nC, nL, 0, nC};                 // counts, first descriptor row of Cur / of Last
+    const int* dHdr = m->stage(hdr, 4);
+    A.nC = dHdr; A.nL = dHdr + 1; A.cRow = dHdr + 2; A.lRow = dHdr + 3;
+    MCK(m->flush_stage());
+    A.stride = m->maxFeat;
     A.minX = minX; A.maxX = maxX; A.minY = minY; A.maxY = maxY; A.invW = invW; A.invH = invH;
     for (int i = 0; i < nLevels; ++i) A.scale[i] = scaleFactors[i];
     A.th = th; A.mbf = mbf; A.searchMode = searchMode; A.checkOri = checkOri;
     A.thAccept = EAOF_TH_HIGH; A.cut = EAOF_TH_HIGH; A.histMode = 2; A.checkBounds = 1;
-    int rc = run_projection(m, A, 1, nL, m->outMatch, m->outDist, m->outN);
+    int* dN = m->outArenaD;
+    int* dM = m->outArenaD + 4;
+    int* dD = dM + nC;
+    int rc = run_projection(m, A, 1, nL, dM, dD, dN);
     if (rc) return rc;
-    MCK(cudaMemcpyAsync(matchCur, m->outMatch, sizeof(int) * nC, cudaMemcpyDeviceToHost, s));
-    if (distCur) MCK(cudaMemcpyAsync(distCur, m->outDist, sizeof(int) * nC, cudaMemcpyDeviceToHost, s));
-    MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(m->outArenaH, m->outArenaD, sizeof(int) * (4 + 2 * (size_t)nC), cudaMemcpyDeviceToHost, s));
     MCK(cudaStreamSynchronize(s));
+    *nMatches = m->outArenaH[0];
+    memcpy(matchCur, m->outArenaH + 4, sizeof(int) * nC);
+    if (distCur) memcpy(distCur, m->outArenaH + 4 + nC, sizeof(int) * nC);
     return EAOF_OK;
 }
 
@@ -1840,30 +1864,29 @@ int eaof_match_windows(eaof_matcher* m, int rule, int nT, const float* tx, const
     if (turight && !qUr) return mfail(EAOF_ERR_ARG, "t_uright given without q_ur");
     MCK(cudaSetDevice(m->device));
     cudaStream_t s = m->stream;
-#define UP(dst, src, n, T) MCK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(n), cudaMemcpyHostToDevice, s))
-    UP(m->cx, tx, nT, float); UP(m->cy, ty, nT, float); UP(m->coct, toct, nT, int);
-    if (tangle) UP(m->cangle, tangle, nT, float);
-    if (turight) UP(m->curight, turight, nT, float);
-    if (ttaken) UP(m->ctaken, ttaken, nT, uint8_t);
-    UP(m->lu, qU, nQ, float); UP(m->lv, qV, nQ, float); UP(m->qRadius, qRadius, nQ, float);
-    UP(m->loct, qMinLevel, nQ, int); UP(m->qMaxL, qMaxLevel, nQ, int);
-    if (qUr) UP(m->linvz, qUr, nQ, float);
-    if (qAngle) UP(m->langle, qAngle, nQ, float);
-    if (qValid) UP(m->lvalid, qValid, nQ, uint8_t);
-    if (qObs) UP(m->lobs, qObs, nQ, uint8_t);
-    UP(m->desc2, tdesc, 32 * (size_t)nT, uint8_t);
-    UP(m->desc2 + 32 * (size_t)m->maxFeat, qDesc, 32 * (size_t)nQ, uint8_t);
-    const int hdr[4] = {nT, nQ, 0, m->maxFeat};
-    UP(m->nC, &hdr[0], 1, int); UP(m->nL, &hdr[1], 1, int); UP(m->cRow, &hdr[2], 1, int); UP(m->lRow, &hdr[3], 1, int);
-#undef UP
+    // one pinned block, one upload (see eaof_match_projection)
+    m->upOff = 0;
     ProjArgs A{};
-    A.cx = m->cx; A.cy = m->cy; A.coct = m->coct; A.cangle = m->cangle; A.curight = turight ? m->curight : nullptr;
-    A.ctaken = ttaken ? m->ctaken : nullptr; A.nC = m->nC; A.lu = m->lu; A.lv = m->lv; A.linvz = nullptr;
-    A.loct = m->loct; A.langle = m->langle; A.lvalid = qValid ? m->lvalid : nullptr; A.lobs = qObs ? m->lobs : nullptr;
-    A.nL = m->nL; A.desc = m->desc2; A.cRow = m->cRow; A.lRow = m->lRow; A.stride = m->maxFeat;
+    A.cx = m->stage(tx, nT); A.cy = m->stage(ty, nT); A.coct = m->stage(toct, nT);
+    A.cangle = tangle ? m->stage(tangle, nT) : m->cangle;
+    A.curight = turight ? m->stage(turight, nT) : nullptr;
+    A.ctaken = ttaken ? m->stage(ttaken, nT) : nullptr;
+    A.lu = m->stage(qU, nQ); A.lv = m->stage(qV, nQ); A.qRadius = m->stage(qRadius, nQ);
+    A.loct = m->stage(qMinLevel, nQ); A.qMinL = A.loct; A.qMaxL = m->stage(qMaxLevel, nQ);
+    A.qUr = qUr ? m->stage(qUr, nQ) : A.lu;  // without a stereo prediction qUr is never read
+    A.langle = qAngle ? m->stage(qAngle, nQ) : m->langle;
+    A.lvalid = qValid ? m->stage(qValid, nQ) : nullptr;
+    A.lobs = qObs ? m->stage(qObs, nQ) : nullptr;
+    A.linvz = nullptr;
+    A.desc = m->stage(tdesc, 32 * (size_t)nT);
+    m->stage(qDesc, 32 * (size_t)nQ);
+    const int hdr[4] = {nT, nQ, 0, nT};
+    const int* dHdr = m->stage(hdr, 4);
+    A.nC = dHdr; A.nL = dHdr + 1; A.cRow = dHdr + 2; A.lRow = dHdr + 3;
+    MCK(m->flush_stage());
+    A.stride = m->maxFeat;
     A.minX = minX; A.maxX = maxX; A.minY = minY; A.maxY = maxY; A.invW = invW; A.invH = invH;
-    A.qRadius = m->qRadius; A.qMinL = m->loct; A.qMaxL = m->qMaxL; A.qUr = qUr ? m->linvz : m->lu;  // without a stereo
-    A.checkOri = histMode != 0; A.histMode = histMode; A.checkBounds = checkBounds;                  // prediction qUr is never read
+    A.checkOri = histMode != 0; A.histMode = histMode; A.checkBounds = checkBounds;
     A.thAccept = thAccept; A.ratio = nnratio;
     if (rule == EAOF_WIN_BEST) {
         A.cut = thAccept;
@@ -1877,15 +1900,19 @@ int eaof_match_windows(eaof_matcher* m, int rule, int nT, const float* tx, const
     k_build_grid<<<1, 256, 0, s>>>(A, m->cellStart, m->cellIdx, m->cellPack);
     k_proj_dense<0><<<dim3((nQ * PROJ_LANES + 127) / 128, 1), 128, 0, s>>>(A, m->cellStart, m->cellPack, m->nearBuf);
     const size_t bm = sizeof(uint32_t) * ((A.stride + 31) / 32);
+    int* dN = m->outArenaD;
+    int* dM = m->outArenaD + 4;
+    int* dD = dM + nT;
     if (rule == EAOF_WIN_BEST)
-        k_proj_resolve<<<1, 32, bm, s>>>(A, m->cellStart, m->cellPack, m->nearBuf, m->accBuf, m->outMatch, m->outDist, m->outN);
+        k_proj_resolve<<<1, 32, bm, s>>>(A, m->cellStart, m->cellPack, m->nearBuf, m->accBuf, dM, dD, dN);
     else
-        k_win_resolve_ratio<<<1, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, m->outMatch, m->outDist, m->outN);
+        k_win_resolve_ratio<<<1, 32, bm, s>>>(A, m->cellStart, m->cellIdx, m->nearBuf, dM, dD, dN);
     MCK(cudaGetLastError());
-    MCK(cudaMemcpyAsync(matchT, m->outMatch, sizeof(int) * nT, cudaMemcpyDeviceToHost, s));
-    if (distT) MCK(cudaMemcpyAsync(distT, m->outDist, sizeof(int) * nT, cudaMemcpyDeviceToHost, s));
-    MCK(cudaMemcpyAsync(nMatches, m->outN, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MCK(cudaMemcpyAsync(m->outArenaH, m->outArenaD, sizeof(int) * (4 + 2 * (size_t)nT), cudaMemcpyDeviceToHost, s));
     MCK(cudaStreamSynchronize(s));
+    *nMatches = m->outArenaH[0];
+    memcpy(matchT, m->outArenaH + 4, sizeof(int) * nT);
+    if (distT) memcpy(distT, m->outArenaH + 4 + nT, sizeof(int) * nT);
     return EAOF_OK;
 }
 

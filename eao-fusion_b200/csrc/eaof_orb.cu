@@ -50,6 +50,9 @@ extern "C" int* eaof_debug_tma_records() { return g_tmaDbgHost; }
 #endif
 // Which FAST kernel a handle uses unless $EAOF_FAST_TMA says otherwise (0 LDG-staged, 1 persistent TMA, 2 one-shot TMA);
 // the measurements behind the default are in DESIGN.md §4.
+#ifndef EAOF_FUSED_MAX_CTAS
+#define EAOF_FUSED_MAX_CTAS 296  // two tiles per SM
+#endif
 #ifndef EAOF_FAST_TMA_DEFAULT
 #define EAOF_FAST_TMA_DEFAULT 0
 #endif
@@ -79,6 +82,13 @@ struct eaof_orb {
     eaof_kp* pendKps = nullptr;
     uint8_t* pendDesc = nullptr;
     bool pendDirect = false;
+    bool pendGraph = false;
+    // single-frame latency path: the kernel sequence + the three result downloads of one frame captured once as a CUDA
+    // graph (one cudaGraphLaunch per frame instead of ~15 launches / copies / event calls)
+    cudaGraph_t graph1 = nullptr;
+    cudaGraphExec_t graphExec1 = nullptr;
+    bool graphTried = false;
+    bool capturing = false;
     Geom g{};
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
@@ -113,6 +123,16 @@ struct eaof_orb {
     eaof::FastTmaMaps fastMaps{};
     unsigned int* dFastCtr = nullptr;   // [kMaxChunks]
     eaof::FastTmaArgs fastT{};
+    // k_pyramid_fused: tile plan (built at create), input tensor map (re-encoded when the input pointer / pitches change)
+    bool fused = false;
+    eaof::FusedArgs fusedA{};
+    eaof::FusedAxis* dFusedAxes = nullptr;
+    size_t fusedSmem = 0;
+    eaof::FastTmaMaps fusedInMap{};
+    const uint8_t* fusedMapPtr = nullptr;
+    size_t fusedMapStride = 0, fusedMapPitch = 0;
+    int fusedMapN = 0;
+    void* encodeTiled = nullptr;  // cuTensorMapEncodeTiled
     int fastTma = 0;  // 0: k_fast (LDG-staged tile), 1: k_fast_tma (persistent, double-buffered TMA), 2: k_fast_tma1
     int fastTmaGrid = 0;
     size_t fastTmaSmem = 0;
@@ -285,6 +305,85 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
     return EAOF_OK;
 }
 
+// Tile plan of k_pyramid_fused along one axis: own ranges [a, b) per (level, tile) that nest through the resize tables
+// (a_{l-1} = source index of a_l), and the needed ranges [lo, lo+n) = own range + what the deeper levels read.
+bool fused_axis(const Geom& g, bool xAxis, const std::vector<int>& tabs, int& nT, std::vector<eaof::FusedAxis>& out) {
+    const int nl = g.nlevels;
+    auto size = [&](int l) { return xAxis ? g.L[l].w : g.L[l].h; };
+    auto src = [&](int l, int d) {  // source index in level l-1 of destination index d of level l, clamped like the kernels do
+        const int v = tabs[(xAxis ? g.L[l].xTab : g.L[l].yTab) + 2 * d];
+        return std::min(std::max(v, 0), size(l - 1) - 1);
+    };
+    const int last = nl - 1;
+    const int nLast = size(last);
+    nT = std::max(1, std::min((nLast + 16) / 32, nLast / 20));
+    std::vector<std::vector<int>> a(nl, std::vector<int>(nT + 1));
+    for (int t = 0; t <= nT; ++t) {
+        a[last][t] = (int)((long long)t * nLast / nT);
+        if (xAxis && t > 0 && t < nT) a[last][t] &= ~3;
+    }
+    for (int l = last; l >= 1; --l)
+        for (int t = 0; t <= nT; ++t)  // x boundaries on multiples of 4: whole words change hands between tiles
+            a[l - 1][t] = t == 0 ? 0 : t == nT ? size(l - 1) : (xAxis ? src(l, a[l][t]) & ~3 : src(l, a[l][t]));
+    out.assign((size_t)nl * nT, eaof::FusedAxis{0, 0, 0, 0});
+    for (int t = 0; t < nT; ++t) {
+        int lo = a[last][t], hi = a[last][t + 1] - 1;
+        for (int l = last; l >= 0; --l) {
+            if (a[l][t + 1] - a[l][t] < 1) return false;
+            // the mirror sources of the 19-px border must lie inside the edge tiles' own ranges
+            if (nT > 1 && (t == 0 || t == nT - 1) && a[l][t + 1] - a[l][t] < EAOF_EDGE + 1) return false;
+            if (hi - lo + 1 > 30000) return false;
+            out[(size_t)l * nT + t] = eaof::FusedAxis{(short)a[l][t], (short)a[l][t + 1], (short)lo, (short)(hi - lo + 1)};
+            if (l >= 1) {
+                const int lo2 = std::min(a[l - 1][t], src(l, lo));
+                const int hi2 = std::max(a[l - 1][t + 1] - 1, std::min(src(l, hi) + 1, size(l - 1) - 1));
+                lo = lo2;
+                hi = hi2;
+            }
+        }
+    }
+    return true;
+}
+
+int build_fused_plan(eaof_orb* c, const std::vector<int>& tabs, std::vector<eaof::FusedAxis>& axes) {
+    const Geom& g = c->g;
+    c->fused = false;
+    const char* e = getenv("EAOF_PYR_FUSED");
+    if (e && *e == '0') return EAOF_OK;
+    if (g.nlevels < 2) return EAOF_OK;
+    for (int l = 0; l < g.nlevels; ++l)
+        if (g.L[l].w < 2 * EAOF_EDGE + 2 || g.L[l].h < 2 * EAOF_EDGE + 2) return EAOF_OK;  // borders fold more than once: per-level kernels
+    std::vector<eaof::FusedAxis> ax, ay;
+    int nTx = 0, nTy = 0;
+    if (!fused_axis(g, true, tabs, nTx, ax) || !fused_axis(g, false, tabs, nTy, ay)) return EAOF_OK;
+    eaof::FusedArgs& A = c->fusedA;
+    A = eaof::FusedArgs{};
+    A.nTx = nTx; A.nTy = nTy;
+    size_t bytes[2] = {0, 0};
+    for (int l = 0; l < g.nlevels; ++l) {
+        int wMax = 0, hMax = 0;
+        for (int t = 0; t < nTx; ++t) {
+            const eaof::FusedAxis& X = ax[(size_t)l * nTx + t];
+            const int ox = l == 0 ? (X.lo & ~15) : (X.lo & ~3);
+            wMax = std::max(wMax, X.lo + X.n - ox);
+        }
+        for (int t = 0; t < nTy; ++t) hMax = std::max(hMax, (int)ay[(size_t)l * nTy + t].n);
+        A.pitchT[l] = (wMax + 8 + 15) & ~15;  // + 8: the horizontal pass reads the word after the one holding column sx (zero coefficient at the image edge)
+        if (l == 0) { A.boxW0 = A.pitchT[0]; A.boxH0 = hMax; }
+        if (hMax > EAOF_FUSED_MAX_ROWS) return EAOF_OK;
+        bytes[l & 1] = std::max(bytes[l & 1], (size_t)A.pitchT[l] * (hMax + 1));
+    }
+    if (A.boxW0 > 256 || A.boxH0 > 256) return EAOF_OK;
+    A.bufBytes[0] = (int)((bytes[0] + 127) & ~(size_t)127);
+    A.bufBytes[1] = (int)((bytes[1] + 127) & ~(size_t)127);
+    c->fusedSmem = (size_t)A.bufBytes[0] + A.bufBytes[1] + 128;
+    if (c->fusedSmem > 110 * 1024) return EAOF_OK;
+    axes = ax;
+    axes.insert(axes.end(), ay.begin(), ay.end());
+    c->fused = true;
+    return EAOF_OK;
+}
+
 // Issues the kernel sequence for frames [f0, f0+n) of the workspace; dImgs points at frame f0's image.
 // Kernels of different handles that run at the same time slow each other down on B200 (measured: two handles
 // alternating full batches reach 115 k frames/s against 132 k for one, tools/lanes_experiment.py), while uploads and
@@ -299,6 +398,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     cudaStream_t s = c->stream;
     // every per-frame array is frame-major, so a chunk is addressed by offsetting the base pointers
     uint8_t* const dPyr = c->dPyr + (size_t)f0 * g.pyrFrameBytes;
+    uint8_t* const dPyrBase = c->dPyr;  // k_pyramid_fused offsets by f0 itself
     uint8_t* const dBlur = c->dBlur + (size_t)f0 * g.pyrFrameBytes;
     uint32_t* const dCand = c->dCand + (size_t)f0 * g.candPerFrame;
     uint16_t* const dLabel = c->dLabel + (size_t)f0 * g.candPerFrame;
@@ -314,11 +414,45 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     if (prof) CK(cudaEventRecord(c->ev[0], s));
     nvtxRangePushA("eaof:pyramid");
     CK(cudaMemsetAsync(dCandCount, 0, sizeof(uint32_t) * (size_t)n * g.nlevels, s));
-    if (c->pyrReaderPending) {
+    if (c->pyrReaderPending && !c->capturing) {
         CK(cudaStreamWaitEvent(s, c->evPyrReader, 0));
         c->pyrReaderPending = false;
     }
-    {
+    // One launch for the whole pyramid pays off while the frames of a call cannot fill the GPU level by level (the chain of
+    // per-level launches is then pure latency); big batches keep the per-level kernels, which do less redundant work
+    // (measured crossover: DESIGN.md §4).  EAOF_PYR_FUSED=2 forces the fused kernel for every batch size.
+    static const int fusedMode = getenv("EAOF_PYR_FUSED") ? atoi(getenv("EAOF_PYR_FUSED")) : 1;
+    const bool fusedNow = c->fused && c->colorCh == 0 && (fusedMode == 2 || n * c->fusedA.nTx * c->fusedA.nTy <= EAOF_FUSED_MAX_CTAS);
+    if (fusedNow) {
+        eaof::FusedArgs A = c->fusedA;
+        A.in = dImgs; A.stride = stride; A.framePitch = framePitch; A.f0 = f0;
+        // TMA takes the level-0 boxes when the frames are 16-byte aligned in every dimension; the map is re-encoded only
+        // when the input changes (the host-buffer paths always read the handle's own staging buffer)
+        A.useTma = c->encodeTiled && (reinterpret_cast<uintptr_t>(dImgs) & 15) == 0 && (stride & 15) == 0 && (framePitch & 15) == 0;
+        if (A.useTma && (c->fusedMapPtr != dImgs || c->fusedMapStride != stride || c->fusedMapPitch != framePitch || c->fusedMapN < n)) {
+            typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                            const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            CUtensorMap m;
+            const cuuint64_t dims[3] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)n};
+            const cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)framePitch};
+            const cuuint32_t box[3] = {(cuuint32_t)A.boxW0, (cuuint32_t)A.boxH0, 1}, es[3] = {1, 1, 1};
+            const CUresult r = ((EncodeTiled)c->encodeTiled)(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(dImgs), dims, strides,
+                                                             box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) {
+                memcpy(&c->fusedInMap.m[0][0], &m, sizeof m);
+                c->fusedMapPtr = dImgs; c->fusedMapStride = stride; c->fusedMapPitch = framePitch; c->fusedMapN = n;
+            } else {
+                A.useTma = 0;
+            }
+        }
+        // few frames: wide CTAs shorten the per-level critical path of a tile; many frames: narrow ones fill the SMs better
+        static const int forced = getenv("EAOF_FUSED_THREADS") ? atoi(getenv("EAOF_FUSED_THREADS")) : 0;
+        const int threads = forced ? forced : (n * A.nTx * A.nTy < 1024 ? 512 : 256);
+        eaof::k_pyramid_fused<<<dim3(A.nTx * A.nTy, n), threads, c->fusedSmem, s>>>(c->fusedInMap, A, dPyrBase, c->dTabs, g);
+        ++launches;
+    } else {
         const LevelGeom& L = g.L[0];
         dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
         const dim3 gr8(gr.x, (L.rows + 4 * LEVEL0_ROWS - 1) / (4 * LEVEL0_ROWS), n);  // k_level0: LEVEL0_ROWS rows per thread
@@ -330,7 +464,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
             eaof::k_level0<<<gr8, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g);
         ++launches;
     }
-    for (int l = 1; l < g.nlevels; ++l) {
+    for (int l = 1; l < g.nlevels && !fusedNow; ++l) {
         const LevelGeom& L = g.L[l];
         if (L.h >= 40) {
             // rows per thread: long walks reuse source rows, but small levels / small batches need the threads
@@ -404,7 +538,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     nvtxRangePop();
     if (prof) CK(cudaEventRecord(c->ev[4], s));
     nvtxRangePushA("eaof:angle+descriptor");
-    if (c->readerPending) {
+    if (c->readerPending && !c->capturing) {
         CK(cudaStreamWaitEvent(s, c->evReader, 0));
         c->readerPending = false;
     }
@@ -562,6 +696,28 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
         CKD(cudaFuncSetAttribute(eaof::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     {
+        // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            c->encodeTiled = fn;
+        else
+            cudaGetLastError();
+        // k_pyramid_fused: tile plan + shared-memory size
+        std::vector<eaof::FusedAxis> axes;
+        build_fused_plan(c, tabs, axes);
+        if (c->fused) {
+            CKD(cudaMalloc(&c->dFusedAxes, sizeof(eaof::FusedAxis) * axes.size()));
+            CKD(cudaMemcpy(c->dFusedAxes, axes.data(), sizeof(eaof::FusedAxis) * axes.size(), cudaMemcpyHostToDevice));
+            c->fusedA.ax = c->dFusedAxes;
+            c->fusedA.ay = c->dFusedAxes + (size_t)g.nlevels * c->fusedA.nTx;
+            static std::mutex muP;
+            std::lock_guard<std::mutex> lk(muP);
+            CKD(cudaFuncSetAttribute(eaof::k_pyramid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        }
+    }
+    {
         // k_fast_tma: tensor maps (CU_TENSOR_MAP_DATA_TYPE_UINT8, rank 3: byte column, row, frame) and shared-memory shape.
         // EAOF_FAST_TMA=0 keeps the LDG-staged k_fast (A/B measurements).
         const char* e = getenv("EAOF_FAST_TMA");
@@ -575,14 +731,12 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
         T.lstCap = 248;  // phase (A) refills the list in rounds of <= 128 entries
         T.warpBytes = (3 * T.tileBytes + 2 * FAST_CLST + 2 * T.lstCap + 16 + 127) & ~127;
         c->fastTmaSmem = (size_t)FASTT_WARPS * T.warpBytes + 128;
-        if (want && !cells.empty() && T.boxW <= 256 && T.boxH <= 256 && (c->fastTmaSmem + 1024) * FASTT_MINB <= 227 * 1024) {
+        if (want > 0 && !cells.empty() && T.boxW <= 256 && T.boxH <= 256 && (c->fastTmaSmem + 1024) * FASTT_MINB <= 227 * 1024) {
             typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            CKD(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-            if (!fn || qres != cudaDriverEntryPointSuccess) {
+            void* fn = c->encodeTiled;
+            if (!fn) {
                 fail(EAOF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
                 eaof_orb_destroy(c);
                 return EAOF_ERR_CUDA;
@@ -670,6 +824,9 @@ void eaof_orb_destroy(eaof_orb* c) {
     if (c->evPyrReader) cudaEventDestroy(c->evPyrReader);
     cudaFree(c->dSad);
     cudaFree(c->dFastCtr);
+    cudaFree(c->dFusedAxes);
+    if (c->graphExec1) cudaGraphExecDestroy(c->graphExec1);
+    if (c->graph1) cudaGraphDestroy(c->graph1);
     if (c->streamIn) { cudaStreamSynchronize(c->streamIn); cudaStreamDestroy(c->streamIn); }
     if (c->streamOut) { cudaStreamSynchronize(c->streamOut); cudaStreamDestroy(c->streamOut); }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -958,6 +1115,46 @@ int eaof_orb_extract_batch_async(eaof_orb* c, const uint8_t* imgs, int n, int wi
     const bool direct = cap == c->kpCap;
     eaof_kp* hK = kps ? (direct ? kps : c->hKps) : nullptr;
     uint8_t* hD = desc ? (direct ? desc : c->hDesc) : nullptr;
+    static const bool noGraph = getenv("EAOF_NO_GRAPH") != nullptr;  // experiment knob
+    if (n == 1 && !c->profiling && !noGraph && !(c->graphTried && !c->graphExec1)) {
+        // ---- latency path: upload on the compute stream, then the captured graph (kernels + downloads into the pinned staging)
+        cudaStream_t s = c->stream;
+        if (c->pyrReaderPending) { CK(cudaStreamWaitEvent(s, c->evPyrReader, 0)); c->pyrReaderPending = false; }
+        if (c->readerPending) { CK(cudaStreamWaitEvent(s, c->evReader, 0)); c->readerPending = false; }
+        if (packed)
+            CK(cudaMemcpyAsync(c->dIn, imgs, frameBytes, cudaMemcpyHostToDevice, s));
+        else
+            CK(cudaMemcpy2DAsync(c->dIn, (size_t)width, imgs, stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, s));
+        if (!c->graphExec1) {
+            c->graphTried = true;
+            c->capturing = true;
+            cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+            int rcb = EAOF_OK;
+            if (e == cudaSuccess) {
+                rcb = run_batch(c, c->dIn, 1, (size_t)width, frameBytes, 0, 0);
+                if (rcb == EAOF_OK) {
+                    cudaMemcpyAsync(c->hKpCount, c->dKpCount, sizeof(int), cudaMemcpyDeviceToHost, s);
+                    cudaMemcpyAsync(c->hKps, c->dKps, sizeof(eaof_kp) * (size_t)c->kpCap, cudaMemcpyDeviceToHost, s);
+                    cudaMemcpyAsync(c->hDesc, c->dDesc, 32 * (size_t)c->kpCap, cudaMemcpyDeviceToHost, s);
+                }
+                e = cudaStreamEndCapture(s, &c->graph1);
+                if (e == cudaSuccess && rcb == EAOF_OK) e = cudaGraphInstantiate(&c->graphExec1, c->graph1, 0);
+            }
+            c->capturing = false;
+            if (e != cudaSuccess || rcb != EAOF_OK || !c->graphExec1) {
+                // not capturable here: this handle stays on the stream path below (graphTried keeps it there)
+                cudaGetLastError();
+                if (c->graph1) { cudaGraphDestroy(c->graph1); c->graph1 = nullptr; }
+                c->graphExec1 = nullptr;
+            }
+        }
+        if (c->graphExec1) {
+            CK(cudaGraphLaunch(c->graphExec1, s));
+            c->lastFrames = 1;
+            c->pendN = 1; c->pendCap = cap; c->pendKps = kps; c->pendDesc = desc; c->pendDirect = false; c->pendGraph = true;
+            return EAOF_OK;
+        }
+    }
     const bool pipelined = !c->profiling && n > c->chunkFrames;
     const int chunk = pipelined ? c->chunkFrames : n;
     // the download stream may still be busy with the previous call's copies out of the same device buffers
@@ -994,7 +1191,7 @@ int eaof_orb_extract_batch_async(eaof_orb* c, const uint8_t* imgs, int n, int wi
     if (!g_tok[dev]) CK(cudaEventCreateWithFlags(&g_tok[dev], cudaEventDisableTiming));
     CK(cudaEventRecord(g_tok[dev], c->stream));
     g_tokSet[dev] = true;
-    c->pendN = n; c->pendCap = cap; c->pendKps = kps; c->pendDesc = desc; c->pendDirect = direct;
+    c->pendN = n; c->pendCap = cap; c->pendKps = kps; c->pendDesc = desc; c->pendDirect = direct; c->pendGraph = false;
     return EAOF_OK;
 }
 
@@ -1007,7 +1204,7 @@ int eaof_orb_extract_batch_wait(eaof_orb* c, int* nOut) {
     const bool direct = c->pendDirect;
     c->pendN = 0;
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->streamOut));
+    if (!c->pendGraph) CK(cudaStreamSynchronize(c->streamOut));  // the graph downloads on the compute stream itself
     int rc = eaof_orb_sync(c);
     if (rc) return rc;
     for (int f = 0; f < n; ++f) {

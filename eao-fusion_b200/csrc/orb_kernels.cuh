@@ -27,6 +27,42 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
+// ---- TMA / mbarrier primitives (sm_100a PTX) shared by k_pyramid_fused and the k_fast_tma variants
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int x, int y, int z, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+// One CUtensorMap (128 bytes, 64-byte aligned) per pyramid level, passed as a __grid_constant__ kernel parameter (the
+// canonical way: a descriptor that merely sits in global memory would need a fence.proxy.tensormap acquire first).
+struct alignas(64) FastTmaMaps {
+    unsigned long long m[EAOF_MAX_LEVELS][16];
+};
+
+
 // ------------------------------------------------------------------------------------------------
 // Pyramid.  A level row is `pitch` bytes; inner pixel x sits at byte EAOF_INNER_X0 + x, so the bordered
 // span is bytes [13, w+51).  
@@ -450,6 +486,192 @@ __global__ void __launch_bounds__(RSZ_THREADS) k_resize(uint8_t* __restrict__ py
     }
 }
 
+// ---- k_pyramid_fused: ComputePyramid in ONE launch ---------------------------------------------------------------
+// src/ORBextractor.cc:1107-1132 is a dependent chain: level l is cv::resize of level l-1.  Instead of one launch per level
+// (each a pass over global memory, each a launch on the critical path of a single frame), a CTA owns a tile of the LAST
+// level and carries the part of the image that tile descends from down through all levels in shared memory:
+//   * the tile plan is built on the host from the reference's own resize tables: own ranges [a, b) per level nest exactly
+//     (a_{l-1} = sx_l(a_l)), so every pixel of every level is written by exactly one CTA; what a CTA needs beyond its own
+//     range is a halo on the right / bottom only (1 px at the last level, growing by the scale factor per level: 17 px at
+//     level 0 of an 8-level 1.2 pyramid), recomputed, never exchanged;
+//   * the level-0 region arrives with one cp.async.bulk.tensor box of the input frames' {width, height, frames} tensor
+//     (box start rounded down to a 16-byte column, TMA's rule) completing on an mbarrier; inputs TMA cannot take
+//     (row stride or base not multiples of 16) are fetched with plain loads into the same layout;
+//   * per level: thread = (destination column, chunk of rows); the horizontal pass of the two source rows lives in
+//     registers (the lower row of one output row is usually the upper row of the next), vertical pass and rounding exactly
+//     as k_resize (11-bit coefficients, (b*(h>>4))>>16 per term, +2 >> 2);
+//   * every level is written to the bordered pyramid from shared memory: own pixels, and for tiles on the image edge their
+//     REFLECT_101 mirror images (the source of a border pixel within 19 px of the edge always lies in the edge tile).
+// Tiles are stored with their x origin rounded down to a multiple of 4, which makes a shared-memory word and the global
+// word it goes to share their alignment (global inner pixel x sits at byte 32 + x).
+struct FusedAxis { short a, b, lo, n; };  // per (level, tile index): own [a, b), needed [lo, lo + n)
+struct FusedArgs {
+    const FusedAxis* ax;   // [nlevels][nTx]
+    const FusedAxis* ay;   // [nlevels][nTy]
+    int nTx, nTy;
+    int pitchT[EAOF_MAX_LEVELS];  // shared-memory row pitch of a tile of level l (bytes, multiple of 16)
+    int bufBytes[2];       // even levels / odd levels
+    int boxW0, boxH0;      // TMA box of level 0 (= pitchT[0] x rows)
+    int useTma;
+    const uint8_t* in;     // input frames (device)
+    size_t stride, framePitch;
+    int f0;                // first frame of this launch inside the handle's pyramid buffer
+};
+
+#define EAOF_FUSED_MAX_ROWS 160
+__global__ void __launch_bounds__(512) k_pyramid_fused(const __grid_constant__ FastTmaMaps inMap, const FusedArgs A,
+                                                       uint8_t* __restrict__ pyr, const int* __restrict__ tabs,
+                                                       const __grid_constant__ Geom g) {
+    extern __shared__ __align__(128) uint8_t fusedSmem[];
+    __shared__ __align__(8) unsigned long long fusedBar;
+    __shared__ int4 fusedRows[EAOF_FUSED_MAX_ROWS];  // per destination row of the level in flight: (source row 0, source row 1, b0|b1<<16)
+    const int tid = threadIdx.x, nThreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nWarps = nThreads >> 5;
+    const int ty = blockIdx.x / A.nTx, tx = blockIdx.x - ty * A.nTx;
+    const int f = blockIdx.y;
+    uint8_t* const buf0 = fusedSmem + ((128u - (smem_u32(fusedSmem) & 127u)) & 127u);  // even levels; odd levels behind it
+    auto buf = [&](int parity) { return buf0 + (parity ? A.bufBytes[0] : 0); };
+    uint8_t* frame = pyr + (size_t)(A.f0 + f) * g.pyrFrameBytes;
+
+    // writes level l from its shared-memory tile: own pixels + mirrored border.  Own ranges start on multiples of 4 in x
+    // (host plan), so all words but the ones touching the image border are plain word copies (pass 1, no divergence);
+    // the border words of edge tiles go byte by byte through the reflection (pass 2, lanes = those words only).
+    auto write_level = [&](int l, const uint8_t* tile, int pitch, int ox, int oy) {
+        const LevelGeom& L = g.L[l];
+        const FusedAxis X = A.ax[l * A.nTx + tx], Y = A.ay[l * A.nTy + ty];
+        const int bx0 = X.a == 0 ? -EAOF_EDGE : X.a, bx1 = X.b == L.w ? L.w + EAOF_EDGE : X.b;   // bordered own span, inner coordinates
+        const int by0 = Y.a == 0 ? -EAOF_EDGE : Y.a, by1 = Y.b == L.h ? L.h + EAOF_EDGE : Y.b;
+        const int nRows = by1 - by0;
+        uint8_t* out = frame + L.off + EAOF_INNER_X0;                   // inner pixel (x, bordered row r) at out[r*pitch + x]
+        auto refl = [](int p, int len) { return p < 0 ? -p : p >= len ? 2 * (len - 1) - p : p; };  // one fold: levels are >= 40 px
+        // pass 1: whole words inside both the own range and the image
+        const int fx0 = (max(bx0, 0) + 3) & ~3, fx1 = min(bx1, L.w) & ~3;
+        const int nFast = max(fx1 - fx0, 0) >> 2;
+        for (int r = warp; r < nRows; r += nWarps) {
+            const int by = by0 + r;
+            const uint32_t* srow = reinterpret_cast<const uint32_t*>(tile + (refl(by, L.h) - oy) * pitch + (fx0 - ox));
+            uint32_t* drow = reinterpret_cast<uint32_t*>(out + (size_t)(by + EAOF_EDGE) * L.pitch + fx0);
+            for (int wi = lane; wi < nFast; wi += 32) drow[wi] = srow[wi];
+        }
+        // pass 2: the bytes left and right of the whole words (image border columns, and a ragged last word)
+        const int nLeft = fx0 - bx0, nRight = bx1 - max(fx1, fx0);
+        const int nSlow = nLeft + nRight;
+        if (nSlow > 0) {
+            for (int i = tid; i < nSlow * nRows; i += nThreads) {
+                const int r = i / nSlow, k = i - r * nSlow;
+                const int xx = k < nLeft ? bx0 + k : max(fx1, fx0) + (k - nLeft);
+                const int by = by0 + r;
+                out[(size_t)(by + EAOF_EDGE) * L.pitch + xx] = tile[(refl(by, L.h) - oy) * pitch + refl(xx, L.w) - ox];
+            }
+        }
+    };
+
+    // ---- level 0: the needed region of the input frame
+    const FusedAxis X0 = A.ax[tx], Y0 = A.ay[ty];
+    int ox = X0.lo & ~15, oy = Y0.lo;    // tile origin (x rounded down: TMA's 16-byte rule, and word alignment)
+    {
+        uint8_t* t0 = buf(0);
+        const int pitch0 = A.pitchT[0];
+        if (A.useTma) {
+            const uint32_t bar = smem_u32(&fusedBar);
+            if (tid == 0) {
+                mbar_init(bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, (uint32_t)(A.boxW0 * A.boxH0));
+                tma_load_3d(smem_u32(t0), &inMap.m[0][0], ox, oy, f, bar);
+            }
+            __syncthreads();
+            mbar_wait(bar, 0);
+        } else {
+            const uint8_t* src = A.in + (size_t)f * A.framePitch;
+            const int w = g.L[0].w, h = g.L[0].h;
+            const int nx = min(X0.lo + X0.n, w) - ox, ny = min(Y0.lo + Y0.n, h) - oy;
+            for (int r = warp; r < ny; r += nWarps)
+                for (int cx = lane; cx < nx; cx += 32) t0[r * pitch0 + cx] = __ldg(src + (size_t)(oy + r) * A.stride + ox + cx);
+            __syncthreads();
+        }
+        write_level(0, t0, pitch0, ox, oy);
+    }
+
+    // ---- levels 1 .. n-1
+    for (int l = 1; l < g.nlevels; ++l) {
+        const LevelGeom& D = g.L[l];
+        const LevelGeom& S = g.L[l - 1];
+        const FusedAxis X = A.ax[l * A.nTx + tx], Y = A.ay[l * A.nTy + ty];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(buf((l - 1) & 1));
+        uint8_t* dst = buf(l & 1);
+        const int pitchSW = A.pitchT[l - 1] >> 2, pitchD = A.pitchT[l];
+        const int oxD = X.lo & ~3, oyD = Y.lo;
+        const int nRows = Y.n;
+        // rows of this tile: word offsets of the two source rows inside the source tile and the packed (b0, b1)
+        for (int r = tid; r < nRows; r += nThreads) {
+            const int y = Y.lo + r;
+            const int sy = __ldg(tabs + D.yTab + 2 * y);
+            const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
+            fusedRows[r] = make_int4((sy0 - oy) * pitchSW, (sy1 - oy) * pitchSW, __ldg(tabs + D.yTab + 2 * y + 1), 0);
+        }
+        __syncthreads();
+        // work item = (word of 4 destination columns, chunk of rows); per-thread constants: source word offsets, byte
+        // selectors and packed (a0, a1) of its 4 columns — the arithmetic of k_resize on shared memory
+        const int nWordsD = (X.lo + X.n - oxD + 3) >> 2;
+        int chunks = nThreads / nWordsD;
+        if (chunks < 1) chunks = 1;
+        if (chunks > nRows) chunks = nRows;
+        const int rowsPer = (nRows + chunks - 1) / chunks;
+        for (int task = tid; task < nWordsD * chunks; task += nThreads) {
+            const int ch = task / nWordsD, wd = task - ch * nWordsD;
+            int wofs[4];
+            unsigned sel[4], coef[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = min(max(oxD + 4 * wd + j, (int)X.lo), X.lo + X.n - 1);  // columns outside the needed range repeat its edge
+                const int sx = __ldg(tabs + D.xTab + 2 * x) - ox;
+                coef[j] = (unsigned)__ldg(tabs + D.xTab + 2 * x + 1);
+                wofs[j] = sx >> 2;
+                sel[j] = (unsigned)(sx & 3) | ((unsigned)((sx & 3) + 1) << 4);  // bytes sx, sx+1 of the word pair; a1 == 0
+            }                                                                    // whenever sx+1 would leave the image
+            auto hrow = [&](int rowW, unsigned (&h)[4]) {
+                const uint32_t* r = src + rowW;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    h[j] = __dp2a_lo(coef[j], __byte_perm(r[wofs[j]], r[wofs[j] + 1], sel[j]), 0u) >> 4;  // every use is (sum >> 4), A.2
+            };
+            const int r0 = ch * rowsPer, r1 = min(r0 + rowsPer, nRows);
+            int cached = -1;
+            unsigned hB[4] = {0, 0, 0, 0};
+            uint32_t* dcol = reinterpret_cast<uint32_t*>(dst) + wd;
+            const int pitchDW = pitchD >> 2;
+            for (int r = r0; r < r1; ++r) {
+                const int4 rw = fusedRows[r];
+                const unsigned b0s = (unsigned)rw.z << 16, b1s = (unsigned)rw.z & 0xffff0000u;
+                unsigned hA[4];
+                if (rw.x == cached) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) hA[j] = hB[j];
+                } else {
+                    hrow(rw.x, hA);
+                }
+                if (rw.y != rw.x) hrow(rw.y, hB);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) hB[j] = hA[j];
+                }
+                cached = rw.y;
+                unsigned d[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = mad_hi_u32(b1s, hB[j], mad_hi_u32(b0s, hA[j], 2u)) >> 2;  // <= 255
+                dcol[r * pitchDW] = ((d[3] * 256u + d[2]) * 256u + d[1]) * 256u + d[0];
+            }
+        }
+        __syncthreads();
+        write_level(l, dst, pitchD, oxD, oyD);
+        ox = oxD;
+        oy = oyD;
+        // the tile just written becomes the source of the next level; its buffer is not touched again until the level
+        // after that is computed, by which time every thread has passed the barriers above once more
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // FAST-9/16.  Ring offsets k=0..15: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)
 // (-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3).
@@ -766,40 +988,6 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
 #ifndef FASTT_MINB
 #define FASTT_MINB 6
 #endif
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int x, int y, int z, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar)
-        : "memory");
-}
-
-// One CUtensorMap (128 bytes, 64-byte aligned) per pyramid level, passed as a __grid_constant__ kernel parameter (the
-// canonical way: a descriptor that merely sits in global memory would need a fence.proxy.tensormap acquire first).
-struct alignas(64) FastTmaMaps {
-    unsigned long long m[EAOF_MAX_LEVELS][16];
-};
 
 struct FastTmaArgs {
     int boxW, boxH;      // box = tile geometry: boxW bytes per row (multiple of 16), boxH rows

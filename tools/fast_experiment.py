@@ -50,6 +50,15 @@ def main():
     d0, t0, w0 = run(0, d, B, W, H, nf)
     d1, t1, w1 = run(1, d, B, W, H, nf)
     d2, t2, w2 = run(2, d, B, W, H, nf)
+    if os.environ.get("EAOF_EXPERIMENT") == "pyramid":
+        os.environ["EAOF_PYR_FUSED"] = "0"
+        dp, tp, wp = run(0, d, B, W, H, nf)
+        os.environ["EAOF_PYR_FUSED"] = "2"
+        d0, t0, w0 = run(0, d, B, W, H, nf)
+        os.environ["EAOF_PYR_FUSED"] = "1"
+        print(f"{name} B={B}: per-level pyramid={tp['pyramid']:.3f} batch={wp:.3f} | fused pyramid={t0['pyramid']:.3f} batch={w0:.3f} ms | "
+              f"same output: {dp == d0}", flush=True)
+        return
     print(f"{os.path.basename(os.environ.get('EAOF_LIB_PATH', 'default'))} {name} B={B}: ldg fast={t0['fast']:.3f} batch={w0:.3f} | "
           f"tma-persistent fast={t1['fast']:.3f} batch={w1:.3f} | tma-oneshot fast={t2['fast']:.3f} batch={w2:.3f} ms | "
           f"same output: {d0 == d1 == d2}", flush=True)
