@@ -134,6 +134,7 @@ struct eaof_orb {
     int fusedMapN = 0;
     void* encodeTiled = nullptr;  // cuTensorMapEncodeTiled
     int fastTma = 0;  // 0: k_fast (LDG-staged tile), 1: k_fast_tma (persistent, double-buffered TMA), 2: k_fast_tma1
+    bool fastGeneric = false;  // k_fast_generic instead of k_fast (geometry / thresholds outside what fast_cell_rows covers)
     int fastTmaGrid = 0;
     size_t fastTmaSmem = 0;
     bool profiling = false;
@@ -185,7 +186,7 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
     uint64_t off = 0;
     uint32_t candOff = 0;
     int slotOff = 0;
-    int fastRows = 7, fastWords = 2, fastList = 160, fastOut = 1;
+    int fastRows = 7, fastWords = 2, fastList = 160, fastOut = 1, fastInnerWords = 1;
     for (int l = 0; l < g.nlevels; ++l) {
         LevelGeom& L = g.L[l];
         L.w = cv_round_f((float)g.W * c->invScale[l]);  // :1112
@@ -249,10 +250,11 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
                     const int nW = ((mis + cw - 4) >> 2) - ((mis + 3) >> 2) + 1;
                     fastRows = std::max(fastRows, ch);
                     fastWords = std::max(fastWords, nwords);
+                    fastInnerWords = std::max(fastInnerWords, nW);
 #ifdef FAST_LIST_CAP
                     fastList = FAST_LIST_CAP;
 #else
-                    fastList = std::max(fastList, std::max(2 * (ch - 6) * nW, 160));  // k_fast refills it in rounds of <= 128
+                    fastList = std::max(fastList, std::max(4 * (ch - 6) * nW, 160));  // every pixel of the inner rows (fast_cell_rows lists a whole attempt at once)
 #endif
                     fastOut = std::max(fastOut, ((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2));
                 }
@@ -296,7 +298,10 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
     g.fastPW = (fastWords + 2) | 1;  // one pad word on the left, one spare on the right (phase A reads word w+1), odd pitch
     g.fastMapWords = std::max(fastRows * g.fastPW + 2, fastOut);
     g.fastMapWords = (g.fastMapWords + 3) & ~3;
-    g.fastWarpWords = (2 * g.fastMapWords + FAST_CLST / 2 + (fastList + 1) / 2 + 3) & ~3;
+    g.fastWarpWords = (2 * g.fastMapWords + FAST_CLST2 + 2 * FAST_ROWS2 + (fastList + 1) / 2 + 3) & ~3;
+    // fast_cell_rows (k_fast) covers rows of <= 16 inner words and minThFAST < iniThFAST < 128; anything else runs k_fast_generic
+    c->fastGeneric = fastInnerWords > 16 || fastRows - 6 > FAST_ROWS2 || !(g.minTh < g.iniTh && g.iniTh < 128);
+    if (const char* e = getenv("EAOF_FAST_GENERIC")) if (*e) c->fastGeneric = atoi(e) != 0;
     g.pyrFrameBytes = off + 4096;  // slack: tile loaders may read a few bytes past the last row
     g.candPerFrame = candOff;
     g.slotsPerFrame = slotOff;
@@ -520,8 +525,12 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         ++launches;
     } else if (g.cellsPerFrame > 0) {
         const size_t smem = (size_t)FAST_WARPS * g.fastWarpWords * 4;
-        eaof::k_fast<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
-            dPyr, c->dCells, dCand, dCandCount, g);
+        if (c->fastGeneric)
+            eaof::k_fast_generic<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
+                dPyr, c->dCells, dCand, dCandCount, g);
+        else
+            eaof::k_fast<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
+                dPyr, c->dCells, dCand, dCandCount, g);
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[2], s));
@@ -690,10 +699,12 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     // k_fast: a few KB of shared memory per warp — ask for the largest carve-out so that shared memory does not cap the
     // resident warps below what the register file allows
     cudaFuncSetAttribute(eaof::k_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(eaof::k_fast_generic, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if ((size_t)FAST_WARPS * g.fastWarpWords * 4 > 48 * 1024) {
         static std::mutex muF;
         std::lock_guard<std::mutex> lk(muF);
         CKD(cudaFuncSetAttribute(eaof::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CKD(cudaFuncSetAttribute(eaof::k_fast_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     {
         // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)

@@ -927,6 +927,256 @@ __device__ __forceinline__ void fast_cell(uint32_t* tile, uint32_t* Bm, uint16_t
     for (int i = lane; i < no; i += 32) dst[i] = outl[i];
 }
 
+// ---- fast_cell_rows: the same search with LANE = ROW in the pre-test -------------------------------------------------
+// Phase (A) of fast_cell spends more issue slots on bookkeeping than on the test: a task index -> (row, word) division,
+// five shared-memory loads per word, and four ballots + prefix + store per word to compact the survivors.  Here a lane
+// walks one row of the cell from left to right instead: the word to the right becomes the centre word of the next step
+// (three loads per word), and the survivors of the row are collected as a bit mask in two registers — word k of the row,
+// pixel j -> bit 8j + (k & 7) of register k >> 3 — with one shift + OR per word and NO warp vote.  The odd tile pitch
+// makes "same column, 32 consecutive rows" conflict-free.  One warp scan over the per-row counts then gives every lane its
+// place in the survivor list, and a lane emits its own row's pixels (one FLO + a few ALU per survivor).  Columns outside
+// the inner area of the cell are masked before emission, so phase (B) no longer scores pixels cv::FAST never looks at.
+// The iniThFAST masks are parked in shared memory: the minThFAST attempt of an empty cell (:808-816) lists and scores only
+// the pixels that pass the pre-test at minThFAST but did not at iniThFAST; pixels scored by the first attempt whose arc
+// score lies in (minThFAST, iniThFAST] were appended to the corner list together with that score (they are not corners at
+// iniThFAST: their score is not in the map during the first NMS) and are written to the map before the second.
+// The code is kept small on purpose — one instance of every phase serves both attempts and all row rounds: with one-warp
+// CTAs at unrelated program counters an unrolled 6000-instruction version of this function spent a third of its stall
+// samples waiting for instruction fetch.
+// Requires nW <= 16 words per row, <= 64 rows and minThFAST < iniThFAST < 128: eaof_orb_create picks k_fast_generic otherwise.
+#define FAST_CLST2 128  // corner list entries (u32: row << 8 | tile byte column | score << 16)
+#define FAST_ROWS2 64   // rows whose masks are parked
+template <int PAD>
+__device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uint32_t* clst, uint16_t* lst, uint2* rowMask,
+                                               const CellDesc c, const int f, const int mis, const int PW, const int lane,
+                                               uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount, const Geom& g) {
+    uint32_t* outl = tile;
+    const LevelGeom& L = g.L[c.level];
+    const int cw = c.cw, ch = c.ch;
+    const int ih = ch - 6;
+    const int cLo = mis + 3, cHi = mis + cw - 4;  // first / last valid tile byte column
+    const int wLo = cLo >> 2, nW = (cHi >> 2) - wLo + 1;
+    const unsigned below = (1u << lane) - 1;
+    const int pitchB = 4 * PW;
+    const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+    uint8_t* mb = reinterpret_cast<uint8_t*>(Bm);
+    // valid-column masks in the row-mask layout (warp-uniform)
+    unsigned vm0, vm1;
+    {
+        const int n0 = min(nW, 8), n1 = nW - 8;
+        vm0 = 0x01010101u * ((1u << n0) - 1u);
+        vm1 = n1 > 0 ? 0x01010101u * ((1u << n1) - 1u) : 0u;
+        vm0 &= ~(((1u << (8 * (cLo & 3))) - 1u) & 0x01010101u);  // first word: pixels j < cLo & 3 lie left of the inner area
+        const int kl = (nW - 1) & 7, jl = cHi & 3;               // last word: pixels j > cHi & 3 lie right of it
+        const unsigned clr = jl < 3 ? (0x01010101u << kl) & ~((2u << (8 * jl + kl)) - 1u) : 0u;
+        if (nW > 8) vm1 &= ~clr; else vm0 &= ~clr;
+    }
+    const int nGroups = (nW + 3) >> 2;
+
+    int no = 0;
+    int ncorn = 0;       // entries of clst (capped at FAST_CLST2 when it overflowed)
+    bool ovf = false;    // more corners above minThFAST than clst holds
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2 && no == 0; ++attempt) {
+        const int th = attempt == 0 ? g.iniTh : g.minTh;
+        const unsigned thK = (unsigned)(127 - th) * 0x01010101u;
+        if (attempt == 1) {
+            if (!ovf) {
+                // scores in (minTh, iniTh] found by the first attempt become corners now
+                for (int i = lane; i < ncorn; i += 32) {
+                    const unsigned e = clst[i];
+                    mb[(((e >> 8) & 255u) * PW + PAD) * 4 + (e & 255u)] = (uint8_t)(e >> 16);
+                }
+            } else {
+                ncorn = 0;  // the list lost entries: every survivor is scored again, the map is complete afterwards
+            }
+        }
+        // ---- (A) + emission, 32 rows at a time
+        int nl = 0;
+#pragma unroll 1
+        for (int r0 = 0; r0 < ih; r0 += 32) {
+            const int r = r0 + lane;
+            unsigned acc0 = 0u, acc1 = 0u;
+            if (r < ih) {
+                // words beyond nW (the unrolled groups of four) read the rest of the tile row or the row below: masked by vm
+                const uint32_t* t = tile + (r + 3) * PW + PAD + wLo;
+                unsigned Wm = t[-1], W0 = t[0];
+#pragma unroll 1
+                for (int gi = 0; gi < nGroups; ++gi, t += 4) {
+                    unsigned x = 0u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const unsigned Wp = t[i + 1], Wu = t[i - 3 * PW], Wd = t[i + 3 * PW];
+                        const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
+                        const unsigned a0 = __vabsdiffu4(W0, Wd), a8 = __vabsdiffu4(W0, Wu);
+                        const unsigned a4 = __vabsdiffu4(W0, V4), a12 = __vabsdiffu4(W0, V12);
+                        const unsigned t0 = (a0 & 0x7f7f7f7fu) + thK, t8 = (a8 & 0x7f7f7f7fu) + thK;
+                        const unsigned t4 = (a4 & 0x7f7f7f7fu) + thK, t12 = (a12 & 0x7f7f7f7fu) + thK;
+                        const unsigned m = ((t0 | a0) | (t8 | a8)) & ((t4 | a4) | (t12 | a12)) & 0x80808080u;
+                        x |= m >> (3 - i);  // word 4 gi + i -> bit 4 + i of every byte
+                        Wm = W0;
+                        W0 = Wp;
+                    }
+                    x = (gi & 1) ? x : x >> 4;
+                    if (gi < 2) acc0 |= x; else acc1 |= x;
+                }
+                acc0 &= vm0;
+                acc1 &= vm1;
+                if (attempt == 0) {
+                    rowMask[r] = make_uint2(acc0, acc1);
+                } else if (!ovf) {
+                    const uint2 o = rowMask[r];  // known not to be corners at minTh either (or already listed): not scored again
+                    acc0 &= ~o.x;
+                    acc1 &= ~o.y;
+                }
+            }
+            const int cnt = __popc(acc0) + __popc(acc1);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            uint16_t* p = lst + nl + (incl - cnt);
+            nl += __shfl_sync(0xffffffffu, incl, 31);
+            const unsigned e0 = ((unsigned)(r + 3) << 8) | ((unsigned)wLo << 2);
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+                unsigned m = q ? acc1 : acc0;
+                const unsigned eq = e0 + 32u * q;
+                while (m) {
+                    const int b = 31 - __clz((int)m);
+                    m ^= 1u << b;
+                    *p++ = (uint16_t)(eq + ((b & 7) << 2) + (b >> 3));
+                }
+            }
+        }
+        ovf = false;
+        __syncwarp();
+        // ---- (B) as in fast_cell: two list entries per lane on u16x2; every pixel with score > minTh is listed, only
+        // corners at the threshold of this attempt are written to the map
+        const int thW = g.minTh;
+#pragma unroll 1
+        for (int p0 = 0; p0 < nl; p0 += 64) {
+            const int iA = p0 + 2 * lane;
+            const bool actA = iA < nl, actB = iA + 1 < nl;
+            const int eA = lst[actA ? iA : 0], eB = lst[actB ? iA + 1 : (actA ? iA : 0)];
+            const int oA = ((eA >> 8) * PW + PAD) * 4 + (eA & 255), oB = ((eB >> 8) * PW + PAD) * 4 + (eB & 255);
+            const uint8_t* pA = tb + oA;
+            const uint8_t* pB = tb + oB;
+            const unsigned nc = FAST_BIAS2 - ((unsigned)pA[0] | ((unsigned)pB[0] << 16));
+            unsigned d[16];
+#define RING2(k, off) d[k] = ((unsigned)pA[off] | ((unsigned)pB[off] << 16)) + nc;
+            RING2(0, 3 * pitchB) RING2(1, 3 * pitchB + 1) RING2(2, 2 * pitchB + 2) RING2(3, pitchB + 3)
+            RING2(4, 3) RING2(5, -pitchB + 3) RING2(6, -2 * pitchB + 2) RING2(7, -3 * pitchB + 1)
+            RING2(8, -3 * pitchB) RING2(9, -3 * pitchB - 1) RING2(10, -2 * pitchB - 2) RING2(11, -pitchB - 3)
+            RING2(12, -3) RING2(13, pitchB - 3) RING2(14, 2 * pitchB - 2) RING2(15, 3 * pitchB - 1)
+#undef RING2
+            const unsigned b2 = arc_best2(d);
+            const int bLo = (int)(b2 & 0xffffu) - 256, bHi = (int)(b2 >> 16) - 256;
+            const bool k0 = actA && bLo > thW, k2 = actB && bHi > thW;
+            if (k0 && bLo > th) mb[oA] = (uint8_t)bLo;
+            if (k2 && bHi > th) mb[oB] = (uint8_t)bHi;
+            const unsigned m0 = __ballot_sync(0xffffffffu, k0), m2 = __ballot_sync(0xffffffffu, k2);
+            const int p0c = ncorn + __popc(m0 & below), p2c = ncorn + __popc(m0) + __popc(m2 & below);
+            if (k0 && p0c < FAST_CLST2) clst[p0c] = (uint32_t)eA | ((uint32_t)bLo << 16);
+            if (k2 && p2c < FAST_CLST2) clst[p2c] = (uint32_t)eB | ((uint32_t)bHi << 16);
+            ncorn += __popc(m0) + __popc(m2);
+        }
+        __syncwarp();
+        if (ncorn > FAST_CLST2) {
+            ovf = true;
+            ncorn = FAST_CLST2;
+        }
+        if (ncorn == 0) continue;
+        // ---- (C)
+        if (!ovf) {
+#pragma unroll 1
+            for (int i0 = 0; i0 < ncorn; i0 += 32) {
+                const bool act = i0 + lane < ncorn;
+                const unsigned e = clst[act ? i0 + lane : 0];
+                const int y = (e >> 8) & 255, col = e & 255, s = (int)(e >> 16) - 1;
+                const uint8_t* q = reinterpret_cast<const uint8_t*>(Bm + y * PW + PAD) + col;
+                int nbMax = 0;  // stored scores are either 0 or > th
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dx == 0 && dy == 0) continue;
+                        nbMax = max(nbMax, (int)q[dy * pitchB + dx]);
+                    }
+                // listed pixels with a score <= th are not corners in this attempt
+                const bool keep = act && s >= th && s > (nbMax > 0 ? nbMax - 1 : 0);
+                const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int x = col - mis;  // cell coordinates
+                    const int wx = x + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
+                    outl[no + __popc(mk & below)] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
+                }
+                no += __popc(mk);
+            }
+        } else {  // more corners than the list holds (noise-like cells): scan the score map of the inner area
+            const int nTasks = ih * nW * 4;
+            const unsigned rcpW = (1u << 20) / (unsigned)(4 * nW) + 1u;  // exact for i < 4096, divisor <= 64
+#pragma unroll 1
+            for (int i0 = 0; i0 < nTasks; i0 += 32) {
+                const int i = min(i0 + lane, nTasks - 1);
+                const int r = (int)(((unsigned)i * rcpW) >> 20);
+                const int bc = 4 * wLo + (i - r * 4 * nW), y = r + 3;
+                const uint8_t* q = reinterpret_cast<const uint8_t*>(Bm + y * PW + PAD) + bc;
+                const int s = (i0 + lane < nTasks ? (int)q[0] : 0) - 1;
+                bool keep = false;
+                if (s >= 0) {
+                    int nbMax = 0;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            if (dx == 0 && dy == 0) continue;
+                            nbMax = max(nbMax, (int)q[dy * pitchB + dx]);
+                        }
+                    keep = s > (nbMax > 0 ? nbMax - 1 : 0);
+                }
+                const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    const int wx = bc - mis + c.iniX - EAOF_MIN_BORDER, wy = y + c.iniY - EAOF_MIN_BORDER;
+                    outl[no + __popc(mk & below)] = (uint32_t)wx | ((uint32_t)wy << 12) | ((uint32_t)s << 24);
+                }
+                no += __popc(mk);
+            }
+        }
+        __syncwarp();
+    }
+    if (no == 0) return;
+    uint32_t gBase = 0;
+    if (lane == 0) gBase = atomicAdd(&candCount[f * g.nlevels + c.level], (uint32_t)no);
+    gBase = __shfl_sync(0xffffffffu, gBase, 0);
+    uint32_t* dst = cand + (size_t)f * g.candPerFrame + L.candOff + gBase;
+    for (int i = lane; i < no; i += 32) dst[i] = outl[i];
+}
+
+// Tile of one cell -> shared memory, score map cleared (one warp)
+__device__ __forceinline__ void fast_stage_tile(const uint8_t* __restrict__ pyr, uint32_t* tile, uint32_t* Bm, const CellDesc c,
+                                                const int f, const int lane, const Geom& g) {
+    const LevelGeom& L = g.L[c.level];
+    const int PW = g.fastPW, ch = c.ch;
+    const int col0 = EAOF_INNER_X0 + c.iniX;
+    const int mis = col0 & 3;  // cell pixel x sits at tile byte column mis + x
+    const int nwords = (mis + c.cw + 3) >> 2;
+    const uint32_t* src32 = reinterpret_cast<const uint32_t*>(
+        pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + c.iniY) * L.pitch + (col0 - mis));
+    const int pitchW = L.pitch >> 2;
+    if (2 * nwords <= 32) {  // two rows per pass
+        const int half = lane >= 16, wl = lane & 15;
+        if (wl < nwords)
+            for (int r = half; r < ch; r += 2) tile[r * PW + 1 + wl] = __ldg(src32 + r * pitchW + wl);
+    } else if (lane < nwords) {
+        for (int r = 0; r < ch; ++r) tile[r * PW + 1 + lane] = __ldg(src32 + r * pitchW + lane);
+    }
+    for (int i = lane; i < g.fastMapWords / 4; i += 32) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8_t* __restrict__ pyr,
                                                                      const CellDesc* __restrict__ cells,
                                                                      uint32_t* __restrict__ cand,
@@ -936,38 +1186,41 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cell = blockIdx.x * FAST_WARPS + warp;
     if (cell >= g.cellsPerFrame) return;
-    const int PW = g.fastPW;                     // tile / score pitch in words: 1 pad word + data words
     const int mapWords = g.fastMapWords;         // multiple of 4
     uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;  // pixel (row r, tile byte column c) at byte (r*PW + 1)*4 + c
     uint32_t* Bm = tile + mapWords;              // arc score of corners (0 elsewhere), same layout
-    uint16_t* clst = reinterpret_cast<uint16_t*>(Bm + mapWords);  // corners found by (B): (row, tile byte column)
-    uint16_t* lst = clst + FAST_CLST;                             // surviving (row, word, pixel pair (0,1) or (2,3))
+    uint32_t* clst = Bm + mapWords;              // corners found by (B): row << 8 | tile byte column | score << 16
+    uint2* rowMask = reinterpret_cast<uint2*>(clst + FAST_CLST2);         // iniThFAST pre-test masks per row
+    uint16_t* lst = reinterpret_cast<uint16_t*>(rowMask + FAST_ROWS2);    // surviving pixels: row << 8 | tile byte column
     const CellDesc c = cells[cell];
     const int f = blockIdx.y;
-    const LevelGeom& L = g.L[c.level];
-    const int cw = c.cw, ch = c.ch;
-    const int ih = ch - 6;
-    if (cw <= 6 || ih <= 0) return;
+    if (c.cw <= 6 || c.ch <= 6) return;
+    fast_stage_tile(pyr, tile, Bm, c, f, lane, g);
+    fast_cell_rows<1>(tile, Bm, clst, lst, rowMask, c, f, (EAOF_INNER_X0 + c.iniX) & 3, g.fastPW, lane, cand, candCount, g);
+}
 
-    const int col0 = EAOF_INNER_X0 + c.iniX;
-    const int mis = col0 & 3;  // cell pixel x sits at tile byte column mis + x
-    const int nwords = (mis + cw + 3) >> 2;
-    {
-        const uint32_t* src32 = reinterpret_cast<const uint32_t*>(
-            pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + c.iniY) * L.pitch + (col0 - mis));
-        const int pitchW = L.pitch >> 2;
-        if (2 * nwords <= 32) {  // two rows per pass
-            const int half = lane >= 16, wl = lane & 15;
-            if (wl < nwords)
-                for (int r = half; r < ch; r += 2) tile[r * PW + 1 + wl] = __ldg(src32 + r * pitchW + wl);
-        } else if (lane < nwords) {
-            for (int r = 0; r < ch; ++r) tile[r * PW + 1 + lane] = __ldg(src32 + r * pitchW + lane);
-        }
-    }
-    for (int i = lane; i < mapWords / 4; i += 32) reinterpret_cast<uint4*>(Bm)[i] = make_uint4(0, 0, 0, 0);
-    __syncwarp();
+// The task-per-word search (fast_cell) for handles whose geometry or thresholds fast_cell_rows does not cover: cells wider
+// than 16 inner words, minThFAST >= iniThFAST, iniThFAST >= 128.  Same shared-memory carve-up as k_fast.
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast_generic(const uint8_t* __restrict__ pyr,
+                                                                             const CellDesc* __restrict__ cells,
+                                                                             uint32_t* __restrict__ cand,
+                                                                             uint32_t* __restrict__ candCount,
+                                                                             const __grid_constant__ Geom g) {
+    extern __shared__ __align__(16) uint32_t fastSmem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cell = blockIdx.x * FAST_WARPS + warp;
+    if (cell >= g.cellsPerFrame) return;
+    const int mapWords = g.fastMapWords;
+    uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;
+    uint32_t* Bm = tile + mapWords;
+    uint16_t* clst = reinterpret_cast<uint16_t*>(Bm + mapWords);
+    uint16_t* lst = clst + FAST_CLST;
+    const CellDesc c = cells[cell];
+    const int f = blockIdx.y;
+    if (c.cw <= 6 || c.ch <= 6) return;
+    fast_stage_tile(pyr, tile, Bm, c, f, lane, g);
     const int lstCap = 2 * (g.fastWarpWords - 2 * mapWords) - FAST_CLST;  // entries the survivor list holds
-    fast_cell<1>(tile, Bm, clst, lst, lstCap, c, f, mis, PW, lane, cand, candCount, g);
+    fast_cell<1>(tile, Bm, clst, lst, lstCap, c, f, (EAOF_INNER_X0 + c.iniX) & 3, g.fastPW, lane, cand, candCount, g);
 }
 
 // ---- k_fast_tma: the same cell search with the tile staged by TMA --------------------------------------------------
