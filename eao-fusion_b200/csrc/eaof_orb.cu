@@ -134,6 +134,7 @@ struct eaof_orb {
     int fusedMapN = 0;
     void* encodeTiled = nullptr;  // cuTensorMapEncodeTiled
     int fastTma = 0;  // 0: k_fast (LDG-staged tile), 1: k_fast_tma (persistent, double-buffered TMA), 2: k_fast_tma1
+    void (*fastKernel)(const uint8_t*, const CellDesc*, uint32_t*, uint32_t*, const Geom) = nullptr;  // k_fast<PW> of this geometry
     bool fastGeneric = false;  // k_fast_generic instead of k_fast (geometry / thresholds outside what fast_cell_rows covers)
     int fastTmaGrid = 0;
     size_t fastTmaSmem = 0;
@@ -295,12 +296,12 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
         g.blurTasksPerFrame += ((L.w + 3) / 4) * ((L.h + BLUR_ROWS - 1) / BLUR_ROWS);
         if (L.winW + 3 > 4095 || L.winH + 3 > 4095) return fail(EAOF_ERR_UNSUPPORTED, "frames larger than 4096 px are not supported");
     }
-    g.fastPW = (fastWords + 2) | 1;  // one pad word on the left, one spare on the right (phase A reads word w+1), odd pitch
+    g.fastPW = std::max((fastWords + 2) | 1, 11);  // one pad word on the left, one spare on the right (phase A reads word w+1), odd pitch; k_fast<PW> is instantiated for 11..21
     g.fastMapWords = std::max(fastRows * g.fastPW + 2, fastOut);
     g.fastMapWords = (g.fastMapWords + 3) & ~3;
-    g.fastWarpWords = (2 * g.fastMapWords + FAST_CLST2 + 2 * FAST_ROWS2 + (fastList + 1) / 2 + 3) & ~3;
+    g.fastWarpWords = (2 * g.fastMapWords + FAST_CLST2 / 2 + (fastList + 1) / 2 + 3) & ~3;
     // fast_cell_rows (k_fast) covers rows of <= 16 inner words and minThFAST < iniThFAST < 128; anything else runs k_fast_generic
-    c->fastGeneric = fastInnerWords > 16 || fastRows - 6 > FAST_ROWS2 || !(g.minTh < g.iniTh && g.iniTh < 128);
+    c->fastGeneric = fastInnerWords > 16 || g.fastPW > 21 || g.iniTh >= 128 || g.minTh >= 128 || g.iniTh < 0 || g.minTh < 0;
     if (const char* e = getenv("EAOF_FAST_GENERIC")) if (*e) c->fastGeneric = atoi(e) != 0;
     g.pyrFrameBytes = off + 4096;  // slack: tile loaders may read a few bytes past the last row
     g.candPerFrame = candOff;
@@ -529,7 +530,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
             eaof::k_fast_generic<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
                 dPyr, c->dCells, dCand, dCandCount, g);
         else
-            eaof::k_fast<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
+            c->fastKernel<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
                 dPyr, c->dCells, dCand, dCandCount, g);
         ++launches;
     }
@@ -698,12 +699,21 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     }
     // k_fast: a few KB of shared memory per warp — ask for the largest carve-out so that shared memory does not cap the
     // resident warps below what the register file allows
-    cudaFuncSetAttribute(eaof::k_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    switch (g.fastPW) {  // tile pitch as a template parameter (ring offsets become immediates)
+        case 11: c->fastKernel = eaof::k_fast<11>; break;
+        case 13: c->fastKernel = eaof::k_fast<13>; break;
+        case 15: c->fastKernel = eaof::k_fast<15>; break;
+        case 17: c->fastKernel = eaof::k_fast<17>; break;
+        case 19: c->fastKernel = eaof::k_fast<19>; break;
+        case 21: c->fastKernel = eaof::k_fast<21>; break;
+        default: c->fastKernel = eaof::k_fast_generic; c->fastGeneric = true; break;
+    }
+    cudaFuncSetAttribute(c->fastKernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(eaof::k_fast_generic, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if ((size_t)FAST_WARPS * g.fastWarpWords * 4 > 48 * 1024) {
         static std::mutex muF;
         std::lock_guard<std::mutex> lk(muF);
-        CKD(cudaFuncSetAttribute(eaof::k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CKD(cudaFuncSetAttribute(c->fastKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CKD(cudaFuncSetAttribute(eaof::k_fast_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     {

@@ -927,6 +927,31 @@ __device__ __forceinline__ void fast_cell(uint32_t* tile, uint32_t* Bm, uint16_t
     for (int i = lane; i < no; i += 32) dst[i] = outl[i];
 }
 
+// Arc score of two pixels from RAW ring values: r[k] = ring_k of pixel A | ring_k of pixel B << 16, cc = the two centres
+// packed the same way.  max over arcs of min(ring) - centre (brighter) and centre - min over arcs of max(ring) (darker)
+// are translation invariant, so the centre is subtracted once at the end instead of from each of the 16 ring values.
+// Returns 256 + max(bright, dark) per lane like arc_best2.
+__device__ __forceinline__ unsigned arc_best2_raw(const unsigned (&r)[16], const unsigned cc) {
+    unsigned lo3[16], hi3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        lo3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        hi3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    }
+    unsigned best = 0u, worst = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const unsigned a = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+        const unsigned b = __vimin3_u16x2(lo3[k + 1], lo3[(k + 4) & 15], lo3[(k + 7) & 15]);
+        best = __vimax3_u16x2(best, a, b);
+        const unsigned c = __vimax3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+        const unsigned e = __vimax3_u16x2(hi3[k + 1], hi3[(k + 4) & 15], hi3[(k + 7) & 15]);
+        worst = __vimin3_u16x2(worst, c, e);
+    }
+    // every lane value is in 0..255: 256 + best - c and 256 + c - worst stay in 1..511, no borrow or carry crosses the lanes
+    return __vmaxu2(best + (FAST_BIAS2 - cc), (FAST_BIAS2 + cc) - worst);
+}
+
 // ---- fast_cell_rows: the same search with LANE = ROW in the pre-test -------------------------------------------------
 // Phase (A) of fast_cell spends more issue slots on bookkeeping than on the test: a task index -> (row, word) division,
 // five shared-memory loads per word, and four ballots + prefix + store per word to compact the survivors.  Here a lane
@@ -936,20 +961,19 @@ __device__ __forceinline__ void fast_cell(uint32_t* tile, uint32_t* Bm, uint16_t
 // makes "same column, 32 consecutive rows" conflict-free.  One warp scan over the per-row counts then gives every lane its
 // place in the survivor list, and a lane emits its own row's pixels (one FLO + a few ALU per survivor).  Columns outside
 // the inner area of the cell are masked before emission, so phase (B) no longer scores pixels cv::FAST never looks at.
-// The iniThFAST masks are parked in shared memory: the minThFAST attempt of an empty cell (:808-816) lists and scores only
-// the pixels that pass the pre-test at minThFAST but did not at iniThFAST; pixels scored by the first attempt whose arc
-// score lies in (minThFAST, iniThFAST] were appended to the corner list together with that score (they are not corners at
-// iniThFAST: their score is not in the map during the first NMS) and are written to the map before the second.
+// The tile pitch PW (words) is a template parameter: every ring / neighbour offset is then an immediate of the load
+// instead of a register (phase (B) alone formed 14 such addresses per pixel pair).
 // The code is kept small on purpose — one instance of every phase serves both attempts and all row rounds: with one-warp
 // CTAs at unrelated program counters an unrolled 6000-instruction version of this function spent a third of its stall
 // samples waiting for instruction fetch.
-// Requires nW <= 16 words per row, <= 64 rows and minThFAST < iniThFAST < 128: eaof_orb_create picks k_fast_generic otherwise.
-#define FAST_CLST2 128  // corner list entries (u32: row << 8 | tile byte column | score << 16)
-#define FAST_ROWS2 64   // rows whose masks are parked
-template <int PAD>
-__device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uint32_t* clst, uint16_t* lst, uint2* rowMask,
-                                               const CellDesc c, const int f, const int mis, const int PW, const int lane,
+// Requires nW <= 16 words per row and thresholds < 128: eaof_orb_create picks k_fast_generic otherwise.
+#define FAST_CLST2 128  // corner list entries (u16: row << 8 | tile byte column)
+template <int PW>
+__device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uint16_t* clst, uint16_t* lst,
+                                               const CellDesc c, const int f, const int mis, const int lane,
                                                uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount, const Geom& g) {
+    constexpr int PAD = 1;
+    constexpr int pitchB = 4 * PW;
     uint32_t* outl = tile;
     const LevelGeom& L = g.L[c.level];
     const int cw = c.cw, ch = c.ch;
@@ -957,7 +981,6 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
     const int cLo = mis + 3, cHi = mis + cw - 4;  // first / last valid tile byte column
     const int wLo = cLo >> 2, nW = (cHi >> 2) - wLo + 1;
     const unsigned below = (1u << lane) - 1;
-    const int pitchB = 4 * PW;
     const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
     uint8_t* mb = reinterpret_cast<uint8_t*>(Bm);
     // valid-column masks in the row-mask layout (warp-uniform)
@@ -973,24 +996,13 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
     }
     const int nGroups = (nW + 3) >> 2;
 
+    // The cell is first searched at iniThFAST; only a cell with no keypoint after NMS is searched again at minThFAST
+    // (:808-816).  Arc scores are threshold independent, so what the first attempt wrote into the score map stays valid.
     int no = 0;
-    int ncorn = 0;       // entries of clst (capped at FAST_CLST2 when it overflowed)
-    bool ovf = false;    // more corners above minThFAST than clst holds
 #pragma unroll 1
     for (int attempt = 0; attempt < 2 && no == 0; ++attempt) {
         const int th = attempt == 0 ? g.iniTh : g.minTh;
         const unsigned thK = (unsigned)(127 - th) * 0x01010101u;
-        if (attempt == 1) {
-            if (!ovf) {
-                // scores in (minTh, iniTh] found by the first attempt become corners now
-                for (int i = lane; i < ncorn; i += 32) {
-                    const unsigned e = clst[i];
-                    mb[(((e >> 8) & 255u) * PW + PAD) * 4 + (e & 255u)] = (uint8_t)(e >> 16);
-                }
-            } else {
-                ncorn = 0;  // the list lost entries: every survivor is scored again, the map is complete afterwards
-            }
-        }
         // ---- (A) + emission, 32 rows at a time
         int nl = 0;
 #pragma unroll 1
@@ -1008,6 +1020,9 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
                     for (int i = 0; i < 4; ++i) {
                         const unsigned Wp = t[i + 1], Wu = t[i - 3 * PW], Wd = t[i + 3 * PW];
                         const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
+                        // Every 9-arc of the ring holds one of the pixels {0, 8} and one of {4, 12}: a corner at threshold th
+                        // has |ring - centre| > th on one pixel of each pair.  "byte > th" = carry into bit 7 of
+                        // (low 7 bits + 127 - th), or the byte's own top bit.
                         const unsigned a0 = __vabsdiffu4(W0, Wd), a8 = __vabsdiffu4(W0, Wu);
                         const unsigned a4 = __vabsdiffu4(W0, V4), a12 = __vabsdiffu4(W0, V12);
                         const unsigned t0 = (a0 & 0x7f7f7f7fu) + thK, t8 = (a8 & 0x7f7f7f7fu) + thK;
@@ -1022,13 +1037,6 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
                 }
                 acc0 &= vm0;
                 acc1 &= vm1;
-                if (attempt == 0) {
-                    rowMask[r] = make_uint2(acc0, acc1);
-                } else if (!ovf) {
-                    const uint2 o = rowMask[r];  // known not to be corners at minTh either (or already listed): not scored again
-                    acc0 &= ~o.x;
-                    acc1 &= ~o.y;
-                }
             }
             const int cnt = __popc(acc0) + __popc(acc1);
             int incl = cnt;
@@ -1051,11 +1059,10 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
                 }
             }
         }
-        ovf = false;
+        if (nl == 0) continue;
         __syncwarp();
-        // ---- (B) as in fast_cell: two list entries per lane on u16x2; every pixel with score > minTh is listed, only
-        // corners at the threshold of this attempt are written to the map
-        const int thW = g.minTh;
+        // ---- (B): two list entries per lane on u16x2, ring pixels read as bytes
+        int ncorn = 0;  // corners found; the first FAST_CLST2 of them are listed for (C)
 #pragma unroll 1
         for (int p0 = 0; p0 < nl; p0 += 64) {
             const int iA = p0 + 2 * lane;
@@ -1064,39 +1071,35 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
             const int oA = ((eA >> 8) * PW + PAD) * 4 + (eA & 255), oB = ((eB >> 8) * PW + PAD) * 4 + (eB & 255);
             const uint8_t* pA = tb + oA;
             const uint8_t* pB = tb + oB;
-            const unsigned nc = FAST_BIAS2 - ((unsigned)pA[0] | ((unsigned)pB[0] << 16));
+            const unsigned cc = (unsigned)pA[0] | ((unsigned)pB[0] << 16);
             unsigned d[16];
-#define RING2(k, off) d[k] = ((unsigned)pA[off] | ((unsigned)pB[off] << 16)) + nc;
+#define RING2(k, off) d[k] = (unsigned)pA[off] | ((unsigned)pB[off] << 16);
             RING2(0, 3 * pitchB) RING2(1, 3 * pitchB + 1) RING2(2, 2 * pitchB + 2) RING2(3, pitchB + 3)
             RING2(4, 3) RING2(5, -pitchB + 3) RING2(6, -2 * pitchB + 2) RING2(7, -3 * pitchB + 1)
             RING2(8, -3 * pitchB) RING2(9, -3 * pitchB - 1) RING2(10, -2 * pitchB - 2) RING2(11, -pitchB - 3)
             RING2(12, -3) RING2(13, pitchB - 3) RING2(14, 2 * pitchB - 2) RING2(15, 3 * pitchB - 1)
 #undef RING2
-            const unsigned b2 = arc_best2(d);
+            const unsigned b2 = arc_best2_raw(d, cc);
             const int bLo = (int)(b2 & 0xffffu) - 256, bHi = (int)(b2 >> 16) - 256;
-            const bool k0 = actA && bLo > thW, k2 = actB && bHi > thW;
-            if (k0 && bLo > th) mb[oA] = (uint8_t)bLo;
-            if (k2 && bHi > th) mb[oB] = (uint8_t)bHi;
+            const bool k0 = actA && bLo > th, k2 = actB && bHi > th;
+            if (k0) mb[oA] = (uint8_t)bLo;
+            if (k2) mb[oB] = (uint8_t)bHi;
             const unsigned m0 = __ballot_sync(0xffffffffu, k0), m2 = __ballot_sync(0xffffffffu, k2);
             const int p0c = ncorn + __popc(m0 & below), p2c = ncorn + __popc(m0) + __popc(m2 & below);
-            if (k0 && p0c < FAST_CLST2) clst[p0c] = (uint32_t)eA | ((uint32_t)bLo << 16);
-            if (k2 && p2c < FAST_CLST2) clst[p2c] = (uint32_t)eB | ((uint32_t)bHi << 16);
+            if (k0 && p0c < FAST_CLST2) clst[p0c] = (uint16_t)eA;
+            if (k2 && p2c < FAST_CLST2) clst[p2c] = (uint16_t)eB;
             ncorn += __popc(m0) + __popc(m2);
         }
-        __syncwarp();
-        if (ncorn > FAST_CLST2) {
-            ovf = true;
-            ncorn = FAST_CLST2;
-        }
         if (ncorn == 0) continue;
+        __syncwarp();
         // ---- (C)
-        if (!ovf) {
+        if (ncorn <= FAST_CLST2) {
 #pragma unroll 1
             for (int i0 = 0; i0 < ncorn; i0 += 32) {
                 const bool act = i0 + lane < ncorn;
-                const unsigned e = clst[act ? i0 + lane : 0];
-                const int y = (e >> 8) & 255, col = e & 255, s = (int)(e >> 16) - 1;
-                const uint8_t* q = reinterpret_cast<const uint8_t*>(Bm + y * PW + PAD) + col;
+                const int e = clst[act ? i0 + lane : 0], y = e >> 8, col = e & 255;
+                const uint8_t* q = mb + (y * PW + PAD) * 4 + col;
+                const int s = (int)q[0] - 1;
                 int nbMax = 0;  // stored scores are either 0 or > th
 #pragma unroll
                 for (int dy = -1; dy <= 1; ++dy)
@@ -1105,8 +1108,7 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
                         if (dx == 0 && dy == 0) continue;
                         nbMax = max(nbMax, (int)q[dy * pitchB + dx]);
                     }
-                // listed pixels with a score <= th are not corners in this attempt
-                const bool keep = act && s >= th && s > (nbMax > 0 ? nbMax - 1 : 0);
+                const bool keep = act && s > (nbMax > 0 ? nbMax - 1 : 0);  // s > (neighbour corner ? its score : 0), all 8
                 const unsigned mk = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
                     const int x = col - mis;  // cell coordinates
@@ -1123,7 +1125,7 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
                 const int i = min(i0 + lane, nTasks - 1);
                 const int r = (int)(((unsigned)i * rcpW) >> 20);
                 const int bc = 4 * wLo + (i - r * 4 * nW), y = r + 3;
-                const uint8_t* q = reinterpret_cast<const uint8_t*>(Bm + y * PW + PAD) + bc;
+                const uint8_t* q = mb + (y * PW + PAD) * 4 + bc;
                 const int s = (i0 + lane < nTasks ? (int)q[0] : 0) - 1;
                 bool keep = false;
                 if (s >= 0) {
@@ -1155,21 +1157,33 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
     for (int i = lane; i < no; i += 32) dst[i] = outl[i];
 }
 
-// Tile of one cell -> shared memory, score map cleared (one warp)
+// Tile of one cell -> shared memory (pitch PW words, one pad word on the left), score map cleared (one warp).
 __device__ __forceinline__ void fast_stage_tile(const uint8_t* __restrict__ pyr, uint32_t* tile, uint32_t* Bm, const CellDesc c,
-                                                const int f, const int lane, const Geom& g) {
+                                                const int f, const int lane, const int PW, const Geom& g) {
     const LevelGeom& L = g.L[c.level];
-    const int PW = g.fastPW, ch = c.ch;
+    const int ch = c.ch;
     const int col0 = EAOF_INNER_X0 + c.iniX;
     const int mis = col0 & 3;  // cell pixel x sits at tile byte column mis + x
     const int nwords = (mis + c.cw + 3) >> 2;
     const uint32_t* src32 = reinterpret_cast<const uint32_t*>(
         pyr + (size_t)f * g.pyrFrameBytes + L.off + (size_t)(EAOF_EDGE + c.iniY) * L.pitch + (col0 - mis));
     const int pitchW = L.pitch >> 2;
-    if (2 * nwords <= 32) {  // two rows per pass
+    if (2 * nwords <= 32) {  // two rows per pass, four passes per loop trip (their loads in flight together)
         const int half = lane >= 16, wl = lane & 15;
-        if (wl < nwords)
-            for (int r = half; r < ch; r += 2) tile[r * PW + 1 + wl] = __ldg(src32 + r * pitchW + wl);
+        if (wl < nwords) {
+            const uint32_t* s = src32 + (size_t)half * pitchW + wl;
+            uint32_t* d = tile + half * PW + 1 + wl;
+            const size_t step = (size_t)2 * pitchW;
+            int r = half;
+            for (; r + 6 < ch; r += 8, s += 4 * step, d += 8 * PW) {
+                const uint32_t v0 = __ldg(s), v1 = __ldg(s + step), v2 = __ldg(s + 2 * step), v3 = __ldg(s + 3 * step);
+                d[0] = v0;
+                d[2 * PW] = v1;
+                d[4 * PW] = v2;
+                d[6 * PW] = v3;
+            }
+            for (; r < ch; r += 2, s += step, d += 2 * PW) d[0] = __ldg(s);
+        }
     } else if (lane < nwords) {
         for (int r = 0; r < ch; ++r) tile[r * PW + 1 + lane] = __ldg(src32 + r * pitchW + lane);
     }
@@ -1177,6 +1191,7 @@ __device__ __forceinline__ void fast_stage_tile(const uint8_t* __restrict__ pyr,
     __syncwarp();
 }
 
+template <int PW>
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8_t* __restrict__ pyr,
                                                                      const CellDesc* __restrict__ cells,
                                                                      uint32_t* __restrict__ cand,
@@ -1189,14 +1204,13 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     const int mapWords = g.fastMapWords;         // multiple of 4
     uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;  // pixel (row r, tile byte column c) at byte (r*PW + 1)*4 + c
     uint32_t* Bm = tile + mapWords;              // arc score of corners (0 elsewhere), same layout
-    uint32_t* clst = Bm + mapWords;              // corners found by (B): row << 8 | tile byte column | score << 16
-    uint2* rowMask = reinterpret_cast<uint2*>(clst + FAST_CLST2);         // iniThFAST pre-test masks per row
-    uint16_t* lst = reinterpret_cast<uint16_t*>(rowMask + FAST_ROWS2);    // surviving pixels: row << 8 | tile byte column
+    uint16_t* clst = reinterpret_cast<uint16_t*>(Bm + mapWords);  // corners found by (B): row << 8 | tile byte column
+    uint16_t* lst = clst + FAST_CLST2;                            // surviving pixels, same encoding
     const CellDesc c = cells[cell];
     const int f = blockIdx.y;
     if (c.cw <= 6 || c.ch <= 6) return;
-    fast_stage_tile(pyr, tile, Bm, c, f, lane, g);
-    fast_cell_rows<1>(tile, Bm, clst, lst, rowMask, c, f, (EAOF_INNER_X0 + c.iniX) & 3, g.fastPW, lane, cand, candCount, g);
+    fast_stage_tile(pyr, tile, Bm, c, f, lane, PW, g);
+    fast_cell_rows<PW>(tile, Bm, clst, lst, c, f, (EAOF_INNER_X0 + c.iniX) & 3, lane, cand, candCount, g);
 }
 
 // The task-per-word search (fast_cell) for handles whose geometry or thresholds fast_cell_rows does not cover: cells wider
@@ -1218,7 +1232,7 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast_generic(con
     const CellDesc c = cells[cell];
     const int f = blockIdx.y;
     if (c.cw <= 6 || c.ch <= 6) return;
-    fast_stage_tile(pyr, tile, Bm, c, f, lane, g);
+    fast_stage_tile(pyr, tile, Bm, c, f, lane, g.fastPW, g);
     const int lstCap = 2 * (g.fastWarpWords - 2 * mapWords) - FAST_CLST;  // entries the survivor list holds
     fast_cell<1>(tile, Bm, clst, lst, lstCap, c, f, (EAOF_INNER_X0 + c.iniX) & 3, g.fastPW, lane, cand, candCount, g);
 }
