@@ -1013,11 +1013,14 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
                 // words beyond nW (the unrolled groups of four) read the rest of the tile row or the row below: masked by vm
                 const uint32_t* t = tile + (r + 3) * PW + PAD + wLo;
                 unsigned Wm = t[-1], W0 = t[0];
+                unsigned Um = t[-1 - 2 * PW], U0 = t[-2 * PW], Dm = t[-1 + 2 * PW], D0 = t[2 * PW];  // rows y -+ 2 (second attempt)
 #pragma unroll 1
                 for (int gi = 0; gi < nGroups; ++gi, t += 4) {
                     unsigned x = 0u;
+                    unsigned Wc[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
+                        Wc[i] = W0;
                         const unsigned Wp = t[i + 1], Wu = t[i - 3 * PW], Wd = t[i + 3 * PW];
                         const unsigned V4 = __byte_perm(W0, Wp, 0x6543), V12 = __byte_perm(Wm, W0, 0x4321);
                         // Every 9-arc of the ring holds one of the pixels {0, 8} and one of {4, 12}: a corner at threshold th
@@ -1031,6 +1034,28 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
                         x |= m >> (3 - i);  // word 4 gi + i -> bit 4 + i of every byte
                         Wm = W0;
                         W0 = Wp;
+                    }
+                    if (attempt) {
+                        // The minThFAST attempt lets a third of all pixels through the compass test, and each of them costs a
+                        // full arc score.  The same argument holds for the diagonal ring pixels: every 9-arc holds one of
+                        // {2, 10} and one of {6, 14}.  max(a, b) > th is tested on a | b >= max(a, b): conservative for any th
+                        // (exact when th + 1 is a power of two, e.g. the default 7), and a pre-test only has to be necessary.
+                        unsigned y = 0u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const unsigned Up = t[i + 1 - 2 * PW], Dp = t[i + 1 + 2 * PW];
+                            const unsigned a2 = __vabsdiffu4(Wc[i], __byte_perm(D0, Dp, 0x5432));
+                            const unsigned a14 = __vabsdiffu4(Wc[i], __byte_perm(Dm, D0, 0x5432));
+                            const unsigned a6 = __vabsdiffu4(Wc[i], __byte_perm(U0, Up, 0x5432));
+                            const unsigned a10 = __vabsdiffu4(Wc[i], __byte_perm(Um, U0, 0x5432));
+                            const unsigned o1 = a2 | a10, o2 = a6 | a14;
+                            const unsigned u1 = (o1 & 0x7f7f7f7fu) + thK, u2 = (o2 & 0x7f7f7f7fu) + thK;
+                            const unsigned m = (u1 | o1) & (u2 | o2) & 0x80808080u;
+                            y |= m >> (3 - i);
+                            Um = U0; U0 = Up;
+                            Dm = D0; D0 = Dp;
+                        }
+                        x &= y;
                     }
                     x = (gi & 1) ? x : x >> 4;
                     if (gi < 2) acc0 |= x; else acc1 |= x;
@@ -1052,10 +1077,18 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
             for (int q = 0; q < 2; ++q) {
                 unsigned m = q ? acc1 : acc0;
                 const unsigned eq = e0 + 32u * q;
-                while (m) {
-                    const int b = 31 - __clz((int)m);
+                while (m) {  // two survivors per trip
+                    unsigned b, b2;
+                    asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(m));
                     m ^= 1u << b;
-                    *p++ = (uint16_t)(eq + ((b & 7) << 2) + (b >> 3));
+                    p[0] = (uint16_t)(eq + ((b & 7u) << 2) + (b >> 3));
+                    const bool more = m != 0u;
+                    asm("bfind.u32 %0, %1;" : "=r"(b2) : "r"(m));
+                    if (more) {
+                        m ^= 1u << b2;
+                        p[1] = (uint16_t)(eq + ((b2 & 7u) << 2) + (b2 >> 3));
+                    }
+                    p += more ? 2 : 1;
                 }
             }
         }
