@@ -135,6 +135,7 @@ struct eaof_orb {
     void* encodeTiled = nullptr;  // cuTensorMapEncodeTiled
     int fastTma = 0;  // 0: k_fast (LDG-staged tile), 1: k_fast_tma (persistent, double-buffered TMA), 2: k_fast_tma1
     void (*fastKernel)(const uint8_t*, const CellDesc*, uint32_t*, uint32_t*, const Geom) = nullptr;  // k_fast<PW> of this geometry
+    bool rszWindow[EAOF_MAX_LEVELS] = {};  // level l: k_resize's 8-byte source window covers every group of 4 columns
     bool fastGeneric = false;  // k_fast_generic instead of k_fast (geometry / thresholds outside what fast_cell_rows covers)
     int fastTmaGrid = 0;
     size_t fastTmaSmem = 0;
@@ -291,6 +292,20 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
             }
         } else {
             L.yTab = L.xTab;
+        }
+        // k_resize reads the source columns of 4 destination columns from an 8-byte window
+        c->rszWindow[l] = true;
+        if (l > 0) {
+            auto refl = [&](int p) { const int n = L.w; if (n == 1) return 0; while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p; return p; };
+            for (int c0 = 12; c0 < L.w + 52 && c->rszWindow[l]; c0 += 4) {
+                int lo = 1 << 30, hi = -1;
+                for (int j = 0; j < 4; ++j) {
+                    const int sx = tabs[L.xTab + 2 * refl(c0 - EAOF_INNER_X0 + j)];
+                    lo = std::min(lo, sx);
+                    hi = std::max(hi, sx);
+                }
+                if (hi + 1 - lo > 7) c->rszWindow[l] = false;
+            }
         }
         L.blurTaskOff = g.blurTasksPerFrame;
         g.blurTasksPerFrame += ((L.w + 3) / 4) * ((L.h + BLUR_ROWS - 1) / BLUR_ROWS);
@@ -472,7 +487,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     }
     for (int l = 1; l < g.nlevels && !fusedNow; ++l) {
         const LevelGeom& L = g.L[l];
-        if (L.h >= 40) {
+        if (L.h >= 40 && c->rszWindow[l]) {
             // rows per thread: long walks reuse source rows, but small levels / small batches need the threads
 #ifndef RSZ_WANT
 #define RSZ_WANT 600000

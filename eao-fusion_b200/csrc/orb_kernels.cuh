@@ -418,6 +418,10 @@ __device__ __forceinline__ unsigned mad_hi_u32(unsigned a, unsigned b, unsigned 
     asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// The 4 destination columns of a thread read source columns sx_j, sx_j + 1 that lie within 8 consecutive bytes (any scale
+// factor up to 2; eaof_orb_create checks the tables and sends larger steps to k_resize_generic): three aligned words from
+// ONE row pointer (immediate offsets 0 / 4 / 8), two funnel shifts that bring the window's first byte to bit 0, and one
+// PRMT per column with a per-thread constant selector — instead of two loads from a 64-bit address of its own per column.
 template <int RSZ_ROWS>
 __global__ void __launch_bounds__(RSZ_THREADS) k_resize(uint8_t* __restrict__ pyr, const int* __restrict__ tabs,
                                                         const __grid_constant__ Geom g, int l) {
@@ -431,33 +435,41 @@ __global__ void __launch_bounds__(RSZ_THREADS) k_resize(uint8_t* __restrict__ py
     const int f = blockIdx.y;
     uint8_t* frame = pyr + (size_t)f * g.pyrFrameBytes;
     const int c0 = 12 + 4 * cwd;
-    int wofs[4];
+    int sx[4];
     unsigned sel[4], coef[4];
+    int sxMin = 0x7fffffff;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int x = reflect101(c0 - EAOF_INNER_X0 + j, D.w);
-        const int sx = tabs[D.xTab + 2 * x];
-        coef[j] = (unsigned)tabs[D.xTab + 2 * x + 1];
-        wofs[j] = sx >> 2;
-        sel[j] = (unsigned)(sx & 3) | ((unsigned)((sx & 3) + 1) << 4);  // bytes sx, sx+1 of the word pair; a1 == 0
-    }                                                                    // whenever sx+1 would leave the image
-    const uint32_t* sIn = reinterpret_cast<const uint32_t*>(frame + S.off + (size_t)EAOF_EDGE * S.pitch + EAOF_INNER_X0);
+        const int2 e = __ldg(reinterpret_cast<const int2*>(tabs + D.xTab) + x);
+        sx[j] = e.x;
+        coef[j] = (unsigned)e.y;
+        sxMin = min(sxMin, e.x);
+    }
+    const int wofs = sxMin >> 2;
+    const unsigned sh = 8u * (unsigned)(sxMin & 3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned dlt = (unsigned)(sx[j] - sxMin);  // <= 6: bytes dlt, dlt + 1 of the shifted window; a1 == 0 whenever
+        sel[j] = dlt | ((dlt + 1u) << 4);                // sx + 1 would leave the image
+    }
+    const uint32_t* sIn = reinterpret_cast<const uint32_t*>(frame + S.off + (size_t)EAOF_EDGE * S.pitch + EAOF_INNER_X0) + wofs;
     const int sPitchW = S.pitch >> 2;
     uint8_t* dOut = frame + D.off + c0;
     int cached = -1;
     unsigned hB[4] = {0, 0, 0, 0};
     auto hrow = [&](int sy, unsigned (&h)[4]) {
-        const uint32_t* r = sIn + sy * sPitchW;
+        const uint32_t* r = sIn + (ptrdiff_t)sy * sPitchW;
+        const unsigned w0 = __ldg(r), w1 = __ldg(r + 1), w2 = __ldg(r + 2);
+        const unsigned X = __funnelshift_r(w0, w1, sh), Y = __funnelshift_r(w1, w2, sh);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned lo = __ldg(r + wofs[j]), hi = __ldg(r + wofs[j] + 1);
-            h[j] = __dp2a_lo(coef[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;  // every use is (sum >> 4), A.2
-        }
+        for (int j = 0; j < 4; ++j) h[j] = __dp2a_lo(coef[j], __byte_perm(X, Y, sel[j]), 0u) >> 4;  // every use is (sum >> 4), A.2
     };
     const int yEnd = min(y0 + RSZ_ROWS, D.h);
+    const int2* yt = reinterpret_cast<const int2*>(tabs + D.yTab);
     for (int y = y0; y < yEnd; ++y) {
-        const int sy = __ldg(tabs + D.yTab + 2 * y);
-        const int bb = __ldg(tabs + D.yTab + 2 * y + 1);
+        const int2 e = __ldg(yt + y);
+        const int sy = e.x, bb = e.y;
         // (b * (S >> 4)) >> 16 == high word of (b << 16) * (S >> 4): one IMAD.HI (FMA pipe) per product, the second one
         // adding the first and the rounding constant; b in [0, 2048]
         const unsigned b0s = (unsigned)bb << 16, b1s = (unsigned)bb & 0xffff0000u;
