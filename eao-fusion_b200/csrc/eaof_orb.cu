@@ -136,6 +136,9 @@ struct eaof_orb {
     int fastTma = 0;  // 0: k_fast (LDG-staged tile), 1: k_fast_tma (persistent, double-buffered TMA), 2: k_fast_tma1
     void (*fastKernel)(const uint8_t*, const CellDesc*, uint32_t*, uint32_t*, const Geom) = nullptr;  // k_fast<PW> of this geometry
     bool rszWindow[EAOF_MAX_LEVELS] = {};  // level l: k_resize's 8-byte source window covers every group of 4 columns
+    int rszBulkRows[EAOF_MAX_LEVELS] = {};      // k_resize_bulk: destination rows per CTA (0: level not eligible)
+    size_t rszBulkSmem[EAOF_MAX_LEVELS] = {};
+    bool bulkPyr = true;                        // EAOF_PYR_BULK=0: per-thread loads (k_level0 / k_resize) for A/B runs
     bool fastGeneric = false;  // k_fast_generic instead of k_fast (geometry / thresholds outside what fast_cell_rows covers)
     int fastTmaGrid = 0;
     size_t fastTmaSmem = 0;
@@ -307,6 +310,24 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
                 if (hi + 1 - lo > 7) c->rszWindow[l] = false;
             }
         }
+        // k_resize_bulk: shared memory for the source rows of a chunk of 16 (or 8) destination rows
+        c->rszBulkRows[l] = 0;
+        if (l > 0) {
+            const LevelGeom& S = g.L[l - 1];
+            const int srcBytes = (S.w + 12 + 15) & ~15;
+            for (int rows = 16; rows >= 8 && !c->rszBulkRows[l]; rows >>= 1) {
+                int nsMax = 0;
+                for (int y0 = 0; y0 < L.h; y0 += rows) {
+                    const int y1 = std::min(y0 + rows, L.h) - 1;
+                    const int a = std::min(std::max(tabs[L.yTab + 2 * y0], 0), S.h - 1), b = std::min(std::max(tabs[L.yTab + 2 * y1] + 1, 0), S.h - 1);
+                    nsMax = std::max(nsMax, b - a + 1);
+                }
+                if ((size_t)nsMax * srcBytes <= 40 * 1024) {
+                    c->rszBulkRows[l] = rows;
+                    c->rszBulkSmem[l] = (size_t)nsMax * srcBytes;
+                }
+            }
+        }
         L.blurTaskOff = g.blurTasksPerFrame;
         g.blurTasksPerFrame += ((L.w + 3) / 4) * ((L.h + BLUR_ROWS - 1) / BLUR_ROWS);
         if (L.winW + 3 > 4095 || L.winH + 3 > 4095) return fail(EAOF_ERR_UNSUPPORTED, "frames larger than 4096 px are not supported");
@@ -318,6 +339,7 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
     // fast_cell_rows (k_fast) covers rows of <= 16 inner words and minThFAST < iniThFAST < 128; anything else runs k_fast_generic
     c->fastGeneric = fastInnerWords > 16 || g.fastPW > 21 || g.iniTh >= 128 || g.minTh >= 128 || g.iniTh < 0 || g.minTh < 0;
     if (const char* e = getenv("EAOF_FAST_GENERIC")) if (*e) c->fastGeneric = atoi(e) != 0;
+    if (const char* e = getenv("EAOF_PYR_BULK")) if (*e) c->bulkPyr = atoi(e) != 0;
     g.pyrFrameBytes = off + 4096;  // slack: tile loaders may read a few bytes past the last row
     g.candPerFrame = candOff;
     g.slotsPerFrame = slotOff;
@@ -481,13 +503,25 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
             eaof::k_level0_color<3><<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g, c->colorK[0], c->colorK[1], c->colorK[2], c->colorShift);
         else if (c->colorCh == 4)
             eaof::k_level0_color<4><<<gr, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g, c->colorK[0], c->colorK[1], c->colorK[2], c->colorShift);
-        else
+        else if (c->bulkPyr && L.w % 16 == 0 && L.w >= 20 && L.h >= 20 && ((reinterpret_cast<uintptr_t>(dImgs) | stride | framePitch) & 15) == 0) {
+            // copyMakeBorder as bulk asynchronous copies through shared memory
+            const int span = (EAOF_INNER_X0 + L.w + EAOF_EDGE + 15) & ~15;
+            const int rows = span * 16 <= 40 * 1024 ? 16 : span * 8 <= 40 * 1024 ? 8 : 4;
+            eaof::k_level0_bulk<<<dim3((L.h + rows - 1) / rows, n), 128, (size_t)rows * span, s>>>(dImgs, framePitch, stride, dPyr, g, rows);
+        } else
             eaof::k_level0<<<gr8, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g);
         ++launches;
     }
     for (int l = 1; l < g.nlevels && !fusedNow; ++l) {
         const LevelGeom& L = g.L[l];
-        if (L.h >= 40 && c->rszWindow[l]) {
+        if (L.h >= 40 && c->rszWindow[l] && c->bulkPyr && c->rszBulkRows[l]) {
+            // source rows staged in shared memory by bulk asynchronous copies, CTA = chunk of rows over the whole width
+            const int nCW = (L.w + 43) / 4, rows = c->rszBulkRows[l];
+            const int threads = std::min(256, (nCW + 31) & ~31);
+            const dim3 gr((L.h + rows - 1) / rows, n);
+            if (rows == 16) eaof::k_resize_bulk<16><<<gr, threads, c->rszBulkSmem[l], s>>>(dPyr, c->dTabs, g, l);
+            else eaof::k_resize_bulk<8><<<gr, threads, c->rszBulkSmem[l], s>>>(dPyr, c->dTabs, g, l);
+        } else if (L.h >= 40 && c->rszWindow[l]) {
             // rows per thread: long walks reuse source rows, but small levels / small batches need the threads
 #ifndef RSZ_WANT
 #define RSZ_WANT 600000

@@ -56,6 +56,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
         : "memory");
 }
 
+// Bulk asynchronous copies (the 1-D form of TMA: no tensor map, 16-byte aligned addresses and sizes).
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_and_drain() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be released once it has been read
+}
+
 // One CUtensorMap (128 bytes, 64-byte aligned) per pyramid level, passed as a __grid_constant__ kernel parameter (the
 // canonical way: a descriptor that merely sits in global memory would need a fence.proxy.tensormap acquire first).
 struct alignas(64) FastTmaMaps {
@@ -97,6 +111,60 @@ __global__ void __launch_bounds__(256) k_level0(const uint8_t* __restrict__ in, 
                 ((uint32_t)__ldg(src + xs[3]) << 24);
         }
         *reinterpret_cast<uint32_t*>(dst + (size_t)by * L.pitch) = v;
+    }
+}
+
+// k_level0_bulk: the same copyMakeBorder as a pair of bulk asynchronous copies.  Level 0 is a copy of the input with a
+// reflected border; a thread per 4 bytes spends ~100 issue slots on addresses for one load and one store and waits on the
+// load (72 % of k_level0's stall samples).  Here a CTA takes `rowsPerCta` inner rows: one cp.async.bulk per row brings the
+// pixels into shared memory at the byte offset they have inside a padded level row (all rows complete on one mbarrier),
+// the threads write the 19 + 19 reflected border pixels of each row next to them, and one cp.async.bulk per row writes
+// the whole bordered span back; rows that the top / bottom border mirrors are stored a second time from the same bytes.
+// Needs 16-byte aligned input rows (base, stride, frame pitch) and width % 16 == 0, h >= 20: k_level0 otherwise.
+__global__ void __launch_bounds__(128) k_level0_bulk(const uint8_t* __restrict__ in, size_t framePitch, size_t stride,
+                                                     uint8_t* __restrict__ pyr, const __grid_constant__ Geom g, int rowsPerCta) {
+    extern __shared__ __align__(128) uint8_t l0Smem[];
+    __shared__ __align__(8) unsigned long long l0Bar;
+    const LevelGeom& L = g.L[0];
+    const int w = L.w, h = L.h;
+    const int span = (EAOF_INNER_X0 + w + EAOF_EDGE + 15) & ~15;  // bytes [0, span) of a padded row hold the bordered pixels
+    const int y0 = blockIdx.x * rowsPerCta, nr = min(rowsPerCta, h - y0);
+    const int f = blockIdx.y;
+    const uint32_t bar = smem_u32(&l0Bar), base = smem_u32(l0Smem);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)(nr * w));
+    }
+    __syncthreads();
+    if (threadIdx.x < nr)
+        bulk_load(base + threadIdx.x * span + EAOF_INNER_X0, in + (size_t)f * framePitch + (size_t)(y0 + threadIdx.x) * stride, (uint32_t)w, bar);
+    for (int r = threadIdx.x + 128; r < nr; r += 128)
+        bulk_load(base + r * span + EAOF_INNER_X0, in + (size_t)f * framePitch + (size_t)(y0 + r) * stride, (uint32_t)w, bar);
+    mbar_wait(bar, 0);
+    // everything outside the inner pixels: reflected border where the bordered image has pixels, zero elsewhere
+    const int rightN = span - (EAOF_INNER_X0 + w), side = EAOF_INNER_X0 + rightN;
+    for (int i = threadIdx.x; i < nr * side; i += blockDim.x) {
+        const int r = i / side, k = i - r * side;
+        uint8_t* row = l0Smem + r * span;
+        if (k < EAOF_INNER_X0) {  // byte k: pixel x = k - 32 < 0 -> pixel -x
+            const int x = EAOF_INNER_X0 - k;
+            row[k] = x <= EAOF_EDGE ? row[EAOF_INNER_X0 + x] : (uint8_t)0;
+        } else {                  // byte 32 + w + d: pixel w + d -> pixel w - 2 - d
+            const int d = k - EAOF_INNER_X0;
+            row[EAOF_INNER_X0 + w + d] = d < EAOF_EDGE ? row[EAOF_INNER_X0 + w - 2 - d] : (uint8_t)0;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes above -> async-proxy reads below
+    __syncthreads();
+    uint8_t* dst = pyr + (size_t)f * g.pyrFrameBytes + L.off;
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        const int y = y0 + r;
+        const uint32_t src = base + r * span;
+        bulk_store(dst + (size_t)(y + EAOF_EDGE) * L.pitch, src, (uint32_t)span);
+        if (y >= 1 && y <= EAOF_EDGE) bulk_store(dst + (size_t)(EAOF_EDGE - y) * L.pitch, src, (uint32_t)span);
+        if (y >= h - 1 - EAOF_EDGE && y <= h - 2) bulk_store(dst + (size_t)(EAOF_EDGE + 2 * (h - 1) - y) * L.pitch, src, (uint32_t)span);
+        bulk_store_commit_and_drain();
     }
 }
 
@@ -495,6 +563,106 @@ __global__ void __launch_bounds__(RSZ_THREADS) k_resize(uint8_t* __restrict__ py
         if (y >= 1 && y <= EAOF_EDGE) *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE - y) * D.pitch) = v;
         if (y >= D.h - 1 - EAOF_EDGE && y <= D.h - 2)
             *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE + 2 * (D.h - 1) - y) * D.pitch) = v;
+    }
+}
+
+// k_resize_bulk: k_resize with the source rows of a CTA staged in shared memory by bulk asynchronous copies.
+// k_resize is bound by the latency of its global loads (60 % of its stall samples wait on them; a register prefetch queue
+// cost more than it hid).  Here a CTA owns RSZ_ROWS destination rows of one frame over the whole width: warp 0 requests the
+// source rows those need ([sy(y0), sy(yEnd-1) + 1], about 1.2 RSZ_ROWS + 1 rows of S.w + 12 bytes) with one cp.async.bulk per
+// row, all completing on one mbarrier; the threads meanwhile fetch their per-column constants, then run k_resize's row loop
+// with three LDS per source row instead of three LDG (32-bit addresses, ~30 cycles instead of ~600).  Destination rows go
+// straight to global memory as before (one aligned word per thread and row, coalesced), mirrored rows twice.
+template <int RSZ_ROWS>
+__global__ void __launch_bounds__(256) k_resize_bulk(uint8_t* __restrict__ pyr, const int* __restrict__ tabs,
+                                                     const __grid_constant__ Geom g, int l) {
+    extern __shared__ __align__(128) uint8_t rszSmem[];
+    __shared__ __align__(8) unsigned long long rszBar;
+    const LevelGeom& D = g.L[l];
+    const LevelGeom& S = g.L[l - 1];
+    const int y0 = blockIdx.x * RSZ_ROWS, yEnd = min(y0 + RSZ_ROWS, D.h);
+    const int f = blockIdx.y;
+    uint8_t* frame = pyr + (size_t)f * g.pyrFrameBytes;
+    const int2* yt = reinterpret_cast<const int2*>(tabs + D.yTab);
+    const int syA = min(max(__ldg(yt + y0).x, 0), S.h - 1), syB = min(max(__ldg(yt + yEnd - 1).x + 1, 0), S.h - 1);
+    const int nS = syB - syA + 1;
+    const int srcBytes = (S.w + 12 + 15) & ~15;
+    const uint32_t bar = smem_u32(&rszBar), base = smem_u32(rszSmem);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)(nS * srcBytes));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint8_t* src = frame + S.off + (size_t)(EAOF_EDGE + syA) * S.pitch + EAOF_INNER_X0;
+        for (int r = threadIdx.x; r < nS; r += 32) bulk_load(base + r * srcBytes, src + (size_t)r * S.pitch, (uint32_t)srcBytes, bar);
+    }
+    const int nCW = (D.w + 43) >> 2;
+    const int srcWords = srcBytes >> 2;
+    const uint32_t* sW = reinterpret_cast<const uint32_t*>(rszSmem);
+    bool waited = false;
+    for (int cwd = threadIdx.x; cwd < nCW; cwd += blockDim.x) {
+        const int c0 = 12 + 4 * cwd;
+        int sx[4];
+        unsigned sel[4], coef[4];
+        int sxMin = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = reflect101(c0 - EAOF_INNER_X0 + j, D.w);
+            const int2 e = __ldg(reinterpret_cast<const int2*>(tabs + D.xTab) + x);
+            sx[j] = e.x;
+            coef[j] = (unsigned)e.y;
+            sxMin = min(sxMin, e.x);
+        }
+        const unsigned sh = 8u * (unsigned)(sxMin & 3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned dlt = (unsigned)(sx[j] - sxMin);
+            sel[j] = dlt | ((dlt + 1u) << 4);
+        }
+        const int wofs = sxMin >> 2;
+        uint8_t* dOut = frame + D.off + c0;
+        if (!waited) {
+            mbar_wait(bar, 0);
+            waited = true;
+        }
+        int cached = -1;
+        unsigned hB[4] = {0, 0, 0, 0};
+        auto hrow = [&](int sy, unsigned (&h)[4]) {
+            const uint32_t* r = sW + (sy - syA) * srcWords + wofs;
+            const unsigned w0 = r[0], w1 = r[1], w2 = r[2];
+            const unsigned X = __funnelshift_r(w0, w1, sh), Y = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __dp2a_lo(coef[j], __byte_perm(X, Y, sel[j]), 0u) >> 4;
+        };
+        for (int y = y0; y < yEnd; ++y) {
+            const int2 e = __ldg(yt + y);
+            const int sy = e.x, bb = e.y;
+            const unsigned b0s = (unsigned)bb << 16, b1s = (unsigned)bb & 0xffff0000u;
+            const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
+            unsigned hA[4];
+            if (sy0 == cached) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hA[j] = hB[j];
+            } else {
+                hrow(sy0, hA);
+            }
+            if (sy1 != sy0) hrow(sy1, hB);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hB[j] = hA[j];
+            }
+            cached = sy1;
+            unsigned d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = mad_hi_u32(b1s, hB[j], mad_hi_u32(b0s, hA[j], 2u)) >> 2;  // <= 255
+            const uint32_t v = ((d[3] * 256u + d[2]) * 256u + d[1]) * 256u + d[0];
+            *reinterpret_cast<uint32_t*>(dOut + (size_t)(y + EAOF_EDGE) * D.pitch) = v;
+            if (y >= 1 && y <= EAOF_EDGE) *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE - y) * D.pitch) = v;
+            if (y >= D.h - 1 - EAOF_EDGE && y <= D.h - 2)
+                *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE + 2 * (D.h - 1) - y) * D.pitch) = v;
+        }
     }
 }
 
