@@ -634,12 +634,14 @@ __global__ void __launch_bounds__(256) k_resize_bulk(uint8_t* __restrict__ pyr, 
             const unsigned w0 = r[0], w1 = r[1], w2 = r[2];
             const unsigned X = __funnelshift_r(w0, w1, sh), Y = __funnelshift_r(w1, w2, sh);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = __dp2a_lo(coef[j], __byte_perm(X, Y, sel[j]), 0u) >> 4;
+            for (int j = 0; j < 4; ++j) h[j] = __dp2a_lo(coef[j], __byte_perm(X, Y, sel[j]), 0u) >> 4;  // every use is (sum >> 4), A.2
         };
-        for (int y = y0; y < yEnd; ++y) {
+        // one destination row: horizontal pass of the source rows not yet held, vertical pass, packed word
+        auto row = [&](int y) -> uint32_t {
             const int2 e = __ldg(yt + y);
-            const int sy = e.x, bb = e.y;
-            const unsigned b0s = (unsigned)bb << 16, b1s = (unsigned)bb & 0xffff0000u;
+            const int sy = e.x;
+            // b in [0, 2048], h < 2^15: the products fit 32 bits, (b * h) >> 16 is a plain shift (folded into the adds)
+            const unsigned b0 = (unsigned)e.y & 0xffffu, b1 = (unsigned)e.y >> 16;
             const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
             unsigned hA[4];
             if (sy0 == cached) {
@@ -656,12 +658,20 @@ __global__ void __launch_bounds__(256) k_resize_bulk(uint8_t* __restrict__ pyr, 
             cached = sy1;
             unsigned d[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = mad_hi_u32(b1s, hB[j], mad_hi_u32(b0s, hA[j], 2u)) >> 2;  // <= 255
-            const uint32_t v = ((d[3] * 256u + d[2]) * 256u + d[1]) * 256u + d[0];
-            *reinterpret_cast<uint32_t*>(dOut + (size_t)(y + EAOF_EDGE) * D.pitch) = v;
-            if (y >= 1 && y <= EAOF_EDGE) *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE - y) * D.pitch) = v;
-            if (y >= D.h - 1 - EAOF_EDGE && y <= D.h - 2)
-                *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE + 2 * (D.h - 1) - y) * D.pitch) = v;
+            for (int j = 0; j < 4; ++j) d[j] = (((b0 * hA[j]) >> 16) + ((b1 * hB[j]) >> 16) + 2u) >> 2;  // <= 255
+            return ((d[3] * 256u + d[2]) * 256u + d[1]) * 256u + d[0];
+        };
+        uint8_t* o = dOut + (size_t)(y0 + EAOF_EDGE) * D.pitch;
+        if (y0 > EAOF_EDGE && yEnd - 1 < D.h - 1 - EAOF_EDGE) {  // no row of this CTA is mirrored into the border (CTA-uniform)
+            for (int y = y0; y < yEnd; ++y, o += D.pitch) *reinterpret_cast<uint32_t*>(o) = row(y);
+        } else {
+            for (int y = y0; y < yEnd; ++y, o += D.pitch) {
+                const uint32_t v = row(y);
+                *reinterpret_cast<uint32_t*>(o) = v;
+                if (y >= 1 && y <= EAOF_EDGE) *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE - y) * D.pitch) = v;
+                if (y >= D.h - 1 - EAOF_EDGE && y <= D.h - 2)
+                    *reinterpret_cast<uint32_t*>(dOut + (size_t)(EAOF_EDGE + 2 * (D.h - 1) - y) * D.pitch) = v;
+            }
         }
     }
 }
