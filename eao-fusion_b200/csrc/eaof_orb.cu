@@ -119,6 +119,8 @@ struct eaof_orb {
     uint8_t* hDesc = nullptr;
     int* hKpCount = nullptr;
     size_t octSmem = 0;
+    int octKeyCap[3] = {0, 0, 0};  // keys k_octree<256/512/1024> holds in shared memory
+    int octForce = -1;
     // k_fast_tma: one tensor map per pyramid level over the handle's whole pyramid buffer, the work counter, launch shape
     eaof::FastTmaMaps fastMaps{};
     unsigned int* dFastCtr = nullptr;   // [kMaxChunks]
@@ -506,7 +508,8 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         else if (c->bulkPyr && L.w % 16 == 0 && L.w >= 20 && L.h >= 20 && ((reinterpret_cast<uintptr_t>(dImgs) | stride | framePitch) & 15) == 0) {
             // copyMakeBorder as bulk asynchronous copies through shared memory
             const int span = (EAOF_INNER_X0 + L.w + EAOF_EDGE + 15) & ~15;
-            const int rows = span * 16 <= 40 * 1024 ? 16 : span * 8 <= 40 * 1024 ? 8 : 4;
+            int rows = span * 16 <= 40 * 1024 ? 16 : span * 8 <= 40 * 1024 ? 8 : 4;
+            while (rows > 4 && (long long)n * ((L.h + rows - 1) / rows) < 296) rows >>= 1;
             eaof::k_level0_bulk<<<dim3((L.h + rows - 1) / rows, n), 128, (size_t)rows * span, s>>>(dImgs, framePitch, stride, dPyr, g, rows);
         } else
             eaof::k_level0<<<gr8, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g);
@@ -516,11 +519,14 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         const LevelGeom& L = g.L[l];
         if (L.h >= 40 && c->rszWindow[l] && c->bulkPyr && c->rszBulkRows[l]) {
             // source rows staged in shared memory by bulk asynchronous copies, CTA = chunk of rows over the whole width
-            const int nCW = (L.w + 43) / 4, rows = c->rszBulkRows[l];
+            const int nCW = (L.w + 43) / 4;
+            int rows = c->rszBulkRows[l];  // few frames: shorter chunks, so that the level still fills the SMs
+            while (rows > 4 && (long long)n * ((L.h + rows - 1) / rows) < 296) rows >>= 1;
             const int threads = std::min(256, (nCW + 31) & ~31);
             const dim3 gr((L.h + rows - 1) / rows, n);
             if (rows == 16) eaof::k_resize_bulk<16><<<gr, threads, c->rszBulkSmem[l], s>>>(dPyr, c->dTabs, g, l);
-            else eaof::k_resize_bulk<8><<<gr, threads, c->rszBulkSmem[l], s>>>(dPyr, c->dTabs, g, l);
+            else if (rows == 8) eaof::k_resize_bulk<8><<<gr, threads, c->rszBulkSmem[l], s>>>(dPyr, c->dTabs, g, l);
+            else eaof::k_resize_bulk<4><<<gr, threads, c->rszBulkSmem[l], s>>>(dPyr, c->dTabs, g, l);
         } else if (L.h >= 40 && c->rszWindow[l]) {
             // rows per thread: long walks reuse source rows, but small levels / small batches need the threads
 #ifndef RSZ_WANT
@@ -584,8 +590,16 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[2], s));
-    eaof::k_octree<<<dim3(g.nlevels, n), OCT_THREADS, c->octSmem, s>>>(dCand, dCandCount, dLabel, dSlotXY,
-                                                                         dSlotScore, dLvlCount, g);
+    {
+        // CTA width by how many (frame, level) CTAs there are; keys + labels in shared memory up to the width's budget
+        const int ctas = n * g.nlevels;
+        const int v = c->octForce >= 0 ? c->octForce : ctas <= 296 ? 2 : ctas <= 592 ? 1 : 0;
+        const int keyCap = c->octKeyCap[v];
+        const size_t smem = c->octSmem + (size_t)keyCap * 6;
+        if (v == 2) eaof::k_octree<1024><<<dim3(g.nlevels, n), 1024, smem, s>>>(dCand, dCandCount, dLabel, dSlotXY, dSlotScore, dLvlCount, g, keyCap);
+        else if (v == 1) eaof::k_octree<512><<<dim3(g.nlevels, n), 512, smem, s>>>(dCand, dCandCount, dLabel, dSlotXY, dSlotScore, dLvlCount, g, keyCap);
+        else eaof::k_octree<256><<<dim3(g.nlevels, n), 256, smem, s>>>(dCand, dCandCount, dLabel, dSlotXY, dSlotScore, dLvlCount, g, keyCap);
+    }
     ++launches;
     if (prof) CK(cudaEventRecord(c->ev[3], s));
     if (!side) {
@@ -741,6 +755,14 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     for (auto& e : c->ev) CKD(cudaEventCreate(&e));
     c->octSmem = (size_t)g.maxNodeCap * 59 + 64;
     c->octSmem = (c->octSmem + 15) & ~(size_t)15;
+    {
+        // shared-memory budget per CTA width (256 / 512 / 1024 threads): ~7 / 3 / 2 CTAs per SM
+        const size_t budget[3] = {30 * 1024, 64 * 1024, 110 * 1024};
+        for (int v = 0; v < 3; ++v) c->octKeyCap[v] = budget[v] > c->octSmem ? (int)((budget[v] - c->octSmem) / 6) & ~7 : 0;
+        const char* e = getenv("EAOF_OCT_WIDTH");  // 0 / 1 / 2: force a CTA width (A/B runs)
+        c->octForce = e && *e ? atoi(e) : -1;
+        if (const char* k = getenv("EAOF_OCT_KEYS_GLOBAL")) if (*k == '1') c->octKeyCap[0] = c->octKeyCap[1] = c->octKeyCap[2] = 0;
+    }
     if (c->octSmem > 200 * 1024) {
         fail(EAOF_ERR_UNSUPPORTED, "nfeatures too large: quadtree needs %zu B of shared memory", c->octSmem);
         eaof_orb_destroy(c);
@@ -862,9 +884,13 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
         static std::mutex mu;
         static size_t maxSet[64] = {};
         std::lock_guard<std::mutex> lk(mu);
-        if (device < 64 && c->octSmem > maxSet[device]) {
-            CKD(cudaFuncSetAttribute(eaof::k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->octSmem));
-            maxSet[device] = c->octSmem;
+        size_t need = c->octSmem;
+        for (int v = 0; v < 3; ++v) need = std::max(need, c->octSmem + (size_t)c->octKeyCap[v] * 6);
+        if (device < 64 && need > maxSet[device]) {
+            CKD(cudaFuncSetAttribute(eaof::k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CKD(cudaFuncSetAttribute(eaof::k_octree<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CKD(cudaFuncSetAttribute(eaof::k_octree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            maxSet[device] = need;
         }
     }
 #undef CKD

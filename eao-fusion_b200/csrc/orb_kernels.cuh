@@ -1611,7 +1611,11 @@ __global__ void __launch_bounds__(32, 32) k_fast_tma1(const __grid_constant__ Fa
 // 256 threads per (frame, level): the passes are barrier-bound, and twice as many resident CTAs hide more of it than
 // 512-thread CTAs do (measured 0.130 -> 0.102 ms per 250 frames; splitting small and large levels into two launches of
 // different widths was slower than one launch)
-#define OCT_THREADS 256
+// The CTA width is a template parameter chosen per launch: with few (frame, level) CTAs the launch lasts as long as the CTA of
+// the largest level, which then wants 1024 threads; with thousands of CTAs 256-thread ones keep more of them resident.
+// Keys and labels are copied to shared memory when the level's candidates fit the launch's budget (keyCap): every pass
+// reads all keys twice, and from global memory each of those sweeps is a chain of L2 round trips (at 1920x1080 / 4000
+// features the level-0 CTA spent 0.43 ms that way).
 
 struct OctShared {
     int n;        // list size
@@ -1623,6 +1627,7 @@ struct OctShared {
     int warp[32];
 };
 
+template <int OCT_THREADS>
 __device__ __forceinline__ int block_excl_scan(int v, int* total, int* warpSums) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int incl = v;
@@ -1652,11 +1657,12 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total, int* warpSums)
 
 __device__ __forceinline__ int ceil_half(int a) { return (a + 1) >> 1; }  // ceil((float)a/2) for a >= 0
 
-__global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restrict__ cand,
+template <int OCT_THREADS>
+__global__ void __launch_bounds__(OCT_THREADS, OCT_THREADS == 256 ? 6 : OCT_THREADS == 512 ? 2 : 1) k_octree(const uint32_t* __restrict__ cand,
                                                          const uint32_t* __restrict__ candCount,
                                                          uint16_t* __restrict__ label, uint32_t* __restrict__ slotXY,
                                                          uint8_t* __restrict__ slotScore, int* __restrict__ lvlCount,
-                                                         const __grid_constant__ Geom g) {
+                                                         const __grid_constant__ Geom g, const int keyCap) {
     extern __shared__ __align__(16) uint8_t smemRaw[];
     __shared__ OctShared S;
     const int l = blockIdx.x, f = blockIdx.y;
@@ -1680,15 +1686,24 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
     uint8_t* split = wanted + cap;                                        // [cap]
     uint8_t* ne = split + cap;                                            // [cap] non-empty children
 
+    uint32_t* tmpCnt = reinterpret_cast<uint32_t*>(childPos);            // sorted pass only: key counts in tmpIdx order
+    uint32_t* rnk = reinterpret_cast<uint32_t*>(keepPos);                 // sorted pass only: rank accumulators (keepPos + firstChild)
+
     const int nk = (int)candCount[f * g.nlevels + l];
-    const uint32_t* keys = cand + (size_t)f * g.candPerFrame + L.candOff;
-    uint16_t* lab = label + (size_t)f * g.candPerFrame + L.candOff;
+    const uint32_t* gkeys = cand + (size_t)f * g.candPerFrame + L.candOff;
     int* outCount = lvlCount + f * g.nlevels + l;
 
     if (nk == 0 || L.nIni < 1) {
         if (tid == 0) *outCount = 0;
         return;
     }
+    // keys / labels: shared memory behind the node arrays when they fit, else the global candidate / label arrays
+    uint32_t* sKeys = reinterpret_cast<uint32_t*>(smemRaw + ((((size_t)cap * 59 + 64) + 15) & ~(size_t)15));
+    const bool inS = nk <= keyCap;
+    const uint32_t* keys = inS ? sKeys : gkeys;
+    uint16_t* lab = inS ? reinterpret_cast<uint16_t*>(sKeys + keyCap) : label + (size_t)f * g.candPerFrame + L.candOff;
+    if (inS)
+        for (int k = tid; k < nk; k += OCT_THREADS) sKeys[k] = gkeys[k];
 
     // ---- roots (:543-585)
     for (int i = tid; i < cap; i += OCT_THREADS) cc[i] = 0;
@@ -1746,25 +1761,36 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
                 cc[4 * i] = cc[4 * i + 1] = cc[4 * i + 2] = cc[4 * i + 3] = 0;
             }
             int tot;
-            const int e = block_excl_scan(w, &tot, S.warp);
-            if (w) (sorted ? tmpIdx : proc)[mTotal + e] = (uint16_t)i;
+            const int e = block_excl_scan<OCT_THREADS>(w, &tot, S.warp);
+            if (w) {
+                (sorted ? tmpIdx : proc)[mTotal + e] = (uint16_t)i;
+                if (sorted) {
+                    tmpCnt[mTotal + e] = cnt[i];
+                    rnk[mTotal + e] = 0u;
+                }
+            }
             mTotal += tot;
         }
         __syncthreads();
         const int m = mTotal;
         if (sorted) {
-            // rank by (cnt desc, position asc); keys are unique so ranks are a permutation
-            for (int a = tid; a < m; a += OCT_THREADS) {
-                const int pa = tmpIdx[a];
-                const uint32_t ca = cnt[pa];
-                int r = 0;
-                for (int b = 0; b < m; ++b) {
-                    const int pb = tmpIdx[b];
-                    const uint32_t cb = cnt[pb];
-                    r += (cb > ca) || (cb == ca && pb < pa);
+            // rank by (cnt desc, position asc); ranks are a permutation.  tmpIdx is ascending in position, so "position of b <
+            // position of a" is b < a.  The m x m comparisons are dealt to ALL threads: element a x a chunk of b's per thread
+            // (m is a few dozen to a few hundred: one thread per element left most of the CTA idle).
+            const int nCh = m < OCT_THREADS ? OCT_THREADS / m : 1, C = (m + nCh - 1) / nCh;
+            for (int t = tid; t < m * nCh; t += OCT_THREADS) {
+                const int ch = t / m, a = t - ch * m;
+                const int b0 = ch * C, b1 = min(m, b0 + C);
+                const uint32_t ca = tmpCnt[a];
+                unsigned r = 0;
+                for (int b = b0; b < b1; ++b) {
+                    const uint32_t cb = tmpCnt[b];
+                    r += (cb > ca) || (cb == ca && b < a);
                 }
-                proc[r] = (uint16_t)pa;
+                if (nCh > 1) atomicAdd(&rnk[a], r); else rnk[a] = r;
             }
+            __syncthreads();
+            for (int a = tid; a < m; a += OCT_THREADS) proc[rnk[a]] = tmpIdx[a];
             __syncthreads();
         }
         // 2. quadrant populations
@@ -1781,11 +1807,16 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
                     slot = 4 * p + (x < midX ? 0 : 1) + (y < midY ? 0 : 2);
                 }
             }
-            // warp-aggregated shared atomics (early passes put thousands of keys on four counters)
-            const unsigned act = __ballot_sync(0xffffffffu, slot >= 0);
-            if (slot >= 0) {
-                const unsigned peers = __match_any_sync(act, slot);
-                if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&cc[slot], (uint32_t)__popc(peers));
+            // warp-aggregated shared atomics while there are few nodes (early passes put thousands of keys on four
+            // counters); with many nodes the lanes of a warp rarely meet and match_any costs more than it saves
+            if (n <= 16) {
+                const unsigned act = __ballot_sync(0xffffffffu, slot >= 0);
+                if (slot >= 0) {
+                    const unsigned peers = __match_any_sync(act, slot);
+                    if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&cc[slot], (uint32_t)__popc(peers));
+                }
+            } else if (slot >= 0) {
+                atomicAdd(&cc[slot], 1u);
             }
         }
         __syncthreads();
@@ -1802,7 +1833,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
                     v = (cc[4 * p] > 0) + (cc[4 * p + 1] > 0) + (cc[4 * p + 2] > 0) + (cc[4 * p + 3] > 0) - 1;
                 }
                 int tot;
-                const int e = block_excl_scan(v, &tot, S.warp);
+                const int e = block_excl_scan<OCT_THREADS>(v, &tot, S.warp);
                 if (r < m) {
                     const int incl = carry + e + v;       // list growth after splitting r
                     const int before = carry + e;
@@ -1822,7 +1853,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
                 v = (cc[4 * p] > 0) + (cc[4 * p + 1] > 0) + (cc[4 * p + 2] > 0) + (cc[4 * p + 3] > 0);
             }
             int tot;
-            const int e = block_excl_scan(v, &tot, S.warp);
+            const int e = block_excl_scan<OCT_THREADS>(v, &tot, S.warp);
             if (r < nsplit) {
                 split[p] = 1;
                 ne[p] = (uint8_t)v;
@@ -1837,7 +1868,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
             const int i = i0 + tid;
             const int v = (i < n && !split[i]) ? 1 : 0;
             int tot;
-            const int e = block_excl_scan(v, &tot, S.warp);
+            const int e = block_excl_scan<OCT_THREADS>(v, &tot, S.warp);
             if (v) keepPos[i] = (uint16_t)(created + kept + e);
             kept += tot;
         }
@@ -1893,7 +1924,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(const uint32_t* __restri
         int v = 0;
         for (int i = tid; i < cPrev; i += OCT_THREADS) v += cnt[i] > 1;
         int tot;
-        block_excl_scan(v, &tot, S.warp);
+        block_excl_scan<OCT_THREADS>(v, &tot, S.warp);
         return tot;
     };
 
