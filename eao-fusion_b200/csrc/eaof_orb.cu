@@ -141,6 +141,8 @@ struct eaof_orb {
     int rszBulkRows[EAOF_MAX_LEVELS] = {};      // k_resize_bulk: destination rows per CTA (0: level not eligible)
     size_t rszBulkSmem[EAOF_MAX_LEVELS] = {};
     bool bulkPyr = true;                        // EAOF_PYR_BULK=0: per-thread loads (k_level0 / k_resize) for A/B runs
+    eaof::FastTmaMaps descMapsPyr{}, descMapsBlur{};  // k_angle_desc_tma: patch boxes of the unblurred / blurred levels
+    bool descTma = false;
     bool fastGeneric = false;  // k_fast_generic instead of k_fast (geometry / thresholds outside what fast_cell_rows covers)
     int fastTmaGrid = 0;
     size_t fastTmaSmem = 0;
@@ -621,6 +623,11 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
 #endif
         const int warpsPerBlock = DESC_WARPS;
         dim3 gr((g.slotsPerFrame + warpsPerBlock - 1) / warpsPerBlock, n);
+        if (c->descTma) {
+            const dim3 grT((g.slotsPerFrame + DESC_TMA_WARPS - 1) / DESC_TMA_WARPS, n);
+            eaof::k_angle_desc_tma<<<grT, DESC_TMA_WARPS * 32, DESC_TMA_WARPS * (DESC_WARP_BYTES + 8) + 128, s>>>(
+                c->descMapsPyr, c->descMapsBlur, f0, dSlotXY, dSlotScore, dLvlCount, c->dAngleTab, dKps, dDesc, dKpCount, c->kpCap, g);
+        } else
         eaof::k_angle_desc<<<gr, warpsPerBlock * 32, 0, s>>>(dPyr, dBlur, dSlotXY, dSlotScore, dLvlCount,
                                                              c->dAngleTab, dKps, dDesc, dKpCount, c->kpCap, g);
         ++launches;
@@ -807,6 +814,35 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
             static std::mutex muP;
             std::lock_guard<std::mutex> lk(muP);
             CKD(cudaFuncSetAttribute(eaof::k_pyramid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        }
+    }
+    {
+        // k_angle_desc_tma: per level one map over the unblurred pyramid (box 48 x 31: the IC_Angle disc) and one over the
+        // blurred pyramid (box 64 x 39: the rotated rBRIEF taps).  EAOF_DESC_TMA=0 keeps the gather kernel (A/B runs).
+        const char* e = getenv("EAOF_DESC_TMA");
+        const int want = e && *e ? atoi(e) : 1;
+        c->descTma = false;
+        if (want && c->encodeTiled) {
+            typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                            const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            bool ok = true;
+            for (int which = 0; which < 2 && ok; ++which) {
+                std::vector<CUtensorMap> maps(EAOF_MAX_LEVELS);
+                memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
+                for (int l = 0; l < g.nlevels && ok; ++l) {
+                    const LevelGeom& L = g.L[l];
+                    const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)B};
+                    const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.pyrFrameBytes};
+                    const cuuint32_t box[3] = {(cuuint32_t)(which ? DESC_BOXB_W : DESC_BOXA_W), (cuuint32_t)(which ? DESC_BOXB_H : DESC_BOXA_H), 1};
+                    const cuuint32_t estr[3] = {1, 1, 1};
+                    ok = ((EncodeTiled)c->encodeTiled)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (which ? c->dBlur : c->dPyr) + L.off, dims, strides,
+                                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                }
+                memcpy(which ? &c->descMapsBlur : &c->descMapsPyr, maps.data(), sizeof(eaof::FastTmaMaps));
+            }
+            c->descTma = ok;
         }
     }
     {

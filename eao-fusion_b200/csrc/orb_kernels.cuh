@@ -2256,4 +2256,125 @@ __global__ void __launch_bounds__(256) k_angle_desc(const uint8_t* __restrict__ 
     }
 }
 
+// ---- k_angle_desc_tma: the same stage with both patches of a keypoint staged by TMA ---------------------------------
+// k_angle_desc reads the 749-pixel disc (unblurred level) and the 512 rotated rBRIEF taps (blurred level) straight from
+// global memory: 1-byte gathers that touch ~20 different 128-byte lines per warp request and keep the L1 tag stage at 85 %.
+// Here lane 0 of the warp that owns a keypoint requests two boxes — {48 x 31} of the unblurred level around the disc and
+// {64 x 39} of the blurred level around the tap area (x origins rounded down to 16 bytes, TMA's rule; the taps reach at most
+// 18.4 px from the centre) — with two cp.async.bulk.tensor on the warp's own mbarrier, and every later access is a
+// shared-memory load: aligned words for the moments, bytes for the taps.  4 KB of shared memory per warp.
+#define DESC_BOXA_W 48
+#define DESC_BOXA_H 31
+#define DESC_BOXB_W 64
+#define DESC_BOXB_H 39
+#define DESC_BOXA_BYTES 1536  // 48 * 31 = 1488, padded to a multiple of 128
+#define DESC_WARP_BYTES 4096  // + 64 * 39 = 2496
+#define DESC_TMA_WARPS 8
+__global__ void __launch_bounds__(DESC_TMA_WARPS * 32) k_angle_desc_tma(const __grid_constant__ FastTmaMaps mapsPyr,
+                                                                       const __grid_constant__ FastTmaMaps mapsBlur, const int f0,
+                                                                       const uint32_t* __restrict__ slotXY,
+                                                                       const uint8_t* __restrict__ slotScore,
+                                                                       const int* __restrict__ lvlCount,
+                                                                       const uint2* __restrict__ angleTab, void* __restrict__ kpsOut,
+                                                                       uint8_t* __restrict__ descOut, int* __restrict__ kpCount,
+                                                                       int kpCap, const __grid_constant__ Geom g) {
+    extern __shared__ __align__(128) uint8_t adSmem[];
+    const int f = blockIdx.y;
+    const int wIn = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * DESC_TMA_WARPS + wIn;
+    if (warp >= g.slotsPerFrame) return;
+    int l = 0;
+    while (l + 1 < g.nlevels && warp >= g.L[l + 1].slotOff) ++l;
+    const LevelGeom& L = g.L[l];
+    const int p = warp - L.slotOff;
+    const int* lc = lvlCount + f * g.nlevels;
+    if (warp == 0 && lane == 0) {
+        int tot = 0;
+        for (int i = 0; i < g.nlevels; ++i) tot += lc[i];
+        kpCount[f] = tot;
+    }
+    if (p >= lc[l]) return;
+    uint8_t* smem = adSmem + ((128u - (smem_u32(adSmem) & 127u)) & 127u);
+    uint8_t* boxA = smem + wIn * DESC_WARP_BYTES;
+    uint8_t* boxB = boxA + DESC_BOXA_BYTES;
+    const uint32_t bar = smem_u32(smem + DESC_TMA_WARPS * DESC_WARP_BYTES + 8 * wIn);
+
+    const uint32_t xy = slotXY[(size_t)f * g.slotsPerFrame + warp];
+    const int X = (int)(xy & 0xffff) + EAOF_MIN_BORDER, Y = (int)(xy >> 16) + EAOF_MIN_BORDER;  // :841-842
+    const int cxA = EAOF_INNER_X0 + X - EAOF_HALF_PATCH;  // byte column of u = -15 inside the padded row
+    const int cxB = EAOF_INNER_X0 + X - EAOF_EDGE;        // byte column of the leftmost tap column
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)(DESC_BOXA_W * DESC_BOXA_H + DESC_BOXB_W * DESC_BOXB_H));
+        tma_load_3d(smem_u32(boxA), &mapsPyr.m[l][0], cxA & ~15, EAOF_EDGE + Y - EAOF_HALF_PATCH, f0 + f, bar);
+        tma_load_3d(smem_u32(boxB), &mapsBlur.m[l][0], cxB & ~15, Y, f0 + f, bar);
+    }
+    __syncwarp();
+    int outIdx = p;
+    for (int i = 0; i < l; ++i) outIdx += lc[i];
+    const int a = cxA & 3;
+    const uint2* wt = angleTab + a * EAOF_ANGLE_TASKS_PAD;
+    uint2 wgt[(EAOF_ANGLE_TASKS + 31) / 32];
+#pragma unroll
+    for (int k = 0; k < (EAOF_ANGLE_TASKS + 31) / 32; ++k) wgt[k] = __ldg(wt + min(lane + 32 * k, EAOF_ANGLE_TASKS_PAD - 1));
+    const int4 pa = reinterpret_cast<const int4*>(d_pattern)[2 * lane];
+    const int4 pb = reinterpret_cast<const int4*>(d_pattern)[2 * lane + 1];
+    mbar_wait(bar, 0);
+
+    int m10 = 0, m01 = 0;
+    {
+        const uint32_t* wA = reinterpret_cast<const uint32_t*>(boxA) + (((cxA & 15) - a) >> 2);
+#pragma unroll
+        for (int k = 0; k < (EAOF_ANGLE_TASKS + 31) / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i < EAOF_ANGLE_TASKS) {
+                const int r = (i * 57) >> 9;  // i / 9 for i < 288
+                const int j = i - 9 * r;
+                const unsigned pix = wA[r * (DESC_BOXA_W / 4) + j];
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(pix), "r"(wgt[k].x));
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m01) : "r"(pix), "r"(wgt[k].y));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    float ca, sb;
+    glibc_sincosf(__fmul_rn(angle, factorPI), &sb, &ca);
+    const uint8_t* bc = boxB + EAOF_EDGE * DESC_BOXB_W + (cxB & 15) + EAOF_EDGE;  // the keypoint inside the blurred box
+    const int words[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float x0 = (float)(signed char)(words[k] & 0xff), y0 = (float)(signed char)((words[k] >> 8) & 0xff);
+        const float x1 = (float)(signed char)((words[k] >> 16) & 0xff), y1 = (float)(signed char)(words[k] >> 24);
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)));
+        const int t0 = bc[r0 * DESC_BOXB_W + c0], t1 = bc[r1 * DESC_BOXB_W + c1];
+        val |= (t0 < t1) << k;
+    }
+    if (outIdx < kpCap) {
+        descOut[((size_t)f * kpCap + outIdx) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            float* o = reinterpret_cast<float*>(kpsOut) + ((size_t)f * kpCap + outIdx) * 6;
+            float px = (float)X, py = (float)Y;
+            if (l != 0) { px = __fmul_rn(px, L.scale); py = __fmul_rn(py, L.scale); }
+            o[0] = px;
+            o[1] = py;
+            o[2] = L.kpSize;
+            o[3] = angle;
+            o[4] = (float)slotScore[(size_t)f * g.slotsPerFrame + warp];
+            reinterpret_cast<int*>(o)[5] = l;
+        }
+    }
+}
+
 }  // namespace eaof
