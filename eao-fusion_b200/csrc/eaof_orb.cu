@@ -143,6 +143,7 @@ struct eaof_orb {
     bool bulkPyr = true;                        // EAOF_PYR_BULK=0: per-thread loads (k_level0 / k_resize) for A/B runs
     eaof::FastTmaMaps descMapsPyr{}, descMapsBlur{};  // k_angle_desc_tma: patch boxes of the unblurred / blurred levels
     bool descTma = false;
+    uint8_t* dSlotLevel = nullptr;
     bool fastGeneric = false;  // k_fast_generic instead of k_fast (geometry / thresholds outside what fast_cell_rows covers)
     int fastTmaGrid = 0;
     size_t fastTmaSmem = 0;
@@ -626,7 +627,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         if (c->descTma) {
             const dim3 grT((g.slotsPerFrame + DESC_TMA_WARPS - 1) / DESC_TMA_WARPS, n);
             eaof::k_angle_desc_tma<<<grT, DESC_TMA_WARPS * 32, DESC_TMA_WARPS * (DESC_WARP_BYTES + 8) + 128, s>>>(
-                c->descMapsPyr, c->descMapsBlur, f0, dSlotXY, dSlotScore, dLvlCount, c->dAngleTab, dKps, dDesc, dKpCount, c->kpCap, g);
+                c->descMapsPyr, c->descMapsBlur, f0, dSlotXY, dSlotScore, dLvlCount, c->dAngleTab, c->dSlotLevel, dKps, dDesc, dKpCount, c->kpCap, g);
         } else
         eaof::k_angle_desc<<<gr, warpsPerBlock * 32, 0, s>>>(dPyr, dBlur, dSlotXY, dSlotScore, dLvlCount,
                                                              c->dAngleTab, dKps, dDesc, dKpCount, c->kpCap, g);
@@ -842,6 +843,13 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
                 }
                 memcpy(which ? &c->descMapsBlur : &c->descMapsPyr, maps.data(), sizeof(eaof::FastTmaMaps));
             }
+            if (ok) {  // slot -> level table of this geometry
+                std::vector<uint8_t> sl((size_t)g.slotsPerFrame);
+                for (int l = 0; l < g.nlevels; ++l)
+                    for (int i = 0; i < g.L[l].nodeCap; ++i) sl[(size_t)g.L[l].slotOff + i] = (uint8_t)l;
+                CKD(cudaMalloc(&c->dSlotLevel, sl.size() + 16));
+                CKD(cudaMemcpy(c->dSlotLevel, sl.data(), sl.size(), cudaMemcpyHostToDevice));
+            }
             c->descTma = ok;
         }
     }
@@ -939,7 +947,7 @@ void eaof_orb_destroy(eaof_orb* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->dAux); cudaFree(c->dURight); cudaFree(c->dDepthKp);
-    cudaFree(c->dIn); cudaFree(c->dPyr); cudaFree(c->dBlur); cudaFree(c->dTabs); cudaFree(c->dAngleTab); cudaFree(c->dCells);
+    cudaFree(c->dIn); cudaFree(c->dPyr); cudaFree(c->dBlur); cudaFree(c->dTabs); cudaFree(c->dAngleTab); cudaFree(c->dSlotLevel); cudaFree(c->dCells);
     cudaFree(c->dCand); cudaFree(c->dLabel); cudaFree(c->dCandCount); cudaFree(c->dSlotXY); cudaFree(c->dSlotScore);
     cudaFree(c->dLvlCount); cudaFree(c->dKps); cudaFree(c->dDesc); cudaFree(c->dKpCount);
     cudaFreeHost(c->hIn); cudaFreeHost(c->hKps); cudaFreeHost(c->hDesc); cudaFreeHost(c->hKpCount);

@@ -2275,7 +2275,8 @@ __global__ void __launch_bounds__(DESC_TMA_WARPS * 32) k_angle_desc_tma(const __
                                                                        const uint32_t* __restrict__ slotXY,
                                                                        const uint8_t* __restrict__ slotScore,
                                                                        const int* __restrict__ lvlCount,
-                                                                       const uint2* __restrict__ angleTab, void* __restrict__ kpsOut,
+                                                                       const uint2* __restrict__ angleTab,
+                                                                       const uint8_t* __restrict__ slotLevel, void* __restrict__ kpsOut,
                                                                        uint8_t* __restrict__ descOut, int* __restrict__ kpCount,
                                                                        int kpCap, const __grid_constant__ Geom g) {
     extern __shared__ __align__(128) uint8_t adSmem[];
@@ -2283,17 +2284,21 @@ __global__ void __launch_bounds__(DESC_TMA_WARPS * 32) k_angle_desc_tma(const __
     const int wIn = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = blockIdx.x * DESC_TMA_WARPS + wIn;
     if (warp >= g.slotsPerFrame) return;
-    int l = 0;
-    while (l + 1 < g.nlevels && warp >= g.L[l + 1].slotOff) ++l;
+    const int l = slotLevel[warp];
     const LevelGeom& L = g.L[l];
     const int p = warp - L.slotOff;
+    // keypoints of the levels below this one (output position) and of the frame: one load per lane + a warp scan
     const int* lc = lvlCount + f * g.nlevels;
-    if (warp == 0 && lane == 0) {
-        int tot = 0;
-        for (int i = 0; i < g.nlevels; ++i) tot += lc[i];
-        kpCount[f] = tot;
+    const int mine = lane < g.nlevels ? lc[lane] : 0;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < EAOF_MAX_LEVELS; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
     }
-    if (p >= lc[l]) return;
+    const int outIdx = p + __shfl_sync(0xffffffffu, incl - mine, l);
+    if (warp == 0 && lane == g.nlevels - 1) kpCount[f] = incl;
+    if (p >= __shfl_sync(0xffffffffu, mine, l)) return;
     uint8_t* smem = adSmem + ((128u - (smem_u32(adSmem) & 127u)) & 127u);
     uint8_t* boxA = smem + wIn * DESC_WARP_BYTES;
     uint8_t* boxB = boxA + DESC_BOXA_BYTES;
@@ -2311,8 +2316,6 @@ __global__ void __launch_bounds__(DESC_TMA_WARPS * 32) k_angle_desc_tma(const __
         tma_load_3d(smem_u32(boxB), &mapsBlur.m[l][0], cxB & ~15, Y, f0 + f, bar);
     }
     __syncwarp();
-    int outIdx = p;
-    for (int i = 0; i < l; ++i) outIdx += lc[i];
     const int a = cxA & 3;
     const uint2* wt = angleTab + a * EAOF_ANGLE_TASKS_PAD;
     uint2 wgt[(EAOF_ANGLE_TASKS + 31) / 32];
@@ -2347,18 +2350,24 @@ __global__ void __launch_bounds__(DESC_TMA_WARPS * 32) k_angle_desc_tma(const __
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     float ca, sb;
     glibc_sincosf(__fmul_rn(angle, factorPI), &sb, &ca);
-    const uint8_t* bc = boxB + EAOF_EDGE * DESC_BOXB_W + (cxB & 15) + EAOF_EDGE;  // the keypoint inside the blurred box
+    // Tap coordinates: round-to-nearest-even of an fp32 value below 2^22 = low bits of (value + 1.5 * 2^23): one FADD on the
+    // FMA pipe instead of an F2I on the conversion pipe (70 % busy once the gathers were cheap).  The 0x4B400000 biases of row
+    // and column are folded into the base address (shared-memory addresses are 32-bit: the sum wraps).
+    const float magic = 12582912.f;
+    const uint32_t bcAddr = smem_u32(boxB) + EAOF_EDGE * DESC_BOXB_W + (cxB & 15) + EAOF_EDGE - 0x4B400000u * (DESC_BOXB_W + 1u);
     const int words[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const float x0 = (float)(signed char)(words[k] & 0xff), y0 = (float)(signed char)((words[k] >> 8) & 0xff);
         const float x1 = (float)(signed char)((words[k] >> 16) & 0xff), y1 = (float)(signed char)(words[k] >> 24);
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)));
-        const int t0 = bc[r0 * DESC_BOXB_W + c0], t1 = bc[r1 * DESC_BOXB_W + c1];
+        const uint32_t r0 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca)), magic));
+        const uint32_t c0 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)), magic));
+        const uint32_t r1 = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca)), magic));
+        const uint32_t c1 = __float_as_uint(__fadd_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)), magic));
+        uint32_t t0, t1;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(t0) : "r"(bcAddr + r0 * DESC_BOXB_W + c0));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(t1) : "r"(bcAddr + r1 * DESC_BOXB_W + c1));
         val |= (t0 < t1) << k;
     }
     if (outIdx < kpCap) {
