@@ -717,6 +717,20 @@ def next_rows(eaof, torch, device, ex, d_frames, B, W, H):
                                    "calls": len(lat), "median_us": lat[len(lat) // 2] * 1e6, "p5_us": lat[int(len(lat) * 0.05)] * 1e6,
                                    "p95_us": lat[int(len(lat) * 0.95)] * 1e6, "keypoints": int(len(k1)),
                                    "launches_per_call": ex1.last_launch_count()}
+    # the same call made from C++ through the drop-in class itself (tests/cpp/dropin_harness.cc times operator() with
+    # steady_clock): no ctypes / numpy work around it, cv::KeyPoint conversion included — what Frame::ExtractORB sees
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import dropin
+        dx = dropin.DropinExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+        dx.time_calls(f_host, 16)
+        us = np.sort(dx.time_calls(f_host, 300))
+        out["single_frame_latency"]["cpp_dropin"] = {
+            "what": "ORB_SLAM2::ORBextractor::operator() of the drop-in class, timed inside C++ (300 calls, pageable cv::Mat input)",
+            "median_us": float(us[len(us) // 2]), "p5_us": float(us[int(len(us) * 0.05)]), "p95_us": float(us[int(len(us) * 0.95)])}
+        dx.close()
+    except Exception as e:  # the harness is test infrastructure: report, never require
+        out["single_frame_latency"]["cpp_dropin"] = {"failed": repr(e)}
     # the Tracking-shaped loop (src/Tracking.cc:1717-1763): extract frame t, then SearchByProjection(Cur = t, Last = t-1)
     # through the single-pair host-buffer call the drop-in ORBmatcher makes; beside it stands cpu_baseline_alpha
     mt1 = eaof.ORBmatcher(0.9, True, max_features=4096, device=device)

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -142,6 +143,7 @@ struct eaof_orb {
     size_t rszBulkSmem[EAOF_MAX_LEVELS] = {};
     bool bulkPyr = true;                        // EAOF_PYR_BULK=0: per-thread loads (k_level0 / k_resize) for A/B runs
     eaof::FastTmaMaps descMapsPyr{}, descMapsBlur{};  // k_angle_desc_tma: patch boxes of the unblurred / blurred levels
+    double latT[8] = {};  // single-frame path: host timestamps (s) at enter / upload queued / graph launched / wait entered / synced / copied out
     bool descTma = false;
     uint8_t* dSlotLevel = nullptr;
     bool fastGeneric = false;  // k_fast_generic instead of k_fast (geometry / thresholds outside what fast_cell_rows covers)
@@ -364,7 +366,8 @@ bool fused_axis(const Geom& g, bool xAxis, const std::vector<int>& tabs, int& nT
     };
     const int last = nl - 1;
     const int nLast = size(last);
-    nT = std::max(1, std::min((nLast + 16) / 32, nLast / 20));
+    static const int tilePx = getenv("EAOF_FUSED_TILE") ? std::max(20, atoi(getenv("EAOF_FUSED_TILE"))) : 22;  // last-level tile edge: 22 px = 48 CTAs per 640x480 frame (41 -> 35 us for one frame against 32 px)
+    nT = std::max(1, std::min((nLast + tilePx / 2) / tilePx, nLast / 20));
     std::vector<std::vector<int>> a(nl, std::vector<int>(nT + 1));
     for (int t = 0; t <= nT; ++t) {
         a[last][t] = (int)((long long)t * nLast / nT);
@@ -1241,6 +1244,10 @@ int eaof_orb_fetch_results(eaof_orb* c, int n, eaof_kp* kps, uint8_t* desc, int 
     return EAOF_OK;
 }
 
+static inline double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int eaof_orb_extract_batch_async(eaof_orb* c, const uint8_t* imgs, int n, int width, int height, size_t stride,
                                  size_t framePitch, eaof_kp* kps, uint8_t* desc, int cap) {
     int rc = check_shape(c, width, height, n);
@@ -1259,12 +1266,14 @@ int eaof_orb_extract_batch_async(eaof_orb* c, const uint8_t* imgs, int n, int wi
     if (n == 1 && !c->profiling && !noGraph && !(c->graphTried && !c->graphExec1)) {
         // ---- latency path: upload on the compute stream, then the captured graph (kernels + downloads into the pinned staging)
         cudaStream_t s = c->stream;
+        c->latT[0] = now_s();
         if (c->pyrReaderPending) { CK(cudaStreamWaitEvent(s, c->evPyrReader, 0)); c->pyrReaderPending = false; }
         if (c->readerPending) { CK(cudaStreamWaitEvent(s, c->evReader, 0)); c->readerPending = false; }
         if (packed)
             CK(cudaMemcpyAsync(c->dIn, imgs, frameBytes, cudaMemcpyHostToDevice, s));
         else
             CK(cudaMemcpy2DAsync(c->dIn, (size_t)width, imgs, stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, s));
+        c->latT[1] = now_s();
         if (!c->graphExec1) {
             c->graphTried = true;
             c->capturing = true;
@@ -1290,6 +1299,7 @@ int eaof_orb_extract_batch_async(eaof_orb* c, const uint8_t* imgs, int n, int wi
         }
         if (c->graphExec1) {
             CK(cudaGraphLaunch(c->graphExec1, s));
+            c->latT[2] = now_s();
             c->lastFrames = 1;
             c->pendN = 1; c->pendCap = cap; c->pendKps = kps; c->pendDesc = desc; c->pendDirect = false; c->pendGraph = true;
             return EAOF_OK;
@@ -1343,10 +1353,12 @@ int eaof_orb_extract_batch_wait(eaof_orb* c, int* nOut) {
     uint8_t* desc = c->pendDesc;
     const bool direct = c->pendDirect;
     c->pendN = 0;
+    c->latT[3] = now_s();
     CK(cudaSetDevice(c->device));
     if (!c->pendGraph) CK(cudaStreamSynchronize(c->streamOut));  // the graph downloads on the compute stream itself
     int rc = eaof_orb_sync(c);
     if (rc) return rc;
+    c->latT[4] = now_s();
     for (int f = 0; f < n; ++f) {
         const int k = c->hKpCount[f];
         nOut[f] = k;
@@ -1356,6 +1368,13 @@ int eaof_orb_extract_batch_wait(eaof_orb* c, int* nOut) {
             if (desc) memcpy(desc + (size_t)f * cap * 32, c->hDesc + (size_t)f * c->kpCap * 32, 32 * (size_t)k);
         }
     }
+    c->latT[5] = now_s();
+    return EAOF_OK;
+}
+
+int eaof_debug_latency_trace(eaof_orb* c, double* out6) {
+    if (!c || !out6) return fail(EAOF_ERR_ARG, "null argument");
+    for (int i = 0; i < 6; ++i) out6[i] = c->latT[i];
     return EAOF_OK;
 }
 

@@ -191,6 +191,9 @@ int eaof_orb_debug_candidates(eaof_orb* ctx, int frame, int level, int* xys, int
 /* Runs the device restatement of glibc sinf/cosf (used by the descriptor rotation) over every `stride`-th float in
  * [0, hi] and compares with this host's libm; returns the number of mismatching results (0 expected), -1 on error. */
 long eaof_debug_sincosf_mismatches(float hi, uint32_t stride);
+/* Host timestamps (seconds, steady clock) of the last single-frame call on this handle: entered / upload queued / graph
+ * launched / wait entered / stream synchronised / results copied out.  Measurement aid for the latency path. */
+int eaof_debug_latency_trace(eaof_orb* h, double* out6);
 /* Per-stage GPU time of the last batched call in milliseconds (CUDA events on the handle's stream):
  * [0] pyramid, [1] FAST, [2] octree, [3] blur, [4] angle+descriptor, [5] total.  Requires
  * eaof_orb_set_profiling(ctx, 1) before the call. */

@@ -2,6 +2,7 @@
 // against oracle/cvshim in place of OpenCV (this container has no OpenCV C++), so that tests/test_gpu_dropin.py can
 // call the class exactly the way Frame::ExtractORB does (src/Frame.cc:616-622) and compare it with the reference
 // class behind oracle/_ref/liborb_ref.so, which exposes the same C calls (oracle/ref_harness.cc).
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -61,6 +62,25 @@ int dropin_extract(void* h, const uint8_t* img, int w, int hgt, size_t stride, d
         if (desc && i < d.rows) memcpy(desc + (size_t)i * 32, d.ptr(i), 32);
     }
     if (desc_rows) *desc_rows = d.rows;
+    return n;
+}
+
+// Times `calls` consecutive operator() calls on the C++ side (steady_clock around the call, nothing else inside): the latency
+// a Frame constructor sees (src/Frame.cc:193,229-231 print exactly this).  Frames cycle through imgs[0..n_imgs).
+int dropin_time_calls(void* h, const uint8_t* imgs, int n_imgs, int w, int hgt, size_t stride, int calls, double* out_us) {
+    ORB_SLAM2::ORBextractor* e = (ORB_SLAM2::ORBextractor*)h;
+    std::vector<cv::KeyPoint> k;
+    cv::Mat d;
+    int n = 0;
+    try {
+        for (int i = 0; i < calls; ++i) {
+            cv::Mat image(hgt, w, CV_8UC1, (void*)(imgs + (size_t)(i % n_imgs) * stride * hgt), stride);
+            const auto t0 = std::chrono::steady_clock::now();
+            (*e)(image, cv::Mat(), k, d);
+            out_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+            n = (int)k.size();
+        }
+    } catch (...) { return -2; }
     return n;
 }
 

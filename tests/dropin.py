@@ -25,6 +25,7 @@ def lib():
         L.dropin_tables.argtypes = [vp, vp, vp, vp, vp, C.POINTER(ci), C.POINTER(C.c_float)]
         L.dropin_extract.argtypes = [vp, vp, ci, ci, C.c_size_t, vp, vp, ci, ci, C.POINTER(ci)]
         L.dropin_level.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), vp, C.c_size_t, ci]
+        L.dropin_time_calls.argtypes = [vp, vp, ci, ci, ci, C.c_size_t, ci, vp]
         _L = L
     return _L
 
@@ -64,6 +65,16 @@ class DropinExtractor:
                                       desc.ctypes.data, self.cap, pre_n, C.byref(rows))
         assert n != -2, "drop-in threw (no CUDA device?)"
         return n, rows.value, kps[:n].copy(), desc[:max(rows.value, 0)].copy()
+
+    def time_calls(self, frames, calls, download_pyramid=False):
+        """Microseconds of `calls` consecutive operator() calls measured on the C++ side; frames: (n, h, w) u8."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        out = np.zeros(calls, np.float64)
+        self.L.dropin_set_pyramid(self.h, 1 if download_pyramid else 0)
+        n = self.L.dropin_time_calls(self.h, frames.ctypes.data, frames.shape[0], frames.shape[2], frames.shape[1], frames.strides[1],
+                                     calls, out.ctypes.data)
+        assert n != -2, "drop-in threw (no CUDA device?)"
+        return out
 
     def level(self, l, with_border=False):
         w, h = C.c_int(), C.c_int()
