@@ -476,6 +476,36 @@ def measure_config(eaof, torch, dist, rank, world, device, name, B, steps, warmu
     return out
 
 
+def pcie_ceiling(torch, dist, world, h2d_bytes, d2h_bytes, frames, reps=12):
+    """What the host side can feed: every rank copies one batch's upload (pinned -> device) and download (device -> pinned)
+    at the same time on two streams, all ranks together; max over ranks.  Returns the frames/s this alone allows at N GPUs."""
+    hu = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory(); du = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+    hd = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory(); dd = torch.empty(d2h_bytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(2):
+        du.copy_(hu, non_blocking=True); hd.copy_(dd, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        with torch.cuda.stream(s1):
+            du.copy_(hu, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hd.copy_(dd, non_blocking=True)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    del hu, du, hd, dd
+    return {"frames_per_s_ceiling": world * frames * reps / dt, "h2d_gbs_aggregate": world * h2d_bytes * reps / dt / 1e9,
+            "d2h_gbs_aggregate": world * d2h_bytes * reps / dt / 1e9,
+            "how": "all ranks copy one batch's upload and download bytes concurrently (pinned buffers, two streams per rank), "
+                   "no kernels: the host/PCIe side alone"}
+
+
 def stage_table(m, width, height, hbm_peak, B):
     alg = algorithmic_bytes(width, height, m["level_sizes"], m["kp_per_frame"], m["cand_per_frame"])
     stages = {}
@@ -952,6 +982,8 @@ def main():
     sus_clocks = sampler.summary(*m["sustained"]["t_host"]) if "sustained" in m else None
     rig, d_seq = m["rig"], m["d_seq"]
 
+    e2e_roof = pcie_ceiling(torch, dist, world, m["e2e"]["h2d_bytes_per_step"] // m["n_batches"],
+                            m["e2e"]["d2h_bytes_per_step"] // m["n_batches"], B)
     sweep = None
     if not args.no_sweep:
         sweep = hamming_sweep(eaof, torch, dist, rank, world, local_rank)
@@ -1020,6 +1052,7 @@ def main():
                        "parallelism": f"frame-sharded x{world} (rank r owns frames [1000r, 1000(r+1)) + 1 halo), no collective"},
             "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": m["e2e"]["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": m["e2e"]["d2h_bytes_per_step"]},
+            "e2e_roofline": dict(e2e_roof, frac=e2e_val / e2e_roof["frames_per_s_ceiling"]),
             "gpu_launches": m["launches_per_step"] * args.steps,
             "e2e_detail": {"steps": m["e2e"]["steps"], "pipeline": f"{m['e2e']['slots']} handles in rotation: uploads of the next batches "
                            "under the kernels of batch k", "gpu_launches": m["e2e"]["launches"],
