@@ -144,6 +144,7 @@ struct eaof_orb {
     bool bulkPyr = true;                        // EAOF_PYR_BULK=0: per-thread loads (k_level0 / k_resize) for A/B runs
     eaof::FastTmaMaps descMapsPyr{}, descMapsBlur{};  // k_angle_desc_tma: patch boxes of the unblurred / blurred levels
     double latT[8] = {};  // single-frame path: host timestamps (s) at enter / upload queued / graph launched / wait entered / synced / copied out
+    int fusedMode = 1;  // EAOF_PYR_FUSED: 0 never, 1 for small batches, 2 always (read at create)
     bool descTma = false;
     uint8_t* dSlotLevel = nullptr;
     bool fastGeneric = false;  // k_fast_generic instead of k_fast (geometry / thresholds outside what fast_cell_rows covers)
@@ -400,7 +401,8 @@ int build_fused_plan(eaof_orb* c, const std::vector<int>& tabs, std::vector<eaof
     const Geom& g = c->g;
     c->fused = false;
     const char* e = getenv("EAOF_PYR_FUSED");
-    if (e && *e == '0') return EAOF_OK;
+    c->fusedMode = e && *e ? atoi(e) : 1;
+    if (c->fusedMode == 0) return EAOF_OK;
     if (g.nlevels < 2) return EAOF_OK;
     for (int l = 0; l < g.nlevels; ++l)
         if (g.L[l].w < 2 * EAOF_EDGE + 2 || g.L[l].h < 2 * EAOF_EDGE + 2) return EAOF_OK;  // borders fold more than once: per-level kernels
@@ -472,8 +474,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     // One launch for the whole pyramid pays off while the frames of a call cannot fill the GPU level by level (the chain of
     // per-level launches is then pure latency); big batches keep the per-level kernels, which do less redundant work
     // (measured crossover: DESIGN.md §4).  EAOF_PYR_FUSED=2 forces the fused kernel for every batch size.
-    static const int fusedMode = getenv("EAOF_PYR_FUSED") ? atoi(getenv("EAOF_PYR_FUSED")) : 1;
-    const bool fusedNow = c->fused && c->colorCh == 0 && (fusedMode == 2 || n * c->fusedA.nTx * c->fusedA.nTy <= EAOF_FUSED_MAX_CTAS);
+    const bool fusedNow = c->fused && c->colorCh == 0 && (c->fusedMode == 2 || n * c->fusedA.nTx * c->fusedA.nTy <= EAOF_FUSED_MAX_CTAS);
     if (fusedNow) {
         eaof::FusedArgs A = c->fusedA;
         A.in = dImgs; A.stride = stride; A.framePitch = framePitch; A.f0 = f0;

@@ -413,3 +413,47 @@ def test_tma_staged_fast_variants_match(size, monkeypatch):
         ex.close()
         dig[mode] = [workload.frame_digest(k, d) for k, d in res]
     assert dig["1"] == dig["0"] and dig["2"] == dig["0"]
+
+
+@pytest.mark.parametrize("size", [(640, 480, 1000), (848, 480, 1200), (333, 251, 600), (1920, 1080, 4000)])
+@pytest.mark.parametrize("knob", ["EAOF_FAST_GENERIC=1", "EAOF_PYR_BULK=0", "EAOF_DESC_TMA=0", "EAOF_PYR_FUSED=0", "EAOF_PYR_FUSED=2",
+                                  "EAOF_OCT_WIDTH=0", "EAOF_OCT_WIDTH=1", "EAOF_OCT_WIDTH=2", "EAOF_OCT_KEYS_GLOBAL=1"])
+def test_kernel_variants_match_the_default(size, knob, monkeypatch):
+    """Every stage has more than one kernel behind it (lane = row FAST vs the task-per-word k_fast_generic, bulk-copy pyramid vs
+    per-thread loads vs the fused one-launch pyramid, TMA-staged descriptor patches vs gathers, three quadtree CTA widths with
+    keys in shared or global memory); the library picks by geometry, batch size and alignment.  Whichever it picks, the output
+    must be the same bytes: each knob forces one alternative, compared with the default choice (itself pinned to the oracle by
+    the tests above)."""
+    import eaof
+    from eaof import synth, workload
+    w, h, nf = size
+    n = 5 if w < 1000 else 2
+    frames = synth.make_frames(n, w, h, tex=synth.base_texture(w, h, seed=91))
+
+    def run():
+        ex = eaof.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=n)
+        res = ex.extract_batch(frames)
+        ex.close()
+        return [workload.frame_digest(k, d) for k, d in res]
+
+    base = run()
+    name, val = knob.split("=")
+    monkeypatch.setenv(name, val)
+    assert run() == base
+
+
+def test_fast_thresholds_outside_the_row_kernel(monkeypatch):
+    """iniThFAST >= 128 (the carry trick of the byte-lane pre-test changes form) and minThFAST >= iniThFAST run through
+    k_fast_generic by the library's own choice: against the oracle."""
+    import eaof
+    from eaof import synth
+    from oracle import pyoracle as po
+    frames = synth.make_frames(2, 320, 240, tex=synth.base_texture(320, 240, seed=5))
+    for ini, mn in ((130, 40), (20, 20), (12, 30)):
+        ex = eaof.ORBextractor(300, 1.2, 8, ini, mn, width=320, height=240, max_batch=2)
+        res = ex.extract_batch(frames)
+        ex.close()
+        for f in range(2):
+            ok, od = po.o_extract(frames[f], nfeatures=300, ini_th=ini, min_th=mn)
+            k, d = res[f]
+            assert len(k) == len(ok) and np.array_equal(k, ok) and np.array_equal(d, od), (ini, mn, f)
