@@ -137,7 +137,12 @@ struct eaof_orb {
     int fusedMapN = 0;
     void* encodeTiled = nullptr;  // cuTensorMapEncodeTiled
     int fastTma = 0;  // 0: k_fast (LDG-staged tile), 1: k_fast_tma (persistent, double-buffered TMA), 2: k_fast_tma1
-    void (*fastKernel)(const uint8_t*, const CellDesc*, uint32_t*, uint32_t*, const Geom) = nullptr;  // k_fast<PW> of this geometry
+    void (*fastKernel)(const uint8_t*, const CellDesc*, uint32_t*, uint32_t*, const Geom, int, int) = nullptr;  // k_fast<PW> of this geometry
+    // single-frame latency path: per-level DAG inside the captured graph (level l -> FAST of level l -> quadtree of level l on
+    // a stream of its own), EAOF_LAT_DAG=0 keeps the stage-by-stage order
+    bool latDag = true;
+    cudaStream_t dagStream[EAOF_MAX_LEVELS] = {};
+    cudaEvent_t evLvl[EAOF_MAX_LEVELS] = {}, evOct[EAOF_MAX_LEVELS] = {};
     bool rszWindow[EAOF_MAX_LEVELS] = {};  // level l: k_resize's 8-byte source window covers every group of 4 columns
     int rszBulkRows[EAOF_MAX_LEVELS] = {};      // k_resize_bulk: destination rows per CTA (0: level not eligible)
     size_t rszBulkSmem[EAOF_MAX_LEVELS] = {};
@@ -474,7 +479,9 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
     // One launch for the whole pyramid pays off while the frames of a call cannot fill the GPU level by level (the chain of
     // per-level launches is then pure latency); big batches keep the per-level kernels, which do less redundant work
     // (measured crossover: DESIGN.md §4).  EAOF_PYR_FUSED=2 forces the fused kernel for every batch size.
-    const bool fusedNow = c->fused && c->colorCh == 0 && (c->fusedMode == 2 || n * c->fusedA.nTx * c->fusedA.nTy <= EAOF_FUSED_MAX_CTAS);
+    // latency path (graph capture of one frame): per-level DAG, which needs the per-level pyramid kernels
+    const bool dagNow = c->capturing && n == 1 && c->latDag && c->fastTma == 0 && !prof && g.cellsPerFrame > 0;
+    const bool fusedNow = !dagNow && c->fused && c->colorCh == 0 && (c->fusedMode == 2 || n * c->fusedA.nTx * c->fusedA.nTy <= EAOF_FUSED_MAX_CTAS);
     if (fusedNow) {
         eaof::FusedArgs A = c->fusedA;
         A.in = dImgs; A.stride = stride; A.framePitch = framePitch; A.f0 = f0;
@@ -522,7 +529,7 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
             eaof::k_level0<<<gr8, b, 0, s>>>(dImgs, framePitch, stride, dPyr, g);
         ++launches;
     }
-    for (int l = 1; l < g.nlevels && !fusedNow; ++l) {
+    auto launch_resize = [&](int l, cudaStream_t st) {
         const LevelGeom& L = g.L[l];
         if (L.h >= 40 && c->rszWindow[l] && c->bulkPyr && c->rszBulkRows[l]) {
             // source rows staged in shared memory by bulk asynchronous copies, CTA = chunk of rows over the whole width
@@ -531,9 +538,9 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
             while (rows > 4 && (long long)n * ((L.h + rows - 1) / rows) < 296) rows >>= 1;
             const int threads = std::min(256, (nCW + 31) & ~31);
             const dim3 gr((L.h + rows - 1) / rows, n);
-            if (rows == 16) eaof::k_resize_bulk<16><<<gr, threads, c->rszBulkSmem[l], s>>>(dPyr, c->dTabs, g, l);
-            else if (rows == 8) eaof::k_resize_bulk<8><<<gr, threads, c->rszBulkSmem[l], s>>>(dPyr, c->dTabs, g, l);
-            else eaof::k_resize_bulk<4><<<gr, threads, c->rszBulkSmem[l], s>>>(dPyr, c->dTabs, g, l);
+            if (rows == 16) eaof::k_resize_bulk<16><<<gr, threads, c->rszBulkSmem[l], st>>>(dPyr, c->dTabs, g, l);
+            else if (rows == 8) eaof::k_resize_bulk<8><<<gr, threads, c->rszBulkSmem[l], st>>>(dPyr, c->dTabs, g, l);
+            else eaof::k_resize_bulk<4><<<gr, threads, c->rszBulkSmem[l], st>>>(dPyr, c->dTabs, g, l);
         } else if (L.h >= 40 && c->rszWindow[l]) {
             // rows per thread: long walks reuse source rows, but small levels / small batches need the threads
 #ifndef RSZ_WANT
@@ -545,14 +552,36 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
             while (rows > 8 && (long long)nCW * ((L.h + rows - 1) / rows) * n < want) rows >>= 1;
             const int tasks = nCW * ((L.h + rows - 1) / rows);
             const dim3 gr((tasks + RSZ_THREADS - 1) / RSZ_THREADS, n);
-            if (rows == 32) eaof::k_resize<32><<<gr, RSZ_THREADS, 0, s>>>(dPyr, c->dTabs, g, l);
-            else if (rows == 16) eaof::k_resize<16><<<gr, RSZ_THREADS, 0, s>>>(dPyr, c->dTabs, g, l);
-            else eaof::k_resize<8><<<gr, RSZ_THREADS, 0, s>>>(dPyr, c->dTabs, g, l);
+            if (rows == 32) eaof::k_resize<32><<<gr, RSZ_THREADS, 0, st>>>(dPyr, c->dTabs, g, l);
+            else if (rows == 16) eaof::k_resize<16><<<gr, RSZ_THREADS, 0, st>>>(dPyr, c->dTabs, g, l);
+            else eaof::k_resize<8><<<gr, RSZ_THREADS, 0, st>>>(dPyr, c->dTabs, g, l);
         } else {  // tiny levels: border rows may fold more than once
             dim3 b(64, 4), gr(((L.w + 43) / 4 + 63) / 64, (L.rows + 3) / 4, n);
-            eaof::k_resize_generic<<<gr, b, 0, s>>>(dPyr, c->dTabs, g, l);
+            eaof::k_resize_generic<<<gr, b, 0, st>>>(dPyr, c->dTabs, g, l);
         }
         ++launches;
+        };
+    auto launch_fast = [&](int cellBegin, int cellEnd, cudaStream_t st) {
+        const size_t smem = (size_t)FAST_WARPS * g.fastWarpWords * 4;
+        const dim3 gr((cellEnd - cellBegin + FAST_WARPS - 1) / FAST_WARPS, n);
+        if (c->fastGeneric) eaof::k_fast_generic<<<gr, FAST_WARPS * 32, smem, st>>>(dPyr, c->dCells, dCand, dCandCount, g, cellBegin, cellEnd);
+        else c->fastKernel<<<gr, FAST_WARPS * 32, smem, st>>>(dPyr, c->dCells, dCand, dCandCount, g, cellBegin, cellEnd);
+    };
+    auto launch_octree = [&](int levelBegin, int nLevels, cudaStream_t st) {
+        // CTA width by how many (frame, level) CTAs there are; keys + labels in shared memory up to the width's budget
+        const int ctas = n * g.nlevels;
+        const int v = c->octForce >= 0 ? c->octForce : ctas <= 296 ? 2 : ctas <= 592 ? 1 : 0;
+        const int keyCap = c->octKeyCap[v];
+        const size_t smem = c->octSmem + (size_t)keyCap * 6;
+        const dim3 gr(nLevels, n);
+        if (v == 2) eaof::k_octree<1024><<<gr, 1024, smem, st>>>(dCand, dCandCount, dLabel, dSlotXY, dSlotScore, dLvlCount, g, keyCap, levelBegin);
+        else if (v == 1) eaof::k_octree<512><<<gr, 512, smem, st>>>(dCand, dCandCount, dLabel, dSlotXY, dSlotScore, dLvlCount, g, keyCap, levelBegin);
+        else eaof::k_octree<256><<<gr, 256, smem, st>>>(dCand, dCandCount, dLabel, dSlotXY, dSlotScore, dLvlCount, g, keyCap, levelBegin);
+    };
+    if (dagNow) CK(cudaEventRecord(c->evLvl[0], s));
+    for (int l = 1; l < g.nlevels && !fusedNow; ++l) {
+        launch_resize(l, s);
+        if (dagNow) CK(cudaEventRecord(c->evLvl[l], s));
     }
     nvtxRangePop();
     if (prof) CK(cudaEventRecord(c->ev[1], s));
@@ -586,28 +615,27 @@ int run_batch(eaof_orb* c, const uint8_t* dImgs, int n, size_t stride, size_t fr
         const int grid = std::min(c->fastTmaGrid, (A.nItems + FASTT_WARPS - 1) / FASTT_WARPS);
         eaof::k_fast_tma<<<grid, FASTT_WARPS * 32, c->fastTmaSmem, s>>>(c->fastMaps, A, c->dCells, dCand, dCandCount, ctr, g);
         ++launches;
-    } else if (g.cellsPerFrame > 0) {
-        const size_t smem = (size_t)FAST_WARPS * g.fastWarpWords * 4;
-        if (c->fastGeneric)
-            eaof::k_fast_generic<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
-                dPyr, c->dCells, dCand, dCandCount, g);
-        else
-            c->fastKernel<<<dim3((g.cellsPerFrame + FAST_WARPS - 1) / FAST_WARPS, n), FAST_WARPS * 32, smem, s>>>(
-                dPyr, c->dCells, dCand, dCandCount, g);
+    } else if (g.cellsPerFrame > 0 && !dagNow) {
+        launch_fast(0, g.cellsPerFrame, s);
         ++launches;
     }
     if (prof) CK(cudaEventRecord(c->ev[2], s));
-    {
-        // CTA width by how many (frame, level) CTAs there are; keys + labels in shared memory up to the width's budget
-        const int ctas = n * g.nlevels;
-        const int v = c->octForce >= 0 ? c->octForce : ctas <= 296 ? 2 : ctas <= 592 ? 1 : 0;
-        const int keyCap = c->octKeyCap[v];
-        const size_t smem = c->octSmem + (size_t)keyCap * 6;
-        if (v == 2) eaof::k_octree<1024><<<dim3(g.nlevels, n), 1024, smem, s>>>(dCand, dCandCount, dLabel, dSlotXY, dSlotScore, dLvlCount, g, keyCap);
-        else if (v == 1) eaof::k_octree<512><<<dim3(g.nlevels, n), 512, smem, s>>>(dCand, dCandCount, dLabel, dSlotXY, dSlotScore, dLvlCount, g, keyCap);
-        else eaof::k_octree<256><<<dim3(g.nlevels, n), 256, smem, s>>>(dCand, dCandCount, dLabel, dSlotXY, dSlotScore, dLvlCount, g, keyCap);
+    if (!dagNow) {
+        launch_octree(0, g.nlevels, s);
+        ++launches;
+    } else {
+        // per-level branches: FAST + quadtree of level l start as soon as level l exists (events recorded by the pyramid loop)
+        for (int l = 0; l < g.nlevels; ++l) {
+            cudaStream_t st = c->dagStream[l];
+            CK(cudaStreamWaitEvent(st, c->evLvl[l], 0));
+            const int cb = g.L[l].cellOff, ce = l + 1 < g.nlevels ? g.L[l + 1].cellOff : g.cellsPerFrame;
+            if (ce > cb) { launch_fast(cb, ce, st); ++launches; }
+            launch_octree(l, 1, st);
+            ++launches;
+            CK(cudaEventRecord(c->evOct[l], st));
+        }
+        for (int l = 0; l < g.nlevels; ++l) CK(cudaStreamWaitEvent(s, c->evOct[l], 0));
     }
-    ++launches;
     if (prof) CK(cudaEventRecord(c->ev[3], s));
     if (!side) {
         eaof::k_blur<<<dim3((g.blurTasksPerFrame + BLUR_THREADS - 1) / BLUR_THREADS, n), BLUR_THREADS, 0, s>>>(dPyr, dBlur, g);
@@ -700,6 +728,13 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     CKD(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CKD(cudaEventCreateWithFlags(&c->evPyr, cudaEventDisableTiming));
     CKD(cudaEventCreateWithFlags(&c->evBlur, cudaEventDisableTiming));
+    if (const char* e = getenv("EAOF_LAT_DAG")) if (*e) c->latDag = atoi(e) != 0;
+    if (c->latDag)
+        for (int l = 0; l < p.nlevels && l < EAOF_MAX_LEVELS; ++l) {
+            CKD(cudaStreamCreateWithFlags(&c->dagStream[l], cudaStreamNonBlocking));
+            CKD(cudaEventCreateWithFlags(&c->evLvl[l], cudaEventDisableTiming));
+            CKD(cudaEventCreateWithFlags(&c->evOct[l], cudaEventDisableTiming));
+        }
     CKD(cudaStreamCreateWithFlags(&c->streamIn, cudaStreamNonBlocking));
     CKD(cudaStreamCreateWithFlags(&c->streamOut, cudaStreamNonBlocking));
     CKD(cudaEventCreateWithFlags(&c->evOutIdle, cudaEventDisableTiming));
@@ -958,6 +993,11 @@ void eaof_orb_destroy(eaof_orb* c) {
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->evPyr) cudaEventDestroy(c->evPyr);
     if (c->evBlur) cudaEventDestroy(c->evBlur);
+    for (int l = 0; l < EAOF_MAX_LEVELS; ++l) {
+        if (c->dagStream[l]) cudaStreamDestroy(c->dagStream[l]);
+        if (c->evLvl[l]) cudaEventDestroy(c->evLvl[l]);
+        if (c->evOct[l]) cudaEventDestroy(c->evOct[l]);
+    }
     if (c->stream2) cudaStreamDestroy(c->stream2);
     for (int i = 0; i < eaof_orb::kMaxChunks; ++i) {
         if (c->evIn[i]) cudaEventDestroy(c->evIn[i]);

@@ -1419,11 +1419,12 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
                                                                      const CellDesc* __restrict__ cells,
                                                                      uint32_t* __restrict__ cand,
                                                                      uint32_t* __restrict__ candCount,
-                                                                     const __grid_constant__ Geom g) {
+                                                                     const __grid_constant__ Geom g, const int cellBegin,
+                                                                     const int cellEnd) {
     extern __shared__ __align__(16) uint32_t fastSmem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cell = blockIdx.x * FAST_WARPS + warp;
-    if (cell >= g.cellsPerFrame) return;
+    const int cell = cellBegin + blockIdx.x * FAST_WARPS + warp;  // a launch covers cells [cellBegin, cellEnd): all, or one level
+    if (cell >= cellEnd) return;
     const int mapWords = g.fastMapWords;         // multiple of 4
     uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;  // pixel (row r, tile byte column c) at byte (r*PW + 1)*4 + c
     uint32_t* Bm = tile + mapWords;              // arc score of corners (0 elsewhere), same layout
@@ -1442,11 +1443,12 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast_generic(con
                                                                              const CellDesc* __restrict__ cells,
                                                                              uint32_t* __restrict__ cand,
                                                                              uint32_t* __restrict__ candCount,
-                                                                             const __grid_constant__ Geom g) {
+                                                                             const __grid_constant__ Geom g, const int cellBegin,
+                                                                             const int cellEnd) {
     extern __shared__ __align__(16) uint32_t fastSmem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cell = blockIdx.x * FAST_WARPS + warp;
-    if (cell >= g.cellsPerFrame) return;
+    const int cell = cellBegin + blockIdx.x * FAST_WARPS + warp;
+    if (cell >= cellEnd) return;
     const int mapWords = g.fastMapWords;
     uint32_t* tile = fastSmem + (size_t)warp * g.fastWarpWords;
     uint32_t* Bm = tile + mapWords;
@@ -1662,10 +1664,10 @@ __global__ void __launch_bounds__(OCT_THREADS, OCT_THREADS == 256 ? 6 : OCT_THRE
                                                          const uint32_t* __restrict__ candCount,
                                                          uint16_t* __restrict__ label, uint32_t* __restrict__ slotXY,
                                                          uint8_t* __restrict__ slotScore, int* __restrict__ lvlCount,
-                                                         const __grid_constant__ Geom g, const int keyCap) {
+                                                         const __grid_constant__ Geom g, const int keyCap, const int levelBegin) {
     extern __shared__ __align__(16) uint8_t smemRaw[];
     __shared__ OctShared S;
-    const int l = blockIdx.x, f = blockIdx.y;
+    const int l = levelBegin + blockIdx.x, f = blockIdx.y;  // a launch covers levels [levelBegin, levelBegin + gridDim.x)
     const LevelGeom& L = g.L[l];
     const int tid = threadIdx.x, lane = tid & 31;
     const int cap = g.maxNodeCap;

@@ -303,13 +303,24 @@ void ORBextractor::operator()(cv::InputArray imageArray, cv::InputArray, std::ve
     }
     descriptorArray.create(n, 32, CV_8U);
     cv::Mat descriptors = descriptorArray.getMat();
-    keypoints.reserve(n);
+    keypoints.resize(n);
     for(int i = 0; i < n; ++i)
     {
         const eaof_kp& k = kps[i];
-        keypoints.push_back(cv::KeyPoint(k.x, k.y, k.size, k.angle, k.response, k.octave, -1));
-        memcpy(descriptors.ptr(i), &G.descStage[32*(size_t)i], 32);
+        cv::KeyPoint& o = keypoints[i];
+        o.pt.x = k.x;
+        o.pt.y = k.y;
+        o.size = k.size;
+        o.angle = k.angle;
+        o.response = k.response;
+        o.octave = k.octave;
+        o.class_id = -1;
     }
+    if(descriptors.isContinuous())
+        memcpy(descriptors.data, &G.descStage[0], 32*(size_t)n);
+    else
+        for(int i = 0; i < n; ++i)
+            memcpy(descriptors.ptr(i), &G.descStage[32*(size_t)i], 32);
 }
 
 }  // namespace ORB_SLAM2
