@@ -87,6 +87,7 @@ __global__ void k_hamming_pairs(const uint8_t* __restrict__ a, const uint8_t* __
 struct BowSeg { int qOff, qCnt, tOff, tCnt; };  // one vocabulary node present in both feature vectors
 
 struct BowArgs {
+    int spec;  // k_bow_resolve: 32-queries-at-a-time resolution (needs stride * 4 bytes of shared memory for the proposal owners)
     // per pair p: descriptors of the query/target blocks, optional CSR index lists (NULL = identity)
     const uint8_t* desc;      // base
     const float* angle;       // base, same indexing as desc rows
@@ -328,7 +329,10 @@ __global__ void __launch_bounds__(32) k_bow_resolve(BowArgs A, const uint32_t* _
     const uint32_t* nearP = nearBuf + (size_t)pair * A.stride * 8;
 
     const int words = (A.stride + 31) >> 5;
+    uint32_t* owner = smem + words;  // [stride] lowest lane of the current batch that proposes this target (0xffffffff: none)
     for (int i = lane; i < words; i += 32) smem[i] = 0;
+    if (A.spec)
+        for (int i = lane; i < A.stride; i += 32) owner[i] = 0xffffffffu;
     for (int i = lane; i < EAOF_HISTO_LENGTH; i += 32) hist[i] = 0;
     for (int i = lane; i < nOut; i += 32) { mOut[i] = -1; if (dOut) dOut[i] = -1; }
     __syncwarp();
@@ -357,6 +361,53 @@ __global__ void __launch_bounds__(32) k_bow_resolve(BowArgs A, const uint32_t* _
             }
             const int myCnt = ok ? (int)w1.w : 0;
             const unsigned todo = __ballot_sync(0xffffffffu, myCnt > 0);
+            if (todo == 0) continue;
+            if (A.spec && !__any_sync(0xffffffffu, myCnt > NEAR_K)) {
+                // 32 queries at once, exact: every lane resolves its own query against the matched-target bitmap plus the
+                // targets proposed by EARLIER lanes of this batch (owner[t] < lane), proposals are republished and the
+                // evaluation repeated until nothing changes.  Lane 0 is never blocked by a proposal, lane l only by lanes
+                // < l: by induction the fixed point is the result of walking the 32 queries in order, reached after as many
+                // rounds as the longest chain of stolen targets (one or two in practice).  Batches with a query that needs
+                // the exact re-scan (> NEAR_K near candidates) take the sequential loop below.
+                const uint32_t e[NEAR_K] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
+                int accT = -1, accD = 0;
+                for (;;) {
+                    int best1 = 256, best2 = 256, bestIdx = -1;
+#pragma unroll
+                    for (int k = 0; k < NEAR_K; ++k) {
+                        if (k < myCnt) {
+                            const int t = e[k] & 0xffff, d = (int)(e[k] >> 16);
+                            if (!((smem[t >> 5] >> (t & 31)) & 1u) && owner[t] >= (uint32_t)lane) {
+                                if (d < best1) { best2 = best1; best1 = d; bestIdx = t; }
+                                else if (d < best2) best2 = d;
+                            }
+                        }
+                    }
+                    const int newT = (bestIdx >= 0 && best1 <= A.thEff && (float)best1 < __fmul_rn(A.ratio, (float)best2)) ? bestIdx : -1;
+                    const bool changed = newT != accT;
+                    if (!__any_sync(0xffffffffu, changed)) break;
+                    __syncwarp();
+                    if (accT >= 0) owner[accT] = 0xffffffffu;  // retract (a proposal of the same target by another lane is re-published below)
+                    __syncwarp();
+                    accT = newT;
+                    accD = best1;
+                    if (accT >= 0) atomicMin(&owner[accT], (uint32_t)lane);
+                    __syncwarp();
+                }
+                // commit in query order
+                const unsigned am = __ballot_sync(0xffffffffu, accT >= 0);
+                if (accT >= 0) {
+                    const int outIdx = A.mode == EAOF_BOW_KF_FRAME ? accT : myQ;
+                    atomicOr(&smem[accT >> 5], 1u << (accT & 31));
+                    owner[accT] = 0xffffffffu;
+                    mOut[outIdx] = A.mode == EAOF_BOW_KF_FRAME ? myQ : accT;
+                    if (dOut) dOut[outIdx] = accD;
+                    acc[nAcc + __popc(am & ((1u << lane) - 1u))] = (uint32_t)myQ | ((uint32_t)accT << 16);
+                }
+                nAcc += __popc(am);
+                __syncwarp();
+                continue;
+            }
             unsigned rem = todo;
             while (rem) {  // queries with at least one near candidate, in list order
                 const int j = __ffs(rem) - 1;
@@ -1580,7 +1631,8 @@ int eaof_match_bow(eaof_matcher* m, int mode, float ratio, int checkOri, int nQ,
     A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
     MCK(cudaMemsetAsync(m->nearBuf, 0, sizeof(uint32_t) * 8 * (size_t)m->maxFeat, s));
     k_bow_dense<<<dim3((unsigned)tiles.size(), 1), BOW_QT, 0, s>>>(A, m->tiles, m->nearBuf);
-    const size_t bm = sizeof(uint32_t) * ((m->maxFeat + 31) / 32);
+    A.spec = m->maxFeat <= 11000;
+    const size_t bm = sizeof(uint32_t) * ((m->maxFeat + 31) / 32 + (A.spec ? (size_t)m->maxFeat : 0));  // matched bitmap + proposal owners
     k_bow_resolve<<<1, 32, bm, s>>>(A, m->nearBuf, m->accBuf, m->outMatch, m->outDist, m->outN);
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(matchOut, m->outMatch, sizeof(int) * nOut, cudaMemcpyDeviceToHost, s));
@@ -1708,7 +1760,8 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, i
     A.thEff = mode == EAOF_BOW_KF_FRAME ? EAOF_TH_LOW : EAOF_TH_LOW - 1;
     A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
     k_bow_dense<<<dim3((blockStride + BOW_QT - 1) / BOW_QT, nPairs), BOW_QT, 0, s>>>(A, nullptr, m->nearBuf);
-    const size_t bm = sizeof(uint32_t) * ((blockStride + 31) / 32);
+    A.spec = blockStride <= 11000;
+    const size_t bm = sizeof(uint32_t) * ((blockStride + 31) / 32 + (A.spec ? (size_t)blockStride : 0));
     k_bow_resolve<<<nPairs, 32, bm, s>>>(A, m->nearBuf, m->accBuf, dMatch, dDist, dN);
     MCK(cudaGetLastError());
     m->lastDistances = -1;  // counts live on the device; the caller knows nQ*nT per pair
@@ -1731,7 +1784,8 @@ int eaof_internal_bruteforce_pairs_device(eaof_matcher* m, int mode, float ratio
     A.thEff = mode == EAOF_BOW_KF_FRAME ? EAOF_TH_LOW : EAOF_TH_LOW - 1;
     A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
     k_bow_dense<<<dim3((blockStride + BOW_QT - 1) / BOW_QT, nPairs), BOW_QT, 0, s>>>(A, nullptr, m->nearBuf);
-    const size_t bm = sizeof(uint32_t) * ((blockStride + 31) / 32);
+    A.spec = blockStride <= 11000;
+    const size_t bm = sizeof(uint32_t) * ((blockStride + 31) / 32 + (A.spec ? (size_t)blockStride : 0));
     k_bow_resolve<<<nPairs, 32, bm, s>>>(A, m->nearBuf, m->accBuf, dMatch, dDist, dN);
     MCK(cudaGetLastError());
     m->lastDistances = -1;
@@ -1779,7 +1833,8 @@ int eaof_match_bow_orb_device(eaof_matcher* m, eaof_orb* ex, int nFrames, int mo
     A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
     k_bow_plan<<<nPairs, 32, 0, s>>>(A, dNFNodes, dNodeIds, dNodeStart, m->segsBatch, m->segCountBatch);
     k_bow_dense_nodes<<<dim3((cap + BOW_QT - 1) / BOW_QT, nPairs), BOW_QT, 0, s>>>(A, m->nearBuf);
-    const size_t bm = sizeof(uint32_t) * ((cap + 31) / 32);
+    A.spec = cap <= 11000;
+    const size_t bm = sizeof(uint32_t) * ((cap + 31) / 32 + (A.spec ? (size_t)cap : 0));
     k_bow_resolve<<<nPairs, 32, bm, s>>>(A, m->nearBuf, m->accBuf, dMatch, dDist, dN);
     MCK(cudaGetLastError());
     m->lastDistances = -1;
