@@ -134,8 +134,9 @@ __global__ void __launch_bounds__(128) k_level0_bulk(const uint8_t* __restrict__
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar, (uint32_t)(nr * w));
     }
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(nr * w));
     __syncthreads();
     if (threadIdx.x < nr)
         bulk_load(base + threadIdx.x * span + EAOF_INNER_X0, in + (size_t)f * framePitch + (size_t)(y0 + threadIdx.x) * stride, (uint32_t)w, bar);
@@ -591,10 +592,11 @@ __global__ void __launch_bounds__(256) k_resize_bulk(uint8_t* __restrict__ pyr, 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar, (uint32_t)(nS * srcBytes));
     }
     __syncthreads();
     if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(nS * srcBytes));
+        __syncwarp();
         const uint8_t* src = frame + S.off + (size_t)(EAOF_EDGE + syA) * S.pitch + EAOF_INNER_X0;
         for (int r = threadIdx.x; r < nS; r += 32) bulk_load(base + r * srcBytes, src + (size_t)r * S.pitch, (uint32_t)srcBytes, bar);
     }
@@ -1313,8 +1315,8 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
             if (k2 && p2c < FAST_CLST2) clst[p2c] = (uint16_t)eB;
             ncorn += __popc(m0) + __popc(m2);
         }
+        __syncwarp();  // the list is rewritten by the next attempt, the score map read by (C)
         if (ncorn == 0) continue;
-        __syncwarp();
         // ---- (C)
         if (ncorn <= FAST_CLST2) {
 #pragma unroll 1
@@ -2313,6 +2315,9 @@ __global__ void __launch_bounds__(DESC_TMA_WARPS * 32) k_angle_desc_tma(const __
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
         mbar_expect_tx(bar, (uint32_t)(DESC_BOXA_W * DESC_BOXA_H + DESC_BOXB_W * DESC_BOXB_H));
         tma_load_3d(smem_u32(boxA), &mapsPyr.m[l][0], cxA & ~15, EAOF_EDGE + Y - EAOF_HALF_PATCH, f0 + f, bar);
         tma_load_3d(smem_u32(boxB), &mapsBlur.m[l][0], cxB & ~15, Y, f0 + f, bar);
