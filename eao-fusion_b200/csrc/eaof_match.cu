@@ -24,6 +24,8 @@
 #include <vector>
 
 #include "../../include/eaof_match.h"
+#include "bow_umma.cuh"
+#include <cuda.h>
 
 extern "C" int eaof_internal_fail(int code, const char* msg);  // sets eaof_last_error (eaof_orb.cu)
 // device-resident results of an extractor handle, and the hook that makes its next batch wait for a reader (eaof_orb.cu)
@@ -1414,6 +1416,15 @@ struct eaof_matcher {
     cudaStream_t stream = nullptr;
     cudaEvent_t evDep = nullptr;
     uint32_t *nearBuf = nullptr, *accBuf = nullptr;
+    // tcgen05 path of the brute-force matcher (bow_umma.cuh): +-1-expanded copy of a descriptor array and its tensor maps
+    int8_t* umma8 = nullptr;
+    size_t ummaCap = 0;                 // descriptors the buffer holds
+    const uint8_t* ummaSrc = nullptr;   // array the expansion was made from (valid between prepare and release)
+    int ummaBlocks = 0, ummaStride = 0;
+    eaof_umma::TMap ummaMapA{}, ummaMapB{};
+    void* encodeTiled = nullptr;
+    int sms = 0;
+    bool ummaOn = true;                 // EAOF_BOW_UMMA=0: POPC kernel (k_bow_dense)
     int *cellStart = nullptr, *cellIdx = nullptr;
     float4* cellPack = nullptr;  // grid lists as (x, y, octave, index) entries
     // SoA staging, [maxPairs][maxFeat]
@@ -1501,6 +1512,16 @@ int eaof_matcher_create(int device, int maxPairs, int maxFeat, eaof_matcher** ou
     cudaError_t e = cudaSuccess;
 #define A_(x) if (e == cudaSuccess) e = (x)
     A_(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            m->encodeTiled = fn;
+        else
+            cudaGetLastError();
+        cudaDeviceGetAttribute(&m->sms, cudaDevAttrMultiProcessorCount, device);
+        if (const char* e = getenv("EAOF_BOW_UMMA")) if (*e) m->ummaOn = atoi(e) != 0;
+    }
     A_(cudaEventCreateWithFlags(&m->evDep, cudaEventDisableTiming));
     A_(cudaEventCreateWithFlags(&m->evStage, cudaEventDisableTiming));
     A_(cudaMallocHost(&m->hStage, sizeof(int) * 4 * (size_t)maxPairs));
@@ -1540,6 +1561,7 @@ void eaof_matcher_destroy(eaof_matcher* m) {
                     m->pairIdx, m->pairShift, m->outMatch, m->outDist, m->outN, m->qRadius, m->qMaxL, m->initBin, m->cellPack,
                     m->segsBatch, m->segCountBatch, m->orbAngle};
     for (void* p : ptrs) cudaFree(p);
+    cudaFree(m->umma8);
     if (m->evDep) cudaEventDestroy(m->evDep);
     if (m->evStage) cudaEventDestroy(m->evStage);
     cudaFreeHost(m->hStage);
@@ -1743,6 +1765,71 @@ double eaof_debug_popc_rate(int device) {
     return best;
 }
 
+// ---- tcgen05 path of phase 1 (bow_umma.cuh) ----------------------------------------------------------------------------
+// prepare: +-1 expansion of blocks [0, nBlocks) of a descriptor array on the matcher's stream + tensor maps over it; valid
+// until release (the array may be rewritten by the caller between calls, so nothing is cached across API calls).
+// Returns false when the path is unavailable (no cuTensorMapEncodeTiled, switched off, allocation failure): callers fall
+// back to k_bow_dense.
+static bool umma_prepare(eaof_matcher* m, const uint8_t* dDesc, int nBlocks, int blockStride) {
+    m->ummaSrc = nullptr;
+    if (!m->ummaOn || !m->encodeTiled || nBlocks < 1 || m->sms < 1) return false;
+    const size_t nDesc = (size_t)nBlocks * blockStride;
+    if (nDesc >= ((size_t)1 << 31)) return false;
+    if (nDesc > m->ummaCap) {
+        cudaStreamSynchronize(m->stream);
+        cudaFree(m->umma8);
+        m->umma8 = nullptr; m->ummaCap = 0;
+        if (cudaMalloc(&m->umma8, nDesc * 256) != cudaSuccess) { cudaGetLastError(); return false; }
+        m->ummaCap = nDesc;
+    }
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    for (int which = 0; which < 2; ++which) {
+        const cuuint64_t dims[2] = {256, (cuuint64_t)nDesc};
+        const cuuint64_t strides[1] = {256};
+        const cuuint32_t box[2] = {128, (cuuint32_t)(which ? eaof_umma::kTileT : eaof_umma::kTileQ)}, es[2] = {1, 1};
+        if (((EncodeTiled)m->encodeTiled)(reinterpret_cast<CUtensorMap*>(which ? &m->ummaMapB : &m->ummaMapA), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                                          m->umma8, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    static bool attrSet[64] = {};
+    if (m->device < 64 && !attrSet[m->device]) {
+        if (cudaFuncSetAttribute(eaof_umma::k_bow_dense_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, eaof_umma::kSmemBytes) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attrSet[m->device] = true;
+    }
+    eaof_umma::k_expand_pm1<<<(unsigned)((nDesc * 16 + 255) / 256), 256, 0, m->stream>>>(dDesc, m->umma8, nDesc);
+    if (cudaGetLastError() != cudaSuccess) return false;
+    m->ummaSrc = dDesc; m->ummaBlocks = nBlocks; m->ummaStride = blockStride;
+    return true;
+}
+static void umma_release(eaof_matcher* m) { m->ummaSrc = nullptr; }
+// phase 1 of a brute-force chunk: tensor cores when the expansion of this array is in place, POPC kernel otherwise
+static void bruteforce_dense(eaof_matcher* m, const BowArgs& A, int nPairs, const uint8_t* dDesc, int blockStride) {
+    cudaStream_t s = m->stream;
+    if (m->ummaSrc == dDesc && m->ummaStride == blockStride) {
+        eaof_umma::Args U{A.pairQ, A.pairT, A.counts, blockStride, nPairs, (blockStride + eaof_umma::kTileQ - 1) / eaof_umma::kTileQ, A.D};
+        eaof_umma::k_bow_dense_umma<<<m->sms, eaof_umma::kThreads, eaof_umma::kSmemBytes, s>>>(m->ummaMapA, m->ummaMapB, U, m->nearBuf);
+    } else {
+        k_bow_dense<<<dim3((blockStride + BOW_QT - 1) / BOW_QT, nPairs), BOW_QT, 0, s>>>(A, nullptr, m->nearBuf);
+    }
+}
+extern "C" int eaof_internal_bruteforce_prepare(eaof_matcher* m, const uint8_t* dDesc, int nBlocks, int blockStride) {
+    if (!m || !dDesc) return mfail(EAOF_ERR_ARG, "null argument");
+    MCK(cudaSetDevice(m->device));
+    umma_prepare(m, dDesc, nBlocks, blockStride);  // false = the POPC kernel serves the chunks
+    return EAOF_OK;
+}
+extern "C" int eaof_internal_bruteforce_release(eaof_matcher* m) {
+    if (!m) return mfail(EAOF_ERR_ARG, "null argument");
+    umma_release(m);
+    return EAOF_OK;
+}
+
 int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, int checkOri, int nPairs, const int* pairQ,
                                        const int* pairT, const uint8_t* dDesc, const float* dAngle, const int* dCounts,
                                        int blockStride, int* dMatch, int* dDist, int* dN) {
@@ -1759,7 +1846,17 @@ int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float ratio, i
     A.blockStride = blockStride; A.stride = blockStride; A.mode = mode;
     A.thEff = mode == EAOF_BOW_KF_FRAME ? EAOF_TH_LOW : EAOF_TH_LOW - 1;
     A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
-    k_bow_dense<<<dim3((blockStride + BOW_QT - 1) / BOW_QT, nPairs), BOW_QT, 0, s>>>(A, nullptr, m->nearBuf);
+    {
+        int maxBlock = 0;
+        for (int p = 0; p < nPairs; ++p) {
+            if (pairQ[p] < 0 || pairT[p] < 0) return mfail(EAOF_ERR_ARG, "negative block index in pair %d", p);
+            maxBlock = std::max(maxBlock, std::max(pairQ[p], pairT[p]));
+        }
+        // worth the expansion (256 B written per descriptor) when the pairs outnumber the blocks they touch
+        if (nPairs >= 4 && nPairs * 2 >= maxBlock + 1) umma_prepare(m, dDesc, maxBlock + 1, blockStride);
+    }
+    bruteforce_dense(m, A, nPairs, dDesc, blockStride);
+    umma_release(m);
     A.spec = blockStride <= 11000;
     const size_t bm = sizeof(uint32_t) * ((blockStride + 31) / 32 + (A.spec ? (size_t)blockStride : 0));
     k_bow_resolve<<<nPairs, 32, bm, s>>>(A, m->nearBuf, m->accBuf, dMatch, dDist, dN);
@@ -1783,7 +1880,7 @@ int eaof_internal_bruteforce_pairs_device(eaof_matcher* m, int mode, float ratio
     A.blockStride = blockStride; A.stride = blockStride; A.mode = mode;
     A.thEff = mode == EAOF_BOW_KF_FRAME ? EAOF_TH_LOW : EAOF_TH_LOW - 1;
     A.D = near_threshold(A.thEff, ratio); A.ratio = ratio; A.checkOri = checkOri;
-    k_bow_dense<<<dim3((blockStride + BOW_QT - 1) / BOW_QT, nPairs), BOW_QT, 0, s>>>(A, nullptr, m->nearBuf);
+    bruteforce_dense(m, A, nPairs, dDesc, blockStride);  // tensor cores when eaof_internal_bruteforce_prepare expanded this array
     A.spec = blockStride <= 11000;
     const size_t bm = sizeof(uint32_t) * ((blockStride + 31) / 32 + (A.spec ? (size_t)blockStride : 0));
     k_bow_resolve<<<nPairs, 32, bm, s>>>(A, m->nearBuf, m->accBuf, dMatch, dDist, dN);

@@ -22,6 +22,8 @@ extern "C" int eaof_internal_bruteforce_pairs_device(eaof_matcher* m, int mode, 
                                                      const float* dAngle, const int* dCounts, int blockStride, int* dMatch,
                                                      int* dDist, int* dN);
 extern "C" int eaof_internal_matcher_limits(const eaof_matcher* m, int* maxPairs, int* maxFeat, int* device);
+extern "C" int eaof_internal_bruteforce_prepare(eaof_matcher* m, const uint8_t* dDesc, int nBlocks, int blockStride);
+extern "C" int eaof_internal_bruteforce_release(eaof_matcher* m);
 
 namespace {
 
@@ -224,14 +226,18 @@ int eaof_sweep_match(eaof_sweep* s, eaof_matcher* m, int mode, float nnratio, in
     SCK(cudaMemcpyAsync(s->dPairs, s->hPairs, sizeof(int) * (size_t)nPairs, cudaMemcpyHostToDevice, st));
     SCK(cudaMemcpyAsync(s->dPairs + s->pairCap, s->hPairs + s->pairCap, sizeof(int) * (size_t)nPairs, cudaMemcpyHostToDevice, st));
     SCK(cudaEventRecord(s->evPairs, st));
+    // the gathered descriptors are expanded once for the tensor-core distance kernel, every chunk of pairs reads the expansion
+    rc = eaof_internal_bruteforce_prepare(m, dDescAll, nBlocks, blockStride);
+    if (rc) return rc;
     for (int p0 = 0; p0 < nPairs; p0 += maxPairs) {
         const int n = nPairs - p0 < maxPairs ? nPairs - p0 : maxPairs;
         rc = eaof_internal_bruteforce_pairs_device(m, mode, nnratio, checkOri, n, s->dPairs + p0, s->dPairs + s->pairCap + p0,
                                                    dDescAll, dAngleAll, dCountAll, blockStride,
                                                    dMatch + (size_t)p0 * blockStride, dDist + (size_t)p0 * blockStride, dN + p0);
-        if (rc) return rc;
+        if (rc) break;
     }
-    return EAOF_OK;
+    eaof_internal_bruteforce_release(m);
+    return rc;
 }
 
 int eaof_sweep_last_allgather(eaof_sweep* s, float* ms, long long* bytes) {
