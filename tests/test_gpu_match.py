@@ -473,3 +473,62 @@ def test_distinctive_descriptors(matcher_factory):
         for p, d in enumerate(descs):
             ob, om = po.o_distinctive_descriptor(d)
             assert best[p] == ob and (ob < 0 or med[p] == om), (p, len(d), best[p], ob)
+
+
+def test_tensor_core_hamming_equals_popc_kernel(matcher_factory, monkeypatch):
+    """Phase 1 of the brute-force matcher has two kernels: k_bow_dense (XOR + POPC) and k_bow_dense_umma (tcgen05.mma kind::i8 on
+    +-1-expanded descriptors, near lists scanned out of TMEM).  Ragged blocks (2000 / 1999 / 257 / 130 / 128 / 1 / 0 descriptors),
+    planted near-duplicates with few flipped bits (lists longer than NEAR_K -> exact re-scan in phase 2) and plain noise: both
+    kernels must give identical matches, distances and counts, and equal the oracle's SearchByBoW on single pairs."""
+    import torch
+    import eaof
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(123)
+    stride = 2000
+    counts = np.array([2000, 1999, 257, 130, 128, 1, 0, 2000, 777, 2000], np.int32)
+    nb = len(counts)
+    desc = rng.integers(0, 256, (nb, stride, 32), dtype=np.uint8)
+    for b in range(1, nb):  # most descriptors of block b are noisy copies of descriptors of block b-1
+        if counts[b - 1] == 0:
+            continue
+        for i in range(counts[b]):
+            if i % 4 == 3:
+                continue
+            j = (i * 7) % counts[b - 1] if i % 4 else (i // 8) % counts[b - 1]  # every 4th: many queries share a target
+            d = desc[b - 1, j].copy()
+            flips = rng.integers(0, 256, rng.integers(0, 60))
+            for f in flips:
+                d[f >> 3] ^= np.uint8(1 << (f & 7))
+            desc[b, i] = d
+    angle = rng.uniform(0, 360, (nb, stride)).astype(np.float32)
+    pq = [b for b in range(1, nb)] + [0, 7, 9, 1, 8, 2]
+    pt = [b - 1 for b in range(1, nb)] + [7, 9, 0, 8, 1, 9]
+    d_desc, d_angle, d_cnt = torch.from_numpy(desc).cuda(), torch.from_numpy(angle).cuda(), torch.from_numpy(counts).cuda()
+    out = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("EAOF_BOW_UMMA", knob)
+        m = matcher_factory(0.8, True, max_features=stride, max_pairs=32)
+        res = []
+        for mode in (0, 1):
+            bm = torch.full((len(pq), stride), -7, dtype=torch.int32, device="cuda")
+            bd = torch.full((len(pq), stride), -7, dtype=torch.int32, device="cuda")
+            bn = torch.zeros(len(pq), dtype=torch.int32, device="cuda")
+            m.bruteforce_batch_device(mode, pq, pt, d_desc.data_ptr(), d_angle.data_ptr(), d_cnt.data_ptr(), stride, bm.data_ptr(),
+                                      bd.data_ptr(), bn.data_ptr())
+            m.sync()
+            res.append((bm.cpu().numpy(), bd.cpu().numpy(), bn.cpu().numpy()))
+        out[knob] = res
+    for mode in (0, 1):
+        for a, b in zip(out["1"][mode], out["0"][mode]):
+            assert np.array_equal(a, b), f"tensor-core and POPC kernels differ (mode {mode})"
+        hm, hd, hn = out["1"][mode]
+        assert hn.sum() > 300
+        for k in (0, 1, 2, 9, 11):
+            i, j = pq[k], pt[k]
+            nq, nt = int(counts[i]), int(counts[j])
+            nodes_q, nodes_t = eaof.csr_from_nodes(np.zeros(nq, int)), eaof.csr_from_nodes(np.zeros(nt, int))
+            on, omatch, odist = po.o_search_by_bow(mode, 0.8, True, desc[i, :nq], angle[i, :nq], None, nodes_q, desc[j, :nt], angle[j, :nt],
+                                                   None, nodes_t)
+            nout = nt if mode == 0 else nq
+            assert hn[k] == on
+            assert np.array_equal(hm[k, :nout], omatch) and np.array_equal(hd[k, :nout], odist)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Opcode histogram of every kernel in libeaof_orb.so (cuobjdump -sass), with the Blackwell tells called out:
-UTMALDG (cp.async.bulk.tensor), UBLKCP (cp.async.bulk), SYNCS (mbarrier), VIMNMX3 / VABSDIFF4 / IDP (DPX and byte-SIMD).
+UTCIMMA (tcgen05.mma kind::i8), LDTM (tcgen05.ld), UTCBAR (tcgen05.commit), UTMALDG (cp.async.bulk.tensor), UBLKCP
+(cp.async.bulk), SYNCS (mbarrier), VIMNMX3 / VABSDIFF4 / IDP (DPX and byte-SIMD).
 python tools/sass_histogram.py > profiles/rNN_sass_histogram.txt"""
 import collections
 import os
@@ -16,7 +17,7 @@ cur = None
 for line in txt.splitlines():
     m = re.search(r"Function : (\S+)", line)
     if m:
-        dem = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        dem = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().replace("(anonymous namespace)::", "")
         depth, cut = 0, len(dem)
         for i, ch in enumerate(dem):  # argument list = first "(" outside template brackets
             if ch == "<":
@@ -32,7 +33,7 @@ for line in txt.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m and cur:
         per[cur][m.group(1).split(".")[0]] += 1
-tells = ["UTMALDG", "UBLKCP", "SYNCS", "VIMNMX3", "VIMNMX", "VABSDIFF4", "IDP", "POPC", "LDGSTS", "REDUX", "MATCH", "SHFL", "VOTE"]
+tells = ["UTCIMMA", "LDTM", "UTCBAR", "UTMALDG", "UBLKCP", "SYNCS", "VIMNMX3", "VABSDIFF4", "IDP", "POPC", "MATCH", "SHFL", "VOTE"]
 print(f"# cuobjdump -sass {os.path.relpath(so, ROOT)} (sm_100a): static instruction counts per kernel")
 print(f"{'kernel':58s} {'total':>6s} " + " ".join(f"{t:>9s}" for t in tells))
 for k, c in per.items():
