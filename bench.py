@@ -698,11 +698,19 @@ def hamming_sweep(eaof, torch, dist, rank, world, device, n_blocks=448, n_feat=2
            "single_gpu_pairs_per_s": npm / min(secs_local, secs) if world == 1 else npm / secs_local,
            "efficiency_vs_n1": 1.0 if world == 1 else (n_pairs / secs_max) / (world * npm / secs_local),
            "matches_total": int(chk[0]), "matches_per_pair": float(chk[0]) / n_pairs, "checksum": int(chk[1]),
+           # phase 1 runs on the tensor cores (k_bow_dense_umma: tcgen05.mma kind::i8 on +-1-expanded descriptors, one distance
+           # = a 256-long int8 dot product = 512 int8 ops) unless EAOF_BOW_UMMA=0; its floor is reading the int32 accumulators
+           # out of TMEM (4 B per distance at 64 B per clock and SM), not the MMAs
+           "kernel": "k_bow_dense (XOR + POPC)" if os.environ.get("EAOF_BOW_UMMA", "1") == "0" else
+                     "k_bow_dense_umma (tcgen05.mma kind::i8, TMA operands, TMEM accumulators)",
+           "int8_tops_achieved_per_gpu": 512.0 * dists / secs_max / world / 1e12,
+           "int8_tops_nominal_dense": 4500.0,
+           "tmem_read_floor_distances_per_s_per_gpu": 148 * 1.965e9 * 64 / 4,
+           "frac_of_tmem_read_floor": (dists / secs_max / world) / (148 * 1.965e9 * 64 / 4),
+           # the POPC kernel's roofline, kept for comparison: 8 XOR words per distance, carry-save adders fold them to 5 POPC
            "popc_peak_per_s": popc,
-           # 8 XOR words per distance; three carry-save adders fold them so that 5 POPC are executed per distance
-           "popc_executed_per_distance": 5,
-           "xu_pipe_frac": (5.0 * dists / secs_max) / (popc * world) if popc > 0 else None,
-           "frac_of_naive_popc_roofline": (8.0 * dists / secs_max) / (popc * world) if popc > 0 else None}
+           "distances_per_s_if_popc_bound_8_per_distance": popc / 8.0 if popc > 0 else None,
+           "speedup_over_naive_popc_roofline": (8.0 * dists / secs_max) / (popc * world) if popc > 0 else None}
     del st, e0, e1, e2, e3
     sw.close(); sw1.close(); mt.close()
     return out
