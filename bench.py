@@ -637,7 +637,7 @@ def hamming_sweep(eaof, torch, dist, rank, world, device, n_blocks=448, n_feat=2
     gt = ((i * 7 + 1 + i // n_blocks) % n_blocks).astype(np.int32)
     mine = np.arange(rank, n_pairs, world)
     pq, pt = gq[mine], gt[mine]
-    mt = eaof.ORBmatcher(0.9, True, max_features=n_feat, max_pairs=1024, device=device)
+    mt = eaof.ORBmatcher(0.9, True, max_features=n_feat, max_pairs=4096, device=device)
     g_desc = torch.empty((n_blocks, n_feat, 32), dtype=torch.uint8, device="cuda")
     g_ang = torch.empty((n_blocks, n_feat), dtype=torch.float32, device="cuda")
     g_cnt = torch.empty((n_blocks,), dtype=torch.int32, device="cuda")
