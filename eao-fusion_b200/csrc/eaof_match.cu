@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(32) k_bow_resolve(BowArgs A, const uint32_t* _
                     __syncwarp();
                 }
                 // commit in query order
+                __syncwarp();  // every lane has finished reading the bitmap and the owners
                 const unsigned am = __ballot_sync(0xffffffffu, accT >= 0);
                 if (accT >= 0) {
                     const int outIdx = A.mode == EAOF_BOW_KF_FRAME ? accT : myQ;
