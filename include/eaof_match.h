@@ -177,7 +177,11 @@ int eaof_match_projection_batch_device(eaof_matcher* m, eaof_orb* ex, int n_pair
 /* Brute-force SearchByBoW semantics (one vocabulary node holding every feature) over pairs of descriptor blocks
  * resident on the device: block f = d_desc + f*block_stride*32 with d_counts[f] features and angles
  * d_angle + f*block_stride.  Pair p: queries = block pair_q[p], targets = block pair_t[p].  Outputs as
- * eaof_match_bow, laid out [pair][block_stride].  pair_q/pair_t are host arrays. */
+ * eaof_match_bow, laid out [pair][block_stride].  pair_q/pair_t are host arrays.
+ * The distances are computed on the tensor cores (tcgen05.mma kind::i8 on a +-1 expansion of blocks 0..max index, made on
+ * the matcher's stream at every call since the caller may rewrite the array in between; 256 B of scratch per descriptor)
+ * when the pairs outnumber the blocks they touch, by the XOR + POPC kernel otherwise or with EAOF_BOW_UMMA=0; both give the
+ * same matches. */
 int eaof_match_bruteforce_batch_device(eaof_matcher* m, int mode, float nnratio, int check_orientation, int n_pairs,
                                        const int* pair_q, const int* pair_t, const uint8_t* d_desc,
                                        const float* d_angle, const int* d_counts, int block_stride, int* d_match,
