@@ -579,6 +579,7 @@ __global__ void __launch_bounds__(256) k_resize_bulk(uint8_t* __restrict__ pyr, 
                                                      const __grid_constant__ Geom g, int l) {
     extern __shared__ __align__(128) uint8_t rszSmem[];
     __shared__ __align__(8) unsigned long long rszBar;
+    __shared__ int4 rszRows[16];  // per destination row of this CTA: source rows sy0, sy1 (clamped) and the coefficients b0, b1
     const LevelGeom& D = g.L[l];
     const LevelGeom& S = g.L[l - 1];
     const int y0 = blockIdx.x * RSZ_ROWS, yEnd = min(y0 + RSZ_ROWS, D.h);
@@ -592,6 +593,10 @@ __global__ void __launch_bounds__(256) k_resize_bulk(uint8_t* __restrict__ pyr, 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((int)threadIdx.x < yEnd - y0) {  // the row constants are the same for every thread of the CTA: fetched and clamped once
+        const int2 e = __ldg(yt + y0 + threadIdx.x);
+        rszRows[threadIdx.x] = make_int4(min(max(e.x, 0), S.h - 1), min(max(e.x + 1, 0), S.h - 1), e.y & 0xffff, (int)((unsigned)e.y >> 16));
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -640,11 +645,10 @@ __global__ void __launch_bounds__(256) k_resize_bulk(uint8_t* __restrict__ pyr, 
         };
         // one destination row: horizontal pass of the source rows not yet held, vertical pass, packed word
         auto row = [&](int y) -> uint32_t {
-            const int2 e = __ldg(yt + y);
-            const int sy = e.x;
+            const int4 e = rszRows[y - y0];
             // b in [0, 2048], h < 2^15: the products fit 32 bits, (b * h) >> 16 is a plain shift (folded into the adds)
-            const unsigned b0 = (unsigned)e.y & 0xffffu, b1 = (unsigned)e.y >> 16;
-            const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
+            const unsigned b0 = (unsigned)e.z, b1 = (unsigned)e.w;
+            const int sy0 = e.x, sy1 = e.y;
             unsigned hA[4];
             if (sy0 == cached) {
 #pragma unroll
