@@ -508,20 +508,22 @@ def pcie_ceiling(torch, dist, world, h2d_bytes, d2h_bytes, frames, reps=12):
     for _ in range(2):
         du.copy_(hu, non_blocking=True); hd.copy_(dd, non_blocking=True)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        with torch.cuda.stream(s1):
-            du.copy_(hu, non_blocking=True)
-        with torch.cuda.stream(s2):
-            hd.copy_(dd, non_blocking=True)
-    torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    dt = None
+    for _ in range(3):  # best of three: a ceiling, not an average (other tenants of the host share the root complex)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(s1):
+                du.copy_(hu, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hd.copy_(dd, non_blocking=True)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item()) if dt is None else min(dt, float(t.item()))
     del hu, du, hd, dd
     return {"frames_per_s_ceiling": world * frames * reps / dt, "h2d_gbs_aggregate": world * h2d_bytes * reps / dt / 1e9,
             "d2h_gbs_aggregate": world * d2h_bytes * reps / dt / 1e9,
