@@ -370,7 +370,7 @@ def measure_config(eaof, torch, dist, rank, world, device, name, B, steps, warmu
     torch.cuda.synchronize()
     t_host1 = time.perf_counter()
     dt = ev0.elapsed_time(ev1) * 1e-3
-    launches_per_batch = ex.last_launch_count() + 3  # + k_build_grid, k_proj_dense, k_proj_resolve
+    launches_per_batch = ex.last_launch_count() + 4  # + k_proj_prepare, k_build_grid, k_proj_dense, k_proj_resolve
     counts = ex.fetch_counts(B + 1)[1:]
     kp_per_frame = float(counts.mean())
     matches_per_pair = float(rig.d_nm.float().mean().item())
