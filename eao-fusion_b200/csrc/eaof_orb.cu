@@ -272,7 +272,7 @@ int build_geometry(eaof_orb* c, std::vector<int>& tabs, std::vector<CellDesc>& c
 #ifdef FAST_LIST_CAP
                     fastList = FAST_LIST_CAP;
 #else
-                    fastList = std::max(fastList, std::max(4 * (ch - 6) * nW, 160));  // every pixel of the inner rows (fast_cell_rows lists a whole attempt at once)
+                    fastList = std::max(fastList, std::max(64 * nW, 160));  // 16 rows of pixels: fast_cell_rows lists 32 rows at once, or two halves
 #endif
                     fastOut = std::max(fastOut, ((cw - 6 + 1) / 2) * ((ch - 6 + 1) / 2));
                 }

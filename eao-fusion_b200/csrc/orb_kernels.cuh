@@ -1165,7 +1165,7 @@ __device__ __forceinline__ unsigned arc_best2_raw(const unsigned (&r)[16], const
 // Requires nW <= 16 words per row and thresholds < 128: eaof_orb_create picks k_fast_generic otherwise.
 #define FAST_CLST2 128  // corner list entries (u16: row << 8 | tile byte column)
 template <int PW>
-__device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uint16_t* clst, uint16_t* lst,
+__device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uint16_t* clst, uint16_t* lst, const int lstCap,
                                                const CellDesc c, const int f, const int mis, const int lane,
                                                uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount, const Geom& g) {
     constexpr int PAD = 1;
@@ -1199,8 +1199,8 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
     for (int attempt = 0; attempt < 2 && no == 0; ++attempt) {
         const int th = attempt == 0 ? g.iniTh : g.minTh;
         const unsigned thK = (unsigned)(127 - th) * 0x01010101u;
-        // ---- (A) + emission, 32 rows at a time
-        int nl = 0;
+        // ---- (A) + emission + (B), 32 rows at a time
+        int ncorn = 0;  // corners found by (B); the first FAST_CLST2 of them are listed for (C)
 #pragma unroll 1
         for (int r0 = 0; r0 < ih; r0 += 32) {
             const int r = r0 + lane;
@@ -1266,58 +1266,69 @@ __device__ __forceinline__ void fast_cell_rows(uint32_t* tile, uint32_t* Bm, uin
                 const int v = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += v;
             }
-            uint16_t* p = lst + nl + (incl - cnt);
-            nl += __shfl_sync(0xffffffffu, incl, 31);
-            const unsigned e0 = ((unsigned)(r + 3) << 8) | ((unsigned)wLo << 2);
+            const int total = __shfl_sync(0xffffffffu, incl, 31), lowHalf = __shfl_sync(0xffffffffu, incl, 15);
+            if (total == 0) continue;
+            // The survivor list holds 16 rows' worth of pixels (it is the largest per-warp array and decides how many warps an
+            // SM keeps resident): a round whose 32 rows have more survivors than that — noise-like cells — is listed and
+            // scored in two halves.
+            const int nsub = total > lstCap ? 2 : 1;
 #pragma unroll 1
-            for (int q = 0; q < 2; ++q) {
-                unsigned m = q ? acc1 : acc0;
-                const unsigned eq = e0 + 32u * q;
-                while (m) {  // two survivors per trip
-                    unsigned b, b2;
-                    asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(m));
-                    m ^= 1u << b;
-                    p[0] = (uint16_t)(eq + ((b & 7u) << 2) + (b >> 3));
-                    const bool more = m != 0u;
-                    asm("bfind.u32 %0, %1;" : "=r"(b2) : "r"(m));
-                    if (more) {
-                        m ^= 1u << b2;
-                        p[1] = (uint16_t)(eq + ((b2 & 7u) << 2) + (b2 >> 3));
+            for (int sub = 0; sub < nsub; ++sub) {
+                const bool mineNow = nsub == 1 || (lane >> 4) == sub;
+                const int nl = nsub == 1 ? total : (sub ? total - lowHalf : lowHalf);
+                if (mineNow) {
+                    uint16_t* p = lst + (incl - cnt) - (sub ? lowHalf : 0);
+                    const unsigned e0 = ((unsigned)(r + 3) << 8) | ((unsigned)wLo << 2);
+#pragma unroll 1
+                    for (int q = 0; q < 2; ++q) {
+                        unsigned m = q ? acc1 : acc0;
+                        const unsigned eq = e0 + 32u * q;
+                        while (m) {  // two survivors per trip
+                            unsigned b, b2;
+                            asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(m));
+                            m ^= 1u << b;
+                            p[0] = (uint16_t)(eq + ((b & 7u) << 2) + (b >> 3));
+                            const bool more = m != 0u;
+                            asm("bfind.u32 %0, %1;" : "=r"(b2) : "r"(m));
+                            if (more) {
+                                m ^= 1u << b2;
+                                p[1] = (uint16_t)(eq + ((b2 & 7u) << 2) + (b2 >> 3));
+                            }
+                            p += more ? 2 : 1;
+                        }
                     }
-                    p += more ? 2 : 1;
                 }
+                __syncwarp();
+                // ---- (B): two list entries per lane on u16x2, ring pixels read as bytes
+                #pragma unroll 1
+                for (int p0 = 0; p0 < nl; p0 += 64) {
+                    const int iA = p0 + 2 * lane;
+                    const bool actA = iA < nl, actB = iA + 1 < nl;
+                    const int eA = lst[actA ? iA : 0], eB = lst[actB ? iA + 1 : (actA ? iA : 0)];
+                    const int oA = ((eA >> 8) * PW + PAD) * 4 + (eA & 255), oB = ((eB >> 8) * PW + PAD) * 4 + (eB & 255);
+                    const uint8_t* pA = tb + oA;
+                    const uint8_t* pB = tb + oB;
+                    const unsigned cc = (unsigned)pA[0] | ((unsigned)pB[0] << 16);
+                    unsigned d[16];
+        #define RING2(k, off) d[k] = (unsigned)pA[off] | ((unsigned)pB[off] << 16);
+                    RING2(0, 3 * pitchB) RING2(1, 3 * pitchB + 1) RING2(2, 2 * pitchB + 2) RING2(3, pitchB + 3)
+                    RING2(4, 3) RING2(5, -pitchB + 3) RING2(6, -2 * pitchB + 2) RING2(7, -3 * pitchB + 1)
+                    RING2(8, -3 * pitchB) RING2(9, -3 * pitchB - 1) RING2(10, -2 * pitchB - 2) RING2(11, -pitchB - 3)
+                    RING2(12, -3) RING2(13, pitchB - 3) RING2(14, 2 * pitchB - 2) RING2(15, 3 * pitchB - 1)
+        #undef RING2
+                    const unsigned b2 = arc_best2_raw(d, cc);
+                    const int bLo = (int)(b2 & 0xffffu) - 256, bHi = (int)(b2 >> 16) - 256;
+                    const bool k0 = actA && bLo > th, k2 = actB && bHi > th;
+                    if (k0) mb[oA] = (uint8_t)bLo;
+                    if (k2) mb[oB] = (uint8_t)bHi;
+                    const unsigned m0 = __ballot_sync(0xffffffffu, k0), m2 = __ballot_sync(0xffffffffu, k2);
+                    const int p0c = ncorn + __popc(m0 & below), p2c = ncorn + __popc(m0) + __popc(m2 & below);
+                    if (k0 && p0c < FAST_CLST2) clst[p0c] = (uint16_t)eA;
+                    if (k2 && p2c < FAST_CLST2) clst[p2c] = (uint16_t)eB;
+                    ncorn += __popc(m0) + __popc(m2);
+                }
+                __syncwarp();  // the list is rewritten by the next sub-pass / round
             }
-        }
-        if (nl == 0) continue;
-        __syncwarp();
-        // ---- (B): two list entries per lane on u16x2, ring pixels read as bytes
-        int ncorn = 0;  // corners found; the first FAST_CLST2 of them are listed for (C)
-#pragma unroll 1
-        for (int p0 = 0; p0 < nl; p0 += 64) {
-            const int iA = p0 + 2 * lane;
-            const bool actA = iA < nl, actB = iA + 1 < nl;
-            const int eA = lst[actA ? iA : 0], eB = lst[actB ? iA + 1 : (actA ? iA : 0)];
-            const int oA = ((eA >> 8) * PW + PAD) * 4 + (eA & 255), oB = ((eB >> 8) * PW + PAD) * 4 + (eB & 255);
-            const uint8_t* pA = tb + oA;
-            const uint8_t* pB = tb + oB;
-            const unsigned cc = (unsigned)pA[0] | ((unsigned)pB[0] << 16);
-            unsigned d[16];
-#define RING2(k, off) d[k] = (unsigned)pA[off] | ((unsigned)pB[off] << 16);
-            RING2(0, 3 * pitchB) RING2(1, 3 * pitchB + 1) RING2(2, 2 * pitchB + 2) RING2(3, pitchB + 3)
-            RING2(4, 3) RING2(5, -pitchB + 3) RING2(6, -2 * pitchB + 2) RING2(7, -3 * pitchB + 1)
-            RING2(8, -3 * pitchB) RING2(9, -3 * pitchB - 1) RING2(10, -2 * pitchB - 2) RING2(11, -pitchB - 3)
-            RING2(12, -3) RING2(13, pitchB - 3) RING2(14, 2 * pitchB - 2) RING2(15, 3 * pitchB - 1)
-#undef RING2
-            const unsigned b2 = arc_best2_raw(d, cc);
-            const int bLo = (int)(b2 & 0xffffu) - 256, bHi = (int)(b2 >> 16) - 256;
-            const bool k0 = actA && bLo > th, k2 = actB && bHi > th;
-            if (k0) mb[oA] = (uint8_t)bLo;
-            if (k2) mb[oB] = (uint8_t)bHi;
-            const unsigned m0 = __ballot_sync(0xffffffffu, k0), m2 = __ballot_sync(0xffffffffu, k2);
-            const int p0c = ncorn + __popc(m0 & below), p2c = ncorn + __popc(m0) + __popc(m2 & below);
-            if (k0 && p0c < FAST_CLST2) clst[p0c] = (uint16_t)eA;
-            if (k2 && p2c < FAST_CLST2) clst[p2c] = (uint16_t)eB;
-            ncorn += __popc(m0) + __popc(m2);
         }
         __syncwarp();  // the list is rewritten by the next attempt, the score map read by (C)
         if (ncorn == 0) continue;
@@ -1440,7 +1451,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MINB) k_fast(const uint8
     const int f = blockIdx.y;
     if (c.cw <= 6 || c.ch <= 6) return;
     fast_stage_tile(pyr, tile, Bm, c, f, lane, PW, g);
-    fast_cell_rows<PW>(tile, Bm, clst, lst, c, f, (EAOF_INNER_X0 + c.iniX) & 3, lane, cand, candCount, g);
+    const int lstCap = 2 * (g.fastWarpWords - 2 * mapWords) - FAST_CLST2;  // entries the survivor list holds (>= 16 rows of pixels)
+    fast_cell_rows<PW>(tile, Bm, clst, lst, lstCap, c, f, (EAOF_INNER_X0 + c.iniX) & 3, lane, cand, candCount, g);
 }
 
 // The task-per-word search (fast_cell) for handles whose geometry or thresholds fast_cell_rows does not cover: cells wider
