@@ -532,3 +532,21 @@ def test_tensor_core_hamming_equals_popc_kernel(matcher_factory, monkeypatch):
             nout = nt if mode == 0 else nq
             assert hn[k] == on
             assert np.array_equal(hm[k, :nout], omatch) and np.array_equal(hd[k, :nout], odist)
+
+
+def test_bow_resolve_without_the_proposal_owners(matcher_factory):
+    """A matcher whose max_features exceeds what phase 2's shared-memory owner array covers (11000) resolves every batch
+    sequentially (BowArgs::spec == 0): same answers as the oracle, as for the 32-at-a-time resolution."""
+    import eaof
+    from oracle import pyoracle as po
+    m = matcher_factory(0.8, True, max_features=12000)
+    total = 0
+    for mode in (0, 1):
+        for seed, (nq, nt) in enumerate([(2000, 2000), (300, 900)]):
+            q, aq, t, at = planted_pair(nq, nt, 60 + seed, dup=5)
+            nodes_q, nodes_t = eaof.csr_from_nodes(np.zeros(nq, int)), eaof.csr_from_nodes(np.zeros(nt, int))
+            n, match, dist = m.SearchByBoW(mode, q, aq, None, nodes_q, t, at, None, nodes_t)
+            on, omatch, odist = po.o_search_by_bow(mode, 0.8, True, q, aq, None, nodes_q, t, at, None, nodes_t)
+            assert n == on and np.array_equal(match, omatch) and np.array_equal(dist, odist)
+            total += on
+    assert total > 100
