@@ -1094,33 +1094,64 @@ __global__ void __launch_bounds__(32) k_proj_resolve(ProjArgs A, const int* __re
                 const int nMaxCellY = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(v, A.minY), r), A.invH)));
                 const bool any = !(nMinCellX >= GRID_COLS || nMaxCellX < 0 || nMinCellY >= GRID_ROWS || nMaxCellY < 0);
                 const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+                int ordBase = 0;
                 unsigned long long bestKey = ~0ull;  // dist << 40 | ordinal << 16 | candidate index
-                int ord = 0;
-                if (any)
-                    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix) {
-                        const int b = cs[ix * GRID_ROWS + nMinCellY], e = cs[ix * GRID_ROWS + nMaxCellY + 1];
-                        for (int jj = b + lane; jj < e; jj += 32) {
+                // The window's grid columns are contiguous runs of the packed cell list.  Lane x fetches the run of column
+                // nMinCellX + x, a warp scan turns the run lengths into arrival ordinals, and the candidates of ALL columns are
+                // then dealt to the lanes in one flat loop: the chain entry -> (right coordinate, descriptor) of dependent L2
+                // loads is walked once or twice per re-scan instead of once or twice per column.
+                const int nColsW = any ? nMaxCellX - nMinCellX + 1 : 0;
+                for (int cx0 = 0; cx0 < nColsW; cx0 += 32) {
+                    int rb = 0, rn = 0;
+                    if (cx0 + lane < nColsW) {
+                        const int ix = nMinCellX + cx0 + lane;
+                        rb = cs[ix * GRID_ROWS + nMinCellY];
+                        rn = cs[ix * GRID_ROWS + nMaxCellY + 1] - rb;
+                    }
+                    int incl = rn;
+#pragma unroll
+                    for (int d2 = 1; d2 < 32; d2 <<= 1) {
+                        const int v2 = __shfl_up_sync(0xffffffffu, incl, d2);
+                        if (lane >= d2) incl += v2;
+                    }
+                    const int totalC = __shfl_sync(0xffffffffu, incl, 31);
+                    const int nHere = min(32, nColsW - cx0);
+                    for (int t0 = 0; t0 < totalC; t0 += 32) {
+                        const int t = t0 + lane;
+                        // column of flat position t = number of columns whose inclusive count is <= t (every lane takes part
+                        // in the shuffles, lanes past the end with a clamped column)
+                        int col = 0;
+                        for (int x = 0; x < nHere; ++x) col += (__shfl_sync(0xffffffffu, incl, x) <= t) ? 1 : 0;
+                        col = min(col, nHere - 1);
+                        const int cb = __shfl_sync(0xffffffffu, rb, col), ce = __shfl_sync(0xffffffffu, incl, col);
+                        const int cn = __shfl_sync(0xffffffffu, rn, col);
+                        if (t < totalC) {
+                            const int jj = cb + (t - (ce - cn));
                             const float4 ent = __ldg(pk + jj);
                             const int k = __float_as_int(ent.w);
+                            bool ok = true;
                             if (bCheckLevels) {
                                 const int o = __float_as_int(ent.z);
-                                if (o < minLevel) continue;
-                                if (maxLevel >= 0 && o > maxLevel) continue;
+                                if (o < minLevel) ok = false;
+                                if (maxLevel >= 0 && o > maxLevel) ok = false;
                             }
                             const float dx = __fsub_rn(ent.x, u), dy = __fsub_rn(ent.y, v);
-                            if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
-                            if ((smem[k >> 5] >> (k & 31)) & 1u) continue;
-                            if (cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) continue;
-                            uint32_t td[8];
-                            const uint4* pp = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
-                            const uint4 a2 = pp[0], b2 = pp[1];
-                            td[0] = a2.x; td[1] = a2.y; td[2] = a2.z; td[3] = a2.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
-                            const unsigned long long key = ((unsigned long long)hamming256(qd, td) << 40) |
-                                                           ((unsigned long long)(ord + (jj - b)) << 16) | (unsigned long long)k;
-                            bestKey = key < bestKey ? key : bestKey;
+                            if (!(fabsf(dx) < r && fabsf(dy) < r)) ok = false;
+                            if (ok && ((smem[k >> 5] >> (k & 31)) & 1u)) ok = false;
+                            if (ok && cur && cur[k] > 0 && fabsf(__fsub_rn(ur, cur[k])) > r) ok = false;
+                            if (ok) {
+                                uint32_t td[8];
+                                const uint4* pp = reinterpret_cast<const uint4*>(cd + 32 * (size_t)k);
+                                const uint4 a2 = pp[0], b2 = pp[1];
+                                td[0] = a2.x; td[1] = a2.y; td[2] = a2.z; td[3] = a2.w; td[4] = b2.x; td[5] = b2.y; td[6] = b2.z; td[7] = b2.w;
+                                const unsigned long long key = ((unsigned long long)hamming256(qd, td) << 40) |
+                                                               ((unsigned long long)(ordBase + t) << 16) | (unsigned long long)k;
+                                bestKey = key < bestKey ? key : bestKey;
+                            }
                         }
-                        ord += e - b;
                     }
+                    ordBase += totalC;
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const unsigned long long other = __shfl_xor_sync(0xffffffffu, bestKey, o);
