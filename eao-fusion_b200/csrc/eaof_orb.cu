@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <chrono>
 #include <mutex>
@@ -682,6 +683,14 @@ int check_shape(const eaof_orb* c, int width, int height, int n) {
 }
 
 }  // namespace
+
+struct eaof_ring {
+    int slots = 0, width = 0, height = 0, channels = 0;
+    size_t stride = 0, slotBytes = 0;
+    uint8_t* base = nullptr;  // cudaHostAlloc: slots x slotBytes
+    std::vector<double> stamps;
+    std::atomic<uint64_t> head{0}, tail{0};
+};
 
 extern "C" {
 
@@ -1534,6 +1543,104 @@ int eaof_orb_stage_times(eaof_orb* c, float* ms6) {
     for (int i = 0; i < 6; ++i) ms6[i] = c->stageMs[i];
     return EAOF_OK;
 }
+// ---- pinned frame ring (include/eaof_orb.h; ros_test/src/message_flow.cc:250-254 -> src/Tracking.cc:324-337) ----------
+// head counts the frames the producer committed, tail the frames the consumer released; slot of frame i = i % slots.  The
+// producer only writes head (and the slot it acquired), the consumer only writes tail: two atomics, no lock.
+int eaof_ring_create(int slots, int width, int height, int channels, eaof_ring** out) {
+    if (!out) return fail(EAOF_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (slots < 1 || slots > 65536 || width <= 0 || height <= 0 || (channels != 1 && channels != 3 && channels != 4))
+        return fail(EAOF_ERR_ARG, "bad ring shape: %d slots of %dx%dx%d", slots, width, height, channels);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(EAOF_ERR_CUDA, "no CUDA device: libeaof_orb has no CPU fallback");
+    }
+    eaof_ring* r = new eaof_ring();
+    r->slots = slots; r->width = width; r->height = height; r->channels = channels;
+    r->stride = (size_t)width * channels;
+    r->slotBytes = (r->stride * height + 4095) & ~(size_t)4095;
+    cudaError_t e = cudaHostAlloc((void**)&r->base, r->slotBytes * slots, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete r;
+        return fail(EAOF_ERR_CUDA, "cudaHostAlloc of %zu ring bytes: %s", (size_t)slots * width * height * channels, cudaGetErrorString(e));
+    }
+    r->stamps.assign(slots, 0.0);
+    *out = r;
+    return EAOF_OK;
+}
+
+void eaof_ring_destroy(eaof_ring* r) {
+    if (!r) return;
+    if (r->base) cudaFreeHost(r->base);
+    delete r;
+}
+
+int eaof_ring_acquire(eaof_ring* r, uint8_t** slot, size_t* stride) {
+    if (!r || !slot) return fail(EAOF_ERR_ARG, "null argument");
+    const uint64_t h = r->head.load(std::memory_order_relaxed), t = r->tail.load(std::memory_order_acquire);
+    if (h - t >= (uint64_t)r->slots) return fail(EAOF_ERR_BUSY, "frame ring full: %d frames pending", r->slots);
+    *slot = r->base + (size_t)(h % r->slots) * r->slotBytes;
+    if (stride) *stride = r->stride;
+    return EAOF_OK;
+}
+
+int eaof_ring_commit(eaof_ring* r, double timestamp) {
+    if (!r) return fail(EAOF_ERR_ARG, "null argument");
+    const uint64_t h = r->head.load(std::memory_order_relaxed);
+    if (h - r->tail.load(std::memory_order_acquire) >= (uint64_t)r->slots) return fail(EAOF_ERR_BUSY, "commit without a free slot");
+    r->stamps[h % r->slots] = timestamp;
+    r->head.store(h + 1, std::memory_order_release);  // publishes the pixels and the time stamp
+    return EAOF_OK;
+}
+
+int eaof_ring_pending(const eaof_ring* r) {
+    if (!r) return fail(EAOF_ERR_ARG, "null argument");
+    return (int)(r->head.load(std::memory_order_acquire) - r->tail.load(std::memory_order_relaxed));
+}
+
+int eaof_ring_peek(const eaof_ring* r, int k, const uint8_t** slot, double* timestamp) {
+    if (!r) return fail(EAOF_ERR_ARG, "null argument");
+    const uint64_t h = r->head.load(std::memory_order_acquire), t = r->tail.load(std::memory_order_relaxed);
+    if (k < 0 || (uint64_t)k >= h - t) return fail(EAOF_ERR_ARG, "frame %d of %d pending", k, (int)(h - t));
+    const size_t i = (size_t)((t + k) % r->slots);
+    if (slot) *slot = r->base + i * r->slotBytes;
+    if (timestamp) *timestamp = r->stamps[i];
+    return EAOF_OK;
+}
+
+int eaof_ring_release(eaof_ring* r, int n) {
+    if (!r) return fail(EAOF_ERR_ARG, "null argument");
+    const uint64_t h = r->head.load(std::memory_order_acquire), t = r->tail.load(std::memory_order_relaxed);
+    if (n < 0 || (uint64_t)n > h - t) return fail(EAOF_ERR_ARG, "release of %d frames, %d pending", n, (int)(h - t));
+    r->tail.store(t + n, std::memory_order_release);
+    return EAOF_OK;
+}
+
+int eaof_orb_extract_ring(eaof_orb* c, eaof_ring* r, int maxFrames, int color, int grayMode, eaof_kp* kps, uint8_t* desc,
+                          int cap, int* nOut, double* timestamps, int* nFrames) {
+    if (!c || !r || !nOut || !nFrames) return fail(EAOF_ERR_ARG, "null argument");
+    *nFrames = 0;
+    if (r->width != c->p.width || r->height != c->p.height)
+        return fail(EAOF_ERR_ARG, "ring of %dx%d frames, extractor built for %dx%d", r->width, r->height, c->p.width, c->p.height);
+    const uint64_t h = r->head.load(std::memory_order_acquire), t = r->tail.load(std::memory_order_relaxed);
+    const size_t first = (size_t)(t % r->slots);
+    const int n = (int)std::min<uint64_t>({h - t, (uint64_t)std::max(maxFrames, 0), (uint64_t)c->p.max_batch, (uint64_t)(r->slots - first)});
+    if (n == 0) return EAOF_OK;
+    if (r->channels != 1 && (r->channels == 4) != (color == EAOF_COLOR_BGRA || color == EAOF_COLOR_RGBA))
+        return fail(EAOF_ERR_ARG, "colour order %d does not fit a ring of %d-channel frames", color, r->channels);
+    const uint8_t* imgs = r->base + first * r->slotBytes;
+    const int rc = r->channels == 1
+        ? eaof_orb_extract_batch(c, imgs, n, r->width, r->height, r->stride, r->slotBytes, kps, desc, cap, nOut)
+        : eaof_orb_extract_batch_color(c, imgs, n, r->width, r->height, r->stride, r->slotBytes, color, grayMode, kps, desc, cap, nOut);
+    if (rc) return rc;
+    if (timestamps)
+        for (int i = 0; i < n; ++i) timestamps[i] = r->stamps[first + i];
+    *nFrames = n;
+    return EAOF_OK;
+}
+
 // ---- internal hooks for eaof_match.cu (not part of the public ABI)
 int eaof_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 int eaof_internal_orb_view(eaof_orb* c, const eaof_kp** kps, const uint8_t** desc, const int** counts, int* cap, int* w,

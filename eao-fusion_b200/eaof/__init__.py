@@ -15,6 +15,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("EAOF_LIB_PATH") or os.path.join(PKG_DIR, "lib", "libeaof_orb.so")  # override: build-variant experiments
 
 BLUR_CV331, BLUR_CV4, BLUR_CV331_SSE2 = 0, 1, 2
+ERR_BUSY = -6  # EAOF_ERR_BUSY, include/eaof_orb.h
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                      ("octave", "<i4")])
 
@@ -68,6 +69,14 @@ def lib():
         L.eaof_orb_set_profiling.argtypes = [vp, ci]
         L.eaof_orb_stage_times.argtypes = [vp, vp]
         L.eaof_orb_last_launch_count.argtypes = [vp]
+        L.eaof_ring_create.argtypes = [ci, ci, ci, ci, C.POINTER(vp)]
+        L.eaof_ring_destroy.argtypes = [vp]
+        L.eaof_ring_acquire.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+        L.eaof_ring_commit.argtypes = [vp, C.c_double]
+        L.eaof_ring_pending.argtypes = [vp]
+        L.eaof_ring_peek.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(C.c_double)]
+        L.eaof_ring_release.argtypes = [vp, ci]
+        L.eaof_orb_extract_ring.argtypes = [vp, vp, ci, ci, ci, vp, vp, ci, vp, vp, C.POINTER(ci)]
         L.eaof_orb_stream.restype = vp
         L.eaof_orb_stream.argtypes = [vp]
         _lib = L
@@ -292,6 +301,71 @@ GRAY_CV331, GRAY_CV4 = 0, 1
 TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # ORBmatcher::TH_HIGH/TH_LOW/HISTO_LENGTH, src/ORBmatcher.cc:37-39
 BOW_KF_FRAME, BOW_KF_KF = 0, 1
 _mlib_ready = False
+
+
+class RingFull(EaofError):
+    """eaof_ring_acquire found no free slot (EAOF_ERR_BUSY): the consumer is behind."""
+
+
+class FrameRing:
+    """Pinned frame ring (include/eaof_orb.h): the camera callback (ros_test/src/message_flow.cc:250-254)
+    writes frames into page-locked slots, the tracker takes every pending frame in one batched extraction.  One producer
+    thread (push), one consumer thread (extract / release)."""
+
+    def __init__(self, slots, width, height, channels=1):
+        self.L = lib()
+        h = C.c_void_p()
+        _ck(self.L.eaof_ring_create(slots, width, height, channels, C.byref(h)))
+        self.h = h
+        self.slots, self.width, self.height, self.channels = slots, width, height, channels
+        self.slot_bytes = (width * height * channels + 4095) // 4096 * 4096  # slot pitch inside the ring (include/eaof_orb.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.eaof_ring_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _view(self, ptr):
+        shape = (self.height, self.width) if self.channels == 1 else (self.height, self.width, self.channels)
+        n = self.height * self.width * self.channels
+        return np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr)).reshape(shape)
+
+    def push(self, image: np.ndarray, timestamp=0.0):
+        """Producer: copy one frame into the next free slot and publish it.  Raises RingFull when no slot is free."""
+        slot, stride = C.c_void_p(), C.c_size_t()
+        rc = self.L.eaof_ring_acquire(self.h, C.byref(slot), C.byref(stride))
+        if rc == ERR_BUSY:
+            raise RingFull(self.L.eaof_last_error().decode())
+        _ck(rc)
+        self._view(slot.value)[...] = image
+        _ck(self.L.eaof_ring_commit(self.h, float(timestamp)))
+
+    def pending(self):
+        return self.L.eaof_ring_pending(self.h)
+
+    def peek(self, k=0):
+        """Consumer: (view of the k-th oldest pending frame inside the ring, its time stamp)."""
+        slot, ts = C.c_void_p(), C.c_double()
+        _ck(self.L.eaof_ring_peek(self.h, k, C.byref(slot), C.byref(ts)))
+        return self._view(slot.value), ts.value
+
+    def release(self, n):
+        _ck(self.L.eaof_ring_release(self.h, n))
+
+    def extract(self, ex: "ORBextractor", max_frames=None, color=0, gray_mode=0):
+        """Consumer: extract the oldest pending frames (eaof_orb_extract_ring).  Returns (results, timestamps) with
+        results = list of (keypoints, descriptors); the frames stay pending until release()."""
+        m = ex.max_batch if max_frames is None else max_frames
+        kps = np.zeros((max(m, 1), ex.cap), KP_DTYPE)
+        desc = np.zeros((max(m, 1), ex.cap, 32), np.uint8)
+        cnt = np.zeros(max(m, 1), np.int32)
+        ts = np.zeros(max(m, 1), np.float64)
+        n = C.c_int()
+        _ck(self.L.eaof_orb_extract_ring(ex.h, self.h, m, int(color), int(gray_mode), kps.ctypes.data, desc.ctypes.data,
+                                         ex.cap, cnt.ctypes.data, ts.ctypes.data, C.byref(n)))
+        return [(kps[f, :cnt[f]].copy(), desc[f, :cnt[f]].copy()) for f in range(n.value)], ts[:n.value].copy()
 
 
 def _mlib():

@@ -31,7 +31,8 @@ enum {
     EAOF_ERR_CUDA = -2,        /* CUDA runtime/driver failure (no device, launch error, out of memory) */
     EAOF_ERR_UNSUPPORTED = -3, /* shape the reference itself has undefined behaviour for */
     EAOF_ERR_EMPTY = -4,       /* empty image: the reference returns silently, src/ORBextractor.cc:1046-1047 */
-    EAOF_ERR_NCCL = -5
+    EAOF_ERR_NCCL = -5,
+    EAOF_ERR_BUSY = -6         /* frame ring full (the consumer is behind): drop the frame, like a ROS queue_size does */
 };
 
 /* Gaussian-blur arithmetic: OpenCV-version-dependent, so explicit. */
@@ -127,6 +128,32 @@ int eaof_orb_extract_batch_device_color(eaof_orb* ctx, const uint8_t* d_imgs, in
 int eaof_orb_extract_batch_color(eaof_orb* ctx, const uint8_t* imgs, int n_frames, int width, int height, size_t stride,
                                  size_t frame_pitch, int color, int gray_mode, eaof_kp* kps, uint8_t* desc, int cap,
                                  int* n_out);
+
+/* Pinned frame ring (the ingest side).  The reference's camera callback copies every ROS image message
+ * into a fresh pageable cv::Mat (cv_bridge::toCvCopy, ros_test/src/message_flow.cc:250-254) that Tracking::GrabImageRGBD
+ * converts and hands to the Frame constructor (src/Tracking.cc:324-337, src/Frame.cc:193).  With a ring the callback writes
+ * the frame into a slot of page-locked memory instead, so the extractor's upload is an asynchronous DMA straight from the
+ * slot (a pageable image costs 19-30 us of driver staging per 640x480 frame) and a tracker that has fallen
+ * behind takes every pending frame in ONE batched call.  Single producer (acquire -> fill -> commit), single consumer
+ * (pending -> peek / extract_ring -> release); the two sides may be different threads, no lock is taken.
+ * channels = 1 (gray), 3 or 4 (interleaved colour, converted on the device by the colour path above).
+ * Rows are tightly packed (stride = width * channels), slots are 4096-byte aligned. */
+typedef struct eaof_ring eaof_ring;
+int eaof_ring_create(int slots, int width, int height, int channels, eaof_ring** out);
+void eaof_ring_destroy(eaof_ring* ring);
+/* producer: the next free slot (EAOF_ERR_BUSY when all slots hold unreleased frames), then publish it with its time stamp */
+int eaof_ring_acquire(eaof_ring* ring, uint8_t** slot, size_t* stride);
+int eaof_ring_commit(eaof_ring* ring, double timestamp);
+/* consumer: number of committed, unreleased frames; the k-th oldest of them; give the n oldest back to the producer */
+int eaof_ring_pending(const eaof_ring* ring);
+int eaof_ring_peek(const eaof_ring* ring, int k, const uint8_t** slot, double* timestamp);
+int eaof_ring_release(eaof_ring* ring, int n);
+/* Extract the oldest pending frames: up to max_frames of them (and at most max_batch, and only up to the end of the slot
+ * array: a run that wraps around is taken by the next call).  *n_frames receives how many were taken (0: nothing pending);
+ * outputs as in eaof_orb_extract_batch; color / gray_mode are used by colour rings only.  The frames stay in the ring
+ * until eaof_ring_release (Tracking keeps mImGray for the viewer and the semantic thread). */
+int eaof_orb_extract_ring(eaof_orb* ctx, eaof_ring* ring, int max_frames, int color, int gray_mode, eaof_kp* kps,
+                          uint8_t* desc, int cap, int* n_out, double* timestamps, int* n_frames);
 
 /* Frame::UndistortKeyPoints()  src/Frame.cc:773-803 for the keypoints of the last batch: mvKeysUn
  * positions = cv::undistortPoints(mvKeys, mK, mDistCoef, cv::Mat(), mK) with mK = (fx, fy, cx, cy) and `dist` = k1 k2 p1 p2

@@ -52,6 +52,25 @@ def test_product_fails_loudly_without_a_gpu():
     from eaof import sweep
     with pytest.raises(eaof.EaofError, match="no CUDA device"):
         sweep.Sweep(0, 1, 0)
+    with pytest.raises(eaof.EaofError, match="no CUDA device"):
+        eaof.FrameRing(4, 640, 480)
+
+
+def test_frame_ring_argument_errors():
+    """include/eaof_orb.h eaof_ring_*: shape and null-pointer errors come back as EAOF_ERR_ARG before any CUDA call."""
+    import eaof
+    L = eaof.lib()
+    h = ctypes.c_void_p()
+    for slots, w, hh, ch in ((0, 640, 480, 1), (4, 0, 480, 1), (4, 640, 480, 2), (4, 640, -1, 3)):
+        assert L.eaof_ring_create(slots, w, hh, ch, ctypes.byref(h)) == -1
+        assert b"bad ring shape" in L.eaof_last_error() and not h.value
+    assert L.eaof_ring_create(4, 640, 480, 1, None) == -1
+    assert L.eaof_ring_pending(None) == -1
+    assert L.eaof_ring_release(None, 0) == -1
+    assert L.eaof_ring_commit(None, 0.0) == -1
+    n = ctypes.c_int(7)
+    assert L.eaof_orb_extract_ring(None, None, 1, 0, 0, None, None, 0, None, None, ctypes.byref(n)) == -1
+    L.eaof_ring_destroy(None)  # a no-op, like eaof_orb_destroy
 
 
 def test_sweep_cabi_argument_errors_and_nccl_binding():
