@@ -203,14 +203,15 @@ int eaof_sweep_match(eaof_sweep* s, eaof_matcher* m, int mode, float nnratio, in
     if (rc) return rc;
     if (mdev != s->device) return sfail(EAOF_ERR_ARG, "matcher lives on device %d, the sweep handle on %d", mdev, s->device);
     const int nBlocks = s->world * blocksPerRank;
-    for (int p = 0; p < nPairs; ++p)
-        if (pairQ[p] < 0 || pairQ[p] >= nBlocks || pairT[p] < 0 || pairT[p] >= nBlocks)
-            return sfail(EAOF_ERR_ARG, "pair %d names a block outside [0,%d)", p, nBlocks);
     cudaStream_t st = (cudaStream_t)eaof_matcher_stream(m);
-    // every rank takes part in the collective even when its share of the pair list is empty
+    // every rank takes part in the collective even when its share of the pair list is empty — or wrong: the pair list is
+    // this rank's own data and is checked after the exchange, so that one rank's bad list cannot leave the others waiting
     rc = eaof_sweep_allgather_blocks(s, blocksPerRank, blockStride, dDescLocal, dAngleLocal, dCountLocal, dDescAll, dAngleAll,
                                      dCountAll, st);
     if (rc || nPairs == 0) return rc;
+    for (int p = 0; p < nPairs; ++p)
+        if (pairQ[p] < 0 || pairQ[p] >= nBlocks || pairT[p] < 0 || pairT[p] >= nBlocks)
+            return sfail(EAOF_ERR_ARG, "pair %d names a block outside [0,%d)", p, nBlocks);
     if (nPairs > s->pairCap) {
         SCK(cudaStreamSynchronize(st));
         cudaFree(s->dPairs); cudaFreeHost(s->hPairs);

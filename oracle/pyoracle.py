@@ -15,7 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "liborb_ref.so")
-ORACLE_SO = os.path.join(HERE, "liborb_oracle.so")
+ORACLE_SO = os.environ.get("EAOF_ORACLE_SO") or os.path.join(HERE, "liborb_oracle.so")  # override: the ASan/UBSan build (make -C oracle asan)
 
 BLUR_CV331, BLUR_CV4, BLUR_CV331_SSE2 = 0, 1, 2
 
