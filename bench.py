@@ -267,7 +267,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -988,6 +988,27 @@ def other_config(eaof, torch, dist, rank, world, device, name, B, n_seq, hbm_pea
     return out
 
 
+_JSON_OUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries loaded later write there too (NCCL prints its "NCCL version ..."
+    banner on stdout at communicator creation): descriptor 1 is pointed at stderr for the rest of the process and the JSON
+    line goes to the saved descriptor."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        _JSON_OUT = os.fdopen(saved, "w")
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1002,6 +1023,7 @@ def main():
     ap.add_argument("--no-determinism", action="store_true")
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
     args = ap.parse_args()
+    guard_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -1133,7 +1155,7 @@ def main():
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "cpu_baseline_alpha": alpha,
             "cpu_baseline_cv2": cv2est, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     # release everything torch holds on the library's streams (pinned tensors record an event on every stream that used them
     # when they are freed) before the handles, and with them the streams, go away
     torch.cuda.synchronize()
