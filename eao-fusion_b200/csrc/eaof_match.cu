@@ -1519,7 +1519,12 @@ struct eaof_matcher {
 };
 
 namespace {
-template <typename T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(p, sizeof(T) * (n ? n : 1)); }
+// workspace arrays start out zeroed: tails that no kernel writes are never stale memory when an output block is downloaded
+template <typename T> cudaError_t dalloc(T** p, size_t n) {
+    const size_t bytes = sizeof(T) * (n ? n : 1);
+    cudaError_t e = cudaMalloc(p, bytes);
+    return e != cudaSuccess ? e : cudaMemset(*p, 0, bytes);
+}
 
 int near_threshold(int thEff, float ratio) {
     int s = 0;

@@ -801,6 +801,16 @@ int eaof_orb_create(const eaof_orb_params* params, int device, eaof_orb** out) {
     CKD(cudaMemset(c->dPyr, 0, B * g.pyrFrameBytes));
     CKD(cudaMemset(c->dBlur, 0, B * g.pyrFrameBytes));
     CKD(cudaMemset(c->dKpCount, 0, sizeof(int) * B));
+    // outputs are downloaded with all their cap slots: what the kernels do not fill stays zero instead of whatever the
+    // allocation held before (and compute-sanitizer initcheck stays quiet about the copies)
+    CKD(cudaMemset(c->dKps, 0, sizeof(eaof_kp) * B * c->kpCap));
+    CKD(cudaMemset(c->dDesc, 0, 32 * B * c->kpCap));
+    CKD(cudaMemset(c->dCand, 0, sizeof(uint32_t) * B * (size_t)(g.candPerFrame + 64)));
+    CKD(cudaMemset(c->dLabel, 0, sizeof(uint16_t) * B * (size_t)(g.candPerFrame + 64)));
+    CKD(cudaMemset(c->dCandCount, 0, sizeof(uint32_t) * B * g.nlevels));
+    CKD(cudaMemset(c->dSlotXY, 0, sizeof(uint32_t) * B * g.slotsPerFrame));
+    CKD(cudaMemset(c->dSlotScore, 0, B * g.slotsPerFrame));
+    CKD(cudaMemset(c->dLvlCount, 0, sizeof(int) * B * g.nlevels));
     CKD(cudaMemcpy(c->dTabs, tabs.data(), sizeof(int) * tabs.size(), cudaMemcpyHostToDevice));
     if (!cells.empty()) CKD(cudaMemcpy(c->dCells, cells.data(), sizeof(CellDesc) * cells.size(), cudaMemcpyHostToDevice));
     CKD(cudaMemcpyToSymbol(eaof::d_pattern, kOrbPattern31, EAOF_ORB_PATTERN_INTS));

@@ -271,7 +271,12 @@ int launch(eaof_voc* v, const uint8_t* feats, const int* base, const int* count,
     VCK(cudaGetLastError());
     return EAOF_OK;
 }
-template <typename T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(p, sizeof(T) * (n ? n : 1)); }
+// workspace arrays start out zeroed: tails that no kernel writes are never stale memory when an output block is downloaded
+template <typename T> cudaError_t dalloc(T** p, size_t n) {
+    const size_t bytes = sizeof(T) * (n ? n : 1);
+    cudaError_t e = cudaMalloc(p, bytes);
+    return e != cudaSuccess ? e : cudaMemset(*p, 0, bytes);
+}
 }  // namespace
 
 extern "C" {

@@ -20,6 +20,9 @@ single)  # GPU test suite, bench, reference arm, launch list, sanitizer passes o
     timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 9 python -m pytest tests/test_gpu_extract.py tests/test_gpu_match.py -x -q \
         -k "stages_match_oracle or batch_equals_single or (kernel_variants and 333 and (BULK or TMA or OCT_WIDTH)) or bow or tensor_core" \
         > gpurun_out/${R}_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"
+    timeout 400 compute-sanitizer --tool initcheck --print-limit 400 --error-exitcode 9 python -m pytest tests/test_gpu_extract.py tests/test_gpu_match.py tests/test_gpu_ingest.py -x -q \
+        -k "stages_match_oracle or batch_equals_single or adversarial or bow or tensor_core or ring or projection" \
+        > gpurun_out/${R}_sanitizer_initcheck.log 2>&1; echo "initcheck rc=$?"
     ;;
 multi)   # N GPUs of one box: multi-GPU pytest, sharded extraction + NCCL all-gather sweep against one GPU, host-feed ceiling, bench
     R=$2; T=$3; N=$4
