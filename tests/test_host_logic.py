@@ -421,3 +421,23 @@ def test_dropin_selects_the_blur_arithmetic_of_its_opencv():
         if old is not None:
             os.environ["EAOF_BLUR_MODE"] = old
         L.dropin_shim_set_blur_mode(0)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): stdout is ONE JSON line with the contract's keys —
+    anything a library prints on descriptor 1 after argument parsing lands on stderr (bench.guard_stdout)."""
+    import json
+    code = ("import os, sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0']; "
+            "import bench; bench.guard_stdout(); os.write(1, b'noise from a library\\n'); bench.main()")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1, r.stdout[:500]
+    assert "noise from a library" in r.stderr
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config",
+                "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
