@@ -2209,7 +2209,6 @@ __global__ void __launch_bounds__(256) k_angle_desc(const uint8_t* __restrict__ 
     const uint32_t xy = slotXY[(size_t)f * g.slotsPerFrame + warp];
     const int X = (int)(xy & 0xffff) + EAOF_MIN_BORDER, Y = (int)(xy >> 16) + EAOF_MIN_BORDER;  // :841-842
     const size_t lvlBase = (size_t)f * g.pyrFrameBytes + L.off + (size_t)EAOF_EDGE * L.pitch + EAOF_INNER_X0;
-    const uint8_t* ctr = pyr + lvlBase + (size_t)Y * L.pitch + X;
 
     // IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc (749 pixels).  The 31 rows are read as 9 aligned
     // words each; for every (row, word) the table holds the four u weights and the four v weights as signed bytes
